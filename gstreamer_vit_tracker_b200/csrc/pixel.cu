@@ -1,0 +1,461 @@
+// pixel.cu — byte/integer kernels of the per-frame path (HBM-bound; no tensor cores on purpose).
+//
+//   K1  nv12_to_rgb_*        ≙ nv12_full_to_rgb_parallel        /root/reference/src/nv12_convert.rs:46-169
+//   K2  crop_resize_norm     ≙ K1 fused with VitTrack's crop/resize/blob (OpenCV TrackerVit semantics)
+//   K9  overlay / box_overlay ≙ draw_*_nv12 (src/nv12_convert.rs:172-343), draw_cursor/draw_selection (src/drawing.rs:5-50),
+//                               draw_*_rgb (src/drawing_rgb.rs:30-128)
+#include "vt_internal.h"
+
+namespace vt {
+
+// ------------------------------------------------------------------------------------------------
+// BT.601 limited-range integer conversion, bit-exact with src/nv12_convert.rs:24-30,124-126,41-43
+// (arithmetic >> on negative int, clamp to 0..255).
+// ------------------------------------------------------------------------------------------------
+struct Chroma { int rv, guv, bu; };
+__device__ __forceinline__ Chroma chroma_terms(int u, int v) {
+    Chroma c;
+    c.rv = 409 * (v - 128) + 128;
+    c.guv = -100 * (u - 128) - 208 * (v - 128) + 128;
+    c.bu = 516 * (u - 128) + 128;
+    return c;
+}
+__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ void yuv_px(int y, const Chroma& c, int& r, int& g, int& b) {
+    const int yv = 298 * (y - 16);
+    r = clamp255((yv + c.rv) >> 8);
+    g = clamp255((yv + c.guv) >> 8);
+    b = clamp255((yv + c.bu) >> 8);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 fast path: W % 16 == 0, H even.  One warp converts a 256-px segment of one row pair:
+// each lane loads 8 Y bytes from two rows + 4 UV pairs (8-byte loads, 256 B contiguous per warp),
+// converts 16 pixels, stages 2 x 768 B in shared memory and the warp writes them back as
+// 16-byte coalesced stores.  Algorithmic traffic: 1.5*W*H read + 3*W*H written.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCvtWarps = 8;
+
+__global__ void __launch_bounds__(kCvtWarps * 32) nv12_to_rgb_vec_kernel(const uint8_t* __restrict__ in, size_t stride_in,
+                                                                       uint8_t* __restrict__ out, size_t stride_out, int W, int H,
+                                                                       int n_frames) {
+    __shared__ __align__(16) uint8_t stage[kCvtWarps][2][768];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int segs = (W + 255) >> 8, pairs = H >> 1;
+    const long long total = (long long)n_frames * pairs * segs;
+    const long long wstride = (long long)gridDim.x * kCvtWarps;
+    for (long long item = (long long)blockIdx.x * kCvtWarps + warp; item < total; item += wstride) {
+        const int seg = (int)(item % segs);
+        const long long t = item / segs;
+        const int pair = (int)(t % pairs);
+        const int frame = (int)(t / pairs);
+        const uint8_t* yp = in + (size_t)frame * stride_in;
+        const uint8_t* uvp = yp + (size_t)W * H;
+        uint8_t* op = out + (size_t)frame * stride_out;
+        const int x = seg * 256 + lane * 8;
+        const int seg_px = min(256, W - seg * 256);
+        if (x < W) {
+            const uint2 ya = __ldg(reinterpret_cast<const uint2*>(yp + (size_t)(2 * pair) * W + x));
+            const uint2 yb = __ldg(reinterpret_cast<const uint2*>(yp + (size_t)(2 * pair + 1) * W + x));
+            const uint2 uv = __ldg(reinterpret_cast<const uint2*>(uvp + (size_t)pair * W + x));
+            const uint32_t yw[2][2] = {{ya.x, ya.y}, {yb.x, yb.y}};
+            const uint32_t uvw[2] = {uv.x, uv.y};
+            uint8_t px[2][24];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // 4 chroma pairs
+                const uint32_t w = uvw[q >> 1] >> ((q & 1) * 16);
+                const Chroma c = chroma_terms((int)(w & 0xff), (int)((w >> 8) & 0xff));
+#pragma unroll
+                for (int row = 0; row < 2; ++row)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int i = q * 2 + k;
+                        const int yv = (int)((yw[row][i >> 2] >> ((i & 3) * 8)) & 0xff);
+                        int r, g, b;
+                        yuv_px(yv, c, r, g, b);
+                        px[row][i * 3 + 0] = (uint8_t)r;
+                        px[row][i * 3 + 1] = (uint8_t)g;
+                        px[row][i * 3 + 2] = (uint8_t)b;
+                    }
+            }
+#pragma unroll
+            for (int row = 0; row < 2; ++row) {
+                uint2* dst = reinterpret_cast<uint2*>(&stage[warp][row][lane * 24]);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    uint2 v;
+                    v.x = px[row][j * 8 + 0] | (px[row][j * 8 + 1] << 8) | (px[row][j * 8 + 2] << 16) | ((uint32_t)px[row][j * 8 + 3] << 24);
+                    v.y = px[row][j * 8 + 4] | (px[row][j * 8 + 5] << 8) | (px[row][j * 8 + 6] << 16) | ((uint32_t)px[row][j * 8 + 7] << 24);
+                    dst[j] = v;
+                }
+            }
+        }
+        __syncwarp();
+        const int row_bytes = seg_px * 3;  // multiple of 48
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+            uint8_t* g = op + ((size_t)(2 * pair + row) * W + (size_t)seg * 256) * 3;
+            for (int off = lane * 16; off < row_bytes; off += 32 * 16)
+                *reinterpret_cast<uint4*>(g + off) = *reinterpret_cast<const uint4*>(&stage[warp][row][off]);
+        }
+        __syncwarp();
+    }
+}
+
+// K1 generic path (odd sizes, W % 16 != 0): one thread per 2x2 quad, byte accesses.
+__global__ void nv12_to_rgb_generic_kernel(const uint8_t* __restrict__ in, size_t stride_in, uint8_t* __restrict__ out,
+                                           size_t stride_out, int W, int H, int n_frames) {
+    const int qw = (W + 1) >> 1, qh = (H + 1) >> 1;
+    const long long total = (long long)n_frames * qw * qh;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int qx = (int)(i % qw);
+        const long long t = i / qw;
+        const int qy = (int)(t % qh);
+        const int frame = (int)(t / qh);
+        const uint8_t* yp = in + (size_t)frame * stride_in;
+        const uint8_t* uvp = yp + (size_t)W * H;
+        uint8_t* op = out + (size_t)frame * stride_out;
+        const int x = qx * 2, y = qy * 2;
+        const size_t uvi = (size_t)qy * W + x;  // src/nv12_convert.rs:109 / :152 (odd-width tail uses the pair at even col)
+        const Chroma c = chroma_terms(uvp[uvi], uvp[uvi + 1]);
+        for (int dy = 0; dy < 2 && y + dy < H; ++dy)
+            for (int dx = 0; dx < 2 && x + dx < W; ++dx) {
+                int r, g, b;
+                yuv_px(yp[(size_t)(y + dy) * W + x + dx], c, r, g, b);
+                uint8_t* o = op + ((size_t)(y + dy) * W + x + dx) * 3;
+                o[0] = (uint8_t)r, o[1] = (uint8_t)g, o[2] = (uint8_t)b;
+            }
+    }
+}
+
+cudaError_t launch_nv12_to_rgb(const uint8_t* d_nv12, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int width, int height,
+                               int n_frames, cudaStream_t s) {
+    if (width <= 0 || height <= 0 || n_frames <= 0) return cudaSuccess;
+    const bool aligned = (width % 16 == 0) && (height % 2 == 0) && (stride_in % 16 == 0) && (stride_out % 16 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(d_nv12) | reinterpret_cast<uintptr_t>(d_rgb)) % 16 == 0);
+    if (aligned) {
+        const long long items = (long long)n_frames * (height / 2) * ((width + 255) / 256);
+        long long blocks = (items + kCvtWarps - 1) / kCvtWarps;
+        const long long cap = 148LL * 8 * 4;  // multiple of the SM count; grid-stride beyond that
+        if (blocks > cap) blocks = cap;
+        nv12_to_rgb_vec_kernel<<<(unsigned)blocks, kCvtWarps * 32, 0, s>>>(d_nv12, stride_in, d_rgb, stride_out, width, height, n_frames);
+    } else {
+        const long long items = (long long)n_frames * ((width + 1) / 2) * ((height + 1) / 2);
+        long long blocks = (items + 255) / 256;
+        if (blocks > 148LL * 32) blocks = 148LL * 32;
+        nv12_to_rgb_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_nv12, stride_in, d_rgb, stride_out, width, height, n_frames);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: fused crop (zero border) + NV12->RGB + OpenCV INTER_LINEAR (fixed point) + normalise.
+// One thread per output pixel; output goes straight into the patch-major A operand of the
+// patch-embed GEMM: patches[target][token][c*256 + py*16 + px].
+// ------------------------------------------------------------------------------------------------
+struct Tap { int ofs; int a0, a1; };
+
+// OpenCV resize coefficient for destination index i. clamp_frac: horizontal taps clamp
+// the fraction at the borders, vertical taps keep it and clamp the row index instead.
+__device__ __forceinline__ Tap lin_tap(int i, int s, int d, bool clamp_frac) {
+    const double scale = __ddiv_rn(1.0, __ddiv_rn((double)d, (double)s));
+    float f = (float)__dadd_rn(__dmul_rn((double)i + 0.5, scale), -0.5);
+    int ix = (int)floorf(f);
+    f = __fsub_rn(f, (float)ix);
+    if (clamp_frac) {
+        if (ix < 0) ix = 0, f = 0.f;
+        if (ix >= s - 1) ix = s - 1, f = 0.f;
+    }
+    Tap t;
+    t.ofs = ix;
+    t.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    t.a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+    return t;
+}
+
+// RGB of the frame pixel (fx, fy); zero outside the frame (constant border of the crop).
+__device__ __forceinline__ void frame_rgb(const FrameDesc& f, int fx, int fy, int& r, int& g, int& b) {
+    r = g = b = 0;
+    if (!f.valid || fx < 0 || fy < 0 || fx >= f.width || fy >= f.height) return;
+    if (f.format == VT_FMT_RGB24) {
+        const uint8_t* p = f.data + ((size_t)fy * f.width + fx) * 3;
+        r = p[0], g = p[1], b = p[2];
+    } else {
+        const size_t ysz = (size_t)f.width * f.height;
+        const int yv = f.data[(size_t)fy * f.width + fx];
+        const size_t uvi = ysz + (size_t)(fy >> 1) * f.width + (fx & ~1);
+        const Chroma c = chroma_terms(f.data[uvi], f.data[uvi + 1]);
+        yuv_px(yv, c, r, g, b);
+    }
+}
+
+__global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, TargetState* __restrict__ state,
+                                                               const int32_t* __restrict__ slots, int factor, int S,
+                                                               const float* __restrict__ lut, float* __restrict__ patches,
+                                                               size_t patches_stride) {
+    const int bi = blockIdx.y;
+    const int slot = slots[bi];
+    TargetState* st = state + slot;
+    const int bx = st->rect[0], by = st->rect[1], bw = st->rect[2], bh = st->rect[3];
+    // A.1: c = ceil(sqrt(w*h) * factor); origin by C truncating division
+    const long long area = (long long)bw * bh;
+    int c = 0;
+    if (bw > 0 && bh > 0) c = (int)ceil(__dmul_rn(sqrt((double)(int)area), (double)factor));
+    const int x1 = bx + (bw - c) / 2, y1 = by + (bh - c) / 2;
+    const int pl = max(0, -x1), pt = max(0, -y1);
+    const int pr = max(x1 + c - f.width, 0), pb = max(y1 + c - f.height, 0);
+    const bool outside = (c <= 0) || (c - pl - pr <= 0) || (c - pt - pb <= 0);
+    if (threadIdx.x == 0 && blockIdx.x == 0 && factor == 4) st->crop_err = outside ? 1 : 0;
+    if (outside) return;
+
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * S) return;
+    const int dx = idx % S, dy = idx / S;
+    const Tap tx = lin_tap(dx, c, S, true);
+    const Tap ty = lin_tap(dy, c, S, false);
+    const int cx0 = tx.ofs, cx1 = min(tx.ofs + 1, c - 1);
+    const int cy0 = min(max(ty.ofs, 0), c - 1), cy1 = min(max(ty.ofs + 1, 0), c - 1);
+    int p00[3], p01[3], p10[3], p11[3];
+    frame_rgb(f, x1 + cx0, y1 + cy0, p00[0], p00[1], p00[2]);
+    frame_rgb(f, x1 + cx1, y1 + cy0, p01[0], p01[1], p01[2]);
+    frame_rgb(f, x1 + cx0, y1 + cy1, p10[0], p10[1], p10[2]);
+    frame_rgb(f, x1 + cx1, y1 + cy1, p11[0], p11[1], p11[2]);
+    const int nt = S >> 4;
+    const int token = (dy >> 4) * nt + (dx >> 4);
+    float* dst = patches + (size_t)bi * patches_stride + (size_t)token * kPatchK + (dy & 15) * 16 + (dx & 15);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const int t0 = p00[ch] * tx.a0 + p01[ch] * tx.a1;
+        const int t1 = p10[ch] * tx.a0 + p11[ch] * tx.a1;
+        const int v = (((ty.a0 * (t0 >> 4)) >> 16) + ((ty.a1 * (t1 >> 4)) >> 16) + 2) >> 2;
+        dst[ch * 256] = lut[ch * 256 + (v & 255)];
+    }
+}
+
+cudaError_t launch_crop_resize_norm(FrameDesc f, TargetState* d_state, const int32_t* d_slots, int n, int factor, int out_size,
+                                    const float* d_norm_lut, float* d_patches, size_t patches_stride, const int32_t*, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    dim3 grid((out_size * out_size + 255) / 256, n);
+    crop_resize_norm_kernel<<<grid, 256, 0, s>>>(f, d_state, d_slots, factor, out_size, d_norm_lut, d_patches, patches_stride);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9 overlay.  One CTA walks the command list in order (a barrier between commands keeps the
+// reference's draw order where commands overlap: background dim -> text -> cursor -> box).
+// Each primitive is a flattened parallel loop over exactly the pixels the reference loop nests
+// visit; usize/i32 semantics of the Rust code are reproduced with 64-bit integers.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 i32_as_usize(int v) { return (u64)(long long)v; }
+__device__ __forceinline__ u64 sat_sub(u64 a, u64 b) { return a > b ? a - b : 0; }
+__device__ __forceinline__ u64 umin64(u64 a, u64 b) { return a < b ? a : b; }
+
+struct Surface {
+    uint8_t* d;
+    size_t len;
+    int W, H, fmt;
+};
+// NV12: luma write (Y plane). RGB: bounds-checked colour write (src/drawing_rgb.rs:18-28).
+__device__ __forceinline__ void put_y(const Surface& s, u64 x, u64 y, uint8_t v) { s.d[y * (u64)s.W + x] = v; }
+__device__ __forceinline__ void put_rgb(const Surface& s, int x, int y, uint8_t r, uint8_t g, uint8_t b) {
+    if (x < 0 || y < 0 || x >= s.W || y >= s.H) return;
+    const size_t off = ((size_t)y * s.W + x) * 3;
+    if (off + 2 < s.len) s.d[off] = r, s.d[off + 1] = g, s.d[off + 2] = b;
+}
+
+__device__ void ov_rect_nv12(const Surface& s, int x, int y, int w, int h, int thickness, uint8_t v) {  // src/nv12_convert.rs:172-213
+    const u64 W = s.W, H = s.H, th = (u64)max(thickness, 0);
+    const u64 x1 = (u64)max(x, 0), y1 = (u64)max(y, 0);
+    const u64 x2 = umin64(i32_as_usize((int)((unsigned)x + (unsigned)w)), sat_sub(W, 1));
+    const u64 y2 = umin64(i32_as_usize((int)((unsigned)y + (unsigned)h)), sat_sub(H, 1));
+    const u64 nx = x2 >= x1 ? x2 - x1 + 1 : 0, ny = y2 >= y1 ? y2 - y1 + 1 : 0;
+    const u64 n_h = th * 2 * nx;  // horizontal runs
+    for (u64 i = threadIdx.x; i < n_h; i += blockDim.x) {
+        const u64 px = x1 + i % nx, k = i / nx, t = k >> 1;
+        if ((k & 1) == 0) {
+            if (y1 + t < H) put_y(s, px, y1 + t, v);
+        } else if (y2 >= t && y2 - t < H) {
+            put_y(s, px, y2 - t, v);
+        }
+    }
+    const u64 n_v = ny * th * 2;  // vertical runs
+    for (u64 i = threadIdx.x; i < n_v; i += blockDim.x) {
+        const u64 py = y1 + i / (th * 2), k = i % (th * 2), t = k >> 1;
+        if ((k & 1) == 0) {
+            if (x1 + t < W) put_y(s, x1 + t, py, v);
+        } else if (x2 >= t && x2 - t < W) {
+            put_y(s, x2 - t, py, v);
+        }
+    }
+}
+__device__ void ov_rect_rgb(const Surface& s, int x, int y, int rw, int rh, int thickness, uint8_t r, uint8_t g, uint8_t b) {  // src/drawing_rgb.rs:55-66
+    const long long nw = max(rw, 0), nh = max(rh, 0), th = max(thickness, 0);
+    for (long long i = threadIdx.x; i < th * nw * 2; i += blockDim.x) {
+        const int t = (int)(i / (nw * 2)), j = (int)(i % (nw * 2)), k = j >> 1;
+        if ((j & 1) == 0) put_rgb(s, x + k, y + t, r, g, b);
+        else put_rgb(s, x + k, y + rh - 1 - t, r, g, b);
+    }
+    for (long long i = threadIdx.x; i < th * nh * 2; i += blockDim.x) {
+        const int t = (int)(i / (nh * 2)), j = (int)(i % (nh * 2)), k = j >> 1;
+        if ((j & 1) == 0) put_rgb(s, x + t, y + k, r, g, b);
+        else put_rgb(s, x + rw - 1 - t, y + k, r, g, b);
+    }
+}
+__device__ void ov_crosshair_nv12(const Surface& s, int cx_, int cy_, int size_, uint8_t v) {  // src/nv12_convert.rs:216-242
+    const u64 W = s.W, H = s.H, cx = (u64)max(cx_, 0), cy = (u64)max(cy_, 0), size = i32_as_usize(size_);
+    if (cy < H) {
+        const u64 a = sat_sub(cx, size), b = umin64(cx + size, W - 1);
+        for (u64 x = a + threadIdx.x; x <= b && b >= a; x += blockDim.x) put_y(s, x, cy, v);
+    }
+    if (cx < W) {
+        const u64 a = sat_sub(cy, size), b = umin64(cy + size, H - 1);
+        for (u64 y = a + threadIdx.x; y <= b && b >= a; y += blockDim.x) put_y(s, cx, y, v);
+    }
+}
+__device__ void ov_crosshair_rgb(const Surface& s, int cx, int cy, int size, uint8_t r, uint8_t g, uint8_t b) {  // src/drawing_rgb.rs:68-73
+    for (int i = -size + (int)threadIdx.x; i <= size; i += blockDim.x) {
+        put_rgb(s, cx + i, cy, r, g, b);
+        put_rgb(s, cx, cy + i, r, g, b);
+    }
+}
+__device__ void ov_text(const Surface& s, const OverlayCmdDev& c) {  // src/nv12_convert.rs:245-321 / src/drawing_rgb.rs:86-104
+    const int scale = max(c.a, 0);
+    const long long per_char = 35LL * scale * scale;
+    const long long total = per_char * c.nchar;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        const int ch = (int)(i / per_char);
+        long long r = i % per_char;
+        const int cell = (int)(r / (scale * scale)), sub = (int)(r % (scale * scale));
+        const int row = cell / 5, col = cell % 5, dy = sub / scale, dx = sub % scale;
+        if (!c.known[ch] || !((c.glyph[ch][row] >> (4 - col)) & 1)) continue;
+        if (s.fmt == VT_FMT_NV12) {
+            const u64 px = (u64)c.x + (u64)ch * 6 * scale + (u64)col * scale + dx, py = (u64)c.y + (u64)row * scale + dy;
+            if (px < (u64)s.W && py < (u64)s.H) put_y(s, px, py, c.r);
+        } else {
+            put_rgb(s, c.x + ch * 6 * scale + col * scale + dx, c.y + row * scale + dy, c.r, c.r, c.r);
+        }
+    }
+}
+__device__ void ov_background(const Surface& s, const OverlayCmdDev& c) {
+    if (s.fmt == VT_FMT_NV12) {  // src/nv12_convert.rs:324-343: Y = (Y * (255-darkness)) / 255 in u16
+        const u64 x0 = (u64)c.x, y0 = (u64)c.y;
+        const u64 x1 = umin64(x0 + (u64)c.w, (u64)s.W), y1 = umin64(y0 + (u64)c.h, (u64)s.H);
+        if (x1 <= x0 || y1 <= y0) return;
+        const u64 nx = x1 - x0, n = nx * (y1 - y0);
+        const unsigned factor = 255u - (unsigned)(uint8_t)c.a;
+        for (u64 i = threadIdx.x; i < n; i += blockDim.x) {
+            const u64 idx = (y0 + i / nx) * (u64)s.W + x0 + i % nx;
+            s.d[idx] = (uint8_t)(((unsigned)s.d[idx] * factor) / 255u);
+        }
+    } else {  // src/drawing_rgb.rs:30-53: fill with 30
+        const u64 xs = (u64)max(c.x, 0), xe = umin64(i32_as_usize((int)((unsigned)c.x + (unsigned)c.w)), (u64)s.W);
+        const u64 ys = (u64)max(c.y, 0), ye = umin64(i32_as_usize((int)((unsigned)c.y + (unsigned)c.h)), (u64)s.H);
+        if (xe <= xs || ye <= ys) return;
+        const u64 rb = (xe - xs) * 3, n = rb * (ye - ys);
+        for (u64 i = threadIdx.x; i < n; i += blockDim.x) {
+            const u64 row = ys + i / rb;
+            const u64 off = (row * (u64)s.W + xs) * 3;
+            if (off + rb <= s.len) s.d[off + i % rb] = 30;
+        }
+    }
+}
+__device__ void ov_cursor(const Surface& s, int x_, int y_) {
+    if (s.fmt == VT_FMT_NV12) {  // src/drawing.rs:5-23
+        const u64 W = s.W, H = s.H;
+        const u64 x = (u64)min(max(x_, 0), s.W - 1), y = (u64)min(max(y_, 0), s.H - 1);
+        const u64 ax = sat_sub(x, 25), bx = umin64(x + 25, W - 1);
+        for (u64 px = ax + threadIdx.x; px <= bx; px += blockDim.x)
+            if (!(px >= sat_sub(x, 5) && px <= x + 5)) put_y(s, px, y, 255);
+        const u64 ay = sat_sub(y, 25), by = umin64(y + 25, H - 1);
+        for (u64 py = ay + threadIdx.x; py <= by; py += blockDim.x)
+            if (!(py >= sat_sub(y, 5) && py <= y + 5)) put_y(s, x, py, 255);
+    } else {  // src/drawing_rgb.rs:75-84
+        for (int i = 5 + (int)threadIdx.x; i <= 25; i += blockDim.x) {
+            put_rgb(s, x_ + i, y_, 0, 255, 0);
+            put_rgb(s, x_ - i, y_, 0, 255, 0);
+            put_rgb(s, x_, y_ + i, 0, 255, 0);
+            put_rgb(s, x_, y_ - i, 0, 255, 0);
+        }
+    }
+}
+__device__ void ov_selection(const Surface& s, int sx, int sy, int cx, int cy) {
+    if (s.fmt == VT_FMT_NV12) {  // src/drawing.rs:25-50
+        const u64 x1 = (u64)max(min(sx, cx), 0), y1 = (u64)max(min(sy, cy), 0);
+        const u64 x2 = umin64(i32_as_usize(max(sx, cx)), (u64)s.W - 1), y2 = umin64(i32_as_usize(max(sy, cy)), (u64)s.H - 1);
+        for (u64 x = x1 + threadIdx.x; x <= x2; x += blockDim.x)
+            if ((x / 6) % 2 == 0) put_y(s, x, y1, 255), put_y(s, x, y2, 255);
+        for (u64 y = y1 + threadIdx.x; y <= y2; y += blockDim.x)
+            if ((y / 6) % 2 == 0) put_y(s, x1, y, 255), put_y(s, x2, y, 255);
+    } else {  // src/drawing_rgb.rs:106-128
+        const int x1 = max(min(sx, cx), 0), y1 = max(min(sy, cy), 0);
+        const int x2 = min(max(sx, cx), s.W - 1), y2 = min(max(sy, cy), s.H - 1);
+        for (int x = x1 + (int)threadIdx.x; x <= x2; x += blockDim.x)
+            if ((x / 6) % 2 == 0) put_rgb(s, x, y1, 255, 255, 0), put_rgb(s, x, y2, 255, 255, 0);
+        for (int y = y1 + (int)threadIdx.x; y <= y2; y += blockDim.x)
+            if ((y / 6) % 2 == 0) put_rgb(s, x1, y, 255, 255, 0), put_rgb(s, x2, y, 255, 255, 0);
+    }
+}
+
+__device__ void ov_dispatch(const Surface& s, const OverlayCmdDev& c) {
+    switch (c.kind) {
+        case VT_OV_RECT:
+            if (s.fmt == VT_FMT_NV12) ov_rect_nv12(s, c.x, c.y, c.w, c.h, c.a, c.r);
+            else ov_rect_rgb(s, c.x, c.y, c.w, c.h, c.a, c.r, c.g, c.b);
+            break;
+        case VT_OV_CROSSHAIR:
+            if (s.fmt == VT_FMT_NV12) ov_crosshair_nv12(s, c.x, c.y, c.a, c.r);
+            else ov_crosshair_rgb(s, c.x, c.y, c.a, c.r, c.g, c.b);
+            break;
+        case VT_OV_TEXT: ov_text(s, c); break;
+        case VT_OV_BACKGROUND: ov_background(s, c); break;
+        case VT_OV_CURSOR: ov_cursor(s, c.x, c.y); break;
+        case VT_OV_SELECTION: ov_selection(s, c.x, c.y, c.w, c.h); break;
+        default: break;
+    }
+}
+
+__global__ void __launch_bounds__(1024) overlay_kernel(uint8_t* frame, size_t len, int W, int H, int fmt,
+                                                       const OverlayCmdDev* __restrict__ cmds, int n) {
+    Surface s{frame, len, W, H, fmt};
+    for (int i = 0; i < n; ++i) {
+        ov_dispatch(s, cmds[i]);
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const OverlayCmdDev* d_cmds, int n,
+                           cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    overlay_kernel<<<1, 1024, 0, s>>>(d_frame, len, width, height, format, d_cmds, n);
+    return cudaGetLastError();
+}
+
+// Box overlay straight from the device-side decode result: one CTA per target,
+// rect (thickness 3) then crosshair (size 15) at the box centre ≙ src/pipeline.rs:165-168 / src/pipeline_ir.rs:192-195.
+__global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t len, int W, int H, int fmt,
+                                                          const DeviceResult* __restrict__ res, const int32_t* __restrict__ slots,
+                                                          float gate) {
+    Surface s{frame, len, W, H, fmt};
+    const DeviceResult r = res[slots[blockIdx.x]];
+    if (r.status != VT_OK || !r.success || !(r.score > gate)) return;
+    const int x = r.bbox[0], y = r.bbox[1], w = r.bbox[2], h = r.bbox[3];
+    if (fmt == VT_FMT_NV12) {
+        ov_rect_nv12(s, x, y, w, h, 3, 255);
+        __syncthreads();
+        ov_crosshair_nv12(s, x + w / 2, y + h / 2, 15, 255);
+    } else {
+        ov_rect_rgb(s, x, y, w, h, 3, 0, 255, 0);
+        __syncthreads();
+        ov_crosshair_rgb(s, x + w / 2, y + h / 2, 15, 0, 255, 0);
+    }
+}
+
+cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
+                               const int32_t* d_slots, int n, float gate, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    box_overlay_kernel<<<n, 256, 0, s>>>(d_frame, len, width, height, format, d_res, d_slots, gate);
+    return cudaGetLastError();
+}
+
+}  // namespace vt

@@ -1,0 +1,960 @@
+// tracker.cu — vt_tracker: device memory, per-handle CUDA stream, CUDA-graph replay of the per-frame
+// kernel chain, and the VitTrack / convert / overlay / timing entry points of include/vt_tracker.h.
+//
+// Per frame (update/submit):   H2D frame (pinned, cudaMemcpyAsync on the handle's stream)
+//   -> K2 crop+convert+resize+normalise (search window of every active target, rect_last read on device)
+//   -> template-token gather -> patch-embed GEMM -> depth x [LN+QKV, attention, proj+res, LN+FC1+GELU, FC2+res]
+//   -> final LN -> 3x3 head conv (im2col GEMM) -> K8 decode (updates rect_last on device)
+//   -> optional K9 box overlay -> D2H results (+ touched rows).
+// rect_last never leaves the device between frames, so consecutive frames can be enqueued without a
+// host round trip.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <map>
+#include <mutex>
+
+#include "vt_internal.h"
+
+namespace vt {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct BlockW {
+    const float *ln1_g, *ln1_b, *qkv_w, *qkv_b, *proj_w, *proj_b, *ln2_g, *ln2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+};
+
+enum { EV_START = 0, EV_H2D, EV_PRE, EV_VIT, EV_DEC, EV_OVL, EV_END, EV_COUNT };
+
+}  // namespace vt
+
+using namespace vt;
+
+struct vt_tracker {
+    vt_config cfg;
+    int D = 0, depth = 0, heads = 0, hidden = 0, head_ch = 0;
+    int W = 0, H = 0, fmt = 0, maxT = 1;
+    size_t frame_bytes = 0;
+    float threshold = 0.2f;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool ev_valid = false;
+
+    // weights (one device allocation)
+    float* d_weights = nullptr;
+    const float *patch_w, *patch_b, *pos_z, *pos_x, *lnf_g, *lnf_b, *h1_w, *h1_b, *h2_w, *h2_b;
+    std::vector<BlockW> blk;
+    float *d_lut = nullptr, *d_hann = nullptr;
+
+    // frame + state
+    uint8_t* d_frame = nullptr;
+    uint8_t* d_rgb = nullptr;  // lazily allocated, vt_convert_nv12_rgb
+    uint8_t* h_stage = nullptr;  // pinned staging for non-pinned callers
+    size_t h_stage_bytes = 0;
+    int frame_valid = 1;
+    TargetState* d_state = nullptr;
+    int32_t* d_slots = nullptr;
+    DeviceResult *d_res = nullptr, *h_res = nullptr;
+    float* d_maps = nullptr;
+    OverlayCmdDev *d_cmds = nullptr, *h_cmds = nullptr;
+    std::vector<int> active;          // slot indices, ascending
+    std::vector<vt_bbox> rect_mirror; // host mirror of rect_last (valid after wait)
+    std::vector<int> inited;
+
+    // activations
+    float *patches_x = nullptr, *patches_z = nullptr, *Zemb = nullptr, *X = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr,
+          *Yf = nullptr, *H1 = nullptr, *d_dbg = nullptr;
+    int debug_capture = 0;
+
+    std::map<int, cudaGraphExec_t> graphs;
+    int kernels_per_frame = 0;
+    uint64_t kernel_launches = 0, frames = 0;
+
+    // in-flight frame
+    bool in_flight = false;
+    uint8_t* inflight_frame = nullptr;
+    bool inflight_staged = false;
+    std::chrono::steady_clock::time_point t_submit;
+
+    TimingStats stats;
+    Ring<float> r_h2d, r_pre, r_vit, r_dec, r_ovl, r_d2h, r_tot;
+    float last[7] = {0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace vt {
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static vt_status load_weights(vt_tracker* t, const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        set_error("cannot open weight file %s", path);
+        return VT_ERR_WEIGHTS;
+    }
+    char magic[4];
+    int32_t hdr[7];
+    if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "VTW1", 4) != 0 || fread(hdr, 4, 7, f) != 7) {
+        fclose(f);
+        set_error("%s is not a VTW1 weight file", path);
+        return VT_ERR_WEIGHTS;
+    }
+    t->D = hdr[0], t->depth = hdr[1], t->heads = hdr[2], t->hidden = hdr[3], t->head_ch = hdr[4];
+    const size_t D = t->D, H = t->hidden, C = t->head_ch;
+    if (D == 0 || D % 32 || H % 32 || C % 32 || t->heads <= 0 || D % t->heads || (D / t->heads != 16 && D / t->heads != 32 && D / t->heads != 64)) {
+        fclose(f);
+        set_error("unsupported model shape D=%d heads=%d hidden=%d head_ch=%d", t->D, t->heads, t->hidden, t->head_ch);
+        return VT_ERR_WEIGHTS;
+    }
+    const size_t n = D * kPatchK + D + kNTz * D + kNTx * D + (size_t)t->depth * (4 * D + 3 * D * D + 3 * D + D * D + D + H * D + H + D * H + D) +
+                     2 * D + C * D * 9 + C + 5 * C + 5;
+    std::vector<float> host(n);
+    const size_t got = fread(host.data(), sizeof(float), n, f);
+    fclose(f);
+    if (got != n) {
+        set_error("weight file %s is truncated (%zu of %zu floats)", path, got, n);
+        return VT_ERR_WEIGHTS;
+    }
+    // head conv weight [C, D, 3, 3] -> [C, tap, D] so that the im2col K axis is tap-major
+    const size_t h1_off = n - (5 + 5 * C + C + C * D * 9);
+    {
+        std::vector<float> re(C * D * 9);
+        for (size_t c = 0; c < C; ++c)
+            for (size_t d = 0; d < D; ++d)
+                for (size_t tap = 0; tap < 9; ++tap) re[(c * 9 + tap) * D + d] = host[h1_off + (c * D + d) * 9 + tap];
+        std::copy(re.begin(), re.end(), host.begin() + h1_off);
+    }
+    VT_CUDA(cudaMalloc(&t->d_weights, n * sizeof(float)));
+    VT_CUDA(cudaMemcpy(t->d_weights, host.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    const float* p = t->d_weights;
+    auto take = [&](size_t cnt) {
+        const float* r = p;
+        p += cnt;
+        return r;
+    };
+    t->patch_w = take(D * kPatchK), t->patch_b = take(D), t->pos_z = take(kNTz * D), t->pos_x = take(kNTx * D);
+    t->blk.resize(t->depth);
+    for (auto& b : t->blk) {
+        b.ln1_g = take(D), b.ln1_b = take(D), b.qkv_w = take(3 * D * D), b.qkv_b = take(3 * D);
+        b.proj_w = take(D * D), b.proj_b = take(D), b.ln2_g = take(D), b.ln2_b = take(D);
+        b.fc1_w = take(H * D), b.fc1_b = take(H), b.fc2_w = take(D * H), b.fc2_b = take(D);
+    }
+    t->lnf_g = take(D), t->lnf_b = take(D), t->h1_w = take(C * D * 9), t->h1_b = take(C), t->h2_w = take(5 * C), t->h2_b = take(5);
+    return VT_OK;
+}
+
+__global__ void gather_template_kernel(float* __restrict__ X, const float* __restrict__ Zemb, const int32_t* __restrict__ slots, int D) {
+    const int bi = blockIdx.y;
+    const int n = kNTz * D;
+    const float* src = Zemb + (size_t)slots[bi] * n;
+    float* dst = X + (size_t)bi * kNTok * D;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+static GemmArgs gemm_args(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc, int M, int N, int K) {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = A, g.lda = lda, g.W = W, g.bias = bias, g.C = C, g.ldc = ldc, g.M = M, g.N = N, g.K = K;
+    g.a_rows_in = g.c_rows_in = 1 << 30;
+    return g;
+}
+
+#define VT_LAUNCH(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return VT_ERR_CUDA;                                                           \
+        }                                                                                 \
+        ++launches;                                                                       \
+    } while (0)
+
+// Enqueues crop -> ViT -> decode (-> box overlay) for the n active targets on t->stream.
+static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool record_events) {
+    const int D = t->D, Hd = t->hidden, C = t->head_ch;
+    cudaStream_t s = t->stream;
+    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid};
+    VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, n, 4, kSearch, t->d_lut, t->patches_x, (size_t)kNTx * kPatchK, nullptr, s));
+    if (record_events) VT_CUDA(cudaEventRecord(t->ev[EV_PRE], s));
+    {
+        dim3 grid((kNTz * D + 255) / 256, n);
+        gather_template_kernel<<<grid, 256, 0, s>>>(t->X, t->Zemb, t->d_slots, D);
+        VT_LAUNCH(cudaGetLastError());
+    }
+    {
+        GemmArgs g = gemm_args(t->patches_x, kPatchK, t->patch_w, t->patch_b, t->X, D, n * kNTx, D, kPatchK);
+        g.pos = t->pos_x;
+        g.c_rows_in = kNTx, g.c_rows_stride = kNTok, g.c_row_off = kNTz;
+        VT_LAUNCH(launch_gemm_simt(g, s));
+    }
+    const int M = n * kNTok;
+    if (t->debug_capture) VT_CUDA(cudaMemcpyAsync(t->d_dbg, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
+    for (int l = 0; l < t->depth; ++l) {
+        const BlockW& b = t->blk[l];
+        {
+            GemmArgs g = gemm_args(t->X, D, b.qkv_w, b.qkv_b, t->QKV, 3 * D, M, 3 * D, D);
+            g.ln_g = b.ln1_g, g.ln_b = b.ln1_b;
+            VT_LAUNCH(launch_gemm_simt(g, s));
+        }
+        VT_LAUNCH(launch_attention(t->QKV, t->ATT, n, D, t->heads, s));
+        {
+            GemmArgs g = gemm_args(t->ATT, D, b.proj_w, b.proj_b, t->X, D, M, D, D);
+            g.residual = 1;
+            VT_LAUNCH(launch_gemm_simt(g, s));
+        }
+        {
+            GemmArgs g = gemm_args(t->X, D, b.fc1_w, b.fc1_b, t->HID, Hd, M, Hd, D);
+            g.ln_g = b.ln2_g, g.ln_b = b.ln2_b, g.gelu = 1;
+            VT_LAUNCH(launch_gemm_simt(g, s));
+        }
+        {
+            GemmArgs g = gemm_args(t->HID, Hd, b.fc2_w, b.fc2_b, t->X, D, M, D, Hd);
+            g.residual = 1;
+            VT_LAUNCH(launch_gemm_simt(g, s));
+        }
+        if (t->debug_capture)
+            VT_CUDA(cudaMemcpyAsync(t->d_dbg + (size_t)(l + 1) * t->maxT * kNTok * D, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
+    }
+    VT_LAUNCH(launch_layernorm(t->X, D, t->lnf_g, t->lnf_b, t->Yf, D, n * kNTx, D, kNTx, kNTok, kNTz, s));
+    {
+        GemmArgs g = gemm_args(t->Yf, D, t->h1_w, t->h1_b, t->H1, C, n * kNTx, C, 9 * D);
+        g.relu = 1, g.im2col_feat = D;
+        g.a_rows_in = kNTx, g.a_rows_stride = kNTx, g.a_row_off = 0;
+        VT_LAUNCH(launch_gemm_simt(g, s));
+    }
+    if (record_events) VT_CUDA(cudaEventRecord(t->ev[EV_VIT], s));
+    VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, s));
+    if (record_events) VT_CUDA(cudaEventRecord(t->ev[EV_DEC], s));
+    if (t->cfg.box_overlay)
+        VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, t->fmt, t->d_res, t->d_slots, n, t->cfg.overlay_gate, s));
+    if (record_events) VT_CUDA(cudaEventRecord(t->ev[EV_OVL], s));
+    return VT_OK;
+}
+
+static vt_status run_forward(vt_tracker* t) {
+    const int n = (int)t->active.size();
+    if (n == 0) {
+        VT_CUDA(cudaEventRecord(t->ev[EV_PRE], t->stream));
+        VT_CUDA(cudaEventRecord(t->ev[EV_VIT], t->stream));
+        VT_CUDA(cudaEventRecord(t->ev[EV_DEC], t->stream));
+        VT_CUDA(cudaEventRecord(t->ev[EV_OVL], t->stream));
+        return VT_OK;
+    }
+    int launches = 0;
+    if (!t->cfg.use_cuda_graph || t->debug_capture) {
+        vt_status st = enqueue_forward(t, n, launches, true);
+        t->kernel_launches += launches;
+        t->kernels_per_frame = launches;
+        return st;
+    }
+    auto it = t->graphs.find(n);
+    if (it == t->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        VT_CUDA(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
+        vt_status st = enqueue_forward(t, n, launches, true);
+        cudaError_t e = cudaStreamEndCapture(t->stream, &graph);
+        if (st != VT_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return st;
+        }
+        if (e != cudaSuccess) {
+            set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+            return VT_ERR_CUDA;
+        }
+        cudaGraphExec_t exec = nullptr;
+        VT_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        it = t->graphs.emplace(n, exec).first;
+        t->kernels_per_frame = launches;
+    }
+    VT_CUDA(cudaGraphLaunch(it->second, t->stream));
+    t->kernel_launches += t->kernels_per_frame;
+    return VT_OK;
+}
+
+static vt_status sync_slots(vt_tracker* t) {
+    if (!t->active.empty())
+        VT_CUDA(cudaMemcpyAsync(t->d_slots, t->active.data(), sizeof(int32_t) * t->active.size(), cudaMemcpyHostToDevice, t->stream));
+    VT_CUDA(cudaStreamSynchronize(t->stream));  // t->active is pageable: make the copy complete before it can change
+    return VT_OK;
+}
+
+// host -> device frame upload (pinned: direct async; pageable: staged through the handle's pinned buffer)
+static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len) {
+    size_t n = std::min(len, t->frame_bytes);
+    t->frame_valid = (t->fmt == VT_FMT_NV12) ? (len >= (size_t)t->W * t->H * 3 / 2) : (len >= t->frame_bytes);
+    if (!t->frame_valid && t->fmt == VT_FMT_NV12) n = 0;  // src/nv12_convert.rs:48-50 -> black image
+    if (n == 0) return VT_OK;
+    if (is_pinned(frame)) {
+        VT_CUDA(cudaMemcpyAsync(t->d_frame, frame, n, cudaMemcpyHostToDevice, t->stream));
+    } else {
+        memcpy(t->h_stage, frame, n);
+        VT_CUDA(cudaMemcpyAsync(t->d_frame, t->h_stage, n, cudaMemcpyHostToDevice, t->stream));
+    }
+    return VT_OK;
+}
+
+static void fill_results(vt_tracker* t, vt_result* results) {
+    for (int s = 0; s < t->maxT; ++s) {
+        vt_result r;
+        memset(&r, 0, sizeof(r));
+        if (!t->inited[s]) {
+            r.status = VT_ERR_NOT_INIT;
+        } else {
+            const DeviceResult& d = t->h_res[s];
+            r.success = d.success, r.score = d.score, r.status = d.status;
+            r.bbox = vt_bbox{d.bbox[0], d.bbox[1], d.bbox[2], d.bbox[3]};
+            if (d.status == VT_OK && d.success) t->rect_mirror[s] = r.bbox;
+        }
+        if (results) results[s] = r;
+    }
+}
+
+// Rows touched by a rect / crosshair, following the reference's clamping exactly
+// (src/nv12_convert.rs:181-212,224-241; src/drawing_rgb.rs:55-73).  Returns false if nothing is drawn.
+static bool rect_rows(int fmt, long long H, int y, int h, int th, long long& r0, long long& r1) {
+    if (H <= 0) return false;
+    if (fmt == VT_FMT_NV12) {
+        const long long y1 = std::max(y, 0);
+        const long long sum = (long long)(int32_t)((uint32_t)y + (uint32_t)h);
+        const long long y2 = sum < 0 ? H - 1 : std::min(sum, H - 1);  // negative i32 -> huge usize -> clamped
+        const long long t = std::max(th, 1);
+        r0 = std::min(y1, std::max(0LL, y2 - t + 1));
+        r1 = std::max(y2, std::min(y1 + t - 1, H - 1));
+    } else {
+        r0 = y, r1 = (long long)y + h - 1;
+    }
+    r0 = std::max(0LL, std::min(r0, H - 1)), r1 = std::max(0LL, std::min(r1, H - 1));
+    return r1 >= r0;
+}
+static bool cross_rows(long long H, int cy, int size, long long& r0, long long& r1) {
+    const long long c = std::max(cy, 0), s = std::max(size, 0);
+    r0 = std::max(0LL, std::min(c - s, H - 1)), r1 = std::max(0LL, std::min(c + s, H - 1));
+    return r1 >= r0;
+}
+
+// rows of the frame touched by the box overlay of the current results, merged
+static void box_rows(const vt_tracker* t, std::vector<std::pair<int, int>>& spans) {
+    for (int s : t->active) {
+        const DeviceResult& d = t->h_res[s];
+        if (d.status != VT_OK || !d.success || !(d.score > t->cfg.overlay_gate)) continue;
+        long long r0, r1;
+        if (rect_rows(t->fmt, t->H, d.bbox[1], d.bbox[3], 3, r0, r1)) spans.emplace_back((int)r0, (int)r1);
+        if (cross_rows(t->H, d.bbox[1] + d.bbox[3] / 2, 15, r0, r1)) spans.emplace_back((int)r0, (int)r1);
+    }
+}
+
+static void merge_spans(std::vector<std::pair<int, int>>& spans) {
+    std::sort(spans.begin(), spans.end());
+    std::vector<std::pair<int, int>> out;
+    for (auto& sp : spans) {
+        if (!out.empty() && sp.first <= out.back().second + 8) out.back().second = std::max(out.back().second, sp.second);
+        else out.push_back(sp);
+    }
+    spans.swap(out);
+}
+
+// device -> host copy of whole rows [r0, r1] of the drawable plane (Y plane for NV12, the image for RGB24)
+static vt_status download_rows(vt_tracker* t, uint8_t* frame, size_t len, const std::vector<std::pair<int, int>>& spans, bool* staged) {
+    const size_t pitch = (size_t)t->W * (t->fmt == VT_FMT_NV12 ? 1 : 3);
+    const bool pinned = is_pinned(frame);
+    *staged = !pinned;
+    for (auto& sp : spans) {
+        const size_t off = (size_t)sp.first * pitch;
+        size_t n = (size_t)(sp.second - sp.first + 1) * pitch;
+        if (off >= len) continue;
+        n = std::min(n, len - off);
+        VT_CUDA(cudaMemcpyAsync((pinned ? frame : t->h_stage) + off, t->d_frame + off, n, cudaMemcpyDeviceToHost, t->stream));
+    }
+    return VT_OK;
+}
+static void unstage_rows(vt_tracker* t, uint8_t* frame, size_t len, const std::vector<std::pair<int, int>>& spans) {
+    const size_t pitch = (size_t)t->W * (t->fmt == VT_FMT_NV12 ? 1 : 3);
+    for (auto& sp : spans) {
+        const size_t off = (size_t)sp.first * pitch;
+        size_t n = (size_t)(sp.second - sp.first + 1) * pitch;
+        if (off >= len) continue;
+        memcpy(frame + off, t->h_stage + off, std::min(n, len - off));
+    }
+}
+
+static void collect_timing(vt_tracker* t) {
+    float ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int a[7] = {EV_START, EV_H2D, EV_PRE, EV_VIT, EV_DEC, EV_OVL, EV_START};
+    const int b[7] = {EV_H2D, EV_PRE, EV_VIT, EV_DEC, EV_OVL, EV_END, EV_END};
+    for (int i = 0; i < 7; ++i)
+        if (cudaEventElapsedTime(&ms[i], t->ev[a[i]], t->ev[b[i]]) != cudaSuccess) {
+            cudaGetLastError();
+            ms[i] = 0.f;
+        }
+    memcpy(t->last, ms, sizeof(ms));
+    t->r_h2d.push(ms[0]), t->r_pre.push(ms[1]), t->r_vit.push(ms[2]), t->r_dec.push(ms[3]), t->r_ovl.push(ms[4]), t->r_d2h.push(ms[5]),
+        t->r_tot.push(ms[6]);
+}
+
+static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_src, size_t len) {
+    if (t->in_flight) {
+        set_error("a frame is already in flight on this handle");
+        return VT_ERR_INVALID;
+    }
+    t->t_submit = std::chrono::steady_clock::now();
+    VT_CUDA(cudaEventRecord(t->ev[EV_START], t->stream));
+    if (d_src) {
+        t->frame_valid = (t->fmt == VT_FMT_NV12) ? (len >= (size_t)t->W * t->H * 3 / 2) : (len >= t->frame_bytes);
+        if (t->frame_valid || t->fmt == VT_FMT_RGB24)
+            VT_CUDA(cudaMemcpyAsync(t->d_frame, d_src, std::min(len, t->frame_bytes), cudaMemcpyDeviceToDevice, t->stream));
+    } else {
+        vt_status st = upload_frame(t, frame, len);
+        if (st != VT_OK) return st;
+    }
+    VT_CUDA(cudaEventRecord(t->ev[EV_H2D], t->stream));
+    vt_status st = run_forward(t);
+    if (st != VT_OK) return st;
+    VT_CUDA(cudaMemcpyAsync(t->h_res, t->d_res, sizeof(DeviceResult) * t->maxT, cudaMemcpyDeviceToHost, t->stream));
+    VT_CUDA(cudaEventRecord(t->ev[EV_END], t->stream));
+    t->in_flight = true;
+    t->inflight_frame = d_src ? nullptr : frame;
+    return VT_OK;
+}
+
+static vt_status wait_common(vt_tracker* t, size_t len, vt_result* results) {
+    if (!t->in_flight) {
+        set_error("no frame in flight");
+        return VT_ERR_INVALID;
+    }
+    t->in_flight = false;
+    VT_CUDA(cudaStreamSynchronize(t->stream));
+    fill_results(t, results);
+    if (t->cfg.box_overlay && t->inflight_frame) {
+        std::vector<std::pair<int, int>> spans;
+        box_rows(t, spans);
+        merge_spans(spans);
+        if (!spans.empty()) {
+            bool staged = false;
+            vt_status st = download_rows(t, t->inflight_frame, len, spans, &staged);
+            if (st != VT_OK) return st;
+            VT_CUDA(cudaEventRecord(t->ev[EV_END], t->stream));
+            VT_CUDA(cudaStreamSynchronize(t->stream));
+            if (staged) unstage_rows(t, t->inflight_frame, len, spans);
+        }
+    }
+    collect_timing(t);
+    ++t->frames;
+    return VT_OK;
+}
+
+}  // namespace vt
+
+// ==================================================================================================
+// C ABI
+// ==================================================================================================
+extern "C" {
+
+int32_t vt_abi_version(void) { return VT_ABI_VERSION; }
+const char* vt_last_error(void) { return vt::g_err; }
+
+void vt_config_default(vt_config* c) {
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->struct_size = sizeof(vt_config);
+    c->format = VT_FMT_NV12;
+    c->width = 1920, c->height = 1080;  // src/pipeline.rs:26-27
+    c->max_targets = 1;
+    c->score_threshold = 0.20f;
+    c->gemm_mode = VT_GEMM_FP32_SIMT;
+    c->use_cuda_graph = 1;
+    c->box_overlay = 0;
+    c->overlay_gate = 0.25f;  // src/tracker_context.rs:93,122
+}
+
+vt_status vt_alloc_pinned(size_t bytes, void** out) {
+    if (!out) return VT_ERR_INVALID;
+    VT_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return VT_OK;
+}
+void vt_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+void vt_tracker_destroy(vt_tracker* t) {
+    if (!t) return;
+    cudaSetDevice(t->cfg.device);
+    if (t->stream) cudaStreamSynchronize(t->stream);
+    for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& e : t->ev)
+        if (e) cudaEventDestroy(e);
+    void* dev[] = {t->d_weights, t->d_lut, t->d_hann, t->d_frame, t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
+                   t->patches_x, t->patches_z, t->Zemb, t->X, t->QKV, t->ATT, t->HID, t->Yf, t->H1, t->d_dbg};
+    for (void* p : dev)
+        if (p) cudaFree(p);
+    if (t->h_stage) cudaFreeHost(t->h_stage);
+    if (t->h_res) cudaFreeHost(t->h_res);
+    if (t->h_cmds) cudaFreeHost(t->h_cmds);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    delete t;
+}
+
+vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
+    if (!cfg || !out || !cfg->weights_path || cfg->width <= 0 || cfg->height <= 0 || cfg->max_targets <= 0 || cfg->max_targets > 64 ||
+        (cfg->format != VT_FMT_NV12 && cfg->format != VT_FMT_RGB24)) {
+        set_error("vt_tracker_create: invalid configuration");
+        return VT_ERR_INVALID;
+    }
+    if (cfg->gemm_mode != VT_GEMM_FP32_SIMT) {
+        set_error("vt_tracker_create: gemm_mode %d is not available in this build", cfg->gemm_mode);
+        return VT_ERR_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: libvittrack_b200 has no CPU fallback");
+        return VT_ERR_CUDA;
+    }
+    VT_CUDA(cudaSetDevice(cfg->device));
+    vt_tracker* t = new vt_tracker();
+    t->cfg = *cfg;
+    t->cfg.weights_path = nullptr;
+    t->W = cfg->width, t->H = cfg->height, t->fmt = cfg->format, t->maxT = cfg->max_targets;
+    t->frame_bytes = cfg->format == VT_FMT_NV12 ? (size_t)t->W * t->H + (size_t)((t->H + 1) / 2) * t->W + (t->W & 1) : (size_t)t->W * t->H * 3;
+    t->threshold = cfg->score_threshold > 0.f ? cfg->score_threshold : 0.20f;
+    t->debug_capture = cfg->reserved[0];
+    auto fail = [&](vt_status st) {
+        vt_tracker_destroy(t);
+        return st;
+    };
+    vt_status st = load_weights(t, cfg->weights_path);
+    if (st != VT_OK) return fail(st);
+#define VT_TRY(call)                                                                                             \
+    do {                                                                                                         \
+        cudaError_t e_ = (call);                                                                                 \
+        if (e_ != cudaSuccess) {                                                                                 \
+            set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);             \
+            return fail(VT_ERR_CUDA);                                                                            \
+        }                                                                                                        \
+    } while (0)
+    VT_TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    for (auto& e : t->ev) VT_TRY(cudaEventCreate(&e));
+    const size_t D = t->D, Hd = t->hidden, C = t->head_ch, B = t->maxT;
+    // A.4 normalisation LUT: (v/255 - mean_c)/std_c in double, rounded once to fp32 (channels in memory order)
+    {
+        const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};
+        float lut[768];
+        for (int c = 0; c < 3; ++c)
+            for (int v = 0; v < 256; ++v) lut[c * 256 + v] = (float)(((double)v / 255.0 - mean[c]) / stdv[c]);
+        VT_TRY(cudaMalloc(&t->d_lut, sizeof(lut)));
+        VT_TRY(cudaMemcpy(t->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+        // A.5 hann window, fp32 exactly as OpenCV builds it
+        float h1[16], hann[256];
+        for (int i = 0; i < 16; ++i) h1[i] = 0.5f * (1.f - cosf((float)(2 * M_PI / 17) * (float)(i + 1)));
+        for (int y = 0; y < 16; ++y)
+            for (int x = 0; x < 16; ++x) hann[y * 16 + x] = h1[y] * h1[x];
+        VT_TRY(cudaMalloc(&t->d_hann, sizeof(hann)));
+        VT_TRY(cudaMemcpy(t->d_hann, hann, sizeof(hann), cudaMemcpyHostToDevice));
+    }
+    VT_TRY(cudaMalloc(&t->d_frame, t->frame_bytes + 256));
+    VT_TRY(cudaMemset(t->d_frame, 0, t->frame_bytes + 256));
+    t->h_stage_bytes = t->frame_bytes + 256;
+    VT_TRY(cudaHostAlloc(&t->h_stage, t->h_stage_bytes, cudaHostAllocDefault));
+    VT_TRY(cudaMalloc(&t->d_state, sizeof(TargetState) * B));
+    VT_TRY(cudaMemset(t->d_state, 0, sizeof(TargetState) * B));
+    VT_TRY(cudaMalloc(&t->d_slots, sizeof(int32_t) * B));
+    VT_TRY(cudaMalloc(&t->d_res, sizeof(DeviceResult) * B));
+    VT_TRY(cudaMemset(t->d_res, 0, sizeof(DeviceResult) * B));
+    VT_TRY(cudaHostAlloc(&t->h_res, sizeof(DeviceResult) * B, cudaHostAllocDefault));
+    memset(t->h_res, 0, sizeof(DeviceResult) * B);
+    VT_TRY(cudaMalloc(&t->d_maps, sizeof(float) * 1280 * B));
+    VT_TRY(cudaMemset(t->d_maps, 0, sizeof(float) * 1280 * B));
+    VT_TRY(cudaMalloc(&t->d_cmds, sizeof(OverlayCmdDev) * kMaxCmds));
+    VT_TRY(cudaHostAlloc(&t->h_cmds, sizeof(OverlayCmdDev) * kMaxCmds, cudaHostAllocDefault));
+    VT_TRY(cudaMalloc(&t->patches_x, sizeof(float) * B * kNTx * kPatchK));
+    VT_TRY(cudaMalloc(&t->patches_z, sizeof(float) * kNTz * kPatchK));
+    VT_TRY(cudaMalloc(&t->Zemb, sizeof(float) * B * kNTz * D));
+    VT_TRY(cudaMalloc(&t->X, sizeof(float) * B * kNTok * D));
+    VT_TRY(cudaMalloc(&t->QKV, sizeof(float) * B * kNTok * 3 * D));
+    VT_TRY(cudaMalloc(&t->ATT, sizeof(float) * B * kNTok * D));
+    VT_TRY(cudaMalloc(&t->HID, sizeof(float) * B * kNTok * Hd));
+    VT_TRY(cudaMalloc(&t->Yf, sizeof(float) * B * kNTx * D));
+    VT_TRY(cudaMalloc(&t->H1, sizeof(float) * B * kNTx * C));
+    VT_TRY(cudaMemset(t->patches_x, 0, sizeof(float) * B * kNTx * kPatchK));
+    VT_TRY(cudaMemset(t->patches_z, 0, sizeof(float) * kNTz * kPatchK));
+    if (t->debug_capture) VT_TRY(cudaMalloc(&t->d_dbg, sizeof(float) * (size_t)(t->depth + 1) * B * kNTok * D));
+    t->rect_mirror.assign(B, vt_bbox{0, 0, 0, 0});
+    t->inited.assign(B, 0);
+    VT_TRY(cudaStreamSynchronize(t->stream));
+#undef VT_TRY
+    *out = t;
+    return VT_OK;
+}
+
+vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, size_t len, vt_bbox box) {
+    if (!t || !frame || target < 0 || target >= t->maxT) {
+        set_error("vt_tracker_init: invalid argument");
+        return VT_ERR_INVALID;
+    }
+    if (t->in_flight) {
+        set_error("vt_tracker_init: a frame is in flight");
+        return VT_ERR_INVALID;
+    }
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    // the template window must intersect the frame (cv2 raises an ROI assertion otherwise, App. A.1)
+    {
+        if (box.width <= 0 || box.height <= 0) {
+            set_error("vt_tracker_init: empty box");
+            return VT_ERR_CROP_OUTSIDE;
+        }
+        const int c = (int)ceil(sqrt((double)((long long)box.width * box.height)) * 2.0);
+        const int x1 = box.x + (box.width - c) / 2, y1 = box.y + (box.height - c) / 2;
+        const int pl = std::max(0, -x1), pt = std::max(0, -y1), pr = std::max(x1 + c - t->W, 0), pb = std::max(y1 + c - t->H, 0);
+        if (c - pl - pr <= 0 || c - pt - pb <= 0) {
+            set_error("vt_tracker_init: template window lies outside the frame");
+            return VT_ERR_CROP_OUTSIDE;
+        }
+    }
+    vt_status st = upload_frame(t, frame, len);
+    if (st != VT_OK) return st;
+    TargetState hs;
+    memset(&hs, 0, sizeof(hs));
+    hs.rect[0] = box.x, hs.rect[1] = box.y, hs.rect[2] = box.width, hs.rect[3] = box.height, hs.active = 1;
+    int32_t slot = target;
+    VT_CUDA(cudaMemcpyAsync(t->d_state + target, &hs, sizeof(hs), cudaMemcpyHostToDevice, t->stream));
+    // d_slots is reused as a one-element list for the template pass, then restored
+    VT_CUDA(cudaMemcpyAsync(t->d_slots, &slot, sizeof(slot), cudaMemcpyHostToDevice, t->stream));
+    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid};
+    int launches = 0;
+    VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, 1, 2, kTemplate, t->d_lut, t->patches_z, (size_t)kNTz * kPatchK, nullptr, t->stream));
+    {
+        GemmArgs g = gemm_args(t->patches_z, kPatchK, t->patch_w, t->patch_b, t->Zemb + (size_t)target * kNTz * t->D, t->D, kNTz, t->D, kPatchK);
+        g.pos = t->pos_z;
+        g.c_rows_in = kNTz, g.c_rows_stride = kNTz, g.c_row_off = 0;
+        VT_LAUNCH(launch_gemm_simt(g, t->stream));
+    }
+    t->kernel_launches += launches;
+    VT_CUDA(cudaStreamSynchronize(t->stream));
+    if (!t->inited[target]) {
+        t->inited[target] = 1;
+        t->active.push_back(target);
+        std::sort(t->active.begin(), t->active.end());
+    }
+    t->rect_mirror[target] = box;
+    return sync_slots(t);
+}
+
+vt_status vt_tracker_drop(vt_tracker* t, int32_t target) {
+    if (!t || target < 0 || target >= t->maxT || t->in_flight) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    if (t->inited[target]) {
+        t->inited[target] = 0;
+        t->active.erase(std::remove(t->active.begin(), t->active.end(), target), t->active.end());
+        VT_CUDA(cudaMemsetAsync(t->d_state + target, 0, sizeof(TargetState), t->stream));
+    }
+    return sync_slots(t);
+}
+
+vt_status vt_tracker_submit(vt_tracker* t, uint8_t* frame, size_t len) {
+    if (!t || !frame) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    return submit_common(t, frame, nullptr, len);
+}
+
+vt_status vt_tracker_wait(vt_tracker* t, vt_result* results) {
+    if (!t) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    return wait_common(t, t->frame_bytes, results);
+}
+
+vt_status vt_tracker_update(vt_tracker* t, uint8_t* frame, size_t len, vt_result* results) {
+    if (!t || !frame) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    vt_status st = submit_common(t, frame, nullptr, len);
+    if (st != VT_OK) return st;
+    return wait_common(t, len, results);
+}
+
+vt_status vt_tracker_update_device(vt_tracker* t, const uint8_t* d_frame, size_t len, vt_result* results) {
+    if (!t || !d_frame) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    vt_status st = submit_common(t, nullptr, d_frame, len);
+    if (st != VT_OK) return st;
+    return wait_common(t, len, results);
+}
+
+vt_status vt_tracker_get_rect(vt_tracker* t, int32_t target, vt_bbox* out) {
+    if (!t || !out || target < 0 || target >= t->maxT) return VT_ERR_INVALID;
+    if (!t->inited[target]) return VT_ERR_NOT_INIT;
+    *out = t->rect_mirror[target];
+    return VT_OK;
+}
+
+vt_status vt_tracker_set_rect(vt_tracker* t, int32_t target, vt_bbox box) {
+    if (!t || target < 0 || target >= t->maxT || t->in_flight) return VT_ERR_INVALID;
+    if (!t->inited[target]) return VT_ERR_NOT_INIT;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    int32_t r[4] = {box.x, box.y, box.width, box.height};
+    VT_CUDA(cudaMemcpyAsync(&t->d_state[target].rect[0], r, sizeof(r), cudaMemcpyHostToDevice, t->stream));
+    VT_CUDA(cudaStreamSynchronize(t->stream));
+    t->rect_mirror[target] = box;
+    return VT_OK;
+}
+
+int32_t vt_tracker_model_dim(const vt_tracker* t, int32_t which) {
+    if (!t) return 0;
+    switch (which) {
+        case 0: return t->D;
+        case 1: return t->depth;
+        case 2: return t->heads;
+        case 3: return t->hidden;
+        default: return t->head_ch;
+    }
+}
+
+// patch-major [tokens][768] -> planar CHW blob
+static void patches_to_chw(const std::vector<float>& p, int size, float* chw) {
+    const int nt = size / 16;
+    for (int tok = 0; tok < nt * nt; ++tok)
+        for (int c = 0; c < 3; ++c)
+            for (int py = 0; py < 16; ++py)
+                for (int px = 0; px < 16; ++px)
+                    chw[(size_t)c * size * size + (size_t)((tok / nt) * 16 + py) * size + (tok % nt) * 16 + px] =
+                        p[(size_t)tok * kPatchK + c * 256 + py * 16 + px];
+}
+
+vt_status vt_tracker_debug_read(vt_tracker* t, int32_t target, float* search_blob, float* template_blob, float* conf_win, float* size_map,
+                                float* off_map, float* tokens) {
+    if (!t || target < 0 || target >= t->maxT || t->in_flight) return VT_ERR_INVALID;
+    if (!t->inited[target]) return VT_ERR_NOT_INIT;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    VT_CUDA(cudaStreamSynchronize(t->stream));
+    const int bi = (int)(std::find(t->active.begin(), t->active.end(), target) - t->active.begin());
+    if (search_blob) {
+        std::vector<float> p((size_t)kNTx * kPatchK);
+        VT_CUDA(cudaMemcpy(p.data(), t->patches_x + (size_t)bi * kNTx * kPatchK, p.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        patches_to_chw(p, kSearch, search_blob);
+    }
+    if (template_blob) {  // patches_z holds the most recently initialised template
+        std::vector<float> p((size_t)kNTz * kPatchK);
+        VT_CUDA(cudaMemcpy(p.data(), t->patches_z, p.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        patches_to_chw(p, kTemplate, template_blob);
+    }
+    if (conf_win || size_map || off_map) {
+        float m[1280];
+        VT_CUDA(cudaMemcpy(m, t->d_maps + (size_t)target * 1280, sizeof(m), cudaMemcpyDeviceToHost));
+        if (conf_win) memcpy(conf_win, m, 256 * sizeof(float));
+        if (size_map) memcpy(size_map, m + 256, 512 * sizeof(float));
+        if (off_map) memcpy(off_map, m + 768, 512 * sizeof(float));
+    }
+    if (tokens) {  // final-LN search-token features [256, D] placed at rows 64..319; template rows zero
+        memset(tokens, 0, sizeof(float) * kNTok * t->D);
+        VT_CUDA(cudaMemcpy(tokens + (size_t)kNTz * t->D, t->Yf + (size_t)bi * kNTx * t->D, sizeof(float) * kNTx * t->D, cudaMemcpyDeviceToHost));
+    }
+    return VT_OK;
+}
+
+// which: 0 embeddings, 1..depth block outputs (needs cfg.reserved[0] = 1)
+vt_status vt_tracker_debug_tokens(vt_tracker* t, int32_t target, int32_t which, float* out) {
+    if (!t || !out || target < 0 || target >= t->maxT || !t->debug_capture || which < 0 || which > t->depth) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    VT_CUDA(cudaStreamSynchronize(t->stream));
+    const int bi = (int)(std::find(t->active.begin(), t->active.end(), target) - t->active.begin());
+    VT_CUDA(cudaMemcpy(out, t->d_dbg + ((size_t)which * t->maxT + bi) * kNTok * t->D, sizeof(float) * kNTok * t->D, cudaMemcpyDeviceToHost));
+    return VT_OK;
+}
+
+// ---- NV12 -> RGB -------------------------------------------------------------------------------
+vt_status vt_convert_nv12_rgb(vt_tracker* t, const uint8_t* nv12, size_t len, uint8_t* rgb_out) {
+    if (!t || !nv12 || !rgb_out || t->in_flight) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    const size_t W = t->W, H = t->H, out_bytes = W * H * 3;
+    if (len < W * H * 3 / 2) {  // src/nv12_convert.rs:48-50
+        memset(rgb_out, 0, out_bytes);
+        return VT_OK;
+    }
+    if (t->fmt != VT_FMT_NV12) {
+        set_error("vt_convert_nv12_rgb: handle was created for RGB24 frames");
+        return VT_ERR_INVALID;
+    }
+    if (!t->d_rgb) VT_CUDA(cudaMalloc(&t->d_rgb, out_bytes + 256));
+    const size_t n = std::min(len, t->frame_bytes);
+    const bool pin_in = is_pinned(nv12), pin_out = is_pinned(rgb_out);
+    if (!pin_in) memcpy(t->h_stage, nv12, n);
+    VT_CUDA(cudaMemcpyAsync(t->d_frame, pin_in ? nv12 : t->h_stage, n, cudaMemcpyHostToDevice, t->stream));
+    cudaError_t e = launch_nv12_to_rgb(t->d_frame, t->frame_bytes, t->d_rgb, out_bytes, t->W, t->H, 1, t->stream);
+    if (e != cudaSuccess) {
+        set_error("nv12_to_rgb launch failed: %s", cudaGetErrorString(e));
+        return VT_ERR_CUDA;
+    }
+    ++t->kernel_launches;
+    if (pin_out) {
+        VT_CUDA(cudaMemcpyAsync(rgb_out, t->d_rgb, out_bytes, cudaMemcpyDeviceToHost, t->stream));
+        VT_CUDA(cudaStreamSynchronize(t->stream));
+    } else {
+        VT_CUDA(cudaStreamSynchronize(t->stream));
+        VT_CUDA(cudaMemcpy(rgb_out, t->d_rgb, out_bytes, cudaMemcpyDeviceToHost));
+    }
+    return VT_OK;
+}
+
+vt_status vt_convert_nv12_rgb_device(vt_tracker* t, const uint8_t* d_nv12, size_t stride_in, uint8_t* d_rgb, size_t stride_out,
+                                     int32_t n_frames) {
+    if (!t || !d_nv12 || !d_rgb || n_frames <= 0) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    cudaError_t e = launch_nv12_to_rgb(d_nv12, stride_in, d_rgb, stride_out, t->W, t->H, n_frames, t->stream);
+    if (e != cudaSuccess) {
+        set_error("nv12_to_rgb launch failed: %s", cudaGetErrorString(e));
+        return VT_ERR_CUDA;
+    }
+    ++t->kernel_launches;
+    return VT_OK;
+}
+
+// exposed for bench.py: stream handle so that device-side timing happens on the launching stream
+void* vt_tracker_stream(vt_tracker* t) { return t ? (void*)t->stream : nullptr; }
+vt_status vt_tracker_sync(vt_tracker* t) {
+    if (!t) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    VT_CUDA(cudaStreamSynchronize(t->stream));
+    return VT_OK;
+}
+
+// ---- overlay -------------------------------------------------------------------------------------
+int vt_glyph_rows(int ch, uint8_t rows[7]);  // host_state.cpp
+
+static vt_status build_cmds(vt_tracker* t, const vt_overlay_cmd* cmds, int n, std::vector<std::pair<int, int>>& spans) {
+    if (n < 0 || n > kMaxCmds) {
+        set_error("vt_overlay: at most %d commands", kMaxCmds);
+        return VT_ERR_INVALID;
+    }
+    const long long H = t->H;
+    for (int i = 0; i < n; ++i) {
+        const vt_overlay_cmd& c = cmds[i];
+        OverlayCmdDev& d = t->h_cmds[i];
+        memset(&d, 0, sizeof(d));
+        d.kind = c.kind, d.x = c.x, d.y = c.y, d.w = c.w, d.h = c.h, d.a = c.a, d.r = c.r, d.g = c.g, d.b = c.b;
+        long long r0 = 0, r1 = -1;
+        switch (c.kind) {
+            case VT_OV_RECT:
+                if (!rect_rows(t->fmt, H, c.y, c.h, c.a, r0, r1)) r0 = 0, r1 = -1;
+                break;
+            case VT_OV_CROSSHAIR:
+                if (!cross_rows(H, c.y, c.a, r0, r1)) r0 = 0, r1 = -1;
+                break;
+            case VT_OV_TEXT: {
+                size_t len = strnlen(c.text, sizeof(c.text));
+                d.nchar = (uint8_t)len;
+                for (size_t k = 0; k < len; ++k) {
+                    uint8_t rows[7];
+                    if (vt_glyph_rows((unsigned char)c.text[k], rows) == 0) {
+                        d.known[k] = 1;
+                        memcpy(d.glyph[k], rows, 7);
+                    } else if (c.strict_glyphs) {
+                        set_error("vt_overlay: no glyph for character 0x%02x", (unsigned char)c.text[k]);
+                        return VT_ERR_GLYPH;
+                    }
+                }
+                r0 = c.y, r1 = (long long)c.y + 7LL * std::max(c.a, 0);
+                break;
+            }
+            case VT_OV_BACKGROUND: r0 = c.y, r1 = (long long)c.y + c.h; break;
+            case VT_OV_CURSOR: {
+                const long long yc = std::max(0LL, std::min<long long>(c.y, H - 1));  // src/drawing.rs:7 clamps, the RGB path does not
+                r0 = std::min<long long>(c.y, yc) - 26, r1 = std::max<long long>(c.y, yc) + 26;
+                break;
+            }
+            case VT_OV_SELECTION: r0 = std::min(c.y, c.h), r1 = std::max(c.y, c.h); break;
+            default: set_error("vt_overlay: unknown command kind %d", c.kind); return VT_ERR_INVALID;
+        }
+        if (r1 >= r0 && r1 >= 0 && r0 <= H - 1) spans.emplace_back((int)std::max(0LL, r0), (int)std::min(r1, H - 1));
+    }
+    return VT_OK;
+}
+
+static vt_status overlay_impl(vt_tracker* t, uint8_t* frame, size_t len, const vt_overlay_cmd* cmds, int32_t n, bool upload) {
+    if (!t || !frame || (n > 0 && !cmds) || t->in_flight) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    const size_t need = t->fmt == VT_FMT_NV12 ? (size_t)t->W * t->H : 0;
+    if (len < need) {
+        set_error("vt_overlay: frame shorter than its Y plane");
+        return VT_ERR_INVALID;
+    }
+    std::vector<std::pair<int, int>> spans;
+    vt_status st = build_cmds(t, cmds, n, spans);
+    if (st != VT_OK) return st;
+    if (n == 0) return VT_OK;
+    VT_CUDA(cudaEventRecord(t->ev[EV_DEC], t->stream));
+    if (upload) {
+        const size_t nb = std::min(len, t->frame_bytes);
+        if (is_pinned(frame)) {
+            VT_CUDA(cudaMemcpyAsync(t->d_frame, frame, nb, cudaMemcpyHostToDevice, t->stream));
+        } else {
+            memcpy(t->h_stage, frame, nb);
+            VT_CUDA(cudaMemcpyAsync(t->d_frame, t->h_stage, nb, cudaMemcpyHostToDevice, t->stream));
+        }
+    }
+    VT_CUDA(cudaMemcpyAsync(t->d_cmds, t->h_cmds, sizeof(OverlayCmdDev) * n, cudaMemcpyHostToDevice, t->stream));
+    cudaError_t e = launch_overlay(t->d_frame, std::min(len, t->frame_bytes), t->W, t->H, t->fmt, t->d_cmds, n, t->stream);
+    if (e != cudaSuccess) {
+        set_error("overlay launch failed: %s", cudaGetErrorString(e));
+        return VT_ERR_CUDA;
+    }
+    ++t->kernel_launches;
+    VT_CUDA(cudaEventRecord(t->ev[EV_OVL], t->stream));
+    merge_spans(spans);
+    bool staged = false;
+    st = download_rows(t, frame, len, spans, &staged);
+    if (st != VT_OK) return st;
+    VT_CUDA(cudaStreamSynchronize(t->stream));
+    if (staged) unstage_rows(t, frame, len, spans);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t->ev[EV_DEC], t->ev[EV_OVL]) == cudaSuccess) t->last[4] = ms;
+    else cudaGetLastError();
+    return VT_OK;
+}
+
+vt_status vt_overlay(vt_tracker* t, uint8_t* frame, size_t len, const vt_overlay_cmd* cmds, int32_t n) {
+    return overlay_impl(t, frame, len, cmds, n, true);
+}
+vt_status vt_overlay_current(vt_tracker* t, uint8_t* frame, size_t len, const vt_overlay_cmd* cmds, int32_t n) {
+    return overlay_impl(t, frame, len, cmds, n, false);
+}
+
+// ---- timing --------------------------------------------------------------------------------------
+vt_status vt_timing_get(vt_tracker* t, vt_timing* o) {
+    if (!t || !o) return VT_ERR_INVALID;
+    memset(o, 0, sizeof(*o));
+    o->fps = t->stats.fps(), o->avg_conv_ms = t->stats.avg_conv_ms(), o->avg_track_ms = t->stats.avg_track_ms();
+    o->h2d_ms = t->last[0], o->preprocess_ms = t->last[1], o->vit_ms = t->last[2], o->decode_ms = t->last[3], o->overlay_ms = t->last[4];
+    o->d2h_ms = t->last[5], o->total_ms = t->last[6];
+    o->avg_h2d_ms = (float)t->r_h2d.mean(), o->avg_preprocess_ms = (float)t->r_pre.mean(), o->avg_vit_ms = (float)t->r_vit.mean();
+    o->avg_decode_ms = (float)t->r_dec.mean(), o->avg_overlay_ms = (float)t->r_ovl.mean(), o->avg_d2h_ms = (float)t->r_d2h.mean();
+    o->avg_total_ms = (float)t->r_tot.mean();
+    o->frames = t->frames, o->kernel_launches = t->kernel_launches;
+    return VT_OK;
+}
+vt_status vt_timing_add_interval(vt_tracker* t, uint64_t us) {
+    if (!t) return VT_ERR_INVALID;
+    t->stats.add_interval(us);
+    return VT_OK;
+}
+vt_status vt_timing_add_times(vt_tracker* t, uint64_t conv_us, uint64_t track_us) {
+    if (!t) return VT_ERR_INVALID;
+    t->stats.add_times(conv_us, track_us);
+    return VT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// vit.cu — fp32 CUDA-core kernels of the ViT forward pass and the score-map decode.
+//
+// These are the numerically-anchoring kernels (fp32 everywhere, oracle-order accumulation
+// where it matters).  The tensor-core path (gemm_tcgen05.cu) replaces launch_gemm_simt for the
+// dense contractions; LayerNorm / attention softmax / decode stay as warp-shuffle kernels.
+// Replaces VitTrack::update's network + decode (call site /root/reference/src/tracker_context.rs:120;
+// algorithm: OpenCV TrackerVit).
+#include "vt_internal.h"
+
+namespace vt {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+// ------------------------------------------------------------------------------------------------
+// GEMM  C[M,N] = epi( pro(A)[M,K] * W[N,K]^T + bias )       (fp32 SIMT, BK = 32)
+// ------------------------------------------------------------------------------------------------
+constexpr int kBK = 32;
+
+__device__ __forceinline__ int map_row(int m, int rows_in, int rows_stride, int row_off) {
+    return (m / rows_in) * rows_stride + row_off + (m % rows_in);
+}
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
+    static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+    __shared__ float As[kBK][BM + 4];
+    __shared__ float Ws[kBK][BN + 4];
+    __shared__ float s_mean[BM], s_rstd[BM];
+
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+
+    // LayerNorm statistics of this CTA's rows (two-pass, like the oracle)
+    if (g.ln_g) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < BM; r += 8) {
+            const int m = m0 + r;
+            float mean = 0.f, rstd = 0.f;
+            if (m < g.M) {
+                const float* a = g.A + (int64_t)map_row(m, g.a_rows_in, g.a_rows_stride, g.a_row_off) * g.lda;
+                float s = 0.f;
+                for (int k = lane; k < g.K; k += 32) s += a[k];
+                mean = warp_sum(s) / (float)g.K;
+                float v = 0.f;
+                for (int k = lane; k < g.K; k += 32) {
+                    const float d = a[k] - mean;
+                    v += d * d;
+                }
+                v = warp_sum(v) / (float)g.K;
+                rstd = 1.f / sqrtf(v + 1e-6f);
+            }
+            if (lane == 0) s_mean[r] = mean, s_rstd[r] = rstd;
+        }
+        __syncthreads();
+    }
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < g.K; k0 += kBK) {
+        // ---- A tile -> As[k][m]
+        for (int v = tid; v < BM * (kBK / 4); v += 256) {
+            const int r = v / (kBK / 4), kq = (v % (kBK / 4)) * 4;
+            const int m = m0 + r;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < g.M) {
+                if (g.im2col_feat) {
+                    const int feat = g.im2col_feat;
+                    const int tap = k0 / feat, d0 = k0 % feat;
+                    const int p = m % g.a_rows_in, b = m / g.a_rows_in;
+                    const int yy = p / kMap + tap / 3 - 1, xx = p % kMap + tap % 3 - 1;
+                    if (yy >= 0 && yy < kMap && xx >= 0 && xx < kMap)
+                        a = *reinterpret_cast<const float4*>(g.A + (int64_t)(b * g.a_rows_stride + g.a_row_off + yy * kMap + xx) * g.lda + d0 + kq);
+                } else {
+                    a = *reinterpret_cast<const float4*>(g.A + (int64_t)map_row(m, g.a_rows_in, g.a_rows_stride, g.a_row_off) * g.lda + k0 + kq);
+                    if (g.ln_g) {
+                        const float mu = s_mean[r], rs = s_rstd[r];
+                        const float4 gg = *reinterpret_cast<const float4*>(g.ln_g + k0 + kq);
+                        const float4 bb = *reinterpret_cast<const float4*>(g.ln_b + k0 + kq);
+                        a.x = (a.x - mu) * rs * gg.x + bb.x;
+                        a.y = (a.y - mu) * rs * gg.y + bb.y;
+                        a.z = (a.z - mu) * rs * gg.z + bb.z;
+                        a.w = (a.w - mu) * rs * gg.w + bb.w;
+                    }
+                }
+            }
+            As[kq + 0][r] = a.x, As[kq + 1][r] = a.y, As[kq + 2][r] = a.z, As[kq + 3][r] = a.w;
+        }
+        // ---- W tile -> Ws[k][n]
+        for (int v = tid; v < BN * (kBK / 4); v += 256) {
+            const int r = v / (kBK / 4), kq = (v % (kBK / 4)) * 4;
+            const int n = n0 + r;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < g.N) w = *reinterpret_cast<const float4*>(g.W + (int64_t)n * g.K + k0 + kq);
+            Ws[kq + 0][r] = w.x, Ws[kq + 1][r] = w.y, Ws[kq + 2][r] = w.z, Ws[kq + 3][r] = w.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kBK; ++kk) {
+            float a[TM], w[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) w[j] = Ws[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= g.M) continue;
+        const int64_t row = (int64_t)map_row(m, g.c_rows_in, g.c_rows_stride, g.c_row_off) * g.ldc;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j] + (g.bias ? g.bias[n] : 0.f);
+            if (g.gelu) v = gelu_exact(v);
+            if (g.relu) v = fmaxf(v, 0.f);
+            if (g.pos) v += g.pos[(int64_t)(m % g.c_rows_in) * g.N + n];
+            if (g.residual) v += g.C[row + n];
+            g.C[row + n] = v;
+        }
+    }
+}
+
+cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t s) {
+    if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+    if (g.K % kBK != 0 || (g.im2col_feat && g.im2col_feat % kBK != 0)) return cudaErrorInvalidValue;
+    // pick the tile that gives the most CTAs up to ~2 waves of 148 SMs
+    const long long ctas64 = (long long)((g.M + 63) / 64) * ((g.N + 63) / 64);
+    const long long ctas32x64 = (long long)((g.M + 31) / 32) * ((g.N + 63) / 64);
+    if (ctas64 >= 296) {
+        dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
+        gemm_simt_kernel<64, 64, 4, 4><<<grid, 256, 0, s>>>(g);
+    } else if (ctas32x64 >= 148) {
+        dim3 grid((g.N + 63) / 64, (g.M + 31) / 32);
+        gemm_simt_kernel<32, 64, 2, 4><<<grid, 256, 0, s>>>(g);
+    } else {
+        dim3 grid((g.N + 31) / 32, (g.M + 31) / 32);
+        gemm_simt_kernel<32, 32, 2, 2><<<grid, 256, 0, s>>>(g);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm, one warp per row (two-pass statistics, eps 1e-6)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g,
+                                                        const float* __restrict__ b, float* __restrict__ y, int64_t ldy, int M, int D,
+                                                        int rows_in, int rows_stride, int row_off) {
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float* r = x + (int64_t)map_row(m, rows_in, rows_stride, row_off) * ldx;
+    float s = 0.f;
+    for (int k = lane; k < D; k += 32) s += r[k];
+    const float mean = warp_sum(s) / (float)D;
+    float v = 0.f;
+    for (int k = lane; k < D; k += 32) {
+        const float d = r[k] - mean;
+        v += d * d;
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(v) / (float)D + 1e-6f);
+    for (int k = lane; k < D; k += 32) y[(int64_t)m * ldy + k] = (r[k] - mean) * rstd * g[k] + b[k];
+}
+
+cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* g, const float* b, float* y, int64_t ldy, int M, int D,
+                             int rows_in, int rows_stride, int row_off, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    layernorm_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ldx, g, b, y, ldy, M, D, rows_in, rows_stride, row_off);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention over the joint 320-token sequence: one CTA per (16-query tile, head, target).
+// scores -> shared memory, warp-shuffle softmax, P*V from shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBQ = 16, kKT = 64;
+
+template <int DH>
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int D) {
+    __shared__ float Qs[kBQ][DH];
+    __shared__ float S[kBQ][kNTok];
+    __shared__ float KV[kKT][DH + 1];
+    const int tid = threadIdx.x, q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
+    const int64_t ld = 3 * (int64_t)D;
+    const float* base = qkv + (int64_t)b * kNTok * ld + h * DH;
+    const float scale = 1.f / sqrtf((float)DH);
+
+    for (int i = tid; i < kBQ * DH; i += 128) Qs[i / DH][i % DH] = base[(int64_t)(q0 + i / DH) * ld + i % DH];
+
+    // scores
+    for (int kt = 0; kt < kNTok; kt += kKT) {
+        __syncthreads();
+        for (int i = tid; i < kKT * DH; i += 128) KV[i / DH][i % DH] = base[(int64_t)(kt + i / DH) * ld + D + i % DH];
+        __syncthreads();
+        const int j = tid % kKT, qh = tid / kKT;  // 2 groups of 8 queries
+#pragma unroll
+        for (int qi = 0; qi < 8; ++qi) {
+            const int q = qh * 8 + qi;
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc = fmaf(Qs[q][d], KV[j][d], acc);
+            S[q][kt + j] = acc * scale;
+        }
+    }
+    __syncthreads();
+    // softmax: warp w owns rows 4w..4w+3
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int q = warp * 4; q < warp * 4 + 4; ++q) {
+            float mx = -INFINITY;
+            for (int j = lane; j < kNTok; j += 32) mx = fmaxf(mx, S[q][j]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int j = lane; j < kNTok; j += 32) {
+                const float e = expf(S[q][j] - mx);
+                S[q][j] = e;
+                sum += e;
+            }
+            const float inv = 1.f / warp_sum(sum);
+            for (int j = lane; j < kNTok; j += 32) S[q][j] *= inv;
+        }
+    }
+    // O = P V
+    constexpr int kGroups = 128 / DH, kQPer = kBQ / kGroups;
+    const int d = tid % DH, qg = tid / DH;
+    float o[kQPer];
+#pragma unroll
+    for (int i = 0; i < kQPer; ++i) o[i] = 0.f;
+    for (int kt = 0; kt < kNTok; kt += kKT) {
+        __syncthreads();
+        for (int i = tid; i < kKT * DH; i += 128) KV[i / DH][i % DH] = base[(int64_t)(kt + i / DH) * ld + 2 * D + i % DH];
+        __syncthreads();
+        for (int j = 0; j < kKT; ++j) {
+            const float v = KV[j][d];
+#pragma unroll
+            for (int i = 0; i < kQPer; ++i) o[i] = fmaf(S[qg * kQPer + i][kt + j], v, o[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kQPer; ++i) out[((int64_t)b * kNTok + q0 + qg * kQPer + i) * D + h * DH + d] = o[i];
+}
+
+cudaError_t launch_attention(const float* qkv, float* out, int B, int D, int heads, cudaStream_t s) {
+    if (B <= 0) return cudaSuccess;
+    const int dh = D / heads;
+    dim3 grid(kNTok / kBQ, heads, B);
+    switch (dh) {
+        case 16: attention_kernel<16><<<grid, 128, 0, s>>>(qkv, out, D); break;
+        case 32: attention_kernel<32><<<grid, 128, 0, s>>>(qkv, out, D); break;
+        case 64: attention_kernel<64><<<grid, 128, 0, s>>>(qkv, out, D); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8 decode: 1x1 conv -> sigmoid -> hann window -> first-maximum argmax -> bbox (App. A.5-A.6).
+// One CTA (256 threads = 256 map cells) per target; the winning cell is found with a
+// warp-shuffle (value, index) reduction; thread 0 updates rect_last on the device so the next
+// frame's crop needs no host round trip.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ h1, int C, const float* __restrict__ w2,
+                                                     const float* __restrict__ b2, const float* __restrict__ hann,
+                                                     TargetState* __restrict__ state, const int32_t* __restrict__ slots, float threshold,
+                                                     DeviceResult* __restrict__ res, float* __restrict__ maps) {
+    __shared__ float s_val[8];
+    __shared__ int s_idx[8];
+    __shared__ float s_out[4];
+    const int bi = blockIdx.x, slot = slots[bi], p = threadIdx.x;
+    const float* f = h1 + ((int64_t)bi * kNTx + p) * C;
+    float o[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float acc = b2[k];
+        for (int c = 0; c < C; ++c) acc = __fadd_rn(acc, __fmul_rn(f[c], w2[k * C + c]));  // oracle order, unfused
+        o[k] = acc;
+    }
+    const float conf = 1.f / (1.f + expf(-o[0]));
+    const float sw = 1.f / (1.f + expf(-o[1])), sh = 1.f / (1.f + expf(-o[2]));
+    const float cw = __fmul_rn(conf, hann[p]);
+    float* m = maps + (int64_t)slot * 1280;
+    m[p] = cw, m[256 + p] = sw, m[512 + p] = sh, m[768 + p] = o[3], m[1024 + p] = o[4];
+
+    // first row-major maximum
+    float bv = cw;
+    int bidx = p;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+        if (ov > bv || (ov == bv && oi < bidx)) bv = ov, bidx = oi;
+    }
+    if ((p & 31) == 0) s_val[p >> 5] = bv, s_idx[p >> 5] = bidx;
+    __syncthreads();
+    if (p < 32) {
+        bv = p < 8 ? s_val[p] : -INFINITY;
+        bidx = p < 8 ? s_idx[p] : 0x7fffffff;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+            if (ov > bv || (ov == bv && oi < bidx)) bv = ov, bidx = oi;
+        }
+        if (p == 0) s_idx[0] = bidx, s_val[0] = bv;
+    }
+    __syncthreads();
+    const int best = s_idx[0];
+    if (p == best) s_out[0] = o[3], s_out[1] = o[4], s_out[2] = sw, s_out[3] = sh;
+    __syncthreads();
+    if (p == 0) {
+        TargetState* st = state + slot;
+        DeviceResult r;
+        r.success = 0, r.score = 0.f, r.bbox[0] = r.bbox[1] = r.bbox[2] = r.bbox[3] = 0, r.best = best;
+        r.status = VT_OK;
+        if (!st->active) {
+            r.status = VT_ERR_NOT_INIT;
+        } else if (st->crop_err) {
+            r.status = VT_ERR_CROP_OUTSIDE;
+        } else {
+            r.score = s_val[0];
+            if (r.score >= threshold) {
+                const int my = best / kMap, mx = best % kMap;
+                const float cx = __fdiv_rn(__fadd_rn((float)mx, s_out[0]), 16.f);
+                const float cy = __fdiv_rn(__fadd_rn((float)my, s_out[1]), 16.f);
+                const float bw = s_out[2], bh = s_out[3];
+                const int lx = st->rect[0], ly = st->rect[1], lw = st->rect[2], lh = st->rect[3];
+                const int cwin = (int)ceil(__dmul_rn(sqrt((double)((long long)lw * lh)), 4.0));
+                const int x0 = lx + (lw - cwin) / 2, y0 = ly + (lh - cwin) / 2;
+                const float fc = (float)cwin;
+                r.bbox[0] = (int)floorf(__fadd_rn(__fmul_rn(__fsub_rn(cx, __fdiv_rn(bw, 2.f)), fc), (float)x0));
+                r.bbox[1] = (int)floorf(__fadd_rn(__fmul_rn(__fsub_rn(cy, __fdiv_rn(bh, 2.f)), fc), (float)y0));
+                r.bbox[2] = (int)floorf(__fmul_rn(bw, fc));
+                r.bbox[3] = (int)floorf(__fmul_rn(bh, fc));
+                r.success = 1;
+                st->rect[0] = r.bbox[0], st->rect[1] = r.bbox[1], st->rect[2] = r.bbox[2], st->rect[3] = r.bbox[3];
+            }
+        }
+        res[slot] = r;
+    }
+}
+
+cudaError_t launch_decode(const float* h1, int head_ch, const float* w2, const float* b2, const float* hann, TargetState* d_state,
+                          const int32_t* d_slots, int n, float threshold, DeviceResult* d_res, float* d_maps, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    decode_kernel<<<n, 256, 0, s>>>(h1, head_ch, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps);
+    return cudaGetLastError();
+}
+
+}  // namespace vt

@@ -1,0 +1,142 @@
+// vt_internal.h — shared declarations of libvittrack_b200 (not installed; the public ABI is include/vt_tracker.h)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "vt_tracker.h"
+
+namespace vt {
+
+constexpr int kNTz = 64;        // template tokens (128/16)^2
+constexpr int kNTx = 256;       // search tokens (256/16)^2
+constexpr int kNTok = 320;      // joint sequence
+constexpr int kPatchK = 768;    // 3*16*16
+constexpr int kSearch = 256;
+constexpr int kTemplate = 128;
+constexpr int kMap = 16;        // score map side
+constexpr int kWindow = 120;    // TimingStats window (src/timing_stats.rs:19)
+constexpr int kMaxCmds = 32;
+
+void set_error(const char* fmt, ...);
+
+#define VT_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ::vt::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return VT_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+// ---- TimingStats, src/timing_stats.rs:3-60 (same window, same arithmetic) -------------------------
+template <typename T>
+struct Ring {
+    T v[kWindow];
+    int head = 0, len = 0;
+    void push(T x) {
+        if (len >= kWindow) head = (head + 1) % kWindow, --len;
+        v[(head + len) % kWindow] = x;
+        ++len;
+    }
+    double mean() const {
+        if (!len) return 0.0;
+        double s = 0;
+        for (int i = 0; i < len; ++i) s += (double)v[(head + i) % kWindow];
+        return s / len;
+    }
+};
+struct TimingStats {
+    Ring<uint64_t> intervals, conv, track;
+    void add_interval(uint64_t us) { intervals.push(us); }
+    void add_times(uint64_t c, uint64_t t) { conv.push(c), track.push(t); }
+    double fps() const {
+        if (!intervals.len) return 0.0;
+        const double avg = intervals.mean();
+        return avg > 0.0 ? 1000000.0 / avg : 0.0;
+    }
+    double avg_conv_ms() const { return conv.len ? conv.mean() / 1000.0 : 0.0; }
+    double avg_track_ms() const { return track.len ? track.mean() / 1000.0 : 0.0; }
+};
+
+// ---- per-target device state -----------------------------------------------------------------
+struct TargetState {       // lives in device memory, one per target slot
+    int32_t rect[4];       // rect_last x, y, w, h  (≙ TrackerVit::rect_last)
+    int32_t active;        // 1 after init
+    int32_t crop_err;      // set by the crop kernel when the window is entirely outside the frame
+    int32_t pad[2];
+};
+
+struct DeviceResult {      // written by the decode kernel, copied to pinned host memory
+    int32_t success;
+    float score;
+    int32_t bbox[4];
+    int32_t status;
+    int32_t best;          // argmax index (diagnostic)
+};
+
+// ---- pixel kernels (pixel.cu) ------------------------------------------------------------------
+struct FrameDesc {
+    const uint8_t* data;   // device pointer, tightly packed
+    int32_t width, height;
+    int32_t format;        // vt_format
+    int32_t valid;         // 0: buffer was short -> black image (src/nv12_convert.rs:48-50)
+};
+
+cudaError_t launch_nv12_to_rgb(const uint8_t* d_nv12, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int width, int height,
+                               int n_frames, cudaStream_t s);
+
+// fused crop + (NV12->RGB) + bilinear resize + normalise -> patch-major tokens A[target][n_tok][768]
+// slots: list of target slot indices processed (device array), n = count. factor 2 -> 128 template, 4 -> 256 search
+cudaError_t launch_crop_resize_norm(FrameDesc f, TargetState* d_state, const int32_t* d_slots, int n, int factor, int out_size,
+                                    const float* d_norm_lut, float* d_patches, size_t patches_stride, const int32_t* d_init_rect,
+                                    cudaStream_t s);
+
+struct OverlayCmdDev {     // device-side copy of vt_overlay_cmd with resolved glyph rows
+    int32_t kind, x, y, w, h, a;
+    uint8_t r, g, b, nchar;
+    uint8_t glyph[48][7];  // rows per character; 0xFF in row 0 marks "unknown: skip"
+    uint8_t known[48];
+};
+cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const OverlayCmdDev* d_cmds, int n,
+                           cudaStream_t s);
+// device-side box overlay straight from the decode result (rect thickness 3 + crosshair 15, src/pipeline.rs:165-168)
+cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
+                               const int32_t* d_slots, int n, float gate, cudaStream_t s);
+
+// ---- ViT kernels (vit.cu) ----------------------------------------------------------------------
+struct GemmArgs {
+    const float* A;        // activations, row-major
+    int64_t lda;
+    const float* W;        // [N, K] row-major (torch Linear layout)
+    const float* bias;     // [N] or null
+    float* C;
+    int64_t ldc;
+    int M, N, K;
+    // optional LayerNorm over the K axis of A (K == feature dim)
+    const float* ln_g;
+    const float* ln_b;
+    // epilogue
+    int gelu;              // exact erf GELU
+    int relu;
+    int residual;          // C = C + result
+    const float* pos;      // [a_rows_in, N] added per row (pos-embed), or null
+    // row maps: logical row m -> physical row (m / rows_in) * rows_stride + row_off + (m % rows_in)
+    int a_rows_in, a_rows_stride, a_row_off;
+    int c_rows_in, c_rows_stride, c_row_off;
+    // im2col mode for the 3x3 head conv: K = 9*feat, tap-major; A rows are 16x16 grid tokens
+    int im2col_feat;       // 0 = off, else feature dim D
+};
+cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
+cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* g, const float* b, float* y, int64_t ldy, int M, int D,
+                             int rows_in, int rows_stride, int row_off, cudaStream_t s);
+// qkv: [B*320, 3D]; out: [B*320, D]
+cudaError_t launch_attention(const float* qkv, float* out, int B, int D, int heads, cudaStream_t s);
+// head 1x1 conv + sigmoid + hann + argmax + bbox decode, one CTA per target
+cudaError_t launch_decode(const float* h1, int head_ch, const float* w2, const float* b2, const float* hann, TargetState* d_state,
+                          const int32_t* d_slots, int n, float threshold, DeviceResult* d_res, float* d_maps, cudaStream_t s);
+
+}  // namespace vt

@@ -1,0 +1,252 @@
+/*
+ * vt_tracker.h — C ABI of the B200-native ViT tracker hot path (libvittrack_b200.so).
+ *
+ * This is the drop-in boundary for the per-frame path of frodik13/gstreamer-vit-tracker.  The
+ * reference has no FFI of its own for this path: it is plain Rust calling
+ *   - nv12_convert::nv12_full_to_rgb_parallel / draw_*_nv12     (src/nv12_convert.rs:46,172-343)
+ *   - drawing::{draw_cursor, draw_selection, get_glyph}          (src/drawing.rs:5-100)
+ *   - drawing_rgb::draw_*_rgb                                    (src/drawing_rgb.rs:30-128)
+ *   - vit_tracker::VitTrack::{new, init, update}                 (call sites src/tracker_context.rs:21,88,90,120)
+ *   - TrackerContext::{new, handle_command, process_frame, state_name} (src/tracker_context.rs:19-166)
+ *   - TimingStats::{add_interval, add_times, fps, avg_*_ms}      (src/timing_stats.rs:17-60)
+ * from the pad-probe closures (src/pipeline.rs:67-184, src/pipeline_ir.rs:100-228).  Each entry
+ * point below names the reference interface it replaces; INTEGRATION.md shows the Rust
+ * `extern "C"` block a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; no exceptions cross the boundary; every call
+ * returns vt_status (0 = ok, negative = error).  A handle is thread-compatible (calls on one
+ * handle must be serialised, exactly like the reference's Arc<Mutex<TrackerContext>>,
+ * src/pipeline.rs:55,111); different handles may be used concurrently from different threads.
+ * Frame memory is owned by the caller and never retained after a call returns (the reference
+ * borrows the mapped GstBuffer for the duration of the probe, src/pipeline.rs:96).  There is no
+ * CPU fallback: without a CUDA device every device entry point fails with VT_ERR_CUDA.
+ */
+#ifndef VT_TRACKER_H
+#define VT_TRACKER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_ABI_VERSION 1
+
+typedef int32_t vt_status;
+enum {
+    VT_OK = 0,
+    VT_ERR_INVALID = -1,      /* bad argument */
+    VT_ERR_CUDA = -2,         /* CUDA runtime / driver failure (vt_last_error() has the text) */
+    VT_ERR_WEIGHTS = -3,      /* weight file missing or malformed            ≙ VitTrack::new Err */
+    VT_ERR_CROP_OUTSIDE = -4, /* crop window lies entirely outside the frame ≙ VitTrack::update Err */
+    VT_ERR_NOT_INIT = -5,     /* update() before init()                       */
+    VT_ERR_GLYPH = -6         /* unknown character in strict text mode        ≙ get_glyph panic, src/drawing.rs:99 */
+};
+
+typedef enum { VT_FMT_NV12 = 0, VT_FMT_RGB24 = 1 } vt_format;
+typedef enum { VT_GEMM_FP32_SIMT = 0, VT_GEMM_TCGEN05_BF16X3 = 1, VT_GEMM_TCGEN05_BF16 = 2 } vt_gemm_mode;
+
+/* ≙ vit_tracker::BBox {x, y, width, height: i32} (uses: src/selection_state.rs:44, src/pipeline.rs:166) */
+typedef struct { int32_t x, y, width, height; } vt_bbox;
+
+/* ≙ the Ok(result) of VitTrack::update: result.success, result.score, result.bbox
+ * (src/tracker_context.rs:92-94,121-123).  status != VT_OK ≙ the Err branch for that target. */
+typedef struct {
+    int32_t success;
+    float score;
+    vt_bbox bbox;
+    vt_status status;
+    int32_t reserved;
+} vt_result;
+
+/* Hard-coded constants of the reference become fields (SURVEY.md §5 "config / flags"). */
+typedef struct {
+    uint32_t struct_size;        /* sizeof(vt_config), for ABI evolution */
+    const char* weights_path;    /* ≙ MODEL_PATH, src/pipeline.rs:11 (flat "VTW1" file instead of .rknn) */
+    int32_t device;              /* CUDA device ordinal */
+    int32_t format;              /* vt_format of the frames handed to init/update */
+    int32_t width, height;       /* ≙ the caps of src/pipeline.rs:26-36 / src/pipeline_ir.rs:27-41 */
+    int32_t max_targets;         /* 1 in the reference (one VitTrack, src/tracker_context.rs:8) */
+    float score_threshold;       /* TrackerVit's own threshold (0.20); <=0 selects the default */
+    int32_t gemm_mode;           /* vt_gemm_mode */
+    int32_t use_cuda_graph;      /* 1: replay the per-frame kernel chain from a CUDA graph */
+    int32_t box_overlay;         /* 1: update() also draws rect+crosshair for gated targets (device) and
+                                       copies the touched rows back into the caller's frame */
+    float overlay_gate;          /* gate for box_overlay: success && score > gate (0.25, src/tracker_context.rs:93) */
+    int32_t reserved[8];
+} vt_config;
+
+typedef struct vt_tracker vt_tracker;
+
+/* ------------------------------------------------------------------------------------------- */
+/* library                                                                                      */
+/* ------------------------------------------------------------------------------------------- */
+int32_t vt_abi_version(void);
+/* thread-local text of the last failure on the calling thread (never NULL) */
+const char* vt_last_error(void);
+void vt_config_default(vt_config* cfg);
+/* pinned host memory for frames (what a GstAllocator for the upstream element would hand out) */
+vt_status vt_alloc_pinned(size_t bytes, void** out);
+void vt_free_pinned(void* p);
+
+/* ------------------------------------------------------------------------------------------- */
+/* VitTrack                                                                                     */
+/* ------------------------------------------------------------------------------------------- */
+/* ≙ VitTrack::new(model_path) (src/tracker_context.rs:21) */
+vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out);
+void vt_tracker_destroy(vt_tracker* t);
+
+/* ≙ VitTrack::init(&frame, bbox) (src/tracker_context.rs:88).  `frame` is host memory in the
+ * handle's format, tightly packed (NV12: w*h*3/2 bytes, src/nv12_convert.rs:48; RGB24: h*w*3,
+ * src/pipeline_ir.rs:142).  A short NV12 buffer is treated as an all-black image
+ * (src/nv12_convert.rs:48-50). */
+vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, size_t len, vt_bbox box);
+
+/* ≙ VitTrack::update(&frame) (src/tracker_context.rs:90,120) for every initialised target, one
+ * batched forward.  results[max_targets]; entries of targets that are not initialised get
+ * status VT_ERR_NOT_INIT.  With cfg.box_overlay the rows touched by the box overlay are written
+ * back into `frame` (≙ draw_rect_nv12 + draw_crosshair_nv12, src/pipeline.rs:165-168). */
+vt_status vt_tracker_update(vt_tracker* t, uint8_t* frame, size_t len, vt_result* results);
+
+/* Asynchronous pair used by the multi-stream driver: submit() enqueues upload + kernels on the
+ * handle's CUDA stream and returns; wait() blocks until that frame's results are in host memory.
+ * At most one frame may be in flight per handle. `frame` must stay valid until wait() returns. */
+vt_status vt_tracker_submit(vt_tracker* t, uint8_t* frame, size_t len);
+vt_status vt_tracker_wait(vt_tracker* t, vt_result* results);
+
+/* Same as update() but the frame is already in device memory (bench `value` leg, NVDEC/NVMM producers). */
+vt_status vt_tracker_update_device(vt_tracker* t, const uint8_t* d_frame, size_t len, vt_result* results);
+
+/* tracker state access (≙ rect_last inside VitTrack; used by tests for teacher forcing) */
+vt_status vt_tracker_get_rect(vt_tracker* t, int32_t target, vt_bbox* out);
+vt_status vt_tracker_set_rect(vt_tracker* t, int32_t target, vt_bbox box);
+vt_status vt_tracker_drop(vt_tracker* t, int32_t target); /* forget a target */
+
+/* diagnostics for parity tests: copies of device intermediates of the last update (any pointer may be NULL)
+ *   search_blob  float[3*256*256]  planar CHW normalised search crop of `target`
+ *   conf_win     float[256]        conf * hann
+ *   size_map     float[512], off_map float[512]
+ *   tokens       float[320*D]      final-LayerNorm token features */
+vt_status vt_tracker_debug_read(vt_tracker* t, int32_t target, float* search_blob, float* template_blob,
+                                float* conf_win, float* size_map, float* off_map, float* tokens);
+int32_t vt_tracker_model_dim(const vt_tracker* t, int32_t which); /* 0 D, 1 depth, 2 heads, 3 hidden, 4 head_ch */
+/* token features [320*D] after the embeddings (which = 0) or after block `which` (1..depth).  Needs
+ * cfg.reserved[0] = 1 at create time (captures one copy per block; disables graph replay). */
+vt_status vt_tracker_debug_tokens(vt_tracker* t, int32_t target, int32_t which, float* out);
+/* the handle's CUDA stream (cudaStream_t) so that callers can time on the launching stream, and a stream sync */
+void* vt_tracker_stream(vt_tracker* t);
+vt_status vt_tracker_sync(vt_tracker* t);
+
+/* ------------------------------------------------------------------------------------------- */
+/* NV12 -> RGB (parity / bench entry)                                                           */
+/* ------------------------------------------------------------------------------------------- */
+/* ≙ nv12_full_to_rgb_parallel(nv12, width, height) -> Array3<u8>(h, w, 3) in R,G,B order
+ * (src/nv12_convert.rs:46-92).  Host buffers; len < w*h*3/2 -> rgb_out is all zeros (:48-50). */
+vt_status vt_convert_nv12_rgb(vt_tracker* t, const uint8_t* nv12, size_t len, uint8_t* rgb_out);
+/* device-resident, batched: n_frames frames of the handle's geometry, frame i at d_nv12 + i*stride_in */
+vt_status vt_convert_nv12_rgb_device(vt_tracker* t, const uint8_t* d_nv12, size_t stride_in, uint8_t* d_rgb,
+                                     size_t stride_out, int32_t n_frames);
+
+/* ------------------------------------------------------------------------------------------- */
+/* overlay                                                                                      */
+/* ------------------------------------------------------------------------------------------- */
+typedef enum {
+    VT_OV_RECT = 0,       /* ≙ draw_rect_nv12 (src/nv12_convert.rs:172) / draw_rect_rgb (src/drawing_rgb.rs:55): x,y,w,h,a=thickness */
+    VT_OV_CROSSHAIR = 1,  /* ≙ draw_crosshair_nv12 (:216) / draw_crosshair_rgb (:68): x=cx,y=cy,a=size */
+    VT_OV_TEXT = 2,       /* ≙ draw_text_nv12 (:245) / draw_text_rgb (:86): x,y,a=scale,text */
+    VT_OV_BACKGROUND = 3, /* ≙ draw_background_nv12 (:324; a=darkness) / draw_background_rgb (:30; fill 30) */
+    VT_OV_CURSOR = 4,     /* ≙ draw_cursor (src/drawing.rs:5) / draw_cursor_rgb (src/drawing_rgb.rs:75): x,y */
+    VT_OV_SELECTION = 5   /* ≙ draw_selection (src/drawing.rs:25) / draw_selection_rgb (:106): x,y=start, w,h=cursor */
+} vt_overlay_kind;
+
+typedef struct {
+    int32_t kind;
+    int32_t x, y, w, h;
+    int32_t a;            /* thickness | size | scale | darkness */
+    uint8_t r, g, b;      /* NV12: r is the luma/brightness; RGB: colour (text uses r as luma) */
+    uint8_t strict_glyphs;/* text: 1 = unknown char is VT_ERR_GLYPH (RGB path panics in the reference), 0 = skip+advance (NV12 path) */
+    char text[48];
+} vt_overlay_cmd;
+
+/* Applies cmds in order to a host frame (upload, draw on device, copy the touched rows back). */
+vt_status vt_overlay(vt_tracker* t, uint8_t* frame, size_t len, const vt_overlay_cmd* cmds, int32_t n);
+/* Same, on the device-resident copy of the frame most recently given to update()/submit(); only the
+ * touched rows travel back into `frame`.  This is what the probe shim uses. */
+vt_status vt_overlay_current(vt_tracker* t, uint8_t* frame, size_t len, const vt_overlay_cmd* cmds, int32_t n);
+
+/* ------------------------------------------------------------------------------------------- */
+/* timing                                                                                       */
+/* ------------------------------------------------------------------------------------------- */
+/* ≙ TimingStats (src/timing_stats.rs): same 120-sample windows and accessors, plus the
+ * device-timed (cudaEvent) stage breakdown of the last frame and its rolling means. */
+typedef struct {
+    double fps;            /* ≙ TimingStats::fps()          1e6 / mean(interval_us) */
+    double avg_conv_ms;    /* ≙ TimingStats::avg_conv_ms()  (device: preprocess stage) */
+    double avg_track_ms;   /* ≙ TimingStats::avg_track_ms() (host wall time of update) */
+    /* device-timed stages, last frame (ms) */
+    float h2d_ms, preprocess_ms, vit_ms, decode_ms, overlay_ms, d2h_ms, total_ms;
+    /* rolling means over the same 120-frame window (ms) */
+    float avg_h2d_ms, avg_preprocess_ms, avg_vit_ms, avg_decode_ms, avg_overlay_ms, avg_d2h_ms, avg_total_ms;
+    uint64_t frames;
+    uint64_t kernel_launches;  /* kernels launched by this handle so far (graph nodes count individually) */
+} vt_timing;
+vt_status vt_timing_get(vt_tracker* t, vt_timing* out);
+/* ≙ TimingStats::add_interval / add_times for callers that keep the reference's host timers */
+vt_status vt_timing_add_interval(vt_tracker* t, uint64_t us);
+vt_status vt_timing_add_times(vt_tracker* t, uint64_t conv_us, uint64_t track_us);
+
+/* ≙ TimingStats::new() as a free-standing object for callers that keep their own timers (no device needed) */
+typedef struct vt_timing_stats vt_timing_stats;
+vt_timing_stats* vt_timing_stats_create(void);
+void vt_timing_stats_destroy(vt_timing_stats* s);
+void vt_timing_stats_add_interval(vt_timing_stats* s, uint64_t us);
+void vt_timing_stats_add_times(vt_timing_stats* s, uint64_t conv_us, uint64_t track_us);
+double vt_timing_stats_fps(const vt_timing_stats* s);
+double vt_timing_stats_avg_conv_ms(const vt_timing_stats* s);
+double vt_timing_stats_avg_track_ms(const vt_timing_stats* s);
+
+/* ------------------------------------------------------------------------------------------- */
+/* host state machine (≙ TrackerContext / SelectionState / UserCommand / AppState)              */
+/* ------------------------------------------------------------------------------------------- */
+/* ≙ UserCommand (src/user_commands.rs:2-9); `fast` is the bool payload of the Move* variants */
+typedef enum { VT_CMD_MOVE_UP = 0, VT_CMD_MOVE_DOWN, VT_CMD_MOVE_LEFT, VT_CMD_MOVE_RIGHT, VT_CMD_CONFIRM, VT_CMD_CANCEL, VT_CMD_QUIT } vt_command;
+/* ≙ state_name() values (src/tracker_context.rs:157-166) */
+typedef enum { VT_STATE_SELECT_START = 0, VT_STATE_SELECT_END, VT_STATE_TRACKING, VT_STATE_LOST } vt_state;
+/* ≙ SelectionState (src/selection_state.rs:9-18) */
+typedef struct { int32_t cursor_x, cursor_y, start_x, start_y, phase, step, fast_step; } vt_selection;
+
+typedef struct vt_context vt_context;
+/* ≙ TrackerContext::new(model_path, width, height) (src/tracker_context.rs:19); creates its tracker from cfg */
+vt_status vt_context_create(const vt_config* cfg, vt_context** out);
+void vt_context_destroy(vt_context* c);
+/* ≙ TrackerContext::handle_command (src/tracker_context.rs:36) */
+vt_status vt_context_handle_command(vt_context* c, int32_t cmd, int32_t fast);
+/* ≙ TrackerContext::process_frame(&frame) -> Option<BBox> (src/tracker_context.rs:64).
+ * *has_bbox = 1 and *bbox filled ≙ Some(bbox). Frame in the handle's format (NV12 frames are
+ * converted on the device inside the fused crop kernel; the RGB image is never materialised). */
+vt_status vt_context_process_frame(vt_context* c, uint8_t* frame, size_t len, int32_t* has_bbox, vt_bbox* bbox);
+/* The same state machine with the outcome of VitTrack::update supplied by the caller (err != 0 ≙ Err);
+ * no device is involved.  Used to exercise the host logic without a GPU. */
+vt_status vt_context_create_scripted(int32_t width, int32_t height, vt_context** out);
+vt_status vt_context_process_scripted(vt_context* c, const vt_result* scripted, int32_t err, int32_t* has_bbox, vt_bbox* bbox);
+int32_t vt_context_state(const vt_context* c);
+const char* vt_context_state_name(const vt_context* c);            /* "SELECT START" | "SELECT END" | "TRACKING" | "LOST" */
+float vt_context_current_score(const vt_context* c);                /* ≙ ctx.current_score (src/pipeline.rs:116) */
+int32_t vt_context_current_bbox(const vt_context* c, vt_bbox* out); /* ≙ ctx.current_bbox (src/pipeline.rs:170); 1 = Some */
+void vt_context_selection(const vt_context* c, vt_selection* out);  /* ≙ ctx.selection.clone() (src/pipeline.rs:117) */
+uint64_t vt_context_lost_frames(const vt_context* c);
+vt_tracker* vt_context_tracker(vt_context* c);
+
+/* ≙ the body of the pad-probe closure, src/pipeline.rs:67-184 (NV12) / src/pipeline_ir.rs:100-228
+ * (RGB24, chosen by cfg.format): interval timing, process_frame, HUD + cursor/selection + box
+ * overlay written in place into `frame`.  Commands are delivered beforehand with
+ * vt_context_handle_command (≙ draining cmd_rx, src/pipeline.rs:84-88).  hud_override (may be
+ * NULL) replaces the timing-dependent HUD strings so that pixel parity is testable:
+ * {fps_line, timing_line}. */
+vt_status vt_probe_frame(vt_context* c, uint8_t* frame, size_t len, const char* const* hud_override);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VT_TRACKER_H */
