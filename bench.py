@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: 1080p tracked frames/s (BASELINE.json `metric`).
+
+A "step" is one pass of the per-frame hot path (NV12 ingest -> fused crop/convert/resize/normalise ->
+ViT forward -> score-map decode -> box overlay) over one frame of every stream this rank owns.
+Workload at N=1: BASELINE.json configs[1] — a single 1920x1080 NV12 stream, one target.
+For N>1 every rank runs its own independent stream(s) (seeds 2000+i, cfg5 geometry): no data-path
+collective exists, `scaling` is "weak", value = frames of all ranks / max-over-ranks device time.
+
+  value  frames/s with the frames already resident in HBM (vt_tracker_update_device)
+  e2e    frames/s through the reference-facing C-ABI call vt_tracker_update with pinned HOST buffers
+         (H2D of the frame and D2H of result + overlaid rows inside the timed region)
+  roofline      dominant unit of the step (the ViT forward: dense contractions, tensor bound) measured live with
+                CUDA events recorded inside the replayed graph; `roofline_convert` is the HBM-bound NV12->RGB kernel
+  cpu_baseline  the CPU oracle (a port: the reference itself is Rust + an absent crate) on the host cores
+  --impl reference   times that CPU path alone, same metric/config
+
+Only the cpu_baseline / --impl reference legs touch oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "1080p tracked frames/s"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--warmup", type=int, default=60)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="tiny", choices=["tiny", "nano"])
+    ap.add_argument("--streams-per-gpu", type=int, default=1)
+    ap.add_argument("--ring", type=int, default=128, help="distinct frames per stream (ring > L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-frames", type=int, default=0)
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def workload_name(args):
+    return (f"cfg2: single 1920x1080 NV12 synthetic stream, one target, model={args.model}, "
+            f"{args.streams_per_gpu} stream(s) per GPU" + (" (cfg5 seeds, one stream set per rank)" if args.gpus > 1 else ""))
+
+
+def stream_spec(rank, k, args):
+    from gstreamer_vit_tracker_b200 import synth
+    if args.gpus == 1 and args.streams_per_gpu == 1:
+        return synth.CONFIGS["cfg2"]
+    return synth.cfg5_stream((rank * args.streams_per_gpu + k) % 64)
+
+
+def weight_path(model):
+    from gstreamer_vit_tracker_b200 import weights
+    return weights.ensure_weight_file(model, os.path.join(tempfile.gettempdir(), "vt_b200_weights"))
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.p, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the Rust reference cannot be built here) on all host threads."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from gstreamer_vit_tracker_b200 import synth
+    from oracle import oracle
+    threads = len(os.sched_getaffinity(0)) or 1
+    spec = synth.CONFIGS["cfg2"]
+    st = synth.SyntheticStream(spec)
+    W, H = spec.width, spec.height
+    trk = oracle.VitTrack(weight_path(args.model), threads=threads)
+    ring = [st.frame(i) for i in range(min(args.ring, args.warmup + args.steps))]
+    rgb0 = oracle.nv12_to_rgb(ring[0], W, H, threads)
+    trk.init(rgb0, st.target_boxes(0)[0])
+
+    def step(i):
+        fr = ring[i % len(ring)].copy()
+        rgb = oracle.nv12_to_rgb(fr, W, H, threads)               # conv  (src/pipeline.rs:105)
+        rc, ok, score, bb = trk.update(rgb)                       # track (src/pipeline.rs:112)
+        if rc == 0 and ok and score > 0.25:                       # overlay (src/pipeline.rs:165-168)
+            oracle.draw_rect_nv12(fr, W, H, bb[0], bb[1], bb[2], bb[3], 3, 255)
+            oracle.draw_crosshair_nv12(fr, W, H, bb[0] + bb[2] // 2, bb[1] + bb[3] // 2, 15, 255)
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(args), "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} frames of cfg2 after {args.warmup} warm-up: convert + VitTrack::update + box overlay, OpenMP {threads} threads"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = CPU oracle port (the Rust reference + absent vit_tracker crate cannot be built in this image)"}))
+
+
+def cpu_baseline(args, n_frames):
+    from gstreamer_vit_tracker_b200 import synth
+    from oracle import oracle
+    threads = len(os.sched_getaffinity(0)) or 1
+    spec = synth.CONFIGS["cfg2"]
+    st = synth.SyntheticStream(spec)
+    W, H = spec.width, spec.height
+    trk = oracle.VitTrack(weight_path(args.model), threads=threads)
+    frames = [st.frame(i) for i in range(n_frames + 2)]
+    trk.init(oracle.nv12_to_rgb(frames[0], W, H, threads), st.target_boxes(0)[0])
+    t_conv = t_track = 0.0
+    for i in range(2):
+        trk.update(oracle.nv12_to_rgb(frames[i], W, H, threads))
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        fr = frames[2 + i]
+        a = time.perf_counter()
+        rgb = oracle.nv12_to_rgb(fr, W, H, threads)
+        b = time.perf_counter()
+        rc, ok, score, bb = trk.update(rgb)
+        c = time.perf_counter()
+        if ok:
+            oracle.draw_rect_nv12(fr, W, H, bb[0], bb[1], bb[2], bb[3], 3, 255)
+            oracle.draw_crosshair_nv12(fr, W, H, bb[0] + bb[2] // 2, bb[1] + bb[3] // 2, 15, 255)
+        t_conv += b - a
+        t_track += c - b
+    dt = time.perf_counter() - t0
+    return {"value": n_frames / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_frames} frames of cfg2 (convert + VitTrack::update + box overlay), OpenMP {threads} threads",
+            "conv_ms": t_conv / n_frames * 1e3, "track_ms": t_track / n_frames * 1e3}
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from gstreamer_vit_tracker_b200 import api, weights
+
+    wpath = weight_path(args.model)
+    cfg_model = weights.MODELS[args.model]
+    S = args.streams_per_gpu
+    K, Wm = args.steps, args.warmup
+    ring_n = max(8, min(args.ring, K + Wm))
+
+    # ---- streams: tracker handle, pinned host ring, device ring -----------------------------------------
+    streams = []
+    from gstreamer_vit_tracker_b200 import synth
+    for k in range(S):
+        spec = stream_spec(rank, k, args)
+        st = synth.SyntheticStream(spec)
+        fb = st.frame_bytes()
+        trk = api.VitTrack.new(wpath, spec.width, spec.height, fmt="nv12", device=local_rank, box_overlay=True)
+        pin = api.PinnedBuffer(ring_n * fb)
+        host = pin.array.reshape(ring_n, fb)
+        for i in range(ring_n):
+            host[i] = st.frame(i)
+        pristine = host.copy()  # the overlay writes into the frame; restore before reuse
+        dev = torch.from_numpy(pristine).cuda(local_rank)
+        trk.init(host[0], api.BBox(*st.target_boxes(0)[0]))
+        streams.append(dict(spec=spec, trk=trk, pin=pin, host=host, pristine=pristine, dev=dev, fb=fb, init_box=st.target_boxes(0)[0]))
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_leg(kind, n_steps, offset):
+        """Runs n_steps steps on every stream of this rank (one host thread per stream); returns per-frame host latencies (s)."""
+        lat = [[] for _ in streams]
+
+        def worker(si):
+            s = streams[si]
+            trk, host, dev, fb = s["trk"], s["host"], s["dev"], s["fb"]
+            for i in range(n_steps):
+                j = (offset + i) % ring_n
+                t0 = time.perf_counter()
+                if kind == "device":
+                    trk.update_device(dev[j].data_ptr(), fb)
+                else:
+                    trk.update_all(host[j])
+                lat[si].append(time.perf_counter() - t0)
+        if len(streams) == 1:
+            worker(0)
+        else:
+            th = [threading.Thread(target=worker, args=(i,)) for i in range(len(streams))]
+            [t.start() for t in th]
+            [t.join() for t in th]
+        return lat
+
+    n_steps_timed = K
+
+    def timed(kind):
+        for s in streams:  # same starting state for both legs
+            s["host"][:] = s["pristine"]
+            s["trk"].init(s["host"][0], api.BBox(*s["init_box"]))
+        run_leg(kind, Wm, 0)
+        tm0 = [s["trk"].timing() for s in streams]
+        launches0 = sum(t.kernel_launches for t in tm0)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # events on the handle's own stream (the stream the kernels are launched on)
+        ext = torch.cuda.ExternalStream(streams[0]["trk"].stream, device=local_rank)
+        ev0.record(ext)
+        lat = run_leg(kind, K, Wm)
+        ev1.record(ext)
+        for s in streams:
+            s["trk"].sync()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        tm1 = [s["trk"].timing() for s in streams]
+        launches = sum(t.kernel_launches for t in tm1) - launches0
+        h2d = sum(b.h2d_bytes - a.h2d_bytes for a, b in zip(tm0, tm1)) / n_steps_timed
+        d2h = sum(b.d2h_bytes - a.d2h_bytes for a, b in zip(tm0, tm1)) / n_steps_timed
+        return ms, lat, launches, h2d, d2h
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, lat_dev, launches_dev, _, _ = timed("device")
+    tm = streams[0]["trk"].timing()
+    stage = {k: getattr(tm, "avg_" + k) for k in ("h2d_ms", "preprocess_ms", "vit_ms", "decode_ms", "overlay_ms", "d2h_ms", "total_ms")}
+    ms_e2e, lat_e2e, launches_e2e, h2d_step, d2h_step = timed("host")
+    tm_e2e = streams[0]["trk"].timing()
+    clocks = sampler.stop()
+    stage_e2e = {k: getattr(tm_e2e, "avg_" + k) for k in ("h2d_ms", "preprocess_ms", "vit_ms", "decode_ms", "overlay_ms", "d2h_ms", "total_ms")}
+
+    # ---- NV12->RGB full-frame kernel (HBM roofline), device resident, batch larger than L2 -------------------
+    s0 = streams[0]
+    nb = min(ring_n, 64)
+    fb, w, h = s0["fb"], s0["spec"].width, s0["spec"].height
+    rgb_out = torch.empty((nb, h * w * 3), dtype=torch.uint8, device=f"cuda:{local_rank}")
+    ext = torch.cuda.ExternalStream(s0["trk"].stream, device=local_rank)
+    for _ in range(3):
+        s0["trk"].nv12_to_rgb_device(s0["dev"].data_ptr(), fb, rgb_out.data_ptr(), h * w * 3, nb)
+    s0["trk"].sync()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(reps):
+        s0["trk"].nv12_to_rgb_device(s0["dev"].data_ptr(), fb, rgb_out.data_ptr(), h * w * 3, nb)
+    e1.record(ext)
+    s0["trk"].sync()
+    cvt_ms = e0.elapsed_time(e1) / reps
+    cvt_bytes = nb * (w * h * 3 // 2 + w * h * 3)
+
+    # ---- aggregate over ranks: max time, sum of frames ------------------------------------------------------
+    frames_rank = K * S
+    t = torch.tensor([ms_dev, ms_e2e, float(frames_rank), float(launches_dev)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_dev_g, ms_e2e_g, frames_g, launches_g = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tsum[3])
+    else:
+        ms_dev_g, ms_e2e_g, frames_g, launches_g = ms_dev, ms_e2e, float(frames_rank), float(launches_dev)
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tf_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        flops = weights.flops_per_frame(cfg_model)
+        vit_s = stage["vit_ms"] * 1e-3
+        ach_tf = (flops / vit_s / 1e12) if vit_s > 0 else None
+        lat_all = np.array([x for l in lat_e2e for x in l]) * 1e3
+        lat_d = np.array([x for l in lat_dev for x in l]) * 1e3
+        fb0 = streams[0]["fb"]
+        out = {
+            "metric": METRIC, "value": frames_g / (ms_dev_g * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_dev_g / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "resolution": "1920x1080", "format": "NV12", "targets": 1, "model": args.model,
+                       "streams_per_gpu": S, "weights": "constructed random-init (SURVEY.md §8c)",
+                       "l2": f"inputs larger than L2: ring of {ring_n} distinct frames = {ring_n * fb0 / 1e6:.0f} MB per stream"},
+            "e2e": {"value": frames_g / (ms_e2e_g * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
+                    "p50_latency_ms": float(np.percentile(lat_all, 50)), "p99_latency_ms": float(np.percentile(lat_all, 99)),
+                    "stages_ms": stage_e2e},
+            "latency_ms": {"device_resident_p50": float(np.percentile(lat_d, 50)), "host_p50": float(np.percentile(lat_all, 50))},
+            "gpu_launches": int(launches_g), "stages_ms": stage,
+            "roofline": {"kernel": "ViT forward (patch-embed, QKV, attention, proj, MLP, head: fp32 SIMT GEMM/attention kernels)",
+                         "bound": "tensor", "achieved": ach_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": (ach_tf / tf_peak) if ach_tf else None, "traffic": None, "peak_source": peak_src,
+                         "note": "B=1 (320 tokens) is launch/latency bound; FLOPs/frame = %.3f G" % (flops / 1e9)},
+            "roofline_convert": {"kernel": "nv12_to_rgb_vec_kernel", "bound": "hbm", "achieved": cvt_bytes / (cvt_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s", "frac": cvt_bytes / (cvt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                                 "frames_per_launch": nb, "bytes_per_launch": cvt_bytes, "ms_per_launch": cvt_ms, "peak_source": peak_src},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n = args.cpu_sample_frames or (60 if args.model == "tiny" else 300)
+            out["cpu_baseline"] = cpu_baseline(args, n)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

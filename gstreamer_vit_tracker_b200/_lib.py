@@ -53,7 +53,7 @@ class vt_timing(C.Structure):
         ("overlay_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
         ("avg_h2d_ms", C.c_float), ("avg_preprocess_ms", C.c_float), ("avg_vit_ms", C.c_float), ("avg_decode_ms", C.c_float),
         ("avg_overlay_ms", C.c_float), ("avg_d2h_ms", C.c_float), ("avg_total_ms", C.c_float),
-        ("frames", C.c_uint64), ("kernel_launches", C.c_uint64),
+        ("frames", C.c_uint64), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
     ]
 
 

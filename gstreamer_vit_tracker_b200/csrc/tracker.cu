@@ -78,7 +78,7 @@ struct vt_tracker {
 
     std::map<int, cudaGraphExec_t> graphs;
     int kernels_per_frame = 0;
-    uint64_t kernel_launches = 0, frames = 0;
+    uint64_t kernel_launches = 0, frames = 0, h2d_bytes = 0, d2h_bytes = 0;
 
     // in-flight frame
     bool in_flight = false;
@@ -301,6 +301,7 @@ static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len) {
     t->frame_valid = (t->fmt == VT_FMT_NV12) ? (len >= (size_t)t->W * t->H * 3 / 2) : (len >= t->frame_bytes);
     if (!t->frame_valid && t->fmt == VT_FMT_NV12) n = 0;  // src/nv12_convert.rs:48-50 -> black image
     if (n == 0) return VT_OK;
+    t->h2d_bytes += n;
     if (is_pinned(frame)) {
         VT_CUDA(cudaMemcpyAsync(t->d_frame, frame, n, cudaMemcpyHostToDevice, t->stream));
     } else {
@@ -380,6 +381,7 @@ static vt_status download_rows(vt_tracker* t, uint8_t* frame, size_t len, const 
         size_t n = (size_t)(sp.second - sp.first + 1) * pitch;
         if (off >= len) continue;
         n = std::min(n, len - off);
+        t->d2h_bytes += n;
         VT_CUDA(cudaMemcpyAsync((pinned ? frame : t->h_stage) + off, t->d_frame + off, n, cudaMemcpyDeviceToHost, t->stream));
     }
     return VT_OK;
@@ -427,6 +429,7 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     vt_status st = run_forward(t);
     if (st != VT_OK) return st;
     VT_CUDA(cudaMemcpyAsync(t->h_res, t->d_res, sizeof(DeviceResult) * t->maxT, cudaMemcpyDeviceToHost, t->stream));
+    t->d2h_bytes += sizeof(DeviceResult) * t->maxT;
     VT_CUDA(cudaEventRecord(t->ev[EV_END], t->stream));
     t->in_flight = true;
     t->inflight_frame = d_src ? nullptr : frame;
@@ -870,7 +873,10 @@ static vt_status build_cmds(vt_tracker* t, const vt_overlay_cmd* cmds, int n, st
                 r0 = c.y, r1 = (long long)c.y + 7LL * std::max(c.a, 0);
                 break;
             }
-            case VT_OV_BACKGROUND: r0 = c.y, r1 = (long long)c.y + c.h; break;
+            case VT_OV_BACKGROUND:
+                r0 = c.y, r1 = (long long)c.y + c.h;
+                if (t->fmt == VT_FMT_RGB24 && (long long)c.y + c.h < 0) r0 = 0, r1 = H - 1;  // (y+bh) as usize wraps, src/drawing_rgb.rs:45
+                break;
             case VT_OV_CURSOR: {
                 const long long yc = std::max(0LL, std::min<long long>(c.y, H - 1));  // src/drawing.rs:7 clamps, the RGB path does not
                 r0 = std::min<long long>(c.y, yc) - 26, r1 = std::max<long long>(c.y, yc) + 26;
@@ -944,6 +950,7 @@ vt_status vt_timing_get(vt_tracker* t, vt_timing* o) {
     o->avg_decode_ms = (float)t->r_dec.mean(), o->avg_overlay_ms = (float)t->r_ovl.mean(), o->avg_d2h_ms = (float)t->r_d2h.mean();
     o->avg_total_ms = (float)t->r_tot.mean();
     o->frames = t->frames, o->kernel_launches = t->kernel_launches;
+    o->h2d_bytes = t->h2d_bytes, o->d2h_bytes = t->d2h_bytes;
     return VT_OK;
 }
 vt_status vt_timing_add_interval(vt_tracker* t, uint64_t us) {

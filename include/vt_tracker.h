@@ -190,6 +190,7 @@ typedef struct {
     float avg_h2d_ms, avg_preprocess_ms, avg_vit_ms, avg_decode_ms, avg_overlay_ms, avg_d2h_ms, avg_total_ms;
     uint64_t frames;
     uint64_t kernel_launches;  /* kernels launched by this handle so far (graph nodes count individually) */
+    uint64_t h2d_bytes, d2h_bytes; /* bytes this handle copied host->device / device->host so far */
 } vt_timing;
 vt_status vt_timing_get(vt_tracker* t, vt_timing* out);
 /* ≙ TimingStats::add_interval / add_times for callers that keep the reference's host timers */

@@ -1,0 +1,67 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/vt_tracker.h declares.
+No compute calls: without a GPU the device entry points must fail loudly, never fall back."""
+import ctypes as C
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared_functions():
+    txt = open(os.path.join(ROOT, "include", "vt_tracker.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(vt_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_exports_every_declared_symbol(built):
+    from gstreamer_vit_tracker_b200 import _lib
+
+    L = C.CDLL(_lib.LIB_PATH)
+    names = _declared_functions()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), f"{n} is declared in include/vt_tracker.h but not exported"
+    # and the Python binding table covers the same set
+    assert set(_lib.SYMBOLS) == set(names)
+    assert _lib.lib().vt_abi_version() == 1
+
+
+def test_struct_layouts_match_header(built):
+    from gstreamer_vit_tracker_b200 import _lib
+
+    assert C.sizeof(_lib.vt_bbox) == 16
+    assert C.sizeof(_lib.vt_result) == 32
+    assert C.sizeof(_lib.vt_overlay_cmd) == 24 + 4 + 48
+    cfg = _lib.vt_config()
+    _lib.lib().vt_config_default(C.byref(cfg))
+    assert cfg.struct_size == C.sizeof(_lib.vt_config)
+    assert (cfg.width, cfg.height, cfg.max_targets) == (1920, 1080, 1)
+    assert abs(cfg.overlay_gate - 0.25) < 1e-7 and abs(cfg.score_threshold - 0.20) < 1e-7
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device create() must fail with VT_ERR_CUDA (or VT_ERR_WEIGHTS for a bad path on a GPU box)."""
+    import torch
+
+    from gstreamer_vit_tracker_b200 import _lib
+
+    cfg = _lib.vt_config()
+    _lib.lib().vt_config_default(C.byref(cfg))
+    cfg.weights_path = b"/nonexistent/weights.vtw"
+    h = C.c_void_p()
+    st = _lib.lib().vt_tracker_create(C.byref(cfg), C.byref(h))
+    assert st == (_lib.VT_ERR_WEIGHTS if torch.cuda.is_available() else _lib.VT_ERR_CUDA)
+    assert not h.value
+    assert _lib.lib().vt_last_error()
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under the product package or include/ may import, link or call oracle/."""
+    pkg = os.path.join(ROOT, "gstreamer_vit_tracker_b200")
+    for base, _, files in os.walk(pkg):
+        if "build" in base.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(base, f), errors="replace").read()
+                assert "vt_oracle" not in txt and "vto_" not in txt and "from oracle" not in txt and "import oracle" not in txt, os.path.join(base, f)

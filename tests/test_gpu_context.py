@@ -1,0 +1,163 @@
+"""TrackerContext + probe on the GPU against the oracle's TrackerContext driven by the same commands:
+states, boxes, scores and the overlaid pixels (HUD strings pinned, since they are timing dependent)."""
+import numpy as np
+import pytest
+
+from gstreamer_vit_tracker_b200 import synth, weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(built):
+    from gstreamer_vit_tracker_b200 import api as _api
+    return _api
+
+
+@pytest.fixture(scope="module")
+def oracle(built):
+    from oracle import oracle as _o
+    return _o
+
+
+def _select(ctx_g, ctx_o, api, moves1, moves2):
+    for (c, fast) in moves1:
+        ctx_g.handle_command(c, fast)
+        ctx_o.handle_command({0: "up", 1: "down", 2: "left", 3: "right"}[c], fast)
+
+
+def test_context_flow_nv12(api, oracle, weight_dir):
+    spec = synth.CONFIGS["cfg1"]
+    W, H = spec.width, spec.height
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    g = api.TrackerContext.new(wpath, W, H, fmt="nv12")
+    otrk = oracle.VitTrack(wpath, threads=8)
+    o = oracle.TrackerContext(otrk, W, H)
+    U = api.UserCommand
+    names = {U.MoveUp: "up", U.MoveDown: "down", U.MoveLeft: "left", U.MoveRight: "right", U.Confirm: "confirm", U.Cancel: "cancel"}
+
+    def cmd(c, fast=False):
+        g.handle_command(c, fast)
+        o.handle_command(names[c], fast)
+
+    hud = ("FPS: 60", "conv:0.1ms trk:0.5ms")
+    n = 0
+
+    def frame():
+        nonlocal n
+        fr = st.frame(n)
+        n += 1
+        got = fr.copy()
+        g.probe(got, hud)
+        rgb = oracle.nv12_to_rgb(fr, W, H, 8)
+        bb = o.process_frame(rgb)
+        # oracle-side overlay, reference order (src/pipeline.rs:125-174)
+        ref = fr.copy()
+        name = o.state_name()
+        oracle.draw_background_nv12(ref, W, H, 10, 10, 400, 80, 150)
+        oracle.draw_text_nv12(ref, W, H, name, 15, 15, 2, 255)
+        oracle.draw_text_nv12(ref, W, H, hud[0], 15, 40, 2, 255)
+        oracle.draw_text_nv12(ref, W, H, hud[1], 15, 65, 1, 200)
+        if name == "TRACKING":
+            oracle.draw_text_nv12(ref, W, H, "score: %.0f%%" % (o.current_score * 100.0), 250, 15, 2, 255)
+        sel = o.selection
+        if name.startswith("SELECT"):
+            oracle.draw_cursor_nv12(ref, W, H, sel[0], sel[1])
+            oracle.draw_selection_nv12(ref, W, H, sel[2], sel[3], sel[0], sel[1], sel[4] == 1)
+        box = bb if bb is not None else (o.current_bbox if name == "TRACKING" else None)
+        if box is not None:
+            oracle.draw_rect_nv12(ref, W, H, box[0], box[1], box[2], box[3], 3, 255)
+            oracle.draw_crosshair_nv12(ref, W, H, box[0] + box[2] // 2, box[1] + box[3] // 2, 15, 255)
+        assert g.state_name() == name, n
+        gb = g.current_bbox
+        assert (gb.tuple() if gb else None) == o.current_bbox, n
+        assert abs(g.current_score - o.current_score) <= 1e-3, n
+        assert np.array_equal(got, ref), (n, name, int((got != ref).sum()))
+
+    frame()                                   # SELECT START, cursor in the centre
+    for _ in range(1):
+        cmd(U.MoveLeft, True)
+    for _ in range(2):
+        cmd(U.MoveUp, False)
+    cmd(U.Confirm)
+    frame()                                   # start point set -> SELECT END
+    assert g.state_name() == "SELECT END"
+    for _ in range(2):
+        cmd(U.MoveRight, True)
+    for _ in range(8):
+        cmd(U.MoveDown, False)
+    frame()                                   # dashed selection visible
+    cmd(U.Confirm)
+    frame()                                   # init + update on the same frame -> TRACKING
+    assert g.state_name() == "TRACKING"
+    for _ in range(10):
+        frame()
+    cmd(U.Cancel)
+    frame()
+    assert g.state_name() == "SELECT START" and g.current_bbox is None
+
+
+def test_context_lost_and_auto_reset(api, weight_dir):
+    """Force a loss by moving the search window outside the frame (≙ update Err -> Lost, 61 frames later auto reset)."""
+    spec = synth.StreamSpec("lost", 640, 360, 5, [(280, 150, 80, 60, 2, 1)])
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    g = api.TrackerContext.new(wpath, spec.width, spec.height)
+    U = api.UserCommand
+    g.handle_command(U.Confirm)
+    g.process_frame(st.frame(0))
+    g.handle_command(U.MoveRight, True)
+    g.handle_command(U.MoveDown, True)
+    g.handle_command(U.Confirm)
+    assert g.process_frame(st.frame(1)) is not None and g.state_name() == "TRACKING"
+    g.tracker.set_rect((-5000, -5000, 20, 20))
+    assert g.process_frame(st.frame(2)) is None and g.state_name() == "LOST"
+    for i in range(61):
+        g.process_frame(st.frame(3))
+        assert g.state_name() == "LOST"
+    g.process_frame(st.frame(3))
+    assert g.state_name() == "SELECT START" and g.lost_frames == 61
+
+
+def test_context_flow_rgb24(api, oracle, weight_dir):
+    """The path main() actually runs (src/pipeline_ir.rs): RGB24 640x512, RGB overlay set."""
+    spec = synth.CONFIGS["cfg3"]
+    W, H = spec.width, spec.height
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    g = api.TrackerContext.new(wpath, W, H, fmt="rgb24")
+    otrk = oracle.VitTrack(wpath, threads=8)
+    o = oracle.TrackerContext(otrk, W, H)
+    U = api.UserCommand
+    hud = ("FPS: 60", "trk:0.5ms")
+    seq = [(U.Confirm, "confirm", False), None, (U.MoveRight, "right", True), (U.MoveDown, "down", True), (U.Confirm, "confirm", False), None, None, None, None]
+    n = 0
+    for step in seq:
+        if step is not None:
+            g.handle_command(step[0], step[2])
+            o.handle_command(step[1], step[2])
+            continue
+        fr = st.frame(n).reshape(-1)
+        n += 1
+        got = fr.copy()
+        g.probe(got, hud)
+        bb = o.process_frame(fr.reshape(H, W, 3))
+        ref = fr.copy()
+        name = o.state_name()
+        oracle.draw_text_rgb(ref, W, H, name, 15, 15, 2, 255)
+        oracle.draw_text_rgb(ref, W, H, hud[0], 15, 40, 2, 255)
+        oracle.draw_text_rgb(ref, W, H, hud[1], 15, 65, 1, 200)
+        if name == "TRACKING":
+            oracle.draw_text_rgb(ref, W, H, "score: %.0f%%" % (o.current_score * 100.0), 200, 15, 2, 255)
+        sel = o.selection
+        if name.startswith("SELECT"):
+            oracle.draw_cursor_rgb(ref, W, H, sel[0], sel[1])
+            oracle.draw_selection_rgb(ref, W, H, sel[2], sel[3], sel[0], sel[1], sel[4] == 1)
+        box = bb if bb is not None else (o.current_bbox if name == "TRACKING" else None)
+        if box is not None:
+            oracle.draw_rect_rgb(ref, W, H, box[0], box[1], box[2], box[3], 3, (0, 255, 0))
+            oracle.draw_crosshair_rgb(ref, W, H, box[0] + box[2] // 2, box[1] + box[3] // 2, 15, (0, 255, 0))
+        assert g.state_name() == name
+        assert np.array_equal(got, ref), (n, name, int((got != ref).sum()))
+    assert g.state_name() == "TRACKING"

@@ -1,0 +1,376 @@
+"""GPU parity of the tracker path (crop/convert/resize/normalise -> ViT -> decode) through the C ABI
+against the CPU oracle and the cv2.TrackerVit fixtures.
+
+Tolerances (BASELINE.json north_star): NV12 conversion and the u8 preprocessing bit-exact; score within
+1e-3 absolute; boxes IoU >= 0.99.  Boxes are floor()s of fp32 expressions scaled by the crop size, so a
+relative error e in the size/offset maps moves a pre-floor coordinate by ~e*crop px: frames whose oracle
+pre-floor value lies within BOUNDARY_PX of an integer may legitimately differ by one pixel and are counted
+separately (reported, bounded), everything else must match exactly."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from gstreamer_vit_tracker_b200 import synth, weights
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-3
+IOU_MIN = 0.99
+TIE_MARGIN = 2e-3     # hann-weighted top-1/top-2 margin under which the argmax is numerically undecidable
+BOUNDARY_PX = 0.02    # distance of a pre-floor coordinate from an integer under which +-1 px is accepted
+
+
+@pytest.fixture(scope="module")
+def api(built):
+    from gstreamer_vit_tracker_b200 import api as _api
+    return _api
+
+
+@pytest.fixture(scope="module")
+def oracle(built):
+    from oracle import oracle as _o
+    return _o
+
+
+def iou(a, b):
+    ax, ay, aw, ah = a
+    bx, by, bw, bh = b
+    ix = max(0, min(ax + aw, bx + bw) - max(ax, bx))
+    iy = max(0, min(ay + ah, by + bh) - max(ay, by))
+    inter = ix * iy
+    union = aw * ah + bw * bh - inter
+    return inter / union if union > 0 else 1.0
+
+
+def oracle_prefloor(ref, rect_before):
+    """Pre-floor bbox coordinates of the oracle's last update (fp32 arithmetic as in App. A.6)."""
+    cw, sm, om, _ = ref.last_maps()
+    best = int(np.argmax(cw))
+    my, mx = divmod(best, 16)
+    f = np.float32
+    cx = (f(mx) + om[best]) / f(16)
+    cy = (f(my) + om[256 + best]) / f(16)
+    bw, bh = sm[best], sm[256 + best]
+    x, y, w, h = rect_before
+    c = int(np.ceil(np.sqrt(float(w * h)) * 4))
+    x0, y0 = x + int((w - c) / 2), y + int((h - c) / 2)
+    vals = [(cx - bw / f(2)) * f(c) + f(x0), (cy - bh / f(2)) * f(c) + f(y0), bw * f(c), bh * f(c)]
+    srt = np.sort(cw)[::-1]
+    return [float(v) for v in vals], float(srt[0] - srt[1])
+
+
+def compare_step(r, ok, score, bb, prefloor, margin, stats, where):
+    """One teacher-forced step: GPU result r vs oracle (ok, score, bb)."""
+    assert abs(r.score - score) <= SCORE_TOL or margin < TIE_MARGIN, (where, r.score, score)
+    stats["max_dscore"] = max(stats["max_dscore"], abs(r.score - score) if margin >= TIE_MARGIN else 0.0)
+    if margin < TIE_MARGIN:
+        stats["ties"] += 1
+        return
+    assert r.success == ok, where
+    if not ok:
+        return
+    if tuple(r.bbox) == tuple(bb):
+        stats["exact"] += 1
+        return
+    near = [abs(v - round(v)) < BOUNDARY_PX for v in prefloor]
+    diff = [abs(a - b) for a, b in zip(r.bbox, bb)]
+    assert all(d <= 1 for d in diff) and all(n for d, n in zip(diff, near) if d), (where, r.bbox, bb, prefloor)
+    stats["boundary"] += 1
+    stats["min_iou_boundary"] = min(stats["min_iou_boundary"], iou(r.bbox, bb))
+
+
+def new_stats():
+    return {"exact": 0, "boundary": 0, "ties": 0, "max_dscore": 0.0, "min_iou_boundary": 1.0}
+
+
+# ---- preprocessing: bit-exact ----------------------------------------------------------------------
+@pytest.mark.parametrize("fmt", ["nv12", "rgb24"])
+def test_search_and_template_blobs_bit_exact(api, oracle, weight_dir, fmt):
+    """K2 (fused crop + NV12->RGB + OpenCV bilinear + normalise) == oracle crop/resize/norm on the converted frame,
+    for boxes inside, hanging over each edge, tiny (up-scale) and huge."""
+    W, H = 1280, 720
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    spec = synth.StreamSpec("pp", W, H, 41, [(500, 300, 120, 90, 3, 2)], fmt=fmt)
+    st = synth.SyntheticStream(spec)
+    frame = st.frame(3)
+    rgb = frame if fmt == "rgb24" else oracle.nv12_to_rgb(frame, W, H, 8)
+    trk = api.VitTrack.new(wpath, W, H, fmt=fmt)
+    ref = oracle.VitTrack(wpath, threads=4)
+    boxes = [(500, 300, 120, 90), (0, 0, 60, 40), (-30, -20, 100, 80), (1200, 650, 120, 90), (640, -40, 90, 100), (-50, 400, 150, 60),
+             (600, 700, 40, 40), (100, 100, 21, 23), (300, 200, 10, 12), (200, 100, 400, 300), (0, 0, 1280, 720), (639, 359, 2, 2),
+             (700, 300, 64, 64), (700, 300, 63, 65), (50, 60, 33, 31)]
+    for box in boxes:
+        flat = np.ascontiguousarray(frame).reshape(-1)
+        trk.init(flat, api.BBox(*box))
+        ref.init(rgb, box)
+        trk.update_all(flat)
+        ref.rect = box
+        rc = ref.update(rgb)[0]
+        assert rc == 0
+        sb, tb = ref.last_blobs()
+        d = trk.debug_read(0)
+        assert np.array_equal(d["template_blob"], tb), ("template", box, int((d["template_blob"] != tb).sum()))
+        assert np.array_equal(d["search_blob"], sb), ("search", box, int((d["search_blob"] != sb).sum()))
+
+
+def test_short_nv12_frame_is_black(api, oracle, weight_dir):
+    """A too-short NV12 buffer is an all-zero image to the tracker (src/nv12_convert.rs:48-50)."""
+    W, H = 640, 360
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    trk = api.VitTrack.new(wpath, W, H)
+    ref = oracle.VitTrack(wpath, threads=2)
+    short = np.full(W * H * 3 // 2 - 7, 180, np.uint8)
+    black = np.zeros((H, W, 3), np.uint8)
+    trk.init(short, api.BBox(300, 150, 60, 50))
+    ref.init(black, (300, 150, 60, 50))
+    r = trk.update(short)
+    rc, ok, score, bb = ref.update(black)
+    assert abs(r.score - score) <= SCORE_TOL and r.success == ok and (not ok or tuple(r.bbox) == tuple(bb))
+
+
+# ---- network: layer-wise ------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", ["nano", "tiny"])
+def test_layerwise_tokens(api, oracle, weight_dir, model):
+    """Token features after the embeddings and after every block vs the fp32 oracle (relative 2e-4 of the layer's scale)."""
+    W, H = 1280, 720
+    wpath = weights.ensure_weight_file(model, weight_dir, variant="wild")
+    st = synth.SyntheticStream(synth.CONFIGS["cfg1"])
+    frame = st.frame(0)
+    rgb = oracle.nv12_to_rgb(frame, W, H, 8)
+    box = st.target_boxes(0)[0]
+    trk = api.VitTrack.new(wpath, W, H, debug_capture=True)
+    ref = oracle.VitTrack(wpath, threads=8)
+    trk.init(frame, api.BBox(*box))
+    ref.init(rgb, box)
+    trk.update_all(frame)
+    assert ref.update(rgb)[0] == 0
+    depth = trk.model_dim(1)
+    for which in range(depth + 1):
+        a, b = trk.debug_tokens(which), ref.debug_tokens(which)
+        scale = float(np.abs(b).max())
+        err = float(np.abs(a - b).max())
+        assert err <= 2e-4 * scale, (model, which, err, scale)
+    fin = trk.debug_read(0)["tokens"][64:]
+    b = ref.debug_tokens(depth + 1)[64:]
+    assert float(np.abs(fin - b).max()) <= 2e-4 * float(np.abs(b).max())
+    cw, sm, om, _ = ref.last_maps()
+    d = trk.debug_read(0)
+    assert float(np.abs(d["conf_win"] - cw).max()) <= SCORE_TOL
+    assert float(np.abs(d["size_map"] - sm).max()) <= 1e-4
+    assert float(np.abs(d["off_map"] - om).max()) <= 1e-3
+
+
+# ---- against the third-party cv2.TrackerVit fixtures -----------------------------------------------------
+@pytest.mark.parametrize("variant", ["stable", "wild"])
+def test_sequences_vs_cv2_golden(api, weight_dir, variant):
+    g = golden("trackervit_nano.json")["models"][variant]
+    wpath = weights.ensure_weight_file("nano", weight_dir, variant=variant)
+    assert hashlib.sha256(open(wpath, "rb").read()).hexdigest() == g["weights_sha256"]
+    for seq in g["sequences"]:
+        sp = seq["spec"]
+        spec = synth.StreamSpec(seq["name"], sp["w"], sp["h"], sp["seed"], [tuple(t) for t in sp["targets"]])
+        st = synth.SyntheticStream(spec)
+        trk = api.VitTrack.new(wpath, spec.width, spec.height)
+        trk.init(st.frame(0), api.BBox(*seq["init_box"]))
+        n_exact = 0
+        for i, fr in enumerate(seq["frames"]):
+            r = trk.update(st.frame(i))
+            assert abs(r.score - fr["score"]) <= SCORE_TOL, (seq["name"], i, r.score, fr["score"])
+            assert r.success == fr["ok"]
+            if fr["ok"]:
+                if list(r.bbox) == fr["bbox"]:
+                    n_exact += 1
+                else:  # resynchronise on cv2's box so that one boundary flip cannot cascade
+                    assert iou(r.bbox, fr["bbox"]) >= 0.95 and max(abs(a - b) for a, b in zip(r.bbox, fr["bbox"])) <= 1, (seq["name"], i, r.bbox, fr["bbox"])
+                    trk.set_rect(fr["bbox"])
+        assert n_exact >= len(seq["frames"]) - 2, (seq["name"], n_exact)
+
+
+@pytest.mark.parametrize("variant", ["stable", "wild"])
+def test_single_steps_vs_cv2_golden(api, weight_dir, variant):
+    g = golden("trackervit_nano.json")["models"][variant]
+    wpath = weights.ensure_weight_file("nano", weight_dir, variant=variant)
+    sp = g["steps_spec"]
+    spec = synth.StreamSpec("steps", sp["w"], sp["h"], sp["seed"], [tuple(t) for t in sp["targets"]])
+    st = synth.SyntheticStream(spec)
+    f0, f1 = st.frame(sp["frames"][0]), st.frame(sp["frames"][1])
+    trk = api.VitTrack.new(wpath, spec.width, spec.height)
+    n_exact = n = 0
+    for s in g["single_steps"]:
+        if s.get("error"):
+            with pytest.raises(api.VtError) as e:
+                trk.init(f0, api.BBox(*s["box"]))
+                trk.update(f1)
+            assert e.value.status == -4  # VT_ERR_CROP_OUTSIDE ≙ Err
+            continue
+        trk.init(f0, api.BBox(*s["box"]))
+        r = trk.update(f1)
+        assert abs(r.score - s["score"]) <= SCORE_TOL, (s, r.score)
+        assert r.success == s["ok"]
+        n += 1
+        if s["ok"]:
+            d = max(abs(a - b) for a, b in zip(r.bbox, s["bbox"]))
+            assert d <= 1, (s, r.bbox)
+            n_exact += d == 0
+    assert n_exact >= n - 2, (n_exact, n)
+
+
+# ---- teacher-forced long sequences vs the oracle ------------------------------------------------------------
+@pytest.mark.parametrize("model,cfg,frames", [("nano", "cfg1", 120), ("tiny", "cfg2", 60)])
+def test_teacher_forced_sequence(api, oracle, weight_dir, model, cfg, frames):
+    spec = synth.CONFIGS[cfg]
+    W, H = spec.width, spec.height
+    wpath = weights.ensure_weight_file(model, weight_dir)
+    st = synth.SyntheticStream(spec)
+    trk = api.VitTrack.new(wpath, W, H)
+    ref = oracle.VitTrack(wpath, threads=8)
+    f0 = st.frame(0)
+    box = st.target_boxes(0)[0]
+    trk.init(f0, api.BBox(*box))
+    ref.init(oracle.nv12_to_rgb(f0, W, H, 8), box)
+    stats = new_stats()
+    for n in range(frames):
+        fr = st.frame(n)
+        before = ref.rect
+        trk.set_rect(before)
+        r = trk.update(fr)
+        rc, ok, score, bb = ref.update(oracle.nv12_to_rgb(fr, W, H, 8))
+        assert rc == 0
+        pre, margin = oracle_prefloor(ref, before)
+        compare_step(r, ok, score, bb, pre, margin, stats, (model, cfg, n))
+    print(f"\n[parity {model}/{cfg}] {frames} frames: exact {stats['exact']}, boundary(+-1px) {stats['boundary']}, ties {stats['ties']}, "
+          f"max|dscore| {stats['max_dscore']:.2e}, min IoU on boundary frames {stats['min_iou_boundary']:.4f}")
+    assert stats["exact"] >= 0.9 * frames
+    assert stats["max_dscore"] <= SCORE_TOL
+
+
+def test_free_running_sequence_iou(api, oracle, weight_dir):
+    """No teacher forcing: both trackers run free for 60 frames; IoU >= 0.99 on every frame up to the first
+    numerically undecidable frame (tie / floor boundary), which must not come early."""
+    spec = synth.CONFIGS["cfg1"]
+    W, H = spec.width, spec.height
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    st = synth.SyntheticStream(spec)
+    trk = api.VitTrack.new(wpath, W, H)
+    ref = oracle.VitTrack(wpath, threads=8)
+    box = st.target_boxes(0)[0]
+    trk.init(st.frame(0), api.BBox(*box))
+    ref.init(oracle.nv12_to_rgb(st.frame(0), W, H, 8), box)
+    agreed = 0
+    for n in range(60):
+        fr = st.frame(n)
+        before = ref.rect
+        r = trk.update(fr)
+        rc, ok, score, bb = ref.update(oracle.nv12_to_rgb(fr, W, H, 8))
+        pre, margin = oracle_prefloor(ref, before)
+        if tuple(r.bbox) != tuple(bb):
+            assert margin < TIE_MARGIN or any(abs(v - round(v)) < BOUNDARY_PX for v in pre), (n, r.bbox, bb, pre, margin)
+            break
+        assert iou(r.bbox, bb) >= IOU_MIN and abs(r.score - score) <= SCORE_TOL
+        agreed += 1
+    assert agreed >= 30, agreed
+
+
+# ---- multi-target, formats, errors -----------------------------------------------------------------------------
+def test_multi_target_equals_independent_singles(api, weight_dir):
+    """16 targets batched through one forward (cfg4 geometry at 1/2 scale for speed) == 16 single-target trackers, bit for bit."""
+    spec = synth.StreamSpec("mt", 1920, 1080, 1004, [(190 + (i % 4) * 450, 110 + (i // 4) * 250, 100, 75, 3 + i % 4, 2 + i // 4) for i in range(16)])
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir, variant="wild")
+    multi = api.VitTrack.new(wpath, spec.width, spec.height, max_targets=16)
+    singles = [api.VitTrack.new(wpath, spec.width, spec.height) for _ in range(16)]
+    f0 = st.frame(0)
+    for i, b in enumerate(st.target_boxes(0)):
+        multi.init(f0, api.BBox(*b), target=i)
+        singles[i].init(f0, api.BBox(*b))
+    for n in range(5):
+        fr = st.frame(n)
+        rs = multi.update_all(fr)
+        for i in range(16):
+            r1 = singles[i].update(fr)
+            assert rs[i].status == 0 and rs[i].success == r1.success and rs[i].bbox == r1.bbox and rs[i].score == r1.score, (n, i, rs[i], r1)
+    # dropping a target leaves the others untouched; un-initialised slots report VT_ERR_NOT_INIT
+    multi.drop(3)
+    rs = multi.update_all(st.frame(5))
+    assert rs[3].status == -5
+    assert rs[4].bbox == singles[4].update(st.frame(5)).bbox
+
+
+def test_graph_and_eager_paths_agree(api, weight_dir):
+    spec = synth.CONFIGS["cfg1"]
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    a = api.VitTrack.new(wpath, spec.width, spec.height, use_cuda_graph=True)
+    b = api.VitTrack.new(wpath, spec.width, spec.height, use_cuda_graph=False)
+    box = api.BBox(*st.target_boxes(0)[0])
+    a.init(st.frame(0), box)
+    b.init(st.frame(0), box)
+    for n in range(8):
+        ra, rb = a.update(st.frame(n)), b.update(st.frame(n))
+        assert ra == rb, (n, ra, rb)
+    assert a.timing().kernel_launches == b.timing().kernel_launches > 0
+
+
+def test_submit_wait_and_device_resident_frame(api, weight_dir):
+    import torch
+
+    spec = synth.CONFIGS["cfg1"]
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    a = api.VitTrack.new(wpath, spec.width, spec.height)
+    b = api.VitTrack.new(wpath, spec.width, spec.height)
+    c = api.VitTrack.new(wpath, spec.width, spec.height)
+    box = api.BBox(*st.target_boxes(0)[0])
+    for t in (a, b, c):
+        t.init(st.frame(0), box)
+    pin = api.PinnedBuffer(st.frame_bytes())
+    for n in range(6):
+        fr = st.frame(n)
+        ra = a.update(fr)
+        pin.array[:] = fr
+        b.submit(pin.array)
+        rb = b.wait()[0]
+        d = torch.from_numpy(fr).cuda()
+        torch.cuda.synchronize()
+        rc = c.update_device(d.data_ptr(), fr.size)[0]
+        assert ra == rb == rc, (n, ra, rb, rc)
+
+
+def test_error_paths(api, weight_dir):
+    spec = synth.CONFIGS["cfg1"]
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    with pytest.raises(api.VtError) as e:
+        api.VitTrack.new("/nonexistent/model.vtw", 640, 480)
+    assert e.value.status == -3  # ≙ VitTrack::new Err -> TrackerContext::new fails (src/tracker_context.rs:21)
+    trk = api.VitTrack.new(wpath, spec.width, spec.height)
+    r = trk.update_all(st.frame(0))[0]
+    assert r.status == -5 and not r.success  # update before init
+    with pytest.raises(api.VtError) as e:
+        trk.init(st.frame(0), api.BBox(5000, 5000, 40, 40))
+    assert e.value.status == -4
+    trk.init(st.frame(0), api.BBox(600, 300, 100, 80))
+    trk.set_rect((-900, -900, 30, 30))  # search window now entirely outside
+    r = trk.update_all(st.frame(1))[0]
+    assert r.status == -4 and not r.success
+
+
+def test_box_overlay_fused_path(api, oracle, weight_dir):
+    """cfg.box_overlay: update() draws rect + crosshair of the gated result on the device and returns the touched rows."""
+    spec = synth.CONFIGS["cfg1"]
+    W, H = spec.width, spec.height
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    trk = api.VitTrack.new(wpath, W, H, box_overlay=True)
+    trk.init(st.frame(0), api.BBox(*st.target_boxes(0)[0]))
+    for n in range(4):
+        fr = st.frame(n)
+        ref = fr.copy()
+        r = trk.update(fr)
+        if r.success and r.score > 0.25:
+            x, y, w, h = r.bbox
+            oracle.draw_rect_nv12(ref, W, H, x, y, w, h, 3, 255)
+            oracle.draw_crosshair_nv12(ref, W, H, x + w // 2, y + h // 2, 15, 255)
+        assert np.array_equal(fr, ref), (n, int((fr != ref).sum()))

@@ -1,0 +1,91 @@
+"""TrackerContext / SelectionState / TimingStats: the C oracle AND the product's host logic (C++ inside
+libvittrack_b200.so, no GPU needed) against traces of a pure-Python reading of the reference
+(src/tracker_context.rs, src/selection_state.rs, src/timing_stats.rs)."""
+import pytest
+
+from conftest import golden
+from oracle import oracle
+
+CMD_NAMES = {"up": 0, "down": 1, "left": 2, "right": 3, "confirm": 4, "cancel": 5, "quit": 6}
+
+
+def _check(step_no, rec, returned, state, score, bbox, sel, lost):
+    where = f"step {step_no}: {rec['step']}"
+    assert state == rec["state"], where
+    assert (list(returned) if returned is not None else None) == rec["returned"], where
+    assert abs(score - rec["score"]) < 1e-7, where
+    assert (list(bbox) if bbox is not None else None) == rec["bbox"], where
+    assert list(sel[:5]) == rec["selection"], where
+    assert lost == rec["lost"], where
+
+
+def test_oracle_state_machine_trace():
+    g = golden("state_traces.json")
+    ctx = oracle.TrackerContext(None, g["w"], g["h"])
+    for i, rec in enumerate(g["trace"]):
+        kind, a, b = rec["step"]
+        ret = None
+        if kind == "cmd":
+            ctx.handle_command(a, bool(b))
+        elif isinstance(a, str):
+            ret = ctx.process_frame(None, scripted=(False, 0.0, (0, 0, 0, 0)), scripted_err=True)
+        else:
+            ret = ctx.process_frame(None, scripted=(a[0], a[1], tuple(a[2])))
+        _check(i, rec, ret, ctx.state_name(), ctx.current_score, ctx.current_bbox, ctx.selection, ctx.lost_frames)
+
+
+def test_product_state_machine_trace(built):
+    from gstreamer_vit_tracker_b200 import api
+
+    g = golden("state_traces.json")
+    ctx = api.TrackerContext.scripted(g["w"], g["h"])
+    for i, rec in enumerate(g["trace"]):
+        kind, a, b = rec["step"]
+        ret = None
+        if kind == "cmd":
+            ctx.handle_command(CMD_NAMES[a], bool(b))
+        elif isinstance(a, str):
+            ret = ctx.process_scripted(None, err=True)
+        else:
+            ret = ctx.process_scripted(api.TrackResult(a[0], a[1], tuple(a[2])))
+        s = ctx.selection
+        sel = (s.cursor_x, s.cursor_y, s.start_x, s.start_y, s.phase)
+        bb = ctx.current_bbox
+        _check(i, rec, ret.tuple() if ret else None, ctx.state_name(), ctx.current_score, bb.tuple() if bb else None, sel, ctx.lost_frames)
+        assert (s.step, s.fast_step) == (10, 50)
+
+
+def test_selection_bbox_min_side(built):
+    """get_bbox(): min side 20 (src/selection_state.rs:39-45)."""
+    from gstreamer_vit_tracker_b200 import api
+
+    for rec in golden("state_traces.json")["trace"]:
+        cx, cy, sx, sy, _ = rec["selection"]
+        assert rec["sel_bbox"] == [min(sx, cx), min(sy, cy), max(abs(sx - cx), 20), max(abs(sy - cy), 20)]
+    ctx = api.TrackerContext.scripted(100, 80)
+    for _ in range(30):
+        ctx.handle_command(api.UserCommand.MoveRight, True)
+        ctx.handle_command(api.UserCommand.MoveDown, True)
+    assert (ctx.selection.cursor_x, ctx.selection.cursor_y) == (99, 79)  # clamp to w-1 / h-1
+
+
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+def test_timing_stats(impl, built):
+    g = golden("state_traces.json")["timing"]
+    if impl == "oracle":
+        make = oracle.TimingStats
+    else:
+        from gstreamer_vit_tracker_b200 import api
+
+        make = api.TimingStats.new
+    for chk in g["checks"]:
+        t = make()
+        for i in range(chk["n"]):
+            t.add_interval(g["intervals"][i])
+            t.add_times(g["conv"][i], g["track"][i])
+        assert t.fps() == pytest.approx(chk["fps"], rel=1e-12)
+        assert t.avg_conv_ms() == pytest.approx(chk["conv_ms"], rel=1e-12)
+        assert t.avg_track_ms() == pytest.approx(chk["track_ms"], rel=1e-12)
+    t = make()
+    t.add_interval(0)
+    assert t.fps() == 0.0  # avg == 0 -> 0.0 (src/timing_stats.rs:41-45)
