@@ -186,12 +186,15 @@ static GemmArgs gemm_args(const float* A, int64_t lda, const float* W, const flo
     } while (0)
 
 // Enqueues crop -> ViT -> decode (-> box overlay) for the n active targets on t->stream.
-static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool record_events) {
+static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool record_events, bool capturing) {
     const int D = t->D, Hd = t->hidden, C = t->head_ch;
+    // inside a stream capture a plain cudaEventRecord only expresses a dependency; the External flag makes a real
+    // event-record node so that the stage times can be read after every replay
+    const unsigned ev_flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
     cudaStream_t s = t->stream;
     FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid};
     VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, n, 4, kSearch, t->d_lut, t->patches_x, (size_t)kNTx * kPatchK, nullptr, s));
-    if (record_events) VT_CUDA(cudaEventRecord(t->ev[EV_PRE], s));
+    if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_PRE], s, ev_flags));
     {
         dim3 grid((kNTz * D + 255) / 256, n);
         gather_template_kernel<<<grid, 256, 0, s>>>(t->X, t->Zemb, t->d_slots, D);
@@ -238,12 +241,12 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
         g.a_rows_in = kNTx, g.a_rows_stride = kNTx, g.a_row_off = 0;
         VT_LAUNCH(launch_gemm_simt(g, s));
     }
-    if (record_events) VT_CUDA(cudaEventRecord(t->ev[EV_VIT], s));
+    if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_VIT], s, ev_flags));
     VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, s));
-    if (record_events) VT_CUDA(cudaEventRecord(t->ev[EV_DEC], s));
+    if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_DEC], s, ev_flags));
     if (t->cfg.box_overlay)
         VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, t->fmt, t->d_res, t->d_slots, n, t->cfg.overlay_gate, s));
-    if (record_events) VT_CUDA(cudaEventRecord(t->ev[EV_OVL], s));
+    if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_OVL], s, ev_flags));
     return VT_OK;
 }
 
@@ -258,7 +261,7 @@ static vt_status run_forward(vt_tracker* t) {
     }
     int launches = 0;
     if (!t->cfg.use_cuda_graph || t->debug_capture) {
-        vt_status st = enqueue_forward(t, n, launches, true);
+        vt_status st = enqueue_forward(t, n, launches, true, false);
         t->kernel_launches += launches;
         t->kernels_per_frame = launches;
         return st;
@@ -267,7 +270,7 @@ static vt_status run_forward(vt_tracker* t) {
     if (it == t->graphs.end()) {
         cudaGraph_t graph = nullptr;
         VT_CUDA(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
-        vt_status st = enqueue_forward(t, n, launches, true);
+        vt_status st = enqueue_forward(t, n, launches, true, true);
         cudaError_t e = cudaStreamEndCapture(t->stream, &graph);
         if (st != VT_OK) {
             if (graph) cudaGraphDestroy(graph);
@@ -338,8 +341,10 @@ static bool rect_rows(int fmt, long long H, int y, int h, int th, long long& r0,
         const long long t = std::max(th, 1);
         r0 = std::min(y1, std::max(0LL, y2 - t + 1));
         r1 = std::max(y2, std::min(y1 + t - 1, H - 1));
-    } else {
-        r0 = y, r1 = (long long)y + h - 1;
+    } else {  // rows y+t, y+rh-1-t (t < thickness) and y..y+rh-1, each bounds-checked per pixel
+        const long long t = std::max(th, 1);
+        r0 = std::min<long long>(y, (long long)y + h - t), r1 = std::max<long long>((long long)y + h - 1, (long long)y + t - 1);
+        if (r1 < 0 || r0 > H - 1) return false;
     }
     r0 = std::max(0LL, std::min(r0, H - 1)), r1 = std::max(0LL, std::min(r1, H - 1));
     return r1 >= r0;
