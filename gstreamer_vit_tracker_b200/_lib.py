@@ -87,6 +87,8 @@ SYMBOLS = {
     "vt_tracker_debug_tokens": (C.c_int32, [_vp, C.c_int32, C.c_int32, _f32p]),
     "vt_tracker_stream": (_vp, [_vp]),
     "vt_tracker_sync": (C.c_int32, [_vp]),
+    "vt_debug_gemm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, _f32p,
+                                  C.POINTER(C.c_int32)]),
     "vt_convert_nv12_rgb": (C.c_int32, [_vp, _vp, C.c_size_t, _vp]),
     "vt_convert_nv12_rgb_device": (C.c_int32, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.c_int32]),
     "vt_overlay": (C.c_int32, [_vp, _vp, C.c_size_t, C.POINTER(vt_overlay_cmd), C.c_int32]),

@@ -228,6 +228,21 @@ class VitTrack:
         check(fn(self._h, _ptr(frame), frame.size, arr, len(cmds)), "vt_overlay")
 
 
+def debug_gemm(A: np.ndarray, W: np.ndarray, bias: Optional[np.ndarray] = None, nsplit: int = 3, gelu: bool = False, device: int = 0):
+    """C = A @ W.T (+bias) through the tcgen05 GEMM kernel; returns (C, err_flag)."""
+    A = np.ascontiguousarray(A, np.float32)
+    W = np.ascontiguousarray(W, np.float32)
+    M, K = A.shape
+    N = W.shape[0]
+    out = np.empty((M, N), np.float32)
+    err = C.c_int32(0)
+    f = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    b = np.ascontiguousarray(bias, np.float32) if bias is not None else None
+    check(lib().vt_debug_gemm(device, M, N, K, f(A), f(W), f(b) if b is not None else None, nsplit, int(gelu), f(out), C.byref(err)),
+          "vt_debug_gemm")
+    return out, err.value
+
+
 def overlay_cmd(kind: int, x=0, y=0, w=0, h=0, a=0, r=255, g=0, b=0, text: str = "", strict: bool = False) -> vt_overlay_cmd:
     c = vt_overlay_cmd()
     c.kind, c.x, c.y, c.w, c.h, c.a, c.r, c.g, c.b, c.strict_glyphs = kind, x, y, w, h, a, r, g, b, int(strict)

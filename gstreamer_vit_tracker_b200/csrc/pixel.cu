@@ -192,7 +192,8 @@ __device__ __forceinline__ void frame_rgb(const FrameDesc& f, int fx, int fy, in
 __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, TargetState* __restrict__ state,
                                                                const int32_t* __restrict__ slots, int factor, int S,
                                                                const float* __restrict__ lut, float* __restrict__ patches,
-                                                               size_t patches_stride) {
+                                                               size_t patches_stride, __nv_bfloat16* __restrict__ p_hi,
+                                                               __nv_bfloat16* __restrict__ p_lo) {
     const int bi = blockIdx.y;
     const int slot = slots[bi];
     TargetState* st = state + slot;
@@ -222,21 +223,28 @@ __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, Targ
     frame_rgb(f, x1 + cx1, y1 + cy1, p11[0], p11[1], p11[2]);
     const int nt = S >> 4;
     const int token = (dy >> 4) * nt + (dx >> 4);
-    float* dst = patches + (size_t)bi * patches_stride + (size_t)token * kPatchK + (dy & 15) * 16 + (dx & 15);
+    const size_t off = (size_t)bi * patches_stride + (size_t)token * kPatchK + (dy & 15) * 16 + (dx & 15);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const int t0 = p00[ch] * tx.a0 + p01[ch] * tx.a1;
         const int t1 = p10[ch] * tx.a0 + p11[ch] * tx.a1;
         const int v = (((ty.a0 * (t0 >> 4)) >> 16) + ((ty.a1 * (t1 >> 4)) >> 16) + 2) >> 2;
-        dst[ch * 256] = lut[ch * 256 + (v & 255)];
+        const float val = lut[ch * 256 + (v & 255)];
+        patches[off + ch * 256] = val;
+        if (p_hi) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(val);
+            p_hi[off + ch * 256] = h;
+            p_lo[off + ch * 256] = __float2bfloat16_rn(val - __bfloat162float(h));
+        }
     }
 }
 
 cudaError_t launch_crop_resize_norm(FrameDesc f, TargetState* d_state, const int32_t* d_slots, int n, int factor, int out_size,
-                                    const float* d_norm_lut, float* d_patches, size_t patches_stride, const int32_t*, cudaStream_t s) {
+                                    const float* d_norm_lut, float* d_patches, size_t patches_stride, __nv_bfloat16* p_hi,
+                                    __nv_bfloat16* p_lo, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     dim3 grid((out_size * out_size + 255) / 256, n);
-    crop_resize_norm_kernel<<<grid, 256, 0, s>>>(f, d_state, d_slots, factor, out_size, d_norm_lut, d_patches, patches_stride);
+    crop_resize_norm_kernel<<<grid, 256, 0, s>>>(f, d_state, d_slots, factor, out_size, d_norm_lut, d_patches, patches_stride, p_hi, p_lo);
     return cudaGetLastError();
 }
 

@@ -52,6 +52,7 @@ struct vt_tracker {
 
     // weights (one device allocation)
     float* d_weights = nullptr;
+    size_t n_weights = 0;
     const float *patch_w, *patch_b, *pos_z, *pos_x, *lnf_g, *lnf_b, *h1_w, *h1_b, *h2_w, *h2_b;
     std::vector<BlockW> blk;
     float *d_lut = nullptr, *d_hann = nullptr;
@@ -75,6 +76,18 @@ struct vt_tracker {
     float *patches_x = nullptr, *patches_z = nullptr, *Zemb = nullptr, *X = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr,
           *Yf = nullptr, *H1 = nullptr, *d_dbg = nullptr;
     int debug_capture = 0;
+
+    // tensor-core mode (gemm_mode != VT_GEMM_FP32_SIMT): bf16 (hi, lo) copies of the weights and of every GEMM A operand
+    int nsplit = 0;  // 0 = fp32 SIMT, 1 = bf16, 3 = bf16x3
+    __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
+    __nv_bfloat16 *px_hi = nullptr, *px_lo = nullptr, *pz_hi = nullptr, *pz_lo = nullptr, *ln_hi = nullptr, *ln_lo = nullptr, *att_hi = nullptr,
+                  *att_lo = nullptr, *hid_hi = nullptr, *hid_lo = nullptr, *yf_hi = nullptr, *yf_lo = nullptr;
+    int* d_tc_err = nullptr;
+    TcGemmPlan plan_patch_x, plan_patch_z, plan_head;
+    struct BlockPlans {
+        TcGemmPlan qkv, proj, fc1, fc2;
+    };
+    std::vector<BlockPlans> plans;
 
     std::map<int, cudaGraphExec_t> graphs;
     int kernels_per_frame = 0;
@@ -140,6 +153,7 @@ static vt_status load_weights(vt_tracker* t, const char* path) {
                 for (size_t tap = 0; tap < 9; ++tap) re[(c * 9 + tap) * D + d] = host[h1_off + (c * D + d) * 9 + tap];
         std::copy(re.begin(), re.end(), host.begin() + h1_off);
     }
+    t->n_weights = n;
     VT_CUDA(cudaMalloc(&t->d_weights, n * sizeof(float)));
     VT_CUDA(cudaMemcpy(t->d_weights, host.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     const float* p = t->d_weights;
@@ -193,53 +207,78 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     const unsigned ev_flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
     cudaStream_t s = t->stream;
     FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid};
-    VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, n, 4, kSearch, t->d_lut, t->patches_x, (size_t)kNTx * kPatchK, nullptr, s));
+    VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, n, 4, kSearch, t->d_lut, t->patches_x, (size_t)kNTx * kPatchK, t->px_hi,
+                                      t->px_lo, s));
     if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_PRE], s, ev_flags));
     {
         dim3 grid((kNTz * D + 255) / 256, n);
         gather_template_kernel<<<grid, 256, 0, s>>>(t->X, t->Zemb, t->d_slots, D);
         VT_LAUNCH(cudaGetLastError());
     }
-    {
-        GemmArgs g = gemm_args(t->patches_x, kPatchK, t->patch_w, t->patch_b, t->X, D, n * kNTx, D, kPatchK);
-        g.pos = t->pos_x;
-        g.c_rows_in = kNTx, g.c_rows_stride = kNTok, g.c_row_off = kNTz;
-        VT_LAUNCH(launch_gemm_simt(g, s));
-    }
     const int M = n * kNTok;
-    if (t->debug_capture) VT_CUDA(cudaMemcpyAsync(t->d_dbg, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
-    for (int l = 0; l < t->depth; ++l) {
-        const BlockW& b = t->blk[l];
+    if (t->nsplit == 0) {
+        // ---------------- fp32 CUDA-core path ----------------
         {
-            GemmArgs g = gemm_args(t->X, D, b.qkv_w, b.qkv_b, t->QKV, 3 * D, M, 3 * D, D);
-            g.ln_g = b.ln1_g, g.ln_b = b.ln1_b;
+            GemmArgs g = gemm_args(t->patches_x, kPatchK, t->patch_w, t->patch_b, t->X, D, n * kNTx, D, kPatchK);
+            g.pos = t->pos_x;
+            g.c_rows_in = kNTx, g.c_rows_stride = kNTok, g.c_row_off = kNTz;
             VT_LAUNCH(launch_gemm_simt(g, s));
         }
-        VT_LAUNCH(launch_attention(t->QKV, t->ATT, n, D, t->heads, s));
+        if (t->debug_capture) VT_CUDA(cudaMemcpyAsync(t->d_dbg, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
+        for (int l = 0; l < t->depth; ++l) {
+            const BlockW& b = t->blk[l];
+            {
+                GemmArgs g = gemm_args(t->X, D, b.qkv_w, b.qkv_b, t->QKV, 3 * D, M, 3 * D, D);
+                g.ln_g = b.ln1_g, g.ln_b = b.ln1_b;
+                VT_LAUNCH(launch_gemm_simt(g, s));
+            }
+            VT_LAUNCH(launch_attention(t->QKV, t->ATT, nullptr, nullptr, n, D, t->heads, s));
+            {
+                GemmArgs g = gemm_args(t->ATT, D, b.proj_w, b.proj_b, t->X, D, M, D, D);
+                g.residual = 1;
+                VT_LAUNCH(launch_gemm_simt(g, s));
+            }
+            {
+                GemmArgs g = gemm_args(t->X, D, b.fc1_w, b.fc1_b, t->HID, Hd, M, Hd, D);
+                g.ln_g = b.ln2_g, g.ln_b = b.ln2_b, g.gelu = 1;
+                VT_LAUNCH(launch_gemm_simt(g, s));
+            }
+            {
+                GemmArgs g = gemm_args(t->HID, Hd, b.fc2_w, b.fc2_b, t->X, D, M, D, Hd);
+                g.residual = 1;
+                VT_LAUNCH(launch_gemm_simt(g, s));
+            }
+            if (t->debug_capture)
+                VT_CUDA(cudaMemcpyAsync(t->d_dbg + (size_t)(l + 1) * t->maxT * kNTok * D, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
+        }
+        VT_LAUNCH(launch_layernorm(t->X, D, t->lnf_g, t->lnf_b, t->Yf, D, n * kNTx, D, kNTx, kNTok, kNTz, s));
         {
-            GemmArgs g = gemm_args(t->ATT, D, b.proj_w, b.proj_b, t->X, D, M, D, D);
-            g.residual = 1;
+            GemmArgs g = gemm_args(t->Yf, D, t->h1_w, t->h1_b, t->H1, C, n * kNTx, C, 9 * D);
+            g.relu = 1, g.im2col_feat = D;
+            g.a_rows_in = kNTx, g.a_rows_stride = kNTx, g.a_row_off = 0;
             VT_LAUNCH(launch_gemm_simt(g, s));
         }
-        {
-            GemmArgs g = gemm_args(t->X, D, b.fc1_w, b.fc1_b, t->HID, Hd, M, Hd, D);
-            g.ln_g = b.ln2_g, g.ln_b = b.ln2_b, g.gelu = 1;
-            VT_LAUNCH(launch_gemm_simt(g, s));
+    } else {
+        // ---------------- tensor-core path: tcgen05 GEMMs fed by TMA, bf16 (x3 split) operands, fp32 TMEM accumulators ----------------
+        const int ns = t->nsplit;
+        VT_LAUNCH(tc_gemm_launch(t->plan_patch_x, n * kNTx, ns, s));
+        if (t->debug_capture) VT_CUDA(cudaMemcpyAsync(t->d_dbg, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
+        for (int l = 0; l < t->depth; ++l) {
+            const BlockW& b = t->blk[l];
+            const vt_tracker::BlockPlans& p = t->plans[l];
+            VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s));
+            VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s));
+            VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
+            VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s));
+            VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s));
+            VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s));
+            VT_LAUNCH(tc_gemm_launch(p.fc2, M, ns, s));
+            if (t->debug_capture)
+                VT_CUDA(cudaMemcpyAsync(t->d_dbg + (size_t)(l + 1) * t->maxT * kNTok * D, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
         }
-        {
-            GemmArgs g = gemm_args(t->HID, Hd, b.fc2_w, b.fc2_b, t->X, D, M, D, Hd);
-            g.residual = 1;
-            VT_LAUNCH(launch_gemm_simt(g, s));
-        }
-        if (t->debug_capture)
-            VT_CUDA(cudaMemcpyAsync(t->d_dbg + (size_t)(l + 1) * t->maxT * kNTok * D, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
-    }
-    VT_LAUNCH(launch_layernorm(t->X, D, t->lnf_g, t->lnf_b, t->Yf, D, n * kNTx, D, kNTx, kNTok, kNTz, s));
-    {
-        GemmArgs g = gemm_args(t->Yf, D, t->h1_w, t->h1_b, t->H1, C, n * kNTx, C, 9 * D);
-        g.relu = 1, g.im2col_feat = D;
-        g.a_rows_in = kNTx, g.a_rows_stride = kNTx, g.a_row_off = 0;
-        VT_LAUNCH(launch_gemm_simt(g, s));
+        VT_LAUNCH(launch_layernorm(t->X, D, t->lnf_g, t->lnf_b, t->Yf, D, n * kNTx, D, kNTx, kNTok, kNTz, s));  // fp32 copy for diagnostics
+        VT_LAUNCH(launch_layernorm_split(t->X, D, t->lnf_g, t->lnf_b, t->yf_hi, t->yf_lo, n * kNTx, D, kNTx, kNTok, kNTz, s));
+        VT_LAUNCH(tc_gemm_launch(t->plan_head, n * kNTx, ns, s));
     }
     if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_VIT], s, ev_flags));
     VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, s));
@@ -448,6 +487,15 @@ static vt_status wait_common(vt_tracker* t, size_t len, vt_result* results) {
     }
     t->in_flight = false;
     VT_CUDA(cudaStreamSynchronize(t->stream));
+    if (t->d_tc_err) {
+        int e = 0;
+        VT_CUDA(cudaMemcpy(&e, t->d_tc_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) {
+            cudaMemset(t->d_tc_err, 0, sizeof(int));
+            set_error("tcgen05 GEMM: a bounded mbarrier wait expired (pipeline protocol error)");
+            return VT_ERR_CUDA;
+        }
+    }
     fill_results(t, results);
     if (t->cfg.box_overlay && t->inflight_frame) {
         std::vector<std::pair<int, int>> spans;
@@ -508,7 +556,9 @@ void vt_tracker_destroy(vt_tracker* t) {
     for (auto& e : t->ev)
         if (e) cudaEventDestroy(e);
     void* dev[] = {t->d_weights, t->d_lut, t->d_hann, t->d_frame, t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
-                   t->patches_x, t->patches_z, t->Zemb, t->X, t->QKV, t->ATT, t->HID, t->Yf, t->H1, t->d_dbg};
+                   t->patches_x, t->patches_z, t->Zemb, t->X, t->QKV, t->ATT, t->HID, t->Yf, t->H1, t->d_dbg,
+                   t->w_hi, t->w_lo, t->px_hi, t->px_lo, t->pz_hi, t->pz_lo, t->ln_hi, t->ln_lo, t->att_hi, t->att_lo,
+                   t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->d_tc_err};
     for (void* p : dev)
         if (p) cudaFree(p);
     if (t->h_stage) cudaFreeHost(t->h_stage);
@@ -524,8 +574,8 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         set_error("vt_tracker_create: invalid configuration");
         return VT_ERR_INVALID;
     }
-    if (cfg->gemm_mode != VT_GEMM_FP32_SIMT) {
-        set_error("vt_tracker_create: gemm_mode %d is not available in this build", cfg->gemm_mode);
+    if (cfg->gemm_mode != VT_GEMM_FP32_SIMT && cfg->gemm_mode != VT_GEMM_TCGEN05_BF16X3 && cfg->gemm_mode != VT_GEMM_TCGEN05_BF16) {
+        set_error("vt_tracker_create: unknown gemm_mode %d", cfg->gemm_mode);
         return VT_ERR_INVALID;
     }
     *out = nullptr;
@@ -603,6 +653,68 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     VT_TRY(cudaMemset(t->patches_x, 0, sizeof(float) * B * kNTx * kPatchK));
     VT_TRY(cudaMemset(t->patches_z, 0, sizeof(float) * kNTz * kPatchK));
     if (t->debug_capture) VT_TRY(cudaMalloc(&t->d_dbg, sizeof(float) * (size_t)(t->depth + 1) * B * kNTok * D));
+    t->nsplit = cfg->gemm_mode == VT_GEMM_TCGEN05_BF16X3 ? 3 : (cfg->gemm_mode == VT_GEMM_TCGEN05_BF16 ? 1 : 0);
+    if (t->nsplit) {
+        if (D % 64 || Hd % 64 || C % 64) {
+            set_error("the tcgen05 path needs D, hidden and head_ch to be multiples of 64 (D=%zu hidden=%zu head_ch=%zu)", D, Hd, C);
+            return fail(VT_ERR_WEIGHTS);
+        }
+        VT_TRY(tc_gemm_setup());
+        const size_t nw = t->n_weights;
+        VT_TRY(cudaMalloc(&t->w_hi, nw * 2)); VT_TRY(cudaMalloc(&t->w_lo, nw * 2));
+        VT_TRY(launch_split_bf16(t->d_weights, t->w_hi, t->w_lo, nw, t->stream));
+        auto balloc = [&](__nv_bfloat16** hi, __nv_bfloat16** lo, size_t n) -> cudaError_t {
+            cudaError_t e = cudaMalloc(hi, n * 2);
+            if (e == cudaSuccess) e = cudaMalloc(lo, n * 2);
+            if (e == cudaSuccess) e = cudaMemset(*hi, 0, n * 2);
+            if (e == cudaSuccess) e = cudaMemset(*lo, 0, n * 2);
+            return e;
+        };
+        VT_TRY(balloc(&t->px_hi, &t->px_lo, B * kNTx * kPatchK));
+        VT_TRY(balloc(&t->pz_hi, &t->pz_lo, (size_t)128 * kPatchK));  // one 128-row tile; rows 64..127 stay zero
+        VT_TRY(balloc(&t->ln_hi, &t->ln_lo, B * kNTok * D));
+        VT_TRY(balloc(&t->att_hi, &t->att_lo, B * kNTok * D));
+        VT_TRY(balloc(&t->hid_hi, &t->hid_lo, B * kNTok * Hd));
+        VT_TRY(balloc(&t->yf_hi, &t->yf_lo, B * kNTx * D));
+        VT_TRY(cudaMalloc(&t->d_tc_err, sizeof(int)));
+        VT_TRY(cudaMemset(t->d_tc_err, 0, sizeof(int)));
+        auto whi = [&](const float* w) { return t->w_hi + (w - t->d_weights); };
+        auto wlo = [&](const float* w) { return t->w_lo + (w - t->d_weights); };
+        bool ok = true;
+        const uint64_t rows = B * kNTok;
+        // patch embed (search): A = patches [B*256, 768] -> X rows 64.. of every target, + pos_x
+        ok &= tc_plan_init(&t->plan_patch_x, t->px_hi, t->px_lo, B * kNTx, whi(t->patch_w), wlo(t->patch_w), (int)D, kPatchK, 0, 0);
+        {
+            TcGemmArgs& a = t->plan_patch_x.args;
+            a.bias = t->patch_b, a.pos = t->pos_x, a.pos_rows = kNTx, a.C = t->X, a.ldc = D;
+            a.c_rows_in = kNTx, a.c_rows_stride = kNTok, a.c_row_off = kNTz;
+        }
+        // patch embed (template, at init): C is set per target
+        ok &= tc_plan_init(&t->plan_patch_z, t->pz_hi, t->pz_lo, 128, whi(t->patch_w), wlo(t->patch_w), (int)D, kPatchK, 0, 0);
+        {
+            TcGemmArgs& a = t->plan_patch_z.args;
+            a.bias = t->patch_b, a.pos = t->pos_z, a.pos_rows = kNTz, a.ldc = D;
+        }
+        t->plans.resize(t->depth);
+        for (int l = 0; l < t->depth && ok; ++l) {
+            const BlockW& b = t->blk[l];
+            vt_tracker::BlockPlans& p = t->plans[l];
+            ok &= tc_plan_init(&p.qkv, t->ln_hi, t->ln_lo, rows, whi(b.qkv_w), wlo(b.qkv_w), (int)(3 * D), (int)D, 0, 0);
+            p.qkv.args.bias = b.qkv_b, p.qkv.args.C = t->QKV, p.qkv.args.ldc = 3 * D;
+            ok &= tc_plan_init(&p.proj, t->att_hi, t->att_lo, rows, whi(b.proj_w), wlo(b.proj_w), (int)D, (int)D, 0, 0);
+            p.proj.args.bias = b.proj_b, p.proj.args.C = t->X, p.proj.args.ldc = D, p.proj.args.residual = 1;
+            ok &= tc_plan_init(&p.fc1, t->ln_hi, t->ln_lo, rows, whi(b.fc1_w), wlo(b.fc1_w), (int)Hd, (int)D, 0, 0);
+            p.fc1.args.bias = b.fc1_b, p.fc1.args.gelu = 1, p.fc1.args.Ohi = t->hid_hi, p.fc1.args.Olo = t->hid_lo, p.fc1.args.ldo = Hd;
+            ok &= tc_plan_init(&p.fc2, t->hid_hi, t->hid_lo, rows, whi(b.fc2_w), wlo(b.fc2_w), (int)D, (int)Hd, 0, 0);
+            p.fc2.args.bias = b.fc2_b, p.fc2.args.C = t->X, p.fc2.args.ldc = D, p.fc2.args.residual = 1;
+        }
+        // 3x3 head conv: A gathered by TMA from the [B,16,16,D] final-LN grid (zero fill = zero padding), weights [C][tap][D]
+        ok &= tc_plan_init(&t->plan_head, t->yf_hi, t->yf_lo, 0, whi(t->h1_w), wlo(t->h1_w), (int)C, (int)(9 * D), (int)D, (int)B);
+        t->plan_head.args.bias = t->h1_b, t->plan_head.args.relu = 1, t->plan_head.args.C = t->H1, t->plan_head.args.ldc = C;
+        if (!ok) return fail(VT_ERR_CUDA);
+        for (TcGemmPlan* p : {&t->plan_patch_x, &t->plan_patch_z, &t->plan_head}) p->args.err = t->d_tc_err;
+        for (auto& p : t->plans) p.qkv.args.err = p.proj.args.err = p.fc1.args.err = p.fc2.args.err = t->d_tc_err;
+    }
     t->rect_mirror.assign(B, vt_bbox{0, 0, 0, 0});
     t->inited.assign(B, 0);
     VT_TRY(cudaStreamSynchronize(t->stream));
@@ -646,12 +758,17 @@ vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, s
     VT_CUDA(cudaMemcpyAsync(t->d_slots, &slot, sizeof(slot), cudaMemcpyHostToDevice, t->stream));
     FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid};
     int launches = 0;
-    VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, 1, 2, kTemplate, t->d_lut, t->patches_z, (size_t)kNTz * kPatchK, nullptr, t->stream));
-    {
+    VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, 1, 2, kTemplate, t->d_lut, t->patches_z, (size_t)kNTz * kPatchK, t->pz_hi,
+                                      t->pz_lo, t->stream));
+    if (t->nsplit == 0) {
         GemmArgs g = gemm_args(t->patches_z, kPatchK, t->patch_w, t->patch_b, t->Zemb + (size_t)target * kNTz * t->D, t->D, kNTz, t->D, kPatchK);
         g.pos = t->pos_z;
         g.c_rows_in = kNTz, g.c_rows_stride = kNTz, g.c_row_off = 0;
         VT_LAUNCH(launch_gemm_simt(g, t->stream));
+    } else {
+        TcGemmPlan p = t->plan_patch_z;
+        p.args.C = t->Zemb + (size_t)target * kNTz * t->D;
+        VT_LAUNCH(tc_gemm_launch(p, kNTz, t->nsplit, t->stream));
     }
     t->kernel_launches += launches;
     VT_CUDA(cudaStreamSynchronize(t->stream));

@@ -190,6 +190,37 @@ cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* g, const 
     return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g,
+                                                              const float* __restrict__ b, __nv_bfloat16* __restrict__ hi,
+                                                              __nv_bfloat16* __restrict__ lo, int M, int D, int rows_in, int rows_stride,
+                                                              int row_off) {
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float* r = x + (int64_t)map_row(m, rows_in, rows_stride, row_off) * ldx;
+    float s = 0.f;
+    for (int k = lane; k < D; k += 32) s += r[k];
+    const float mean = warp_sum(s) / (float)D;
+    float v = 0.f;
+    for (int k = lane; k < D; k += 32) {
+        const float d = r[k] - mean;
+        v += d * d;
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(v) / (float)D + 1e-6f);
+    for (int k = lane; k < D; k += 32) {
+        const float y = (r[k] - mean) * rstd * g[k] + b[k];
+        const __nv_bfloat16 h = __float2bfloat16_rn(y);
+        hi[(int64_t)m * D + k] = h;
+        lo[(int64_t)m * D + k] = __float2bfloat16_rn(y - __bfloat162float(h));
+    }
+}
+
+cudaError_t launch_layernorm_split(const float* x, int64_t ldx, const float* g, const float* b, __nv_bfloat16* hi, __nv_bfloat16* lo, int M,
+                                   int D, int rows_in, int rows_stride, int row_off, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    layernorm_split_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ldx, g, b, hi, lo, M, D, rows_in, rows_stride, row_off);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Attention over the joint 320-token sequence: one CTA per (16-query tile, head, target).
 // scores -> shared memory, warp-shuffle softmax, P*V from shared memory.
@@ -197,7 +228,8 @@ cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* g, const 
 constexpr int kBQ = 16, kKT = 64;
 
 template <int DH>
-__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int D) {
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                        __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int D) {
     __shared__ float Qs[kBQ][DH];
     __shared__ float S[kBQ][kNTok];
     __shared__ float KV[kKT][DH + 1];
@@ -258,17 +290,26 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
         }
     }
 #pragma unroll
-    for (int i = 0; i < kQPer; ++i) out[((int64_t)b * kNTok + q0 + qg * kQPer + i) * D + h * DH + d] = o[i];
+    for (int i = 0; i < kQPer; ++i) {
+        const int64_t idx = ((int64_t)b * kNTok + q0 + qg * kQPer + i) * D + h * DH + d;
+        if (out) out[idx] = o[i];
+        if (out_hi) {
+            const __nv_bfloat16 hh = __float2bfloat16_rn(o[i]);
+            out_hi[idx] = hh;
+            out_lo[idx] = __float2bfloat16_rn(o[i] - __bfloat162float(hh));
+        }
+    }
 }
 
-cudaError_t launch_attention(const float* qkv, float* out, int B, int D, int heads, cudaStream_t s) {
+cudaError_t launch_attention(const float* qkv, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int B, int D, int heads,
+                             cudaStream_t s) {
     if (B <= 0) return cudaSuccess;
     const int dh = D / heads;
     dim3 grid(kNTok / kBQ, heads, B);
     switch (dh) {
-        case 16: attention_kernel<16><<<grid, 128, 0, s>>>(qkv, out, D); break;
-        case 32: attention_kernel<32><<<grid, 128, 0, s>>>(qkv, out, D); break;
-        case 64: attention_kernel<64><<<grid, 128, 0, s>>>(qkv, out, D); break;
+        case 16: attention_kernel<16><<<grid, 128, 0, s>>>(qkv, out, out_hi, out_lo, D); break;
+        case 32: attention_kernel<32><<<grid, 128, 0, s>>>(qkv, out, out_hi, out_lo, D); break;
+        case 64: attention_kernel<64><<<grid, 128, 0, s>>>(qkv, out, out_hi, out_lo, D); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -1,6 +1,8 @@
 // vt_internal.h — shared declarations of libvittrack_b200 (not installed; the public ABI is include/vt_tracker.h)
 #pragma once
 
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -91,9 +93,10 @@ cudaError_t launch_nv12_to_rgb(const uint8_t* d_nv12, size_t stride_in, uint8_t*
 
 // fused crop + (NV12->RGB) + bilinear resize + normalise -> patch-major tokens A[target][n_tok][768]
 // slots: list of target slot indices processed (device array), n = count. factor 2 -> 128 template, 4 -> 256 search
+// p_hi / p_lo (nullable): the same values as a bf16 (hi, lo) split, the A operand of the tensor-core patch-embed GEMM
 cudaError_t launch_crop_resize_norm(FrameDesc f, TargetState* d_state, const int32_t* d_slots, int n, int factor, int out_size,
-                                    const float* d_norm_lut, float* d_patches, size_t patches_stride, const int32_t* d_init_rect,
-                                    cudaStream_t s);
+                                    const float* d_norm_lut, float* d_patches, size_t patches_stride, __nv_bfloat16* p_hi,
+                                    __nv_bfloat16* p_lo, cudaStream_t s);
 
 struct OverlayCmdDev {     // device-side copy of vt_overlay_cmd with resolved glyph rows
     int32_t kind, x, y, w, h, a;
@@ -133,10 +136,39 @@ struct GemmArgs {
 cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
 cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* g, const float* b, float* y, int64_t ldy, int M, int D,
                              int rows_in, int rows_stride, int row_off, cudaStream_t s);
-// qkv: [B*320, 3D]; out: [B*320, D]
-cudaError_t launch_attention(const float* qkv, float* out, int B, int D, int heads, cudaStream_t s);
+// LayerNorm whose output is written as a bf16 (hi, lo) split [M, D] (dense rows) for the tensor-core GEMMs
+cudaError_t launch_layernorm_split(const float* x, int64_t ldx, const float* g, const float* b, __nv_bfloat16* hi, __nv_bfloat16* lo, int M,
+                                   int D, int rows_in, int rows_stride, int row_off, cudaStream_t s);
+// qkv: [B*320, 3D]; out: [B*320, D] fp32 (nullable) and/or bf16 split (nullable)
+cudaError_t launch_attention(const float* qkv, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int B, int D, int heads,
+                             cudaStream_t s);
 // head 1x1 conv + sigmoid + hann + argmax + bbox decode, one CTA per target
 cudaError_t launch_decode(const float* h1, int head_ch, const float* w2, const float* b2, const float* hann, TargetState* d_state,
                           const int32_t* d_slots, int n, float threshold, DeviceResult* d_res, float* d_maps, cudaStream_t s);
+
+// ---- tensor-core GEMM (gemm_tc.cu) ------------------------------------------------------------------
+struct TcGemmArgs {
+    int M, N, K;
+    int conv_feat;            // 0, or the feature dim D of the 3x3 head conv (A gathered from the [B,16,16,D] grid by TMA)
+    const float* bias;        // [N] or null
+    const float* pos;         // [pos_rows, N] added to row (m % pos_rows), or null
+    int pos_rows;
+    int gelu, relu, residual;
+    float* C;                 // fp32 output (nullable); row m -> (m / c_rows_in) * c_rows_stride + c_row_off + m % c_rows_in
+    int64_t ldc;
+    int c_rows_in, c_rows_stride, c_row_off;
+    __nv_bfloat16 *Ohi, *Olo; // bf16 split output [M, ldo] (nullable)
+    int64_t ldo;
+    int* err;                 // set to 1 if a bounded mbarrier wait expired
+};
+struct TcGemmPlan {
+    CUtensorMap mAhi, mAlo, mBhi, mBlo;
+    TcGemmArgs args;
+};
+bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, uint64_t a_rows, const __nv_bfloat16* Whi,
+                  const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch);
+cudaError_t tc_gemm_setup();
+cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s);
+cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t s);
 
 }  // namespace vt

@@ -138,6 +138,11 @@ vt_status vt_tracker_debug_tokens(vt_tracker* t, int32_t target, int32_t which, 
 void* vt_tracker_stream(vt_tracker* t);
 vt_status vt_tracker_sync(vt_tracker* t);
 
+/* diagnostics: one C[M,N] = A[M,K] * W[N,K]^T (+bias, optional GELU) on host data through the tcgen05 GEMM kernel
+ * (nsplit 1 = bf16, 3 = bf16x3); *err_out != 0 reports an expired pipeline wait.  N and K multiples of 64. */
+vt_status vt_debug_gemm(int32_t device, int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias,
+                        int32_t nsplit, int32_t gelu, float* C_out, int32_t* err_out);
+
 /* ------------------------------------------------------------------------------------------- */
 /* NV12 -> RGB (parity / bench entry)                                                           */
 /* ------------------------------------------------------------------------------------------- */

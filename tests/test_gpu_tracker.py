@@ -131,8 +131,9 @@ def test_short_nv12_frame_is_black(api, oracle, weight_dir):
 
 
 # ---- network: layer-wise ------------------------------------------------------------------------------
+@pytest.mark.parametrize("gemm_mode", [0, 1], ids=["fp32simt", "tcgen05x3"])
 @pytest.mark.parametrize("model", ["nano", "tiny"])
-def test_layerwise_tokens(api, oracle, weight_dir, model):
+def test_layerwise_tokens(api, oracle, weight_dir, model, gemm_mode):
     """Token features after the embeddings and after every block vs the fp32 oracle (relative 2e-4 of the layer's scale)."""
     W, H = 1280, 720
     wpath = weights.ensure_weight_file(model, weight_dir, variant="wild")
@@ -140,7 +141,7 @@ def test_layerwise_tokens(api, oracle, weight_dir, model):
     frame = st.frame(0)
     rgb = oracle.nv12_to_rgb(frame, W, H, 8)
     box = st.target_boxes(0)[0]
-    trk = api.VitTrack.new(wpath, W, H, debug_capture=True)
+    trk = api.VitTrack.new(wpath, W, H, debug_capture=True, gemm_mode=gemm_mode)
     ref = oracle.VitTrack(wpath, threads=8)
     trk.init(frame, api.BBox(*box))
     ref.init(rgb, box)
@@ -163,8 +164,9 @@ def test_layerwise_tokens(api, oracle, weight_dir, model):
 
 
 # ---- against the third-party cv2.TrackerVit fixtures -----------------------------------------------------
+@pytest.mark.parametrize("gemm_mode", [0, 1], ids=["fp32simt", "tcgen05x3"])
 @pytest.mark.parametrize("variant", ["stable", "wild"])
-def test_sequences_vs_cv2_golden(api, weight_dir, variant):
+def test_sequences_vs_cv2_golden(api, weight_dir, variant, gemm_mode):
     g = golden("trackervit_nano.json")["models"][variant]
     wpath = weights.ensure_weight_file("nano", weight_dir, variant=variant)
     assert hashlib.sha256(open(wpath, "rb").read()).hexdigest() == g["weights_sha256"]
@@ -172,7 +174,7 @@ def test_sequences_vs_cv2_golden(api, weight_dir, variant):
         sp = seq["spec"]
         spec = synth.StreamSpec(seq["name"], sp["w"], sp["h"], sp["seed"], [tuple(t) for t in sp["targets"]])
         st = synth.SyntheticStream(spec)
-        trk = api.VitTrack.new(wpath, spec.width, spec.height)
+        trk = api.VitTrack.new(wpath, spec.width, spec.height, gemm_mode=gemm_mode)
         trk.init(st.frame(0), api.BBox(*seq["init_box"]))
         n_exact = 0
         for i, fr in enumerate(seq["frames"]):
@@ -188,15 +190,16 @@ def test_sequences_vs_cv2_golden(api, weight_dir, variant):
         assert n_exact >= len(seq["frames"]) - 2, (seq["name"], n_exact)
 
 
+@pytest.mark.parametrize("gemm_mode", [0, 1], ids=["fp32simt", "tcgen05x3"])
 @pytest.mark.parametrize("variant", ["stable", "wild"])
-def test_single_steps_vs_cv2_golden(api, weight_dir, variant):
+def test_single_steps_vs_cv2_golden(api, weight_dir, variant, gemm_mode):
     g = golden("trackervit_nano.json")["models"][variant]
     wpath = weights.ensure_weight_file("nano", weight_dir, variant=variant)
     sp = g["steps_spec"]
     spec = synth.StreamSpec("steps", sp["w"], sp["h"], sp["seed"], [tuple(t) for t in sp["targets"]])
     st = synth.SyntheticStream(spec)
     f0, f1 = st.frame(sp["frames"][0]), st.frame(sp["frames"][1])
-    trk = api.VitTrack.new(wpath, spec.width, spec.height)
+    trk = api.VitTrack.new(wpath, spec.width, spec.height, gemm_mode=gemm_mode)
     n_exact = n = 0
     for s in g["single_steps"]:
         if s.get("error"):
@@ -218,13 +221,14 @@ def test_single_steps_vs_cv2_golden(api, weight_dir, variant):
 
 
 # ---- teacher-forced long sequences vs the oracle ------------------------------------------------------------
+@pytest.mark.parametrize("gemm_mode", [0, 1], ids=["fp32simt", "tcgen05x3"])
 @pytest.mark.parametrize("model,cfg,frames", [("nano", "cfg1", 120), ("tiny", "cfg2", 60)])
-def test_teacher_forced_sequence(api, oracle, weight_dir, model, cfg, frames):
+def test_teacher_forced_sequence(api, oracle, weight_dir, model, cfg, frames, gemm_mode):
     spec = synth.CONFIGS[cfg]
     W, H = spec.width, spec.height
     wpath = weights.ensure_weight_file(model, weight_dir)
     st = synth.SyntheticStream(spec)
-    trk = api.VitTrack.new(wpath, W, H)
+    trk = api.VitTrack.new(wpath, W, H, gemm_mode=gemm_mode)
     ref = oracle.VitTrack(wpath, threads=8)
     f0 = st.frame(0)
     box = st.target_boxes(0)[0]
@@ -240,7 +244,7 @@ def test_teacher_forced_sequence(api, oracle, weight_dir, model, cfg, frames):
         assert rc == 0
         pre, margin = oracle_prefloor(ref, before)
         compare_step(r, ok, score, bb, pre, margin, stats, (model, cfg, n))
-    print(f"\n[parity {model}/{cfg}] {frames} frames: exact {stats['exact']}, boundary(+-1px) {stats['boundary']}, ties {stats['ties']}, "
+    print(f"\n[parity {model}/{cfg}/gemm_mode={gemm_mode}] {frames} frames: exact {stats['exact']}, boundary(+-1px) {stats['boundary']}, ties {stats['ties']}, "
           f"max|dscore| {stats['max_dscore']:.2e}, min IoU on boundary frames {stats['min_iou_boundary']:.4f}")
     assert stats["exact"] >= 0.9 * frames
     assert stats["max_dscore"] <= SCORE_TOL
@@ -274,13 +278,14 @@ def test_free_running_sequence_iou(api, oracle, weight_dir):
 
 
 # ---- multi-target, formats, errors -----------------------------------------------------------------------------
-def test_multi_target_equals_independent_singles(api, weight_dir):
+@pytest.mark.parametrize("gemm_mode", [0, 1], ids=["fp32simt", "tcgen05x3"])
+def test_multi_target_equals_independent_singles(api, weight_dir, gemm_mode):
     """16 targets batched through one forward (cfg4 geometry at 1/2 scale for speed) == 16 single-target trackers, bit for bit."""
     spec = synth.StreamSpec("mt", 1920, 1080, 1004, [(190 + (i % 4) * 450, 110 + (i // 4) * 250, 100, 75, 3 + i % 4, 2 + i // 4) for i in range(16)])
     st = synth.SyntheticStream(spec)
     wpath = weights.ensure_weight_file("nano", weight_dir, variant="wild")
-    multi = api.VitTrack.new(wpath, spec.width, spec.height, max_targets=16)
-    singles = [api.VitTrack.new(wpath, spec.width, spec.height) for _ in range(16)]
+    multi = api.VitTrack.new(wpath, spec.width, spec.height, max_targets=16, gemm_mode=gemm_mode)
+    singles = [api.VitTrack.new(wpath, spec.width, spec.height, gemm_mode=gemm_mode) for _ in range(16)]
     f0 = st.frame(0)
     for i, b in enumerate(st.target_boxes(0)):
         multi.init(f0, api.BBox(*b), target=i)
