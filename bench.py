@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=60)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="tiny", choices=["tiny", "nano"])
+    ap.add_argument("--gemm", default="tcgen05x3", choices=["fp32simt", "tcgen05x3", "tcgen05"],
+                    help="precision/engine of the dense contractions (tcgen05x3 = bf16 split operands, the parity-safe default)")
     ap.add_argument("--streams-per-gpu", type=int, default=1)
     ap.add_argument("--ring", type=int, default=128, help="distinct frames per stream (ring > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,7 +218,8 @@ def run_b200(args):
         spec = stream_spec(rank, k, args)
         st = synth.SyntheticStream(spec)
         fb = st.frame_bytes()
-        trk = api.VitTrack.new(wpath, spec.width, spec.height, fmt="nv12", device=local_rank, box_overlay=True)
+        trk = api.VitTrack.new(wpath, spec.width, spec.height, fmt="nv12", device=local_rank, box_overlay=True,
+                               gemm_mode={"fp32simt": 0, "tcgen05x3": 1, "tcgen05": 2}[args.gemm])
         pin = api.PinnedBuffer(ring_n * fb)
         host = pin.array.reshape(ring_n, fb)
         for i in range(ring_n):
@@ -339,9 +342,10 @@ def run_b200(args):
         fb0 = streams[0]["fb"]
         out = {
             "metric": METRIC, "value": frames_g / (ms_dev_g * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms_dev_g / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_dev_g / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32simt": "f32", "tcgen05x3": "bf16x3 (split bf16 operands, fp32 accumulate)", "tcgen05": "bf16"}[args.gemm],
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "resolution": "1920x1080", "format": "NV12", "targets": 1, "model": args.model,
+            "config": {"workload": workload_name(args), "resolution": "1920x1080", "format": "NV12", "targets": 1, "model": args.model, "gemm": args.gemm,
                        "streams_per_gpu": S, "weights": "constructed random-init (SURVEY.md §8c)",
                        "l2": f"inputs larger than L2: ring of {ring_n} distinct frames = {ring_n * fb0 / 1e6:.0f} MB per stream"},
             "e2e": {"value": frames_g / (ms_e2e_g * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
@@ -349,7 +353,7 @@ def run_b200(args):
                     "stages_ms": stage_e2e},
             "latency_ms": {"device_resident_p50": float(np.percentile(lat_d, 50)), "host_p50": float(np.percentile(lat_all, 50))},
             "gpu_launches": int(launches_g), "stages_ms": stage,
-            "roofline": {"kernel": "ViT forward (patch-embed, QKV, attention, proj, MLP, head: fp32 SIMT GEMM/attention kernels)",
+            "roofline": {"kernel": "ViT forward (patch-embed, QKV, attention, proj, MLP, head) gemm=" + args.gemm,
                          "bound": "tensor", "achieved": ach_tf, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": (ach_tf / tf_peak) if ach_tf else None, "traffic": None, "peak_source": peak_src,
                          "note": "B=1 (320 tokens) is launch/latency bound; FLOPs/frame = %.3f G" % (flops / 1e9)},

@@ -166,6 +166,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
+            if (a.qkv_heads) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(v[j], h0, l0), split_bf16(v[j + 1], h1, l1);
+                    hi[j >> 1] = pack_bf16(h0, h1), lo[j >> 1] = pack_bf16(l0, l1);
+                }
+                const int Dm = a.N / 3, which = n0 / Dm, hh = (n0 % Dm) / kTcBN;
+                const int64_t bh = (int64_t)(m / kNTok) * a.qkv_heads + hh;
+                const int tok = m % kNTok;
+                if (which < 2) {  // Q / K: [bh][tok][64], this thread's 32 columns are contiguous
+                    __nv_bfloat16* dh_ = (which == 0 ? a.Qhi : a.Khi) + (bh * kNTok + tok) * kTcBN + c0;
+                    __nv_bfloat16* dl_ = (which == 0 ? a.Qlo : a.Klo) + (bh * kNTok + tok) * kTcBN + c0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        reinterpret_cast<uint4*>(dh_)[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        reinterpret_cast<uint4*>(dl_)[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                    }
+                } else {  // V^T: [bh][d][tok]; a warp's 32 rows are 32 consecutive tokens -> 64-byte coalesced stores per d
+                    unsigned short* vh = reinterpret_cast<unsigned short*>(a.Vthi) + (bh * kTcBN + c0) * kNTok + tok;
+                    unsigned short* vl = reinterpret_cast<unsigned short*>(a.Vtlo) + (bh * kTcBN + c0) * kNTok + tok;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        vh[(int64_t)j * kNTok] = (unsigned short)((j & 1) ? (hi[j >> 1] >> 16) : (hi[j >> 1] & 0xffffu));
+                        vl[(int64_t)j * kNTok] = (unsigned short)((j & 1) ? (lo[j >> 1] >> 16) : (lo[j >> 1] & 0xffffu));
+                    }
+                }
+            }
             if (a.Ohi) {
                 uint32_t hi[16], lo[16];
 #pragma unroll

@@ -82,6 +82,9 @@ struct vt_tracker {
     __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
     __nv_bfloat16 *px_hi = nullptr, *px_lo = nullptr, *pz_hi = nullptr, *pz_lo = nullptr, *ln_hi = nullptr, *ln_lo = nullptr, *att_hi = nullptr,
                   *att_lo = nullptr, *hid_hi = nullptr, *hid_lo = nullptr, *yf_hi = nullptr, *yf_lo = nullptr;
+    __nv_bfloat16 *q_hi = nullptr, *q_lo = nullptr, *k_hi = nullptr, *k_lo = nullptr, *vt_hi = nullptr, *vt_lo = nullptr;
+    bool tc_attention = false;  // head_dim == 64
+    TcAttentionPlan plan_att;
     int* d_tc_err = nullptr;
     TcGemmPlan plan_patch_x, plan_patch_z, plan_head;
     struct BlockPlans {
@@ -268,7 +271,10 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             const vt_tracker::BlockPlans& p = t->plans[l];
             VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s));
             VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s));
-            VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
+            if (t->tc_attention)
+                VT_LAUNCH(tc_attention_launch(t->plan_att, t->att_hi, t->att_lo, n, D, t->heads, ns, t->d_tc_err, s));
+            else
+                VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
             VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s));
             VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s));
             VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s));
@@ -558,7 +564,7 @@ void vt_tracker_destroy(vt_tracker* t) {
     void* dev[] = {t->d_weights, t->d_lut, t->d_hann, t->d_frame, t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
                    t->patches_x, t->patches_z, t->Zemb, t->X, t->QKV, t->ATT, t->HID, t->Yf, t->H1, t->d_dbg,
                    t->w_hi, t->w_lo, t->px_hi, t->px_lo, t->pz_hi, t->pz_lo, t->ln_hi, t->ln_lo, t->att_hi, t->att_lo,
-                   t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->d_tc_err};
+                   t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->d_tc_err, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo};
     for (void* p : dev)
         if (p) cudaFree(p);
     if (t->h_stage) cudaFreeHost(t->h_stage);
@@ -676,6 +682,15 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         VT_TRY(balloc(&t->att_hi, &t->att_lo, B * kNTok * D));
         VT_TRY(balloc(&t->hid_hi, &t->hid_lo, B * kNTok * Hd));
         VT_TRY(balloc(&t->yf_hi, &t->yf_lo, B * kNTx * D));
+        t->tc_attention = (D / t->heads == 64);
+        if (t->tc_attention) {
+            const size_t nq = B * t->heads * kNTok * 64;
+            VT_TRY(balloc(&t->q_hi, &t->q_lo, nq));
+            VT_TRY(balloc(&t->k_hi, &t->k_lo, nq));
+            VT_TRY(balloc(&t->vt_hi, &t->vt_lo, nq));
+            VT_TRY(tc_attention_setup());
+            if (!tc_attention_plan_init(&t->plan_att, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, (int)(B * t->heads))) return fail(VT_ERR_CUDA);
+        }
         VT_TRY(cudaMalloc(&t->d_tc_err, sizeof(int)));
         VT_TRY(cudaMemset(t->d_tc_err, 0, sizeof(int)));
         auto whi = [&](const float* w) { return t->w_hi + (w - t->d_weights); };
@@ -700,7 +715,13 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             const BlockW& b = t->blk[l];
             vt_tracker::BlockPlans& p = t->plans[l];
             ok &= tc_plan_init(&p.qkv, t->ln_hi, t->ln_lo, rows, whi(b.qkv_w), wlo(b.qkv_w), (int)(3 * D), (int)D, 0, 0);
-            p.qkv.args.bias = b.qkv_b, p.qkv.args.C = t->QKV, p.qkv.args.ldc = 3 * D;
+            p.qkv.args.bias = b.qkv_b;
+            if (t->tc_attention) {
+                TcGemmArgs& a = p.qkv.args;
+                a.qkv_heads = t->heads, a.Qhi = t->q_hi, a.Qlo = t->q_lo, a.Khi = t->k_hi, a.Klo = t->k_lo, a.Vthi = t->vt_hi, a.Vtlo = t->vt_lo;
+            } else {
+                p.qkv.args.C = t->QKV, p.qkv.args.ldc = 3 * D;
+            }
             ok &= tc_plan_init(&p.proj, t->att_hi, t->att_lo, rows, whi(b.proj_w), wlo(b.proj_w), (int)D, (int)D, 0, 0);
             p.proj.args.bias = b.proj_b, p.proj.args.C = t->X, p.proj.args.ldc = D, p.proj.args.residual = 1;
             ok &= tc_plan_init(&p.fc1, t->ln_hi, t->ln_lo, rows, whi(b.fc1_w), wlo(b.fc1_w), (int)Hd, (int)D, 0, 0);

@@ -328,14 +328,24 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ h
     __shared__ float s_val[8];
     __shared__ int s_idx[8];
     __shared__ float s_out[4];
+    __shared__ float tile[kNTx][33];   // 32-channel slab of the head features, padded: conflict-free row reads
+    __shared__ float w2s[5][32];
     const int bi = blockIdx.x, slot = slots[bi], p = threadIdx.x;
-    const float* f = h1 + ((int64_t)bi * kNTx + p) * C;
+    const float* f = h1 + (int64_t)bi * kNTx * C;
     float o[5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        float acc = b2[k];
-        for (int c = 0; c < C; ++c) acc = __fadd_rn(acc, __fmul_rn(f[c], w2[k * C + c]));  // oracle order, unfused
-        o[k] = acc;
+    for (int k = 0; k < 5; ++k) o[k] = b2[k];
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        __syncthreads();
+        for (int i = p; i < kNTx * 32; i += 256) tile[i >> 5][i & 31] = f[(int64_t)(i >> 5) * C + c0 + (i & 31)];  // coalesced 128-byte rows
+        if (p < 160) w2s[p >> 5][p & 31] = w2[(p >> 5) * C + c0 + (p & 31)];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float x = tile[p][j];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) o[k] = __fadd_rn(o[k], __fmul_rn(x, w2s[k][j]));  // oracle order (c ascending), unfused
+        }
     }
     const float conf = 1.f / (1.f + expf(-o[0]));
     const float sw = 1.f / (1.f + expf(-o[1])), sh = 1.f / (1.f + expf(-o[2]));

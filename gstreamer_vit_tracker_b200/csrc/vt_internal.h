@@ -159,6 +159,10 @@ struct TcGemmArgs {
     int c_rows_in, c_rows_stride, c_row_off;
     __nv_bfloat16 *Ohi, *Olo; // bf16 split output [M, ldo] (nullable)
     int64_t ldo;
+    // QKV scatter for the tensor-core attention (head_dim 64 == the N tile): rows are (target, token) pairs
+    int qkv_heads;            // 0 = off
+    __nv_bfloat16 *Qhi, *Qlo, *Khi, *Klo;    // [B*heads][320][64]
+    __nv_bfloat16 *Vthi, *Vtlo;              // [B*heads][64][320]  (V transposed: keys contiguous = K-major B operand of P*V)
     int* err;                 // set to 1 if a bounded mbarrier wait expired
 };
 struct TcGemmPlan {
@@ -169,6 +173,14 @@ bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* 
                   const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch);
 cudaError_t tc_gemm_setup();
 cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s);
+struct TcAttentionPlan {
+    CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo;
+};
+bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const __nv_bfloat16* Qlo, const __nv_bfloat16* Khi, const __nv_bfloat16* Klo,
+                            const __nv_bfloat16* Vthi, const __nv_bfloat16* Vtlo, int batch_heads);
+cudaError_t tc_attention_setup();
+cudaError_t tc_attention_launch(const TcAttentionPlan& p, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int B, int D, int heads, int nsplit,
+                                int* err, cudaStream_t s);
 cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t s);
 
 }  // namespace vt
