@@ -85,6 +85,7 @@ SYMBOLS = {
     "vt_tracker_debug_read": (C.c_int32, [_vp, C.c_int32, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p]),
     "vt_tracker_model_dim": (C.c_int32, [_vp, C.c_int32]),
     "vt_tracker_debug_tokens": (C.c_int32, [_vp, C.c_int32, C.c_int32, _f32p]),
+    "vt_tracker_debug_trace": (C.c_int32, [_vp, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int32)]),
     "vt_tracker_stream": (_vp, [_vp]),
     "vt_tracker_sync": (C.c_int32, [_vp]),
     "vt_debug_gemm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, _f32p,

@@ -200,6 +200,13 @@ class VitTrack:
         check(lib().vt_tracker_debug_tokens(self._h, target, which, out.ctypes.data_as(C.POINTER(C.c_float))), "vt_tracker_debug_tokens")
         return out
 
+    def debug_trace(self, max_records: int = 2048) -> np.ndarray:
+        """Device timeline since the last call: rows of (kernel id, t_entry, t_after_wait, t_end, m4..m7) in ns (VT_B200_TRACE=1)."""
+        out = np.zeros((max_records, 8), np.uint64)
+        n = C.c_int32(0)
+        check(lib().vt_tracker_debug_trace(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), max_records, C.byref(n)), "vt_tracker_debug_trace")
+        return out[: n.value]
+
     def timing(self) -> vt_timing:
         t = vt_timing()
         check(lib().vt_timing_get(self._h, C.byref(t)), "vt_timing_get")

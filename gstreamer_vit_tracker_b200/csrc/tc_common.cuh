@@ -44,6 +44,70 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     return false;
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------
+// Every kernel of the per-frame chain is launched with cudaLaunchAttributeProgrammaticStreamSerialization and follows
+//   prologue (barrier init, TMEM alloc, descriptor prefetch, weight TMA)  ->  pdl_wait()  ->  pdl_launch_dependents()  ->  work
+// pdl_wait() returns when the preceding kernel has completed and its writes are visible.  Triggering the dependents only
+// AFTER the wait bounds residency to two kernels of the chain (the running one and the next one's prologue), so a waiting
+// prologue can never hold shared memory / TMEM that an earlier kernel still needs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- device-side timeline (diagnostics; enabled per handle with VT_B200_TRACE=1) -----------------------------------
+// trace[0] = record counter; record i = trace[1 + 8 i ..]: {kernel id, t_entry, t_after_pdl_wait, t_end, 4 kernel-specific marks}
+// in %globaltimer ns, written by threads of CTA (0,0,0) only.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    return t;
+}
+struct TraceRec {
+    unsigned long long** slot;  // shared-memory cell holding the record pointer (null when tracing is off / not CTA 0)
+    __device__ __forceinline__ void begin(unsigned long long** shared_slot, unsigned long long* trace, int id) {
+        slot = shared_slot;
+        if (threadIdx.x == 0) {
+            unsigned long long* rec = nullptr;
+            if (trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+                const unsigned long long i = atomicAdd(trace, 1ull);
+                if (i < 2048) {
+                    rec = trace + 1 + 8 * i;
+                    rec[0] = (unsigned long long)id, rec[1] = globaltimer_ns();
+                }
+            }
+            *slot = rec;
+        }
+    }
+    // valid after the first __syncthreads() following begin()
+    __device__ __forceinline__ void mark(int k) const {
+        unsigned long long* rec = *slot;
+        if (rec) rec[k] = globaltimer_ns();
+    }
+};
+constexpr size_t kTraceWords = 1 + 8 * 2048;
+
+// ---- thread-block clusters / distributed shared memory ------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// address of the same shared-memory variable in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t cluster_map_shared(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_shared_cluster_f2(uint32_t addr, float x, float y) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // ---- async-proxy fences ---------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -128,6 +192,61 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+#define VT_TMEM_REGS32(r, o)                                                                                                         \
+    "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7]),       \
+        "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]), "=r"(r[o + 12]), "=r"(r[o + 13]), "=r"(r[o + 14]),              \
+        "=r"(r[o + 15]), "=r"(r[o + 16]), "=r"(r[o + 17]), "=r"(r[o + 18]), "=r"(r[o + 19]), "=r"(r[o + 20]), "=r"(r[o + 21]),            \
+        "=r"(r[o + 22]), "=r"(r[o + 23]), "=r"(r[o + 24]), "=r"(r[o + 25]), "=r"(r[o + 26]), "=r"(r[o + 27]), "=r"(r[o + 28]),            \
+        "=r"(r[o + 29]), "=r"(r[o + 30]), "=r"(r[o + 31])
+#define VT_TMEM_TIE32(r, o)                                                                                                          \
+    "+r"(r[o + 0]), "+r"(r[o + 1]), "+r"(r[o + 2]), "+r"(r[o + 3]), "+r"(r[o + 4]), "+r"(r[o + 5]), "+r"(r[o + 6]), "+r"(r[o + 7]),       \
+        "+r"(r[o + 8]), "+r"(r[o + 9]), "+r"(r[o + 10]), "+r"(r[o + 11]), "+r"(r[o + 12]), "+r"(r[o + 13]), "+r"(r[o + 14]),              \
+        "+r"(r[o + 15]), "+r"(r[o + 16]), "+r"(r[o + 17]), "+r"(r[o + 18]), "+r"(r[o + 19]), "+r"(r[o + 20]), "+r"(r[o + 21]),            \
+        "+r"(r[o + 22]), "+r"(r[o + 23]), "+r"(r[o + 24]), "+r"(r[o + 25]), "+r"(r[o + 26]), "+r"(r[o + 27]), "+r"(r[o + 28]),            \
+        "+r"(r[o + 29]), "+r"(r[o + 30]), "+r"(r[o + 31])
+#define VT_TMEM_LD32_ASM                                                                                         \
+    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                    \
+    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+
+// TMEM -> registers, 64 consecutive fp32 columns of this thread's lane: both loads are in flight before the single wait
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile(VT_TMEM_LD32_ASM : VT_TMEM_REGS32(r, 0) : "r"(taddr));
+    asm volatile(VT_TMEM_LD32_ASM : VT_TMEM_REGS32(r, 32) : "r"(taddr + 32));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : VT_TMEM_TIE32(r, 0)::"memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : VT_TMEM_TIE32(r, 32)::"memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+// issue-only / wait-only pair for software-pipelined readers (raw registers; convert after tmem_ld_wait32)
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(VT_TMEM_LD32_ASM : VT_TMEM_REGS32(r, 0) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : VT_TMEM_TIE32(r, 0)::"memory");
+}
+
+// TMEM -> registers: 16 consecutive fp32 columns of this thread's lane
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // fp32 -> (hi, lo) bf16 split: v ~= hi + lo with ~16 mantissa bits

@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -18,6 +19,7 @@
 #include <map>
 #include <mutex>
 
+#include "tc_common.cuh"
 #include "vt_internal.h"
 
 namespace vt {
@@ -83,9 +85,13 @@ struct vt_tracker {
     __nv_bfloat16 *px_hi = nullptr, *px_lo = nullptr, *pz_hi = nullptr, *pz_lo = nullptr, *ln_hi = nullptr, *ln_lo = nullptr, *att_hi = nullptr,
                   *att_lo = nullptr, *hid_hi = nullptr, *hid_lo = nullptr, *yf_hi = nullptr, *yf_lo = nullptr;
     __nv_bfloat16 *q_hi = nullptr, *q_lo = nullptr, *k_hi = nullptr, *k_lo = nullptr, *vt_hi = nullptr, *vt_lo = nullptr;
+    __nv_bfloat16 *zln_hi = nullptr, *zln_lo = nullptr;  // LN1 (block 0) of the template tokens, [B][64][D], computed at init
+    bool fuse_ln = false;       // LayerNorm fused into the producing GEMM's epilogue (cluster of D / 64 CTAs)
+    bool pdl = true;            // programmatic dependent launch along the kernel chain
     bool tc_attention = false;  // head_dim == 64
     TcAttentionPlan plan_att;
     int* d_tc_err = nullptr;
+    unsigned long long* d_trace = nullptr;  // VT_B200_TRACE=1: device timeline of the chain (vt_tracker_debug_trace)
     TcGemmPlan plan_patch_x, plan_patch_z, plan_head;
     struct BlockPlans {
         TcGemmPlan qkv, proj, fc1, fc2;
@@ -176,12 +182,20 @@ static vt_status load_weights(vt_tracker* t, const char* path) {
     return VT_OK;
 }
 
-__global__ void gather_template_kernel(float* __restrict__ X, const float* __restrict__ Zemb, const int32_t* __restrict__ slots, int D) {
+// template tokens (fixed since init) -> rows 0..63 of every target's sequence: residual stream X and, on the fused-LN
+// tensor-core path, their block-0 LN1 as the bf16 split A operand of the first QKV GEMM
+__global__ void gather_template_kernel(float* __restrict__ X, const float* __restrict__ Zemb, const int32_t* __restrict__ slots, int D,
+                                       uint32_t* __restrict__ ln_hi, uint32_t* __restrict__ ln_lo, const uint32_t* __restrict__ zln_hi,
+                                       const uint32_t* __restrict__ zln_lo) {
+    tc::pdl_wait();
+    tc::pdl_launch_dependents();
     const int bi = blockIdx.y;
     const int n = kNTz * D;
-    const float* src = Zemb + (size_t)slots[bi] * n;
-    float* dst = X + (size_t)bi * kNTok * D;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+    const size_t so = (size_t)slots[bi] * n, xo = (size_t)bi * kNTok * D;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        X[xo + i] = Zemb[so + i];
+        if (ln_hi && i < n / 2) ln_hi[xo / 2 + i] = zln_hi[so / 2 + i], ln_lo[xo / 2 + i] = zln_lo[so / 2 + i];
+    }
 }
 
 static GemmArgs gemm_args(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc, int M, int N, int K) {
@@ -215,7 +229,9 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_PRE], s, ev_flags));
     {
         dim3 grid((kNTz * D + 255) / 256, n);
-        gather_template_kernel<<<grid, 256, 0, s>>>(t->X, t->Zemb, t->d_slots, D);
+        const bool f = t->fuse_ln;
+        gather_template_kernel<<<grid, 256, 0, s>>>(t->X, t->Zemb, t->d_slots, D, f ? (uint32_t*)t->ln_hi : nullptr, (uint32_t*)t->ln_lo,
+                                                    (const uint32_t*)t->zln_hi, (const uint32_t*)t->zln_lo);
         VT_LAUNCH(cudaGetLastError());
     }
     const int M = n * kNTok;
@@ -264,27 +280,27 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     } else {
         // ---------------- tensor-core path: tcgen05 GEMMs fed by TMA, bf16 (x3 split) operands, fp32 TMEM accumulators ----------------
         const int ns = t->nsplit;
-        VT_LAUNCH(tc_gemm_launch(t->plan_patch_x, n * kNTx, ns, s));
+        const bool pdl = t->pdl && !t->debug_capture, fuse = t->fuse_ln;
+        VT_LAUNCH(tc_gemm_launch(t->plan_patch_x, n * kNTx, ns, s, pdl));  // fused: + LN1 of block 0 for the search rows
         if (t->debug_capture) VT_CUDA(cudaMemcpyAsync(t->d_dbg, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
         for (int l = 0; l < t->depth; ++l) {
             const BlockW& b = t->blk[l];
             const vt_tracker::BlockPlans& p = t->plans[l];
-            VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s));
-            VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s));
+            if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
+            VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s, pdl));
             if (t->tc_attention)
-                VT_LAUNCH(tc_attention_launch(t->plan_att, t->att_hi, t->att_lo, n, D, t->heads, ns, t->d_tc_err, s));
+                VT_LAUNCH(tc_attention_launch(t->plan_att, t->att_hi, t->att_lo, n, D, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace));
             else
                 VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
-            VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s));
-            VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s));
-            VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s));
-            VT_LAUNCH(tc_gemm_launch(p.fc2, M, ns, s));
+            VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention));  // fused: + LN2
+            if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
+            VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s, pdl));
+            VT_LAUNCH(tc_gemm_launch(p.fc2, M, ns, s, pdl));  // fused: + LN1 of the next block / the final LN of the search rows
             if (t->debug_capture)
                 VT_CUDA(cudaMemcpyAsync(t->d_dbg + (size_t)(l + 1) * t->maxT * kNTok * D, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
         }
-        VT_LAUNCH(launch_layernorm(t->X, D, t->lnf_g, t->lnf_b, t->Yf, D, n * kNTx, D, kNTx, kNTok, kNTz, s));  // fp32 copy for diagnostics
-        VT_LAUNCH(launch_layernorm_split(t->X, D, t->lnf_g, t->lnf_b, t->yf_hi, t->yf_lo, n * kNTx, D, kNTx, kNTok, kNTz, s));
-        VT_LAUNCH(tc_gemm_launch(t->plan_head, n * kNTx, ns, s));
+        if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, t->lnf_g, t->lnf_b, t->yf_hi, t->yf_lo, n * kNTx, D, kNTx, kNTok, kNTz, s, pdl));
+        VT_LAUNCH(tc_gemm_launch(t->plan_head, n * kNTx, ns, s, pdl));
     }
     if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_VIT], s, ev_flags));
     VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, s));
@@ -564,7 +580,7 @@ void vt_tracker_destroy(vt_tracker* t) {
     void* dev[] = {t->d_weights, t->d_lut, t->d_hann, t->d_frame, t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
                    t->patches_x, t->patches_z, t->Zemb, t->X, t->QKV, t->ATT, t->HID, t->Yf, t->H1, t->d_dbg,
                    t->w_hi, t->w_lo, t->px_hi, t->px_lo, t->pz_hi, t->pz_lo, t->ln_hi, t->ln_lo, t->att_hi, t->att_lo,
-                   t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->d_tc_err, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo};
+                   t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->d_tc_err, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, t->zln_hi, t->zln_lo, t->d_trace};
     for (void* p : dev)
         if (p) cudaFree(p);
     if (t->h_stage) cudaFreeHost(t->h_stage);
@@ -666,6 +682,8 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             return fail(VT_ERR_WEIGHTS);
         }
         VT_TRY(tc_gemm_setup());
+        t->fuse_ln = D / 64 <= 8 && !getenv("VT_B200_NO_FUSE_LN");
+        t->pdl = !getenv("VT_B200_NO_PDL");
         const size_t nw = t->n_weights;
         VT_TRY(cudaMalloc(&t->w_hi, nw * 2)); VT_TRY(cudaMalloc(&t->w_lo, nw * 2));
         VT_TRY(launch_split_bf16(t->d_weights, t->w_hi, t->w_lo, nw, t->stream));
@@ -679,6 +697,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         VT_TRY(balloc(&t->px_hi, &t->px_lo, B * kNTx * kPatchK));
         VT_TRY(balloc(&t->pz_hi, &t->pz_lo, (size_t)128 * kPatchK));  // one 128-row tile; rows 64..127 stay zero
         VT_TRY(balloc(&t->ln_hi, &t->ln_lo, B * kNTok * D));
+        VT_TRY(balloc(&t->zln_hi, &t->zln_lo, B * kNTz * D));
         VT_TRY(balloc(&t->att_hi, &t->att_lo, B * kNTok * D));
         VT_TRY(balloc(&t->hid_hi, &t->hid_lo, B * kNTok * Hd));
         VT_TRY(balloc(&t->yf_hi, &t->yf_lo, B * kNTx * D));
@@ -703,6 +722,10 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             TcGemmArgs& a = t->plan_patch_x.args;
             a.bias = t->patch_b, a.pos = t->pos_x, a.pos_rows = kNTx, a.C = t->X, a.ldc = D;
             a.c_rows_in = kNTx, a.c_rows_stride = kNTok, a.c_row_off = kNTz;
+            if (t->fuse_ln) {  // LN1 of block 0 for the search rows, straight into the first QKV GEMM's A operand
+                a.ln_g = t->blk[0].ln1_g, a.ln_b = t->blk[0].ln1_b, a.ln_hi = t->ln_hi, a.ln_lo = t->ln_lo;
+                a.ln_rows_in = kNTx, a.ln_rows_stride = kNTok, a.ln_row_off = kNTz, a.ln_skip = 0;
+            }
         }
         // patch embed (template, at init): C is set per target
         ok &= tc_plan_init(&t->plan_patch_z, t->pz_hi, t->pz_lo, 128, whi(t->patch_w), wlo(t->patch_w), (int)D, kPatchK, 0, 0);
@@ -724,10 +747,20 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             }
             ok &= tc_plan_init(&p.proj, t->att_hi, t->att_lo, rows, whi(b.proj_w), wlo(b.proj_w), (int)D, (int)D, 0, 0);
             p.proj.args.bias = b.proj_b, p.proj.args.C = t->X, p.proj.args.ldc = D, p.proj.args.residual = 1;
+            if (t->fuse_ln) p.proj.args.ln_g = b.ln2_g, p.proj.args.ln_b = b.ln2_b, p.proj.args.ln_hi = t->ln_hi, p.proj.args.ln_lo = t->ln_lo;
             ok &= tc_plan_init(&p.fc1, t->ln_hi, t->ln_lo, rows, whi(b.fc1_w), wlo(b.fc1_w), (int)Hd, (int)D, 0, 0);
             p.fc1.args.bias = b.fc1_b, p.fc1.args.gelu = 1, p.fc1.args.Ohi = t->hid_hi, p.fc1.args.Olo = t->hid_lo, p.fc1.args.ldo = Hd;
             ok &= tc_plan_init(&p.fc2, t->hid_hi, t->hid_lo, rows, whi(b.fc2_w), wlo(b.fc2_w), (int)D, (int)Hd, 0, 0);
             p.fc2.args.bias = b.fc2_b, p.fc2.args.C = t->X, p.fc2.args.ldc = D, p.fc2.args.residual = 1;
+            if (t->fuse_ln) {
+                TcGemmArgs& a = p.fc2.args;
+                if (l + 1 < t->depth) {
+                    a.ln_g = t->blk[l + 1].ln1_g, a.ln_b = t->blk[l + 1].ln1_b, a.ln_hi = t->ln_hi, a.ln_lo = t->ln_lo;
+                } else {  // final LN, search rows only -> the head conv's [B,16,16,D] grid
+                    a.ln_g = t->lnf_g, a.ln_b = t->lnf_b, a.ln_hi = t->yf_hi, a.ln_lo = t->yf_lo;
+                    a.ln_rows_in = kNTok, a.ln_rows_stride = kNTx, a.ln_row_off = -kNTz, a.ln_skip = kNTz;
+                }
+            }
         }
         // 3x3 head conv: A gathered by TMA from the [B,16,16,D] final-LN grid (zero fill = zero padding), weights [C][tap][D]
         ok &= tc_plan_init(&t->plan_head, t->yf_hi, t->yf_lo, 0, whi(t->h1_w), wlo(t->h1_w), (int)C, (int)(9 * D), (int)D, (int)B);
@@ -735,6 +768,17 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         if (!ok) return fail(VT_ERR_CUDA);
         for (TcGemmPlan* p : {&t->plan_patch_x, &t->plan_patch_z, &t->plan_head}) p->args.err = t->d_tc_err;
         for (auto& p : t->plans) p.qkv.args.err = p.proj.args.err = p.fc1.args.err = p.fc2.args.err = t->d_tc_err;
+        if (getenv("VT_B200_TRACE")) {
+            VT_TRY(cudaMalloc(&t->d_trace, tc::kTraceWords * 8));
+            VT_TRY(cudaMemset(t->d_trace, 0, tc::kTraceWords * 8));
+            t->plan_patch_x.args.trace = t->plan_head.args.trace = t->d_trace;
+            t->plan_patch_x.args.trace_id = 1, t->plan_head.args.trace_id = 6;
+            for (auto& p : t->plans) {
+                p.qkv.args.trace = p.proj.args.trace = p.fc1.args.trace = p.fc2.args.trace = t->d_trace;
+                p.qkv.args.trace_id = 2, p.proj.args.trace_id = 3, p.fc1.args.trace_id = 4, p.fc2.args.trace_id = 5;
+                if (getenv("VT_B200_REP")) p.qkv.args.trace_id = 102, p.fc1.args.trace_id = 104;
+            }
+        }
     }
     t->rect_mirror.assign(B, vt_bbox{0, 0, 0, 0});
     t->inited.assign(B, 0);
@@ -789,7 +833,9 @@ vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, s
     } else {
         TcGemmPlan p = t->plan_patch_z;
         p.args.C = t->Zemb + (size_t)target * kNTz * t->D;
-        VT_LAUNCH(tc_gemm_launch(p, kNTz, t->nsplit, t->stream));
+        VT_LAUNCH(tc_gemm_launch(p, kNTz, t->nsplit, t->stream, false));
+        VT_LAUNCH(launch_layernorm_split(p.args.C, t->D, t->blk[0].ln1_g, t->blk[0].ln1_b, t->zln_hi + (size_t)target * kNTz * t->D,
+                                         t->zln_lo + (size_t)target * kNTz * t->D, kNTz, t->D, 1 << 30, 0, 0, t->stream, false));
     }
     t->kernel_launches += launches;
     VT_CUDA(cudaStreamSynchronize(t->stream));
@@ -907,8 +953,27 @@ vt_status vt_tracker_debug_read(vt_tracker* t, int32_t target, float* search_blo
     }
     if (tokens) {  // final-LN search-token features [256, D] placed at rows 64..319; template rows zero
         memset(tokens, 0, sizeof(float) * kNTok * t->D);
+        if (t->nsplit) {  // the tensor-core path keeps only the bf16 split of the final LN: recompute the fp32 copy from X
+            VT_CUDA(launch_layernorm(t->X, t->D, t->lnf_g, t->lnf_b, t->Yf, t->D, (int)t->active.size() * kNTx, t->D, kNTx, kNTok, kNTz, t->stream));
+            VT_CUDA(cudaStreamSynchronize(t->stream));
+        }
         VT_CUDA(cudaMemcpy(tokens + (size_t)kNTz * t->D, t->Yf + (size_t)bi * kNTx * t->D, sizeof(float) * kNTx * t->D, cudaMemcpyDeviceToHost));
     }
+    return VT_OK;
+}
+
+// Device timeline of the kernels launched since the last call (VT_B200_TRACE=1 at create): out[8 i ..] = {kernel id, t_entry,
+// t_after_pdl_wait, t_end, 4 kernel-specific marks} in ns; returns the number of records (<= max_records) through *n and resets the counter.
+vt_status vt_tracker_debug_trace(vt_tracker* t, unsigned long long* out, int32_t max_records, int32_t* n) {
+    if (!t || !out || !n || !t->d_trace) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    VT_CUDA(cudaStreamSynchronize(t->stream));
+    unsigned long long cnt = 0;
+    VT_CUDA(cudaMemcpy(&cnt, t->d_trace, 8, cudaMemcpyDeviceToHost));
+    const int32_t k = (int32_t)std::min<unsigned long long>(std::min<unsigned long long>(cnt, 2048), (unsigned long long)std::max(max_records, 0));
+    if (k > 0) VT_CUDA(cudaMemcpy(out, t->d_trace + 1, (size_t)k * 64, cudaMemcpyDeviceToHost));
+    VT_CUDA(cudaMemset(t->d_trace, 0, 8));
+    *n = k;
     return VT_OK;
 }
 

@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
                                                               const float* __restrict__ b, __nv_bfloat16* __restrict__ hi,
                                                               __nv_bfloat16* __restrict__ lo, int M, int D, int rows_in, int rows_stride,
                                                               int row_off) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (m >= M) return;
     const float* r = x + (int64_t)map_row(m, rows_in, rows_stride, row_off) * ldx;
@@ -215,10 +217,9 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
 }
 
 cudaError_t launch_layernorm_split(const float* x, int64_t ldx, const float* g, const float* b, __nv_bfloat16* hi, __nv_bfloat16* lo, int M,
-                                   int D, int rows_in, int rows_stride, int row_off, cudaStream_t s) {
+                                   int D, int rows_in, int rows_stride, int row_off, cudaStream_t s, bool pdl) {
     if (M <= 0) return cudaSuccess;
-    layernorm_split_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ldx, g, b, hi, lo, M, D, rows_in, rows_stride, row_off);
-    return cudaGetLastError();
+    return launch_ex(layernorm_split_kernel, dim3((M + 7) / 8), dim3(256), 0, s, pdl, 1, x, ldx, g, b, hi, lo, M, D, rows_in, rows_stride, row_off);
 }
 
 // ------------------------------------------------------------------------------------------------

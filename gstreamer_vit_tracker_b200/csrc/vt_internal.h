@@ -34,6 +34,28 @@ void set_error(const char* fmt, ...);
         }                                                                                          \
     } while (0)
 
+// Launch with optional programmatic dependent launch (the kernel calls griddepcontrol.wait before touching anything the
+// preceding kernel of the stream wrote) and an optional thread-block cluster along x.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster_x, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = attr, cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- TimingStats, src/timing_stats.rs:3-60 (same window, same arithmetic) -------------------------
 template <typename T>
 struct Ring {
@@ -138,7 +160,7 @@ cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* g, const 
                              int rows_in, int rows_stride, int row_off, cudaStream_t s);
 // LayerNorm whose output is written as a bf16 (hi, lo) split [M, D] (dense rows) for the tensor-core GEMMs
 cudaError_t launch_layernorm_split(const float* x, int64_t ldx, const float* g, const float* b, __nv_bfloat16* hi, __nv_bfloat16* lo, int M,
-                                   int D, int rows_in, int rows_stride, int row_off, cudaStream_t s);
+                                   int D, int rows_in, int rows_stride, int row_off, cudaStream_t s, bool pdl = false);
 // qkv: [B*320, 3D]; out: [B*320, D] fp32 (nullable) and/or bf16 split (nullable)
 cudaError_t launch_attention(const float* qkv, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int B, int D, int heads,
                              cudaStream_t s);
@@ -163,7 +185,15 @@ struct TcGemmArgs {
     int qkv_heads;            // 0 = off
     __nv_bfloat16 *Qhi, *Qlo, *Khi, *Klo;    // [B*heads][320][64]
     __nv_bfloat16 *Vthi, *Vtlo;              // [B*heads][64][320]  (V transposed: keys contiguous = K-major B operand of P*V)
+    // LayerNorm of the full output row fused into the epilogue (cluster of N / 64 CTAs, gemm_tc.cu): y = LN(row) * g + b written
+    // as a bf16 split to row (m / ln_rows_in) * ln_rows_stride + ln_row_off + m % ln_rows_in of ln_hi / ln_lo ([rows][N]);
+    // rows with m % ln_rows_in < ln_skip are not written
+    const float *ln_g, *ln_b; // null = off
+    __nv_bfloat16 *ln_hi, *ln_lo;
+    int ln_rows_in, ln_rows_stride, ln_row_off, ln_skip;
     int* err;                 // set to 1 if a bounded mbarrier wait expired
+    unsigned long long* trace; // device timeline buffer (diagnostics) or null
+    int trace_id;
 };
 struct TcGemmPlan {
     CUtensorMap mAhi, mAlo, mBhi, mBlo;
@@ -172,7 +202,7 @@ struct TcGemmPlan {
 bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, uint64_t a_rows, const __nv_bfloat16* Whi,
                   const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch);
 cudaError_t tc_gemm_setup();
-cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s);
+cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl);
 struct TcAttentionPlan {
     CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo;
 };
@@ -180,7 +210,7 @@ bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const 
                             const __nv_bfloat16* Vthi, const __nv_bfloat16* Vtlo, int batch_heads);
 cudaError_t tc_attention_setup();
 cudaError_t tc_attention_launch(const TcAttentionPlan& p, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int B, int D, int heads, int nsplit,
-                                int* err, cudaStream_t s);
+                                int* err, cudaStream_t s, bool pdl, unsigned long long* trace = nullptr);
 cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t s);
 
 }  // namespace vt

@@ -134,6 +134,10 @@ int32_t vt_tracker_model_dim(const vt_tracker* t, int32_t which); /* 0 D, 1 dept
 /* token features [320*D] after the embeddings (which = 0) or after block `which` (1..depth).  Needs
  * cfg.reserved[0] = 1 at create time (captures one copy per block; disables graph replay). */
 vt_status vt_tracker_debug_tokens(vt_tracker* t, int32_t target, int32_t which, float* out);
+/* Device timeline of the tensor-core kernels launched since the previous call (set VT_B200_TRACE=1 in the environment before
+ * vt_tracker_create; VT_ERR_INVALID otherwise): out[8 i ..] = {kernel id, t_entry, t_after_dependency_wait, t_end, 4 kernel-specific
+ * marks} in ns of the GPU's global timer; *n = records written (<= max_records).  ≙ the finer per-stage timers of src/pipeline_ir.rs:126-208. */
+vt_status vt_tracker_debug_trace(vt_tracker* t, unsigned long long* out, int32_t max_records, int32_t* n);
 /* the handle's CUDA stream (cudaStream_t) so that callers can time on the launching stream, and a stream sync */
 void* vt_tracker_stream(vt_tracker* t);
 vt_status vt_tracker_sync(vt_tracker* t);
