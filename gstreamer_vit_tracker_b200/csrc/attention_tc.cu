@@ -1,14 +1,17 @@
 // attention_tc.cu — joint attention over the 320-token sequence on tcgen05 tensor cores (head_dim 64).
 //
-// One CTA (512 threads) per (128-query tile, head, target):
+// One CTA (16 softmax warps + 1 control warp) per (128-query tile, head, target):
 //   TMA        Q tile [128 x 64], K [320 x 64] and V^T [64 x 320] (bf16 hi/lo parts, 128B swizzle) -> shared memory
 //   tcgen05    S[128 x 320] = Q K^T  -> TMEM columns 0..319 (two UMMAs per K-step: N = 256 and N = 64)
+//   control    warp 16 issues every TMA load and every UMMA (one elected lane) and owns the TMEM allocation, so that no softmax
+//              warp ever serialises MMA issue with its share of the exp work; chunks are handed over through mbarriers
+//              (p_full: one arrival per softmax warp, p_free: tcgen05.commit) — there is no CTA-wide barrier in the chunk loop
 //   softmax    FOUR threads per query row (warp w reads TMEM lane quarter w % 4; column group g = w / 4): the exp work is what
-//              bounds this kernel, so it is spread over all 16 warps.  Per 64-key chunk thread (row, g) owns 16 keys:
+//              bounds this kernel, so it is spread over 16 warps.  Per 64-key chunk thread (row, g) owns 16 keys:
 //              tcgen05.ld.x16 -> ex2(s * k - max * k) -> bf16 (hi, lo) split -> 2 x 16 B stores into the 128B-swizzled K-major
 //              P tile (double buffered); row max / row sum partials are combined through shared memory in a fixed order
 //   tcgen05    O[128 x 64] += P_chunk V_chunk -> TMEM columns 320..383, overlapped with the next chunk's softmax
-//   epilogue   O / sum -> bf16 (hi, lo) rows of the proj GEMM's A operand (16 columns per thread).
+//   epilogue   O / sum -> bf16 (hi, lo) tile staged in shared memory -> TMA tile store into the proj GEMM's A operand.
 // The P buffers alias the Q/K staging area once S is complete, which keeps the CTA at ~192 KB of shared memory.
 #include "tc_common.cuh"
 #include "vt_internal.h"
@@ -27,8 +30,9 @@ constexpr int kVBytes = kDh * kNTok * 2;          // 40 KB (5 blocks of [64 x 64
 constexpr int kPBytes = kQTile * kKeyChunk * 2;   // 16 KB
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColO = 320;
-constexpr int kAttThreads = 512;
-constexpr int kColGroups = kAttThreads / kQTile;  // 4 threads per query row
+constexpr int kSoftmaxWarps = 16, kSoftmaxThreads = kSoftmaxWarps * 32;
+constexpr int kAttThreads = kSoftmaxThreads + 32;     // + one control warp (TMA, MMA issue, TMEM alloc)
+constexpr int kColGroups = kSoftmaxThreads / kQTile;  // 4 threads per query row
 constexpr int kKeysPerThread = kKeyChunk / kColGroups;  // 16 keys of every chunk
 
 template <int NSPLIT>
@@ -41,16 +45,18 @@ struct AttSmem {
     static constexpr int kTotal = kRegion1 + kV + 1024;
 };
 
+// named barrier over the 16 softmax warps only (the control warp never joins it)
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxThreads) : "memory"); }
+
 template <int NSPLIT>
 __global__ void __launch_bounds__(kAttThreads, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constant__ CUtensorMap mQlo, const __grid_constant__ CUtensorMap mKhi,
-                    const __grid_constant__ CUtensorMap mKlo, const __grid_constant__ CUtensorMap mVhi, const __grid_constant__ CUtensorMap mVlo,
-                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int D, int heads, int* err,
-                    unsigned long long* trace) {
+attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, int heads, int* err, unsigned long long* trace) {
+    const CUtensorMap &mQhi = mp.mQhi, &mQlo = mp.mQlo, &mKhi = mp.mKhi, &mKlo = mp.mKlo, &mVhi = mp.mVhi, &mVlo = mp.mVlo;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_qk, bar_v, bar_s, bar_p[2], bar_o;
+    __shared__ __align__(8) uint64_t bar_qk, bar_v, bar_s, p_full[2], p_free[2], bar_o;
     __shared__ uint32_t tmem_base_s;
     __shared__ float red[kColGroups][kQTile];  // row-max partials, then row-sum partials
+    __shared__ unsigned long long* trace_slot;
     using SM = AttSmem<NSPLIT>;
     constexpr int P = SM::kParts;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -60,23 +66,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_const
     uint8_t* sV = smem + SM::kRegion1;        // [P][5 blocks][64 x 128B]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool ctrl = warp == kSoftmaxWarps;  // warp 16: TMA + MMA issue (one elected lane), TMEM alloc / dealloc
     const int row = (warp & 3) * 32 + lane;   // query row inside the tile = TMEM lane
-    const int g = warp >> 2;                  // column group
+    const int g = (warp >> 2) & 3;            // column group
     const int q0 = blockIdx.x * kQTile, h = blockIdx.y, b = blockIdx.z;
     const int bh = b * heads + h;
     const bool q_ok = q0 + row < kNTok;       // uniform per warp (320 = 2 * 128 + 64)
     bool ok = true;
-    __shared__ unsigned long long* trace_slot;
     TraceRec tr;
     tr.begin(&trace_slot, trace, 10);
 
     if (tid == 0) {
-        tma_prefetch_desc(&mQhi), tma_prefetch_desc(&mKhi), tma_prefetch_desc(&mVhi);
-        if (P == 2) tma_prefetch_desc(&mQlo), tma_prefetch_desc(&mKlo), tma_prefetch_desc(&mVlo);
-        mbar_init(&bar_qk, 1), mbar_init(&bar_v, 1), mbar_init(&bar_s, 1), mbar_init(&bar_p[0], 1), mbar_init(&bar_p[1], 1), mbar_init(&bar_o, 1);
+        mbar_init(&bar_qk, 1), mbar_init(&bar_v, 1), mbar_init(&bar_s, 1), mbar_init(&bar_o, 1);
+        mbar_init(&p_full[0], kSoftmaxWarps), mbar_init(&p_full[1], kSoftmaxWarps), mbar_init(&p_free[0], 1), mbar_init(&p_free[1], 1);
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (ctrl) {
+        if (lane == 0) {
+            tma_prefetch_desc(&mQhi), tma_prefetch_desc(&mKhi), tma_prefetch_desc(&mVhi), tma_prefetch_desc(&mp.mOhi);
+            if (P == 2) tma_prefetch_desc(&mQlo), tma_prefetch_desc(&mKlo), tma_prefetch_desc(&mVlo), tma_prefetch_desc(&mp.mOlo);
+        }
         tmem_alloc(&tmem_base_s, kTmemCols);
         tmem_relinquish();
     }
@@ -89,155 +98,162 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_const
     if (tid == 0) tr.mark(2);
     pdl_launch_dependents();
 
-    if (tid == 0) {  // ---- TMA: Q + K on one barrier, V^T on another (only needed after the softmax of the first chunk)
-        mbar_arrive_expect_tx(&bar_qk, P * (kQBytes + kKBytes));
-        tma_load_3d(sQ, &mQhi, &bar_qk, 0, q0, bh);
-        if (P == 2) tma_load_3d(sQ + kQBytes, &mQlo, &bar_qk, 0, q0, bh);
-        for (int c = 0; c < kNChunks; ++c) {
-            tma_load_3d(sK + c * kKeyChunk * 128, &mKhi, &bar_qk, 0, c * kKeyChunk, bh);
-            if (P == 2) tma_load_3d(sK + kKBytes + c * kKeyChunk * 128, &mKlo, &bar_qk, 0, c * kKeyChunk, bh);
-        }
-        mbar_arrive_expect_tx(&bar_v, P * kVBytes);
-        for (int c = 0; c < kNChunks; ++c) {
-            tma_load_3d(sV + c * (kDh * 128), &mVhi, &bar_v, c * kKeyChunk, 0, bh);
-            if (P == 2) tma_load_3d(sV + kVBytes + c * (kDh * 128), &mVlo, &bar_v, c * kKeyChunk, 0, bh);
-        }
-    }
-    if (tid == 32) {  // ---- S = Q K^T
-        ok &= mbar_wait(&bar_qk, 0);
-        tcgen05_fence_after();
-        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
-        constexpr uint32_t idesc256 = umma_idesc_bf16(kQTile, 256), idesc64 = umma_idesc_bf16(kQTile, 64);
-#pragma unroll
-        for (int k = 0; k < kDh / 16; ++k) {
-            const uint32_t koff = k * 32;
-            const uint64_t qh = umma_desc_sw128(aQ + koff), kh0 = umma_desc_sw128(aK + koff), kh1 = umma_desc_sw128(aK + 256 * 128 + koff);
-            umma_bf16(tmem, qh, kh0, idesc256, k != 0);
-            umma_bf16(tmem + 256, qh, kh1, idesc64, k != 0);
-            if (NSPLIT == 3) {
-                const uint64_t ql = umma_desc_sw128(aQ + kQBytes + koff);
-                const uint64_t kl0 = umma_desc_sw128(aK + kKBytes + koff), kl1 = umma_desc_sw128(aK + kKBytes + 256 * 128 + koff);
-                umma_bf16(tmem, qh, kl0, idesc256, 1);
-                umma_bf16(tmem + 256, qh, kl1, idesc64, 1);
-                umma_bf16(tmem, ql, kh0, idesc256, 1);
-                umma_bf16(tmem + 256, ql, kh1, idesc64, 1);
+    if (ctrl) {
+        if (lane == 0) {
+            // ---- TMA: Q + K on one barrier, V^T on another (only needed after the softmax of the first chunk)
+            mbar_arrive_expect_tx(&bar_qk, P * (kQBytes + kKBytes));
+            tma_load_3d(sQ, &mQhi, &bar_qk, 0, q0, bh);
+            if (P == 2) tma_load_3d(sQ + kQBytes, &mQlo, &bar_qk, 0, q0, bh);
+            for (int c = 0; c < kNChunks; ++c) {
+                tma_load_3d(sK + c * kKeyChunk * 128, &mKhi, &bar_qk, 0, c * kKeyChunk, bh);
+                if (P == 2) tma_load_3d(sK + kKBytes + c * kKeyChunk * 128, &mKlo, &bar_qk, 0, c * kKeyChunk, bh);
             }
-        }
-        umma_commit(&bar_s);
-    }
-    __syncwarp();
-
-    // ---- softmax: thread (row, g) owns keys 64 c + 16 g .. + 15 of every chunk c
-    ok &= mbar_wait(&bar_s, 0);
-    tcgen05_fence_after();
-    if (tid == 0) tr.mark(4);
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const float k2 = 1.4426950408889634f / sqrtf((float)kDh);  // scale * log2(e)
-    float mx = -INFINITY;
-    if (q_ok) {
-#pragma unroll
-        for (int c = 0; c < kNChunks; ++c) {
-            float v[16];
-            tmem_ld_32x16(lane_addr + c * kKeyChunk + g * kKeysPerThread, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j]);
-        }
-    }
-    red[g][row] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(red[0][row], red[1][row]), fmaxf(red[2][row], red[3][row]));
-    if (tid == 0) tr.mark(5);
-    const float mk = mx * k2;
-    float sum = 0.f;
-    for (int c = 0; c < kNChunks; ++c) {
-        const int buf = c & 1;
-        if (c >= 2) ok &= mbar_wait(&bar_p[buf], ((c >> 1) - 1) & 1);  // the UMMAs that read this buffer are done
-        if (q_ok) {
-            float v[16];
-            tmem_ld_32x16(lane_addr + c * kKeyChunk + g * kKeysPerThread, v);
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                const float e0 = ex2_approx(fmaf(v[j], k2, -mk)), e1 = ex2_approx(fmaf(v[j + 1], k2, -mk));
-                sum += e0;
-                sum += e1;
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(e0, h0, l0), split_bf16(e1, h1, l1);
-                hi[j >> 1] = pack_bf16(h0, h1), lo[j >> 1] = pack_bf16(l0, l1);
+            mbar_arrive_expect_tx(&bar_v, P * kVBytes);
+            for (int c = 0; c < kNChunks; ++c) {
+                tma_load_3d(sV + c * (kDh * 128), &mVhi, &bar_v, c * kKeyChunk, 0, bh);
+                if (P == 2) tma_load_3d(sV + kVBytes + c * (kDh * 128), &mVlo, &bar_v, c * kKeyChunk, 0, bh);
             }
-            uint8_t* pb = sP + buf * (P * kPBytes) + row * 128;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {  // 16-byte chunk index within the 128-byte row, XOR-swizzled with the row (Swizzle<3,4,3>)
-                const int off = (((2 * g + j) ^ (row & 7)) << 4);
-                *reinterpret_cast<uint4*>(pb + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                if (P == 2) *reinterpret_cast<uint4*>(pb + kPBytes + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-        }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        tcgen05_fence_before();
-        __syncthreads();
-        if (tid == 0 && c == 0) tr.mark(6);
-        if (tid == 32) {  // ---- O += P_c V_c
+            // ---- S = Q K^T
+            ok &= mbar_wait(&bar_qk, 0);
             tcgen05_fence_after();
-            if (c == 0) ok &= mbar_wait(&bar_v, 0);
-            const uint32_t aP = smem_u32(sP + buf * (P * kPBytes)), aV = smem_u32(sV + c * (kDh * 128));
-            constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kDh);
+            const uint64_t dQ = umma_desc_sw128(smem_u32(sQ)), dK = umma_desc_sw128(smem_u32(sK));
+            constexpr uint32_t idesc256 = umma_idesc_bf16(kQTile, 256), idesc64 = umma_idesc_bf16(kQTile, 64);
+            constexpr uint64_t kLoQ = kQBytes >> 4, kLoK = kKBytes >> 4, kK256 = (256 * 128) >> 4;  // descriptor address units (16 B)
 #pragma unroll
-            for (int k = 0; k < kKeyChunk / 16; ++k) {
-                const uint32_t koff = k * 32;
-                const uint64_t ph = umma_desc_sw128(aP + koff), vh = umma_desc_sw128(aV + koff);
-                umma_bf16(tmem + kColO, ph, vh, idesc, (c | k) != 0);
+            for (int k = 0; k < kDh / 16; ++k) {
+                const uint64_t qh = dQ + 2 * k, kh0 = dK + 2 * k, kh1 = kh0 + kK256;
+                umma_bf16(tmem, qh, kh0, idesc256, k != 0);
+                umma_bf16(tmem + 256, qh, kh1, idesc64, k != 0);
                 if (NSPLIT == 3) {
-                    umma_bf16(tmem + kColO, ph, umma_desc_sw128(aV + kVBytes + koff), idesc, 1);
-                    umma_bf16(tmem + kColO, umma_desc_sw128(aP + kPBytes + koff), vh, idesc, 1);
+                    umma_bf16(tmem, qh, kh0 + kLoK, idesc256, 1);
+                    umma_bf16(tmem + 256, qh, kh1 + kLoK, idesc64, 1);
+                    umma_bf16(tmem, qh + kLoQ, kh0, idesc256, 1);
+                    umma_bf16(tmem + 256, qh + kLoQ, kh1, idesc64, 1);
                 }
             }
-            umma_commit(&bar_p[buf]);
-            if (c == kNChunks - 1) umma_commit(&bar_o);
+            umma_commit(&bar_s);
+            // ---- O += P_c V_c as the softmax warps hand the chunks over
+            const uint64_t dP = umma_desc_sw128(smem_u32(sP)), dV = umma_desc_sw128(smem_u32(sV));
+            constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kDh);
+            constexpr uint64_t kLoP = kPBytes >> 4, kLoV = kVBytes >> 4, kBufP = (uint64_t)(P * kPBytes) >> 4, kBlkV = (kDh * 128) >> 4;
+            ok &= mbar_wait(&bar_v, 0);
+            for (int c = 0; c < kNChunks; ++c) {
+                const int buf = c & 1;
+                ok &= mbar_wait(&p_full[buf], (c >> 1) & 1);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int k = 0; k < kKeyChunk / 16; ++k) {
+                    const uint64_t ph = dP + buf * kBufP + 2 * k, vh = dV + c * kBlkV + 2 * k;
+                    umma_bf16(tmem + kColO, ph, vh, idesc, (c | k) != 0);
+                    if (NSPLIT == 3) {
+                        umma_bf16(tmem + kColO, ph, vh + kLoV, idesc, 1);
+                        umma_bf16(tmem + kColO, ph + kLoP, vh, idesc, 1);
+                    }
+                }
+                umma_commit(&p_free[buf]);
+            }
+            umma_commit(&bar_o);
         }
         __syncwarp();
-    }
-    if (tid == 0) tr.mark(7);
-    // the row-max partials were consumed before the first chunk barrier: reuse the array for the row sums
-    red[g][row] = sum;
-    __syncthreads();
-    sum = (red[0][row] + red[1][row]) + (red[2][row] + red[3][row]);
-
-    // ---- epilogue: O / sum -> bf16 split rows [token][h*64 + d], 16 columns per thread
-    ok &= mbar_wait(&bar_o, 0);
-    tcgen05_fence_after();
-    if (q_ok) {
-        const float inv = 1.f / sum;
-        float v[16];
-        tmem_ld_32x16(lane_addr + kColO + g * 16, v);
-        uint32_t hi[8], lo[8];
+    } else {
+        // ---- softmax: thread (row, g) owns keys 64 c + 16 g .. + 15 of every chunk c
+        ok &= mbar_wait(&bar_s, 0);
+        tcgen05_fence_after();
+        if (tid == 0) tr.mark(4);
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const float k2 = 1.4426950408889634f / sqrtf((float)kDh);  // scale * log2(e)
+        float mx = -INFINITY;
+        if (q_ok) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[j] * inv, h0, l0), split_bf16(v[j + 1] * inv, h1, l1);
-            hi[j >> 1] = pack_bf16(h0, h1), lo[j >> 1] = pack_bf16(l0, l1);
+            for (int c = 0; c < kNChunks; ++c) {
+                float v[16];
+                tmem_ld_32x16(lane_addr + c * kKeyChunk + g * kKeysPerThread, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j]);
+            }
         }
-        const int64_t idx = ((int64_t)b * kNTok + q0 + row) * D + h * kDh + g * 16;
-        uint4* oh = reinterpret_cast<uint4*>(out_hi + idx);
-        uint4* ol = reinterpret_cast<uint4*>(out_lo + idx);
+        red[g][row] = mx;
+        softmax_bar_sync();  // also: every softmax thread has finished reading Q/K-phase data before P overwrites that memory
+        mx = fmaxf(fmaxf(red[0][row], red[1][row]), fmaxf(red[2][row], red[3][row]));
+        if (tid == 0) tr.mark(5);
+        const float mk = mx * k2;
+        float sum = 0.f;
+        for (int c = 0; c < kNChunks; ++c) {
+            const int buf = c & 1;
+            if (c >= 2) ok &= mbar_wait(&p_free[buf], ((c >> 1) - 1) & 1);  // the UMMAs that read this buffer are done
+            if (q_ok) {
+                float v[16];
+                tmem_ld_32x16(lane_addr + c * kKeyChunk + g * kKeysPerThread, v);
+                uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                for (int j = 0; j < 16; j += 2) {
+                    const float e0 = ex2_approx(fmaf(v[j], k2, -mk)), e1 = ex2_approx(fmaf(v[j + 1], k2, -mk));
+                    sum += e0;
+                    sum += e1;
+                    split2_bf16(e0, e1, hi[j >> 1], lo[j >> 1]);
+                }
+                uint8_t* pb = sP + buf * (P * kPBytes) + row * 128;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {  // 16-byte chunk index within the 128-byte row, XOR-swizzled with the row (Swizzle<3,4,3>)
+                    const int off = (((2 * g + j) ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4*>(pb + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    if (P == 2) *reinterpret_cast<uint4*>(pb + kPBytes + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+            }
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[buf]);  // one arrival per softmax warp: no CTA-wide barrier in this loop
+            if (tid == 0 && c == 0) tr.mark(6);
+        }
+        if (tid == 0) tr.mark(7);
+        // the row-max partials were consumed before the first hand-over: reuse the array for the row sums
+        red[g][row] = sum;
+        softmax_bar_sync();
+        sum = (red[0][row] + red[1][row]) + (red[2][row] + red[3][row]);
+
+        // ---- epilogue: O / sum -> bf16 (hi, lo) tile staged in (dead) shared memory, written with TMA tile stores into columns
+        // h*64.. of the proj GEMM's A operand [B][320][D]; query rows >= 320 are clipped by the TMA unit
+        ok &= mbar_wait(&bar_o, 0);
+        tcgen05_fence_after();
+        {
+            const float inv = q_ok ? 1.f / sum : 0.f;
+            float v[16];
+            tmem_ld_32x16(lane_addr + kColO + g * 16, v);
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) split2_bf16(v[j] * inv, v[j + 1] * inv, hi[j >> 1], lo[j >> 1]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int off = row * 128 + (((2 * g + j) ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(smem + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                if (P == 2) *reinterpret_cast<uint4*>(smem + kPBytes + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+        }
+        fence_proxy_async_smem();
+        softmax_bar_sync();
+        if (tid == 0) {
+            for (int k = 0; k < 2; ++k) {  // 64-row boxes (tc_out_map); rows >= 320 are clipped
+                tma_store_4d(&mp.mOhi, smem + k * 8192, h * kDh, q0 + 64 * k, 0, b);
+                if (P == 2) tma_store_4d(&mp.mOlo, smem + kPBytes + k * 8192, h * kDh, q0 + 64 * k, 0, b);
+            }
+            tma_store_commit();
+            tma_store_wait_read();
         }
     }
     if (!ok && err) atomicExch(err, 2);
     tcgen05_fence_before();
     __syncthreads();
     if (tid == 0) tr.mark(3);
-    if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+    if (ctrl) tmem_dealloc(tmem, kTmemCols);
 }
 
 bool tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
 bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const __nv_bfloat16* Qlo, const __nv_bfloat16* Khi, const __nv_bfloat16* Klo,
-                            const __nv_bfloat16* Vthi, const __nv_bfloat16* Vtlo, int batch_heads) {
-    bool ok = true;
+                            const __nv_bfloat16* Vthi, const __nv_bfloat16* Vtlo, int batch_heads, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int D,
+                            int batch) {
+    bool ok = tc_out_map(&p->mOhi, out_hi, 2, D, kNTok, 1, batch) && tc_out_map(&p->mOlo, out_lo, 2, D, kNTok, 1, batch);
     {   // Q, K: [batch*heads][320][64], box {64, rows, 1}
         const uint64_t dims[3] = {kDh, kNTok, (uint64_t)batch_heads}, strides[2] = {kDh * 2, (uint64_t)kDh * 2 * kNTok};
         const uint32_t boxq[3] = {kDh, kQTile, 1}, boxk[3] = {kDh, kKeyChunk, 1};
@@ -258,15 +274,11 @@ cudaError_t tc_attention_setup() {
     return cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem<3>::kTotal);
 }
 
-cudaError_t tc_attention_launch(const TcAttentionPlan& p, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int B, int D, int heads, int nsplit,
-                                int* err, cudaStream_t s, bool pdl, unsigned long long* trace) {
+cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int nsplit, int* err, cudaStream_t s, bool pdl, unsigned long long* trace) {
     if (B <= 0) return cudaSuccess;
     const dim3 grid((kNTok + kQTile - 1) / kQTile, heads, B);
-    if (nsplit == 3)
-        return launch_ex(attention_tc_kernel<3>, grid, dim3(kAttThreads), AttSmem<3>::kTotal, s, pdl, 1, p.mQhi, p.mQlo, p.mKhi, p.mKlo, p.mVhi,
-                         p.mVlo, out_hi, out_lo, D, heads, err, trace);
-    return launch_ex(attention_tc_kernel<1>, grid, dim3(kAttThreads), AttSmem<1>::kTotal, s, pdl, 1, p.mQhi, p.mQlo, p.mKhi, p.mKlo, p.mVhi, p.mVlo,
-                     out_hi, out_lo, D, heads, err, trace);
+    if (nsplit == 3) return launch_ex(attention_tc_kernel<3>, grid, dim3(kAttThreads), AttSmem<3>::kTotal, s, pdl, 1, p, heads, err, trace);
+    return launch_ex(attention_tc_kernel<1>, grid, dim3(kAttThreads), AttSmem<1>::kTotal, s, pdl, 1, p, heads, err, trace);
 }
 
 }  // namespace vt

@@ -3,18 +3,26 @@
 //   C[M,N] = epilogue( A[M,K] * W[N,K]^T + bias )      A, W: bf16 (optionally split hi+lo), accumulate fp32 in TMEM
 //
 // One CTA (512 threads) computes one 128 x 64 output tile:
-//   warp 0 (one elected lane)  TMA producer: cp.async.bulk.tensor 128B-swizzled boxes of A and W into a 4-stage smem ring,
-//                              completion counted on mbarriers (expect_tx);
+//   warp 0 (one elected lane)  TMA producer: cp.async.bulk.tensor 128B-swizzled boxes of A and W into a 3-stage smem ring,
+//                              completion counted on mbarriers (expect_tx); the weight boxes of the first stages are issued
+//                              BEFORE griddepcontrol.wait (they never depend on the preceding kernel), the activation boxes and
+//                              the fp32 residual tile right after it;
 //   warp 1 (one elected lane)  issues tcgen05.mma (UMMA 128x64x16, kind::f16) from smem descriptors into a TMEM accumulator,
 //                              tcgen05.commit releases each stage and finally signals the accumulator;
 //   all 16 warps               epilogue: four threads per accumulator row (tcgen05.ld.x16: warp w reads lane quarter w % 4, columns
-//                              16 (w / 4) ..) -> bias / GELU / ReLU / pos-embed / residual -> fp32 store and/or bf16 (hi, lo) stores
-//                              that feed the next GEMM, optionally LayerNorm of the full row through a cluster exchange.  The
-//                              epilogue is ALU / latency bound, which is why it is spread over 16 warps instead of 4.
+//                              16 (w / 4) ..) -> bias / GELU / ReLU / pos-embed / residual -> the output tile is STAGED IN SHARED
+//                              MEMORY (128B-swizzled, conflict free) and written with TMA tile stores: a thread-per-row epilogue
+//                              that stores straight to global touches 32 different lines per warp instruction and was measured at
+//                              ~9 B/clk per SM (2 us per 32 KB tile); the tile store moves the same bytes in one instruction.
+//                              Optionally LayerNorm of the full row through a cluster exchange (see below).
+// Output rows are addressed as (target, row-in-target) through 4-D tensor maps {cols, rows per target, heads, targets}: a 128-row
+// tile is written as two 64-row boxes (never straddling a target), rows past a target's end are clipped by the TMA unit; the same
+// mechanism scatters Q / K / V^T into the per-(target, head) layout of the attention kernel and drops the template rows of the
+// final LayerNorm.
 //
 // Precision: VT_GEMM_TCGEN05_BF16 issues A_hi*W_hi only; VT_GEMM_TCGEN05_BF16X3 adds A_hi*W_lo + A_lo*W_hi into the same
 // accumulator (error ~2^-17 relative per product), which is what the 1e-3 score / exact-box parity needs; the extra tensor
-// FLOPs are free at these sizes (the step is launch/latency bound).
+// FLOPs are free at these sizes (the step is latency bound).
 // The 3x3 head convolution runs through the same kernel: its A operand is gathered by TMA from the [B,16,16,D] token grid with
 // shifted (possibly negative) coordinates; out-of-bounds elements are zero-filled by the TMA unit = zero padding of the conv.
 #include <stdlib.h>
@@ -29,53 +37,84 @@ namespace vt {
 
 using namespace tc;
 
-constexpr int kTcBM = 128, kTcBN = 64, kTcBK = 64, kTcStages = 4;
+constexpr int kTcBM = 128, kTcBN = 64, kTcBK = 64, kTcStages = 3;
 constexpr int kTileABytes = kTcBM * kTcBK * 2;  // 16 KB, one precision part
 constexpr int kTileBBytes = kTcBN * kTcBK * 2;  //  8 KB
+constexpr int kTileOBytes = kTcBM * kTcBN * 2;  // 16 KB: one bf16 output tile
+constexpr int kTileCBytes = kTcBM * kTcBN * 4;  // 32 KB: the fp32 tile as two 128-byte-wide boxes
 
 template <int NSPLIT>
 struct TcSmem {
     static constexpr int kParts = NSPLIT == 3 ? 2 : 1;
     static constexpr int kStageBytes = kParts * (kTileABytes + kTileBBytes);
-    static constexpr int kTotal = kTcStages * kStageBytes + 1024;  // + alignment slack
+    static constexpr int kPipeBytes = kTcStages * kStageBytes;
+    // after the main loop the pipeline ring is dead and holds the staged output tiles
+    static constexpr int kOffOhi = 0, kOffOlo = kTileOBytes, kOffLnHi = 2 * kTileOBytes, kOffLnLo = 3 * kTileOBytes;
+    static constexpr int kOffC = kPipeBytes;  // fp32 tile: residual in (TMA load during the main loop), C out, in place
+    static constexpr int kTotal = kPipeBytes + kTileCBytes + 1024;  // + alignment slack
+    static_assert(4 * kTileOBytes <= kPipeBytes, "staging must fit in the dead pipeline ring");
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 // LayerNorm fused into the epilogue of the GEMMs that produce the residual stream (patch-embed, proj, FC2): the N / 64 CTAs
-// that hold the column tiles of one 128-row tile form a thread-block cluster; thread t of every CTA owns row t, computes the
-// (sum, M2) of its 64 columns from registers, pushes the pair into every peer's shared memory (st.shared::cluster), and after
-// one cluster barrier combines the partials in rank order (Chan's parallel variance) — every CTA gets bit-identical
-// statistics — normalises its own 64 columns and stores the bf16 (hi, lo) A operand of the next GEMM.
+// that hold the column tiles of one 128-row tile form a thread-block cluster; every thread computes the (sum, M2) of its 16
+// columns from registers, pushes the pair into every peer's shared memory (st.shared::cluster), and after one cluster barrier
+// combines the partials in a fixed order (Chan's parallel variance) — every CTA gets bit-identical statistics — normalises its
+// own columns and stages the bf16 (hi, lo) A operand of the next GEMM for a TMA tile store.
 constexpr int kMaxLnCluster = 8;
-constexpr int kTcThreads = 512;                       // 16 warps: warp w reads TMEM lane quarter w % 4, column group w / 4
-constexpr int kTcColGroups = kTcThreads / kTcBM;      // 4 threads per accumulator row
+constexpr int kTcThreads = 512;                         // 16 warps: warp w reads TMEM lane quarter w % 4, column group w / 4
+constexpr int kTcColGroups = kTcThreads / kTcBM;        // 4 threads per accumulator row
 constexpr int kTcColsPerThread = kTcBN / kTcColGroups;  // 16 columns each
 
-__device__ __forceinline__ void split_store16(const float (&v)[16], __nv_bfloat16* hi_dst, __nv_bfloat16* lo_dst) {
+// 16 fp32 -> bf16 (hi, lo), 32 bytes each, into 128B-swizzled [128 rows][64 cols] staging tiles (chunk = 16-byte unit in the row)
+__device__ __forceinline__ void stage_split16(const float (&v)[16], uint8_t* tile_hi, uint8_t* tile_lo, int row, int g, bool with_lo) {
     uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[j], h0, l0), split_bf16(v[j + 1], h1, l1);
-        hi[j >> 1] = pack_bf16(h0, h1), lo[j >> 1] = pack_bf16(l0, l1);
+    for (int j = 0; j < 16; j += 2) split2_bf16(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int off = row * 128 + (((2 * g + q) ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+        if (with_lo) *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
     }
-    uint4* oh = reinterpret_cast<uint4*>(hi_dst);
-    uint4* ol = reinterpret_cast<uint4*>(lo_dst);
-    oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]), oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]), ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+}
+
+// One staged 128-row tile -> two 64-row TMA boxes.  Row m of the GEMM is row (m % period + row_off) of target
+// (m / period + batch_off); periods are multiples of 64, so a 64-row box never straddles two targets.  Rows past the end of a
+// target are clipped by the TMA unit; a box that would start at a negative row (the template rows the final LayerNorm drops) is
+// skipped — negative start coordinates are an illegal instruction for tile STORES (measured), unlike loads.
+constexpr int kHalfRows = 64, kHalfBytes = kHalfRows * 128;
+struct TileRows {  // (row-in-target, target) of the two 64-row halves of a tile; computed once, before the accumulator wait
+    int t[2], b[2];
+    __device__ __forceinline__ TileRows(int m0, int period, int batch_off) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int mr = m0 + k * kHalfRows;
+            b[k] = mr / period, t[k] = mr - b[k] * period, b[k] += batch_off;
+        }
+    }
+};
+__device__ __forceinline__ void store_tile(const CUtensorMap* m, const uint8_t* smem_src, int c0, const TileRows& r, int row_off, int h) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (r.t[k] + row_off >= 0) tma_store_4d(m, smem_src + k * kHalfBytes, c0, r.t[k] + row_off, h, r.b[k]);
+}
+// V^T: tokens are the innermost coordinate; staged as two [64 d][64 tokens] sub-tiles
+__device__ __forceinline__ void store_tile_vt(const CUtensorMap* m, const uint8_t* smem_src, const TileRows& r, int h) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) tma_store_4d(m, smem_src + k * kHalfBytes, r.t[k], 0, h, r.b[k]);
 }
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo, const __grid_constant__ CUtensorMap mBhi,
-               const __grid_constant__ CUtensorMap mBlo, const TcGemmArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcGemmArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages], accum_bar;
+    __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages], accum_bar, resid_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float2 ln_part[kMaxLnCluster][kTcColGroups][kTcBM];
     __shared__ unsigned long long* trace_slot;
     using SM = TcSmem<NSPLIT>;
+    constexpr bool kLo = NSPLIT == 3;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -90,18 +129,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__
 
     // ---- prologue: independent of the preceding kernel, overlaps its tail under PDL
     if (tid == 0) {
-        tma_prefetch_desc(&mAhi), tma_prefetch_desc(&mBhi);
-        if (NSPLIT == 3) tma_prefetch_desc(&mAlo), tma_prefetch_desc(&mBlo);
+        tma_prefetch_desc(&mp.Ahi), tma_prefetch_desc(&mp.Bhi);
+        if (kLo) tma_prefetch_desc(&mp.Alo), tma_prefetch_desc(&mp.Blo);
         for (int s = 0; s < kTcStages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
-        mbar_init(&accum_bar, 1);
+        mbar_init(&accum_bar, 1), mbar_init(&resid_bar, 1);
         fence_barrier_init();
         // the weights never depend on the preceding kernel: start streaming them right away
         for (int kb = 0; kb < npre; ++kb) {
             uint8_t* sb = smem + kb * SM::kStageBytes + SM::kParts * kTileABytes;
             mbar_arrive_expect_tx(&full_bar[kb], SM::kStageBytes);
-            tma_load_2d(sb, &mBhi, &full_bar[kb], kb * kTcBK, n0);
-            if (NSPLIT == 3) tma_load_2d(sb + kTileBBytes, &mBlo, &full_bar[kb], kb * kTcBK, n0);
+            tma_load_2d(sb, &mp.Bhi, &full_bar[kb], kb * kTcBK, n0);
+            if (kLo) tma_load_2d(sb + kTileBBytes, &mp.Blo, &full_bar[kb], kb * kTcBK, n0);
         }
+        if (a.residual) tma_prefetch_desc(&mp.R);
+        if (a.c_on) tma_prefetch_desc(&mp.C);
+        if (a.o_mode) tma_prefetch_desc(&mp.O[0]), tma_prefetch_desc(&mp.O[1]);
+        if (a.ln_g) tma_prefetch_desc(&mp.LnHi), tma_prefetch_desc(&mp.LnLo);
     }
     if (warp == 1) {
         tmem_alloc(&tmem_base_s, kTcBN);  // 64 fp32 accumulator columns
@@ -117,6 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__
     if (tid == 0) tr.mark(2);
     pdl_launch_dependents();  // let the next kernel of the chain run its prologue under our main loop
 
+    uint8_t* sC = smem + SM::kOffC;
     if (warp == 0) {
         if (lane == 0) {  // ---- TMA producer
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -126,17 +170,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__
                     ok &= mbar_wait(&empty_bar[s], ((kb / kTcStages) - 1) & 1);
                     mbar_arrive_expect_tx(&full_bar[s], SM::kStageBytes);
                     uint8_t* sb = st + SM::kParts * kTileABytes;
-                    tma_load_2d(sb, &mBhi, &full_bar[s], kb * kTcBK, n0);
-                    if (NSPLIT == 3) tma_load_2d(sb + kTileBBytes, &mBlo, &full_bar[s], kb * kTcBK, n0);
+                    tma_load_2d(sb, &mp.Bhi, &full_bar[s], kb * kTcBK, n0);
+                    if (kLo) tma_load_2d(sb + kTileBBytes, &mp.Blo, &full_bar[s], kb * kTcBK, n0);
                 }
                 if (a.conv_feat) {  // 3x3 conv: K index = tap * feat + d; A rows are the 16x16 grid of one target
                     const int chunks = a.conv_feat / kTcBK, tap = kb / chunks, d0 = (kb % chunks) * kTcBK;
                     const int b = m0 / kNTx, y0 = (m0 % kNTx) / kMap;
-                    tma_load_4d(st, &mAhi, &full_bar[s], d0, tap % 3 - 1, y0 + tap / 3 - 1, b);
-                    if (NSPLIT == 3) tma_load_4d(st + kTileABytes, &mAlo, &full_bar[s], d0, tap % 3 - 1, y0 + tap / 3 - 1, b);
+                    tma_load_4d(st, &mp.Ahi, &full_bar[s], d0, tap % 3 - 1, y0 + tap / 3 - 1, b);
+                    if (kLo) tma_load_4d(st + kTileABytes, &mp.Alo, &full_bar[s], d0, tap % 3 - 1, y0 + tap / 3 - 1, b);
                 } else {
-                    tma_load_2d(st, &mAhi, &full_bar[s], kb * kTcBK, m0);
-                    if (NSPLIT == 3) tma_load_2d(st + kTileABytes, &mAlo, &full_bar[s], kb * kTcBK, m0);
+                    tma_load_2d(st, &mp.Ahi, &full_bar[s], kb * kTcBK, m0);
+                    if (kLo) tma_load_2d(st + kTileABytes, &mp.Alo, &full_bar[s], kb * kTcBK, m0);
+                }
+                if (kb == 0 && a.residual) {  // residual rows of this tile (flat [rows][N] fp32), two 128-byte-wide boxes
+                    mbar_arrive_expect_tx(&resid_bar, kTileCBytes);
+                    tma_load_2d(sC, &mp.R, &resid_bar, n0, m0);
+                    tma_load_2d(sC + kTileCBytes / 2, &mp.R, &resid_bar, n0 + 32, m0);
                 }
             }
         }
@@ -155,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__
                     const uint32_t koff = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
                     const uint64_t dAhi = umma_desc_sw128(sa + koff), dBhi = umma_desc_sw128(sb + koff);
                     umma_bf16(tmem, dAhi, dBhi, idesc, (kb | k) != 0);
-                    if (NSPLIT == 3) {
+                    if (kLo) {
                         const uint64_t dAlo = umma_desc_sw128(sa + kTileABytes + koff), dBlo = umma_desc_sw128(sb + kTileBBytes + koff);
                         umma_bf16(tmem, dAhi, dBlo, idesc, 1);
                         umma_bf16(tmem, dAlo, dBhi, idesc, 1);
@@ -168,84 +217,106 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__
         __syncwarp();
     }
 
-    // ---- epilogue: thread (row, g) owns 16 accumulator columns of its row; 16 warps keep the ALU / store work short
+    // ---- epilogue: thread (row, g) owns 16 accumulator columns of its row
     const int m = m0 + row, nc = n0 + g * kTcColsPerThread;
-    const bool row_ok = m < a.M;
-    const int64_t crow = a.C ? ((int64_t)((m / a.c_rows_in) * a.c_rows_stride + a.c_row_off + (m % a.c_rows_in))) * a.ldc : 0;
-    float v[kTcColsPerThread];
-    if (a.residual && row_ok) {  // the residual rows do not depend on the accumulator: fetch them while the MMAs run
-        const float4* cp = reinterpret_cast<const float4*>(a.C + crow + nc);
+    // this thread's four 16-byte chunks of the fp32 tile: box (g >> 1), chunks 4 (g & 1) .. + 3 of the 128-byte row, swizzled
+    uint8_t* c_row = sC + (g >> 1) * (kTileCBytes / 2) + row * 128;
+    const int c_chunk0 = (g & 1) * 4, sw = row & 7;
+    const TileRows tr_rows(m0, a.period, a.batch_off);
+    int o_which = 0, o_h = 0;
+    if (a.o_mode == 2) {  // QKV: this CTA's 64 columns are one head of Q, K or V
+        const int Dm = a.N / 3;
+        o_which = n0 / Dm, o_h = (n0 - o_which * Dm) / kTcBN;
+    }
+    float bias_v[kTcColsPerThread];
+    if (a.bias) {  // does not depend on the accumulator: fetch while the MMAs run
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 r4 = cp[j];
-            v[4 * j] = r4.x, v[4 * j + 1] = r4.y, v[4 * j + 2] = r4.z, v[4 * j + 3] = r4.w;
+        for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nc + j));
+            bias_v[j] = b4.x, bias_v[j + 1] = b4.y, bias_v[j + 2] = b4.z, bias_v[j + 3] = b4.w;
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < kTcColsPerThread; ++j) v[j] = 0.f;
+        for (int j = 0; j < 16; ++j) bias_v[j] = 0.f;
     }
     ok &= mbar_wait(&accum_bar, 0);
     tcgen05_fence_after();
     if (tid == 0) tr.mark(6);
-    {
-        float acc[kTcColsPerThread];
-        tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kTcColsPerThread, acc);
-        if (tid == 0) tr.mark(4);
-        if (a.bias) {
+    float v[kTcColsPerThread];
+    tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kTcColsPerThread, v);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nc + j));
-                acc[j] += b4.x, acc[j + 1] += b4.y, acc[j + 2] += b4.z, acc[j + 3] += b4.w;
-            }
-        }
-        if (a.gelu) {
+    for (int j = 0; j < 16; ++j) v[j] += bias_v[j];
+    if (a.gelu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = gelu_erf(acc[j]);
-        }
-        if (a.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fmaxf(acc[j], 0.f);
-        }
-        if (a.pos && row_ok) {
-            const float* pp = a.pos + (int64_t)(m % a.pos_rows) * a.N + nc;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + j));
-                acc[j] += p4.x, acc[j + 1] += p4.y, acc[j + 2] += p4.z, acc[j + 3] += p4.w;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = acc[j] + v[j];  // + residual (0 when off): same order as the unfused path
+        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
     }
-    if (tid == 0) tr.mark(5);
-    for (int rep = 0; rep < (a.trace_id >= 100 ? 2 : 1); ++rep) {  // diagnostics: trace ids >= 100 run the store block twice
-    if (row_ok) {
-        if (a.C) {
-            float4* cp = reinterpret_cast<float4*>(a.C + crow + nc);
+    if (a.relu) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (a.pos) {
+        const float* pp = a.pos + (int64_t)(m % a.pos_rows) * a.N + nc;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + j));
+            v[j] += p4.x, v[j + 1] += p4.y, v[j + 2] += p4.z, v[j + 3] += p4.w;
         }
-        if (a.qkv_heads) {
-            const int Dm = a.N / 3, which = n0 / Dm, hh = (n0 % Dm) / kTcBN;
-            const int64_t bh = (int64_t)(m / kNTok) * a.qkv_heads + hh;
-            const int tok = m % kNTok, d0 = g * kTcColsPerThread;
-            if (which < 2) {  // Q / K: [bh][tok][64]
-                const int64_t o = (bh * kNTok + tok) * kTcBN + d0;
-                split_store16(v, (which == 0 ? a.Qhi : a.Khi) + o, (which == 0 ? a.Qlo : a.Klo) + o);
-            } else {  // V^T: [bh][d][tok]; a warp's 32 rows are 32 consecutive tokens -> 64-byte coalesced stores per d
-                __nv_bfloat16* vh = a.Vthi + (bh * kTcBN + d0) * kNTok + tok;
-                __nv_bfloat16* vl = a.Vtlo + (bh * kTcBN + d0) * kNTok + tok;
+    }
+    if (a.residual) {
+        ok &= mbar_wait(&resid_bar, 0);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    __nv_bfloat16 h, l;
-                    split_bf16(v[j], h, l);
-                    vh[(int64_t)j * kNTok] = h, vl[(int64_t)j * kNTok] = l;
-                }
+        for (int q = 0; q < 4; ++q) {
+            const float4 r4 = *reinterpret_cast<const float4*>(c_row + (((c_chunk0 + q) ^ sw) << 4));
+            v[4 * q] += r4.x, v[4 * q + 1] += r4.y, v[4 * q + 2] += r4.z, v[4 * q + 3] += r4.w;
+        }
+    }
+    if (tid == 0) tr.mark(4);
+    // ---- stage the output tiles in shared memory (the pipeline ring is dead: every MMA has completed)
+    if (a.c_on) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(c_row + (((c_chunk0 + q) ^ sw) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    if (a.o_mode) {
+        if (o_which < 2) {
+            stage_split16(v, smem + SM::kOffOhi, smem + SM::kOffOlo, row, g, kLo);
+        } else {  // V^T: two unswizzled [64 d][64 tokens] sub-tiles; lanes are consecutive tokens -> 64-byte contiguous runs
+            const int sub = (row >> 6) * (kHalfBytes / 2) + (g * kTcColsPerThread) * kHalfRows + (row & 63);
+            __nv_bfloat16* th = reinterpret_cast<__nv_bfloat16*>(smem + SM::kOffOhi) + sub;
+            __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(smem + SM::kOffOlo) + sub;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                __nv_bfloat16 h, l;
+                split_bf16(v[j], h, l);
+                th[j * kHalfRows] = h;
+                if (kLo) tl[j * kHalfRows] = l;
             }
         }
-        if (a.Ohi) split_store16(v, a.Ohi + (int64_t)m * a.ldo + nc, a.Olo + (int64_t)m * a.ldo + nc);
     }
-    if (tid == 0) tr.mark(rep ? 4 : 7);
+    if (tid == 0 && !a.ln_g) tr.mark(5);
+    fence_proxy_async_smem();
+    if (tid == 0 && a.trace_id == 4) tr.mark(4);
+    __syncthreads();
+    if (tid == 0 && a.trace_id == 2) tr.mark(4);
+    if (tid == 0) {
+        if (a.c_on) {
+            store_tile(&mp.C, sC, n0, tr_rows, a.c_row_off, 0);
+            store_tile(&mp.C, sC + kTileCBytes / 2, n0 + 32, tr_rows, a.c_row_off, 0);
+        }
+        if (a.o_mode == 1) {
+            store_tile(&mp.O[0], smem + SM::kOffOhi, n0, tr_rows, a.o_row_off, 0);
+            if (kLo) store_tile(&mp.O[1], smem + SM::kOffOlo, n0, tr_rows, a.o_row_off, 0);
+        } else if (a.o_mode == 2) {  // Q / K: {64, 320, heads, B}; V^T: {320, 64, heads, B}
+            if (o_which < 2) {
+                store_tile(&mp.O[2 * o_which], smem + SM::kOffOhi, 0, tr_rows, 0, o_h);
+                if (kLo) store_tile(&mp.O[2 * o_which + 1], smem + SM::kOffOlo, 0, tr_rows, 0, o_h);
+            } else {
+                store_tile_vt(&mp.O[4], smem + SM::kOffOhi, tr_rows, o_h);
+                if (kLo) store_tile_vt(&mp.O[5], smem + SM::kOffOlo, tr_rows, o_h);
+            }
+        }
+        tma_store_commit();
+        tr.mark(7);
     }
     if (a.ln_g) {  // ---- fused LayerNorm over the full row (N columns = cluster of N / 64 CTAs x 4 column groups)
         const uint32_t nct = cluster_nctarank(), me = cluster_ctarank();
@@ -263,7 +334,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__
         cluster_wait_acquire();  // every CTA of the cluster has started (arrive in the prologue)
         for (uint32_t r = 0; r < nct; ++r) st_shared_cluster_f2(cluster_map_shared(mine, r), s, m2);
         cluster_arrive_release();
+        float gam[16], bet[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.ln_g + nc + j)), b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b + nc + j));
+            gam[j] = g4.x, gam[j + 1] = g4.y, gam[j + 2] = g4.z, gam[j + 3] = g4.w;
+            bet[j] = b4.x, bet[j + 1] = b4.y, bet[j + 2] = b4.z, bet[j + 3] = b4.w;
+        }
         cluster_wait_acquire();
+        if (tid == 0) tr.mark(5);
         float tot = 0.f;
         for (uint32_t r = 0; r < nct; ++r)
 #pragma unroll
@@ -278,20 +357,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__
                 M2 += p.y + 16.f * d * d;
             }
         const float rstd = 1.f / sqrtf(M2 / (float)a.N + 1e-6f);
-        const int mi = m % a.ln_rows_in;
-        if (row_ok && mi >= a.ln_skip) {
-            const int64_t lrow = (int64_t)(m / a.ln_rows_in) * a.ln_rows_stride + a.ln_row_off + mi;
-            float y[16];
+        float y[16];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.ln_g + nc + j)), b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b + nc + j));
-                y[j] = (v[j] - mean) * rstd * g4.x + b4.x, y[j + 1] = (v[j + 1] - mean) * rstd * g4.y + b4.y;
-                y[j + 2] = (v[j + 2] - mean) * rstd * g4.z + b4.z, y[j + 3] = (v[j + 3] - mean) * rstd * g4.w + b4.w;
-            }
-            split_store16(y, a.ln_hi + lrow * a.N + nc, a.ln_lo + lrow * a.N + nc);
+        for (int j = 0; j < 16; ++j) y[j] = (v[j] - mean) * rstd * gam[j] + bet[j];
+        stage_split16(y, smem + SM::kOffLnHi, smem + SM::kOffLnLo, row, g, kLo);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            store_tile(&mp.LnHi, smem + SM::kOffLnHi, n0, tr_rows, a.ln_row_off, 0);
+            if (kLo) store_tile(&mp.LnLo, smem + SM::kOffLnLo, n0, tr_rows, a.ln_row_off, 0);
+            tma_store_commit();
         }
     }
     if (!ok && a.err) atomicExch(a.err, 1);
+    if (tid == 0 && a.trace_id >= 100) tr.mark(5);  // diagnostics: stores issued -> completion
+    if (tid == 0) tma_store_wait_read();  // the tile stores have read shared memory: it may be released
     tcgen05_fence_before();
     __syncthreads();
     if (tid == 0) tr.mark(3);
@@ -313,8 +393,9 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// bf16 tensor [dims...] (dims[0] innermost, contiguous), box per dim, 128-byte swizzle, zero OOB fill
-bool tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+// tensor [dims...] (dims[0] innermost, contiguous) of 2-byte (bf16) or 4-byte (fp32) elements, box per dim, zero OOB fill
+bool tc_make_map_ex(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, bool swizzle128) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -324,8 +405,10 @@ bool tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* d
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) gd[i] = dims[i], bx[i] = box[i], es[i] = 1;
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                    const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu)", (int)r, rank, (unsigned long long)dims[0],
                   (unsigned long long)(rank > 1 ? dims[1] : 1));
@@ -333,11 +416,35 @@ bool tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* d
     }
     return true;
 }
+bool tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    return tc_make_map_ex(out, base, 2, rank, dims, strides_bytes, box, true);
+}
 
 bool tc_make_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     const uint64_t dims[2] = {cols, rows}, strides[1] = {cols * 2};
     const uint32_t box[2] = {(uint32_t)kTcBK, box_rows};
     return tc_make_map(out, base, 2, dims, strides, box);
+}
+
+// Output tile map: dense [batch][heads][rows][cols] tensor, one 64-row x (128-byte wide) box
+bool tc_out_map(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint64_t heads, uint64_t batch) {
+    const uint64_t dims[4] = {cols, rows, heads, batch};
+    const uint64_t strides[3] = {cols * elem_bytes, cols * rows * elem_bytes, cols * rows * heads * elem_bytes};
+    const uint32_t box[4] = {(uint32_t)(128 / elem_bytes), (uint32_t)kHalfRows, 1, 1};
+    return tc_make_map_ex(out, base, elem_bytes, 4, dims, strides, box, true);
+}
+// V^T tile map: [batch][heads][64 d][rows = tokens], box {64 tokens, 64 d}, unswizzled
+bool tc_out_map_vt(CUtensorMap* out, const void* base, uint64_t tokens, uint64_t heads, uint64_t batch) {
+    const uint64_t dims[4] = {tokens, (uint64_t)kTcBN, heads, batch};
+    const uint64_t strides[3] = {tokens * 2, tokens * kTcBN * 2, tokens * kTcBN * heads * 2};
+    const uint32_t box[4] = {(uint32_t)kHalfRows, (uint32_t)kTcBN, 1, 1};
+    return tc_make_map_ex(out, base, 2, 4, dims, strides, box, false);
+}
+// flat [rows][cols] fp32 residual tile source (two 32-column boxes per 64-column tile)
+bool tc_resid_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols) {
+    const uint64_t dims[2] = {cols, rows}, strides[1] = {cols * 4};
+    const uint32_t box[2] = {32, (uint32_t)kTcBM};
+    return tc_make_map_ex(out, base, 4, 2, dims, strides, box, true);
 }
 
 bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, uint64_t a_rows, const __nv_bfloat16* Whi,
@@ -352,16 +459,19 @@ bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* 
         const uint64_t dims[4] = {(uint64_t)conv_feat, kMap, kMap, (uint64_t)conv_batch};
         const uint64_t strides[3] = {(uint64_t)conv_feat * 2, (uint64_t)conv_feat * 2 * kMap, (uint64_t)conv_feat * 2 * kMap * kMap};
         const uint32_t box[4] = {(uint32_t)kTcBK, kMap, kTcBM / kMap, 1};
-        ok &= tc_make_map(&p->mAhi, Ahi, 4, dims, strides, box);
-        ok &= tc_make_map(&p->mAlo, Alo ? Alo : Ahi, 4, dims, strides, box);
+        ok &= tc_make_map(&p->maps.Ahi, Ahi, 4, dims, strides, box);
+        ok &= tc_make_map(&p->maps.Alo, Alo ? Alo : Ahi, 4, dims, strides, box);
     } else {
-        ok &= tc_make_map_2d(&p->mAhi, Ahi, a_rows, K, kTcBM);
-        ok &= tc_make_map_2d(&p->mAlo, Alo ? Alo : Ahi, a_rows, K, kTcBM);
+        ok &= tc_make_map_2d(&p->maps.Ahi, Ahi, a_rows, K, kTcBM);
+        ok &= tc_make_map_2d(&p->maps.Alo, Alo ? Alo : Ahi, a_rows, K, kTcBM);
     }
-    ok &= tc_make_map_2d(&p->mBhi, Whi, N, K, kTcBN);
-    ok &= tc_make_map_2d(&p->mBlo, Wlo ? Wlo : Whi, N, K, kTcBN);
+    ok &= tc_make_map_2d(&p->maps.Bhi, Whi, N, K, kTcBN);
+    ok &= tc_make_map_2d(&p->maps.Blo, Wlo ? Wlo : Whi, N, K, kTcBN);
+    // unused output maps must still be valid descriptors (they are never dereferenced when their mode is off)
+    p->maps.R = p->maps.C = p->maps.LnHi = p->maps.LnLo = p->maps.Bhi;
+    for (auto& m : p->maps.O) m = p->maps.Bhi;
     p->args.N = N, p->args.K = K, p->args.conv_feat = conv_feat;
-    p->args.c_rows_in = 1 << 30, p->args.pos_rows = 1, p->args.ln_rows_in = 1 << 30;
+    p->args.pos_rows = 1, p->args.period = 1 << 30;
     return ok;
 }
 
@@ -381,10 +491,8 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t 
         cluster_x = a.N / kTcBN;
         if (cluster_x > kMaxLnCluster) return cudaErrorInvalidValue;
     }
-    static const bool dup = getenv("VT_B200_DUP") != nullptr;  // diagnostics: launch twice to compare cold / warm instruction fetch
-    if (dup && nsplit == 3) launch_ex(gemm_tc_kernel<3>, grid, dim3(kTcThreads), TcSmem<3>::kTotal, s, pdl, cluster_x, p.mAhi, p.mAlo, p.mBhi, p.mBlo, a);
-    if (nsplit == 3) return launch_ex(gemm_tc_kernel<3>, grid, dim3(kTcThreads), TcSmem<3>::kTotal, s, pdl, cluster_x, p.mAhi, p.mAlo, p.mBhi, p.mBlo, a);
-    return launch_ex(gemm_tc_kernel<1>, grid, dim3(kTcThreads), TcSmem<1>::kTotal, s, pdl, cluster_x, p.mAhi, p.mAlo, p.mBhi, p.mBlo, a);
+    if (nsplit == 3) return launch_ex(gemm_tc_kernel<3>, grid, dim3(kTcThreads), TcSmem<3>::kTotal, s, pdl, cluster_x, p.maps, a);
+    return launch_ex(gemm_tc_kernel<1>, grid, dim3(kTcThreads), TcSmem<1>::kTotal, s, pdl, cluster_x, p.maps, a);
 }
 
 // fp32 -> bf16 (hi, lo) split of a dense buffer
@@ -430,7 +538,22 @@ extern "C" vt_status vt_debug_gemm(int32_t device, int32_t M, int32_t N, int32_t
     vt_status st = VT_OK;
     if (!tc_plan_init(&plan, Ahi, Alo, M, Whi, Wlo, N, K, 0, 0)) st = VT_ERR_CUDA;
     if (st == VT_OK) {
-        plan.args.bias = dB, plan.args.C = dC, plan.args.ldc = N, plan.args.gelu = gelu, plan.args.err = dErr;
+        plan.args.bias = dB, plan.args.gelu = gelu, plan.args.err = dErr, plan.args.c_on = 1;
+        // diagnostics knobs: VT_DBG_PERIOD = rows per target of the output addressing (M must be a multiple), VT_DBG_RESID = C += C0
+        const char* per = getenv("VT_DBG_PERIOD");
+        const int period = per ? atoi(per) : 0;
+        if (period > 0 && M % period == 0) {
+            plan.args.period = period;
+            if (!tc_out_map(&plan.maps.C, dC, 4, N, period, 1, M / period)) st = VT_ERR_CUDA;
+        } else if (!tc_out_map(&plan.maps.C, dC, 4, N, M, 1, 1)) {
+            st = VT_ERR_CUDA;
+        }
+        if (getenv("VT_DBG_RESID")) {
+            plan.args.residual = 1;
+            if (!tc_resid_map(&plan.maps.R, dC, M, N)) st = VT_ERR_CUDA;
+        }
+    }
+    if (st == VT_OK) {
         cudaError_t e = tc_gemm_launch(plan, M, nsplit, 0, false);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {

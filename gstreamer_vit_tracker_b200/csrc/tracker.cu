@@ -289,7 +289,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
             VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s, pdl));
             if (t->tc_attention)
-                VT_LAUNCH(tc_attention_launch(t->plan_att, t->att_hi, t->att_lo, n, D, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace));
+                VT_LAUNCH(tc_attention_launch(t->plan_att, n, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace));
             else
                 VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
             VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention));  // fused: + LN2
@@ -708,7 +708,8 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             VT_TRY(balloc(&t->k_hi, &t->k_lo, nq));
             VT_TRY(balloc(&t->vt_hi, &t->vt_lo, nq));
             VT_TRY(tc_attention_setup());
-            if (!tc_attention_plan_init(&t->plan_att, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, (int)(B * t->heads))) return fail(VT_ERR_CUDA);
+            if (!tc_attention_plan_init(&t->plan_att, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, (int)(B * t->heads), t->att_hi, t->att_lo, (int)D, (int)B))
+                return fail(VT_ERR_CUDA);
         }
         VT_TRY(cudaMalloc(&t->d_tc_err, sizeof(int)));
         VT_TRY(cudaMemset(t->d_tc_err, 0, sizeof(int)));
@@ -716,55 +717,73 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         auto wlo = [&](const float* w) { return t->w_lo + (w - t->d_weights); };
         bool ok = true;
         const uint64_t rows = B * kNTok;
+        // output tile maps (tc_out_map: dense [targets][heads][rows][cols])
+        CUtensorMap mX, mXres, mLnHi, mLnLo, mYfHi, mYfLo, mHidHi, mHidLo, mH1, mZ, mQKV, mQ[6];
+        ok &= tc_out_map(&mX, t->X, 4, D, kNTok, 1, B) && tc_resid_map(&mXres, t->X, B * kNTok, D);
+        ok &= tc_out_map(&mLnHi, t->ln_hi, 2, D, kNTok, 1, B) && tc_out_map(&mLnLo, t->ln_lo, 2, D, kNTok, 1, B);
+        ok &= tc_out_map(&mYfHi, t->yf_hi, 2, D, kNTx, 1, B) && tc_out_map(&mYfLo, t->yf_lo, 2, D, kNTx, 1, B);
+        ok &= tc_out_map(&mHidHi, t->hid_hi, 2, Hd, kNTok, 1, B) && tc_out_map(&mHidLo, t->hid_lo, 2, Hd, kNTok, 1, B);
+        ok &= tc_out_map(&mH1, t->H1, 4, C, kNTx, 1, B) && tc_out_map(&mZ, t->Zemb, 4, D, kNTz, 1, B);
+        if (t->tc_attention) {
+            ok &= tc_out_map(&mQ[0], t->q_hi, 2, 64, kNTok, t->heads, B) && tc_out_map(&mQ[1], t->q_lo, 2, 64, kNTok, t->heads, B);
+            ok &= tc_out_map(&mQ[2], t->k_hi, 2, 64, kNTok, t->heads, B) && tc_out_map(&mQ[3], t->k_lo, 2, 64, kNTok, t->heads, B);
+            ok &= tc_out_map_vt(&mQ[4], t->vt_hi, kNTok, t->heads, B) && tc_out_map_vt(&mQ[5], t->vt_lo, kNTok, t->heads, B);
+        } else {
+            ok &= tc_out_map(&mQKV, t->QKV, 4, 3 * D, kNTok, 1, B);
+        }
         // patch embed (search): A = patches [B*256, 768] -> X rows 64.. of every target, + pos_x
         ok &= tc_plan_init(&t->plan_patch_x, t->px_hi, t->px_lo, B * kNTx, whi(t->patch_w), wlo(t->patch_w), (int)D, kPatchK, 0, 0);
         {
             TcGemmArgs& a = t->plan_patch_x.args;
-            a.bias = t->patch_b, a.pos = t->pos_x, a.pos_rows = kNTx, a.C = t->X, a.ldc = D;
-            a.c_rows_in = kNTx, a.c_rows_stride = kNTok, a.c_row_off = kNTz;
+            a.bias = t->patch_b, a.pos = t->pos_x, a.pos_rows = kNTx;
+            a.period = kNTx, a.c_on = 1, a.c_row_off = kNTz, t->plan_patch_x.maps.C = mX;
             if (t->fuse_ln) {  // LN1 of block 0 for the search rows, straight into the first QKV GEMM's A operand
-                a.ln_g = t->blk[0].ln1_g, a.ln_b = t->blk[0].ln1_b, a.ln_hi = t->ln_hi, a.ln_lo = t->ln_lo;
-                a.ln_rows_in = kNTx, a.ln_rows_stride = kNTok, a.ln_row_off = kNTz, a.ln_skip = 0;
+                a.ln_g = t->blk[0].ln1_g, a.ln_b = t->blk[0].ln1_b, a.ln_row_off = kNTz;
+                t->plan_patch_x.maps.LnHi = mLnHi, t->plan_patch_x.maps.LnLo = mLnLo;
             }
         }
-        // patch embed (template, at init): C is set per target
+        // patch embed (template, at init): one 128-row tile whose rows 64.. are clipped; batch_off = the target slot, set per call
         ok &= tc_plan_init(&t->plan_patch_z, t->pz_hi, t->pz_lo, 128, whi(t->patch_w), wlo(t->patch_w), (int)D, kPatchK, 0, 0);
         {
             TcGemmArgs& a = t->plan_patch_z.args;
-            a.bias = t->patch_b, a.pos = t->pos_z, a.pos_rows = kNTz, a.ldc = D;
+            a.bias = t->patch_b, a.pos = t->pos_z, a.pos_rows = kNTz;
+            a.period = 128, a.c_on = 1, t->plan_patch_z.maps.C = mZ;
         }
         t->plans.resize(t->depth);
         for (int l = 0; l < t->depth && ok; ++l) {
             const BlockW& b = t->blk[l];
             vt_tracker::BlockPlans& p = t->plans[l];
             ok &= tc_plan_init(&p.qkv, t->ln_hi, t->ln_lo, rows, whi(b.qkv_w), wlo(b.qkv_w), (int)(3 * D), (int)D, 0, 0);
-            p.qkv.args.bias = b.qkv_b;
+            p.qkv.args.bias = b.qkv_b, p.qkv.args.period = kNTok;
             if (t->tc_attention) {
-                TcGemmArgs& a = p.qkv.args;
-                a.qkv_heads = t->heads, a.Qhi = t->q_hi, a.Qlo = t->q_lo, a.Khi = t->k_hi, a.Klo = t->k_lo, a.Vthi = t->vt_hi, a.Vtlo = t->vt_lo;
+                p.qkv.args.o_mode = 2;
+                for (int i = 0; i < 6; ++i) p.qkv.maps.O[i] = mQ[i];
             } else {
-                p.qkv.args.C = t->QKV, p.qkv.args.ldc = 3 * D;
+                p.qkv.args.c_on = 1, p.qkv.maps.C = mQKV;
             }
             ok &= tc_plan_init(&p.proj, t->att_hi, t->att_lo, rows, whi(b.proj_w), wlo(b.proj_w), (int)D, (int)D, 0, 0);
-            p.proj.args.bias = b.proj_b, p.proj.args.C = t->X, p.proj.args.ldc = D, p.proj.args.residual = 1;
-            if (t->fuse_ln) p.proj.args.ln_g = b.ln2_g, p.proj.args.ln_b = b.ln2_b, p.proj.args.ln_hi = t->ln_hi, p.proj.args.ln_lo = t->ln_lo;
+            p.proj.args.bias = b.proj_b, p.proj.args.period = kNTok, p.proj.args.residual = 1, p.proj.args.c_on = 1;
+            p.proj.maps.R = mXres, p.proj.maps.C = mX;
+            if (t->fuse_ln) p.proj.args.ln_g = b.ln2_g, p.proj.args.ln_b = b.ln2_b, p.proj.maps.LnHi = mLnHi, p.proj.maps.LnLo = mLnLo;
             ok &= tc_plan_init(&p.fc1, t->ln_hi, t->ln_lo, rows, whi(b.fc1_w), wlo(b.fc1_w), (int)Hd, (int)D, 0, 0);
-            p.fc1.args.bias = b.fc1_b, p.fc1.args.gelu = 1, p.fc1.args.Ohi = t->hid_hi, p.fc1.args.Olo = t->hid_lo, p.fc1.args.ldo = Hd;
+            p.fc1.args.bias = b.fc1_b, p.fc1.args.gelu = 1, p.fc1.args.period = kNTok, p.fc1.args.o_mode = 1;
+            p.fc1.maps.O[0] = mHidHi, p.fc1.maps.O[1] = mHidLo;
             ok &= tc_plan_init(&p.fc2, t->hid_hi, t->hid_lo, rows, whi(b.fc2_w), wlo(b.fc2_w), (int)D, (int)Hd, 0, 0);
-            p.fc2.args.bias = b.fc2_b, p.fc2.args.C = t->X, p.fc2.args.ldc = D, p.fc2.args.residual = 1;
+            p.fc2.args.bias = b.fc2_b, p.fc2.args.period = kNTok, p.fc2.args.residual = 1, p.fc2.args.c_on = 1;
+            p.fc2.maps.R = mXres, p.fc2.maps.C = mX;
             if (t->fuse_ln) {
                 TcGemmArgs& a = p.fc2.args;
                 if (l + 1 < t->depth) {
-                    a.ln_g = t->blk[l + 1].ln1_g, a.ln_b = t->blk[l + 1].ln1_b, a.ln_hi = t->ln_hi, a.ln_lo = t->ln_lo;
-                } else {  // final LN, search rows only -> the head conv's [B,16,16,D] grid
-                    a.ln_g = t->lnf_g, a.ln_b = t->lnf_b, a.ln_hi = t->yf_hi, a.ln_lo = t->yf_lo;
-                    a.ln_rows_in = kNTok, a.ln_rows_stride = kNTx, a.ln_row_off = -kNTz, a.ln_skip = kNTz;
+                    a.ln_g = t->blk[l + 1].ln1_g, a.ln_b = t->blk[l + 1].ln1_b, p.fc2.maps.LnHi = mLnHi, p.fc2.maps.LnLo = mLnLo;
+                } else {  // final LN, search rows only -> the head conv's [B,16,16,D] grid (the template rows fall outside and are clipped)
+                    a.ln_g = t->lnf_g, a.ln_b = t->lnf_b, a.ln_row_off = -kNTz, p.fc2.maps.LnHi = mYfHi, p.fc2.maps.LnLo = mYfLo;
                 }
             }
         }
         // 3x3 head conv: A gathered by TMA from the [B,16,16,D] final-LN grid (zero fill = zero padding), weights [C][tap][D]
         ok &= tc_plan_init(&t->plan_head, t->yf_hi, t->yf_lo, 0, whi(t->h1_w), wlo(t->h1_w), (int)C, (int)(9 * D), (int)D, (int)B);
-        t->plan_head.args.bias = t->h1_b, t->plan_head.args.relu = 1, t->plan_head.args.C = t->H1, t->plan_head.args.ldc = C;
+        t->plan_head.args.bias = t->h1_b, t->plan_head.args.relu = 1, t->plan_head.args.period = kNTx, t->plan_head.args.c_on = 1;
+        t->plan_head.maps.C = mH1;
         if (!ok) return fail(VT_ERR_CUDA);
         for (TcGemmPlan* p : {&t->plan_patch_x, &t->plan_patch_z, &t->plan_head}) p->args.err = t->d_tc_err;
         for (auto& p : t->plans) p.qkv.args.err = p.proj.args.err = p.fc1.args.err = p.fc2.args.err = t->d_tc_err;
@@ -832,9 +851,9 @@ vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, s
         VT_LAUNCH(launch_gemm_simt(g, t->stream));
     } else {
         TcGemmPlan p = t->plan_patch_z;
-        p.args.C = t->Zemb + (size_t)target * kNTz * t->D;
+        p.args.batch_off = target;
         VT_LAUNCH(tc_gemm_launch(p, kNTz, t->nsplit, t->stream, false));
-        VT_LAUNCH(launch_layernorm_split(p.args.C, t->D, t->blk[0].ln1_g, t->blk[0].ln1_b, t->zln_hi + (size_t)target * kNTz * t->D,
+        VT_LAUNCH(launch_layernorm_split(t->Zemb + (size_t)target * kNTz * t->D, t->D, t->blk[0].ln1_g, t->blk[0].ln1_b, t->zln_hi + (size_t)target * kNTz * t->D,
                                          t->zln_lo + (size_t)target * kNTz * t->D, kNTz, t->D, 1 << 30, 0, 0, t->stream, false));
     }
     t->kernel_launches += launches;

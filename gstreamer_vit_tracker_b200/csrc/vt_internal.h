@@ -175,42 +175,46 @@ struct TcGemmArgs {
     const float* bias;        // [N] or null
     const float* pos;         // [pos_rows, N] added to row (m % pos_rows), or null
     int pos_rows;
-    int gelu, relu, residual;
-    float* C;                 // fp32 output (nullable); row m -> (m / c_rows_in) * c_rows_stride + c_row_off + m % c_rows_in
-    int64_t ldc;
-    int c_rows_in, c_rows_stride, c_row_off;
-    __nv_bfloat16 *Ohi, *Olo; // bf16 split output [M, ldo] (nullable)
-    int64_t ldo;
-    // QKV scatter for the tensor-core attention (head_dim 64 == the N tile): rows are (target, token) pairs
-    int qkv_heads;            // 0 = off
-    __nv_bfloat16 *Qhi, *Qlo, *Khi, *Klo;    // [B*heads][320][64]
-    __nv_bfloat16 *Vthi, *Vtlo;              // [B*heads][64][320]  (V transposed: keys contiguous = K-major B operand of P*V)
-    // LayerNorm of the full output row fused into the epilogue (cluster of N / 64 CTAs, gemm_tc.cu): y = LN(row) * g + b written
-    // as a bf16 split to row (m / ln_rows_in) * ln_rows_stride + ln_row_off + m % ln_rows_in of ln_hi / ln_lo ([rows][N]);
-    // rows with m % ln_rows_in < ln_skip are not written
+    int gelu, relu;
+    int residual;             // add the fp32 tile read through maps.R (flat [rows][N], same rows as the tile) before storing
+    // Output addressing: row m of the GEMM is (target m / period + batch_off, row-in-target m % period + <x>_row_off) of the
+    // 4-D output maps {cols, rows per target, heads, targets}; rows outside a target's range are clipped by the TMA unit.
+    int period, batch_off;
+    int c_on, c_row_off;      // fp32 tile -> maps.C
+    int o_mode;               // 0 off; 1 bf16 split tile -> maps.O[0] (hi), O[1] (lo); 2 QKV scatter -> O[0..5] = Q, K, V^T (hi, lo)
+    int o_row_off;
+    // LayerNorm of the full output row fused into the epilogue (cluster of N / 64 CTAs): y = LN(row) * g + b -> maps.LnHi / LnLo
     const float *ln_g, *ln_b; // null = off
-    __nv_bfloat16 *ln_hi, *ln_lo;
-    int ln_rows_in, ln_rows_stride, ln_row_off, ln_skip;
+    int ln_row_off;
     int* err;                 // set to 1 if a bounded mbarrier wait expired
     unsigned long long* trace; // device timeline buffer (diagnostics) or null
     int trace_id;
 };
+struct TcMaps {               // kernel parameter block (__grid_constant__): 14 descriptors
+    CUtensorMap Ahi, Alo, Bhi, Blo, R, C, O[6], LnHi, LnLo;
+};
 struct TcGemmPlan {
-    CUtensorMap mAhi, mAlo, mBhi, mBlo;
+    TcMaps maps;
     TcGemmArgs args;
 };
 bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, uint64_t a_rows, const __nv_bfloat16* Whi,
                   const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch);
+// output tile maps over dense [batch][heads][rows][cols] tensors (elem_bytes 2 = bf16, 4 = fp32), V^T [batch][heads][64][tokens],
+// and the flat fp32 residual source
+bool tc_out_map(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint64_t heads, uint64_t batch);
+bool tc_out_map_vt(CUtensorMap* out, const void* base, uint64_t tokens, uint64_t heads, uint64_t batch);
+bool tc_resid_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols);
 cudaError_t tc_gemm_setup();
 cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl);
-struct TcAttentionPlan {
-    CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo;
+struct TcAttentionPlan {      // kernel parameter block (__grid_constant__)
+    CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo, mOhi, mOlo;
 };
 bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const __nv_bfloat16* Qlo, const __nv_bfloat16* Khi, const __nv_bfloat16* Klo,
-                            const __nv_bfloat16* Vthi, const __nv_bfloat16* Vtlo, int batch_heads);
+                            const __nv_bfloat16* Vthi, const __nv_bfloat16* Vtlo, int batch_heads, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int D,
+                            int batch);
 cudaError_t tc_attention_setup();
-cudaError_t tc_attention_launch(const TcAttentionPlan& p, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int B, int D, int heads, int nsplit,
-                                int* err, cudaStream_t s, bool pdl, unsigned long long* trace = nullptr);
+cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int nsplit, int* err, cudaStream_t s, bool pdl,
+                                unsigned long long* trace = nullptr);
 cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t s);
 
 }  // namespace vt

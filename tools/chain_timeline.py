@@ -47,7 +47,7 @@ def main():
     agg = {}
     print(f"{'kernel':8s} {'entry':>8s} {'prolog':>7s} {'body':>7s} {'gap':>7s} | marks 4..7 relative to the dependency wait"
           f"   (us; vit stage {tm.vit_ms * 1e3:.1f} us, total {tm.total_ms * 1e3:.1f} us)")
-    print("  gemm: m6 accumulator ready, m4 tmem loaded, m5 bias+act done, m7 main stores issued; attn: m4 S ready, m5 row max done, m6 chunk 0 handed to the MMA, m7 chunk 4 handed over")
+    print("  gemm: m6 accumulator ready, m4 values final, m7 main stores issued, m5 LN exchange complete; attn: m4 S ready, m5 row max done, m6 chunk 0 handed to the MMA, m7 chunk 4 handed over")
     for kid, te, tw, tend, m4, m5, m6, m7 in rec:
         name = NAMES.get(int(kid), str(kid))
         gap = (tw - prev_end) / 1e3 if prev_end is not None else 0.0
