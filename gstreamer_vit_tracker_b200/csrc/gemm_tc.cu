@@ -42,17 +42,25 @@ constexpr int kTileABytes = kTcBM * kTcBK * 2;  // 16 KB, one precision part
 constexpr int kTileBBytes = kTcBN * kTcBK * 2;  //  8 KB
 constexpr int kTileOBytes = kTcBM * kTcBN * 2;  // 16 KB: one bf16 output tile
 constexpr int kTileCBytes = kTcBM * kTcBN * 4;  // 32 KB: the fp32 tile as two 128-byte-wide boxes
+constexpr int kMaxChainN = 192;                 // widest chained second GEMM (TMEM: 64 + N2 <= 256 columns)
 
 template <int NSPLIT>
 struct TcSmem {
     static constexpr int kParts = NSPLIT == 3 ? 2 : 1;
     static constexpr int kStageBytes = kParts * (kTileABytes + kTileBBytes);
-    static constexpr int kPipeBytes = kTcStages * kStageBytes;
+    // the ring is padded (bf16 mode) so that the chained GEMM's result tile fits behind the staged hidden tile
+    static constexpr int kRingMin = 2 * kTileOBytes + kTcBM * kMaxChainN * 4;
+    static constexpr int kPipeBytes = kTcStages * kStageBytes > kRingMin ? kTcStages * kStageBytes : kRingMin;
     // after the main loop the pipeline ring is dead and holds the staged output tiles
     static constexpr int kOffOhi = 0, kOffOlo = kTileOBytes, kOffLnHi = 2 * kTileOBytes, kOffLnLo = 3 * kTileOBytes;
     static constexpr int kOffC = kPipeBytes;  // fp32 tile: residual in (TMA load during the main loop), C out, in place
-    static constexpr int kTotal = kPipeBytes + kTileCBytes + 1024;  // + alignment slack
+    // chained second GEMM (FC2 partial inside the FC1 kernel): its weight slice [N2 <= 192][64] per part lives where the fp32
+    // tile would be, its fp32 result tile [128][N2] is staged in the dead ring behind the two hidden-tile parts
+    static constexpr int kOffB2 = kPipeBytes, kB2PartBytes = kMaxChainN * 128, kOffP = 2 * kTileOBytes;
+    static constexpr int kTailBytes = kParts * kB2PartBytes > kTileCBytes ? kParts * kB2PartBytes : kTileCBytes;
+    static constexpr int kTotal = kPipeBytes + kTailBytes + 1024;  // + alignment slack
     static_assert(4 * kTileOBytes <= kPipeBytes, "staging must fit in the dead pipeline ring");
+    static_assert(kOffP + kTcBM * kMaxChainN * 4 <= kPipeBytes, "chained result tile must fit in the dead pipeline ring");
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -109,7 +117,7 @@ __device__ __forceinline__ void store_tile_vt(const CUtensorMap* m, const uint8_
 template <int NSPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcGemmArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages], accum_bar, resid_bar;
+    __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages], accum_bar, resid_bar, b2_bar, accum2_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float2 ln_part[kMaxLnCluster][kTcColGroups][kTcBM];
     __shared__ unsigned long long* trace_slot;
@@ -121,8 +129,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const int row = (warp & 3) * 32 + lane;   // accumulator row inside the tile = TMEM lane
     const int g = warp >> 2;                  // column group: columns 16 g .. 16 g + 15 of the tile
     const int n0 = blockIdx.x * kTcBN, m0 = blockIdx.y * kTcBM;
-    const int num_kb = a.K / kTcBK;
+    // split-K over blockIdx.z: this CTA contracts k-blocks [kb0, kb0 + num_kb) and stores its fp32 partial tile to C[.., z]
+    const int num_kb = a.kb_per_split ? a.kb_per_split : a.K / kTcBK;
+    const int kb0 = blockIdx.z * num_kb;
     const int npre = num_kb < kTcStages ? num_kb : kTcStages;
+    const uint32_t tmem_cols = a.chain_n == 0 ? kTcBN : (a.chain_n <= 64 ? 128 : 256);
     bool ok = true;
     TraceRec tr;
     tr.begin(&trace_slot, a.trace, a.trace_id);
@@ -132,14 +143,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         tma_prefetch_desc(&mp.Ahi), tma_prefetch_desc(&mp.Bhi);
         if (kLo) tma_prefetch_desc(&mp.Alo), tma_prefetch_desc(&mp.Blo);
         for (int s = 0; s < kTcStages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
-        mbar_init(&accum_bar, 1), mbar_init(&resid_bar, 1);
+        mbar_init(&accum_bar, 1), mbar_init(&resid_bar, 1), mbar_init(&b2_bar, 1), mbar_init(&accum2_bar, 1);
         fence_barrier_init();
         // the weights never depend on the preceding kernel: start streaming them right away
         for (int kb = 0; kb < npre; ++kb) {
             uint8_t* sb = smem + kb * SM::kStageBytes + SM::kParts * kTileABytes;
             mbar_arrive_expect_tx(&full_bar[kb], SM::kStageBytes);
-            tma_load_2d(sb, &mp.Bhi, &full_bar[kb], kb * kTcBK, n0);
-            if (kLo) tma_load_2d(sb + kTileBBytes, &mp.Blo, &full_bar[kb], kb * kTcBK, n0);
+            tma_load_2d(sb, &mp.Bhi, &full_bar[kb], (kb0 + kb) * kTcBK, n0);
+            if (kLo) tma_load_2d(sb + kTileBBytes, &mp.Blo, &full_bar[kb], (kb0 + kb) * kTcBK, n0);
+        }
+        if (a.chain_n) {  // weight slice of the chained GEMM: W2[0..N2)[n0 .. n0 + 64), one box per precision part
+            tma_prefetch_desc(&mp.B2hi), tma_prefetch_desc(&mp.P);
+            mbar_arrive_expect_tx(&b2_bar, SM::kParts * a.chain_n * 128);
+            tma_load_2d(smem + SM::kOffB2, &mp.B2hi, &b2_bar, n0, 0);
+            if (kLo) tma_load_2d(smem + SM::kOffB2 + SM::kB2PartBytes, &mp.B2lo, &b2_bar, n0, 0);
         }
         if (a.residual) tma_prefetch_desc(&mp.R);
         if (a.c_on) tma_prefetch_desc(&mp.C);
@@ -147,7 +164,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         if (a.ln_g) tma_prefetch_desc(&mp.LnHi), tma_prefetch_desc(&mp.LnLo);
     }
     if (warp == 1) {
-        tmem_alloc(&tmem_base_s, kTcBN);  // 64 fp32 accumulator columns
+        tmem_alloc(&tmem_base_s, tmem_cols);  // 64 fp32 accumulator columns (+ N2 for a chained second GEMM)
         tmem_relinquish();
     }
     tcgen05_fence_before();
@@ -170,17 +187,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     ok &= mbar_wait(&empty_bar[s], ((kb / kTcStages) - 1) & 1);
                     mbar_arrive_expect_tx(&full_bar[s], SM::kStageBytes);
                     uint8_t* sb = st + SM::kParts * kTileABytes;
-                    tma_load_2d(sb, &mp.Bhi, &full_bar[s], kb * kTcBK, n0);
-                    if (kLo) tma_load_2d(sb + kTileBBytes, &mp.Blo, &full_bar[s], kb * kTcBK, n0);
+                    tma_load_2d(sb, &mp.Bhi, &full_bar[s], (kb0 + kb) * kTcBK, n0);
+                    if (kLo) tma_load_2d(sb + kTileBBytes, &mp.Blo, &full_bar[s], (kb0 + kb) * kTcBK, n0);
                 }
                 if (a.conv_feat) {  // 3x3 conv: K index = tap * feat + d; A rows are the 16x16 grid of one target
-                    const int chunks = a.conv_feat / kTcBK, tap = kb / chunks, d0 = (kb % chunks) * kTcBK;
+                    const int chunks = a.conv_feat / kTcBK, tap = (kb0 + kb) / chunks, d0 = ((kb0 + kb) % chunks) * kTcBK;
                     const int b = m0 / kNTx, y0 = (m0 % kNTx) / kMap;
                     tma_load_4d(st, &mp.Ahi, &full_bar[s], d0, tap % 3 - 1, y0 + tap / 3 - 1, b);
                     if (kLo) tma_load_4d(st + kTileABytes, &mp.Alo, &full_bar[s], d0, tap % 3 - 1, y0 + tap / 3 - 1, b);
                 } else {
-                    tma_load_2d(st, &mp.Ahi, &full_bar[s], kb * kTcBK, m0);
-                    if (kLo) tma_load_2d(st + kTileABytes, &mp.Alo, &full_bar[s], kb * kTcBK, m0);
+                    tma_load_2d(st, &mp.Ahi, &full_bar[s], (kb0 + kb) * kTcBK, m0);
+                    if (kLo) tma_load_2d(st + kTileABytes, &mp.Alo, &full_bar[s], (kb0 + kb) * kTcBK, m0);
                 }
                 if (kb == 0 && a.residual) {  // residual rows of this tile (flat [rows][N] fp32), two 128-byte-wide boxes
                     mbar_arrive_expect_tx(&resid_bar, kTileCBytes);
@@ -277,7 +294,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         for (int q = 0; q < 4; ++q)
             *reinterpret_cast<float4*>(c_row + (((c_chunk0 + q) ^ sw) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
-    if (a.o_mode) {
+    if (a.o_mode) {  // (o_mode 3: staged only — the tile is the A operand of the chained GEMM)
         if (o_which < 2) {
             stage_split16(v, smem + SM::kOffOhi, smem + SM::kOffOlo, row, g, kLo);
         } else {  // V^T: two unswizzled [64 d][64 tokens] sub-tiles; lanes are consecutive tokens -> 64-byte contiguous runs
@@ -299,7 +316,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     __syncthreads();
     if (tid == 0 && a.trace_id == 2) tr.mark(4);
     if (tid == 0) {
-        if (a.c_on) {
+        if (a.c_on && a.kb_per_split) {  // split-K partial: C map is {cols, rows per target, targets, splits}
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                tma_store_4d(&mp.C, sC + k * kHalfBytes, n0, tr_rows.t[k], tr_rows.b[k], blockIdx.z);
+                tma_store_4d(&mp.C, sC + kTileCBytes / 2 + k * kHalfBytes, n0 + 32, tr_rows.t[k], tr_rows.b[k], blockIdx.z);
+            }
+        } else if (a.c_on) {
             store_tile(&mp.C, sC, n0, tr_rows, a.c_row_off, 0);
             store_tile(&mp.C, sC + kTileCBytes / 2, n0 + 32, tr_rows, a.c_row_off, 0);
         }
@@ -317,6 +340,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         }
         tma_store_commit();
         tr.mark(7);
+    }
+    if (a.chain_n) {
+        // ---- chained GEMM: P_j[128, N2] = hidden tile (just staged as a 128B-swizzled K-major A operand, bf16 hi / lo) x
+        // W2[:, n0 .. n0 + 64)^T.  The hidden activations never travel to global memory; the N / 64 partial results P_j of one row
+        // tile are summed in a fixed order by reduce_ln_kernel, which also applies bias, residual and the next LayerNorm.
+        const int N2 = a.chain_n;
+        if (warp == 1 && lane == 0) {
+            ok &= mbar_wait(&b2_bar, 0);
+            tcgen05_fence_after();
+            const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2);
+            const uint64_t dA = umma_desc_sw128(smem_u32(smem + SM::kOffOhi)), dB = umma_desc_sw128(smem_u32(smem + SM::kOffB2));
+            constexpr uint64_t kLoA = kTileOBytes >> 4, kLoB = SM::kB2PartBytes >> 4;
+#pragma unroll
+            for (int k = 0; k < kTcBN / 16; ++k) {
+                umma_bf16(tmem + kTcBN, dA + 2 * k, dB + 2 * k, idesc2, k != 0);
+                if (kLo) {
+                    umma_bf16(tmem + kTcBN, dA + 2 * k, dB + kLoB + 2 * k, idesc2, 1);
+                    umma_bf16(tmem + kTcBN, dA + kLoA + 2 * k, dB + 2 * k, idesc2, 1);
+                }
+            }
+            umma_commit(&accum2_bar);
+        }
+        __syncwarp();
+        ok &= mbar_wait(&accum2_bar, 0);
+        tcgen05_fence_after();
+        if (tid == 0) tr.mark(5);
+        // thread (row, g) owns columns g * N2/4 .. of its row; fp32 tile staged as N2/32 boxes of [128 rows][128 B], swizzled
+        const int cols_per = N2 / kTcColGroups;
+        for (int c = g * cols_per; c < (g + 1) * cols_per; c += 16) {
+            float p[16];
+            tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kTcBN + c, p);
+            uint8_t* prow = smem + SM::kOffP + (c >> 5) * (kTcBM * 128) + row * 128;
+            const int ch0 = (c & 31) >> 2;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(prow + (((ch0 + q) ^ sw) << 4)) = make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) tr.mark(4);
+        if (tid < N2 / 32) {  // one thread per 32-column box: two 64-row tile stores each into P[j = blockIdx.x][target][row][col]
+            const uint8_t* src = smem + SM::kOffP + tid * (kTcBM * 128);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) tma_store_4d(&mp.P, src + k * kHalfBytes, tid * 32, tr_rows.t[k], tr_rows.b[k], blockIdx.x);
+            tma_store_commit();
+            if (tid != 0) tma_store_wait_read();
+        }
     }
     if (a.ln_g) {  // ---- fused LayerNorm over the full row (N columns = cluster of N / 64 CTAs x 4 column groups)
         const uint32_t nct = cluster_nctarank(), me = cluster_ctarank();
@@ -375,7 +445,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     tcgen05_fence_before();
     __syncthreads();
     if (tid == 0) tr.mark(3);
-    if (warp == 1) tmem_dealloc(tmem, kTcBN);
+    if (warp == 1) tmem_dealloc(tmem, tmem_cols);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -447,6 +517,21 @@ bool tc_resid_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t c
     return tc_make_map_ex(out, base, 4, 2, dims, strides, box, true);
 }
 
+// chained second GEMM of plan p: weights W2 [N2][K2] (K2 = N of the first GEMM), partial results P [N/64][batch][rows][N2] fp32
+bool tc_plan_chain(TcGemmPlan* p, const __nv_bfloat16* W2hi, const __nv_bfloat16* W2lo, int N2, float* P, uint64_t rows, uint64_t batch) {
+    if (N2 % 64 || N2 > kMaxChainN) {
+        set_error("chained GEMM needs N2 %% 64 == 0 and N2 <= %d (N2=%d)", kMaxChainN, N2);
+        return false;
+    }
+    const uint64_t K2 = (uint64_t)p->args.N;
+    const uint64_t dims[2] = {K2, (uint64_t)N2}, strides[1] = {K2 * 2};
+    const uint32_t box[2] = {(uint32_t)kTcBK, (uint32_t)N2};
+    bool ok = tc_make_map(&p->maps.B2hi, W2hi, 2, dims, strides, box) && tc_make_map(&p->maps.B2lo, W2lo ? W2lo : W2hi, 2, dims, strides, box);
+    ok = ok && tc_out_map(&p->maps.P, P, 4, N2, rows, batch, K2 / kTcBN);
+    p->args.chain_n = N2, p->args.o_mode = 3;
+    return ok;
+}
+
 bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, uint64_t a_rows, const __nv_bfloat16* Whi,
                   const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch) {
     memset(p, 0, sizeof(*p));
@@ -468,7 +553,7 @@ bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* 
     ok &= tc_make_map_2d(&p->maps.Bhi, Whi, N, K, kTcBN);
     ok &= tc_make_map_2d(&p->maps.Blo, Wlo ? Wlo : Whi, N, K, kTcBN);
     // unused output maps must still be valid descriptors (they are never dereferenced when their mode is off)
-    p->maps.R = p->maps.C = p->maps.LnHi = p->maps.LnLo = p->maps.Bhi;
+    p->maps.R = p->maps.C = p->maps.LnHi = p->maps.LnLo = p->maps.B2hi = p->maps.B2lo = p->maps.P = p->maps.Bhi;
     for (auto& m : p->maps.O) m = p->maps.Bhi;
     p->args.N = N, p->args.K = K, p->args.conv_feat = conv_feat;
     p->args.pos_rows = 1, p->args.period = 1 << 30;
@@ -485,7 +570,7 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t 
     if (M <= 0) return cudaSuccess;
     TcGemmArgs a = p.args;
     a.M = M;
-    const dim3 grid(a.N / kTcBN, (M + kTcBM - 1) / kTcBM);
+    const dim3 grid(a.N / kTcBN, (M + kTcBM - 1) / kTcBM, a.kb_per_split ? a.K / kTcBK / a.kb_per_split : 1);
     int cluster_x = 1;
     if (a.ln_g) {
         cluster_x = a.N / kTcBN;

@@ -87,6 +87,11 @@ struct vt_tracker {
     __nv_bfloat16 *q_hi = nullptr, *q_lo = nullptr, *k_hi = nullptr, *k_lo = nullptr, *vt_hi = nullptr, *vt_lo = nullptr;
     __nv_bfloat16 *zln_hi = nullptr, *zln_lo = nullptr;  // LN1 (block 0) of the template tokens, [B][64][D], computed at init
     bool fuse_ln = false;       // LayerNorm fused into the producing GEMM's epilogue (cluster of D / 64 CTAs)
+    bool chain_mlp = false;     // FC2 partial products computed inside the FC1 kernel + reduce_ln_kernel (no hidden round trip)
+    float* Pbuf = nullptr;      // [hidden / 64][B][320][D] fp32 partial FC2 results (also the 4 split-K partials of the patch embed)
+    bool split_k = false;       // patch embed and 3x3 head conv as split-K partial GEMMs + reduce kernels
+    float *Phead = nullptr, *d_cand = nullptr;  // [9 taps][B][256][head_ch] conv partials; [B][16][8] row candidates of the decode
+    unsigned* d_counters = nullptr;
     bool pdl = true;            // programmatic dependent launch along the kernel chain
     bool tc_attention = false;  // head_dim == 64
     TcAttentionPlan plan_att;
@@ -282,6 +287,13 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
         const int ns = t->nsplit;
         const bool pdl = t->pdl && !t->debug_capture, fuse = t->fuse_ln;
         VT_LAUNCH(tc_gemm_launch(t->plan_patch_x, n * kNTx, ns, s, pdl));  // fused: + LN1 of block 0 for the search rows
+        if (t->split_k) {  // X[64.., :] = pos_x + patch_b + sum of the 4 K-slices; LN1 of block 0
+            ReduceLnArgs r{};
+            r.P = t->Pbuf, r.np = 4, r.p_stride = (int64_t)t->maxT * kNTx * D, r.bias = t->patch_b, r.add = t->pos_x, r.add_period = kNTx;
+            r.X = t->X, r.M = n * kNTx, r.D = D, r.period = kNTx, r.x_rows = kNTok, r.x_row_off = kNTz;
+            r.ln_g = t->blk[0].ln1_g, r.ln_b = t->blk[0].ln1_b, r.ln_hi = t->ln_hi, r.ln_lo = t->ln_lo, r.ln_rows = kNTok, r.ln_row_off = kNTz;
+            VT_LAUNCH(launch_reduce_ln(r, s, pdl));
+        }
         if (t->debug_capture) VT_CUDA(cudaMemcpyAsync(t->d_dbg, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
         for (int l = 0; l < t->depth; ++l) {
             const BlockW& b = t->blk[l];
@@ -294,8 +306,19 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                 VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
             VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention));  // fused: + LN2
             if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
-            VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s, pdl));
-            VT_LAUNCH(tc_gemm_launch(p.fc2, M, ns, s, pdl));  // fused: + LN1 of the next block / the final LN of the search rows
+            VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s, pdl));  // chained: + the FC2 partial products of its 64 hidden columns
+            if (t->chain_mlp) {  // X += fc2_b + sum of the partials; LN1 of the next block / the final LN of the search rows
+                const bool last = l + 1 == t->depth;
+                ReduceLnArgs r{};
+                r.P = t->Pbuf, r.np = Hd / 64, r.p_stride = (int64_t)t->maxT * kNTok * D, r.bias = b.fc2_b, r.add = t->X, r.add_period = 0;
+                r.X = t->X, r.M = M, r.D = D, r.period = kNTok, r.x_rows = kNTok, r.x_row_off = 0;
+                r.ln_g = last ? t->lnf_g : t->blk[l + 1].ln1_g, r.ln_b = last ? t->lnf_b : t->blk[l + 1].ln1_b;
+                r.ln_hi = last ? t->yf_hi : t->ln_hi, r.ln_lo = last ? t->yf_lo : t->ln_lo;
+                r.ln_rows = last ? kNTx : kNTok, r.ln_row_off = last ? -kNTz : 0;
+                VT_LAUNCH(launch_reduce_ln(r, s, pdl));
+            } else {
+                VT_LAUNCH(tc_gemm_launch(p.fc2, M, ns, s, pdl));  // fused: + LN1 of the next block / the final LN of the search rows
+            }
             if (t->debug_capture)
                 VT_CUDA(cudaMemcpyAsync(t->d_dbg + (size_t)(l + 1) * t->maxT * kNTok * D, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
         }
@@ -303,7 +326,11 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
         VT_LAUNCH(tc_gemm_launch(t->plan_head, n * kNTx, ns, s, pdl));
     }
     if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_VIT], s, ev_flags));
-    VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, s));
+    if (t->nsplit && t->split_k)
+        VT_LAUNCH(launch_head_decode(t->Phead, 9, (int64_t)t->maxT * kNTx * C, C, t->h1_b, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n,
+                                     t->threshold, t->d_res, t->d_maps, t->d_cand, t->d_counters, s, false));
+    else
+        VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, s));
     if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_DEC], s, ev_flags));
     if (t->cfg.box_overlay)
         VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, t->fmt, t->d_res, t->d_slots, n, t->cfg.overlay_gate, s));
@@ -580,7 +607,7 @@ void vt_tracker_destroy(vt_tracker* t) {
     void* dev[] = {t->d_weights, t->d_lut, t->d_hann, t->d_frame, t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
                    t->patches_x, t->patches_z, t->Zemb, t->X, t->QKV, t->ATT, t->HID, t->Yf, t->H1, t->d_dbg,
                    t->w_hi, t->w_lo, t->px_hi, t->px_lo, t->pz_hi, t->pz_lo, t->ln_hi, t->ln_lo, t->att_hi, t->att_lo,
-                   t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->d_tc_err, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, t->zln_hi, t->zln_lo, t->d_trace};
+                   t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->d_tc_err, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, t->zln_hi, t->zln_lo, t->d_trace, t->Pbuf, t->Phead, t->d_cand, t->d_counters};
     for (void* p : dev)
         if (p) cudaFree(p);
     if (t->h_stage) cudaFreeHost(t->h_stage);
@@ -684,6 +711,15 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         VT_TRY(tc_gemm_setup());
         t->fuse_ln = D / 64 <= 8 && !getenv("VT_B200_NO_FUSE_LN");
         t->pdl = !getenv("VT_B200_NO_PDL");
+        t->chain_mlp = t->fuse_ln && D <= 192 && !getenv("VT_B200_NO_CHAIN");
+        if (t->chain_mlp) VT_TRY(cudaMalloc(&t->Pbuf, sizeof(float) * (Hd / 64) * B * kNTok * D));
+        t->split_k = t->chain_mlp && Hd / 64 >= 4 && (C == 64 || C == 128) && !getenv("VT_B200_NO_SPLITK");
+        if (t->split_k) {
+            VT_TRY(cudaMalloc(&t->Phead, sizeof(float) * 9 * B * kNTx * C));
+            VT_TRY(cudaMalloc(&t->d_cand, sizeof(float) * B * 16 * 8));
+            VT_TRY(cudaMalloc(&t->d_counters, sizeof(unsigned) * B));
+            VT_TRY(cudaMemset(t->d_counters, 0, sizeof(unsigned) * B));
+        }
         const size_t nw = t->n_weights;
         VT_TRY(cudaMalloc(&t->w_hi, nw * 2)); VT_TRY(cudaMalloc(&t->w_lo, nw * 2));
         VT_TRY(launch_split_bf16(t->d_weights, t->w_hi, t->w_lo, nw, t->stream));
@@ -737,7 +773,10 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             TcGemmArgs& a = t->plan_patch_x.args;
             a.bias = t->patch_b, a.pos = t->pos_x, a.pos_rows = kNTx;
             a.period = kNTx, a.c_on = 1, a.c_row_off = kNTz, t->plan_patch_x.maps.C = mX;
-            if (t->fuse_ln) {  // LN1 of block 0 for the search rows, straight into the first QKV GEMM's A operand
+            if (t->split_k) {  // 4 x K = 192 slices -> fp32 partials [4][B][256][D]; bias, pos, LN1 happen in reduce_ln_kernel
+                a.bias = nullptr, a.pos = nullptr, a.c_row_off = 0, a.kb_per_split = kPatchK / 64 / 4;
+                ok &= tc_out_map(&t->plan_patch_x.maps.C, t->Pbuf, 4, D, kNTx, B, 4);
+            } else if (t->fuse_ln) {  // LN1 of block 0 for the search rows, straight into the first QKV GEMM's A operand
                 a.ln_g = t->blk[0].ln1_g, a.ln_b = t->blk[0].ln1_b, a.ln_row_off = kNTz;
                 t->plan_patch_x.maps.LnHi = mLnHi, t->plan_patch_x.maps.LnLo = mLnLo;
             }
@@ -768,6 +807,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             ok &= tc_plan_init(&p.fc1, t->ln_hi, t->ln_lo, rows, whi(b.fc1_w), wlo(b.fc1_w), (int)Hd, (int)D, 0, 0);
             p.fc1.args.bias = b.fc1_b, p.fc1.args.gelu = 1, p.fc1.args.period = kNTok, p.fc1.args.o_mode = 1;
             p.fc1.maps.O[0] = mHidHi, p.fc1.maps.O[1] = mHidLo;
+            if (t->chain_mlp) ok &= tc_plan_chain(&p.fc1, whi(b.fc2_w), wlo(b.fc2_w), (int)D, t->Pbuf, kNTok, B);
             ok &= tc_plan_init(&p.fc2, t->hid_hi, t->hid_lo, rows, whi(b.fc2_w), wlo(b.fc2_w), (int)D, (int)Hd, 0, 0);
             p.fc2.args.bias = b.fc2_b, p.fc2.args.period = kNTok, p.fc2.args.residual = 1, p.fc2.args.c_on = 1;
             p.fc2.maps.R = mXres, p.fc2.maps.C = mX;
@@ -784,6 +824,10 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         ok &= tc_plan_init(&t->plan_head, t->yf_hi, t->yf_lo, 0, whi(t->h1_w), wlo(t->h1_w), (int)C, (int)(9 * D), (int)D, (int)B);
         t->plan_head.args.bias = t->h1_b, t->plan_head.args.relu = 1, t->plan_head.args.period = kNTx, t->plan_head.args.c_on = 1;
         t->plan_head.maps.C = mH1;
+        if (t->split_k) {  // one tap per slice -> fp32 partials [9][B][256][C]; bias, ReLU, 1x1 conv and decode in head_decode_kernel
+            t->plan_head.args.bias = nullptr, t->plan_head.args.relu = 0, t->plan_head.args.kb_per_split = (int)(D / 64);
+            ok &= tc_out_map(&t->plan_head.maps.C, t->Phead, 4, C, kNTx, B, 9);
+        }
         if (!ok) return fail(VT_ERR_CUDA);
         for (TcGemmPlan* p : {&t->plan_patch_x, &t->plan_patch_z, &t->plan_head}) p->args.err = t->d_tc_err;
         for (auto& p : t->plans) p.qkv.args.err = p.proj.args.err = p.fc1.args.err = p.fc2.args.err = t->d_tc_err;

@@ -223,6 +223,98 @@ cudaError_t launch_layernorm_split(const float* x, int64_t ldx, const float* g, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sum of the split partial GEMM results + bias + addend (residual / pos-embed), fused with the following LayerNorm
+// (ReduceLnArgs in vt_internal.h).  One warp per row; lane l owns the column pairs 2 l + 64 i: every partial row is read with
+// fully coalesced 8-byte loads, all issued before the first add (one L2 round trip).  The partials are added in index order,
+// so the result does not depend on scheduling.
+// ------------------------------------------------------------------------------------------------
+template <int NPAIR, int NP>  // D / 64 column pairs per lane; number of partials (0 = runtime np, batches of 4)
+__global__ void __launch_bounds__(256) reduce_ln_kernel(const ReduceLnArgs a) {
+    constexpr int D = NPAIR * 64;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= a.M) return;
+    const int b = m / a.period, t = m - b * a.period;
+    const int64_t xrow = (int64_t)b * a.x_rows + t + a.x_row_off;
+    float2 acc[NPAIR];
+    const float2* ar = reinterpret_cast<const float2*>(a.add + (a.add_period ? (int64_t)(m % a.add_period) : xrow) * D);
+#pragma unroll
+    for (int i = 0; i < NPAIR; ++i) {
+        const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.bias) + lane + 32 * i), x2 = ar[lane + 32 * i];
+        acc[i] = make_float2(x2.x + b2.x, x2.y + b2.y);
+    }
+    const float2* pr = reinterpret_cast<const float2*>(a.P + (int64_t)m * D);
+    const int64_t ps = a.p_stride / 2;
+    if (NP > 0) {
+        float2 v[NP > 0 ? NP : 1][NPAIR];
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+#pragma unroll
+            for (int i = 0; i < NPAIR; ++i) v[j][i] = pr[j * ps + lane + 32 * i];
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+#pragma unroll
+            for (int i = 0; i < NPAIR; ++i) acc[i].x += v[j][i].x, acc[i].y += v[j][i].y;
+    } else {
+        for (int j0 = 0; j0 < a.np; j0 += 4) {
+            float2 v[4][NPAIR];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int i = 0; i < NPAIR; ++i) v[jj][i] = j0 + jj < a.np ? pr[(j0 + jj) * ps + lane + 32 * i] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int i = 0; i < NPAIR; ++i) acc[i].x += v[jj][i].x, acc[i].y += v[jj][i].y;
+        }
+    }
+    float2* xw = reinterpret_cast<float2*>(a.X + xrow * D);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPAIR; ++i) xw[lane + 32 * i] = acc[i], s += acc[i].x + acc[i].y;
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPAIR; ++i) {
+        const float dx = acc[i].x - mean, dy = acc[i].y - mean;
+        q += dx * dx + dy * dy;
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(q) / (float)D + 1e-6f);
+    if (t + a.ln_row_off < 0) return;
+    const int64_t orow = (int64_t)b * a.ln_rows + t + a.ln_row_off;
+    uint32_t* oh = reinterpret_cast<uint32_t*>(a.ln_hi + orow * D);
+    uint32_t* ol = reinterpret_cast<uint32_t*>(a.ln_lo + orow * D);
+#pragma unroll
+    for (int i = 0; i < NPAIR; ++i) {
+        const float2 g2 = __ldg(reinterpret_cast<const float2*>(a.ln_g) + lane + 32 * i), b2 = __ldg(reinterpret_cast<const float2*>(a.ln_b) + lane + 32 * i);
+        const float y0 = (acc[i].x - mean) * rstd * g2.x + b2.x, y1 = (acc[i].y - mean) * rstd * g2.y + b2.y;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+        oh[lane + 32 * i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        ol[lane + 32 * i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+}
+
+cudaError_t launch_reduce_ln(const ReduceLnArgs& a, cudaStream_t s, bool pdl) {
+    if (a.M <= 0) return cudaSuccess;
+    const dim3 grid((a.M + 7) / 8), block(256);
+#define VT_RL(NPAIR_, NP_) return launch_ex(reduce_ln_kernel<NPAIR_, NP_>, grid, block, 0, s, pdl, 1, a)
+    switch (a.D / 64) {
+        case 1:
+            if (a.np == 4) VT_RL(1, 4);
+            VT_RL(1, 0);
+        case 2: VT_RL(2, 0);
+        case 3:
+            if (a.np == 12) VT_RL(3, 12);
+            if (a.np == 4) VT_RL(3, 4);
+            VT_RL(3, 0);
+        default: return cudaErrorInvalidValue;
+    }
+#undef VT_RL
+}
+
+// ------------------------------------------------------------------------------------------------
 // Attention over the joint 320-token sequence: one CTA per (16-query tile, head, target).
 // scores -> shared memory, warp-shuffle softmax, P*V from shared memory.
 // ------------------------------------------------------------------------------------------------
@@ -410,6 +502,142 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ h
         }
         res[slot] = r;
     }
+}
+
+// rect_last update + result record from the winning cell (App. A.6); shared by both decode kernels
+__device__ void decode_finish(TargetState* st, int slot, float threshold, float score, int best, float ox, float oy, float bw, float bh,
+                              DeviceResult* res) {
+    DeviceResult r;
+    r.success = 0, r.score = 0.f, r.bbox[0] = r.bbox[1] = r.bbox[2] = r.bbox[3] = 0, r.best = best;
+    r.status = VT_OK;
+    if (!st->active) {
+        r.status = VT_ERR_NOT_INIT;
+    } else if (st->crop_err) {
+        r.status = VT_ERR_CROP_OUTSIDE;
+    } else {
+        r.score = score;
+        if (r.score >= threshold) {
+            const int my = best / kMap, mx = best % kMap;
+            const float cx = __fdiv_rn(__fadd_rn((float)mx, ox), 16.f);
+            const float cy = __fdiv_rn(__fadd_rn((float)my, oy), 16.f);
+            const int lx = st->rect[0], ly = st->rect[1], lw = st->rect[2], lh = st->rect[3];
+            const int cwin = (int)ceil(__dmul_rn(sqrt((double)((long long)lw * lh)), 4.0));
+            const int x0 = lx + (lw - cwin) / 2, y0 = ly + (lh - cwin) / 2;
+            const float fc = (float)cwin;
+            r.bbox[0] = (int)floorf(__fadd_rn(__fmul_rn(__fsub_rn(cx, __fdiv_rn(bw, 2.f)), fc), (float)x0));
+            r.bbox[1] = (int)floorf(__fadd_rn(__fmul_rn(__fsub_rn(cy, __fdiv_rn(bh, 2.f)), fc), (float)y0));
+            r.bbox[2] = (int)floorf(__fmul_rn(bw, fc));
+            r.bbox[3] = (int)floorf(__fmul_rn(bh, fc));
+            r.success = 1;
+            st->rect[0] = r.bbox[0], st->rect[1] = r.bbox[1], st->rect[2] = r.bbox[2], st->rect[3] = r.bbox[3];
+        }
+    }
+    res[slot] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7b + K8 for the tensor-core path: the 3x3 head conv arrives as one fp32 partial per tap (split-K GEMM); this kernel sums
+// them (+ bias, ReLU), applies the 1x1 conv, sigmoid and hann window and finds the first row-major maximum.
+// grid (16 map rows, targets) x 256 threads: warp w owns cells 2w, 2w+1 of the row, lane l owns channels CPL l .. CPL l + CPL - 1
+// (coalesced 16-byte loads, every partial of a cell in flight at once); the 1x1 conv is a warp-shuffle reduction.
+// The 16 row candidates of a target are merged by the last CTA to arrive (atomic ticket), in row order -> deterministic.
+// ------------------------------------------------------------------------------------------------
+template <int N> struct VecOf;
+template <> struct VecOf<4> { typedef float4 type; };
+template <> struct VecOf<2> { typedef float2 type; };
+constexpr int kCandStride = 8;  // floats per row candidate: value, index, off_x, off_y, size_w, size_h
+template <int CPL>  // channels per lane: head_ch / 32
+__global__ void __launch_bounds__(256) head_decode_kernel(const float* __restrict__ P, int np, int64_t p_stride, const float* __restrict__ b1,
+                                                          const float* __restrict__ w2, const float* __restrict__ b2,
+                                                          const float* __restrict__ hann, TargetState* __restrict__ state,
+                                                          const int32_t* __restrict__ slots, float threshold, DeviceResult* __restrict__ res,
+                                                          float* __restrict__ maps, float* cand, unsigned* counters) {
+    constexpr int C = CPL * 32;
+    __shared__ float s_c[16][6];
+    __shared__ int s_last;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int bi = blockIdx.y, slot = slots[bi], y = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float w[5][CPL], bch[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        bch[c] = __ldg(b1 + lane * CPL + c);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[k][c] = __ldg(w2 + k * C + lane * CPL + c);
+    }
+    using Vec = typename VecOf<CPL>::type;  // float4 / float2: one coalesced load per lane and partial
+    float hsum[2][CPL];
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int cell = y * kMap + 2 * warp + cc;
+        const float* pr = P + ((int64_t)bi * kNTx + cell) * C + lane * CPL;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) hsum[cc][c] = bch[c];
+        for (int j0 = 0; j0 < np; j0 += 3) {  // three taps (one kernel row) in flight per cell
+            Vec v[3];
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) v[jj] = j0 + jj < np ? *reinterpret_cast<const Vec*>(pr + (int64_t)(j0 + jj) * p_stride) : Vec{};
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj)
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) hsum[cc][c] += reinterpret_cast<const float*>(&v[jj])[c];
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int p = y * kMap + 2 * warp + cc;
+        float o[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            float d = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) d = fmaf(fmaxf(hsum[cc][c], 0.f), w[k][c], d);
+            o[k] = warp_sum(d) + __ldg(b2 + k);
+        }
+        if (lane == 0) {
+            const float conf = 1.f / (1.f + expf(-o[0]));
+            const float sw = 1.f / (1.f + expf(-o[1])), sh = 1.f / (1.f + expf(-o[2]));
+            const float cw = __fmul_rn(conf, hann[p]);
+            float* mm = maps + (int64_t)slot * 1280;
+            mm[p] = cw, mm[256 + p] = sw, mm[512 + p] = sh, mm[768 + p] = o[3], mm[1024 + p] = o[4];
+            float* sc = s_c[2 * warp + cc];
+            sc[0] = cw, sc[1] = o[3], sc[2] = o[4], sc[3] = sw, sc[4] = sh;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0;
+        for (int i = 1; i < 16; ++i)
+            if (s_c[i][0] > s_c[best][0]) best = i;  // first maximum of the row
+        float* cd = cand + ((int64_t)bi * 16 + y) * kCandStride;
+        cd[0] = s_c[best][0], cd[1] = (float)(y * kMap + best), cd[2] = s_c[best][1], cd[3] = s_c[best][2], cd[4] = s_c[best][3], cd[5] = s_c[best][4];
+        __threadfence();
+        s_last = atomicAdd(&counters[bi], 1u) == 15u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const volatile float* cd = cand + (int64_t)bi * 16 * kCandStride;
+        int by = 0;
+        for (int i = 1; i < 16; ++i)
+            if (cd[i * kCandStride] > cd[by * kCandStride]) by = i;  // rows in ascending order: first row-major maximum
+        const volatile float* c = cd + by * kCandStride;
+        decode_finish(state + slot, slot, threshold, c[0], (int)c[1], c[2], c[3], c[4], c[5], res);
+        counters[bi] = 0;  // ready for the next frame
+    }
+}
+
+cudaError_t launch_head_decode(const float* P, int np, int64_t p_stride, int head_ch, const float* b1, const float* w2, const float* b2,
+                               const float* hann, TargetState* d_state, const int32_t* d_slots, int n, float threshold, DeviceResult* d_res,
+                               float* d_maps, float* d_cand, unsigned* d_counters, cudaStream_t s, bool pdl) {
+    if (n <= 0) return cudaSuccess;
+    const dim3 grid(kMap, n), block(256);
+    if (head_ch == 128)
+        return launch_ex(head_decode_kernel<4>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters);
+    if (head_ch == 64)
+        return launch_ex(head_decode_kernel<2>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_decode(const float* h1, int head_ch, const float* w2, const float* b2, const float* hann, TargetState* d_state,

@@ -161,6 +161,29 @@ cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* g, const 
 // LayerNorm whose output is written as a bf16 (hi, lo) split [M, D] (dense rows) for the tensor-core GEMMs
 cudaError_t launch_layernorm_split(const float* x, int64_t ldx, const float* g, const float* b, __nv_bfloat16* hi, __nv_bfloat16* lo, int M,
                                    int D, int rows_in, int rows_stride, int row_off, cudaStream_t s, bool pdl = false);
+// Sum of np partial GEMM results (fixed order) + bias + an fp32 addend row, fused with the following LayerNorm; one warp per row m:
+//   v = add[(add_period ? m % add_period : xrow) * D ..] + bias + sum_j P[j][m, :]
+//   X[xrow, :] = v                      xrow = (m / period) * x_rows + m % period + x_row_off
+//   ln_hi/lo[lrow, :] = split(LN(v))    lrow = (m / period) * ln_rows + m % period + ln_row_off   (skipped when m % period + ln_row_off < 0)
+// MLP: add = X (residual), add_period = 0.  Patch embed: add = pos_x, add_period = 256, rows land at 64.. of every target.
+struct ReduceLnArgs {
+    const float* P;
+    int np;
+    int64_t p_stride;         // elements between partials
+    const float *bias, *add;
+    int add_period;
+    float* X;
+    int M, D, period, x_rows, x_row_off;
+    const float *ln_g, *ln_b;
+    __nv_bfloat16 *ln_hi, *ln_lo;
+    int ln_rows, ln_row_off;
+};
+cudaError_t launch_reduce_ln(const ReduceLnArgs& a, cudaStream_t s, bool pdl);
+// 3x3 head conv partials (one per tap) -> + bias, ReLU -> 1x1 conv -> sigmoid / hann / arg-max / bbox decode (App. A.5-A.6).
+// 16 CTAs per target (one map row each); the last one to finish merges the 16 row candidates and updates rect_last.
+cudaError_t launch_head_decode(const float* P, int np, int64_t p_stride, int head_ch, const float* b1, const float* w2, const float* b2,
+                               const float* hann, TargetState* d_state, const int32_t* d_slots, int n, float threshold, DeviceResult* d_res,
+                               float* d_maps, float* d_cand, unsigned* d_counters, cudaStream_t s, bool pdl);
 // qkv: [B*320, 3D]; out: [B*320, D] fp32 (nullable) and/or bf16 split (nullable)
 cudaError_t launch_attention(const float* qkv, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int B, int D, int heads,
                              cudaStream_t s);
@@ -181,7 +204,11 @@ struct TcGemmArgs {
     // 4-D output maps {cols, rows per target, heads, targets}; rows outside a target's range are clipped by the TMA unit.
     int period, batch_off;
     int c_on, c_row_off;      // fp32 tile -> maps.C
-    int o_mode;               // 0 off; 1 bf16 split tile -> maps.O[0] (hi), O[1] (lo); 2 QKV scatter -> O[0..5] = Q, K, V^T (hi, lo)
+    int o_mode;               // 0 off; 1 bf16 split tile -> maps.O[0] (hi), O[1] (lo); 2 QKV scatter -> O[0..5] = Q, K, V^T (hi, lo);
+                              // 3 staged in shared memory only (A operand of the chained GEMM)
+    int kb_per_split;         // split-K: 64-wide k-blocks per blockIdx.z slice (0 = no split); the fp32 partial tile of slice z goes to
+                              // maps.C = {cols, rows per target, targets, splits} and bias / activations / residual must be off
+    int chain_n;              // N2 of a chained second GEMM (0 = off): P[blockIdx.x] = tile x W2[:, n0..n0+64)^T -> maps.P
     int o_row_off;
     // LayerNorm of the full output row fused into the epilogue (cluster of N / 64 CTAs): y = LN(row) * g + b -> maps.LnHi / LnLo
     const float *ln_g, *ln_b; // null = off
@@ -190,8 +217,8 @@ struct TcGemmArgs {
     unsigned long long* trace; // device timeline buffer (diagnostics) or null
     int trace_id;
 };
-struct TcMaps {               // kernel parameter block (__grid_constant__): 14 descriptors
-    CUtensorMap Ahi, Alo, Bhi, Blo, R, C, O[6], LnHi, LnLo;
+struct TcMaps {               // kernel parameter block (__grid_constant__): 17 descriptors
+    CUtensorMap Ahi, Alo, Bhi, Blo, R, C, O[6], LnHi, LnLo, B2hi, B2lo, P;
 };
 struct TcGemmPlan {
     TcMaps maps;
@@ -199,6 +226,7 @@ struct TcGemmPlan {
 };
 bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, uint64_t a_rows, const __nv_bfloat16* Whi,
                   const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch);
+bool tc_plan_chain(TcGemmPlan* p, const __nv_bfloat16* W2hi, const __nv_bfloat16* W2lo, int N2, float* P, uint64_t rows, uint64_t batch);
 // output tile maps over dense [batch][heads][rows][cols] tensors (elem_bytes 2 = bf16, 4 = fp32), V^T [batch][heads][64][tokens],
 // and the flat fp32 residual source
 bool tc_out_map(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint64_t heads, uint64_t batch);
