@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, Targ
                                                                const int32_t* __restrict__ slots, int factor, int S,
                                                                const float* __restrict__ lut, float* __restrict__ patches,
                                                                size_t patches_stride, __nv_bfloat16* __restrict__ p_hi,
-                                                               __nv_bfloat16* __restrict__ p_lo) {
+                                                               __nv_bfloat16* __restrict__ p_lo, unsigned long long* stamp) {
+    if (stamp && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) *stamp = device_time_ns();
     const int bi = blockIdx.y;
     const int slot = slots[bi];
     TargetState* st = state + slot;
@@ -241,10 +242,10 @@ __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, Targ
 
 cudaError_t launch_crop_resize_norm(FrameDesc f, TargetState* d_state, const int32_t* d_slots, int n, int factor, int out_size,
                                     const float* d_norm_lut, float* d_patches, size_t patches_stride, __nv_bfloat16* p_hi,
-                                    __nv_bfloat16* p_lo, cudaStream_t s) {
+                                    __nv_bfloat16* p_lo, cudaStream_t s, unsigned long long* stamp) {
     if (n <= 0) return cudaSuccess;
     dim3 grid((out_size * out_size + 255) / 256, n);
-    crop_resize_norm_kernel<<<grid, 256, 0, s>>>(f, d_state, d_slots, factor, out_size, d_norm_lut, d_patches, patches_stride, p_hi, p_lo);
+    crop_resize_norm_kernel<<<grid, 256, 0, s>>>(f, d_state, d_slots, factor, out_size, d_norm_lut, d_patches, patches_stride, p_hi, p_lo, stamp);
     return cudaGetLastError();
 }
 
@@ -441,28 +442,48 @@ cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, 
 
 // Box overlay straight from the device-side decode result: one CTA per target,
 // rect (thickness 3) then crosshair (size 15) at the box centre ≙ src/pipeline.rs:165-168 / src/pipeline_ir.rs:192-195.
+// `host_slot` (nullable) points at a pinned, device-mapped cell holding the address of the caller's pinned frame (or null): the
+// same pixels are then also written straight into the host frame (zero-copy stores over PCIe, ~3.4 K bytes), so no
+// device->host row copy and no second synchronisation is needed to hand the overlaid frame back.
 __global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t len, int W, int H, int fmt,
                                                           const DeviceResult* __restrict__ res, const int32_t* __restrict__ slots,
-                                                          float gate) {
-    Surface s{frame, len, W, H, fmt};
+                                                          float gate, uint8_t* const* host_slot, unsigned long long* stamp_end) {
+    __shared__ uint8_t* s_host;
+    if (threadIdx.x == 0) s_host = host_slot ? *reinterpret_cast<uint8_t* const volatile*>(host_slot) : nullptr;
+    __syncthreads();
     const DeviceResult r = res[slots[blockIdx.x]];
-    if (r.status != VT_OK || !r.success || !(r.score > gate)) return;
-    const int x = r.bbox[0], y = r.bbox[1], w = r.bbox[2], h = r.bbox[3];
-    if (fmt == VT_FMT_NV12) {
-        ov_rect_nv12(s, x, y, w, h, 3, 255);
-        __syncthreads();
-        ov_crosshair_nv12(s, x + w / 2, y + h / 2, 15, 255);
-    } else {
-        ov_rect_rgb(s, x, y, w, h, 3, 0, 255, 0);
-        __syncthreads();
-        ov_crosshair_rgb(s, x + w / 2, y + h / 2, 15, 0, 255, 0);
+    if (r.status == VT_OK && r.success && r.score > gate) {
+        const int x = r.bbox[0], y = r.bbox[1], w = r.bbox[2], h = r.bbox[3];
+        for (int pass = 0; pass < 2; ++pass) {
+            uint8_t* dst = pass == 0 ? frame : s_host;
+            if (!dst) break;
+            Surface s{dst, len, W, H, fmt};
+            if (fmt == VT_FMT_NV12) {
+                ov_rect_nv12(s, x, y, w, h, 3, 255);
+                __syncthreads();
+                ov_crosshair_nv12(s, x + w / 2, y + h / 2, 15, 255);
+            } else {
+                ov_rect_rgb(s, x, y, w, h, 3, 0, 255, 0);
+                __syncthreads();
+                ov_crosshair_rgb(s, x + w / 2, y + h / 2, 15, 0, 255, 0);
+            }
+            __syncthreads();
+        }
     }
+    if (stamp_end && threadIdx.x == 0 && blockIdx.x == 0) *stamp_end = device_time_ns();
 }
 
 cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
-                               const int32_t* d_slots, int n, float gate, cudaStream_t s) {
+                               const int32_t* d_slots, int n, float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
+                               cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    box_overlay_kernel<<<n, 256, 0, s>>>(d_frame, len, width, height, format, d_res, d_slots, gate);
+    box_overlay_kernel<<<n, 256, 0, s>>>(d_frame, len, width, height, format, d_res, d_slots, gate, host_slot, stamp_end);
+    return cudaGetLastError();
+}
+
+__global__ void stamp_kernel(unsigned long long* stamp) { *stamp = device_time_ns(); }
+cudaError_t launch_stamp(unsigned long long* stamp, cudaStream_t s) {
+    stamp_kernel<<<1, 1, 0, s>>>(stamp);
     return cudaGetLastError();
 }
 

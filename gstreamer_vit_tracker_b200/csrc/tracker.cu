@@ -67,7 +67,13 @@ struct vt_tracker {
     int frame_valid = 1;
     TargetState* d_state = nullptr;
     int32_t* d_slots = nullptr;
+    // one device block [DeviceResult x maxT][u64 stamps x ST_COUNT][int tc_err, pad] mirrored in pinned host memory by one copy
     DeviceResult *d_res = nullptr, *h_res = nullptr;
+    size_t res_block_bytes = 0;
+    unsigned long long *d_stamps = nullptr, *h_stamps = nullptr;
+    int* h_tc_err = nullptr;
+    uint8_t** h_frame_slot = nullptr;  // pinned + device-mapped cell: address of the caller's pinned frame for the zero-copy overlay mirror
+    bool inflight_mirrored = false;
     float* d_maps = nullptr;
     OverlayCmdDev *d_cmds = nullptr, *h_cmds = nullptr;
     std::vector<int> active;          // slot indices, ascending
@@ -112,6 +118,11 @@ struct vt_tracker {
     uint8_t* inflight_frame = nullptr;
     bool inflight_staged = false;
     std::chrono::steady_clock::time_point t_submit;
+
+    // VT_B200_HOSTPROF=1: host-side wall time of the submit / wait phases, printed at destroy (diagnostics)
+    bool hostprof = false;
+    double hp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t hp_n = 0;
 
     TimingStats stats;
     Ring<float> r_h2d, r_pre, r_vit, r_dec, r_ovl, r_d2h, r_tot;
@@ -191,9 +202,10 @@ static vt_status load_weights(vt_tracker* t, const char* path) {
 // tensor-core path, their block-0 LN1 as the bf16 split A operand of the first QKV GEMM
 __global__ void gather_template_kernel(float* __restrict__ X, const float* __restrict__ Zemb, const int32_t* __restrict__ slots, int D,
                                        uint32_t* __restrict__ ln_hi, uint32_t* __restrict__ ln_lo, const uint32_t* __restrict__ zln_hi,
-                                       const uint32_t* __restrict__ zln_lo) {
+                                       const uint32_t* __restrict__ zln_lo, unsigned long long* stamp) {
     tc::pdl_wait();
     tc::pdl_launch_dependents();
+    if (stamp && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) *stamp = device_time_ns();
     const int bi = blockIdx.y;
     const int n = kNTz * D;
     const size_t so = (size_t)slots[bi] * n, xo = (size_t)bi * kNTok * D;
@@ -224,19 +236,16 @@ static GemmArgs gemm_args(const float* A, int64_t lda, const float* W, const flo
 // Enqueues crop -> ViT -> decode (-> box overlay) for the n active targets on t->stream.
 static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool record_events, bool capturing) {
     const int D = t->D, Hd = t->hidden, C = t->head_ch;
-    // inside a stream capture a plain cudaEventRecord only expresses a dependency; the External flag makes a real
-    // event-record node so that the stage times can be read after every replay
-    const unsigned ev_flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
+    (void)record_events, (void)capturing;  // stage times come from device stamps (ST_*), not from event nodes
     cudaStream_t s = t->stream;
     FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid};
     VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, n, 4, kSearch, t->d_lut, t->patches_x, (size_t)kNTx * kPatchK, t->px_hi,
-                                      t->px_lo, s));
-    if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_PRE], s, ev_flags));
+                                      t->px_lo, s, t->d_stamps + ST_PRE));
     {
         dim3 grid((kNTz * D + 255) / 256, n);
         const bool f = t->fuse_ln;
         gather_template_kernel<<<grid, 256, 0, s>>>(t->X, t->Zemb, t->d_slots, D, f ? (uint32_t*)t->ln_hi : nullptr, (uint32_t*)t->ln_lo,
-                                                    (const uint32_t*)t->zln_hi, (const uint32_t*)t->zln_lo);
+                                                    (const uint32_t*)t->zln_hi, (const uint32_t*)t->zln_lo, t->d_stamps + ST_VIT);
         VT_LAUNCH(cudaGetLastError());
     }
     const int M = n * kNTok;
@@ -325,28 +334,20 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
         if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, t->lnf_g, t->lnf_b, t->yf_hi, t->yf_lo, n * kNTx, D, kNTx, kNTok, kNTz, s, pdl));
         VT_LAUNCH(tc_gemm_launch(t->plan_head, n * kNTx, ns, s, pdl));
     }
-    if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_VIT], s, ev_flags));
     if (t->nsplit && t->split_k)
         VT_LAUNCH(launch_head_decode(t->Phead, 9, (int64_t)t->maxT * kNTx * C, C, t->h1_b, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n,
-                                     t->threshold, t->d_res, t->d_maps, t->d_cand, t->d_counters, s, false));
+                                     t->threshold, t->d_res, t->d_maps, t->d_cand, t->d_counters, t->d_stamps, s, t->pdl && !t->debug_capture));
     else
-        VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, s));
-    if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_DEC], s, ev_flags));
+        VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, t->d_stamps, s));
     if (t->cfg.box_overlay)
-        VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, t->fmt, t->d_res, t->d_slots, n, t->cfg.overlay_gate, s));
-    if (record_events) VT_CUDA(cudaEventRecordWithFlags(t->ev[EV_OVL], s, ev_flags));
+        VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, t->fmt, t->d_res, t->d_slots, n, t->cfg.overlay_gate,
+                                     t->h_frame_slot, t->d_stamps + ST_OVL_END, s));
     return VT_OK;
 }
 
 static vt_status run_forward(vt_tracker* t) {
     const int n = (int)t->active.size();
-    if (n == 0) {
-        VT_CUDA(cudaEventRecord(t->ev[EV_PRE], t->stream));
-        VT_CUDA(cudaEventRecord(t->ev[EV_VIT], t->stream));
-        VT_CUDA(cudaEventRecord(t->ev[EV_DEC], t->stream));
-        VT_CUDA(cudaEventRecord(t->ev[EV_OVL], t->stream));
-        return VT_OK;
-    }
+    if (n == 0) return VT_OK;
     int launches = 0;
     if (!t->cfg.use_cuda_graph || t->debug_capture) {
         vt_status st = enqueue_forward(t, n, launches, true, false);
@@ -490,17 +491,25 @@ static void unstage_rows(vt_tracker* t, uint8_t* frame, size_t len, const std::v
 }
 
 static void collect_timing(vt_tracker* t) {
-    float ms[7] = {0, 0, 0, 0, 0, 0, 0};
-    const int a[7] = {EV_START, EV_H2D, EV_PRE, EV_VIT, EV_DEC, EV_OVL, EV_START};
-    const int b[7] = {EV_H2D, EV_PRE, EV_VIT, EV_DEC, EV_OVL, EV_END, EV_END};
-    for (int i = 0; i < 7; ++i)
-        if (cudaEventElapsedTime(&ms[i], t->ev[a[i]], t->ev[b[i]]) != cudaSuccess) {
-            cudaGetLastError();
-            ms[i] = 0.f;
-        }
+    // stage boundaries stamped on the device (ns): submit, crop start, ViT start, decode start, decode end, overlay end
+    const unsigned long long* st = t->h_stamps;
+    auto span = [&](int a, int b) { return st[b] > st[a] && st[a] ? (float)((double)(st[b] - st[a]) * 1e-6) : 0.f; };
+    const int last_dev = t->cfg.box_overlay ? ST_OVL_END : ST_DEC_END;
+    const float wall = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t->t_submit).count();
+    float ms[7];
+    ms[0] = span(ST_SUBMIT, ST_PRE), ms[1] = span(ST_PRE, ST_VIT), ms[2] = span(ST_VIT, ST_DEC), ms[3] = span(ST_DEC, ST_DEC_END);
+    ms[4] = t->cfg.box_overlay ? span(ST_DEC_END, ST_OVL_END) : 0.f;
+    const float dev = span(ST_SUBMIT, last_dev);
+    ms[5] = wall > dev ? wall - dev : 0.f;  // results (and overlay rows) back in host memory + completion latency, host clock
+    ms[6] = wall;
+    if (t->active.empty()) ms[1] = ms[2] = ms[3] = ms[4] = 0.f;
     memcpy(t->last, ms, sizeof(ms));
     t->r_h2d.push(ms[0]), t->r_pre.push(ms[1]), t->r_vit.push(ms[2]), t->r_dec.push(ms[3]), t->r_ovl.push(ms[4]), t->r_d2h.push(ms[5]),
         t->r_tot.push(ms[6]);
+}
+
+static inline double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_src, size_t len) {
@@ -508,8 +517,13 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
         set_error("a frame is already in flight on this handle");
         return VT_ERR_INVALID;
     }
+    const double hp0 = t->hostprof ? now_us() : 0;
     t->t_submit = std::chrono::steady_clock::now();
-    VT_CUDA(cudaEventRecord(t->ev[EV_START], t->stream));
+    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->stream));
+    ++t->kernel_launches;
+    // zero-copy overlay mirror: only when the caller's frame is pinned (device-mapped under UVA)
+    t->inflight_mirrored = t->cfg.box_overlay && frame && !d_src && len >= t->frame_bytes && is_pinned(frame);
+    *t->h_frame_slot = t->inflight_mirrored ? frame : nullptr;
     if (d_src) {
         t->frame_valid = (t->fmt == VT_FMT_NV12) ? (len >= (size_t)t->W * t->H * 3 / 2) : (len >= t->frame_bytes);
         if (t->frame_valid || t->fmt == VT_FMT_RGB24)
@@ -518,12 +532,13 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
         vt_status st = upload_frame(t, frame, len);
         if (st != VT_OK) return st;
     }
-    VT_CUDA(cudaEventRecord(t->ev[EV_H2D], t->stream));
+    const double hp1 = t->hostprof ? now_us() : 0;
     vt_status st = run_forward(t);
     if (st != VT_OK) return st;
-    VT_CUDA(cudaMemcpyAsync(t->h_res, t->d_res, sizeof(DeviceResult) * t->maxT, cudaMemcpyDeviceToHost, t->stream));
-    t->d2h_bytes += sizeof(DeviceResult) * t->maxT;
-    VT_CUDA(cudaEventRecord(t->ev[EV_END], t->stream));
+    const double hp2 = t->hostprof ? now_us() : 0;
+    VT_CUDA(cudaMemcpyAsync(t->h_res, t->d_res, t->res_block_bytes, cudaMemcpyDeviceToHost, t->stream));
+    t->d2h_bytes += t->res_block_bytes;
+    if (t->hostprof) t->hp[0] += hp1 - hp0, t->hp[1] += hp2 - hp1, t->hp[2] += now_us() - hp2;
     t->in_flight = true;
     t->inflight_frame = d_src ? nullptr : frame;
     return VT_OK;
@@ -535,18 +550,24 @@ static vt_status wait_common(vt_tracker* t, size_t len, vt_result* results) {
         return VT_ERR_INVALID;
     }
     t->in_flight = false;
+    const double hp0 = t->hostprof ? now_us() : 0;
     VT_CUDA(cudaStreamSynchronize(t->stream));
-    if (t->d_tc_err) {
-        int e = 0;
-        VT_CUDA(cudaMemcpy(&e, t->d_tc_err, sizeof(int), cudaMemcpyDeviceToHost));
-        if (e) {
-            cudaMemset(t->d_tc_err, 0, sizeof(int));
-            set_error("tcgen05 GEMM: a bounded mbarrier wait expired (pipeline protocol error)");
-            return VT_ERR_CUDA;
-        }
+    const double hp1 = t->hostprof ? now_us() : 0;
+    if (*t->h_tc_err) {  // travels with the results; reset on the device for the next frame
+        cudaMemsetAsync(t->d_tc_err, 0, sizeof(int), t->stream);
+        *t->h_tc_err = 0;
+        set_error("tcgen05 path: a bounded mbarrier wait expired (pipeline protocol error)");
+        return VT_ERR_CUDA;
     }
     fill_results(t, results);
-    if (t->cfg.box_overlay && t->inflight_frame) {
+    const double hp2 = t->hostprof ? now_us() : 0;
+    if (t->cfg.box_overlay && t->inflight_frame && t->inflight_mirrored) {
+        // the overlay kernel wrote the box pixels straight into the caller's pinned frame: count them as device->host traffic
+        for (int sl : t->active) {
+            const DeviceResult& d = t->h_res[sl];
+            if (d.status == VT_OK && d.success && d.score > t->cfg.overlay_gate) t->d2h_bytes += 6ull * (size_t)(std::max(d.bbox[2], 0) + std::max(d.bbox[3], 0)) + 62;
+        }
+    } else if (t->cfg.box_overlay && t->inflight_frame) {
         std::vector<std::pair<int, int>> spans;
         box_rows(t, spans);
         merge_spans(spans);
@@ -554,13 +575,14 @@ static vt_status wait_common(vt_tracker* t, size_t len, vt_result* results) {
             bool staged = false;
             vt_status st = download_rows(t, t->inflight_frame, len, spans, &staged);
             if (st != VT_OK) return st;
-            VT_CUDA(cudaEventRecord(t->ev[EV_END], t->stream));
             VT_CUDA(cudaStreamSynchronize(t->stream));
             if (staged) unstage_rows(t, t->inflight_frame, len, spans);
         }
     }
+    const double hp3 = t->hostprof ? now_us() : 0;
     collect_timing(t);
     ++t->frames;
+    if (t->hostprof) t->hp[3] += hp1 - hp0, t->hp[4] += hp2 - hp1, t->hp[5] += hp3 - hp2, t->hp[6] += now_us() - hp3, ++t->hp_n;
     return VT_OK;
 }
 
@@ -599,6 +621,12 @@ void vt_free_pinned(void* p) {
 
 void vt_tracker_destroy(vt_tracker* t) {
     if (!t) return;
+    if (t->hostprof && t->hp_n) {
+        const double n = (double)t->hp_n;
+        fprintf(stderr, "[vt hostprof] frames %llu  submit: upload %.1f  graph launch %.1f  result copy+event %.1f | wait: stream sync %.1f  "
+                        "err check+results %.1f  overlay rows %.1f  timing %.1f (us / frame)\n",
+                (unsigned long long)t->hp_n, t->hp[0] / n, t->hp[1] / n, t->hp[2] / n, t->hp[3] / n, t->hp[4] / n, t->hp[5] / n, t->hp[6] / n);
+    }
     cudaSetDevice(t->cfg.device);
     if (t->stream) cudaStreamSynchronize(t->stream);
     for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
@@ -607,11 +635,12 @@ void vt_tracker_destroy(vt_tracker* t) {
     void* dev[] = {t->d_weights, t->d_lut, t->d_hann, t->d_frame, t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
                    t->patches_x, t->patches_z, t->Zemb, t->X, t->QKV, t->ATT, t->HID, t->Yf, t->H1, t->d_dbg,
                    t->w_hi, t->w_lo, t->px_hi, t->px_lo, t->pz_hi, t->pz_lo, t->ln_hi, t->ln_lo, t->att_hi, t->att_lo,
-                   t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->d_tc_err, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, t->zln_hi, t->zln_lo, t->d_trace, t->Pbuf, t->Phead, t->d_cand, t->d_counters};
+                   t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, t->zln_hi, t->zln_lo, t->d_trace, t->Pbuf, t->Phead, t->d_cand, t->d_counters};
     for (void* p : dev)
         if (p) cudaFree(p);
     if (t->h_stage) cudaFreeHost(t->h_stage);
     if (t->h_res) cudaFreeHost(t->h_res);
+    if (t->h_frame_slot) cudaFreeHost(t->h_frame_slot);
     if (t->h_cmds) cudaFreeHost(t->h_cmds);
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;
@@ -642,6 +671,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     t->frame_bytes = cfg->format == VT_FMT_NV12 ? (size_t)t->W * t->H + (size_t)((t->H + 1) / 2) * t->W + (t->W & 1) : (size_t)t->W * t->H * 3;
     t->threshold = cfg->score_threshold > 0.f ? cfg->score_threshold : 0.20f;
     t->debug_capture = cfg->reserved[0];
+    t->hostprof = getenv("VT_B200_HOSTPROF") != nullptr;
     auto fail = [&](vt_status st) {
         vt_tracker_destroy(t);
         return st;
@@ -682,10 +712,15 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     VT_TRY(cudaMalloc(&t->d_state, sizeof(TargetState) * B));
     VT_TRY(cudaMemset(t->d_state, 0, sizeof(TargetState) * B));
     VT_TRY(cudaMalloc(&t->d_slots, sizeof(int32_t) * B));
-    VT_TRY(cudaMalloc(&t->d_res, sizeof(DeviceResult) * B));
-    VT_TRY(cudaMemset(t->d_res, 0, sizeof(DeviceResult) * B));
-    VT_TRY(cudaHostAlloc(&t->h_res, sizeof(DeviceResult) * B, cudaHostAllocDefault));
-    memset(t->h_res, 0, sizeof(DeviceResult) * B);
+    t->res_block_bytes = sizeof(DeviceResult) * B + sizeof(unsigned long long) * ST_COUNT + 2 * sizeof(int);
+    VT_TRY(cudaMalloc(&t->d_res, t->res_block_bytes));
+    VT_TRY(cudaMemset(t->d_res, 0, t->res_block_bytes));
+    VT_TRY(cudaHostAlloc(&t->h_res, t->res_block_bytes, cudaHostAllocDefault));
+    memset(t->h_res, 0, t->res_block_bytes);
+    t->d_stamps = reinterpret_cast<unsigned long long*>(t->d_res + B), t->h_stamps = reinterpret_cast<unsigned long long*>(t->h_res + B);
+    t->d_tc_err = reinterpret_cast<int*>(t->d_stamps + ST_COUNT), t->h_tc_err = reinterpret_cast<int*>(t->h_stamps + ST_COUNT);
+    VT_TRY(cudaHostAlloc(&t->h_frame_slot, sizeof(uint8_t*), cudaHostAllocMapped));
+    *t->h_frame_slot = nullptr;
     VT_TRY(cudaMalloc(&t->d_maps, sizeof(float) * 1280 * B));
     VT_TRY(cudaMemset(t->d_maps, 0, sizeof(float) * 1280 * B));
     VT_TRY(cudaMalloc(&t->d_cmds, sizeof(OverlayCmdDev) * kMaxCmds));
@@ -747,8 +782,6 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             if (!tc_attention_plan_init(&t->plan_att, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, (int)(B * t->heads), t->att_hi, t->att_lo, (int)D, (int)B))
                 return fail(VT_ERR_CUDA);
         }
-        VT_TRY(cudaMalloc(&t->d_tc_err, sizeof(int)));
-        VT_TRY(cudaMemset(t->d_tc_err, 0, sizeof(int)));
         auto whi = [&](const float* w) { return t->w_hi + (w - t->d_weights); };
         auto wlo = [&](const float* w) { return t->w_lo + (w - t->d_weights); };
         bool ok = true;

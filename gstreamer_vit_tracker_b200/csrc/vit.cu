@@ -417,7 +417,8 @@ cudaError_t launch_attention(const float* qkv, float* out, __nv_bfloat16* out_hi
 __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ h1, int C, const float* __restrict__ w2,
                                                      const float* __restrict__ b2, const float* __restrict__ hann,
                                                      TargetState* __restrict__ state, const int32_t* __restrict__ slots, float threshold,
-                                                     DeviceResult* __restrict__ res, float* __restrict__ maps) {
+                                                     DeviceResult* __restrict__ res, float* __restrict__ maps, unsigned long long* stamps) {
+    if (stamps && threadIdx.x == 0 && blockIdx.x == 0) stamps[ST_DEC] = device_time_ns();
     __shared__ float s_val[8];
     __shared__ int s_idx[8];
     __shared__ float s_out[4];
@@ -501,6 +502,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ h
             }
         }
         res[slot] = r;
+        if (stamps && blockIdx.x == 0) stamps[ST_DEC_END] = device_time_ns();
     }
 }
 
@@ -551,12 +553,13 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restric
                                                           const float* __restrict__ w2, const float* __restrict__ b2,
                                                           const float* __restrict__ hann, TargetState* __restrict__ state,
                                                           const int32_t* __restrict__ slots, float threshold, DeviceResult* __restrict__ res,
-                                                          float* __restrict__ maps, float* cand, unsigned* counters) {
+                                                          float* __restrict__ maps, float* cand, unsigned* counters, unsigned long long* stamps) {
     constexpr int C = CPL * 32;
     __shared__ float s_c[16][6];
     __shared__ int s_last;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (stamps && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) stamps[ST_DEC] = device_time_ns();
     const int bi = blockIdx.y, slot = slots[bi], y = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float w[5][CPL], bch[CPL];
@@ -625,25 +628,27 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restric
         const volatile float* c = cd + by * kCandStride;
         decode_finish(state + slot, slot, threshold, c[0], (int)c[1], c[2], c[3], c[4], c[5], res);
         counters[bi] = 0;  // ready for the next frame
+        if (stamps && bi == gridDim.y - 1) stamps[ST_DEC_END] = device_time_ns();
     }
 }
 
 cudaError_t launch_head_decode(const float* P, int np, int64_t p_stride, int head_ch, const float* b1, const float* w2, const float* b2,
                                const float* hann, TargetState* d_state, const int32_t* d_slots, int n, float threshold, DeviceResult* d_res,
-                               float* d_maps, float* d_cand, unsigned* d_counters, cudaStream_t s, bool pdl) {
+                               float* d_maps, float* d_cand, unsigned* d_counters, unsigned long long* stamps, cudaStream_t s, bool pdl) {
     if (n <= 0) return cudaSuccess;
     const dim3 grid(kMap, n), block(256);
     if (head_ch == 128)
-        return launch_ex(head_decode_kernel<4>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters);
+        return launch_ex(head_decode_kernel<4>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
     if (head_ch == 64)
-        return launch_ex(head_decode_kernel<2>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters);
+        return launch_ex(head_decode_kernel<2>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_decode(const float* h1, int head_ch, const float* w2, const float* b2, const float* hann, TargetState* d_state,
-                          const int32_t* d_slots, int n, float threshold, DeviceResult* d_res, float* d_maps, cudaStream_t s) {
+                          const int32_t* d_slots, int n, float threshold, DeviceResult* d_res, float* d_maps, unsigned long long* stamps,
+                          cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    decode_kernel<<<n, 256, 0, s>>>(h1, head_ch, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps);
+    decode_kernel<<<n, 256, 0, s>>>(h1, head_ch, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, stamps);
     return cudaGetLastError();
 }
 

@@ -102,6 +102,17 @@ struct DeviceResult {      // written by the decode kernel, copied to pinned hos
     int32_t best;          // argmax index (diagnostic)
 };
 
+// Device-side stage stamps (%globaltimer, ns), copied to the host together with the results: they replace cudaEvent records
+// inside the per-frame graph (an event node between two kernels breaks the programmatic-dependent-launch edge) and the seven
+// cudaEventElapsedTime queries per frame (~20 us of host time).
+enum { ST_SUBMIT = 0, ST_PRE, ST_VIT, ST_DEC, ST_DEC_END, ST_OVL_END, ST_COUNT = 8 };
+__device__ __forceinline__ unsigned long long device_time_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    return t;
+}
+cudaError_t launch_stamp(unsigned long long* stamp, cudaStream_t s);
+
 // ---- pixel kernels (pixel.cu) ------------------------------------------------------------------
 struct FrameDesc {
     const uint8_t* data;   // device pointer, tightly packed
@@ -118,7 +129,7 @@ cudaError_t launch_nv12_to_rgb(const uint8_t* d_nv12, size_t stride_in, uint8_t*
 // p_hi / p_lo (nullable): the same values as a bf16 (hi, lo) split, the A operand of the tensor-core patch-embed GEMM
 cudaError_t launch_crop_resize_norm(FrameDesc f, TargetState* d_state, const int32_t* d_slots, int n, int factor, int out_size,
                                     const float* d_norm_lut, float* d_patches, size_t patches_stride, __nv_bfloat16* p_hi,
-                                    __nv_bfloat16* p_lo, cudaStream_t s);
+                                    __nv_bfloat16* p_lo, cudaStream_t s, unsigned long long* stamp = nullptr);
 
 struct OverlayCmdDev {     // device-side copy of vt_overlay_cmd with resolved glyph rows
     int32_t kind, x, y, w, h, a;
@@ -130,7 +141,8 @@ cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, 
                            cudaStream_t s);
 // device-side box overlay straight from the decode result (rect thickness 3 + crosshair 15, src/pipeline.rs:165-168)
 cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
-                               const int32_t* d_slots, int n, float gate, cudaStream_t s);
+                               const int32_t* d_slots, int n, float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
+                               cudaStream_t s);
 
 // ---- ViT kernels (vit.cu) ----------------------------------------------------------------------
 struct GemmArgs {
@@ -183,13 +195,14 @@ cudaError_t launch_reduce_ln(const ReduceLnArgs& a, cudaStream_t s, bool pdl);
 // 16 CTAs per target (one map row each); the last one to finish merges the 16 row candidates and updates rect_last.
 cudaError_t launch_head_decode(const float* P, int np, int64_t p_stride, int head_ch, const float* b1, const float* w2, const float* b2,
                                const float* hann, TargetState* d_state, const int32_t* d_slots, int n, float threshold, DeviceResult* d_res,
-                               float* d_maps, float* d_cand, unsigned* d_counters, cudaStream_t s, bool pdl);
+                               float* d_maps, float* d_cand, unsigned* d_counters, unsigned long long* stamps, cudaStream_t s, bool pdl);
 // qkv: [B*320, 3D]; out: [B*320, D] fp32 (nullable) and/or bf16 split (nullable)
 cudaError_t launch_attention(const float* qkv, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int B, int D, int heads,
                              cudaStream_t s);
 // head 1x1 conv + sigmoid + hann + argmax + bbox decode, one CTA per target
 cudaError_t launch_decode(const float* h1, int head_ch, const float* w2, const float* b2, const float* hann, TargetState* d_state,
-                          const int32_t* d_slots, int n, float threshold, DeviceResult* d_res, float* d_maps, cudaStream_t s);
+                          const int32_t* d_slots, int n, float threshold, DeviceResult* d_res, float* d_maps, unsigned long long* stamps,
+                          cudaStream_t s);
 
 // ---- tensor-core GEMM (gemm_tc.cu) ------------------------------------------------------------------
 struct TcGemmArgs {
