@@ -62,11 +62,13 @@ def workload_name(args):
             f"{args.streams_per_gpu} stream(s) per GPU" + (" (cfg5 seeds, one stream set per rank)" if args.gpus > 1 else ""))
 
 
-def stream_spec(rank, k, args):
-    from gstreamer_vit_tracker_b200 import synth
-    if args.gpus == 1 and args.streams_per_gpu == 1:
+def stream_spec(rank, k, args, world):
+    """Stream k of this rank: cfg2 for the single-stream headline run, else global stream id -> rank round-robin (sharding.py)."""
+    from gstreamer_vit_tracker_b200 import sharding, synth
+    if world == 1 and args.streams_per_gpu == 1:
         return synth.CONFIGS["cfg2"]
-    return synth.cfg5_stream((rank * args.streams_per_gpu + k) % 64)
+    mine = sharding.streams_of_rank(world * args.streams_per_gpu, rank, world)
+    return synth.cfg5_stream(mine[k] % 64)
 
 
 def weight_path(model):
@@ -215,7 +217,7 @@ def run_b200(args):
     streams = []
     from gstreamer_vit_tracker_b200 import synth
     for k in range(S):
-        spec = stream_spec(rank, k, args)
+        spec = stream_spec(rank, k, args, world)
         st = synth.SyntheticStream(spec)
         fb = st.frame_bytes()
         trk = api.VitTrack.new(wpath, spec.width, spec.height, fmt="nv12", device=local_rank, box_overlay=True,
@@ -295,6 +297,34 @@ def run_b200(args):
     clocks = sampler.stop()
     stage_e2e = {k: getattr(tm_e2e, "avg_" + k) for k in ("h2d_ms", "preprocess_ms", "vit_ms", "decode_ms", "overlay_ms", "d2h_ms", "total_ms")}
 
+    # ---- per-kernel in-chain durations of the tensor-core kernels (device %globaltimer stamps written by the kernels themselves:
+    #      an event between two kernels of the replayed graph would break the programmatic-dependent-launch edge it measures) ----
+    kern = None
+    if args.gemm != "fp32simt":
+        os.environ["VT_B200_TRACE"] = "1"
+        try:
+            s0_ = streams[0]
+            ttrk = api.VitTrack.new(wpath, s0_["spec"].width, s0_["spec"].height, fmt="nv12", device=local_rank, box_overlay=True,
+                                    gemm_mode={"fp32simt": 0, "tcgen05x3": 1, "tcgen05": 2}[args.gemm])
+        finally:
+            del os.environ["VT_B200_TRACE"]
+        ttrk.init(s0_["pristine"][0], api.BBox(*s0_["init_box"]))
+        for i in range(10):
+            ttrk.update_device(s0_["dev"][i % ring_n].data_ptr(), s0_["fb"])
+        ttrk.debug_trace()
+        nfr = 20
+        for i in range(nfr):
+            ttrk.update_device(s0_["dev"][(10 + i) % ring_n].data_ptr(), s0_["fb"])
+        rec = ttrk.debug_trace().astype(np.int64)
+        names = {1: "patch", 2: "qkv", 3: "proj", 4: "fc1+fc2partial", 5: "fc2", 6: "head", 10: "attention"}
+        kern = {}
+        for kid, te, tw, tend, *_ in rec:
+            d = kern.setdefault(names.get(int(kid), str(int(kid))), [0, 0.0])
+            d[0] += 1
+            d[1] += (tend - tw) * 1e-3
+        kern = {k: {"launches_per_frame": v[0] / nfr, "avg_us": v[1] / v[0]} for k, v in kern.items()}
+        del ttrk
+
     # ---- NV12->RGB full-frame kernel (HBM roofline), device resident, batch larger than L2 -------------------
     s0 = streams[0]
     nb = min(ring_n, 64)
@@ -314,17 +344,11 @@ def run_b200(args):
     cvt_ms = e0.elapsed_time(e1) / reps
     cvt_bytes = nb * (w * h * 3 // 2 + w * h * 3)
 
-    # ---- aggregate over ranks: max time, sum of frames ------------------------------------------------------
+    # ---- aggregate over ranks: max time, sum of frames (no data-path collective; see sharding.py) -----------------------
+    from gstreamer_vit_tracker_b200 import sharding
     frames_rank = K * S
-    t = torch.tensor([ms_dev, ms_e2e, float(frames_rank), float(launches_dev)], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_dev_g, ms_e2e_g, frames_g, launches_g = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tsum[3])
-    else:
-        ms_dev_g, ms_e2e_g, frames_g, launches_g = ms_dev, ms_e2e, float(frames_rank), float(launches_dev)
+    tm_all = sharding.combine_timings([ms_dev, ms_e2e], float(frames_rank), float(launches_dev), device=f"cuda:{local_rank}")
+    ms_dev_g, ms_e2e_g, frames_g, launches_g = tm_all.ms_max[0], tm_all.ms_max[1], tm_all.frames, tm_all.launches
 
     if rank == 0:
         peaks = {}
@@ -337,6 +361,18 @@ def run_b200(args):
         flops = weights.flops_per_frame(cfg_model)
         vit_s = stage["vit_ms"] * 1e-3
         ach_tf = (flops / vit_s / 1e12) if vit_s > 0 else None
+        # dominant kernel = gemm_tc_kernel (every dense contraction except attention): algorithmic FLOPs per frame of its launches
+        # (2*M*N*K each) / summed in-chain kernel time per frame
+        cm, Dm, Hm, Cm = cfg_model, cfg_model.D, cfg_model.hidden, cfg_model.head_ch
+        gemm_flops = (2 * 256 * 768 * Dm + cm.depth * (2 * 320 * Dm * 3 * Dm + 2 * 320 * Dm * Dm + 2 * 2 * 320 * Dm * Hm) + 2 * 256 * 9 * Dm * Cm)
+        gemm_kinds = ("patch", "qkv", "proj", "fc1+fc2partial", "fc2", "head")
+        gemm_us = sum(v["launches_per_frame"] * v["avg_us"] for k, v in (kern or {}).items() if k in gemm_kinds)
+        gemm_n = sum(v["launches_per_frame"] for k, v in (kern or {}).items() if k in gemm_kinds)
+        chain_us = sum(v["launches_per_frame"] * v["avg_us"] for v in (kern or {}).values())
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("gemm_tc_kernel", {}).get("dram_bytes_per_launch")
         lat_all = np.array([x for l in lat_e2e for x in l]) * 1e3
         lat_d = np.array([x for l in lat_dev for x in l]) * 1e3
         fb0 = streams[0]["fb"]
@@ -353,10 +389,19 @@ def run_b200(args):
                     "stages_ms": stage_e2e},
             "latency_ms": {"device_resident_p50": float(np.percentile(lat_d, 50)), "host_p50": float(np.percentile(lat_all, 50))},
             "gpu_launches": int(launches_g), "stages_ms": stage,
-            "roofline": {"kernel": "ViT forward (patch-embed, QKV, attention, proj, MLP, head) gemm=" + args.gemm,
-                         "bound": "tensor", "achieved": ach_tf, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": (ach_tf / tf_peak) if ach_tf else None, "traffic": None, "peak_source": peak_src,
-                         "note": "B=1 (320 tokens) is launch/latency bound; FLOPs/frame = %.3f G" % (flops / 1e9)},
+            "roofline": ({"kernel": "gemm_tc_kernel<%s> (tcgen05/TMEM/TMA GEMM: patch-embed, QKV, proj, FC1+chained FC2, 3x3 head conv)" % ("3" if args.gemm == "tcgen05x3" else "1"),
+                          "bound": "tensor", "achieved": gemm_flops / (gemm_us * 1e-6) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                          "frac": gemm_flops / (gemm_us * 1e-6) / 1e12 / tf_peak, "traffic": traffic, "peak_source": peak_src,
+                          "flops_per_launch_avg": gemm_flops / gemm_n, "launches_per_frame": gemm_n, "avg_launch_us": gemm_us / gemm_n,
+                          "share_of_chain": gemm_us / chain_us if chain_us else None,
+                          "timing": "device %globaltimer stamps inside the replayed graph (dependency wait -> kernel end), 20 frames",
+                          "note": "one target = 320 rows: every launch is a 9..36-CTA latency-bound GEMM; algorithmic FLOPs (2MNK), the bf16x3 "
+                                  "split issues 3 UMMAs per product"} if kern and gemm_us > 0 else
+                         {"kernel": "ViT forward, gemm=" + args.gemm, "bound": "tensor", "achieved": ach_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                          "frac": (ach_tf / tf_peak) if ach_tf else None, "traffic": None, "peak_source": peak_src}),
+            "roofline_vit_stage": {"achieved": ach_tf, "unit": "TFLOP/s", "frac": (ach_tf / tf_peak) if ach_tf else None, "flops_per_frame": flops,
+                                   "stage_ms": stage["vit_ms"], "timing": "device stamps, mean of the last 120 frames"},
+            "kernels_in_chain": kern,
             "roofline_convert": {"kernel": "nv12_to_rgb_vec_kernel", "bound": "hbm", "achieved": cvt_bytes / (cvt_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                  "unit": "GB/s", "frac": cvt_bytes / (cvt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                                  "frames_per_launch": nb, "bytes_per_launch": cvt_bytes, "ms_per_launch": cvt_ms, "peak_source": peak_src},
