@@ -204,7 +204,18 @@ def run_b200(args):
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner on stdout while the communicator is created: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.all_reduce(torch.zeros(1, device=f"cuda:{local_rank}"))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from gstreamer_vit_tracker_b200 import api, weights
 
     wpath = weight_path(args.model)
