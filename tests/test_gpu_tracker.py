@@ -379,3 +379,125 @@ def test_box_overlay_fused_path(api, oracle, weight_dir):
             oracle.draw_rect_nv12(ref, W, H, x, y, w, h, 3, 255)
             oracle.draw_crosshair_nv12(ref, W, H, x + w // 2, y + h // 2, 15, 255)
         assert np.array_equal(fr, ref), (n, int((fr != ref).sum()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["nv12", "rgb24"])
+def test_box_overlay_zero_copy_mirror_into_pinned_frame(api, oracle, weight_dir, fmt):
+    """With a pinned caller frame the overlay kernel writes the box pixels straight into host memory (no row copy): the frame must
+    equal the oracle's draw_rect + draw_crosshair on the same result, and the pageable (row-copy) path must give the same bytes."""
+    spec = synth.CONFIGS["cfg1"] if fmt == "nv12" else synth.CONFIGS["cfg3"]
+    W, H = spec.width, spec.height
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    a = api.VitTrack.new(wpath, W, H, fmt=fmt, box_overlay=True)
+    b = api.VitTrack.new(wpath, W, H, fmt=fmt, box_overlay=True)
+    f0 = np.asarray(st.frame(0)).reshape(-1)
+    box = api.BBox(*st.target_boxes(0)[0])
+    a.init(f0, box)
+    b.init(f0, box)
+    pin = api.PinnedBuffer(f0.size)
+    for n in range(4):
+        fr = np.asarray(st.frame(n)).reshape(-1).copy()
+        ref = fr.copy()
+        pin.array[:] = fr
+        ra = a.update(pin.array)   # pinned: zero-copy mirror
+        rb = b.update(fr)          # pageable: touched rows copied back
+        assert ra == rb
+        if ra.success and ra.score > 0.25:
+            x, y, w, h = ra.bbox
+            if fmt == "nv12":
+                oracle.draw_rect_nv12(ref, W, H, x, y, w, h, 3, 255)
+                oracle.draw_crosshair_nv12(ref, W, H, x + w // 2, y + h // 2, 15, 255)
+            else:
+                oracle.draw_rect_rgb(ref, W, H, x, y, w, h, 3, (0, 255, 0))
+                oracle.draw_crosshair_rgb(ref, W, H, x + w // 2, y + h // 2, 15, (0, 255, 0))
+        assert np.array_equal(pin.array, ref), (n, int((pin.array != ref).sum()))
+        assert np.array_equal(fr, ref), (n, int((fr != ref).sum()))
+
+
+@pytest.mark.gpu
+def test_concurrent_streams_equal_sequential(api, weight_dir):
+    """Independent handles driven from different host threads (one CUDA stream + graph each, sharing the GPU) reproduce the
+    single-stream results bit for bit — the multi-stream / multi-GPU sharding has no cross-stream state."""
+    import threading
+
+    wpath = weights.ensure_weight_file("tiny", weight_dir)
+    specs = [synth.cfg5_stream(i) for i in range(4)]
+    frames = [[synth.SyntheticStream(s).frame(n) for n in range(6)] for s in specs]
+    boxes = [synth.SyntheticStream(s).target_boxes(0)[0] for s in specs]
+
+    def run_stream(i, out):
+        trk = api.VitTrack.new(wpath, specs[i].width, specs[i].height, gemm_mode=1, box_overlay=True)
+        trk.init(frames[i][0], api.BBox(*boxes[i]))
+        out[i] = [trk.update(frames[i][n].copy()) for n in range(6)]
+
+    seq, par = {}, {}
+    for i in range(4):
+        run_stream(i, seq)
+    th = [threading.Thread(target=run_stream, args=(i, par)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert seq == par
+
+
+@pytest.mark.gpu
+def test_device_stage_stamps(api, weight_dir):
+    """vt_timing_get: stage times come from device stamps; they are positive, ordered and add up to less than the wall time."""
+    spec = synth.CONFIGS["cfg2"]
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("tiny", weight_dir)
+    trk = api.VitTrack.new(wpath, spec.width, spec.height, gemm_mode=1, box_overlay=True)
+    trk.init(st.frame(0), api.BBox(*st.target_boxes(0)[0]))
+    for n in range(5):
+        trk.update(st.frame(n))
+    t = trk.timing()
+    for f in ("h2d_ms", "preprocess_ms", "vit_ms", "decode_ms", "overlay_ms", "total_ms"):
+        assert getattr(t, f) > 0, f
+    dev = t.h2d_ms + t.preprocess_ms + t.vit_ms + t.decode_ms + t.overlay_ms
+    assert dev <= t.total_ms * 1.001 and t.vit_ms > 0.5 * dev
+    assert t.frames == 5 and t.kernel_launches > 5 * 30 and t.h2d_bytes == 6 * st.frame_bytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg4"])
+def test_full_size_properties(api, oracle, weight_dir, cfg):
+    """BASELINE.json sizes (1080p one target, 2160p 16 targets), properties that do not need the fp32 oracle forward at that size:
+    (1) the search blob of every target is bit-exact against the oracle's crop/resize/normalise of the same frame and rect,
+    (2) the result is invariant to pixels outside every search window (the fused kernel reads only the crop),
+    (3) replaying the same frame from the same state is idempotent in (score, box)."""
+    spec = synth.CONFIGS[cfg]
+    W, H = spec.width, spec.height
+    st = synth.SyntheticStream(spec)
+    nt = len(spec.targets)
+    wpath = weights.ensure_weight_file("tiny", weight_dir)
+    trk = api.VitTrack.new(wpath, W, H, max_targets=nt, gemm_mode=1)
+    f0, f1 = st.frame(0), st.frame(1)
+    boxes = st.target_boxes(0)
+    for k, b in enumerate(boxes):
+        trk.init(f0, api.BBox(*b), target=k)
+    r1 = trk.update_all(f1)
+    rgb1 = oracle.nv12_to_rgb(f1, W, H, 4)
+    for k in (0, nt - 1):
+        blob = np.asarray(trk.debug_read(target=k)["search_blob"]).reshape(-1)
+        rc, crop = oracle.crop_square(rgb1, boxes[k], 4)
+        assert rc == 0
+        ref = oracle.normalize_chw(oracle.resize_linear(crop, 256, 256)).reshape(-1)
+        assert np.array_equal(blob, ref), (cfg, k, int((blob != ref).sum()))
+    # (3) same state, same frame -> same answer
+    for k, b in enumerate(boxes):
+        trk.set_rect(tuple(b), target=k)
+    assert trk.update_all(f1) == r1
+    # (2) scribble outside all search windows (Y plane rows far from every target)
+    f2 = f1.copy()
+    wins = []
+    for b in boxes:
+        c = int(np.ceil(np.sqrt(float(b[2] * b[3])) * 4))
+        wins.append((b[1] + (b[3] - c) // 2 - 2, b[1] + (b[3] - c) // 2 + c + 2))
+    rows = [y for y in range(0, H, 2) if all(not (lo <= y <= hi) for lo, hi in wins)]
+    assert rows, "no row outside the search windows"
+    for y in rows[:64]:
+        f2[y * W:(y + 1) * W] = 255 - f2[y * W:(y + 1) * W]
+    for k, b in enumerate(boxes):
+        trk.set_rect(tuple(b), target=k)
+    assert trk.update_all(f2) == r1
