@@ -92,6 +92,10 @@ SYMBOLS = {
                                   C.POINTER(C.c_int32)]),
     "vt_convert_nv12_rgb": (C.c_int32, [_vp, _vp, C.c_size_t, _vp]),
     "vt_convert_nv12_rgb_device": (C.c_int32, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.c_int32]),
+    "vt_convert_yuy2_rgb": (C.c_int32, [_vp, _vp, C.c_size_t, C.c_int32, C.c_int32, _vp]),
+    "vt_convert_yuy2_rgb_device": (C.c_int32, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.c_int32, C.c_int32, C.c_int32]),
+    "vt_resize_rgb": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32]),
+    "vt_resize_rgb_device": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32]),
     "vt_overlay": (C.c_int32, [_vp, _vp, C.c_size_t, C.POINTER(vt_overlay_cmd), C.c_int32]),
     "vt_overlay_current": (C.c_int32, [_vp, _vp, C.c_size_t, C.POINTER(vt_overlay_cmd), C.c_int32]),
     "vt_timing_get": (C.c_int32, [_vp, C.POINTER(vt_timing)]),
@@ -104,6 +108,7 @@ SYMBOLS = {
     "vt_timing_stats_fps": (C.c_double, [_vp]),
     "vt_timing_stats_avg_conv_ms": (C.c_double, [_vp]),
     "vt_timing_stats_avg_track_ms": (C.c_double, [_vp]),
+    "vt_command_from_key": (C.c_int32, [C.c_uint8, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vt_context_create": (C.c_int32, [C.POINTER(vt_config), C.POINTER(_vp)]),
     "vt_context_create_scripted": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(_vp)]),
     "vt_context_process_scripted": (C.c_int32, [_vp, C.POINTER(vt_result), C.c_int32, C.POINTER(C.c_int32), C.POINTER(vt_bbox)]),

@@ -229,6 +229,29 @@ class VitTrack:
         check(lib().vt_convert_nv12_rgb_device(self._h, C.c_void_p(d_in), stride_in, C.c_void_p(d_out), stride_out, n_frames),
               "vt_convert_nv12_rgb_device")
 
+    # ---- format steps either side of the RGB probe ----
+    def yuy2_to_rgb(self, yuy2: np.ndarray, width: int, height: int) -> np.ndarray:
+        """≙ the videoconvert YUY2 -> RGB step of src/pipeline_ir.rs:27-56."""
+        yuy2 = np.ascontiguousarray(yuy2, dtype=np.uint8).reshape(-1)
+        out = np.empty((height, width, 3), np.uint8)
+        check(lib().vt_convert_yuy2_rgb(self._h, _ptr(yuy2), yuy2.size, width, height, _ptr(out)), "vt_convert_yuy2_rgb")
+        return out
+
+    def yuy2_to_rgb_device(self, d_in: int, stride_in: int, d_out: int, stride_out: int, width: int, height: int, n_frames: int) -> None:
+        check(lib().vt_convert_yuy2_rgb_device(self._h, C.c_void_p(d_in), stride_in, C.c_void_p(d_out), stride_out, width, height, n_frames),
+              "vt_convert_yuy2_rgb_device")
+
+    def resize_rgb(self, rgb: np.ndarray, dst_w: int, dst_h: int) -> np.ndarray:
+        """≙ the rgaconvert display upscale of src/pipeline_ir.rs:62-73 (bilinear, bit-exact with cv2.resize INTER_LINEAR)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        sh, sw = rgb.shape[0], rgb.shape[1]
+        out = np.empty((dst_h, dst_w, 3), np.uint8)
+        check(lib().vt_resize_rgb(self._h, _ptr(rgb), sw, sh, _ptr(out), dst_w, dst_h), "vt_resize_rgb")
+        return out
+
+    def resize_rgb_device(self, d_in: int, sw: int, sh: int, d_out: int, dw: int, dh: int) -> None:
+        check(lib().vt_resize_rgb_device(self._h, C.c_void_p(d_in), sw, sh, C.c_void_p(d_out), dw, dh), "vt_resize_rgb_device")
+
     def overlay(self, frame: np.ndarray, cmds: Sequence[vt_overlay_cmd], current: bool = False) -> None:
         arr = (vt_overlay_cmd * len(cmds))(*cmds)
         fn = lib().vt_overlay_current if current else lib().vt_overlay

@@ -115,6 +115,30 @@ void vt_context_destroy(vt_context* c) {
     delete c;
 }
 
+// ≙ the byte -> UserCommand match of the keyboard reader, src/raw_mode_guard.rs:65-101.  Returns 1 and fills cmd / fast when the
+// byte maps to a command, 0 when it is ignored (the '[' of escape sequences and everything else).
+int32_t vt_command_from_key(uint8_t byte, int32_t* cmd, int32_t* fast) {
+    int c = -1, f = 0;
+    switch (byte) {
+        case 10: case 13: case 32: c = VT_CMD_CONFIRM; break;                       // Enter, Space
+        case 87: case 119: case 73: case 105: c = VT_CMD_MOVE_UP; break;            // W w I i
+        case 83: case 115: case 75: case 107: c = VT_CMD_MOVE_DOWN; break;          // S s K k
+        case 65: case 97: case 74: case 106: c = VT_CMD_MOVE_LEFT; break;           // A a J j
+        case 68: case 100: case 76: case 108: c = VT_CMD_MOVE_RIGHT; break;         // D d L l
+        case 84: case 116: c = VT_CMD_MOVE_UP, f = 1; break;                        // T t   fast
+        case 71: case 103: c = VT_CMD_MOVE_DOWN, f = 1; break;                      // G g
+        case 70: case 102: c = VT_CMD_MOVE_LEFT, f = 1; break;                      // F f
+        case 72: case 104: c = VT_CMD_MOVE_RIGHT, f = 1; break;                     // H h
+        case 82: case 114: case 27: c = VT_CMD_CANCEL; break;                       // R r Escape
+        case 81: case 113: c = VT_CMD_QUIT; break;                                  // Q q
+        default: break;                                                             // 91 '[' and the rest: ignored
+    }
+    if (c < 0) return 0;
+    if (cmd) *cmd = c;
+    if (fast) *fast = f;
+    return 1;
+}
+
 vt_status vt_context_handle_command(vt_context* c, int32_t cmd, int32_t fast) {  // src/tracker_context.rs:36-61
     if (!c) return VT_ERR_INVALID;
     const int w = c->frame_width, h = c->frame_height;

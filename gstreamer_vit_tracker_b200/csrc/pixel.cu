@@ -149,6 +149,99 @@ cudaError_t launch_nv12_to_rgb(const uint8_t* d_nv12, size_t stride_in, uint8_t*
 }
 
 // ------------------------------------------------------------------------------------------------
+// YUY2 (packed 4:2:2: Y0 U Y1 V) -> RGB, SURVEY.md §8(f) row 1 (≙ the videoconvert step of src/pipeline_ir.rs:27-56), same
+// integer arithmetic as K1.  Fast path (W % 8 == 0): one warp converts a 256-px row segment — each lane loads 16 B (8 px),
+// stages 24 B in shared memory, the warp writes 768 B as 16-byte coalesced stores.  2*W*H read + 3*W*H written.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCvtWarps * 32) yuy2_to_rgb_vec_kernel(const uint8_t* __restrict__ in, size_t stride_in,
+                                                                       uint8_t* __restrict__ out, size_t stride_out, int W, int H,
+                                                                       int n_frames) {
+    __shared__ __align__(16) uint8_t stage[kCvtWarps][768];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int segs = (W + 255) >> 8;
+    const size_t row_in = (size_t)W * 2;
+    const long long total = (long long)n_frames * H * segs;
+    const long long wstride = (long long)gridDim.x * kCvtWarps;
+    for (long long item = (long long)blockIdx.x * kCvtWarps + warp; item < total; item += wstride) {
+        const int seg = (int)(item % segs);
+        const long long t = item / segs;
+        const int row = (int)(t % H), frame = (int)(t / H);
+        const uint8_t* ip = in + (size_t)frame * stride_in + (size_t)row * row_in;
+        uint8_t* op = out + (size_t)frame * stride_out + ((size_t)row * W + (size_t)seg * 256) * 3;
+        const int x = seg * 256 + lane * 8;
+        const int seg_px = min(256, W - seg * 256);
+        if (x < W) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(ip + (size_t)x * 2));
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+            uint8_t px[24];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // one Y0 U Y1 V word = two pixels
+                const Chroma c = chroma_terms((int)((w4[k] >> 8) & 0xff), (int)(w4[k] >> 24));
+                int r, g, b;
+                yuv_px((int)(w4[k] & 0xff), c, r, g, b);
+                px[k * 6 + 0] = (uint8_t)r, px[k * 6 + 1] = (uint8_t)g, px[k * 6 + 2] = (uint8_t)b;
+                yuv_px((int)((w4[k] >> 16) & 0xff), c, r, g, b);
+                px[k * 6 + 3] = (uint8_t)r, px[k * 6 + 4] = (uint8_t)g, px[k * 6 + 5] = (uint8_t)b;
+            }
+            uint2* dst = reinterpret_cast<uint2*>(&stage[warp][lane * 24]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                uint2 v;
+                v.x = px[j * 8 + 0] | (px[j * 8 + 1] << 8) | (px[j * 8 + 2] << 16) | ((uint32_t)px[j * 8 + 3] << 24);
+                v.y = px[j * 8 + 4] | (px[j * 8 + 5] << 8) | (px[j * 8 + 6] << 16) | ((uint32_t)px[j * 8 + 7] << 24);
+                dst[j] = v;
+            }
+        }
+        __syncwarp();
+        const int row_bytes = seg_px * 3;  // multiple of 24; the tail (< 16 B) is written bytewise
+        for (int off = lane * 16; off + 16 <= row_bytes; off += 32 * 16)
+            *reinterpret_cast<uint4*>(op + off) = *reinterpret_cast<const uint4*>(&stage[warp][off]);
+        if ((row_bytes & 15) && lane < (row_bytes & 15)) op[(row_bytes & ~15) + lane] = stage[warp][(row_bytes & ~15) + lane];
+        __syncwarp();
+    }
+}
+
+// generic path: one thread per pixel pair, byte accesses, GStreamer row stride (width*2 rounded up to 4)
+__global__ void yuy2_to_rgb_generic_kernel(const uint8_t* __restrict__ in, size_t stride_in, uint8_t* __restrict__ out, size_t stride_out,
+                                           int W, int H, int n_frames) {
+    const int pw = (W + 1) >> 1;
+    const size_t row_in = ((size_t)W * 2 + 3) & ~(size_t)3;
+    const long long total = (long long)n_frames * H * pw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % pw);
+        const long long t = i / pw;
+        const int row = (int)(t % H), frame = (int)(t / H);
+        const uint8_t* q = in + (size_t)frame * stride_in + (size_t)row * row_in + (size_t)p * 4;
+        const Chroma c = chroma_terms(q[1], q[3]);
+        for (int k = 0; k < 2 && 2 * p + k < W; ++k) {
+            int r, g, b;
+            yuv_px(q[2 * k], c, r, g, b);
+            uint8_t* o = out + (size_t)frame * stride_out + ((size_t)row * W + 2 * p + k) * 3;
+            o[0] = (uint8_t)r, o[1] = (uint8_t)g, o[2] = (uint8_t)b;
+        }
+    }
+}
+
+cudaError_t launch_yuy2_to_rgb(const uint8_t* d_yuy2, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int width, int height,
+                               int n_frames, cudaStream_t s) {
+    if (width <= 0 || height <= 0 || n_frames <= 0) return cudaSuccess;
+    const bool aligned = (width % 8 == 0) && (stride_in % 16 == 0) && (stride_out % 16 == 0) && ((size_t)width * 3 % 16 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(d_yuy2) | reinterpret_cast<uintptr_t>(d_rgb)) % 16 == 0);
+    if (aligned) {
+        const long long items = (long long)n_frames * height * ((width + 255) / 256);
+        long long blocks = (items + kCvtWarps - 1) / kCvtWarps;
+        if (blocks > 148LL * 8 * 4) blocks = 148LL * 8 * 4;
+        yuy2_to_rgb_vec_kernel<<<(unsigned)blocks, kCvtWarps * 32, 0, s>>>(d_yuy2, stride_in, d_rgb, stride_out, width, height, n_frames);
+    } else {
+        const long long items = (long long)n_frames * height * ((width + 1) / 2);
+        long long blocks = (items + 255) / 256;
+        if (blocks > 148LL * 32) blocks = 148LL * 32;
+        yuy2_to_rgb_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_yuy2, stride_in, d_rgb, stride_out, width, height, n_frames);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: fused crop (zero border) + NV12->RGB + OpenCV INTER_LINEAR (fixed point) + normalise.
 // One thread per output pixel; output goes straight into the patch-major A operand of the
 // patch-embed GEMM: patches[target][token][c*256 + py*16 + px].
@@ -246,6 +339,39 @@ cudaError_t launch_crop_resize_norm(FrameDesc f, TargetState* d_state, const int
     if (n <= 0) return cudaSuccess;
     dim3 grid((out_size * out_size + 255) / 256, n);
     crop_resize_norm_kernel<<<grid, 256, 0, s>>>(f, d_state, d_slots, factor, out_size, d_norm_lut, d_patches, patches_stride, p_hi, p_lo, stamp);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// RGB24 resize, OpenCV INTER_LINEAR fixed-point semantics (bit-exact with cv2.resize) — SURVEY.md §8(f)
+// row 1: the display upscale after the probe (≙ rgaconvert 640x512 -> 1280x1024, src/pipeline_ir.rs:62-73).  One thread per
+// destination pixel; a warp reads two source rows segments and writes 96 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_rgb_linear_kernel(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst,
+                                                                int dw, int dh) {
+    const long long total = (long long)dw * dh;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int dx = (int)(i % dw), dy = (int)(i / dw);
+        const Tap tx = lin_tap(dx, sw, dw, true);
+        const Tap ty = lin_tap(dy, sh, dh, false);
+        const int x0 = tx.ofs, x1 = min(tx.ofs + 1, sw - 1);
+        const int y0 = min(max(ty.ofs, 0), sh - 1), y1 = min(max(ty.ofs + 1, 0), sh - 1);
+        const uint8_t *r0 = src + (size_t)y0 * sw * 3, *r1 = src + (size_t)y1 * sw * 3;
+        uint8_t* o = dst + (size_t)i * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const int t0 = r0[x0 * 3 + ch] * tx.a0 + r0[x1 * 3 + ch] * tx.a1;
+            const int t1 = r1[x0 * 3 + ch] * tx.a0 + r1[x1 * 3 + ch] * tx.a1;
+            o[ch] = (uint8_t)((((ty.a0 * (t0 >> 4)) >> 16) + ((ty.a1 * (t1 >> 4)) >> 16) + 2) >> 2);
+        }
+    }
+}
+
+cudaError_t launch_resize_rgb_linear(const uint8_t* d_src, int sw, int sh, uint8_t* d_dst, int dw, int dh, cudaStream_t s) {
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return cudaSuccess;
+    long long blocks = ((long long)dw * dh + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    resize_rgb_linear_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_src, sw, sh, d_dst, dw, dh);
     return cudaGetLastError();
 }
 

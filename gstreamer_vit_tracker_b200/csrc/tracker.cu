@@ -62,6 +62,8 @@ struct vt_tracker {
     // frame + state
     uint8_t* d_frame = nullptr;
     uint8_t* d_rgb = nullptr;  // lazily allocated, vt_convert_nv12_rgb
+    uint8_t *d_fmt_in = nullptr, *d_fmt_out = nullptr;  // lazily grown scratch of the format entry points (YUY2, resize)
+    size_t fmt_in_cap = 0, fmt_out_cap = 0;
     uint8_t* h_stage = nullptr;  // pinned staging for non-pinned callers
     size_t h_stage_bytes = 0;
     int frame_valid = 1;
@@ -632,6 +634,8 @@ void vt_tracker_destroy(vt_tracker* t) {
     for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
     for (auto& e : t->ev)
         if (e) cudaEventDestroy(e);
+    if (t->d_fmt_in) cudaFree(t->d_fmt_in);
+    if (t->d_fmt_out) cudaFree(t->d_fmt_out);
     void* dev[] = {t->d_weights, t->d_lut, t->d_hann, t->d_frame, t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
                    t->patches_x, t->patches_z, t->Zemb, t->X, t->QKV, t->ATT, t->HID, t->Yf, t->H1, t->d_dbg,
                    t->w_hi, t->w_lo, t->px_hi, t->px_lo, t->pz_hi, t->pz_lo, t->ln_hi, t->ln_lo, t->att_hi, t->att_lo,
@@ -1127,6 +1131,74 @@ vt_status vt_convert_nv12_rgb_device(vt_tracker* t, const uint8_t* d_nv12, size_
         return VT_ERR_CUDA;
     }
     ++t->kernel_launches;
+    return VT_OK;
+}
+
+// ---- format steps either side of the RGB probe ---------------------------------------------------------------
+static vt_status fmt_scratch(vt_tracker* t, size_t in_bytes, size_t out_bytes) {
+    if (in_bytes > t->fmt_in_cap) {
+        if (t->d_fmt_in) cudaFree(t->d_fmt_in);
+        t->d_fmt_in = nullptr, t->fmt_in_cap = 0;
+        VT_CUDA(cudaMalloc(&t->d_fmt_in, in_bytes + 256));
+        t->fmt_in_cap = in_bytes;
+    }
+    if (out_bytes > t->fmt_out_cap) {
+        if (t->d_fmt_out) cudaFree(t->d_fmt_out);
+        t->d_fmt_out = nullptr, t->fmt_out_cap = 0;
+        VT_CUDA(cudaMalloc(&t->d_fmt_out, out_bytes + 256));
+        t->fmt_out_cap = out_bytes;
+    }
+    return VT_OK;
+}
+
+vt_status vt_convert_yuy2_rgb_device(vt_tracker* t, const uint8_t* d_yuy2, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int32_t width,
+                                     int32_t height, int32_t n_frames) {
+    if (!t || !d_yuy2 || !d_rgb || width <= 0 || height <= 0 || n_frames <= 0) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    VT_CUDA(launch_yuy2_to_rgb(d_yuy2, stride_in, d_rgb, stride_out, width, height, n_frames, t->stream));
+    ++t->kernel_launches;
+    return VT_OK;
+}
+
+vt_status vt_convert_yuy2_rgb(vt_tracker* t, const uint8_t* yuy2, size_t len, int32_t width, int32_t height, uint8_t* rgb_out) {
+    if (!t || !yuy2 || !rgb_out || width <= 0 || height <= 0 || t->in_flight) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    const size_t in_bytes = (((size_t)width * 2 + 3) & ~(size_t)3) * height, out_bytes = (size_t)width * height * 3;
+    if (len < in_bytes) {  // short buffer -> black frame, as the NV12 path (src/nv12_convert.rs:48-50)
+        memset(rgb_out, 0, out_bytes);
+        return VT_OK;
+    }
+    vt_status st = fmt_scratch(t, in_bytes, out_bytes);
+    if (st != VT_OK) return st;
+    VT_CUDA(cudaMemcpyAsync(t->d_fmt_in, yuy2, in_bytes, cudaMemcpyHostToDevice, t->stream));
+    VT_CUDA(launch_yuy2_to_rgb(t->d_fmt_in, in_bytes, t->d_fmt_out, out_bytes, width, height, 1, t->stream));
+    ++t->kernel_launches;
+    VT_CUDA(cudaMemcpyAsync(rgb_out, t->d_fmt_out, out_bytes, cudaMemcpyDeviceToHost, t->stream));
+    VT_CUDA(cudaStreamSynchronize(t->stream));
+    t->h2d_bytes += in_bytes, t->d2h_bytes += out_bytes;
+    return VT_OK;
+}
+
+vt_status vt_resize_rgb_device(vt_tracker* t, const uint8_t* d_rgb, int32_t sw, int32_t sh, uint8_t* d_out, int32_t dw, int32_t dh) {
+    if (!t || !d_rgb || !d_out || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    VT_CUDA(launch_resize_rgb_linear(d_rgb, sw, sh, d_out, dw, dh, t->stream));
+    ++t->kernel_launches;
+    return VT_OK;
+}
+
+vt_status vt_resize_rgb(vt_tracker* t, const uint8_t* rgb, int32_t sw, int32_t sh, uint8_t* out, int32_t dw, int32_t dh) {
+    if (!t || !rgb || !out || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || t->in_flight) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    const size_t in_bytes = (size_t)sw * sh * 3, out_bytes = (size_t)dw * dh * 3;
+    vt_status st = fmt_scratch(t, in_bytes, out_bytes);
+    if (st != VT_OK) return st;
+    VT_CUDA(cudaMemcpyAsync(t->d_fmt_in, rgb, in_bytes, cudaMemcpyHostToDevice, t->stream));
+    VT_CUDA(launch_resize_rgb_linear(t->d_fmt_in, sw, sh, t->d_fmt_out, dw, dh, t->stream));
+    ++t->kernel_launches;
+    VT_CUDA(cudaMemcpyAsync(out, t->d_fmt_out, out_bytes, cudaMemcpyDeviceToHost, t->stream));
+    VT_CUDA(cudaStreamSynchronize(t->stream));
+    t->h2d_bytes += in_bytes, t->d2h_bytes += out_bytes;
     return VT_OK;
 }
 

@@ -124,6 +124,10 @@ struct FrameDesc {
 cudaError_t launch_nv12_to_rgb(const uint8_t* d_nv12, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int width, int height,
                                int n_frames, cudaStream_t s);
 
+cudaError_t launch_yuy2_to_rgb(const uint8_t* d_yuy2, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int width, int height,
+                               int n_frames, cudaStream_t s);
+cudaError_t launch_resize_rgb_linear(const uint8_t* d_src, int sw, int sh, uint8_t* d_dst, int dw, int dh, cudaStream_t s);
+
 // fused crop + (NV12->RGB) + bilinear resize + normalise -> patch-major tokens A[target][n_tok][768]
 // slots: list of target slot indices processed (device array), n = count. factor 2 -> 128 template, 4 -> 256 search
 // p_hi / p_lo (nullable): the same values as a bf16 (hi, lo) split, the A operand of the tensor-core patch-embed GEMM

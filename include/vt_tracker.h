@@ -158,6 +158,20 @@ vt_status vt_convert_nv12_rgb_device(vt_tracker* t, const uint8_t* d_nv12, size_
                                      size_t stride_out, int32_t n_frames);
 
 /* ------------------------------------------------------------------------------------------- */
+/* format steps either side of the RGB probe                            */
+/* ------------------------------------------------------------------------------------------- */
+/* ≙ the `videoconvert` YUY2 -> RGB step of src/pipeline_ir.rs:27-56 (GStreamer element; its source is not in the reference tree,
+ * so this follows the reference's own BT.601 integer arithmetic, src/nv12_convert.rs:24-30,124-126, on packed 4:2:2).
+ * yuy2: rows of (width*2 rounded up to 4) bytes, Y0 U Y1 V; rgb_out: h*w*3, R,G,B.  A short buffer gives a black frame. */
+vt_status vt_convert_yuy2_rgb(vt_tracker* t, const uint8_t* yuy2, size_t len, int32_t width, int32_t height, uint8_t* rgb_out);
+vt_status vt_convert_yuy2_rgb_device(vt_tracker* t, const uint8_t* d_yuy2, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int32_t width,
+                                     int32_t height, int32_t n_frames);
+/* ≙ the `rgaconvert` RGB 640x512 -> 1280x1024 display upscale of src/pipeline_ir.rs:62-73 (hardware scaler element): bilinear with
+ * OpenCV INTER_LINEAR fixed-point semantics, bit-exact with cv2.resize (any source / destination size). */
+vt_status vt_resize_rgb(vt_tracker* t, const uint8_t* rgb, int32_t src_w, int32_t src_h, uint8_t* out, int32_t dst_w, int32_t dst_h);
+vt_status vt_resize_rgb_device(vt_tracker* t, const uint8_t* d_rgb, int32_t src_w, int32_t src_h, uint8_t* d_out, int32_t dst_w, int32_t dst_h);
+
+/* ------------------------------------------------------------------------------------------- */
 /* overlay                                                                                      */
 /* ------------------------------------------------------------------------------------------- */
 typedef enum {
@@ -225,6 +239,10 @@ typedef enum { VT_CMD_MOVE_UP = 0, VT_CMD_MOVE_DOWN, VT_CMD_MOVE_LEFT, VT_CMD_MO
 typedef enum { VT_STATE_SELECT_START = 0, VT_STATE_SELECT_END, VT_STATE_TRACKING, VT_STATE_LOST } vt_state;
 /* ≙ SelectionState (src/selection_state.rs:9-18) */
 typedef struct { int32_t cursor_x, cursor_y, start_x, start_y, phase, step, fast_step; } vt_selection;
+
+/* ≙ the keyboard reader's byte -> UserCommand map (src/raw_mode_guard.rs:65-101): returns 1 and fills cmd (vt_command) / fast
+ * when `byte` maps to a command, 0 when the reference ignores it.  VT_CMD_QUIT is what clears the `running` flag there (:89-92). */
+int32_t vt_command_from_key(uint8_t byte, int32_t* cmd, int32_t* fast);
 
 typedef struct vt_context vt_context;
 /* ≙ TrackerContext::new(model_path, width, height) (src/tracker_context.rs:19); creates its tracker from cfg */

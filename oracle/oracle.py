@@ -47,6 +47,10 @@ def lib() -> C.CDLL:
         L = C.CDLL(_SO)
         L.vto_nv12_to_rgb.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, _u8p, C.c_int]
         L.vto_nv12_to_rgb.restype = None
+        L.vto_yuy2_to_rgb.argtypes = [_u8p, C.c_size_t, C.c_size_t, C.c_size_t, _u8p, C.c_int]
+        L.vto_yuy2_to_rgb.restype = None
+        L.vto_yuy2_stride.argtypes = [C.c_size_t]
+        L.vto_yuy2_stride.restype = C.c_size_t
         for name, n_int in (("vto_draw_rect_nv12", 8), ("vto_draw_crosshair_nv12", 6), ("vto_draw_background_nv12", 7),
                             ("vto_draw_cursor_nv12", 4), ("vto_draw_selection_nv12", 7)):
             getattr(L, name).argtypes = [_u8p] + [C.c_int] * n_int
@@ -123,6 +127,18 @@ def _f32(a: np.ndarray):
 def nv12_to_rgb(nv12: np.ndarray, width: int, height: int, threads: int = 1) -> np.ndarray:
     out = np.empty((height, width, 3), np.uint8)
     lib().vto_nv12_to_rgb(_u8(nv12), nv12.size, width, height, _u8(out), threads)
+    return out
+
+
+def yuy2_stride(width: int) -> int:
+    return lib().vto_yuy2_stride(width)
+
+
+def yuy2_to_rgb(yuy2: np.ndarray, width: int, height: int, threads: int = 1) -> np.ndarray:
+    """YUY2 (packed 4:2:2, rows of yuy2_stride(width) bytes) -> HWC RGB; SURVEY.md §8(f) row 1."""
+    yuy2 = np.ascontiguousarray(yuy2, dtype=np.uint8).reshape(-1)
+    out = np.empty((height, width, 3), np.uint8)
+    lib().vto_yuy2_to_rgb(_u8(yuy2), yuy2.size, width, height, _u8(out), threads)
     return out
 
 

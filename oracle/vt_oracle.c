@@ -86,6 +86,35 @@ void vto_nv12_to_rgb(const uint8_t* nv12, size_t len, int width, int height, uin
 }
 
 /* ======================================================================================= */
+/* YUY2 -> RGB  (the `videoconvert` step of src/pipeline_ir.rs:27-56)   */
+/* ======================================================================================= */
+/* The reference delegates this step to GStreamer's videoconvert element, whose source is not in the reference tree: PARITY
+ * UNPINNED at that boundary.  Restated with the reference's own BT.601 limited-range integer arithmetic
+ * (src/nv12_convert.rs:24-30,124-126,41-43) applied to packed 4:2:2 (bytes Y0 U Y1 V; one chroma pair per two pixels of a row,
+ * row stride = width*2 rounded up to 4 bytes as GStreamer lays YUY2 out); a short buffer yields a black frame like :48-50. */
+size_t vto_yuy2_stride(size_t width) { return (width * 2 + 3) & ~(size_t)3; }
+void vto_yuy2_to_rgb(const uint8_t* yuy2, size_t len, size_t width, size_t height, uint8_t* rgb_out, int threads) {
+    const size_t stride = vto_yuy2_stride(width);
+    memset(rgb_out, 0, width * height * 3);
+    if (len < stride * height) return;
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+#endif
+    for (long long r = 0; r < (long long)height; ++r) {
+        const uint8_t* in = yuy2 + (size_t)r * stride;
+        uint8_t* o = rgb_out + (size_t)r * width * 3;
+        for (size_t col = 0; col < width; ++col) {
+            const uint8_t* q = in + (col >> 1) * 4;
+            const int32_t yv = 298 * ((int32_t)q[(col & 1) * 2] - 16), u = q[1], v = q[3];
+            o[col * 3 + 0] = clamp_u8((yv + 409 * (v - 128) + 128) >> 8);
+            o[col * 3 + 1] = clamp_u8((yv - 100 * (u - 128) - 208 * (v - 128) + 128) >> 8);
+            o[col * 3 + 2] = clamp_u8((yv + 516 * (u - 128) + 128) >> 8);
+        }
+    }
+}
+
+/* ======================================================================================= */
 /* Glyph table — src/nv12_convert.rs:255-296 == src/drawing.rs:53-94                         */
 /* ======================================================================================= */
 typedef struct { char ch; uint8_t rows[7]; } glyph_t;

@@ -28,6 +28,9 @@ extern "C" {
 
 /* ---- NV12 -> RGB, src/nv12_convert.rs:46-169 ------------------------------------------- */
 void vto_nv12_to_rgb(const uint8_t* nv12, size_t len, int width, int height, uint8_t* rgb_out, int threads);
+/* YUY2 (packed 4:2:2) -> RGB with the same integer arithmetic; SURVEY.md §8(f) row 1 (parity unpinned: GStreamer videoconvert) */
+size_t vto_yuy2_stride(size_t width);
+void vto_yuy2_to_rgb(const uint8_t* yuy2, size_t len, size_t width, size_t height, uint8_t* rgb_out, int threads);
 
 /* ---- NV12 overlays (Y plane only), src/nv12_convert.rs:172-343, src/drawing.rs:5-50 ------ */
 void vto_draw_rect_nv12(uint8_t* d, int width, int height, int x, int y, int w, int h, int thickness, int brightness);

@@ -89,3 +89,24 @@ def test_timing_stats(impl, built):
     t = make()
     t.add_interval(0)
     assert t.fps() == 0.0  # avg == 0 -> 0.0 (src/timing_stats.rs:41-45)
+
+
+def test_keyboard_map_matches_reference_source(built):
+    """vt_command_from_key == the byte -> UserCommand match of src/raw_mode_guard.rs:65-101 for all 256 byte values."""
+    import ctypes as C
+    import json
+    import os
+
+    from gstreamer_vit_tracker_b200 import _lib
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "keymap.json")))
+    names = ["MoveUp", "MoveDown", "MoveLeft", "MoveRight", "Confirm", "Cancel", "Quit"]
+    L = _lib.lib()
+    for byte in range(256):
+        cmd, fast = C.c_int32(-1), C.c_int32(-1)
+        hit = L.vt_command_from_key(byte, C.byref(cmd), C.byref(fast))
+        want = gold.get(str(byte))
+        if want is None:
+            assert hit == 0, byte
+        else:
+            assert hit == 1 and names[cmd.value] == want[0] and bool(fast.value) == want[1], (byte, cmd.value, fast.value, want)

@@ -11,6 +11,9 @@ Sources of truth, none of which is the C oracle:
   * state_traces.json    — traces of a pure-Python reading of TrackerContext / SelectionState / TimingStats
                            (src/tracker_context.rs, src/selection_state.rs, src/timing_stats.rs);
   * resize_golden.json   — sha256 of cv2.resize(INTER_LINEAR) outputs (OpenCV 4.13) on hash-generated inputs;
+  * yuy2_golden.json     — YUY2 -> RGB known answers / frame hashes from a pure-Python evaluation of the reference's BT.601 integer
+                           formulas on packed 4:2:2, and cv2.resize(INTER_LINEAR) up-scale hashes (SURVEY.md §8(f) row 1);
+  * keymap.json          — the keyboard byte -> UserCommand table parsed out of /root/reference/src/raw_mode_guard.rs:65-101;
   * trackervit_nano.json — boxes and scores produced by the third-party cv2.TrackerVit (OpenCV 4.13, DNN CPU
                            backend) running an ONNX export of the same weight file.
 The tests compare the C oracle (and, on the GPU, the CUDA path) with these files.
@@ -501,9 +504,74 @@ def gen_trackervit():
     json.dump(out, open(os.path.join(GOLD, "trackervit_nano.json"), "w"))
 
 
+def gen_yuy2():
+    """yuy2_golden.json — (a) known answers and sha256 of frames converted by a pure-Python evaluation of the reference's BT.601
+    integer formulas (/root/reference/src/nv12_convert.rs:24-30,124-126,41-43) on packed 4:2:2 input (rows of round_up_4(2*w) bytes,
+    Y0 U Y1 V); (b) the maximum deviation from the third-party cv2.cvtColor(COLOR_YUV2RGB_YUY2), recorded for information
+    (OpenCV uses 20-bit coefficients: a different rounding of the same BT.601 limited-range matrix);
+    (c) sha256 of cv2.resize(INTER_LINEAR) up-scales of hash-generated RGB frames (640x512 -> 1280x1024 and odd cases)."""
+    import cv2
+
+    def clamp(v):
+        return 0 if v < 0 else (255 if v > 255 else v)
+
+    def px(y, u, v):
+        yv = 298 * (y - 16)
+        return (clamp((yv + 409 * (v - 128) + 128) >> 8), clamp((yv - 100 * (u - 128) - 208 * (v - 128) + 128) >> 8),
+                clamp((yv + 516 * (u - 128) + 128) >> 8))
+
+    def convert(buf, w, h):
+        stride = (2 * w + 3) & ~3
+        out = np.zeros((h, w, 3), np.uint8)
+        if buf.size < stride * h:
+            return out
+        for r in range(h):
+            row = buf[r * stride:(r + 1) * stride]
+            for c in range(w):
+                q = row[(c >> 1) * 4:(c >> 1) * 4 + 4]
+                out[r, c] = px(int(q[(c & 1) * 2]), int(q[1]), int(q[3]))
+        return out
+
+    gold = {"kat": [], "frames": [], "resize": []}
+    for (y, u, v) in [(16, 128, 128), (235, 128, 128), (81, 90, 240), (145, 54, 34), (41, 240, 110), (0, 0, 0), (255, 255, 255), (255, 0, 0), (0, 255, 255)]:
+        gold["kat"].append({"yuv": [y, u, v], "rgb": list(px(y, u, v))})
+    max_dev = 0
+    for i, (w, h) in enumerate([(64, 48), (40, 6), (33, 5), (2, 2), (1, 3), (72, 10)]):
+        stride = (2 * w + 3) & ~3
+        buf = (synth.hash_u64(900 + i, stride * h) & np.uint64(0xFF)).astype(np.uint8)
+        rgb = convert(buf, w, h)
+        gold["frames"].append({"w": w, "h": h, "seed": 900 + i, "sha256": sha(rgb)})
+        if w % 2 == 0:
+            ref = cv2.cvtColor(buf.reshape(h, stride // 2, 2)[:, :w], cv2.COLOR_YUV2RGB_YUY2)
+            max_dev = max(max_dev, int(np.abs(ref.astype(int) - rgb.astype(int)).max()))
+    gold["max_abs_dev_from_cv2_cvtColor"] = max_dev
+    for i, (sw, sh_, dw, dh) in enumerate([(640, 512, 1280, 1024), (64, 48, 128, 96), (33, 17, 100, 41), (640, 512, 960, 768), (50, 40, 25, 20)]):
+        src = (synth.hash_u64(950 + i, sw * sh_ * 3) & np.uint64(0xFF)).astype(np.uint8).reshape(sh_, sw, 3)
+        gold["resize"].append({"sw": sw, "sh": sh_, "dw": dw, "dh": dh, "seed": 950 + i,
+                               "sha256": sha(cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR))})
+    json.dump(gold, open(os.path.join(GOLD, "yuy2_golden.json"), "w"), indent=0)
+
+
+def gen_keymap():
+    """keymap.json — byte -> (UserCommand, fast) parsed out of the match in /root/reference/src/raw_mode_guard.rs:65-101."""
+    src = open(os.path.join(REF, "raw_mode_guard.rs")).read()
+    body = src[src.index("let cmd = match byte {"):src.index("if let Some(c) = cmd")]
+    out = {}
+    for m in re.finditer(r"^\s*((?:\d+\s*\|\s*)*\d+)\s*=>\s*(\{[^}]*\},?|[^,{]*,)", body, re.M | re.S):
+        keys = [int(k) for k in re.findall(r"\d+", m.group(1))]
+        rhs = m.group(2)
+        c = re.search(r"UserCommand::(\w+)(?:\((true|false)\))?", rhs)
+        for k in keys:
+            out[str(k)] = [c.group(1), c.group(2) == "true"] if c else None
+    assert out["91"] is None and out["113"] == ["Quit", False] and out["84"] == ["MoveUp", True] and len(out) == 33, (len(out), out)
+    json.dump(out, open(os.path.join(GOLD, "keymap.json"), "w"), indent=0, sort_keys=True)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["kat", "glyphs", "overlay", "state", "resize", "trackervit"]
+    which = sys.argv[1:] or ["kat", "glyphs", "overlay", "state", "resize", "trackervit", "keymap", "yuy2"]
+    if "keymap" in which: gen_keymap()
+    if "yuy2" in which: gen_yuy2()
     font = gen_glyphs() if ("glyphs" in which or "overlay" in which) else None
     if "kat" in which: gen_nv12_kat()
     if "overlay" in which: gen_overlay(font)
