@@ -28,6 +28,35 @@ __device__ __forceinline__ void yuv_px(int y, const Chroma& c, int& r, int& g, i
     b = clamp255((yv + c.bu) >> 8);
 }
 
+// Vectorised form used by the full-frame kernels: the -16 of the luma term and the +128 rounding are folded into three per-chroma
+// constants, so a pixel costs 3 IMAD + 3 SHR + 3 clamp (VIMNMX.relu) — (298*(y-16) + k + 128) >> 8 == (298*y + (k + 128 - 4768)) >> 8
+// exactly.  Eight pixels (24 bytes) are packed into six words with byte-weight IMADs.
+struct ChromaF { int r, g, b; };
+__device__ __forceinline__ ChromaF chroma_folded(int u, int v) {
+    ChromaF c;
+    c.r = 409 * (v - 128) + (128 - 298 * 16);
+    c.g = -100 * (u - 128) - 208 * (v - 128) + (128 - 298 * 16);
+    c.b = 516 * (u - 128) + (128 - 298 * 16);
+    return c;
+}
+__device__ __forceinline__ void yuv_px_fast(int y, const ChromaF& c, int& r, int& g, int& b) {
+    r = __vimin_s32_relu((298 * y + c.r) >> 8, 255);
+    g = __vimin_s32_relu((298 * y + c.g) >> 8, 255);
+    b = __vimin_s32_relu((298 * y + c.b) >> 8, 255);
+}
+// r/g/b[0..7] (each 0..255) -> 24 interleaved bytes as three uint2
+__device__ __forceinline__ void pack_rgb8(const int (&r)[8], const int (&g)[8], const int (&b)[8], uint2* dst) {
+    uint32_t w[6];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int o = 4 * h;
+        w[3 * h + 0] = (uint32_t)(r[o] + (g[o] << 8) + (b[o] << 16) + (r[o + 1] << 24));
+        w[3 * h + 1] = (uint32_t)(g[o + 1] + (b[o + 1] << 8) + (r[o + 2] << 16) + (g[o + 2] << 24));
+        w[3 * h + 2] = (uint32_t)(b[o + 2] + (r[o + 3] << 8) + (g[o + 3] << 16) + (b[o + 3] << 24));
+    }
+    dst[0] = make_uint2(w[0], w[1]), dst[1] = make_uint2(w[2], w[3]), dst[2] = make_uint2(w[4], w[5]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1 fast path: W % 16 == 0, H even.  One warp converts a 256-px segment of one row pair:
 // each lane loads 8 Y bytes from two rows + 4 UV pairs (8-byte loads, 256 B contiguous per warp),
@@ -41,14 +70,12 @@ __global__ void __launch_bounds__(kCvtWarps * 32) nv12_to_rgb_vec_kernel(const u
                                                                        int n_frames) {
     __shared__ __align__(16) uint8_t stage[kCvtWarps][2][768];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int segs = (W + 255) >> 8, pairs = H >> 1;
-    const long long total = (long long)n_frames * pairs * segs;
-    const long long wstride = (long long)gridDim.x * kCvtWarps;
-    for (long long item = (long long)blockIdx.x * kCvtWarps + warp; item < total; item += wstride) {
-        const int seg = (int)(item % segs);
-        const long long t = item / segs;
-        const int pair = (int)(t % pairs);
-        const int frame = (int)(t / pairs);
+    // grid = (segment groups, row pairs, frames): no index division in the kernel
+    const int segs = (W + 255) >> 8;
+    (void)n_frames;
+    {
+        const int seg = blockIdx.x * (blockDim.x >> 5) + warp, pair = blockIdx.y, frame = blockIdx.z;
+        if (seg >= segs) return;
         const uint8_t* yp = in + (size_t)frame * stride_in;
         const uint8_t* uvp = yp + (size_t)W * H;
         uint8_t* op = out + (size_t)frame * stride_out;
@@ -60,35 +87,21 @@ __global__ void __launch_bounds__(kCvtWarps * 32) nv12_to_rgb_vec_kernel(const u
             const uint2 uv = __ldg(reinterpret_cast<const uint2*>(uvp + (size_t)pair * W + x));
             const uint32_t yw[2][2] = {{ya.x, ya.y}, {yb.x, yb.y}};
             const uint32_t uvw[2] = {uv.x, uv.y};
-            uint8_t px[2][24];
+            int r[2][8], g[2][8], b[2][8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {  // 4 chroma pairs
                 const uint32_t w = uvw[q >> 1] >> ((q & 1) * 16);
-                const Chroma c = chroma_terms((int)(w & 0xff), (int)((w >> 8) & 0xff));
+                const ChromaF c = chroma_folded((int)(w & 0xff), (int)((w >> 8) & 0xff));
 #pragma unroll
                 for (int row = 0; row < 2; ++row)
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const int i = q * 2 + k;
-                        const int yv = (int)((yw[row][i >> 2] >> ((i & 3) * 8)) & 0xff);
-                        int r, g, b;
-                        yuv_px(yv, c, r, g, b);
-                        px[row][i * 3 + 0] = (uint8_t)r;
-                        px[row][i * 3 + 1] = (uint8_t)g;
-                        px[row][i * 3 + 2] = (uint8_t)b;
+                        yuv_px_fast((int)((yw[row][i >> 2] >> ((i & 3) * 8)) & 0xff), c, r[row][i], g[row][i], b[row][i]);
                     }
             }
 #pragma unroll
-            for (int row = 0; row < 2; ++row) {
-                uint2* dst = reinterpret_cast<uint2*>(&stage[warp][row][lane * 24]);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    uint2 v;
-                    v.x = px[row][j * 8 + 0] | (px[row][j * 8 + 1] << 8) | (px[row][j * 8 + 2] << 16) | ((uint32_t)px[row][j * 8 + 3] << 24);
-                    v.y = px[row][j * 8 + 4] | (px[row][j * 8 + 5] << 8) | (px[row][j * 8 + 6] << 16) | ((uint32_t)px[row][j * 8 + 7] << 24);
-                    dst[j] = v;
-                }
-            }
+            for (int row = 0; row < 2; ++row) pack_rgb8(r[row], g[row], b[row], reinterpret_cast<uint2*>(&stage[warp][row][lane * 24]));
         }
         __syncwarp();
         const int row_bytes = seg_px * 3;  // multiple of 48
@@ -98,7 +111,6 @@ __global__ void __launch_bounds__(kCvtWarps * 32) nv12_to_rgb_vec_kernel(const u
             for (int off = lane * 16; off < row_bytes; off += 32 * 16)
                 *reinterpret_cast<uint4*>(g + off) = *reinterpret_cast<const uint4*>(&stage[warp][row][off]);
         }
-        __syncwarp();
     }
 }
 
@@ -131,14 +143,14 @@ __global__ void nv12_to_rgb_generic_kernel(const uint8_t* __restrict__ in, size_
 cudaError_t launch_nv12_to_rgb(const uint8_t* d_nv12, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int width, int height,
                                int n_frames, cudaStream_t s) {
     if (width <= 0 || height <= 0 || n_frames <= 0) return cudaSuccess;
-    const bool aligned = (width % 16 == 0) && (height % 2 == 0) && (stride_in % 16 == 0) && (stride_out % 16 == 0) &&
+    const bool aligned = (width % 16 == 0) && (height % 2 == 0) && (height / 2 <= 65535) && (n_frames <= 65535) && (stride_in % 16 == 0) &&
+                         (stride_out % 16 == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_nv12) | reinterpret_cast<uintptr_t>(d_rgb)) % 16 == 0);
     if (aligned) {
-        const long long items = (long long)n_frames * (height / 2) * ((width + 255) / 256);
-        long long blocks = (items + kCvtWarps - 1) / kCvtWarps;
-        const long long cap = 148LL * 8 * 4;  // multiple of the SM count; grid-stride beyond that
-        if (blocks > cap) blocks = cap;
-        nv12_to_rgb_vec_kernel<<<(unsigned)blocks, kCvtWarps * 32, 0, s>>>(d_nv12, stride_in, d_rgb, stride_out, width, height, n_frames);
+        const int segs = (width + 255) / 256;
+        const int wpb = segs < kCvtWarps ? segs : kCvtWarps;  // narrow frames: no idle warps
+        const dim3 grid((segs + wpb - 1) / wpb, height / 2, n_frames);  // one warp per 256-px x 2-row item
+        nv12_to_rgb_vec_kernel<<<grid, wpb * 32, 0, s>>>(d_nv12, stride_in, d_rgb, stride_out, width, height, n_frames);
     } else {
         const long long items = (long long)n_frames * ((width + 1) / 2) * ((height + 1) / 2);
         long long blocks = (items + 255) / 256;
@@ -160,12 +172,10 @@ __global__ void __launch_bounds__(kCvtWarps * 32) yuy2_to_rgb_vec_kernel(const u
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int segs = (W + 255) >> 8;
     const size_t row_in = (size_t)W * 2;
-    const long long total = (long long)n_frames * H * segs;
-    const long long wstride = (long long)gridDim.x * kCvtWarps;
-    for (long long item = (long long)blockIdx.x * kCvtWarps + warp; item < total; item += wstride) {
-        const int seg = (int)(item % segs);
-        const long long t = item / segs;
-        const int row = (int)(t % H), frame = (int)(t / H);
+    (void)n_frames, (void)H;
+    {
+        const int seg = blockIdx.x * (blockDim.x >> 5) + warp, row = blockIdx.y, frame = blockIdx.z;
+        if (seg >= segs) return;
         const uint8_t* ip = in + (size_t)frame * stride_in + (size_t)row * row_in;
         uint8_t* op = out + (size_t)frame * stride_out + ((size_t)row * W + (size_t)seg * 256) * 3;
         const int x = seg * 256 + lane * 8;
@@ -173,31 +183,20 @@ __global__ void __launch_bounds__(kCvtWarps * 32) yuy2_to_rgb_vec_kernel(const u
         if (x < W) {
             const uint4 q = __ldg(reinterpret_cast<const uint4*>(ip + (size_t)x * 2));
             const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-            uint8_t px[24];
+            int r[8], g[8], b[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {  // one Y0 U Y1 V word = two pixels
-                const Chroma c = chroma_terms((int)((w4[k] >> 8) & 0xff), (int)(w4[k] >> 24));
-                int r, g, b;
-                yuv_px((int)(w4[k] & 0xff), c, r, g, b);
-                px[k * 6 + 0] = (uint8_t)r, px[k * 6 + 1] = (uint8_t)g, px[k * 6 + 2] = (uint8_t)b;
-                yuv_px((int)((w4[k] >> 16) & 0xff), c, r, g, b);
-                px[k * 6 + 3] = (uint8_t)r, px[k * 6 + 4] = (uint8_t)g, px[k * 6 + 5] = (uint8_t)b;
+                const ChromaF c = chroma_folded((int)((w4[k] >> 8) & 0xff), (int)(w4[k] >> 24));
+                yuv_px_fast((int)(w4[k] & 0xff), c, r[2 * k], g[2 * k], b[2 * k]);
+                yuv_px_fast((int)((w4[k] >> 16) & 0xff), c, r[2 * k + 1], g[2 * k + 1], b[2 * k + 1]);
             }
-            uint2* dst = reinterpret_cast<uint2*>(&stage[warp][lane * 24]);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                uint2 v;
-                v.x = px[j * 8 + 0] | (px[j * 8 + 1] << 8) | (px[j * 8 + 2] << 16) | ((uint32_t)px[j * 8 + 3] << 24);
-                v.y = px[j * 8 + 4] | (px[j * 8 + 5] << 8) | (px[j * 8 + 6] << 16) | ((uint32_t)px[j * 8 + 7] << 24);
-                dst[j] = v;
-            }
+            pack_rgb8(r, g, b, reinterpret_cast<uint2*>(&stage[warp][lane * 24]));
         }
         __syncwarp();
         const int row_bytes = seg_px * 3;  // multiple of 24; the tail (< 16 B) is written bytewise
         for (int off = lane * 16; off + 16 <= row_bytes; off += 32 * 16)
             *reinterpret_cast<uint4*>(op + off) = *reinterpret_cast<const uint4*>(&stage[warp][off]);
         if ((row_bytes & 15) && lane < (row_bytes & 15)) op[(row_bytes & ~15) + lane] = stage[warp][(row_bytes & ~15) + lane];
-        __syncwarp();
     }
 }
 
@@ -225,13 +224,14 @@ __global__ void yuy2_to_rgb_generic_kernel(const uint8_t* __restrict__ in, size_
 cudaError_t launch_yuy2_to_rgb(const uint8_t* d_yuy2, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int width, int height,
                                int n_frames, cudaStream_t s) {
     if (width <= 0 || height <= 0 || n_frames <= 0) return cudaSuccess;
-    const bool aligned = (width % 8 == 0) && (stride_in % 16 == 0) && (stride_out % 16 == 0) && ((size_t)width * 3 % 16 == 0) &&
+    const bool aligned = (width % 8 == 0) && (height <= 65535) && (n_frames <= 65535) && (stride_in % 16 == 0) && (stride_out % 16 == 0) &&
+                         ((size_t)width * 3 % 16 == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_yuy2) | reinterpret_cast<uintptr_t>(d_rgb)) % 16 == 0);
     if (aligned) {
-        const long long items = (long long)n_frames * height * ((width + 255) / 256);
-        long long blocks = (items + kCvtWarps - 1) / kCvtWarps;
-        if (blocks > 148LL * 8 * 4) blocks = 148LL * 8 * 4;
-        yuy2_to_rgb_vec_kernel<<<(unsigned)blocks, kCvtWarps * 32, 0, s>>>(d_yuy2, stride_in, d_rgb, stride_out, width, height, n_frames);
+        const int segs = (width + 255) / 256;
+        const int wpb = segs < kCvtWarps ? segs : kCvtWarps;
+        const dim3 grid((segs + wpb - 1) / wpb, height, n_frames);  // one warp per 256-px row segment
+        yuy2_to_rgb_vec_kernel<<<grid, wpb * 32, 0, s>>>(d_yuy2, stride_in, d_rgb, stride_out, width, height, n_frames);
     } else {
         const long long items = (long long)n_frames * height * ((width + 1) / 2);
         long long blocks = (items + 255) / 256;
