@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--streams-per-gpu", type=int, default=1)
     ap.add_argument("--ring", type=int, default=128, help="distinct frames per stream (ring > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-upload", action="store_true",
+                    help="e2e leg uploads the whole frame every step instead of the search windows of the active targets (cfg.upload_window)")
     ap.add_argument("--cpu-sample-frames", type=int, default=0)
     return ap.parse_args()
 
@@ -232,7 +234,7 @@ def run_b200(args):
         st = synth.SyntheticStream(spec)
         fb = st.frame_bytes()
         trk = api.VitTrack.new(wpath, spec.width, spec.height, fmt="nv12", device=local_rank, box_overlay=True,
-                               gemm_mode={"fp32simt": 0, "tcgen05x3": 1, "tcgen05": 2}[args.gemm])
+                               upload_window=not args.full_upload, gemm_mode={"fp32simt": 0, "tcgen05x3": 1, "tcgen05": 2}[args.gemm])
         pin = api.PinnedBuffer(ring_n * fb)
         host = pin.array.reshape(ring_n, fb)
         for i in range(ring_n):
@@ -394,6 +396,7 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "resolution": "1920x1080", "format": "NV12", "targets": 1, "model": args.model, "gemm": args.gemm,
                        "streams_per_gpu": S, "weights": "constructed random-init (SURVEY.md §8c)",
+                       "h2d": "whole frame" if args.full_upload else "search windows of the active targets only (2-D copies out of the pinned frame)",
                        "l2": f"inputs larger than L2: ring of {ring_n} distinct frames = {ring_n * fb0 / 1e6:.0f} MB per stream"},
             "e2e": {"value": frames_g / (ms_e2e_g * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
                     "p50_latency_ms": float(np.percentile(lat_all, 50)), "p99_latency_ms": float(np.percentile(lat_all, 99)),

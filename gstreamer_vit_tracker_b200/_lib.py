@@ -35,7 +35,7 @@ class vt_config(C.Structure):
         ("struct_size", C.c_uint32), ("weights_path", C.c_char_p), ("device", C.c_int32), ("format", C.c_int32),
         ("width", C.c_int32), ("height", C.c_int32), ("max_targets", C.c_int32), ("score_threshold", C.c_float),
         ("gemm_mode", C.c_int32), ("use_cuda_graph", C.c_int32), ("box_overlay", C.c_int32), ("overlay_gate", C.c_float),
-        ("reserved", C.c_int32 * 8),
+        ("debug_capture", C.c_int32), ("upload_window", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

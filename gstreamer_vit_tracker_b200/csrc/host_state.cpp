@@ -98,6 +98,7 @@ vt_status vt_context_create(const vt_config* cfg, vt_context** out) {
     vt_config c = *cfg;
     c.max_targets = 1;   // one VitTrack per TrackerContext (src/tracker_context.rs:8)
     c.box_overlay = 0;   // the probe issues explicit overlay commands
+    c.upload_window = 0; // ... on the device copy of the whole frame (vt_overlay_current)
     vt_tracker* t = nullptr;
     vt_status st = vt_tracker_create(&c, &t);  // ≙ VitTrack::new(model_path)?, src/tracker_context.rs:21
     if (st != VT_OK) return st;

@@ -357,7 +357,8 @@ static vt_status run_forward(vt_tracker* t) {
         t->kernels_per_frame = launches;
         return st;
     }
-    auto it = t->graphs.find(n);
+    const int key = n * 2 + (t->frame_valid ? 1 : 0);  // frame_valid is a kernel parameter baked into the captured graph
+    auto it = t->graphs.find(key);
     if (it == t->graphs.end()) {
         cudaGraph_t graph = nullptr;
         VT_CUDA(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
@@ -374,7 +375,7 @@ static vt_status run_forward(vt_tracker* t) {
         cudaGraphExec_t exec = nullptr;
         VT_CUDA(cudaGraphInstantiate(&exec, graph, 0));
         cudaGraphDestroy(graph);
-        it = t->graphs.emplace(n, exec).first;
+        it = t->graphs.emplace(key, exec).first;
         t->kernels_per_frame = launches;
     }
     VT_CUDA(cudaGraphLaunch(it->second, t->stream));
@@ -389,14 +390,56 @@ static vt_status sync_slots(vt_tracker* t) {
     return VT_OK;
 }
 
-// host -> device frame upload (pinned: direct async; pageable: staged through the handle's pinned buffer)
-static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len) {
+// Search window of a target in frame coordinates (App. A.1 with factor 4), clipped to the frame and grown to even coordinates
+// (NV12 chroma pairs).  Returns false when the window misses the frame.
+static bool search_window(const vt_tracker* t, const vt_bbox& r, int& x0, int& y0, int& x1, int& y1) {
+    if (r.width <= 0 || r.height <= 0) return false;
+    const int c = (int)ceil(sqrt((double)(int)((long long)r.width * r.height)) * 4.0);
+    const int wx = r.x + (r.width - c) / 2, wy = r.y + (r.height - c) / 2;
+    x0 = std::max(wx, 0) & ~1, y0 = std::max(wy, 0) & ~1;
+    x1 = std::min((std::min(wx + c, t->W) + 1) & ~1, t->W), y1 = std::min((std::min(wy + c, t->H) + 1) & ~1, t->H);
+    return x1 > x0 && y1 > y0;
+}
+
+// host -> device frame upload (pinned: direct async; pageable: staged through the handle's pinned buffer).
+// cfg.upload_window: only the search windows of the active targets travel (PCIe is the end-to-end roofline):
+// the fused crop kernel reads nothing else.  rect_mirror is exact whenever no frame is in flight.
+static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, bool allow_window = false) {
     size_t n = std::min(len, t->frame_bytes);
     t->frame_valid = (t->fmt == VT_FMT_NV12) ? (len >= (size_t)t->W * t->H * 3 / 2) : (len >= t->frame_bytes);
     if (!t->frame_valid && t->fmt == VT_FMT_NV12) n = 0;  // src/nv12_convert.rs:48-50 -> black image
     if (n == 0) return VT_OK;
+    const bool pinned = is_pinned(frame);
+    if (allow_window && t->cfg.upload_window && pinned && t->frame_valid && len >= t->frame_bytes && !t->active.empty() && (t->W % 2 == 0) &&
+        (t->H % 2 == 0 || t->fmt == VT_FMT_RGB24)) {
+        struct Win { int x0, y0, x1, y1; };
+        std::vector<Win> wins;
+        size_t bytes = 0;
+        const size_t bpp_num = t->fmt == VT_FMT_NV12 ? 3 : 6;  // bytes per pixel x 2
+        for (int s : t->active) {
+            Win w;
+            if (!search_window(t, t->rect_mirror[s], w.x0, w.y0, w.x1, w.y1)) continue;  // the crop kernel flags it; nothing to read
+            wins.push_back(w);
+            bytes += (size_t)(w.x1 - w.x0) * (w.y1 - w.y0) * bpp_num / 2;
+        }
+        if (bytes * 2 <= t->frame_bytes) {
+            for (const Win& w : wins) {
+                const size_t cols = (size_t)(w.x1 - w.x0), rows = (size_t)(w.y1 - w.y0);
+                if (t->fmt == VT_FMT_NV12) {
+                    const size_t W = (size_t)t->W, yo = (size_t)w.y0 * W + w.x0, uvo = W * t->H + (size_t)(w.y0 / 2) * W + w.x0;
+                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + yo, W, frame + yo, W, cols, rows, cudaMemcpyHostToDevice, t->stream));
+                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + uvo, W, frame + uvo, W, cols, rows / 2, cudaMemcpyHostToDevice, t->stream));
+                } else {
+                    const size_t pitch = (size_t)t->W * 3, o = (size_t)w.y0 * pitch + (size_t)w.x0 * 3;
+                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, pitch, frame + o, pitch, cols * 3, rows, cudaMemcpyHostToDevice, t->stream));
+                }
+            }
+            t->h2d_bytes += bytes;
+            return VT_OK;
+        }
+    }
     t->h2d_bytes += n;
-    if (is_pinned(frame)) {
+    if (pinned) {
         VT_CUDA(cudaMemcpyAsync(t->d_frame, frame, n, cudaMemcpyHostToDevice, t->stream));
     } else {
         memcpy(t->h_stage, frame, n);
@@ -531,7 +574,7 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
         if (t->frame_valid || t->fmt == VT_FMT_RGB24)
             VT_CUDA(cudaMemcpyAsync(t->d_frame, d_src, std::min(len, t->frame_bytes), cudaMemcpyDeviceToDevice, t->stream));
     } else {
-        vt_status st = upload_frame(t, frame, len);
+        vt_status st = upload_frame(t, frame, len, true);
         if (st != VT_OK) return st;
     }
     const double hp1 = t->hostprof ? now_us() : 0;
@@ -674,7 +717,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     t->W = cfg->width, t->H = cfg->height, t->fmt = cfg->format, t->maxT = cfg->max_targets;
     t->frame_bytes = cfg->format == VT_FMT_NV12 ? (size_t)t->W * t->H + (size_t)((t->H + 1) / 2) * t->W + (t->W & 1) : (size_t)t->W * t->H * 3;
     t->threshold = cfg->score_threshold > 0.f ? cfg->score_threshold : 0.20f;
-    t->debug_capture = cfg->reserved[0];
+    t->debug_capture = cfg->debug_capture;
     t->hostprof = getenv("VT_B200_HOSTPROF") != nullptr;
     auto fail = [&](vt_status st) {
         vt_tracker_destroy(t);
@@ -1077,7 +1120,7 @@ vt_status vt_tracker_debug_trace(vt_tracker* t, unsigned long long* out, int32_t
     return VT_OK;
 }
 
-// which: 0 embeddings, 1..depth block outputs (needs cfg.reserved[0] = 1)
+// which: 0 embeddings, 1..depth block outputs (needs cfg.debug_capture = 1)
 vt_status vt_tracker_debug_tokens(vt_tracker* t, int32_t target, int32_t which, float* out) {
     if (!t || !out || target < 0 || target >= t->maxT || !t->debug_capture || which < 0 || which > t->depth) return VT_ERR_INVALID;
     VT_CUDA(cudaSetDevice(t->cfg.device));
@@ -1312,6 +1355,10 @@ vt_status vt_overlay(vt_tracker* t, uint8_t* frame, size_t len, const vt_overlay
     return overlay_impl(t, frame, len, cmds, n, true);
 }
 vt_status vt_overlay_current(vt_tracker* t, uint8_t* frame, size_t len, const vt_overlay_cmd* cmds, int32_t n) {
+    if (t && t->cfg.upload_window) {
+        set_error("vt_overlay_current needs the whole frame on the device: create the handle with upload_window = 0");
+        return VT_ERR_INVALID;
+    }
     return overlay_impl(t, frame, len, cmds, n, false);
 }
 

@@ -74,7 +74,11 @@ typedef struct {
     int32_t box_overlay;         /* 1: update() also draws rect+crosshair for gated targets (device) and
                                        copies the touched rows back into the caller's frame */
     float overlay_gate;          /* gate for box_overlay: success && score > gate (0.25, src/tracker_context.rs:93) */
-    int32_t reserved[8];
+    int32_t debug_capture;       /* 1: keep per-block token copies for vt_tracker_debug_tokens (disables graph replay) */
+    int32_t upload_window;       /* 1: update()/submit() upload only the search windows of the active targets (2-D copies out of a
+                                       pinned frame; rect_last is mirrored on the host) instead of the whole frame.  The device copy
+                                       of the frame is then partial: vt_overlay_current needs upload_window = 0. */
+    int32_t reserved[6];
 } vt_config;
 
 typedef struct vt_tracker vt_tracker;
@@ -132,7 +136,7 @@ vt_status vt_tracker_debug_read(vt_tracker* t, int32_t target, float* search_blo
                                 float* conf_win, float* size_map, float* off_map, float* tokens);
 int32_t vt_tracker_model_dim(const vt_tracker* t, int32_t which); /* 0 D, 1 depth, 2 heads, 3 hidden, 4 head_ch */
 /* token features [320*D] after the embeddings (which = 0) or after block `which` (1..depth).  Needs
- * cfg.reserved[0] = 1 at create time (captures one copy per block; disables graph replay). */
+ * cfg.debug_capture = 1 at create time (captures one copy per block; disables graph replay). */
 vt_status vt_tracker_debug_tokens(vt_tracker* t, int32_t target, int32_t which, float* out);
 /* Device timeline of the tensor-core kernels launched since the previous call (set VT_B200_TRACE=1 in the environment before
  * vt_tracker_create; VT_ERR_INVALID otherwise): out[8 i ..] = {kernel id, t_entry, t_after_dependency_wait, t_end, 4 kernel-specific

@@ -501,3 +501,41 @@ def test_full_size_properties(api, oracle, weight_dir, cfg):
     for k, b in enumerate(boxes):
         trk.set_rect(tuple(b), target=k)
     assert trk.update_all(f2) == r1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt,cfg", [("nv12", "cfg1"), ("rgb24", "cfg3"), ("nv12", "mt")])
+def test_window_upload_equals_full_upload(api, weight_dir, fmt, cfg):
+    """cfg.upload_window: only the search windows travel over PCIe; results and the overlaid host frame are identical to the
+    whole-frame upload, frame after frame (free running, so the host mirror of rect_last is exercised), incl. borders / 16 targets."""
+    if cfg == "mt":
+        spec = synth.StreamSpec("mt", 1920, 1080, 1004, [(190 + (i % 4) * 450, 110 + (i // 4) * 250, 100, 75, 3 + i % 4, 2 + i // 4) for i in range(16)])
+    else:
+        spec = synth.CONFIGS[cfg]
+    st = synth.SyntheticStream(spec)
+    nt = len(spec.targets)
+    wpath = weights.ensure_weight_file("nano", weight_dir, variant="wild")
+    a = api.VitTrack.new(wpath, spec.width, spec.height, fmt=fmt, max_targets=nt, box_overlay=True, gemm_mode=1, upload_window=True)
+    b = api.VitTrack.new(wpath, spec.width, spec.height, fmt=fmt, max_targets=nt, box_overlay=True, gemm_mode=1, upload_window=False)
+    f0 = np.asarray(st.frame(0)).reshape(-1)
+    pa, pb = api.PinnedBuffer(f0.size), api.PinnedBuffer(f0.size)
+    pa.array[:] = f0
+    for k, box in enumerate(st.target_boxes(0)):
+        a.init(pa.array, api.BBox(*box), target=k)
+        b.init(pa.array, api.BBox(*box), target=k)
+    h2d0 = a.timing().h2d_bytes
+    for n in range(1, 9):
+        fr = np.asarray(st.frame(n)).reshape(-1)
+        pa.array[:] = fr
+        pb.array[:] = fr
+        ra, rb = a.update_all(pa.array), b.update_all(pb.array)
+        assert ra == rb, (n, ra, rb)
+        assert np.array_equal(pa.array, pb.array), n
+    if nt == 1:
+        assert a.timing().h2d_bytes - h2d0 < 0.5 * 8 * f0.size  # the window really is smaller than the frame
+    # a box pushed against / over the border still matches
+    a.set_rect((-20, -10, 90, 70))
+    b.set_rect((-20, -10, 90, 70))
+    pa.array[:] = f0
+    pb.array[:] = f0
+    assert a.update_all(pa.array) == b.update_all(pb.array)
