@@ -404,12 +404,13 @@ static bool search_window(const vt_tracker* t, const vt_bbox& r, int& x0, int& y
 // host -> device frame upload (pinned: direct async; pageable: staged through the handle's pinned buffer).
 // cfg.upload_window: only the search windows of the active targets travel (PCIe is the end-to-end roofline):
 // the fused crop kernel reads nothing else.  rect_mirror is exact whenever no frame is in flight.
-static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, bool allow_window = false) {
+static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, bool allow_window = false, bool device_src = false) {
     size_t n = std::min(len, t->frame_bytes);
     t->frame_valid = (t->fmt == VT_FMT_NV12) ? (len >= (size_t)t->W * t->H * 3 / 2) : (len >= t->frame_bytes);
     if (!t->frame_valid && t->fmt == VT_FMT_NV12) n = 0;  // src/nv12_convert.rs:48-50 -> black image
     if (n == 0) return VT_OK;
-    const bool pinned = is_pinned(frame);
+    const bool pinned = device_src || is_pinned(frame);
+    const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (allow_window && t->cfg.upload_window && pinned && t->frame_valid && len >= t->frame_bytes && !t->active.empty() && (t->W % 2 == 0) &&
         (t->H % 2 == 0 || t->fmt == VT_FMT_RGB24)) {
         struct Win { int x0, y0, x1, y1; };
@@ -427,20 +428,20 @@ static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, b
                 const size_t cols = (size_t)(w.x1 - w.x0), rows = (size_t)(w.y1 - w.y0);
                 if (t->fmt == VT_FMT_NV12) {
                     const size_t W = (size_t)t->W, yo = (size_t)w.y0 * W + w.x0, uvo = W * t->H + (size_t)(w.y0 / 2) * W + w.x0;
-                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + yo, W, frame + yo, W, cols, rows, cudaMemcpyHostToDevice, t->stream));
-                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + uvo, W, frame + uvo, W, cols, rows / 2, cudaMemcpyHostToDevice, t->stream));
+                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + yo, W, frame + yo, W, cols, rows, kind, t->stream));
+                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + uvo, W, frame + uvo, W, cols, rows / 2, kind, t->stream));
                 } else {
                     const size_t pitch = (size_t)t->W * 3, o = (size_t)w.y0 * pitch + (size_t)w.x0 * 3;
-                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, pitch, frame + o, pitch, cols * 3, rows, cudaMemcpyHostToDevice, t->stream));
+                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, pitch, frame + o, pitch, cols * 3, rows, kind, t->stream));
                 }
             }
-            t->h2d_bytes += bytes;
+            if (!device_src) t->h2d_bytes += bytes;
             return VT_OK;
         }
     }
-    t->h2d_bytes += n;
+    if (!device_src) t->h2d_bytes += n;
     if (pinned) {
-        VT_CUDA(cudaMemcpyAsync(t->d_frame, frame, n, cudaMemcpyHostToDevice, t->stream));
+        VT_CUDA(cudaMemcpyAsync(t->d_frame, frame, n, kind, t->stream));
     } else {
         memcpy(t->h_stage, frame, n);
         VT_CUDA(cudaMemcpyAsync(t->d_frame, t->h_stage, n, cudaMemcpyHostToDevice, t->stream));
@@ -569,10 +570,9 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     // zero-copy overlay mirror: only when the caller's frame is pinned (device-mapped under UVA)
     t->inflight_mirrored = t->cfg.box_overlay && frame && !d_src && len >= t->frame_bytes && is_pinned(frame);
     *t->h_frame_slot = t->inflight_mirrored ? frame : nullptr;
-    if (d_src) {
-        t->frame_valid = (t->fmt == VT_FMT_NV12) ? (len >= (size_t)t->W * t->H * 3 / 2) : (len >= t->frame_bytes);
-        if (t->frame_valid || t->fmt == VT_FMT_RGB24)
-            VT_CUDA(cudaMemcpyAsync(t->d_frame, d_src, std::min(len, t->frame_bytes), cudaMemcpyDeviceToDevice, t->stream));
+    if (d_src) {  // frame already in device memory: device->device copy of the same bytes (whole frame or the search windows)
+        vt_status st = upload_frame(t, d_src, len, true, true);
+        if (st != VT_OK) return st;
     } else {
         vt_status st = upload_frame(t, frame, len, true);
         if (st != VT_OK) return st;
