@@ -47,7 +47,9 @@ def parse_args():
     ap.add_argument("--gemm", default="tcgen05x3", choices=["fp32simt", "tcgen05x3", "tcgen05"],
                     help="precision/engine of the dense contractions (tcgen05x3 = bf16 split operands, the parity-safe default)")
     ap.add_argument("--streams-per-gpu", type=int, default=1)
-    ap.add_argument("--ring", type=int, default=128, help="distinct frames per stream (ring > L2)")
+    ap.add_argument("--ring", type=int, default=384,
+                    help="distinct frames per stream; the bytes the step actually touches (search windows, ~0.45 MB per frame) over the ring "
+                         "must exceed the 126 MB L2: 384 x 0.45 MB = 171 MB (1.19 GB of frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-upload", action="store_true",
                     help="e2e leg uploads the whole frame every step instead of the search windows of the active targets (cfg.upload_window)")
@@ -397,7 +399,8 @@ def run_b200(args):
             "config": {"workload": workload_name(args), "resolution": "1920x1080", "format": "NV12", "targets": 1, "model": args.model, "gemm": args.gemm,
                        "streams_per_gpu": S, "weights": "constructed random-init (SURVEY.md §8c)",
                        "h2d": "whole frame" if args.full_upload else "search windows of the active targets only (2-D copies out of the pinned frame)",
-                       "l2": f"inputs larger than L2: ring of {ring_n} distinct frames = {ring_n * fb0 / 1e6:.0f} MB per stream"},
+                       "l2": (f"inputs larger than L2: ring of {ring_n} distinct frames per stream = {ring_n * fb0 / 1e6:.0f} MB, of which the step reads "
+                              f"{ring_n * h2d_step / 1e6:.0f} MB (search windows)")},
             "e2e": {"value": frames_g / (ms_e2e_g * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
                     "p50_latency_ms": float(np.percentile(lat_all, 50)), "p99_latency_ms": float(np.percentile(lat_all, 99)),
                     "stages_ms": stage_e2e},
