@@ -11,7 +11,7 @@
 //              tcgen05.ld.x16 -> ex2(s * k - max * k) -> bf16 (hi, lo) split -> 2 x 16 B stores into the 128B-swizzled K-major
 //              P tile (double buffered); row max / row sum partials are combined through shared memory in a fixed order
 //   tcgen05    O[128 x 64] += P_chunk V_chunk -> TMEM columns 320..383, overlapped with the next chunk's softmax
-//   epilogue   O / sum -> bf16 (hi, lo) tile staged in shared memory -> TMA tile store into the proj GEMM's A operand.
+//   epilogue   O / sum -> bf16 (hi, lo) tile staged in shared memory -> coalesced 16-byte stores into the proj GEMM's A operand.
 // The P buffers alias the Q/K staging area once S is complete, which keeps the CTA at ~192 KB of shared memory.
 #include "tc_common.cuh"
 #include "vt_internal.h"
@@ -50,7 +50,8 @@ __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, %
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(kAttThreads, 1)
-attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, int heads, int* err, unsigned long long* trace) {
+attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int D,
+                    int heads, int* err, unsigned long long* trace) {
     const CUtensorMap &mQhi = mp.mQhi, &mQlo = mp.mQlo, &mKhi = mp.mKhi, &mKlo = mp.mKlo, &mVhi = mp.mVhi, &mVlo = mp.mVlo;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_qk, bar_v, bar_s, p_full[2], p_free[2], bar_o;
@@ -83,8 +84,8 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, int heads, int* 
     }
     if (ctrl) {
         if (lane == 0) {
-            tma_prefetch_desc(&mQhi), tma_prefetch_desc(&mKhi), tma_prefetch_desc(&mVhi), tma_prefetch_desc(&mp.mOhi);
-            if (P == 2) tma_prefetch_desc(&mQlo), tma_prefetch_desc(&mKlo), tma_prefetch_desc(&mVlo), tma_prefetch_desc(&mp.mOlo);
+            tma_prefetch_desc(&mQhi), tma_prefetch_desc(&mKhi), tma_prefetch_desc(&mVhi);
+            if (P == 2) tma_prefetch_desc(&mQlo), tma_prefetch_desc(&mKlo), tma_prefetch_desc(&mVlo);
         }
         tmem_alloc(&tmem_base_s, kTmemCols);
         tmem_relinquish();
@@ -212,8 +213,8 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, int heads, int* 
         softmax_bar_sync();
         sum = (red[0][row] + red[1][row]) + (red[2][row] + red[3][row]);
 
-        // ---- epilogue: O / sum -> bf16 (hi, lo) tile staged in (dead) shared memory, written with TMA tile stores into columns
-        // h*64.. of the proj GEMM's A operand [B][320][D]; query rows >= 320 are clipped by the TMA unit
+        // ---- epilogue: O / sum -> bf16 (hi, lo) tile staged in (dead) shared memory, copied with coalesced stores into columns
+        // h*64.. of the proj GEMM's A operand [B][320][D]; query rows >= 320 are skipped
         ok &= mbar_wait(&bar_o, 0);
         tcgen05_fence_after();
         {
@@ -230,15 +231,17 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, int heads, int* 
                 if (P == 2) *reinterpret_cast<uint4*>(smem + kPBytes + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
         }
-        fence_proxy_async_smem();
         softmax_bar_sync();
-        if (tid == 0) {
-            for (int k = 0; k < 2; ++k) {  // 64-row boxes (tc_out_map); rows >= 320 are clipped
-                tma_store_4d(&mp.mOhi, smem + k * 8192, h * kDh, q0 + 64 * k, 0, b);
-                if (P == 2) tma_store_4d(&mp.mOlo, smem + kPBytes + k * 8192, h * kDh, q0 + 64 * k, 0, b);
+        // staged [128][128 B] tiles -> att_hi / att_lo [B][320][D], columns h*64..: coalesced 16-byte stores, 4 rows per warp instruction
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = (tid >> 3) + 64 * i, ch = tid & 7;
+            if (q0 + r < kNTok) {
+                const int off = r * 128 + ((ch ^ (r & 7)) << 4);
+                const int64_t dst = (((int64_t)b * kNTok + q0 + r) * D + h * kDh) * 2 + ch * 16;
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out_hi) + dst) = *reinterpret_cast<const uint4*>(smem + off);
+                if (P == 2) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out_lo) + dst) = *reinterpret_cast<const uint4*>(smem + kPBytes + off);
             }
-            tma_store_commit();
-            tma_store_wait_read();
         }
     }
     if (!ok && err) atomicExch(err, 2);
@@ -253,7 +256,9 @@ bool tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* d
 bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const __nv_bfloat16* Qlo, const __nv_bfloat16* Khi, const __nv_bfloat16* Klo,
                             const __nv_bfloat16* Vthi, const __nv_bfloat16* Vtlo, int batch_heads, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int D,
                             int batch) {
-    bool ok = tc_out_map(&p->mOhi, out_hi, 2, D, kNTok, 1, batch) && tc_out_map(&p->mOlo, out_lo, 2, D, kNTok, 1, batch);
+    bool ok = true;
+    p->out_hi = out_hi, p->out_lo = out_lo, p->D = D;
+    (void)batch;
     {   // Q, K: [batch*heads][320][64], box {64, rows, 1}
         const uint64_t dims[3] = {kDh, kNTok, (uint64_t)batch_heads}, strides[2] = {kDh * 2, (uint64_t)kDh * 2 * kNTok};
         const uint32_t boxq[3] = {kDh, kQTile, 1}, boxk[3] = {kDh, kKeyChunk, 1};
@@ -277,8 +282,8 @@ cudaError_t tc_attention_setup() {
 cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int nsplit, int* err, cudaStream_t s, bool pdl, unsigned long long* trace) {
     if (B <= 0) return cudaSuccess;
     const dim3 grid((kNTok + kQTile - 1) / kQTile, heads, B);
-    if (nsplit == 3) return launch_ex(attention_tc_kernel<3>, grid, dim3(kAttThreads), AttSmem<3>::kTotal, s, pdl, 1, p, heads, err, trace);
-    return launch_ex(attention_tc_kernel<1>, grid, dim3(kAttThreads), AttSmem<1>::kTotal, s, pdl, 1, p, heads, err, trace);
+    if (nsplit == 3) return launch_ex(attention_tc_kernel<3>, grid, dim3(kAttThreads), AttSmem<3>::kTotal, s, pdl, 1, p, p.out_hi, p.out_lo, p.D, heads, err, trace);
+    return launch_ex(attention_tc_kernel<1>, grid, dim3(kAttThreads), AttSmem<1>::kTotal, s, pdl, 1, p, p.out_hi, p.out_lo, p.D, heads, err, trace);
 }
 
 }  // namespace vt

@@ -11,14 +11,14 @@
 //                              tcgen05.commit releases each stage and finally signals the accumulator;
 //   all 16 warps               epilogue: four threads per accumulator row (tcgen05.ld.x16: warp w reads lane quarter w % 4, columns
 //                              16 (w / 4) ..) -> bias / GELU / ReLU / pos-embed / residual -> the output tile is STAGED IN SHARED
-//                              MEMORY (128B-swizzled, conflict free) and written with TMA tile stores: a thread-per-row epilogue
-//                              that stores straight to global touches 32 different lines per warp instruction and was measured at
-//                              ~9 B/clk per SM (2 us per 32 KB tile); the tile store moves the same bytes in one instruction.
+//                              MEMORY (128B-swizzled, conflict free) and copied out by all 16 warps with fully coalesced 16-byte
+//                              stores (a warp instruction writes four 128-byte rows).  A thread-per-row epilogue that stores
+//                              straight from registers touches 32 lines per warp instruction (measured ~9 B/clk per SM, 2 us per
+//                              32 KB tile); TMA tile stores were measured at ~0.16 us per 8 KB box on the issuing SM.
 //                              Optionally LayerNorm of the full row through a cluster exchange (see below).
-// Output rows are addressed as (target, row-in-target) through 4-D tensor maps {cols, rows per target, heads, targets}: a 128-row
-// tile is written as two 64-row boxes (never straddling a target), rows past a target's end are clipped by the TMA unit; the same
-// mechanism scatters Q / K / V^T into the per-(target, head) layout of the attention kernel and drops the template rows of the
-// final LayerNorm.
+// Output rows are addressed as (target, row-in-target) of dense [targets][heads][rows][cols] tensors (TcOut): each 64-row half of a
+// tile stays inside one target, rows outside a target's range are skipped; the same mechanism scatters Q / K / V^T into the
+// per-(target, head) layout of the attention kernel and drops the template rows of the final LayerNorm.
 //
 // Precision: VT_GEMM_TCGEN05_BF16 issues A_hi*W_hi only; VT_GEMM_TCGEN05_BF16X3 adds A_hi*W_lo + A_lo*W_hi into the same
 // accumulator (error ~2^-17 relative per product), which is what the 1e-3 score / exact-box parity needs; the extra tensor
@@ -88,10 +88,13 @@ __device__ __forceinline__ void stage_split16(const float (&v)[16], uint8_t* til
     }
 }
 
-// One staged 128-row tile -> two 64-row TMA boxes.  Row m of the GEMM is row (m % period + row_off) of target
-// (m / period + batch_off); periods are multiples of 64, so a 64-row box never straddles two targets.  Rows past the end of a
-// target are clipped by the TMA unit; a box that would start at a negative row (the template rows the final LayerNorm drops) is
-// skipped — negative start coordinates are an illegal instruction for tile STORES (measured), unlike loads.
+// Staged tile -> global memory.  Row m of the GEMM is row (m % period + row_off) of target (m / period + batch_off) of a dense
+// [targets][heads][rows][cols] output (TcOut); periods are multiples of 64, so each 64-row half of a tile stays inside one target
+// and its (row, target) is computed once (TileRows).  Rows outside [0, rows) — the template rows the final LayerNorm drops, the
+// padding rows of the last tile — and targets >= batch are skipped.
+// The copy is done by all 512 threads with fully coalesced 16-byte stores: 8 lanes cover one 128-byte tile row, a warp instruction
+// writes 4 rows.  (Measured alternatives: thread-per-row stores straight from registers touch 32 lines per instruction and run at
+// ~9 B/clk/SM; TMA tile stores cost ~0.16 us per 8 KB box on the issuing SM, 2 us for the 96 KB partial tile of the chained GEMM.)
 constexpr int kHalfRows = 64, kHalfBytes = kHalfRows * 128;
 struct TileRows {  // (row-in-target, target) of the two 64-row halves of a tile; computed once, before the accumulator wait
     int t[2], b[2];
@@ -103,15 +106,31 @@ struct TileRows {  // (row-in-target, target) of the two 64-row halves of a tile
         }
     }
 };
-__device__ __forceinline__ void store_tile(const CUtensorMap* m, const uint8_t* smem_src, int c0, const TileRows& r, int row_off, int h) {
+// one [128 rows][128 B] 128B-swizzled tile; col_bytes = byte offset of the tile's first column inside a destination row
+__device__ __forceinline__ void tile_to_global(const uint8_t* tile, const TcOut& o, int64_t col_bytes, const TileRows& r, int row_off, int head,
+                                               int plane, int tid) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
-        if (r.t[k] + row_off >= 0) tma_store_4d(m, smem_src + k * kHalfBytes, c0, r.t[k] + row_off, h, r.b[k]);
+    for (int i = 0; i < 2; ++i) {
+        const int row = (tid >> 3) + 64 * i, ch = tid & 7;
+        const int tt = r.t[i] + (tid >> 3) + row_off, b = r.b[i];
+        if (tt >= 0 && tt < o.rows && b < o.batch) {
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 128 + ((ch ^ (row & 7)) << 4));
+            uint8_t* dst = o.base + (int64_t)plane * o.plane_bytes + (((int64_t)b * o.heads + head) * o.rows + tt) * o.row_bytes + col_bytes + ch * 16;
+            *reinterpret_cast<uint4*>(dst) = v;
+        }
+    }
 }
-// V^T: tokens are the innermost coordinate; staged as two [64 d][64 tokens] sub-tiles
-__device__ __forceinline__ void store_tile_vt(const CUtensorMap* m, const uint8_t* smem_src, const TileRows& r, int h) {
+// V^T: two unswizzled [64 d][64 tokens] sub-tiles -> [targets][heads][64 d][tokens]; the token range of sub-tile k is t[k]..t[k]+63
+__device__ __forceinline__ void vt_tile_to_global(const uint8_t* tile, const TcOut& o, const TileRows& r, int head, int tid) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) tma_store_4d(m, smem_src + k * kHalfBytes, r.t[k], 0, h, r.b[k]);
+    for (int i = 0; i < 2; ++i) {
+        const int d = tid >> 3, ch = tid & 7, b = r.b[i];
+        if (b < o.batch && r.t[i] + kHalfRows <= o.rows) {
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + i * kHalfBytes + d * 128 + ch * 16);
+            uint8_t* dst = o.base + (((int64_t)b * o.heads + head) * kTcBN + d) * o.row_bytes + (int64_t)r.t[i] * 2 + ch * 16;
+            *reinterpret_cast<uint4*>(dst) = v;
+        }
+    }
 }
 
 template <int NSPLIT>
@@ -153,15 +172,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             if (kLo) tma_load_2d(sb + kTileBBytes, &mp.Blo, &full_bar[kb], (kb0 + kb) * kTcBK, n0);
         }
         if (a.chain_n) {  // weight slice of the chained GEMM: W2[0..N2)[n0 .. n0 + 64), one box per precision part
-            tma_prefetch_desc(&mp.B2hi), tma_prefetch_desc(&mp.P);
+            tma_prefetch_desc(&mp.B2hi);
             mbar_arrive_expect_tx(&b2_bar, SM::kParts * a.chain_n * 128);
             tma_load_2d(smem + SM::kOffB2, &mp.B2hi, &b2_bar, n0, 0);
             if (kLo) tma_load_2d(smem + SM::kOffB2 + SM::kB2PartBytes, &mp.B2lo, &b2_bar, n0, 0);
         }
         if (a.residual) tma_prefetch_desc(&mp.R);
-        if (a.c_on) tma_prefetch_desc(&mp.C);
-        if (a.o_mode) tma_prefetch_desc(&mp.O[0]), tma_prefetch_desc(&mp.O[1]);
-        if (a.ln_g) tma_prefetch_desc(&mp.LnHi), tma_prefetch_desc(&mp.LnLo);
     }
     if (warp == 1) {
         tmem_alloc(&tmem_base_s, tmem_cols);  // 64 fp32 accumulator columns (+ N2 for a chained second GEMM)
@@ -310,37 +326,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             }
         }
     }
-    if (tid == 0 && !a.ln_g) tr.mark(5);
-    fence_proxy_async_smem();
-    if (tid == 0 && a.trace_id == 4) tr.mark(4);
+    if (a.o_mode == 3) fence_proxy_async_smem();  // the staged tile is read by the tensor core (async proxy) in the chained GEMM
     __syncthreads();
-    if (tid == 0 && a.trace_id == 2) tr.mark(4);
-    if (tid == 0) {
-        if (a.c_on && a.kb_per_split) {  // split-K partial: C map is {cols, rows per target, targets, splits}
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                tma_store_4d(&mp.C, sC + k * kHalfBytes, n0, tr_rows.t[k], tr_rows.b[k], blockIdx.z);
-                tma_store_4d(&mp.C, sC + kTileCBytes / 2 + k * kHalfBytes, n0 + 32, tr_rows.t[k], tr_rows.b[k], blockIdx.z);
-            }
-        } else if (a.c_on) {
-            store_tile(&mp.C, sC, n0, tr_rows, a.c_row_off, 0);
-            store_tile(&mp.C, sC + kTileCBytes / 2, n0 + 32, tr_rows, a.c_row_off, 0);
-        }
-        if (a.o_mode == 1) {
-            store_tile(&mp.O[0], smem + SM::kOffOhi, n0, tr_rows, a.o_row_off, 0);
-            if (kLo) store_tile(&mp.O[1], smem + SM::kOffOlo, n0, tr_rows, a.o_row_off, 0);
-        } else if (a.o_mode == 2) {  // Q / K: {64, 320, heads, B}; V^T: {320, 64, heads, B}
-            if (o_which < 2) {
-                store_tile(&mp.O[2 * o_which], smem + SM::kOffOhi, 0, tr_rows, 0, o_h);
-                if (kLo) store_tile(&mp.O[2 * o_which + 1], smem + SM::kOffOlo, 0, tr_rows, 0, o_h);
-            } else {
-                store_tile_vt(&mp.O[4], smem + SM::kOffOhi, tr_rows, o_h);
-                if (kLo) store_tile_vt(&mp.O[5], smem + SM::kOffOlo, tr_rows, o_h);
-            }
-        }
-        tma_store_commit();
-        tr.mark(7);
+    if (a.c_on) {  // split-K partials: plane = blockIdx.z
+        tile_to_global(sC, a.c, (int64_t)n0 * 4, tr_rows, a.c_row_off, 0, a.kb_per_split ? blockIdx.z : 0, tid);
+        tile_to_global(sC + kTileCBytes / 2, a.c, (int64_t)(n0 + 32) * 4, tr_rows, a.c_row_off, 0, a.kb_per_split ? blockIdx.z : 0, tid);
     }
+    if (a.o_mode == 1) {
+        tile_to_global(smem + SM::kOffOhi, a.o[0], (int64_t)n0 * 2, tr_rows, a.o_row_off, 0, 0, tid);
+        if (kLo) tile_to_global(smem + SM::kOffOlo, a.o[1], (int64_t)n0 * 2, tr_rows, a.o_row_off, 0, 0, tid);
+    } else if (a.o_mode == 2) {  // Q / K: [B][heads][320][64]; V^T: [B][heads][64][320]
+        if (o_which < 2) {
+            tile_to_global(smem + SM::kOffOhi, a.o[2 * o_which], 0, tr_rows, 0, o_h, 0, tid);
+            if (kLo) tile_to_global(smem + SM::kOffOlo, a.o[2 * o_which + 1], 0, tr_rows, 0, o_h, 0, tid);
+        } else {
+            vt_tile_to_global(smem + SM::kOffOhi, a.o[4], tr_rows, o_h, tid);
+            if (kLo) vt_tile_to_global(smem + SM::kOffOlo, a.o[5], tr_rows, o_h, tid);
+        }
+    }
+    if (tid == 0) tr.mark(7);
     if (a.chain_n) {
         // ---- chained GEMM: P_j[128, N2] = hidden tile (just staged as a 128B-swizzled K-major A operand, bf16 hi / lo) x
         // W2[:, n0 .. n0 + 64)^T.  The hidden activations never travel to global memory; the N / 64 partial results P_j of one row
@@ -377,16 +381,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4*>(prow + (((ch0 + q) ^ sw) << 4)) = make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
         }
-        fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0) tr.mark(4);
-        if (tid < N2 / 32) {  // one thread per 32-column box: two 64-row tile stores each into P[j = blockIdx.x][target][row][col]
-            const uint8_t* src = smem + SM::kOffP + tid * (kTcBM * 128);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) tma_store_4d(&mp.P, src + k * kHalfBytes, tid * 32, tr_rows.t[k], tr_rows.b[k], blockIdx.x);
-            tma_store_commit();
-            if (tid != 0) tma_store_wait_read();
-        }
+        for (int cb = 0; cb < N2 / 32; ++cb)  // P[j = blockIdx.x][target][row][32 cb ..]
+            tile_to_global(smem + SM::kOffP + cb * (kTcBM * 128), a.p, (int64_t)cb * 128, tr_rows, 0, 0, blockIdx.x, tid);
     }
     if (a.ln_g) {  // ---- fused LayerNorm over the full row (N columns = cluster of N / 64 CTAs x 4 column groups)
         const uint32_t nct = cluster_nctarank(), me = cluster_ctarank();
@@ -431,17 +429,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 16; ++j) y[j] = (v[j] - mean) * rstd * gam[j] + bet[j];
         stage_split16(y, smem + SM::kOffLnHi, smem + SM::kOffLnLo, row, g, kLo);
-        fence_proxy_async_smem();
         __syncthreads();
-        if (tid == 0) {
-            store_tile(&mp.LnHi, smem + SM::kOffLnHi, n0, tr_rows, a.ln_row_off, 0);
-            if (kLo) store_tile(&mp.LnLo, smem + SM::kOffLnLo, n0, tr_rows, a.ln_row_off, 0);
-            tma_store_commit();
-        }
+        tile_to_global(smem + SM::kOffLnHi, a.ln_out[0], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
+        if (kLo) tile_to_global(smem + SM::kOffLnLo, a.ln_out[1], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
     }
     if (!ok && a.err) atomicExch(a.err, 1);
-    if (tid == 0 && a.trace_id >= 100) tr.mark(5);  // diagnostics: stores issued -> completion
-    if (tid == 0) tma_store_wait_read();  // the tile stores have read shared memory: it may be released
     tcgen05_fence_before();
     __syncthreads();
     if (tid == 0) tr.mark(3);
@@ -496,19 +488,23 @@ bool tc_make_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
     return tc_make_map(out, base, 2, dims, strides, box);
 }
 
-// Output tile map: dense [batch][heads][rows][cols] tensor, one 64-row x (128-byte wide) box
-bool tc_out_map(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint64_t heads, uint64_t batch) {
-    const uint64_t dims[4] = {cols, rows, heads, batch};
-    const uint64_t strides[3] = {cols * elem_bytes, cols * rows * elem_bytes, cols * rows * heads * elem_bytes};
-    const uint32_t box[4] = {(uint32_t)(128 / elem_bytes), (uint32_t)kHalfRows, 1, 1};
-    return tc_make_map_ex(out, base, elem_bytes, 4, dims, strides, box, true);
+// dense [planes][batch][heads][rows][cols] output of elem_bytes-wide elements (planes: split-K / chained partials)
+TcOut tc_out(void* base, int elem_bytes, int64_t cols, int rows, int heads, int batch, int planes) {
+    (void)planes;
+    TcOut o;
+    o.base = static_cast<uint8_t*>(base);
+    o.row_bytes = cols * elem_bytes;
+    o.rows = rows, o.heads = heads, o.batch = batch;
+    o.plane_bytes = o.row_bytes * rows * heads * batch;
+    return o;
 }
-// V^T tile map: [batch][heads][64 d][rows = tokens], box {64 tokens, 64 d}, unswizzled
-bool tc_out_map_vt(CUtensorMap* out, const void* base, uint64_t tokens, uint64_t heads, uint64_t batch) {
-    const uint64_t dims[4] = {tokens, (uint64_t)kTcBN, heads, batch};
-    const uint64_t strides[3] = {tokens * 2, tokens * kTcBN * 2, tokens * kTcBN * heads * 2};
-    const uint32_t box[4] = {(uint32_t)kHalfRows, (uint32_t)kTcBN, 1, 1};
-    return tc_make_map_ex(out, base, 2, 4, dims, strides, box, false);
+// V^T output [batch][heads][64 d][tokens] bf16: rows = tokens (the range check), row_bytes = bytes of one d-row
+TcOut tc_out_vt(void* base, int tokens, int heads, int batch) {
+    TcOut o;
+    o.base = static_cast<uint8_t*>(base);
+    o.row_bytes = (int64_t)tokens * 2;
+    o.rows = tokens, o.heads = heads, o.batch = batch, o.plane_bytes = 0;
+    return o;
 }
 // flat [rows][cols] fp32 residual tile source (two 32-column boxes per 64-column tile)
 bool tc_resid_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols) {
@@ -527,7 +523,7 @@ bool tc_plan_chain(TcGemmPlan* p, const __nv_bfloat16* W2hi, const __nv_bfloat16
     const uint64_t dims[2] = {K2, (uint64_t)N2}, strides[1] = {K2 * 2};
     const uint32_t box[2] = {(uint32_t)kTcBK, (uint32_t)N2};
     bool ok = tc_make_map(&p->maps.B2hi, W2hi, 2, dims, strides, box) && tc_make_map(&p->maps.B2lo, W2lo ? W2lo : W2hi, 2, dims, strides, box);
-    ok = ok && tc_out_map(&p->maps.P, P, 4, N2, rows, batch, K2 / kTcBN);
+    p->args.p = tc_out(P, 4, N2, rows, 1, batch, K2 / kTcBN);
     p->args.chain_n = N2, p->args.o_mode = 3;
     return ok;
 }
@@ -553,8 +549,7 @@ bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* 
     ok &= tc_make_map_2d(&p->maps.Bhi, Whi, N, K, kTcBN);
     ok &= tc_make_map_2d(&p->maps.Blo, Wlo ? Wlo : Whi, N, K, kTcBN);
     // unused output maps must still be valid descriptors (they are never dereferenced when their mode is off)
-    p->maps.R = p->maps.C = p->maps.LnHi = p->maps.LnLo = p->maps.B2hi = p->maps.B2lo = p->maps.P = p->maps.Bhi;
-    for (auto& m : p->maps.O) m = p->maps.Bhi;
+    p->maps.R = p->maps.B2hi = p->maps.B2lo = p->maps.Bhi;
     p->args.N = N, p->args.K = K, p->args.conv_feat = conv_feat;
     p->args.pos_rows = 1, p->args.period = 1 << 30;
     return ok;
@@ -629,9 +624,9 @@ extern "C" vt_status vt_debug_gemm(int32_t device, int32_t M, int32_t N, int32_t
         const int period = per ? atoi(per) : 0;
         if (period > 0 && M % period == 0) {
             plan.args.period = period;
-            if (!tc_out_map(&plan.maps.C, dC, 4, N, period, 1, M / period)) st = VT_ERR_CUDA;
-        } else if (!tc_out_map(&plan.maps.C, dC, 4, N, M, 1, 1)) {
-            st = VT_ERR_CUDA;
+            plan.args.c = tc_out(dC, 4, N, period, 1, M / period, 1);
+        } else {
+            plan.args.c = tc_out(dC, 4, N, M, 1, 1, 1);
         }
         if (getenv("VT_DBG_RESID")) {
             plan.args.residual = 1;

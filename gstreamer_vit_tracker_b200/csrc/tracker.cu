@@ -833,32 +833,34 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         auto wlo = [&](const float* w) { return t->w_lo + (w - t->d_weights); };
         bool ok = true;
         const uint64_t rows = B * kNTok;
-        // output tile maps (tc_out_map: dense [targets][heads][rows][cols])
-        CUtensorMap mX, mXres, mLnHi, mLnLo, mYfHi, mYfLo, mHidHi, mHidLo, mH1, mZ, mQKV, mQ[6];
-        ok &= tc_out_map(&mX, t->X, 4, D, kNTok, 1, B) && tc_resid_map(&mXres, t->X, B * kNTok, D);
-        ok &= tc_out_map(&mLnHi, t->ln_hi, 2, D, kNTok, 1, B) && tc_out_map(&mLnLo, t->ln_lo, 2, D, kNTok, 1, B);
-        ok &= tc_out_map(&mYfHi, t->yf_hi, 2, D, kNTx, 1, B) && tc_out_map(&mYfLo, t->yf_lo, 2, D, kNTx, 1, B);
-        ok &= tc_out_map(&mHidHi, t->hid_hi, 2, Hd, kNTok, 1, B) && tc_out_map(&mHidLo, t->hid_lo, 2, Hd, kNTok, 1, B);
-        ok &= tc_out_map(&mH1, t->H1, 4, C, kNTx, 1, B) && tc_out_map(&mZ, t->Zemb, 4, D, kNTz, 1, B);
+        // outputs of the GEMM epilogues (TcOut: dense [planes][targets][heads][rows][cols]) and the flat residual TMA source
+        CUtensorMap mXres;
+        ok &= tc_resid_map(&mXres, t->X, B * kNTok, D);
+        const int Bi = (int)B, Di = (int)D;
+        const TcOut oX = tc_out(t->X, 4, Di, kNTok, 1, Bi, 1);
+        const TcOut oLn[2] = {tc_out(t->ln_hi, 2, Di, kNTok, 1, Bi, 1), tc_out(t->ln_lo, 2, Di, kNTok, 1, Bi, 1)};
+        const TcOut oYf[2] = {tc_out(t->yf_hi, 2, Di, kNTx, 1, Bi, 1), tc_out(t->yf_lo, 2, Di, kNTx, 1, Bi, 1)};
+        const TcOut oHid[2] = {tc_out(t->hid_hi, 2, (int)Hd, kNTok, 1, Bi, 1), tc_out(t->hid_lo, 2, (int)Hd, kNTok, 1, Bi, 1)};
+        const TcOut oH1 = tc_out(t->H1, 4, (int)C, kNTx, 1, Bi, 1), oZ = tc_out(t->Zemb, 4, Di, kNTz, 1, Bi, 1);
+        const TcOut oQKV = tc_out(t->QKV, 4, 3 * Di, kNTok, 1, Bi, 1);
+        TcOut oQ[6] = {};
         if (t->tc_attention) {
-            ok &= tc_out_map(&mQ[0], t->q_hi, 2, 64, kNTok, t->heads, B) && tc_out_map(&mQ[1], t->q_lo, 2, 64, kNTok, t->heads, B);
-            ok &= tc_out_map(&mQ[2], t->k_hi, 2, 64, kNTok, t->heads, B) && tc_out_map(&mQ[3], t->k_lo, 2, 64, kNTok, t->heads, B);
-            ok &= tc_out_map_vt(&mQ[4], t->vt_hi, kNTok, t->heads, B) && tc_out_map_vt(&mQ[5], t->vt_lo, kNTok, t->heads, B);
-        } else {
-            ok &= tc_out_map(&mQKV, t->QKV, 4, 3 * D, kNTok, 1, B);
+            oQ[0] = tc_out(t->q_hi, 2, 64, kNTok, t->heads, Bi, 1), oQ[1] = tc_out(t->q_lo, 2, 64, kNTok, t->heads, Bi, 1);
+            oQ[2] = tc_out(t->k_hi, 2, 64, kNTok, t->heads, Bi, 1), oQ[3] = tc_out(t->k_lo, 2, 64, kNTok, t->heads, Bi, 1);
+            oQ[4] = tc_out_vt(t->vt_hi, kNTok, t->heads, Bi), oQ[5] = tc_out_vt(t->vt_lo, kNTok, t->heads, Bi);
         }
         // patch embed (search): A = patches [B*256, 768] -> X rows 64.. of every target, + pos_x
         ok &= tc_plan_init(&t->plan_patch_x, t->px_hi, t->px_lo, B * kNTx, whi(t->patch_w), wlo(t->patch_w), (int)D, kPatchK, 0, 0);
         {
             TcGemmArgs& a = t->plan_patch_x.args;
             a.bias = t->patch_b, a.pos = t->pos_x, a.pos_rows = kNTx;
-            a.period = kNTx, a.c_on = 1, a.c_row_off = kNTz, t->plan_patch_x.maps.C = mX;
+            a.period = kNTx, a.c_on = 1, a.c_row_off = kNTz, a.c = oX;
             if (t->split_k) {  // 4 x K = 192 slices -> fp32 partials [4][B][256][D]; bias, pos, LN1 happen in reduce_ln_kernel
                 a.bias = nullptr, a.pos = nullptr, a.c_row_off = 0, a.kb_per_split = kPatchK / 64 / 4;
-                ok &= tc_out_map(&t->plan_patch_x.maps.C, t->Pbuf, 4, D, kNTx, B, 4);
+                a.c = tc_out(t->Pbuf, 4, Di, kNTx, 1, Bi, 4);
             } else if (t->fuse_ln) {  // LN1 of block 0 for the search rows, straight into the first QKV GEMM's A operand
                 a.ln_g = t->blk[0].ln1_g, a.ln_b = t->blk[0].ln1_b, a.ln_row_off = kNTz;
-                t->plan_patch_x.maps.LnHi = mLnHi, t->plan_patch_x.maps.LnLo = mLnLo;
+                a.ln_out[0] = oLn[0], a.ln_out[1] = oLn[1];
             }
         }
         // patch embed (template, at init): one 128-row tile whose rows 64.. are clipped; batch_off = the target slot, set per call
@@ -866,7 +868,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         {
             TcGemmArgs& a = t->plan_patch_z.args;
             a.bias = t->patch_b, a.pos = t->pos_z, a.pos_rows = kNTz;
-            a.period = 128, a.c_on = 1, t->plan_patch_z.maps.C = mZ;
+            a.period = 128, a.c_on = 1, a.c = oZ;
         }
         t->plans.resize(t->depth);
         for (int l = 0; l < t->depth && ok; ++l) {
@@ -876,37 +878,37 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             p.qkv.args.bias = b.qkv_b, p.qkv.args.period = kNTok;
             if (t->tc_attention) {
                 p.qkv.args.o_mode = 2;
-                for (int i = 0; i < 6; ++i) p.qkv.maps.O[i] = mQ[i];
+                for (int i = 0; i < 6; ++i) p.qkv.args.o[i] = oQ[i];
             } else {
-                p.qkv.args.c_on = 1, p.qkv.maps.C = mQKV;
+                p.qkv.args.c_on = 1, p.qkv.args.c = oQKV;
             }
             ok &= tc_plan_init(&p.proj, t->att_hi, t->att_lo, rows, whi(b.proj_w), wlo(b.proj_w), (int)D, (int)D, 0, 0);
             p.proj.args.bias = b.proj_b, p.proj.args.period = kNTok, p.proj.args.residual = 1, p.proj.args.c_on = 1;
-            p.proj.maps.R = mXres, p.proj.maps.C = mX;
-            if (t->fuse_ln) p.proj.args.ln_g = b.ln2_g, p.proj.args.ln_b = b.ln2_b, p.proj.maps.LnHi = mLnHi, p.proj.maps.LnLo = mLnLo;
+            p.proj.maps.R = mXres, p.proj.args.c = oX;
+            if (t->fuse_ln) p.proj.args.ln_g = b.ln2_g, p.proj.args.ln_b = b.ln2_b, p.proj.args.ln_out[0] = oLn[0], p.proj.args.ln_out[1] = oLn[1];
             ok &= tc_plan_init(&p.fc1, t->ln_hi, t->ln_lo, rows, whi(b.fc1_w), wlo(b.fc1_w), (int)Hd, (int)D, 0, 0);
             p.fc1.args.bias = b.fc1_b, p.fc1.args.gelu = 1, p.fc1.args.period = kNTok, p.fc1.args.o_mode = 1;
-            p.fc1.maps.O[0] = mHidHi, p.fc1.maps.O[1] = mHidLo;
+            p.fc1.args.o[0] = oHid[0], p.fc1.args.o[1] = oHid[1];
             if (t->chain_mlp) ok &= tc_plan_chain(&p.fc1, whi(b.fc2_w), wlo(b.fc2_w), (int)D, t->Pbuf, kNTok, B);
             ok &= tc_plan_init(&p.fc2, t->hid_hi, t->hid_lo, rows, whi(b.fc2_w), wlo(b.fc2_w), (int)D, (int)Hd, 0, 0);
             p.fc2.args.bias = b.fc2_b, p.fc2.args.period = kNTok, p.fc2.args.residual = 1, p.fc2.args.c_on = 1;
-            p.fc2.maps.R = mXres, p.fc2.maps.C = mX;
+            p.fc2.maps.R = mXres, p.fc2.args.c = oX;
             if (t->fuse_ln) {
                 TcGemmArgs& a = p.fc2.args;
                 if (l + 1 < t->depth) {
-                    a.ln_g = t->blk[l + 1].ln1_g, a.ln_b = t->blk[l + 1].ln1_b, p.fc2.maps.LnHi = mLnHi, p.fc2.maps.LnLo = mLnLo;
+                    a.ln_g = t->blk[l + 1].ln1_g, a.ln_b = t->blk[l + 1].ln1_b, a.ln_out[0] = oLn[0], a.ln_out[1] = oLn[1];
                 } else {  // final LN, search rows only -> the head conv's [B,16,16,D] grid (the template rows fall outside and are clipped)
-                    a.ln_g = t->lnf_g, a.ln_b = t->lnf_b, a.ln_row_off = -kNTz, p.fc2.maps.LnHi = mYfHi, p.fc2.maps.LnLo = mYfLo;
+                    a.ln_g = t->lnf_g, a.ln_b = t->lnf_b, a.ln_row_off = -kNTz, a.ln_out[0] = oYf[0], a.ln_out[1] = oYf[1];
                 }
             }
         }
         // 3x3 head conv: A gathered by TMA from the [B,16,16,D] final-LN grid (zero fill = zero padding), weights [C][tap][D]
         ok &= tc_plan_init(&t->plan_head, t->yf_hi, t->yf_lo, 0, whi(t->h1_w), wlo(t->h1_w), (int)C, (int)(9 * D), (int)D, (int)B);
         t->plan_head.args.bias = t->h1_b, t->plan_head.args.relu = 1, t->plan_head.args.period = kNTx, t->plan_head.args.c_on = 1;
-        t->plan_head.maps.C = mH1;
+        t->plan_head.args.c = oH1;
         if (t->split_k) {  // one tap per slice -> fp32 partials [9][B][256][C]; bias, ReLU, 1x1 conv and decode in head_decode_kernel
             t->plan_head.args.bias = nullptr, t->plan_head.args.relu = 0, t->plan_head.args.kb_per_split = (int)(D / 64);
-            ok &= tc_out_map(&t->plan_head.maps.C, t->Phead, 4, C, kNTx, B, 9);
+            t->plan_head.args.c = tc_out(t->Phead, 4, (int)C, kNTx, 1, Bi, 9);
         }
         if (!ok) return fail(VT_ERR_CUDA);
         for (TcGemmPlan* p : {&t->plan_patch_x, &t->plan_patch_z, &t->plan_head}) p->args.err = t->d_tc_err;

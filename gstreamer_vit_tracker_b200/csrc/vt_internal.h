@@ -209,6 +209,11 @@ cudaError_t launch_decode(const float* h1, int head_ch, const float* w2, const f
                           cudaStream_t s);
 
 // ---- tensor-core GEMM (gemm_tc.cu) ------------------------------------------------------------------
+struct TcOut {                // dense output [planes][batch][heads][rows][cols] the epilogue copies staged tiles into
+    uint8_t* base;
+    int64_t row_bytes, plane_bytes;
+    int rows, heads, batch;
+};
 struct TcGemmArgs {
     int M, N, K;
     int conv_feat;            // 0, or the feature dim D of the 3x3 head conv (A gathered from the [B,16,16,D] grid by TMA)
@@ -218,24 +223,25 @@ struct TcGemmArgs {
     int gelu, relu;
     int residual;             // add the fp32 tile read through maps.R (flat [rows][N], same rows as the tile) before storing
     // Output addressing: row m of the GEMM is (target m / period + batch_off, row-in-target m % period + <x>_row_off) of the
-    // 4-D output maps {cols, rows per target, heads, targets}; rows outside a target's range are clipped by the TMA unit.
+    // dense [targets][heads][rows][cols] outputs (TcOut); rows outside a target's range are skipped.
     int period, batch_off;
-    int c_on, c_row_off;      // fp32 tile -> maps.C
-    int o_mode;               // 0 off; 1 bf16 split tile -> maps.O[0] (hi), O[1] (lo); 2 QKV scatter -> O[0..5] = Q, K, V^T (hi, lo);
+    int c_on, c_row_off;      // fp32 tile -> c
+    TcOut c, o[6], ln_out[2], p;
+    int o_mode;               // 0 off; 1 bf16 split tile -> o[0] (hi), o[1] (lo); 2 QKV scatter -> o[0..5] = Q, K, V^T (hi, lo);
                               // 3 staged in shared memory only (A operand of the chained GEMM)
     int kb_per_split;         // split-K: 64-wide k-blocks per blockIdx.z slice (0 = no split); the fp32 partial tile of slice z goes to
-                              // maps.C = {cols, rows per target, targets, splits} and bias / activations / residual must be off
-    int chain_n;              // N2 of a chained second GEMM (0 = off): P[blockIdx.x] = tile x W2[:, n0..n0+64)^T -> maps.P
+                              // plane z of c and bias / activations / residual must be off
+    int chain_n;              // N2 of a chained second GEMM (0 = off): P[blockIdx.x] = tile x W2[:, n0..n0+64)^T -> p (plane blockIdx.x)
     int o_row_off;
-    // LayerNorm of the full output row fused into the epilogue (cluster of N / 64 CTAs): y = LN(row) * g + b -> maps.LnHi / LnLo
+    // LayerNorm of the full output row fused into the epilogue (cluster of N / 64 CTAs): y = LN(row) * g + b -> ln_out[0] (hi), ln_out[1] (lo)
     const float *ln_g, *ln_b; // null = off
     int ln_row_off;
     int* err;                 // set to 1 if a bounded mbarrier wait expired
     unsigned long long* trace; // device timeline buffer (diagnostics) or null
     int trace_id;
 };
-struct TcMaps {               // kernel parameter block (__grid_constant__): 17 descriptors
-    CUtensorMap Ahi, Alo, Bhi, Blo, R, C, O[6], LnHi, LnLo, B2hi, B2lo, P;
+struct TcMaps {               // kernel parameter block (__grid_constant__): the TMA load descriptors
+    CUtensorMap Ahi, Alo, Bhi, Blo, R, B2hi, B2lo;
 };
 struct TcGemmPlan {
     TcMaps maps;
@@ -244,15 +250,17 @@ struct TcGemmPlan {
 bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, uint64_t a_rows, const __nv_bfloat16* Whi,
                   const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch);
 bool tc_plan_chain(TcGemmPlan* p, const __nv_bfloat16* W2hi, const __nv_bfloat16* W2lo, int N2, float* P, uint64_t rows, uint64_t batch);
-// output tile maps over dense [batch][heads][rows][cols] tensors (elem_bytes 2 = bf16, 4 = fp32), V^T [batch][heads][64][tokens],
-// and the flat fp32 residual source
-bool tc_out_map(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint64_t heads, uint64_t batch);
-bool tc_out_map_vt(CUtensorMap* out, const void* base, uint64_t tokens, uint64_t heads, uint64_t batch);
+// dense outputs [planes][batch][heads][rows][cols] (elem_bytes 2 = bf16, 4 = fp32), V^T [batch][heads][64][tokens], and the flat fp32
+// residual source (TMA load)
+TcOut tc_out(void* base, int elem_bytes, int64_t cols, int rows, int heads, int batch, int planes);
+TcOut tc_out_vt(void* base, int tokens, int heads, int batch);
 bool tc_resid_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols);
 cudaError_t tc_gemm_setup();
 cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl);
 struct TcAttentionPlan {      // kernel parameter block (__grid_constant__)
-    CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo, mOhi, mOlo;
+    CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo;
+    __nv_bfloat16 *out_hi, *out_lo;  // [B][320][D]: the proj GEMM's A operand
+    int D;
 };
 bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const __nv_bfloat16* Qlo, const __nv_bfloat16* Khi, const __nv_bfloat16* Klo,
                             const __nv_bfloat16* Vthi, const __nv_bfloat16* Vtlo, int batch_heads, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int D,
