@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const int num_kb = a.kb_per_split ? a.kb_per_split : a.K / kTcBK;
     const int kb0 = blockIdx.z * num_kb;
     const int npre = num_kb < kTcStages ? num_kb : kTcStages;
-    const uint32_t tmem_cols = a.chain_n == 0 ? kTcBN : (a.chain_n <= 64 ? 128 : 256);
+    constexpr uint32_t kAcc1Cols = kLo ? 2 * kTcBN : kTcBN;  // bf16x3 keeps hi*lo in a second column half
+    const uint32_t tmem_cols = a.chain_n == 0 ? kAcc1Cols : (kAcc1Cols + a.chain_n <= 128 ? 128 : (kAcc1Cols + a.chain_n <= 256 ? 256 : 512));
     bool ok = true;
     TraceRec tr;
     tr.begin(&trace_slot, a.trace, a.trace_id);
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         if (a.residual) tma_prefetch_desc(&mp.R);
     }
     if (warp == 1) {
-        tmem_alloc(&tmem_base_s, tmem_cols);  // 64 fp32 accumulator columns (+ N2 for a chained second GEMM)
+        tmem_alloc(&tmem_base_s, tmem_cols);  // 64 (bf16x3: 128) fp32 accumulator columns (+ N2 for a chained second GEMM)
         tmem_relinquish();
     }
     tcgen05_fence_before();
@@ -225,7 +226,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer
-            constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, kTcBN);
+            // bf16x3: A_hi x [W_hi; W_lo] as ONE N = 128 UMMA (the two weight parts are adjacent 64-row tiles of the stage) into
+            // accumulator columns [0, 64) (hi*hi) and [64, 128) (hi*lo), then A_lo x W_hi (N = 64) into [0, 64); the epilogue adds the
+            // two halves.  UMMA issue is operand-fetch bound (~85 clk for 4 KB A + 2 KB B): 14 KB per K-step instead of 18 KB.
+            constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, kTcBN), idesc2n = umma_idesc_bf16(kTcBM, 2 * kTcBN);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kTcStages;
                 ok &= mbar_wait(&full_bar[s], (kb / kTcStages) & 1);
@@ -236,11 +240,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 for (int k = 0; k < kTcBK / 16; ++k) {
                     const uint32_t koff = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
                     const uint64_t dAhi = umma_desc_sw128(sa + koff), dBhi = umma_desc_sw128(sb + koff);
-                    umma_bf16(tmem, dAhi, dBhi, idesc, (kb | k) != 0);
                     if (kLo) {
-                        const uint64_t dAlo = umma_desc_sw128(sa + kTileABytes + koff), dBlo = umma_desc_sw128(sb + kTileBBytes + koff);
-                        umma_bf16(tmem, dAhi, dBlo, idesc, 1);
-                        umma_bf16(tmem, dAlo, dBhi, idesc, 1);
+                        umma_bf16(tmem, dAhi, dBhi, idesc2n, (kb | k) != 0);
+                        umma_bf16(tmem, umma_desc_sw128(sa + kTileABytes + koff), dBhi, idesc, 1);
+                    } else {
+                        umma_bf16(tmem, dAhi, dBhi, idesc, (kb | k) != 0);
                     }
                 }
                 umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
@@ -277,6 +281,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     if (tid == 0) tr.mark(6);
     float v[kTcColsPerThread];
     tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kTcColsPerThread, v);
+    if (kLo) {
+        float hl[kTcColsPerThread];
+        tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kTcBN + g * kTcColsPerThread, hl);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += hl[j];
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] += bias_v[j];
     if (a.gelu) {
@@ -358,10 +368,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             constexpr uint64_t kLoA = kTileOBytes >> 4, kLoB = SM::kB2PartBytes >> 4;
 #pragma unroll
             for (int k = 0; k < kTcBN / 16; ++k) {
-                umma_bf16(tmem + kTcBN, dA + 2 * k, dB + 2 * k, idesc2, k != 0);
+                umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + 2 * k, idesc2, k != 0);
                 if (kLo) {
-                    umma_bf16(tmem + kTcBN, dA + 2 * k, dB + kLoB + 2 * k, idesc2, 1);
-                    umma_bf16(tmem + kTcBN, dA + kLoA + 2 * k, dB + 2 * k, idesc2, 1);
+                    umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + kLoB + 2 * k, idesc2, 1);
+                    umma_bf16(tmem + kAcc1Cols, dA + kLoA + 2 * k, dB + 2 * k, idesc2, 1);
                 }
             }
             umma_commit(&accum2_bar);
@@ -374,7 +384,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         const int cols_per = N2 / kTcColGroups;
         for (int c = g * cols_per; c < (g + 1) * cols_per; c += 16) {
             float p[16];
-            tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kTcBN + c, p);
+            tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kAcc1Cols + c, p);
             uint8_t* prow = smem + SM::kOffP + (c >> 5) * (kTcBM * 128) + row * 128;
             const int ch0 = (c & 31) >> 2;
 #pragma unroll
