@@ -67,8 +67,8 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 
 // LayerNorm fused into the epilogue of the GEMMs that produce the residual stream (patch-embed, proj, FC2): the N / 64 CTAs
 // that hold the column tiles of one 128-row tile form a thread-block cluster; every thread computes the (sum, M2) of its 16
-// columns from registers, pushes the pair into every peer's shared memory (st.shared::cluster), and after one cluster barrier
-// combines the partials in a fixed order (Chan's parallel variance) — every CTA gets bit-identical statistics — normalises its
+// columns from registers, pushes the pair into every peer's shared memory with st.async (the store itself signals the peer's
+// mbarrier: no cluster barrier on the critical path), and every CTA combines the partials in a fixed order (Chan's parallel variance) — every CTA gets bit-identical statistics — normalises its
 // own columns and stages the bf16 (hi, lo) A operand of the next GEMM for a TMA tile store.
 constexpr int kMaxLnCluster = 8;
 constexpr int kTcThreads = 512;                         // 16 warps: warp w reads TMEM lane quarter w % 4, column group w / 4
@@ -136,7 +136,7 @@ __device__ __forceinline__ void vt_tile_to_global(const uint8_t* tile, const TcO
 template <int NSPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcGemmArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages], accum_bar, resid_bar, b2_bar, accum2_bar;
+    __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages], accum_bar, resid_bar, b2_bar, accum2_bar, ln_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float2 ln_part[kMaxLnCluster][kTcColGroups][kTcBM];
     __shared__ unsigned long long* trace_slot;
@@ -163,8 +163,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         tma_prefetch_desc(&mp.Ahi), tma_prefetch_desc(&mp.Bhi);
         if (kLo) tma_prefetch_desc(&mp.Alo), tma_prefetch_desc(&mp.Blo);
         for (int s = 0; s < kTcStages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
-        mbar_init(&accum_bar, 1), mbar_init(&resid_bar, 1), mbar_init(&b2_bar, 1), mbar_init(&accum2_bar, 1);
+        mbar_init(&accum_bar, 1), mbar_init(&resid_bar, 1), mbar_init(&b2_bar, 1), mbar_init(&accum2_bar, 1), mbar_init(&ln_bar, 1);
         fence_barrier_init();
+        // LayerNorm exchange: every thread of every CTA of the cluster (this one included) sends one float2 into ln_part of this CTA
+        if (a.ln_g && cluster_nctarank() > 1) mbar_arrive_expect_tx(&ln_bar, cluster_nctarank() * kTcThreads * (uint32_t)sizeof(float2));
         // the weights never depend on the preceding kernel: start streaming them right away
         for (int kb = 0; kb < npre; ++kb) {
             uint8_t* sb = smem + kb * SM::kStageBytes + SM::kParts * kTileABytes;
@@ -408,10 +410,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             const float d = v[j] - mu;
             m2 = fmaf(d, d, m2);
         }
-        const uint32_t mine = smem_u32(&ln_part[me][g][row]);
-        cluster_wait_acquire();  // every CTA of the cluster has started (arrive in the prologue)
-        for (uint32_t r = 0; r < nct; ++r) st_shared_cluster_f2(cluster_map_shared(mine, r), s, m2);
-        cluster_arrive_release();
+        const uint32_t mine = smem_u32(&ln_part[me][g][row]), bar = smem_u32(&ln_bar);
+        cluster_wait_acquire();  // every CTA of the cluster has started and initialised its ln_bar (arrive in the prologue)
+        if (nct > 1) {
+            for (uint32_t r = 0; r < nct; ++r) st_async_cluster_f2(cluster_map_shared(mine, r), s, m2, cluster_map_shared(bar, r));
+        } else {  // N = 64: the row lives in this CTA alone (launched without a cluster: st.async would be an illegal instruction)
+            ln_part[0][g][row] = make_float2(s, m2);
+        }
         float gam[16], bet[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -419,7 +424,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             gam[j] = g4.x, gam[j + 1] = g4.y, gam[j + 2] = g4.z, gam[j + 3] = g4.w;
             bet[j] = b4.x, bet[j + 1] = b4.y, bet[j + 2] = b4.z, bet[j + 3] = b4.w;
         }
-        cluster_wait_acquire();
+        // all partials of this CTA's rows have landed (complete_tx bytes); nobody exits before its own ln_part is complete, and a
+        // peer only completes after receiving ours, so no CTA of the cluster can disappear under an in-flight store
+        if (nct > 1) ok &= mbar_wait(&ln_bar, 0);
+        else __syncthreads();
         if (tid == 0) tr.mark(5);
         float tot = 0.f;
         for (uint32_t r = 0; r < nct; ++r)

@@ -105,6 +105,13 @@ __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t smem_addr, uint3
 __device__ __forceinline__ void st_shared_cluster_f2(uint32_t addr, float x, float y) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
 }
+// asynchronous store into a peer CTA's shared memory that signals the peer's mbarrier with the byte count (no cluster barrier needed:
+// the receiver waits for expect_tx bytes on its own mbarrier)
+__device__ __forceinline__ void st_async_cluster_f2(uint32_t remote_addr, float x, float y, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr), "f"(x), "f"(y),
+                 "r"(remote_mbar)
+                 : "memory");
+}
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
