@@ -94,7 +94,7 @@ def _ptr(a: np.ndarray) -> C.c_void_p:
 
 def make_config(weights: str, width: int, height: int, fmt: str = "nv12", max_targets: int = 1, device: int = 0,
                 use_cuda_graph: bool = True, box_overlay: bool = False, score_threshold: float = 0.20,
-                gemm_mode: int = L.VT_GEMM_FP32_SIMT, debug_capture: bool = False, upload_window: bool = False) -> vt_config:
+                gemm_mode: int = L.VT_GEMM_TCGEN05_BF16X3, debug_capture: bool = False, upload_window: bool = False) -> vt_config:
     cfg = vt_config()
     lib().vt_config_default(C.byref(cfg))
     cfg.weights_path = weights.encode()

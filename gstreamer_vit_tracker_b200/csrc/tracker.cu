@@ -649,7 +649,7 @@ void vt_config_default(vt_config* c) {
     c->width = 1920, c->height = 1080;  // src/pipeline.rs:26-27
     c->max_targets = 1;
     c->score_threshold = 0.20f;
-    c->gemm_mode = VT_GEMM_FP32_SIMT;
+    c->gemm_mode = VT_GEMM_TCGEN05_BF16X3;  // the parity-safe tensor-core path; VT_GEMM_FP32_SIMT is the numerically anchoring fallback
     c->use_cuda_graph = 1;
     c->box_overlay = 0;
     c->overlay_gate = 0.25f;  // src/tracker_context.rs:93,122

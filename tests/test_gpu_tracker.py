@@ -539,3 +539,43 @@ def test_window_upload_equals_full_upload(api, weight_dir, fmt, cfg):
     pa.array[:] = f0
     pb.array[:] = f0
     assert a.update_all(pa.array) == b.update_all(pb.array)
+
+
+@pytest.mark.gpu
+def test_bench_workload_teacher_forced_300_frames(api, oracle, weight_dir):
+    """The exact bench workload (cfg2, tiny, bf16x3, box overlay, window upload from a pinned frame) against the fp32 oracle over 300
+    teacher-forced frames: boxes equal except numerically undecidable floor ties, |dscore| <= 1e-3, overlay pixels as the oracle draws."""
+    spec = synth.CONFIGS["cfg2"]
+    W, H = spec.width, spec.height
+    wpath = weights.ensure_weight_file("tiny", weight_dir)
+    st = synth.SyntheticStream(spec)
+    trk = api.VitTrack.new(wpath, W, H, gemm_mode=1, box_overlay=True, upload_window=True)
+    ref = oracle.VitTrack(wpath, threads=16)
+    f0 = st.frame(0)
+    pin = api.PinnedBuffer(f0.size)
+    pin.array[:] = f0
+    box = st.target_boxes(0)[0]
+    trk.init(pin.array, api.BBox(*box))
+    ref.init(oracle.nv12_to_rgb(f0, W, H, 16), box)
+    stats = new_stats()
+    frames = 300
+    for n in range(frames):
+        fr = st.frame(n)
+        before = ref.rect
+        trk.set_rect(before)
+        pin.array[:] = fr
+        r = trk.update(pin.array)
+        rc, ok, score, bb = ref.update(oracle.nv12_to_rgb(fr, W, H, 16))
+        assert rc == 0
+        pre, margin = oracle_prefloor(ref, before)
+        compare_step(r, ok, score, bb, pre, margin, stats, ("tiny", "cfg2", n))
+        if n % 50 == 0 and r.success and r.score > 0.25:
+            want = fr.copy()
+            x, y, w, h = r.bbox
+            oracle.draw_rect_nv12(want, W, H, x, y, w, h, 3, 255)
+            oracle.draw_crosshair_nv12(want, W, H, x + w // 2, y + h // 2, 15, 255)
+            assert np.array_equal(pin.array, want), n
+    print(f"\n[parity bench workload] {frames} frames: exact {stats['exact']}, boundary(+-1px) {stats['boundary']}, ties {stats['ties']}, "
+          f"max|dscore| {stats['max_dscore']:.2e}, min IoU on boundary frames {stats['min_iou_boundary']:.4f}")
+    assert stats["exact"] >= 0.9 * frames
+    assert stats["max_dscore"] <= SCORE_TOL
