@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, Targ
                                                                size_t patches_stride, __nv_bfloat16* __restrict__ p_hi,
                                                                __nv_bfloat16* __restrict__ p_lo, unsigned long long* stamp) {
     if (stamp && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) *stamp = device_time_ns();
+    if (f.data_slot) f.data = *f.data_slot;
     const int bi = blockIdx.y;
     const int slot = slots[bi];
     TargetState* st = state + slot;
@@ -573,8 +574,10 @@ cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, 
 // device->host row copy and no second synchronisation is needed to hand the overlaid frame back.
 __global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t len, int W, int H, int fmt,
                                                           const DeviceResult* __restrict__ res, const int32_t* __restrict__ slots,
-                                                          float gate, uint8_t* const* host_slot, unsigned long long* stamp_end) {
+                                                          float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
+                                                          uint8_t* const* frame_slot) {
     __shared__ uint8_t* s_host;
+    if (frame_slot) frame = *frame_slot;
     if (threadIdx.x == 0) s_host = host_slot ? *reinterpret_cast<uint8_t* const volatile*>(host_slot) : nullptr;
     __syncthreads();
     const DeviceResult r = res[slots[blockIdx.x]];
@@ -601,15 +604,19 @@ __global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t
 
 cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
                                const int32_t* d_slots, int n, float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
-                               cudaStream_t s) {
+                               cudaStream_t s, uint8_t* const* frame_slot) {
     if (n <= 0) return cudaSuccess;
-    box_overlay_kernel<<<n, 256, 0, s>>>(d_frame, len, width, height, format, d_res, d_slots, gate, host_slot, stamp_end);
+    box_overlay_kernel<<<n, 256, 0, s>>>(d_frame, len, width, height, format, d_res, d_slots, gate, host_slot, stamp_end, frame_slot);
     return cudaGetLastError();
 }
 
-__global__ void stamp_kernel(unsigned long long* stamp) { *stamp = device_time_ns(); }
-cudaError_t launch_stamp(unsigned long long* stamp, cudaStream_t s) {
-    stamp_kernel<<<1, 1, 0, s>>>(stamp);
+// per-frame, outside the graph: submit stamp + the address of the frame this step reads (FrameDesc::data_slot)
+__global__ void stamp_kernel(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame) {
+    *stamp = device_time_ns();
+    if (frame_slot) *frame_slot = frame;
+}
+cudaError_t launch_stamp(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, cudaStream_t s) {
+    stamp_kernel<<<1, 1, 0, s>>>(stamp, frame_slot, frame);
     return cudaGetLastError();
 }
 

@@ -74,6 +74,7 @@ struct vt_tracker {
     size_t res_block_bytes = 0;
     unsigned long long *d_stamps = nullptr, *h_stamps = nullptr;
     int* h_tc_err = nullptr;
+    const uint8_t** d_frame_slot = nullptr;  // device cell: address of the frame the step reads (d_frame, or the caller's device frame)
     uint8_t** h_frame_slot = nullptr;  // pinned + device-mapped cell: address of the caller's pinned frame for the zero-copy overlay mirror
     bool inflight_mirrored = false;
     float* d_maps = nullptr;
@@ -240,7 +241,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     const int D = t->D, Hd = t->hidden, C = t->head_ch;
     (void)record_events, (void)capturing;  // stage times come from device stamps (ST_*), not from event nodes
     cudaStream_t s = t->stream;
-    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid};
+    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid, t->d_frame_slot};
     VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, n, 4, kSearch, t->d_lut, t->patches_x, (size_t)kNTx * kPatchK, t->px_hi,
                                       t->px_lo, s, t->d_stamps + ST_PRE));
     {
@@ -343,7 +344,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
         VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, t->d_stamps, s));
     if (t->cfg.box_overlay)
         VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, t->fmt, t->d_res, t->d_slots, n, t->cfg.overlay_gate,
-                                     t->h_frame_slot, t->d_stamps + ST_OVL_END, s));
+                                     t->h_frame_slot, t->d_stamps + ST_OVL_END, s, (uint8_t* const*)t->d_frame_slot));
     return VT_OK;
 }
 
@@ -565,13 +566,17 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     }
     const double hp0 = t->hostprof ? now_us() : 0;
     t->t_submit = std::chrono::steady_clock::now();
-    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->stream));
+    // device-resident frame: track (and draw the box) straight in the caller's device memory — no device->device copy
+    const bool in_place = d_src && len >= t->frame_bytes;
+    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_frame_slot, in_place ? d_src : t->d_frame, t->stream));
     ++t->kernel_launches;
     // zero-copy overlay mirror: only when the caller's frame is pinned (device-mapped under UVA)
     t->inflight_mirrored = t->cfg.box_overlay && frame && !d_src && len >= t->frame_bytes && is_pinned(frame);
     *t->h_frame_slot = t->inflight_mirrored ? frame : nullptr;
-    if (d_src) {  // frame already in device memory: device->device copy of the same bytes (whole frame or the search windows)
-        vt_status st = upload_frame(t, d_src, len, true, true);
+    if (in_place) {
+        t->frame_valid = 1;
+    } else if (d_src) {  // short device frame: device->device copy of what there is (NV12: black frame, src/nv12_convert.rs:48-50)
+        vt_status st = upload_frame(t, d_src, len, false, true);
         if (st != VT_OK) return st;
     } else {
         vt_status st = upload_frame(t, frame, len, true);
@@ -688,6 +693,7 @@ void vt_tracker_destroy(vt_tracker* t) {
     if (t->h_stage) cudaFreeHost(t->h_stage);
     if (t->h_res) cudaFreeHost(t->h_res);
     if (t->h_frame_slot) cudaFreeHost(t->h_frame_slot);
+    if (t->d_frame_slot) cudaFree(t->d_frame_slot);
     if (t->h_cmds) cudaFreeHost(t->h_cmds);
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;
@@ -766,6 +772,8 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     memset(t->h_res, 0, t->res_block_bytes);
     t->d_stamps = reinterpret_cast<unsigned long long*>(t->d_res + B), t->h_stamps = reinterpret_cast<unsigned long long*>(t->h_res + B);
     t->d_tc_err = reinterpret_cast<int*>(t->d_stamps + ST_COUNT), t->h_tc_err = reinterpret_cast<int*>(t->h_stamps + ST_COUNT);
+    VT_TRY(cudaMalloc(&t->d_frame_slot, sizeof(uint8_t*)));
+    VT_TRY(cudaMemcpy(t->d_frame_slot, &t->d_frame, sizeof(uint8_t*), cudaMemcpyHostToDevice));
     VT_TRY(cudaHostAlloc(&t->h_frame_slot, sizeof(uint8_t*), cudaHostAllocMapped));
     *t->h_frame_slot = nullptr;
     VT_TRY(cudaMalloc(&t->d_maps, sizeof(float) * 1280 * B));
@@ -966,7 +974,7 @@ vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, s
     VT_CUDA(cudaMemcpyAsync(t->d_state + target, &hs, sizeof(hs), cudaMemcpyHostToDevice, t->stream));
     // d_slots is reused as a one-element list for the template pass, then restored
     VT_CUDA(cudaMemcpyAsync(t->d_slots, &slot, sizeof(slot), cudaMemcpyHostToDevice, t->stream));
-    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid};
+    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid, nullptr};
     int launches = 0;
     VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, 1, 2, kTemplate, t->d_lut, t->patches_z, (size_t)kNTz * kPatchK, t->pz_hi,
                                       t->pz_lo, t->stream));
@@ -1024,7 +1032,7 @@ vt_status vt_tracker_update(vt_tracker* t, uint8_t* frame, size_t len, vt_result
     return wait_common(t, len, results);
 }
 
-vt_status vt_tracker_update_device(vt_tracker* t, const uint8_t* d_frame, size_t len, vt_result* results) {
+vt_status vt_tracker_update_device(vt_tracker* t, uint8_t* d_frame, size_t len, vt_result* results) {
     if (!t || !d_frame) return VT_ERR_INVALID;
     VT_CUDA(cudaSetDevice(t->cfg.device));
     vt_status st = submit_common(t, nullptr, d_frame, len);

@@ -111,7 +111,7 @@ __device__ __forceinline__ unsigned long long device_time_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
     return t;
 }
-cudaError_t launch_stamp(unsigned long long* stamp, cudaStream_t s);
+cudaError_t launch_stamp(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, cudaStream_t s);
 
 // ---- pixel kernels (pixel.cu) ------------------------------------------------------------------
 struct FrameDesc {
@@ -119,6 +119,10 @@ struct FrameDesc {
     int32_t width, height;
     int32_t format;        // vt_format
     int32_t valid;         // 0: buffer was short -> black image (src/nv12_convert.rs:48-50)
+    // When non-null the frame address is read from this device cell instead of `data`: the per-frame graph is captured once,
+    // while vt_tracker_update_device tracks straight out of the caller's device frame (no device->device copy) by letting the
+    // per-frame stamp kernel store the caller's pointer here.
+    const uint8_t* const* data_slot;
 };
 
 cudaError_t launch_nv12_to_rgb(const uint8_t* d_nv12, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int width, int height,
@@ -146,7 +150,7 @@ cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, 
 // device-side box overlay straight from the decode result (rect thickness 3 + crosshair 15, src/pipeline.rs:165-168)
 cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
                                const int32_t* d_slots, int n, float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
-                               cudaStream_t s);
+                               cudaStream_t s, uint8_t* const* frame_slot = nullptr);
 
 // ---- ViT kernels (vit.cu) ----------------------------------------------------------------------
 struct GemmArgs {

@@ -119,8 +119,10 @@ vt_status vt_tracker_update(vt_tracker* t, uint8_t* frame, size_t len, vt_result
 vt_status vt_tracker_submit(vt_tracker* t, uint8_t* frame, size_t len);
 vt_status vt_tracker_wait(vt_tracker* t, vt_result* results);
 
-/* Same as update() but the frame is already in device memory (bench `value` leg, NVDEC/NVMM producers). */
-vt_status vt_tracker_update_device(vt_tracker* t, const uint8_t* d_frame, size_t len, vt_result* results);
+/* Same as update() but the frame is already in device memory (bench `value` leg, NVDEC/NVMM producers): the tracker reads the
+ * caller's frame in place (no copy) and, with cfg.box_overlay, draws the box INTO it — the in-place semantics of the reference's
+ * probe (src/pipeline.rs:90-100,165-168) on a device surface. */
+vt_status vt_tracker_update_device(vt_tracker* t, uint8_t* d_frame, size_t len, vt_result* results);
 
 /* tracker state access (≙ rect_last inside VitTrack; used by tests for teacher forcing) */
 vt_status vt_tracker_get_rect(vt_tracker* t, int32_t target, vt_bbox* out);
