@@ -77,6 +77,7 @@ SYMBOLS = {
     "vt_tracker_init": (C.c_int32, [_vp, C.c_int32, _vp, C.c_size_t, vt_bbox]),
     "vt_tracker_update": (C.c_int32, [_vp, _vp, C.c_size_t, C.POINTER(vt_result)]),
     "vt_tracker_submit": (C.c_int32, [_vp, _vp, C.c_size_t]),
+    "vt_tracker_submit_device": (C.c_int32, [_vp, _vp, C.c_size_t]),
     "vt_tracker_wait": (C.c_int32, [_vp, C.POINTER(vt_result)]),
     "vt_tracker_update_device": (C.c_int32, [_vp, _vp, C.c_size_t, C.POINTER(vt_result)]),
     "vt_tracker_get_rect": (C.c_int32, [_vp, C.c_int32, C.POINTER(vt_bbox)]),

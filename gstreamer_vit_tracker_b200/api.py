@@ -163,6 +163,9 @@ class VitTrack:
         check(lib().vt_tracker_update(self._h, _ptr(frame), frame.size, self._res), "vt_tracker_update")
         return self._results()
 
+    def submit_device(self, d_ptr: int, nbytes: int) -> None:
+        check(lib().vt_tracker_submit_device(self._h, C.c_void_p(d_ptr), nbytes), "vt_tracker_submit_device")
+
     def submit(self, frame: np.ndarray) -> None:
         check(lib().vt_tracker_submit(self._h, _ptr(frame), frame.size), "vt_tracker_submit")
 

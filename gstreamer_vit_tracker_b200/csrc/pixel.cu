@@ -569,7 +569,7 @@ cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, 
 
 // Box overlay straight from the device-side decode result: one CTA per target,
 // rect (thickness 3) then crosshair (size 15) at the box centre ≙ src/pipeline.rs:165-168 / src/pipeline_ir.rs:192-195.
-// `host_slot` (nullable) points at a pinned, device-mapped cell holding the address of the caller's pinned frame (or null): the
+// `host_slot` (nullable) points at a device cell (set per frame by stamp_kernel) holding the address of the caller's pinned frame (or null): the
 // same pixels are then also written straight into the host frame (zero-copy stores over PCIe, ~3.4 K bytes), so no
 // device->host row copy and no second synchronisation is needed to hand the overlaid frame back.
 __global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t len, int W, int H, int fmt,
@@ -611,12 +611,14 @@ cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int heig
 }
 
 // per-frame, outside the graph: submit stamp + the address of the frame this step reads (FrameDesc::data_slot)
-__global__ void stamp_kernel(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame) {
+__global__ void stamp_kernel(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, uint8_t** host_slot, uint8_t* host_frame) {
     *stamp = device_time_ns();
     if (frame_slot) *frame_slot = frame;
+    if (host_slot) *host_slot = host_frame;
 }
-cudaError_t launch_stamp(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, cudaStream_t s) {
-    stamp_kernel<<<1, 1, 0, s>>>(stamp, frame_slot, frame);
+cudaError_t launch_stamp(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, uint8_t** host_slot, uint8_t* host_frame,
+                         cudaStream_t s) {
+    stamp_kernel<<<1, 1, 0, s>>>(stamp, frame_slot, frame, host_slot, host_frame);
     return cudaGetLastError();
 }
 

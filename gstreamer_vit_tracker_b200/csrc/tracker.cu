@@ -75,7 +75,7 @@ struct vt_tracker {
     unsigned long long *d_stamps = nullptr, *h_stamps = nullptr;
     int* h_tc_err = nullptr;
     const uint8_t** d_frame_slot = nullptr;  // device cell: address of the frame the step reads (d_frame, or the caller's device frame)
-    uint8_t** h_frame_slot = nullptr;  // pinned + device-mapped cell: address of the caller's pinned frame for the zero-copy overlay mirror
+    uint8_t** d_host_slot = nullptr;   // device cell: address of the caller's pinned host frame for the zero-copy overlay mirror (or null)
     bool inflight_mirrored = false;
     float* d_maps = nullptr;
     OverlayCmdDev *d_cmds = nullptr, *h_cmds = nullptr;
@@ -116,10 +116,20 @@ struct vt_tracker {
     int kernels_per_frame = 0;
     uint64_t kernel_launches = 0, frames = 0, h2d_bytes = 0, d2h_bytes = 0;
 
-    // in-flight frame
-    bool in_flight = false;
+    // in-flight frames: a queue of depth kQueue.  rect_last lives on the device, so frame t+1 can be enqueued before the results of
+    // frame t have been read back; every slot has its own pinned result block and completion event.
+    static constexpr int kQueue = 2;
+    struct Slot {
+        uint8_t* frame = nullptr;  // caller's host frame (null for device-resident frames)
+        size_t len = 0;
+        bool mirrored = false, pageable = false;
+        std::chrono::steady_clock::time_point t_submit;
+    } q[kQueue];
+    int q_head = 0, q_count = 0;
+    DeviceResult* h_blk[kQueue] = {nullptr, nullptr};
+    cudaEvent_t q_done[kQueue] = {nullptr, nullptr};
+    bool in_flight = false;          // q_count > 0
     uint8_t* inflight_frame = nullptr;
-    bool inflight_staged = false;
     std::chrono::steady_clock::time_point t_submit;
 
     // VT_B200_HOSTPROF=1: host-side wall time of the submit / wait phases, printed at destroy (diagnostics)
@@ -344,7 +354,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
         VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, t->d_stamps, s));
     if (t->cfg.box_overlay)
         VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, t->fmt, t->d_res, t->d_slots, n, t->cfg.overlay_gate,
-                                     t->h_frame_slot, t->d_stamps + ST_OVL_END, s, (uint8_t* const*)t->d_frame_slot));
+                                     t->d_host_slot, t->d_stamps + ST_OVL_END, s, (uint8_t* const*)t->d_frame_slot));
     return VT_OK;
 }
 
@@ -559,49 +569,70 @@ static inline double now_us() {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+static void bind_slot(vt_tracker* t, int slot) {
+    t->h_res = t->h_blk[slot];
+    t->h_stamps = reinterpret_cast<unsigned long long*>(t->h_res + t->maxT);
+    t->h_tc_err = reinterpret_cast<int*>(t->h_stamps + ST_COUNT);
+}
+
 static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_src, size_t len) {
-    if (t->in_flight) {
-        set_error("a frame is already in flight on this handle");
+    if (t->q_count >= vt_tracker::kQueue) {
+        set_error("%d frames are already in flight on this handle", t->q_count);
+        return VT_ERR_INVALID;
+    }
+    const bool pinned = d_src || is_pinned(frame);
+    if (t->q_count > 0 && (!pinned || t->q[t->q_head].pageable)) {
+        set_error("pageable host frames are staged through one buffer and cannot be pipelined: wait() first or use pinned frames");
         return VT_ERR_INVALID;
     }
     const double hp0 = t->hostprof ? now_us() : 0;
-    t->t_submit = std::chrono::steady_clock::now();
+    const int slot = (t->q_head + t->q_count) % vt_tracker::kQueue;
+    vt_tracker::Slot& q = t->q[slot];
+    q.t_submit = std::chrono::steady_clock::now();
+    q.frame = d_src ? nullptr : frame, q.len = len, q.pageable = !pinned;
+    // zero-copy overlay mirror: only when the caller's frame is pinned (device-mapped under UVA)
+    q.mirrored = t->cfg.box_overlay && frame && !d_src && len >= t->frame_bytes && pinned;
     // device-resident frame: track (and draw the box) straight in the caller's device memory — no device->device copy
     const bool in_place = d_src && len >= t->frame_bytes;
-    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_frame_slot, in_place ? d_src : t->d_frame, t->stream));
+    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_frame_slot, in_place ? d_src : t->d_frame, t->d_host_slot, q.mirrored ? frame : nullptr, t->stream));
     ++t->kernel_launches;
-    // zero-copy overlay mirror: only when the caller's frame is pinned (device-mapped under UVA)
-    t->inflight_mirrored = t->cfg.box_overlay && frame && !d_src && len >= t->frame_bytes && is_pinned(frame);
-    *t->h_frame_slot = t->inflight_mirrored ? frame : nullptr;
     if (in_place) {
         t->frame_valid = 1;
     } else if (d_src) {  // short device frame: device->device copy of what there is (NV12: black frame, src/nv12_convert.rs:48-50)
         vt_status st = upload_frame(t, d_src, len, false, true);
         if (st != VT_OK) return st;
     } else {
-        vt_status st = upload_frame(t, frame, len, true);
+        vt_status st = upload_frame(t, frame, len, t->q_count == 0);  // the host mirror of rect_last is exact only with an empty queue
         if (st != VT_OK) return st;
     }
     const double hp1 = t->hostprof ? now_us() : 0;
     vt_status st = run_forward(t);
     if (st != VT_OK) return st;
     const double hp2 = t->hostprof ? now_us() : 0;
-    VT_CUDA(cudaMemcpyAsync(t->h_res, t->d_res, t->res_block_bytes, cudaMemcpyDeviceToHost, t->stream));
+    VT_CUDA(cudaMemcpyAsync(t->h_blk[slot], t->d_res, t->res_block_bytes, cudaMemcpyDeviceToHost, t->stream));
+    VT_CUDA(cudaEventRecord(t->q_done[slot], t->stream));
     t->d2h_bytes += t->res_block_bytes;
     if (t->hostprof) t->hp[0] += hp1 - hp0, t->hp[1] += hp2 - hp1, t->hp[2] += now_us() - hp2;
+    ++t->q_count;
     t->in_flight = true;
-    t->inflight_frame = d_src ? nullptr : frame;
     return VT_OK;
 }
 
-static vt_status wait_common(vt_tracker* t, size_t len, vt_result* results) {
-    if (!t->in_flight) {
+static vt_status wait_common(vt_tracker* t, vt_result* results) {
+    if (t->q_count == 0) {
         set_error("no frame in flight");
         return VT_ERR_INVALID;
     }
-    t->in_flight = false;
+    const int slot = t->q_head;
+    const vt_tracker::Slot q = t->q[slot];
+    t->q_head = (t->q_head + 1) % vt_tracker::kQueue;
+    --t->q_count;
+    t->in_flight = t->q_count > 0;
+    t->t_submit = q.t_submit, t->inflight_frame = q.frame, t->inflight_mirrored = q.mirrored;
+    const size_t len = q.len;
     const double hp0 = t->hostprof ? now_us() : 0;
-    VT_CUDA(cudaStreamSynchronize(t->stream));
+    VT_CUDA(cudaEventSynchronize(t->q_done[slot]));
+    bind_slot(t, slot);
     const double hp1 = t->hostprof ? now_us() : 0;
     if (*t->h_tc_err) {  // travels with the results; reset on the device for the next frame
         cudaMemsetAsync(t->d_tc_err, 0, sizeof(int), t->stream);
@@ -617,7 +648,7 @@ static vt_status wait_common(vt_tracker* t, size_t len, vt_result* results) {
             const DeviceResult& d = t->h_res[sl];
             if (d.status == VT_OK && d.success && d.score > t->cfg.overlay_gate) t->d2h_bytes += 6ull * (size_t)(std::max(d.bbox[2], 0) + std::max(d.bbox[3], 0)) + 62;
         }
-    } else if (t->cfg.box_overlay && t->inflight_frame) {
+    } else if (t->cfg.box_overlay && t->inflight_frame) {  // pageable frame (never pipelined): copy the touched rows back
         std::vector<std::pair<int, int>> spans;
         box_rows(t, spans);
         merge_spans(spans);
@@ -691,8 +722,11 @@ void vt_tracker_destroy(vt_tracker* t) {
     for (void* p : dev)
         if (p) cudaFree(p);
     if (t->h_stage) cudaFreeHost(t->h_stage);
-    if (t->h_res) cudaFreeHost(t->h_res);
-    if (t->h_frame_slot) cudaFreeHost(t->h_frame_slot);
+    for (int i = 0; i < vt_tracker::kQueue; ++i) {
+        if (t->h_blk[i]) cudaFreeHost(t->h_blk[i]);
+        if (t->q_done[i]) cudaEventDestroy(t->q_done[i]);
+    }
+    if (t->d_host_slot) cudaFree(t->d_host_slot);
     if (t->d_frame_slot) cudaFree(t->d_frame_slot);
     if (t->h_cmds) cudaFreeHost(t->h_cmds);
     if (t->stream) cudaStreamDestroy(t->stream);
@@ -768,14 +802,18 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     t->res_block_bytes = sizeof(DeviceResult) * B + sizeof(unsigned long long) * ST_COUNT + 2 * sizeof(int);
     VT_TRY(cudaMalloc(&t->d_res, t->res_block_bytes));
     VT_TRY(cudaMemset(t->d_res, 0, t->res_block_bytes));
-    VT_TRY(cudaHostAlloc(&t->h_res, t->res_block_bytes, cudaHostAllocDefault));
-    memset(t->h_res, 0, t->res_block_bytes);
-    t->d_stamps = reinterpret_cast<unsigned long long*>(t->d_res + B), t->h_stamps = reinterpret_cast<unsigned long long*>(t->h_res + B);
-    t->d_tc_err = reinterpret_cast<int*>(t->d_stamps + ST_COUNT), t->h_tc_err = reinterpret_cast<int*>(t->h_stamps + ST_COUNT);
+    for (int i = 0; i < vt_tracker::kQueue; ++i) {
+        VT_TRY(cudaHostAlloc(&t->h_blk[i], t->res_block_bytes, cudaHostAllocDefault));
+        memset(t->h_blk[i], 0, t->res_block_bytes);
+        VT_TRY(cudaEventCreateWithFlags(&t->q_done[i], cudaEventDisableTiming));
+    }
+    t->d_stamps = reinterpret_cast<unsigned long long*>(t->d_res + B);
+    t->d_tc_err = reinterpret_cast<int*>(t->d_stamps + ST_COUNT);
+    bind_slot(t, 0);
     VT_TRY(cudaMalloc(&t->d_frame_slot, sizeof(uint8_t*)));
     VT_TRY(cudaMemcpy(t->d_frame_slot, &t->d_frame, sizeof(uint8_t*), cudaMemcpyHostToDevice));
-    VT_TRY(cudaHostAlloc(&t->h_frame_slot, sizeof(uint8_t*), cudaHostAllocMapped));
-    *t->h_frame_slot = nullptr;
+    VT_TRY(cudaMalloc(&t->d_host_slot, sizeof(uint8_t*)));
+    VT_TRY(cudaMemset(t->d_host_slot, 0, sizeof(uint8_t*)));
     VT_TRY(cudaMalloc(&t->d_maps, sizeof(float) * 1280 * B));
     VT_TRY(cudaMemset(t->d_maps, 0, sizeof(float) * 1280 * B));
     VT_TRY(cudaMalloc(&t->d_cmds, sizeof(OverlayCmdDev) * kMaxCmds));
@@ -1018,26 +1056,40 @@ vt_status vt_tracker_submit(vt_tracker* t, uint8_t* frame, size_t len) {
     return submit_common(t, frame, nullptr, len);
 }
 
+vt_status vt_tracker_submit_device(vt_tracker* t, uint8_t* d_frame, size_t len) {
+    if (!t || !d_frame) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    return submit_common(t, nullptr, d_frame, len);
+}
+
 vt_status vt_tracker_wait(vt_tracker* t, vt_result* results) {
     if (!t) return VT_ERR_INVALID;
     VT_CUDA(cudaSetDevice(t->cfg.device));
-    return wait_common(t, t->frame_bytes, results);
+    return wait_common(t, results);
 }
 
 vt_status vt_tracker_update(vt_tracker* t, uint8_t* frame, size_t len, vt_result* results) {
     if (!t || !frame) return VT_ERR_INVALID;
     VT_CUDA(cudaSetDevice(t->cfg.device));
+    if (t->q_count) {
+        set_error("vt_tracker_update: frames are in flight (submit/wait); drain them first");
+        return VT_ERR_INVALID;
+    }
     vt_status st = submit_common(t, frame, nullptr, len);
     if (st != VT_OK) return st;
-    return wait_common(t, len, results);
+    return wait_common(t, results);
 }
 
 vt_status vt_tracker_update_device(vt_tracker* t, uint8_t* d_frame, size_t len, vt_result* results) {
     if (!t || !d_frame) return VT_ERR_INVALID;
     VT_CUDA(cudaSetDevice(t->cfg.device));
+    if (t->q_count) {
+        set_error("vt_tracker_update_device: frames are in flight (submit/wait); drain them first");
+        return VT_ERR_INVALID;
+    }
     vt_status st = submit_common(t, nullptr, d_frame, len);
     if (st != VT_OK) return st;
-    return wait_common(t, len, results);
+    return wait_common(t, results);
 }
 
 vt_status vt_tracker_get_rect(vt_tracker* t, int32_t target, vt_bbox* out) {

@@ -111,7 +111,8 @@ __device__ __forceinline__ unsigned long long device_time_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
     return t;
 }
-cudaError_t launch_stamp(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, cudaStream_t s);
+cudaError_t launch_stamp(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, uint8_t** host_slot, uint8_t* host_frame,
+                         cudaStream_t s);
 
 // ---- pixel kernels (pixel.cu) ------------------------------------------------------------------
 struct FrameDesc {

@@ -113,10 +113,13 @@ vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, s
  * back into `frame` (≙ draw_rect_nv12 + draw_crosshair_nv12, src/pipeline.rs:165-168). */
 vt_status vt_tracker_update(vt_tracker* t, uint8_t* frame, size_t len, vt_result* results);
 
-/* Asynchronous pair used by the multi-stream driver: submit() enqueues upload + kernels on the
- * handle's CUDA stream and returns; wait() blocks until that frame's results are in host memory.
- * At most one frame may be in flight per handle. `frame` must stay valid until wait() returns. */
+/* Asynchronous pair: submit() enqueues upload + kernels on the handle's CUDA stream and returns; wait() blocks until the OLDEST
+ * submitted frame's results are in host memory.  Up to two frames may be in flight per handle (rect_last lives on the device, so
+ * frame t+1 can be enqueued before the result of frame t has been read): this hides the host round trip between frames.
+ * `frame` must stay valid until its wait() returns.  Pageable (non-pinned) host frames cannot be pipelined (one staging buffer);
+ * with cfg.upload_window a frame submitted while another is in flight is uploaded whole (the host mirror of rect_last lags). */
 vt_status vt_tracker_submit(vt_tracker* t, uint8_t* frame, size_t len);
+vt_status vt_tracker_submit_device(vt_tracker* t, uint8_t* d_frame, size_t len);  /* frame already in device memory, tracked in place */
 vt_status vt_tracker_wait(vt_tracker* t, vt_result* results);
 
 /* Same as update() but the frame is already in device memory (bench `value` leg, NVDEC/NVMM producers): the tracker reads the

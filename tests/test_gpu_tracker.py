@@ -579,3 +579,65 @@ def test_bench_workload_teacher_forced_300_frames(api, oracle, weight_dir):
           f"max|dscore| {stats['max_dscore']:.2e}, min IoU on boundary frames {stats['min_iou_boundary']:.4f}")
     assert stats["exact"] >= 0.9 * frames
     assert stats["max_dscore"] <= SCORE_TOL
+
+
+@pytest.mark.gpu
+def test_pipelined_submit_wait_depth_two(api, weight_dir):
+    """Two frames in flight per handle (rect_last lives on the device): results, overlay pixels and final state equal the synchronous
+    call sequence; a third submit, a pipelined pageable frame and update() with frames in flight are refused."""
+    import torch
+
+    spec = synth.CONFIGS["cfg1"]
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir, variant="wild")
+    a = api.VitTrack.new(wpath, spec.width, spec.height, box_overlay=True, upload_window=True)
+    b = api.VitTrack.new(wpath, spec.width, spec.height, box_overlay=True, upload_window=True)
+    c = api.VitTrack.new(wpath, spec.width, spec.height, box_overlay=True)
+    box = api.BBox(*st.target_boxes(0)[0])
+    n = 10
+    frames = [st.frame(i) for i in range(n)]
+    pins = [api.PinnedBuffer(frames[0].size) for _ in range(n)]
+    sync_frames = []
+    for t in (a, b, c):
+        t.init(frames[0], box)
+    want = []
+    for i in range(n):
+        p = api.PinnedBuffer(frames[0].size)
+        p.array[:] = frames[i]
+        want.append(a.update(p.array))
+        sync_frames.append(p.array.copy())
+    # host frames, pipelined
+    for i in range(n):
+        pins[i].array[:] = frames[i]
+    got = []
+    b.submit(pins[0].array)
+    for i in range(1, n):
+        b.submit(pins[i].array)
+        got.append(b.wait()[0])
+    with pytest.raises(api.VtError):
+        b.update(pins[0].array)          # a frame is still in flight
+    got.append(b.wait()[0])
+    assert got == want
+    for i in range(n):
+        assert np.array_equal(pins[i].array, sync_frames[i]), i
+    # device frames, pipelined, tracked in place
+    dev = [torch.from_numpy(frames[i]).cuda() for i in range(n)]
+    torch.cuda.synchronize()
+    got = []
+    c.submit_device(dev[0].data_ptr(), frames[0].size)
+    c.submit_device(dev[1].data_ptr(), frames[0].size)
+    with pytest.raises(api.VtError):
+        c.submit_device(dev[2].data_ptr(), frames[0].size)   # queue depth is two
+    got.append(c.wait()[0])
+    for i in range(2, n):
+        c.submit_device(dev[i].data_ptr(), frames[0].size)
+        got.append(c.wait()[0])
+    got.append(c.wait()[0])
+    assert got == want
+    for i in range(n):
+        assert np.array_equal(dev[i].cpu().numpy(), sync_frames[i]), i   # the box was drawn into the caller's device frame
+    # pageable frames cannot be pipelined
+    c.submit_device(dev[0].data_ptr(), frames[0].size)
+    with pytest.raises(api.VtError):
+        c.submit(frames[1].copy())
+    c.wait()
