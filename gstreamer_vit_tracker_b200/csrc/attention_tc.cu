@@ -10,7 +10,8 @@
 //              bounds this kernel, so it is spread over 16 warps.  Per 64-key chunk thread (row, g) owns 16 keys:
 //              tcgen05.ld.x16 -> ex2(s * k - max * k) -> bf16 (hi, lo) split -> 2 x 16 B stores into the 128B-swizzled K-major
 //              P tile (double buffered); row max / row sum partials are combined through shared memory in a fixed order
-//   tcgen05    O[128 x 64] += P_chunk V_chunk -> TMEM columns 320..383, overlapped with the next chunk's softmax
+//   tcgen05    O[128 x 64] += P_chunk V_chunk -> TMEM columns 320..383 (+ 384..447 for the hi*lo term), overlapped with the next
+//              chunk's softmax
 //   epilogue   O / sum -> bf16 (hi, lo) tile staged in shared memory -> coalesced 16-byte stores into the proj GEMM's A operand.
 // The P buffers alias the Q/K staging area once S is complete, which keeps the CTA at ~192 KB of shared memory.
 #include "tc_common.cuh"
@@ -110,9 +111,9 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
                 if (P == 2) tma_load_3d(sK + kKBytes + c * kKeyChunk * 128, &mKlo, &bar_qk, 0, c * kKeyChunk, bh);
             }
             mbar_arrive_expect_tx(&bar_v, P * kVBytes);
-            for (int c = 0; c < kNChunks; ++c) {
-                tma_load_3d(sV + c * (kDh * 128), &mVhi, &bar_v, c * kKeyChunk, 0, bh);
-                if (P == 2) tma_load_3d(sV + kVBytes + c * (kDh * 128), &mVlo, &bar_v, c * kKeyChunk, 0, bh);
+            for (int c = 0; c < kNChunks; ++c) {  // per key chunk: [V^T hi 64 x 128 B][V^T lo 64 x 128 B], adjacent = one N = 128 B operand
+                tma_load_3d(sV + c * (P * kDh * 128), &mVhi, &bar_v, c * kKeyChunk, 0, bh);
+                if (P == 2) tma_load_3d(sV + c * (P * kDh * 128) + kDh * 128, &mVlo, &bar_v, c * kKeyChunk, 0, bh);
             }
             // ---- S = Q K^T
             ok &= mbar_wait(&bar_qk, 0);
@@ -135,8 +136,10 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
             umma_commit(&bar_s);
             // ---- O += P_c V_c as the softmax warps hand the chunks over
             const uint64_t dP = umma_desc_sw128(smem_u32(sP)), dV = umma_desc_sw128(smem_u32(sV));
-            constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kDh);
-            constexpr uint64_t kLoP = kPBytes >> 4, kLoV = kVBytes >> 4, kBufP = (uint64_t)(P * kPBytes) >> 4, kBlkV = (kDh * 128) >> 4;
+            // bf16x3 as P_hi x [V_hi; V_lo] (ONE N = 128 UMMA into O columns [0, 64) = hi*hi and [64, 128) = hi*lo) + P_lo x V_hi: the
+            // small-N UMMA is operand-fetch bound, 14 KB instead of 18 KB per K-step; the epilogue adds the two column halves
+            constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kDh), idesc2n = umma_idesc_bf16(kQTile, 2 * kDh);
+            constexpr uint64_t kLoP = kPBytes >> 4, kBufP = (uint64_t)(P * kPBytes) >> 4, kBlkV = (uint64_t)(P * kDh * 128) >> 4;
             ok &= mbar_wait(&bar_v, 0);
             for (int c = 0; c < kNChunks; ++c) {
                 const int buf = c & 1;
@@ -145,10 +148,11 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
 #pragma unroll
                 for (int k = 0; k < kKeyChunk / 16; ++k) {
                     const uint64_t ph = dP + buf * kBufP + 2 * k, vh = dV + c * kBlkV + 2 * k;
-                    umma_bf16(tmem + kColO, ph, vh, idesc, (c | k) != 0);
                     if (NSPLIT == 3) {
-                        umma_bf16(tmem + kColO, ph, vh + kLoV, idesc, 1);
+                        umma_bf16(tmem + kColO, ph, vh, idesc2n, (c | k) != 0);
                         umma_bf16(tmem + kColO, ph + kLoP, vh, idesc, 1);
+                    } else {
+                        umma_bf16(tmem + kColO, ph, vh, idesc, (c | k) != 0);
                     }
                 }
                 umma_commit(&p_free[buf]);
@@ -221,6 +225,12 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
             const float inv = q_ok ? 1.f / sum : 0.f;
             float v[16];
             tmem_ld_32x16(lane_addr + kColO + g * 16, v);
+            if (NSPLIT == 3) {
+                float hl[16];
+                tmem_ld_32x16(lane_addr + kColO + kDh + g * 16, hl);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += hl[j];
+            }
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) split2_bf16(v[j] * inv, v[j + 1] * inv, hi[j >> 1], lo[j >> 1]);
