@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("VT_B200_TRACE", "1")
 from gstreamer_vit_tracker_b200 import api, synth, weights  # noqa: E402
 
-NAMES = {102: "qkv2x", 104: "fc1-2x", 1: "patch", 2: "qkv", 3: "proj", 4: "fc1", 5: "fc2", 6: "head", 10: "attn"}
+NAMES = {1: "patch", 2: "qkv", 3: "proj", 4: "fc1", 5: "fc2", 6: "head", 10: "attn"}
 
 
 def main():
@@ -47,7 +47,7 @@ def main():
     agg = {}
     print(f"{'kernel':8s} {'entry':>8s} {'prolog':>7s} {'body':>7s} {'gap':>7s} | marks 4..7 relative to the dependency wait"
           f"   (us; vit stage {tm.vit_ms * 1e3:.1f} us, total {tm.total_ms * 1e3:.1f} us)")
-    print("  gemm: m6 accumulator ready, m4 values final, m7 main stores issued, m5 LN exchange complete; attn: m4 S ready, m5 row max done, m6 chunk 0 handed to the MMA, m7 chunk 4 handed over")
+    print("  gemm: m6 accumulator ready, m4 values final (FC1: partial tile staged), m7 main copies issued, m5 LN exchange complete (FC1: chained accumulator ready); attn: m4 S ready, m5 row max done, m6 chunk 0 handed to the MMA, m7 chunk 4 handed over")
     for kid, te, tw, tend, m4, m5, m6, m7 in rec:
         name = NAMES.get(int(kid), str(kid))
         gap = (tw - prev_end) / 1e3 if prev_end is not None else 0.0
