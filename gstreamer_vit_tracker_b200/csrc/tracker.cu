@@ -61,6 +61,9 @@ struct vt_tracker {
 
     // frame + state
     uint8_t* d_frame = nullptr;
+    uint8_t* d_frames[2] = {nullptr, nullptr};  // double buffer: d_frame points at the one most recently filled (queue slot s uses [s])
+    cudaStream_t copy_stream = nullptr;          // uploads of pipelined host frames overlap the in-flight frame's kernels
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};
     uint8_t* d_rgb = nullptr;  // lazily allocated, vt_convert_nv12_rgb
     uint8_t *d_fmt_in = nullptr, *d_fmt_out = nullptr;  // lazily grown scratch of the format entry points (YUY2, resize)
     size_t fmt_in_cap = 0, fmt_out_cap = 0;
@@ -415,7 +418,9 @@ static bool search_window(const vt_tracker* t, const vt_bbox& r, int& x0, int& y
 // host -> device frame upload (pinned: direct async; pageable: staged through the handle's pinned buffer).
 // cfg.upload_window: only the search windows of the active targets travel (PCIe is the end-to-end roofline):
 // the fused crop kernel reads nothing else.  rect_mirror is exact whenever no frame is in flight.
-static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, bool allow_window = false, bool device_src = false) {
+static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, bool allow_window = false, bool device_src = false,
+                              cudaStream_t stream = nullptr) {
+    if (!stream) stream = t->stream;
     size_t n = std::min(len, t->frame_bytes);
     t->frame_valid = (t->fmt == VT_FMT_NV12) ? (len >= (size_t)t->W * t->H * 3 / 2) : (len >= t->frame_bytes);
     if (!t->frame_valid && t->fmt == VT_FMT_NV12) n = 0;  // src/nv12_convert.rs:48-50 -> black image
@@ -439,11 +444,11 @@ static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, b
                 const size_t cols = (size_t)(w.x1 - w.x0), rows = (size_t)(w.y1 - w.y0);
                 if (t->fmt == VT_FMT_NV12) {
                     const size_t W = (size_t)t->W, yo = (size_t)w.y0 * W + w.x0, uvo = W * t->H + (size_t)(w.y0 / 2) * W + w.x0;
-                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + yo, W, frame + yo, W, cols, rows, kind, t->stream));
-                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + uvo, W, frame + uvo, W, cols, rows / 2, kind, t->stream));
+                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + yo, W, frame + yo, W, cols, rows, kind, stream));
+                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + uvo, W, frame + uvo, W, cols, rows / 2, kind, stream));
                 } else {
                     const size_t pitch = (size_t)t->W * 3, o = (size_t)w.y0 * pitch + (size_t)w.x0 * 3;
-                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, pitch, frame + o, pitch, cols * 3, rows, kind, t->stream));
+                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, pitch, frame + o, pitch, cols * 3, rows, kind, stream));
                 }
             }
             if (!device_src) t->h2d_bytes += bytes;
@@ -452,10 +457,10 @@ static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, b
     }
     if (!device_src) t->h2d_bytes += n;
     if (pinned) {
-        VT_CUDA(cudaMemcpyAsync(t->d_frame, frame, n, kind, t->stream));
+        VT_CUDA(cudaMemcpyAsync(t->d_frame, frame, n, kind, stream));
     } else {
         memcpy(t->h_stage, frame, n);
-        VT_CUDA(cudaMemcpyAsync(t->d_frame, t->h_stage, n, cudaMemcpyHostToDevice, t->stream));
+        VT_CUDA(cudaMemcpyAsync(t->d_frame, t->h_stage, n, cudaMemcpyHostToDevice, stream));
     }
     return VT_OK;
 }
@@ -594,6 +599,15 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     q.mirrored = t->cfg.box_overlay && frame && !d_src && len >= t->frame_bytes && pinned;
     // device-resident frame: track (and draw the box) straight in the caller's device memory — no device->device copy
     const bool in_place = d_src && len >= t->frame_bytes;
+    if (!in_place) t->d_frame = t->d_frames[slot];  // the slot's own frame buffer: the other one may still be read by the frame in flight
+    if (!in_place && !d_src && t->q_count > 0) {
+        // pipelined host frame: upload on the copy stream while the frame in flight computes (whole frame: the host mirror of
+        // rect_last lags by one frame); the main stream picks it up through an event
+        vt_status st = upload_frame(t, frame, len, false, false, t->copy_stream);
+        if (st != VT_OK) return st;
+        VT_CUDA(cudaEventRecord(t->ev_up[slot], t->copy_stream));
+        VT_CUDA(cudaStreamWaitEvent(t->stream, t->ev_up[slot], 0));
+    }
     VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_frame_slot, in_place ? d_src : t->d_frame, t->d_host_slot, q.mirrored ? frame : nullptr, t->stream));
     ++t->kernel_launches;
     if (in_place) {
@@ -601,8 +615,8 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     } else if (d_src) {  // short device frame: device->device copy of what there is (NV12: black frame, src/nv12_convert.rs:48-50)
         vt_status st = upload_frame(t, d_src, len, false, true);
         if (st != VT_OK) return st;
-    } else {
-        vt_status st = upload_frame(t, frame, len, t->q_count == 0);  // the host mirror of rect_last is exact only with an empty queue
+    } else if (t->q_count == 0) {
+        vt_status st = upload_frame(t, frame, len, true);  // the host mirror of rect_last is exact: the search windows suffice
         if (st != VT_OK) return st;
     }
     const double hp1 = t->hostprof ? now_us() : 0;
@@ -715,7 +729,10 @@ void vt_tracker_destroy(vt_tracker* t) {
         if (e) cudaEventDestroy(e);
     if (t->d_fmt_in) cudaFree(t->d_fmt_in);
     if (t->d_fmt_out) cudaFree(t->d_fmt_out);
-    void* dev[] = {t->d_weights, t->d_lut, t->d_hann, t->d_frame, t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
+    if (t->copy_stream) cudaStreamSynchronize(t->copy_stream), cudaStreamDestroy(t->copy_stream);
+    for (auto& e : t->ev_up)
+        if (e) cudaEventDestroy(e);
+    void* dev[] = {t->d_weights, t->d_lut, t->d_hann, t->d_frames[0], t->d_frames[1], t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
                    t->patches_x, t->patches_z, t->Zemb, t->X, t->QKV, t->ATT, t->HID, t->Yf, t->H1, t->d_dbg,
                    t->w_hi, t->w_lo, t->px_hi, t->px_lo, t->pz_hi, t->pz_lo, t->ln_hi, t->ln_lo, t->att_hi, t->att_lo,
                    t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, t->zln_hi, t->zln_lo, t->d_trace, t->Pbuf, t->Phead, t->d_cand, t->d_counters};
@@ -792,8 +809,13 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         VT_TRY(cudaMalloc(&t->d_hann, sizeof(hann)));
         VT_TRY(cudaMemcpy(t->d_hann, hann, sizeof(hann), cudaMemcpyHostToDevice));
     }
-    VT_TRY(cudaMalloc(&t->d_frame, t->frame_bytes + 256));
-    VT_TRY(cudaMemset(t->d_frame, 0, t->frame_bytes + 256));
+    for (int i = 0; i < 2; ++i) {
+        VT_TRY(cudaMalloc(&t->d_frames[i], t->frame_bytes + 256));
+        VT_TRY(cudaMemset(t->d_frames[i], 0, t->frame_bytes + 256));
+        VT_TRY(cudaEventCreateWithFlags(&t->ev_up[i], cudaEventDisableTiming));
+    }
+    t->d_frame = t->d_frames[0];
+    VT_TRY(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
     t->h_stage_bytes = t->frame_bytes + 256;
     VT_TRY(cudaHostAlloc(&t->h_stage, t->h_stage_bytes, cudaHostAllocDefault));
     VT_TRY(cudaMalloc(&t->d_state, sizeof(TargetState) * B));
