@@ -14,9 +14,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <sys/stat.h>
+
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <memory>
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -36,6 +39,25 @@ struct BlockW {
     const float *ln1_g, *ln1_b, *qkv_w, *qkv_b, *proj_w, *proj_b, *ln2_g, *ln2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
 };
 
+// One device copy of a weight file (fp32 master + bf16 hi / lo split) shared by every handle of that device: with many streams per GPU
+// the 45 MB stay L2 resident once instead of once per stream.  Keyed by device, path, size and mtime; freed with the last handle.
+struct WeightSet {
+    int device = 0;
+    float* d_weights = nullptr;
+    __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
+    size_t n = 0;
+    int32_t hdr[7] = {0, 0, 0, 0, 0, 0, 0};
+    std::mutex split_mutex;
+    ~WeightSet() {
+        cudaSetDevice(device);
+        if (d_weights) cudaFree(d_weights);
+        if (w_hi) cudaFree(w_hi);
+        if (w_lo) cudaFree(w_lo);
+    }
+};
+static std::mutex g_weight_mutex;
+static std::map<std::string, std::weak_ptr<WeightSet>> g_weight_cache;
+
 enum { EV_START = 0, EV_H2D, EV_PRE, EV_VIT, EV_DEC, EV_OVL, EV_END, EV_COUNT };
 
 }  // namespace vt
@@ -52,7 +74,8 @@ struct vt_tracker {
     cudaEvent_t ev[EV_COUNT] = {};
     bool ev_valid = false;
 
-    // weights (one device allocation)
+    // weights (one device allocation, shared between the handles of a device: WeightSet)
+    std::shared_ptr<WeightSet> wset;
     float* d_weights = nullptr;
     size_t n_weights = 0;
     const float *patch_w, *patch_b, *pos_z, *pos_x, *lnf_g, *lnf_b, *h1_w, *h1_b, *h2_w, *h2_b;
@@ -157,46 +180,65 @@ static bool is_pinned(const void* p) {
 }
 
 static vt_status load_weights(vt_tracker* t, const char* path) {
-    FILE* f = fopen(path, "rb");
-    if (!f) {
+    struct stat sb;
+    if (stat(path, &sb) != 0) {
         set_error("cannot open weight file %s", path);
         return VT_ERR_WEIGHTS;
     }
-    char magic[4];
-    int32_t hdr[7];
-    if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "VTW1", 4) != 0 || fread(hdr, 4, 7, f) != 7) {
+    char key[1200];
+    snprintf(key, sizeof(key), "%d|%s|%lld|%lld", t->cfg.device, path, (long long)sb.st_size, (long long)sb.st_mtime);
+    std::lock_guard<std::mutex> lock(g_weight_mutex);
+    std::shared_ptr<WeightSet> ws = g_weight_cache[key].lock();
+    if (!ws) {
+        FILE* f = fopen(path, "rb");
+        if (!f) {
+            set_error("cannot open weight file %s", path);
+            return VT_ERR_WEIGHTS;
+        }
+        char magic[4];
+        int32_t hdr[7];
+        if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "VTW1", 4) != 0 || fread(hdr, 4, 7, f) != 7) {
+            fclose(f);
+            set_error("%s is not a VTW1 weight file", path);
+            return VT_ERR_WEIGHTS;
+        }
+        const size_t D = hdr[0], H = hdr[3], C = hdr[4];
+        const int heads = hdr[2];
+        if (D == 0 || D % 32 || H % 32 || C % 32 || heads <= 0 || D % heads || (D / heads != 16 && D / heads != 32 && D / heads != 64)) {
+            fclose(f);
+            set_error("unsupported model shape D=%d heads=%d hidden=%d head_ch=%d", hdr[0], hdr[2], hdr[3], hdr[4]);
+            return VT_ERR_WEIGHTS;
+        }
+        const size_t n = D * kPatchK + D + kNTz * D + kNTx * D + (size_t)hdr[1] * (4 * D + 3 * D * D + 3 * D + D * D + D + H * D + H + D * H + D) +
+                         2 * D + C * D * 9 + C + 5 * C + 5;
+        std::vector<float> host(n);
+        const size_t got = fread(host.data(), sizeof(float), n, f);
         fclose(f);
-        set_error("%s is not a VTW1 weight file", path);
-        return VT_ERR_WEIGHTS;
+        if (got != n) {
+            set_error("weight file %s is truncated (%zu of %zu floats)", path, got, n);
+            return VT_ERR_WEIGHTS;
+        }
+        // head conv weight [C, D, 3, 3] -> [C, tap, D] so that the im2col K axis is tap-major
+        const size_t h1_off = n - (5 + 5 * C + C + C * D * 9);
+        {
+            std::vector<float> re(C * D * 9);
+            for (size_t c = 0; c < C; ++c)
+                for (size_t d = 0; d < D; ++d)
+                    for (size_t tap = 0; tap < 9; ++tap) re[(c * 9 + tap) * D + d] = host[h1_off + (c * D + d) * 9 + tap];
+            std::copy(re.begin(), re.end(), host.begin() + h1_off);
+        }
+        ws = std::make_shared<WeightSet>();
+        ws->device = t->cfg.device, ws->n = n;
+        memcpy(ws->hdr, hdr, sizeof(hdr));
+        VT_CUDA(cudaMalloc(&ws->d_weights, n * sizeof(float)));
+        VT_CUDA(cudaMemcpy(ws->d_weights, host.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+        g_weight_cache[key] = ws;
     }
-    t->D = hdr[0], t->depth = hdr[1], t->heads = hdr[2], t->hidden = hdr[3], t->head_ch = hdr[4];
+    t->wset = ws;
+    t->D = ws->hdr[0], t->depth = ws->hdr[1], t->heads = ws->hdr[2], t->hidden = ws->hdr[3], t->head_ch = ws->hdr[4];
     const size_t D = t->D, H = t->hidden, C = t->head_ch;
-    if (D == 0 || D % 32 || H % 32 || C % 32 || t->heads <= 0 || D % t->heads || (D / t->heads != 16 && D / t->heads != 32 && D / t->heads != 64)) {
-        fclose(f);
-        set_error("unsupported model shape D=%d heads=%d hidden=%d head_ch=%d", t->D, t->heads, t->hidden, t->head_ch);
-        return VT_ERR_WEIGHTS;
-    }
-    const size_t n = D * kPatchK + D + kNTz * D + kNTx * D + (size_t)t->depth * (4 * D + 3 * D * D + 3 * D + D * D + D + H * D + H + D * H + D) +
-                     2 * D + C * D * 9 + C + 5 * C + 5;
-    std::vector<float> host(n);
-    const size_t got = fread(host.data(), sizeof(float), n, f);
-    fclose(f);
-    if (got != n) {
-        set_error("weight file %s is truncated (%zu of %zu floats)", path, got, n);
-        return VT_ERR_WEIGHTS;
-    }
-    // head conv weight [C, D, 3, 3] -> [C, tap, D] so that the im2col K axis is tap-major
-    const size_t h1_off = n - (5 + 5 * C + C + C * D * 9);
-    {
-        std::vector<float> re(C * D * 9);
-        for (size_t c = 0; c < C; ++c)
-            for (size_t d = 0; d < D; ++d)
-                for (size_t tap = 0; tap < 9; ++tap) re[(c * 9 + tap) * D + d] = host[h1_off + (c * D + d) * 9 + tap];
-        std::copy(re.begin(), re.end(), host.begin() + h1_off);
-    }
-    t->n_weights = n;
-    VT_CUDA(cudaMalloc(&t->d_weights, n * sizeof(float)));
-    VT_CUDA(cudaMemcpy(t->d_weights, host.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    t->n_weights = ws->n;
+    t->d_weights = ws->d_weights;
     const float* p = t->d_weights;
     auto take = [&](size_t cnt) {
         const float* r = p;
@@ -732,9 +774,9 @@ void vt_tracker_destroy(vt_tracker* t) {
     if (t->copy_stream) cudaStreamSynchronize(t->copy_stream), cudaStreamDestroy(t->copy_stream);
     for (auto& e : t->ev_up)
         if (e) cudaEventDestroy(e);
-    void* dev[] = {t->d_weights, t->d_lut, t->d_hann, t->d_frames[0], t->d_frames[1], t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
+    void* dev[] = {t->d_lut, t->d_hann, t->d_frames[0], t->d_frames[1], t->d_rgb, t->d_state, t->d_slots, t->d_res, t->d_maps, t->d_cmds,
                    t->patches_x, t->patches_z, t->Zemb, t->X, t->QKV, t->ATT, t->HID, t->Yf, t->H1, t->d_dbg,
-                   t->w_hi, t->w_lo, t->px_hi, t->px_lo, t->pz_hi, t->pz_lo, t->ln_hi, t->ln_lo, t->att_hi, t->att_lo,
+                   t->px_hi, t->px_lo, t->pz_hi, t->pz_lo, t->ln_hi, t->ln_lo, t->att_hi, t->att_lo,
                    t->hid_hi, t->hid_lo, t->yf_hi, t->yf_lo, t->q_hi, t->q_lo, t->k_hi, t->k_lo, t->vt_hi, t->vt_lo, t->zln_hi, t->zln_lo, t->d_trace, t->Pbuf, t->Phead, t->d_cand, t->d_counters};
     for (void* p : dev)
         if (p) cudaFree(p);
@@ -870,9 +912,17 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             VT_TRY(cudaMalloc(&t->d_counters, sizeof(unsigned) * B));
             VT_TRY(cudaMemset(t->d_counters, 0, sizeof(unsigned) * B));
         }
-        const size_t nw = t->n_weights;
-        VT_TRY(cudaMalloc(&t->w_hi, nw * 2)); VT_TRY(cudaMalloc(&t->w_lo, nw * 2));
-        VT_TRY(launch_split_bf16(t->d_weights, t->w_hi, t->w_lo, nw, t->stream));
+        {   // bf16 (hi, lo) split of the shared weights: done once per WeightSet
+            std::lock_guard<std::mutex> lock(t->wset->split_mutex);
+            if (!t->wset->w_hi) {
+                const size_t nw = t->n_weights;
+                VT_TRY(cudaMalloc(&t->wset->w_hi, nw * 2));
+                VT_TRY(cudaMalloc(&t->wset->w_lo, nw * 2));
+                VT_TRY(launch_split_bf16(t->d_weights, t->wset->w_hi, t->wset->w_lo, nw, t->stream));
+                VT_TRY(cudaStreamSynchronize(t->stream));
+            }
+            t->w_hi = t->wset->w_hi, t->w_lo = t->wset->w_lo;
+        }
         auto balloc = [&](__nv_bfloat16** hi, __nv_bfloat16** lo, size_t n) -> cudaError_t {
             cudaError_t e = cudaMalloc(hi, n * 2);
             if (e == cudaSuccess) e = cudaMalloc(lo, n * 2);
