@@ -99,7 +99,7 @@ def make_config(weights: str, width: int, height: int, fmt: str = "nv12", max_ta
     lib().vt_config_default(C.byref(cfg))
     cfg.weights_path = weights.encode()
     cfg.device = device
-    cfg.format = L.VT_FMT_NV12 if fmt == "nv12" else L.VT_FMT_RGB24
+    cfg.format = {"nv12": L.VT_FMT_NV12, "rgb24": L.VT_FMT_RGB24, "gray8": L.VT_FMT_GRAY8}[fmt]
     cfg.width, cfg.height, cfg.max_targets = width, height, max_targets
     cfg.score_threshold = score_threshold
     cfg.gemm_mode = gemm_mode

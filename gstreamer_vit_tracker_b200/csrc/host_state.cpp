@@ -317,7 +317,7 @@ static vt_overlay_cmd make_cmd(int kind, int x, int y, int w, int h, int a, uint
 vt_status vt_probe_frame(vt_context* c, uint8_t* frame, size_t len, const char* const* hud_override) {
     if (!c || !c->tracker || !frame) return VT_ERR_INVALID;
     vt_tracker* t = c->tracker;
-    const bool nv12 = c->cfg.format == VT_FMT_NV12;
+    const bool nv12 = vt::format_is_luma(c->cfg.format);  // GRAY8 frames take the luma-plane HUD of src/pipeline.rs:125-174
     // interval timing, src/pipeline.rs:69-79
     const auto now = std::chrono::steady_clock::now();
     if (c->have_last) vt_timing_add_interval(t, (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(now - c->last_time).count());

@@ -273,6 +273,8 @@ __device__ __forceinline__ void frame_rgb(const FrameDesc& f, int fx, int fy, in
     if (f.format == VT_FMT_RGB24) {
         const uint8_t* p = f.data + ((size_t)fy * f.width + fx) * 3;
         r = p[0], g = p[1], b = p[2];
+    } else if (f.format == VT_FMT_GRAY8) {
+        r = g = b = f.data[(size_t)fy * f.width + fx];
     } else {
         const size_t ysz = (size_t)f.width * f.height;
         const int yv = f.data[(size_t)fy * f.width + fx];

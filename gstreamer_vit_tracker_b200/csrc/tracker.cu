@@ -398,7 +398,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     else
         VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, t->d_stamps, s));
     if (t->cfg.box_overlay)
-        VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, t->fmt, t->d_res, t->d_slots, n, t->cfg.overlay_gate,
+        VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, overlay_format(t->fmt), t->d_res, t->d_slots, n, t->cfg.overlay_gate,
                                      t->d_host_slot, t->d_stamps + ST_OVL_END, s, (uint8_t* const*)t->d_frame_slot));
     return VT_OK;
 }
@@ -470,11 +470,11 @@ static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, b
     const bool pinned = device_src || is_pinned(frame);
     const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (allow_window && t->cfg.upload_window && pinned && t->frame_valid && len >= t->frame_bytes && !t->active.empty() && (t->W % 2 == 0) &&
-        (t->H % 2 == 0 || t->fmt == VT_FMT_RGB24)) {
+        (t->H % 2 == 0 || t->fmt != VT_FMT_NV12)) {
         struct Win { int x0, y0, x1, y1; };
         std::vector<Win> wins;
         size_t bytes = 0;
-        const size_t bpp_num = t->fmt == VT_FMT_NV12 ? 3 : 6;  // bytes per pixel x 2
+        const size_t bpp_num = t->fmt == VT_FMT_NV12 ? 3 : (t->fmt == VT_FMT_GRAY8 ? 2 : 6);  // bytes per pixel x 2
         for (int s : t->active) {
             Win w;
             if (!search_window(t, t->rect_mirror[s], w.x0, w.y0, w.x1, w.y1)) continue;  // the crop kernel flags it; nothing to read
@@ -484,7 +484,10 @@ static vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, b
         if (bytes * 2 <= t->frame_bytes) {
             for (const Win& w : wins) {
                 const size_t cols = (size_t)(w.x1 - w.x0), rows = (size_t)(w.y1 - w.y0);
-                if (t->fmt == VT_FMT_NV12) {
+                if (t->fmt == VT_FMT_GRAY8) {
+                    const size_t W = (size_t)t->W, o = (size_t)w.y0 * W + w.x0;
+                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, W, frame + o, W, cols, rows, kind, stream));
+                } else if (t->fmt == VT_FMT_NV12) {
                     const size_t W = (size_t)t->W, yo = (size_t)w.y0 * W + w.x0, uvo = W * t->H + (size_t)(w.y0 / 2) * W + w.x0;
                     VT_CUDA(cudaMemcpy2DAsync(t->d_frame + yo, W, frame + yo, W, cols, rows, kind, stream));
                     VT_CUDA(cudaMemcpy2DAsync(t->d_frame + uvo, W, frame + uvo, W, cols, rows / 2, kind, stream));
@@ -527,7 +530,7 @@ static void fill_results(vt_tracker* t, vt_result* results) {
 // (src/nv12_convert.rs:181-212,224-241; src/drawing_rgb.rs:55-73).  Returns false if nothing is drawn.
 static bool rect_rows(int fmt, long long H, int y, int h, int th, long long& r0, long long& r1) {
     if (H <= 0) return false;
-    if (fmt == VT_FMT_NV12) {
+    if (format_is_luma(fmt)) {
         const long long y1 = std::max(y, 0);
         const long long sum = (long long)(int32_t)((uint32_t)y + (uint32_t)h);
         const long long y2 = sum < 0 ? H - 1 : std::min(sum, H - 1);  // negative i32 -> huge usize -> clamped
@@ -571,7 +574,7 @@ static void merge_spans(std::vector<std::pair<int, int>>& spans) {
 
 // device -> host copy of whole rows [r0, r1] of the drawable plane (Y plane for NV12, the image for RGB24)
 static vt_status download_rows(vt_tracker* t, uint8_t* frame, size_t len, const std::vector<std::pair<int, int>>& spans, bool* staged) {
-    const size_t pitch = (size_t)t->W * (t->fmt == VT_FMT_NV12 ? 1 : 3);
+    const size_t pitch = (size_t)t->W * (format_is_luma(t->fmt) ? 1 : 3);
     const bool pinned = is_pinned(frame);
     *staged = !pinned;
     for (auto& sp : spans) {
@@ -585,7 +588,7 @@ static vt_status download_rows(vt_tracker* t, uint8_t* frame, size_t len, const 
     return VT_OK;
 }
 static void unstage_rows(vt_tracker* t, uint8_t* frame, size_t len, const std::vector<std::pair<int, int>>& spans) {
-    const size_t pitch = (size_t)t->W * (t->fmt == VT_FMT_NV12 ? 1 : 3);
+    const size_t pitch = (size_t)t->W * (format_is_luma(t->fmt) ? 1 : 3);
     for (auto& sp : spans) {
         const size_t off = (size_t)sp.first * pitch;
         size_t n = (size_t)(sp.second - sp.first + 1) * pitch;
@@ -794,7 +797,7 @@ void vt_tracker_destroy(vt_tracker* t) {
 
 vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     if (!cfg || !out || !cfg->weights_path || cfg->width <= 0 || cfg->height <= 0 || cfg->max_targets <= 0 || cfg->max_targets > 64 ||
-        (cfg->format != VT_FMT_NV12 && cfg->format != VT_FMT_RGB24)) {
+        (cfg->format != VT_FMT_NV12 && cfg->format != VT_FMT_RGB24 && cfg->format != VT_FMT_GRAY8)) {
         set_error("vt_tracker_create: invalid configuration");
         return VT_ERR_INVALID;
     }
@@ -814,7 +817,9 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     t->cfg = *cfg;
     t->cfg.weights_path = nullptr;
     t->W = cfg->width, t->H = cfg->height, t->fmt = cfg->format, t->maxT = cfg->max_targets;
-    t->frame_bytes = cfg->format == VT_FMT_NV12 ? (size_t)t->W * t->H + (size_t)((t->H + 1) / 2) * t->W + (t->W & 1) : (size_t)t->W * t->H * 3;
+    t->frame_bytes = cfg->format == VT_FMT_NV12    ? (size_t)t->W * t->H + (size_t)((t->H + 1) / 2) * t->W + (t->W & 1)
+                     : cfg->format == VT_FMT_GRAY8 ? (size_t)t->W * t->H
+                                                   : (size_t)t->W * t->H * 3;
     t->threshold = cfg->score_threshold > 0.f ? cfg->score_threshold : 0.20f;
     t->debug_capture = cfg->debug_capture;
     t->hostprof = getenv("VT_B200_HOSTPROF") != nullptr;
@@ -1445,7 +1450,7 @@ static vt_status build_cmds(vt_tracker* t, const vt_overlay_cmd* cmds, int n, st
 static vt_status overlay_impl(vt_tracker* t, uint8_t* frame, size_t len, const vt_overlay_cmd* cmds, int32_t n, bool upload) {
     if (!t || !frame || (n > 0 && !cmds) || t->in_flight) return VT_ERR_INVALID;
     VT_CUDA(cudaSetDevice(t->cfg.device));
-    const size_t need = t->fmt == VT_FMT_NV12 ? (size_t)t->W * t->H : 0;
+    const size_t need = format_is_luma(t->fmt) ? (size_t)t->W * t->H : 0;
     if (len < need) {
         set_error("vt_overlay: frame shorter than its Y plane");
         return VT_ERR_INVALID;
@@ -1465,7 +1470,7 @@ static vt_status overlay_impl(vt_tracker* t, uint8_t* frame, size_t len, const v
         }
     }
     VT_CUDA(cudaMemcpyAsync(t->d_cmds, t->h_cmds, sizeof(OverlayCmdDev) * n, cudaMemcpyHostToDevice, t->stream));
-    cudaError_t e = launch_overlay(t->d_frame, std::min(len, t->frame_bytes), t->W, t->H, t->fmt, t->d_cmds, n, t->stream);
+    cudaError_t e = launch_overlay(t->d_frame, std::min(len, t->frame_bytes), t->W, t->H, overlay_format(t->fmt), t->d_cmds, n, t->stream);
     if (e != cudaSuccess) {
         set_error("overlay launch failed: %s", cudaGetErrorString(e));
         return VT_ERR_CUDA;

@@ -25,6 +25,10 @@ constexpr int kMaxCmds = 32;
 
 void set_error(const char* fmt, ...);
 
+// GRAY8 frames are a bare luma plane: drawn on with the NV12 (Y plane) overlay semantics
+inline int overlay_format(int fmt) { return fmt == VT_FMT_GRAY8 ? VT_FMT_NV12 : fmt; }
+inline bool format_is_luma(int fmt) { return fmt == VT_FMT_NV12 || fmt == VT_FMT_GRAY8; }
+
 #define VT_CUDA(call)                                                                              \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \

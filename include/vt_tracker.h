@@ -44,7 +44,9 @@ enum {
     VT_ERR_GLYPH = -6         /* unknown character in strict text mode        ≙ get_glyph panic, src/drawing.rs:99 */
 };
 
-typedef enum { VT_FMT_NV12 = 0, VT_FMT_RGB24 = 1 } vt_format;
+/* VT_FMT_GRAY8: one byte per pixel (IR sensors; BASELINE config "IR/GRAY8 at 640x512"): the tracker sees r = g = b = gray and the
+ * overlays follow the NV12 luma-plane semantics (src/nv12_convert.rs:172-343 write the Y plane only). */
+typedef enum { VT_FMT_NV12 = 0, VT_FMT_RGB24 = 1, VT_FMT_GRAY8 = 2 } vt_format;
 typedef enum { VT_GEMM_FP32_SIMT = 0, VT_GEMM_TCGEN05_BF16X3 = 1, VT_GEMM_TCGEN05_BF16 = 2 } vt_gemm_mode;
 
 /* ≙ vit_tracker::BBox {x, y, width, height: i32} (uses: src/selection_state.rs:44, src/pipeline.rs:166) */

@@ -641,3 +641,49 @@ def test_pipelined_submit_wait_depth_two(api, weight_dir):
     with pytest.raises(api.VtError):
         c.submit(frames[1].copy())
     c.wait()
+
+
+@pytest.mark.gpu
+def test_gray8_input_format(api, oracle, weight_dir):
+    """BASELINE config "IR/GRAY8 at 640x512": a GRAY8 frame is tracked as r = g = b = gray (search blob bit-exact against the oracle on the
+    replicated RGB frame, boxes / scores as the oracle's), and the box overlay follows the NV12 luma-plane semantics."""
+    spec = synth.CONFIGS["cfg3"]
+    W, H = spec.width, spec.height
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+
+    def gray(n):
+        rgb = np.asarray(st.frame(n)).reshape(H, W, 3).astype(np.uint32)
+        return ((rgb[..., 0] * 77 + rgb[..., 1] * 150 + rgb[..., 2] * 29 + 128) >> 8).astype(np.uint8).reshape(-1)
+
+    trk = api.VitTrack.new(wpath, W, H, fmt="gray8", box_overlay=True, upload_window=True)
+    ref = oracle.VitTrack(wpath, threads=4)
+    box = st.target_boxes(0)[0]
+    g0 = gray(0)
+    pin = api.PinnedBuffer(g0.size)
+    pin.array[:] = g0
+    trk.init(pin.array, api.BBox(*box))
+    ref.init(np.repeat(g0.reshape(H, W, 1), 3, axis=2), box)
+    for n in range(6):
+        g = gray(n)
+        rgb = np.ascontiguousarray(np.repeat(g.reshape(H, W, 1), 3, axis=2))
+        before = ref.rect
+        trk.set_rect(before)
+        pin.array[:] = g
+        r = trk.update(pin.array)
+        rc, ok, score, bb = ref.update(rgb)
+        assert rc == 0 and r.success == ok and abs(r.score - score) <= SCORE_TOL, (n, r, ok, score)
+        sb, _ = ref.last_blobs()
+        assert np.array_equal(np.asarray(trk.debug_read(0)["search_blob"]).reshape(-1), np.asarray(sb).reshape(-1)), n
+        if tuple(r.bbox) == tuple(bb) and ok and score > 0.25:
+            want = np.concatenate([g, np.zeros(W * H // 2, np.uint8)])  # the oracle's NV12 drawing code on a bare luma plane
+            x, y, w, h = bb
+            oracle.draw_rect_nv12(want, W, H, x, y, w, h, 3, 255)
+            oracle.draw_crosshair_nv12(want, W, H, x + w // 2, y + h // 2, 15, 255)
+            assert np.array_equal(pin.array, want[:W * H]), n
+    # pageable frames and the explicit overlay entry point work on the luma plane too
+    fr = gray(2).copy()
+    want = np.concatenate([fr, np.zeros(W * H // 2, np.uint8)])
+    trk.overlay(fr, [api.overlay_cmd(api.L.VT_OV_RECT, 100, 80, 60, 40, 3, 200)])
+    oracle.draw_rect_nv12(want, W, H, 100, 80, 60, 40, 3, 200)
+    assert np.array_equal(fr, want[:W * H])

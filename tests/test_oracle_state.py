@@ -110,3 +110,48 @@ def test_keyboard_map_matches_reference_source(built):
             assert hit == 0, byte
         else:
             assert hit == 1 and names[cmd.value] == want[0] and bool(fast.value) == want[1], (byte, cmd.value, fast.value, want)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_product_vs_oracle_random_walk(built, seed):
+    """20,000 random steps (commands, confirmed acquisitions, good / weak / failed / erroring updates, long losses that trigger the
+    60-frame auto reset): the product's C++ state machine and the C oracle stay in lock step on every observable
+    (returned box, state name, score, bbox, selection, lost counter)."""
+    import random
+
+    from gstreamer_vit_tracker_b200 import api
+
+    rng = random.Random(seed)
+    W, H = 1920, 1080
+    a = oracle.TrackerContext(None, W, H)
+    b = api.TrackerContext.scripted(W, H)
+    names = list(CMD_NAMES)
+    seen = set()
+    for step in range(20000):
+        u = rng.random()
+        if u < 0.45:
+            cmd = rng.choice(names[:4] if u < 0.30 else names)
+            fast = rng.random() < 0.5
+            a.handle_command(cmd, fast)
+            b.handle_command(CMD_NAMES[cmd], fast)
+            ra = rb = None
+        else:
+            err = rng.random() < 0.05
+            ok = rng.random() < 0.8
+            score = rng.choice([0.0, 0.1, 0.2, 0.25, 0.2500001, 0.3, 0.9]) if rng.random() < 0.5 else rng.random()
+            if rng.random() < 0.02:  # a long loss
+                ok, score = False, 0.0
+            bb = (rng.randint(-50, W), rng.randint(-50, H), rng.randint(0, 400), rng.randint(0, 400))
+            ra = a.process_frame(None, scripted=(ok, score, bb), scripted_err=err)
+            rb = b.process_scripted(api.TrackResult(ok, score, bb), err=err)
+            rb = rb.tuple() if rb else None
+        s = b.selection
+        bbb = b.current_bbox
+        assert ra == rb, step
+        assert a.state_name() == b.state_name(), step
+        assert a.current_score == b.current_score, step
+        assert a.current_bbox == (bbb.tuple() if bbb else None), step
+        assert tuple(a.selection[:5]) == (s.cursor_x, s.cursor_y, s.start_x, s.start_y, s.phase), step
+        assert a.lost_frames == b.lost_frames, step
+        seen.add(a.state_name())
+    assert seen == {"SELECT START", "SELECT END", "TRACKING", "LOST"}, seen
