@@ -37,19 +37,22 @@ namespace vt {
 
 using namespace tc;
 
-constexpr int kTcBM = 128, kTcBN = 64, kTcBK = 64, kTcStages = 3;
+constexpr int kTcBM = 128, kTcBK = 64, kTcStages = 3;
 constexpr int kTileABytes = kTcBM * kTcBK * 2;  // 16 KB, one precision part
-constexpr int kTileBBytes = kTcBN * kTcBK * 2;  //  8 KB
-constexpr int kTileOBytes = kTcBM * kTcBN * 2;  // 16 KB: one bf16 output tile
-constexpr int kTileCBytes = kTcBM * kTcBN * 4;  // 32 KB: the fp32 tile as two 128-byte-wide boxes
-constexpr int kMaxChainN = 192;                 // widest chained second GEMM (TMEM: 64 + N2 <= 256 columns)
+constexpr int kMaxChainN = 192;                 // widest chained second GEMM (TMEM: 128 + N2 <= 512 columns)
+constexpr int kChainBN = 64;                    // the chained GEMM consumes a 64-column hidden tile
 
-template <int NSPLIT>
+// BN = 64: the throughput tile (FC1 + chained FC2).  BN = 32: twice the CTAs, half the epilogue per CTA and a shorter operand fetch
+// per UMMA for the GEMMs whose epilogue is on the critical path of a single stream (QKV, proj, patch embed, head conv).
+template <int NSPLIT, int BN>
 struct TcSmem {
     static constexpr int kParts = NSPLIT == 3 ? 2 : 1;
+    static constexpr int kTileBBytes = BN * kTcBK * 2;   // 8 / 4 KB
+    static constexpr int kTileOBytes = kTcBM * BN * 2;   // 16 / 8 KB: one bf16 output tile, rows of 128 / 64 bytes
+    static constexpr int kTileCBytes = kTcBM * BN * 4;   // 32 / 16 KB: the fp32 tile as BN / 32 boxes of [128 rows][128 B]
     static constexpr int kStageBytes = kParts * (kTileABytes + kTileBBytes);
     // the ring is padded (bf16 mode) so that the chained GEMM's result tile fits behind the staged hidden tile
-    static constexpr int kRingMin = 2 * kTileOBytes + kTcBM * kMaxChainN * 4;
+    static constexpr int kRingMin = BN == kChainBN ? 2 * kTileOBytes + kTcBM * kMaxChainN * 4 : 4 * kTileOBytes;
     static constexpr int kPipeBytes = kTcStages * kStageBytes > kRingMin ? kTcStages * kStageBytes : kRingMin;
     // after the main loop the pipeline ring is dead and holds the staged output tiles
     static constexpr int kOffOhi = 0, kOffOlo = kTileOBytes, kOffLnHi = 2 * kTileOBytes, kOffLnLo = 3 * kTileOBytes;
@@ -57,10 +60,9 @@ struct TcSmem {
     // chained second GEMM (FC2 partial inside the FC1 kernel): its weight slice [N2 <= 192][64] per part lives where the fp32
     // tile would be, its fp32 result tile [128][N2] is staged in the dead ring behind the two hidden-tile parts
     static constexpr int kOffB2 = kPipeBytes, kB2PartBytes = kMaxChainN * 128, kOffP = 2 * kTileOBytes;
-    static constexpr int kTailBytes = kParts * kB2PartBytes > kTileCBytes ? kParts * kB2PartBytes : kTileCBytes;
+    static constexpr int kTailBytes = (BN == kChainBN && kParts * kB2PartBytes > kTileCBytes) ? kParts * kB2PartBytes : kTileCBytes;
     static constexpr int kTotal = kPipeBytes + kTailBytes + 1024;  // + alignment slack
     static_assert(4 * kTileOBytes <= kPipeBytes, "staging must fit in the dead pipeline ring");
-    static_assert(kOffP + kTcBM * kMaxChainN * 4 <= kPipeBytes, "chained result tile must fit in the dead pipeline ring");
 };
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf by Abramowitz & Stegun 7.1.26 (one rcp, five FMAs, one ex2): |abs error| < 7e-7 in fp32
@@ -83,17 +85,26 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // own columns and stages the bf16 (hi, lo) A operand of the next GEMM for a TMA tile store.
 constexpr int kMaxLnCluster = 8;
 constexpr int kTcThreads = 512;                         // 16 warps: warp w reads TMEM lane quarter w % 4, column group w / 4
-constexpr int kTcColGroups = kTcThreads / kTcBM;        // 4 threads per accumulator row
-constexpr int kTcColsPerThread = kTcBN / kTcColGroups;  // 16 columns each
+constexpr int kTcColGroups = kTcThreads / kTcBM;        // 4 threads per accumulator row, BN / 4 columns each
 
-// 16 fp32 -> bf16 (hi, lo), 32 bytes each, into 128B-swizzled [128 rows][64 cols] staging tiles (chunk = 16-byte unit in the row)
-__device__ __forceinline__ void stage_split16(const float (&v)[16], uint8_t* tile_hi, uint8_t* tile_lo, int row, int g, bool with_lo) {
-    uint32_t hi[8], lo[8];
+// Staging tiles live in shared memory as [128 rows][RB bytes] (RB = 128: 64 bf16 or 32 fp32 columns; RB = 64: 32 bf16 columns) with
+// the 16-byte chunks of a row XOR-swizzled so that both the per-row writes of the epilogue threads and the row-major reads of the
+// copy-out are bank-conflict free; RB = 128 is the hardware 128B swizzle (the staged hidden tile is a valid UMMA A operand).
+template <int RB>
+__device__ __forceinline__ int swz(int row, int chunk) {
+    return RB == 128 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3));
+}
+
+// CPT (16 or 8) fp32 -> bf16 (hi, lo) into the staging tiles of a BN = 4 CPT column tile
+template <int CPT>
+__device__ __forceinline__ void stage_split(const float (&v)[CPT], uint8_t* tile_hi, uint8_t* tile_lo, int row, int g, bool with_lo) {
+    constexpr int RB = CPT * 8;  // bytes per tile row
+    uint32_t hi[CPT / 2], lo[CPT / 2];
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) split2_bf16(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
+    for (int j = 0; j < CPT; j += 2) split2_bf16(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int off = row * 128 + (((2 * g + q) ^ (row & 7)) << 4);
+    for (int q = 0; q < CPT / 8; ++q) {
+        const int off = row * RB + (swz<RB>(row, (CPT / 8) * g + q) << 4);
         *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
         if (with_lo) *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
     }
@@ -103,10 +114,10 @@ __device__ __forceinline__ void stage_split16(const float (&v)[16], uint8_t* til
 // [targets][heads][rows][cols] output (TcOut); periods are multiples of 64, so each 64-row half of a tile stays inside one target
 // and its (row, target) is computed once (TileRows).  Rows outside [0, rows) — the template rows the final LayerNorm drops, the
 // padding rows of the last tile — and targets >= batch are skipped.
-// The copy is done by all 512 threads with fully coalesced 16-byte stores: 8 lanes cover one 128-byte tile row, a warp instruction
-// writes 4 rows.  (Measured alternatives: thread-per-row stores straight from registers touch 32 lines per instruction and run at
+// The copy is done by all 512 threads with fully coalesced 16-byte stores: RB / 16 lanes cover one tile row, a warp instruction
+// writes 4 (8) rows.  (Measured alternatives: thread-per-row stores straight from registers touch 32 lines per instruction and run at
 // ~9 B/clk/SM; TMA tile stores cost ~0.16 us per 8 KB box on the issuing SM, 2 us for the 96 KB partial tile of the chained GEMM.)
-constexpr int kHalfRows = 64, kHalfBytes = kHalfRows * 128;
+constexpr int kHalfRows = 64;
 struct TileRows {  // (row-in-target, target) of the two 64-row halves of a tile; computed once, before the accumulator wait
     int t[2], b[2];
     __device__ __forceinline__ TileRows(int m0, int period, int batch_off) {
@@ -117,54 +128,61 @@ struct TileRows {  // (row-in-target, target) of the two 64-row halves of a tile
         }
     }
 };
-// one [128 rows][128 B] 128B-swizzled tile; col_bytes = byte offset of the tile's first column inside a destination row
+// one [128 rows][RB bytes] swizzled tile; col_bytes = byte offset of the tile's first column inside a destination row
+template <int RB>
 __device__ __forceinline__ void tile_to_global(const uint8_t* tile, const TcOut& o, int64_t col_bytes, const TileRows& r, int row_off, int head,
                                                int plane, int tid) {
+    constexpr int CH = RB / 16, kRowsPerPass = kTcThreads / CH;  // 8 chunks, 64 rows per pass / 4 chunks, 128 rows in one pass
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int row = (tid >> 3) + 64 * i, ch = tid & 7;
-        const int tt = r.t[i] + (tid >> 3) + row_off, b = r.b[i];
+    for (int i = 0; i < kTcBM / kRowsPerPass; ++i) {
+        const int row = tid / CH + kRowsPerPass * i, ch = tid % CH, half = row >> 6;
+        const int tt = r.t[half] + (row & 63) + row_off, b = r.b[half];
         if (tt >= 0 && tt < o.rows && b < o.batch) {
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 128 + ((ch ^ (row & 7)) << 4));
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + row * RB + (swz<RB>(row, ch) << 4));
             uint8_t* dst = o.base + (int64_t)plane * o.plane_bytes + (((int64_t)b * o.heads + head) * o.rows + tt) * o.row_bytes + col_bytes + ch * 16;
             *reinterpret_cast<uint4*>(dst) = v;
         }
     }
 }
-// V^T: two unswizzled [64 d][64 tokens] sub-tiles -> [targets][heads][64 d][tokens]; the token range of sub-tile k is t[k]..t[k]+63
-__device__ __forceinline__ void vt_tile_to_global(const uint8_t* tile, const TcOut& o, const TileRows& r, int head, int tid) {
+// V^T: two unswizzled [BN d][64 tokens] sub-tiles -> rows d_off.. of [targets][heads][64 d][tokens]; sub-tile k holds tokens t[k]..t[k]+63
+template <int BN>
+__device__ __forceinline__ void vt_tile_to_global(const uint8_t* tile, const TcOut& o, const TileRows& r, int head, int d_off, int tid) {
+    constexpr int kPasses = 2 * BN * 8 / kTcThreads;  // 2 sub-tiles x BN rows x 8 chunks over 512 threads
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int d = tid >> 3, ch = tid & 7, b = r.b[i];
-        if (b < o.batch && r.t[i] + kHalfRows <= o.rows) {
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + i * kHalfBytes + d * 128 + ch * 16);
-            uint8_t* dst = o.base + (((int64_t)b * o.heads + head) * kTcBN + d) * o.row_bytes + (int64_t)r.t[i] * 2 + ch * 16;
+    for (int i = 0; i < kPasses; ++i) {
+        const int idx = tid + i * kTcThreads, sub = idx / (BN * 8), d = (idx >> 3) % BN, ch = idx & 7, b = r.b[sub];
+        if (b < o.batch && r.t[sub] + kHalfRows <= o.rows) {
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + sub * (BN * 128) + d * 128 + ch * 16);
+            uint8_t* dst = o.base + (((int64_t)b * o.heads + head) * 64 + d_off + d) * o.row_bytes + (int64_t)r.t[sub] * 2 + ch * 16;
             *reinterpret_cast<uint4*>(dst) = v;
         }
     }
 }
 
-template <int NSPLIT>
+template <int NSPLIT, int BN>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcGemmArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages], accum_bar, resid_bar, b2_bar, accum2_bar, ln_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float2 ln_part[kMaxLnCluster][kTcColGroups][kTcBM];
     __shared__ unsigned long long* trace_slot;
-    using SM = TcSmem<NSPLIT>;
+    using SM = TcSmem<NSPLIT, BN>;
+    constexpr int CPT = BN / kTcColGroups;   // accumulator columns per thread: 16 / 8
+    constexpr int RB = BN * 2;               // bytes per row of a bf16 staging tile
+    constexpr int kTileBBytes = SM::kTileBBytes, kTileOBytes = SM::kTileOBytes, kTileCBytes = SM::kTileCBytes;
     constexpr bool kLo = NSPLIT == 3;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane;   // accumulator row inside the tile = TMEM lane
-    const int g = warp >> 2;                  // column group: columns 16 g .. 16 g + 15 of the tile
-    const int n0 = blockIdx.x * kTcBN, m0 = blockIdx.y * kTcBM;
+    const int g = warp >> 2;                  // column group: columns CPT g .. CPT g + CPT - 1 of the tile
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kTcBM;
     // split-K over blockIdx.z: this CTA contracts k-blocks [kb0, kb0 + num_kb) and stores its fp32 partial tile to C[.., z]
     const int num_kb = a.kb_per_split ? a.kb_per_split : a.K / kTcBK;
     const int kb0 = blockIdx.z * num_kb;
     const int npre = num_kb < kTcStages ? num_kb : kTcStages;
-    constexpr uint32_t kAcc1Cols = kLo ? 2 * kTcBN : kTcBN;  // bf16x3 keeps hi*lo in a second column half
-    const uint32_t tmem_cols = a.chain_n == 0 ? kAcc1Cols : (kAcc1Cols + a.chain_n <= 128 ? 128 : (kAcc1Cols + a.chain_n <= 256 ? 256 : 512));
+    constexpr uint32_t kAcc1Cols = kLo ? 2 * BN : BN;  // bf16x3 keeps hi*lo in a second column half
+    const uint32_t tmem_cols = a.chain_n == 0 ? (kAcc1Cols < 32 ? 32 : kAcc1Cols) : (kAcc1Cols + a.chain_n <= 128 ? 128 : (kAcc1Cols + a.chain_n <= 256 ? 256 : 512));
     bool ok = true;
     TraceRec tr;
     tr.begin(&trace_slot, a.trace, a.trace_id);
@@ -231,8 +249,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 }
                 if (kb == 0 && a.residual) {  // residual rows of this tile (flat [rows][N] fp32), two 128-byte-wide boxes
                     mbar_arrive_expect_tx(&resid_bar, kTileCBytes);
-                    tma_load_2d(sC, &mp.R, &resid_bar, n0, m0);
-                    tma_load_2d(sC + kTileCBytes / 2, &mp.R, &resid_bar, n0 + 32, m0);
+#pragma unroll
+                    for (int bx = 0; bx < BN / 32; ++bx) tma_load_2d(sC + bx * (kTcBM * 128), &mp.R, &resid_bar, n0 + 32 * bx, m0);
                 }
             }
         }
@@ -242,7 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             // bf16x3: A_hi x [W_hi; W_lo] as ONE N = 128 UMMA (the two weight parts are adjacent 64-row tiles of the stage) into
             // accumulator columns [0, 64) (hi*hi) and [64, 128) (hi*lo), then A_lo x W_hi (N = 64) into [0, 64); the epilogue adds the
             // two halves.  UMMA issue is operand-fetch bound (~85 clk for 4 KB A + 2 KB B): 14 KB per K-step instead of 18 KB.
-            constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, kTcBN), idesc2n = umma_idesc_bf16(kTcBM, 2 * kTcBN);
+            constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, BN), idesc2n = umma_idesc_bf16(kTcBM, 2 * BN);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kTcStages;
                 ok &= mbar_wait(&full_bar[s], (kb / kTcStages) & 1);
@@ -268,52 +286,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     }
 
     // ---- epilogue: thread (row, g) owns 16 accumulator columns of its row
-    const int m = m0 + row, nc = n0 + g * kTcColsPerThread;
-    // this thread's four 16-byte chunks of the fp32 tile: box (g >> 1), chunks 4 (g & 1) .. + 3 of the 128-byte row, swizzled
-    uint8_t* c_row = sC + (g >> 1) * (kTileCBytes / 2) + row * 128;
-    const int c_chunk0 = (g & 1) * 4, sw = row & 7;
+    const int m = m0 + row, nc = n0 + g * CPT;
+    // this thread's CPT / 4 16-byte chunks of the fp32 tile: 32-column box (CPT g) / 32, first chunk ((CPT g) % 32) / 4, swizzled
+    uint8_t* c_row = sC + ((g * CPT) >> 5) * (kTcBM * 128) + row * 128;
+    const int c_chunk0 = ((g * CPT) & 31) >> 2, sw = row & 7;
     const TileRows tr_rows(m0, a.period, a.batch_off);
-    int o_which = 0, o_h = 0;
+    int o_which = 0, o_h = 0, o_d = 0;
     if (a.o_mode == 2) {  // QKV: this CTA's 64 columns are one head of Q, K or V
         const int Dm = a.N / 3;
-        o_which = n0 / Dm, o_h = (n0 - o_which * Dm) / kTcBN;
+        o_which = n0 / Dm, o_h = (n0 - o_which * Dm) / 64, o_d = (n0 - o_which * Dm) % 64;  // head_dim 64; BN = 32: half a head
     }
-    float bias_v[kTcColsPerThread];
+    float bias_v[CPT];
     if (a.bias) {  // does not depend on the accumulator: fetch while the MMAs run
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
+        for (int j = 0; j < CPT; j += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nc + j));
             bias_v[j] = b4.x, bias_v[j + 1] = b4.y, bias_v[j + 2] = b4.z, bias_v[j + 3] = b4.w;
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) bias_v[j] = 0.f;
+        for (int j = 0; j < CPT; ++j) bias_v[j] = 0.f;
     }
     ok &= mbar_wait(&accum_bar, 0);
     tcgen05_fence_after();
     if (tid == 0) tr.mark(6);
-    float v[kTcColsPerThread];
-    tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * kTcColsPerThread, v);
+    float v[CPT];
+    tmem_ld_cols(tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * CPT, v);
     if (kLo) {
-        float hl[kTcColsPerThread];
-        tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kTcBN + g * kTcColsPerThread, hl);
+        float hl[CPT];
+        tmem_ld_cols(tmem + ((uint32_t)((warp & 3) * 32) << 16) + BN + g * CPT, hl);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += hl[j];
+        for (int j = 0; j < CPT; ++j) v[j] += hl[j];
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] += bias_v[j];
+    for (int j = 0; j < CPT; ++j) v[j] += bias_v[j];
     if (a.gelu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < CPT; ++j) v[j] = gelu_erf(v[j]);
     }
     if (a.relu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < CPT; ++j) v[j] = fmaxf(v[j], 0.f);
     }
     if (a.pos) {
         const float* pp = a.pos + (int64_t)(m % a.pos_rows) * a.N + nc;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
+        for (int j = 0; j < CPT; j += 4) {
             const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + j));
             v[j] += p4.x, v[j + 1] += p4.y, v[j + 2] += p4.z, v[j + 3] += p4.w;
         }
@@ -321,7 +339,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     if (a.residual) {
         ok &= mbar_wait(&resid_bar, 0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < CPT / 4; ++q) {
             const float4 r4 = *reinterpret_cast<const float4*>(c_row + (((c_chunk0 + q) ^ sw) << 4));
             v[4 * q] += r4.x, v[4 * q + 1] += r4.y, v[4 * q + 2] += r4.z, v[4 * q + 3] += r4.w;
         }
@@ -330,18 +348,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     // ---- stage the output tiles in shared memory (the pipeline ring is dead: every MMA has completed)
     if (a.c_on) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < CPT / 4; ++q)
             *reinterpret_cast<float4*>(c_row + (((c_chunk0 + q) ^ sw) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
     if (a.o_mode) {  // (o_mode 3: staged only — the tile is the A operand of the chained GEMM)
         if (o_which < 2) {
-            stage_split16(v, smem + SM::kOffOhi, smem + SM::kOffOlo, row, g, kLo);
-        } else {  // V^T: two unswizzled [64 d][64 tokens] sub-tiles; lanes are consecutive tokens -> 64-byte contiguous runs
-            const int sub = (row >> 6) * (kHalfBytes / 2) + (g * kTcColsPerThread) * kHalfRows + (row & 63);
+            stage_split<CPT>(v, smem + SM::kOffOhi, smem + SM::kOffOlo, row, g, kLo);
+        } else {  // V^T: two unswizzled [BN d][64 tokens] sub-tiles; lanes are consecutive tokens -> 64-byte contiguous runs
+            const int sub = (row >> 6) * (BN * kHalfRows) + (g * CPT) * kHalfRows + (row & 63);
             __nv_bfloat16* th = reinterpret_cast<__nv_bfloat16*>(smem + SM::kOffOhi) + sub;
             __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(smem + SM::kOffOlo) + sub;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CPT; ++j) {
                 __nv_bfloat16 h, l;
                 split_bf16(v[j], h, l);
                 th[j * kHalfRows] = h;
@@ -352,23 +370,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     if (a.o_mode == 3) fence_proxy_async_smem();  // the staged tile is read by the tensor core (async proxy) in the chained GEMM
     __syncthreads();
     if (a.c_on) {  // split-K partials: plane = blockIdx.z
-        tile_to_global(sC, a.c, (int64_t)n0 * 4, tr_rows, a.c_row_off, 0, a.kb_per_split ? blockIdx.z : 0, tid);
-        tile_to_global(sC + kTileCBytes / 2, a.c, (int64_t)(n0 + 32) * 4, tr_rows, a.c_row_off, 0, a.kb_per_split ? blockIdx.z : 0, tid);
+#pragma unroll
+        for (int bx = 0; bx < BN / 32; ++bx)
+            tile_to_global<128>(sC + bx * (kTcBM * 128), a.c, (int64_t)(n0 + 32 * bx) * 4, tr_rows, a.c_row_off, 0, a.kb_per_split ? blockIdx.z : 0, tid);
     }
     if (a.o_mode == 1) {
-        tile_to_global(smem + SM::kOffOhi, a.o[0], (int64_t)n0 * 2, tr_rows, a.o_row_off, 0, 0, tid);
-        if (kLo) tile_to_global(smem + SM::kOffOlo, a.o[1], (int64_t)n0 * 2, tr_rows, a.o_row_off, 0, 0, tid);
+        tile_to_global<RB>(smem + SM::kOffOhi, a.o[0], (int64_t)n0 * 2, tr_rows, a.o_row_off, 0, 0, tid);
+        if (kLo) tile_to_global<RB>(smem + SM::kOffOlo, a.o[1], (int64_t)n0 * 2, tr_rows, a.o_row_off, 0, 0, tid);
     } else if (a.o_mode == 2) {  // Q / K: [B][heads][320][64]; V^T: [B][heads][64][320]
         if (o_which < 2) {
-            tile_to_global(smem + SM::kOffOhi, a.o[2 * o_which], 0, tr_rows, 0, o_h, 0, tid);
-            if (kLo) tile_to_global(smem + SM::kOffOlo, a.o[2 * o_which + 1], 0, tr_rows, 0, o_h, 0, tid);
+            tile_to_global<RB>(smem + SM::kOffOhi, a.o[2 * o_which], (int64_t)o_d * 2, tr_rows, 0, o_h, 0, tid);
+            if (kLo) tile_to_global<RB>(smem + SM::kOffOlo, a.o[2 * o_which + 1], (int64_t)o_d * 2, tr_rows, 0, o_h, 0, tid);
         } else {
-            vt_tile_to_global(smem + SM::kOffOhi, a.o[4], tr_rows, o_h, tid);
-            if (kLo) vt_tile_to_global(smem + SM::kOffOlo, a.o[5], tr_rows, o_h, tid);
+            vt_tile_to_global<BN>(smem + SM::kOffOhi, a.o[4], tr_rows, o_h, o_d, tid);
+            if (kLo) vt_tile_to_global<BN>(smem + SM::kOffOlo, a.o[5], tr_rows, o_h, o_d, tid);
         }
     }
     if (tid == 0) tr.mark(7);
-    if (a.chain_n) {
+    if (BN == kChainBN && a.chain_n) {
         // ---- chained GEMM: P_j[128, N2] = hidden tile (just staged as a 128B-swizzled K-major A operand, bf16 hi / lo) x
         // W2[:, n0 .. n0 + 64)^T.  The hidden activations never travel to global memory; the N / 64 partial results P_j of one row
         // tile are summed in a fixed order by reduce_ln_kernel, which also applies bias, residual and the next LayerNorm.
@@ -376,11 +395,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         if (warp == 1 && lane == 0) {
             ok &= mbar_wait(&b2_bar, 0);
             tcgen05_fence_after();
-            const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2);
+            const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2);  // K = the 64 hidden columns of this CTA
             const uint64_t dA = umma_desc_sw128(smem_u32(smem + SM::kOffOhi)), dB = umma_desc_sw128(smem_u32(smem + SM::kOffB2));
             constexpr uint64_t kLoA = kTileOBytes >> 4, kLoB = SM::kB2PartBytes >> 4;
 #pragma unroll
-            for (int k = 0; k < kTcBN / 16; ++k) {
+            for (int k = 0; k < kChainBN / 16; ++k) {
                 umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + 2 * k, idesc2, k != 0);
                 if (kLo) {
                     umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + kLoB + 2 * k, idesc2, 1);
@@ -407,17 +426,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         __syncthreads();
         if (tid == 0) tr.mark(4);
         for (int cb = 0; cb < N2 / 32; ++cb)  // P[j = blockIdx.x][target][row][32 cb ..]
-            tile_to_global(smem + SM::kOffP + cb * (kTcBM * 128), a.p, (int64_t)cb * 128, tr_rows, 0, 0, blockIdx.x, tid);
+            tile_to_global<128>(smem + SM::kOffP + cb * (kTcBM * 128), a.p, (int64_t)cb * 128, tr_rows, 0, 0, blockIdx.x, tid);
     }
     if (a.ln_g) {  // ---- fused LayerNorm over the full row (N columns = cluster of N / 64 CTAs x 4 column groups)
         const uint32_t nct = cluster_nctarank(), me = cluster_ctarank();
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) s += v[j];
-        const float mu = s * (1.f / 16.f);
+        for (int j = 0; j < CPT; ++j) s += v[j];
+        const float mu = s * (1.f / CPT);
         float m2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < CPT; ++j) {
             const float d = v[j] - mu;
             m2 = fmaf(d, d, m2);
         }
@@ -428,9 +447,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         } else {  // N = 64: the row lives in this CTA alone (launched without a cluster: st.async would be an illegal instruction)
             ln_part[0][g][row] = make_float2(s, m2);
         }
-        float gam[16], bet[16];
+        float gam[CPT], bet[CPT];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
+        for (int j = 0; j < CPT; j += 4) {
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.ln_g + nc + j)), b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b + nc + j));
             gam[j] = g4.x, gam[j + 1] = g4.y, gam[j + 2] = g4.z, gam[j + 3] = g4.w;
             bet[j] = b4.x, bet[j + 1] = b4.y, bet[j + 2] = b4.z, bet[j + 3] = b4.w;
@@ -450,17 +469,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
             for (int q = 0; q < kTcColGroups; ++q) {
                 const float2 p = ln_part[r][q][row];
-                const float d = p.x * (1.f / 16.f) - mean;
-                M2 += p.y + 16.f * d * d;
+                const float d = p.x * (1.f / CPT) - mean;
+                M2 += p.y + (float)CPT * d * d;
             }
         const float rstd = 1.f / sqrtf(M2 / (float)a.N + 1e-6f);
-        float y[16];
+        float y[CPT];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) y[j] = (v[j] - mean) * rstd * gam[j] + bet[j];
-        stage_split16(y, smem + SM::kOffLnHi, smem + SM::kOffLnLo, row, g, kLo);
+        for (int j = 0; j < CPT; ++j) y[j] = (v[j] - mean) * rstd * gam[j] + bet[j];
+        stage_split<CPT>(y, smem + SM::kOffLnHi, smem + SM::kOffLnLo, row, g, kLo);
         __syncthreads();
-        tile_to_global(smem + SM::kOffLnHi, a.ln_out[0], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
-        if (kLo) tile_to_global(smem + SM::kOffLnLo, a.ln_out[1], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
+        tile_to_global<RB>(smem + SM::kOffLnHi, a.ln_out[0], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
+        if (kLo) tile_to_global<RB>(smem + SM::kOffLnLo, a.ln_out[1], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
     }
     if (!ok && a.err) atomicExch(a.err, 1);
     tcgen05_fence_before();
@@ -544,6 +563,10 @@ bool tc_resid_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t c
 
 // chained second GEMM of plan p: weights W2 [N2][K2] (K2 = N of the first GEMM), partial results P [N/64][batch][rows][N2] fp32
 bool tc_plan_chain(TcGemmPlan* p, const __nv_bfloat16* W2hi, const __nv_bfloat16* W2lo, int N2, float* P, uint64_t rows, uint64_t batch) {
+    if (p->bn != kChainBN) {
+        set_error("the chained GEMM needs the 64-column tile");
+        return false;
+    }
     if (N2 % 64 || N2 > kMaxChainN) {
         set_error("chained GEMM needs N2 %% 64 == 0 and N2 <= %d (N2=%d)", kMaxChainN, N2);
         return false;
@@ -552,18 +575,19 @@ bool tc_plan_chain(TcGemmPlan* p, const __nv_bfloat16* W2hi, const __nv_bfloat16
     const uint64_t dims[2] = {K2, (uint64_t)N2}, strides[1] = {K2 * 2};
     const uint32_t box[2] = {(uint32_t)kTcBK, (uint32_t)N2};
     bool ok = tc_make_map(&p->maps.B2hi, W2hi, 2, dims, strides, box) && tc_make_map(&p->maps.B2lo, W2lo ? W2lo : W2hi, 2, dims, strides, box);
-    p->args.p = tc_out(P, 4, N2, rows, 1, batch, K2 / kTcBN);
+    p->args.p = tc_out(P, 4, N2, rows, 1, batch, K2 / kChainBN);
     p->args.chain_n = N2, p->args.o_mode = 3;
     return ok;
 }
 
 bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, uint64_t a_rows, const __nv_bfloat16* Whi,
-                  const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch) {
+                  const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch, int bn) {
     memset(p, 0, sizeof(*p));
-    if (N % kTcBN || K % kTcBK || (conv_feat && conv_feat % kTcBK)) {
-        set_error("tcgen05 GEMM needs N %% 64 == 0 and K %% 64 == 0 (N=%d K=%d)", N, K);
+    if ((bn != 32 && bn != 64) || N % bn || K % kTcBK || (conv_feat && conv_feat % kTcBK)) {
+        set_error("tcgen05 GEMM needs a 32- or 64-column tile, N %% tile == 0 and K %% 64 == 0 (N=%d K=%d tile=%d)", N, K, bn);
         return false;
     }
+    p->bn = bn;
     bool ok = true;
     if (conv_feat) {  // A = token grid [batch][16][16][feat]
         const uint64_t dims[4] = {(uint64_t)conv_feat, kMap, kMap, (uint64_t)conv_batch};
@@ -575,8 +599,8 @@ bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* 
         ok &= tc_make_map_2d(&p->maps.Ahi, Ahi, a_rows, K, kTcBM);
         ok &= tc_make_map_2d(&p->maps.Alo, Alo ? Alo : Ahi, a_rows, K, kTcBM);
     }
-    ok &= tc_make_map_2d(&p->maps.Bhi, Whi, N, K, kTcBN);
-    ok &= tc_make_map_2d(&p->maps.Blo, Wlo ? Wlo : Whi, N, K, kTcBN);
+    ok &= tc_make_map_2d(&p->maps.Bhi, Whi, N, K, bn);
+    ok &= tc_make_map_2d(&p->maps.Blo, Wlo ? Wlo : Whi, N, K, bn);
     // unused output maps must still be valid descriptors (they are never dereferenced when their mode is off)
     p->maps.R = p->maps.B2hi = p->maps.B2lo = p->maps.Bhi;
     p->args.N = N, p->args.K = K, p->args.conv_feat = conv_feat;
@@ -585,23 +609,30 @@ bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* 
 }
 
 cudaError_t tc_gemm_setup() {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<1>::kTotal);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<3>::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<1, 64>::kTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<3, 64>::kTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<1, 32>::kTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<3, 32>::kTotal);
+    return e;
 }
 
 cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl) {
     if (M <= 0) return cudaSuccess;
     TcGemmArgs a = p.args;
     a.M = M;
-    const dim3 grid(a.N / kTcBN, (M + kTcBM - 1) / kTcBM, a.kb_per_split ? a.K / kTcBK / a.kb_per_split : 1);
+    const int bn = p.bn;
+    const dim3 grid(a.N / bn, (M + kTcBM - 1) / kTcBM, a.kb_per_split ? a.K / kTcBK / a.kb_per_split : 1);
     int cluster_x = 1;
     if (a.ln_g) {
-        cluster_x = a.N / kTcBN;
+        cluster_x = a.N / bn;
         if (cluster_x > kMaxLnCluster) return cudaErrorInvalidValue;
     }
-    if (nsplit == 3) return launch_ex(gemm_tc_kernel<3>, grid, dim3(kTcThreads), TcSmem<3>::kTotal, s, pdl, cluster_x, p.maps, a);
-    return launch_ex(gemm_tc_kernel<1>, grid, dim3(kTcThreads), TcSmem<1>::kTotal, s, pdl, cluster_x, p.maps, a);
+    if (bn == 64) {
+        if (nsplit == 3) return launch_ex(gemm_tc_kernel<3, 64>, grid, dim3(kTcThreads), TcSmem<3, 64>::kTotal, s, pdl, cluster_x, p.maps, a);
+        return launch_ex(gemm_tc_kernel<1, 64>, grid, dim3(kTcThreads), TcSmem<1, 64>::kTotal, s, pdl, cluster_x, p.maps, a);
+    }
+    if (nsplit == 3) return launch_ex(gemm_tc_kernel<3, 32>, grid, dim3(kTcThreads), TcSmem<3, 32>::kTotal, s, pdl, cluster_x, p.maps, a);
+    return launch_ex(gemm_tc_kernel<1, 32>, grid, dim3(kTcThreads), TcSmem<1, 32>::kTotal, s, pdl, cluster_x, p.maps, a);
 }
 
 // fp32 -> bf16 (hi, lo) split of a dense buffer
@@ -645,7 +676,8 @@ extern "C" vt_status vt_debug_gemm(int32_t device, int32_t M, int32_t N, int32_t
     VT_CUDA(launch_split_bf16(dA, Ahi, Alo, na, 0)); VT_CUDA(launch_split_bf16(dW, Whi, Wlo, nw, 0));
     TcGemmPlan plan;
     vt_status st = VT_OK;
-    if (!tc_plan_init(&plan, Ahi, Alo, M, Whi, Wlo, N, K, 0, 0)) st = VT_ERR_CUDA;
+    const char* tile = getenv("VT_DBG_TILE");  // diagnostics knob: column-tile width 64 (default) or 32
+    if (!tc_plan_init(&plan, Ahi, Alo, M, Whi, Wlo, N, K, 0, 0, tile ? atoi(tile) : 64)) st = VT_ERR_CUDA;
     if (st == VT_OK) {
         plan.args.bias = dB, plan.args.gelu = gelu, plan.args.err = dErr, plan.args.c_on = 1;
         // diagnostics knobs: VT_DBG_PERIOD = rows per target of the output addressing (M must be a multiple), VT_DBG_RESID = C += C0

@@ -255,9 +255,10 @@ struct TcMaps {               // kernel parameter block (__grid_constant__): the
 struct TcGemmPlan {
     TcMaps maps;
     TcGemmArgs args;
+    int bn;                   // column-tile width: 64 (throughput tile; required by the chained GEMM) or 32 (latency tile)
 };
 bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, uint64_t a_rows, const __nv_bfloat16* Whi,
-                  const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch);
+                  const __nv_bfloat16* Wlo, int N, int K, int conv_feat, int conv_batch, int bn = 64);
 bool tc_plan_chain(TcGemmPlan* p, const __nv_bfloat16* W2hi, const __nv_bfloat16* W2lo, int N2, float* P, uint64_t rows, uint64_t batch);
 // dense outputs [planes][batch][heads][rows][cols] (elem_bytes 2 = bf16, 4 = fp32), V^T [batch][heads][64][tokens], and the flat fp32
 // residual source (TMA load)
