@@ -219,11 +219,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = tmem_base_s;
-    if (a.ln_g) cluster_arrive_release();  // "this CTA is running": peers may address its shared memory after the matching wait
+    // cluster handshake ("this CTA is running, its barriers are initialised and armed"): peers may multicast activation tiles into
+    // its shared memory / push LayerNorm partials after the matching wait
+    const bool clustered = a.ln_g != nullptr || a.mcast > 1;
+    if (clustered) cluster_arrive_release();
 
     pdl_wait();               // the activations (A, residual) are complete and visible from here on
     if (tid == 0) tr.mark(2);
     pdl_launch_dependents();  // let the next kernel of the chain run its prologue under our main loop
+    if (clustered) cluster_wait_acquire();
 
     uint8_t* sC = smem + SM::kOffC;
     if (warp == 0) {
@@ -243,6 +247,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     const int b = m0 / kNTx, y0 = (m0 % kNTx) / kMap;
                     tma_load_4d(st, &mp.Ahi, &full_bar[s], d0, tap % 3 - 1, y0 + tap / 3 - 1, b);
                     if (kLo) tma_load_4d(st + kTileABytes, &mp.Alo, &full_bar[s], d0, tap % 3 - 1, y0 + tap / 3 - 1, b);
+                } else if (a.mcast > 1) {
+                    // the a.mcast column-tile CTAs of this cluster share the activation tile: k-block kb is fetched once, by rank kb % mcast,
+                    // and multicast into everybody's stage (each CTA armed its own full barrier with the full stage byte count)
+                    if ((uint32_t)(kb % a.mcast) == cluster_ctarank()) {
+                        const uint16_t mask = (uint16_t)((1u << a.mcast) - 1);
+                        tma_load_2d_mcast(st, &mp.Ahi, &full_bar[s], (kb0 + kb) * kTcBK, m0, mask);
+                        if (kLo) tma_load_2d_mcast(st + kTileABytes, &mp.Alo, &full_bar[s], (kb0 + kb) * kTcBK, m0, mask);
+                    }
                 } else {
                     tma_load_2d(st, &mp.Ahi, &full_bar[s], (kb0 + kb) * kTcBK, m0);
                     if (kLo) tma_load_2d(st + kTileABytes, &mp.Alo, &full_bar[s], (kb0 + kb) * kTcBK, m0);
@@ -440,8 +452,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             const float d = v[j] - mu;
             m2 = fmaf(d, d, m2);
         }
-        const uint32_t mine = smem_u32(&ln_part[me][g][row]), bar = smem_u32(&ln_bar);
-        cluster_wait_acquire();  // every CTA of the cluster has started and initialised its ln_bar (arrive in the prologue)
+        const uint32_t mine = smem_u32(&ln_part[me][g][row]), bar = smem_u32(&ln_bar);  // (peers are known to run: cluster handshake above)
         if (nct > 1) {
             for (uint32_t r = 0; r < nct; ++r) st_async_cluster_f2(cluster_map_shared(mine, r), s, m2, cluster_map_shared(bar, r));
         } else {  // N = 64: the row lives in this CTA alone (launched without a cluster: st.async would be an illegal instruction)
@@ -588,6 +599,7 @@ bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* 
         return false;
     }
     p->bn = bn;
+    p->mcast_ok = getenv("VT_B200_MCAST") != nullptr;  // measured: no gain on one stream, -12 % with 16 streams (profiles/r1d_final.md)
     bool ok = true;
     if (conv_feat) {  // A = token grid [batch][16][16][feat]
         const uint64_t dims[4] = {(uint64_t)conv_feat, kMap, kMap, (uint64_t)conv_batch};
@@ -626,7 +638,17 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t 
     if (a.ln_g) {
         cluster_x = a.N / bn;
         if (cluster_x > kMaxLnCluster) return cudaErrorInvalidValue;
+    } else if (p.mcast_ok) {  // column tiles of one row tile share the activation tile: clusters of 4 / 3 / 2 of them
+        for (int g : {4, 3, 2})
+            if ((a.N / bn) % g == 0) {
+                cluster_x = g;
+                break;
+            }
     }
+    // multicast needs every k-block of a CTA to have its own stage (no ring reuse across CTAs) and plain 2-D activation boxes
+    const int num_kb = a.kb_per_split ? a.kb_per_split : a.K / kTcBK;
+    a.mcast = (p.mcast_ok && cluster_x > 1 && num_kb <= kTcStages && !a.conv_feat) ? cluster_x : 0;
+    if (!a.mcast && !a.ln_g) cluster_x = 1;
     if (bn == 64) {
         if (nsplit == 3) return launch_ex(gemm_tc_kernel<3, 64>, grid, dim3(kTcThreads), TcSmem<3, 64>::kTotal, s, pdl, cluster_x, p.maps, a);
         return launch_ex(gemm_tc_kernel<1, 64>, grid, dim3(kTcThreads), TcSmem<1, 64>::kTotal, s, pdl, cluster_x, p.maps, a);

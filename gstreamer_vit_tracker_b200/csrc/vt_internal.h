@@ -238,6 +238,7 @@ struct TcGemmArgs {
     TcOut c, o[6], ln_out[2], p;
     int o_mode;               // 0 off; 1 bf16 split tile -> o[0] (hi), o[1] (lo); 2 QKV scatter -> o[0..5] = Q, K, V^T (hi, lo);
                               // 3 staged in shared memory only (A operand of the chained GEMM)
+    int mcast;                // set at launch: > 1 = the activation tile is multicast to this many column-tile CTAs of the cluster
     int kb_per_split;         // split-K: 64-wide k-blocks per blockIdx.z slice (0 = no split); the fp32 partial tile of slice z goes to
                               // plane z of c and bias / activations / residual must be off
     int chain_n;              // N2 of a chained second GEMM (0 = off): P[blockIdx.x] = tile x W2[:, n0..n0+64)^T -> p (plane blockIdx.x)
@@ -255,6 +256,7 @@ struct TcMaps {               // kernel parameter block (__grid_constant__): the
 struct TcGemmPlan {
     TcMaps maps;
     TcGemmArgs args;
+    bool mcast_ok;            // TMA multicast of the activation tile across the column-tile CTAs of a cluster may be used
     int bn;                   // column-tile width: 64 (throughput tile; required by the chained GEMM) or 32 (latency tile)
 };
 bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo, uint64_t a_rows, const __nv_bfloat16* Whi,
