@@ -97,6 +97,8 @@ def make_config(weights: str, width: int, height: int, fmt: str = "nv12", max_ta
                 gemm_mode: int = L.VT_GEMM_TCGEN05_BF16X3, debug_capture: bool = False, upload_window: bool = False) -> vt_config:
     cfg = vt_config()
     lib().vt_config_default(C.byref(cfg))
+    if weights.lower().endswith(".onnx"):  # ≙ VitTrack::new(model_path) with the network in its public ONNX form
+        weights = _import_onnx_cached(weights)
     cfg.weights_path = weights.encode()
     cfg.device = device
     cfg.format = {"nv12": L.VT_FMT_NV12, "rgb24": L.VT_FMT_RGB24, "gray8": L.VT_FMT_GRAY8}[fmt]
@@ -108,6 +110,27 @@ def make_config(weights: str, width: int, height: int, fmt: str = "nv12", max_ta
     cfg.debug_capture = int(debug_capture)
     cfg.upload_window = int(upload_window)
     return cfg
+
+
+def _import_onnx_cached(onnx_path: str) -> str:
+    """ONNX model file -> flat VTW1 file next to the system temp dir (keyed by path, size, mtime); see onnx_import.py."""
+    import hashlib
+    import os
+    import tempfile
+
+    from . import onnx_import
+
+    st = os.stat(onnx_path)
+    key = hashlib.sha1(f"{os.path.abspath(onnx_path)}|{st.st_size}|{st.st_mtime_ns}".encode()).hexdigest()[:16]
+    out = os.path.join(tempfile.gettempdir(), "vt_b200_weights", f"onnx_{key}.vtw")
+    if not os.path.exists(out):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        try:
+            onnx_import.import_onnx(onnx_path, out + ".tmp")
+        except onnx_import.OnnxImportError as e:
+            raise VtError(L.VT_ERR_WEIGHTS, f"{onnx_path}: {e}") from None
+        os.replace(out + ".tmp", out)
+    return out
 
 
 # ---- VitTrack ------------------------------------------------------------------------------------
