@@ -2,18 +2,20 @@
 //
 // One CTA (16 softmax warps + 1 control warp) per (128-query tile, head, target):
 //   TMA        Q tile [128 x 64], K [320 x 64] and V^T [64 x 320] (bf16 hi/lo parts, 128B swizzle) -> shared memory
-//   tcgen05    S[128 x 320] = Q K^T  -> TMEM columns 0..319 (two UMMAs per K-step: N = 256 and N = 64)
+//   tcgen05    S[128 x 320] = Q K^T  -> TMEM columns 0..319 (two N = 160 UMMAs per K-step and precision term)
 //   control    warp 16 issues every TMA load and every UMMA (one elected lane) and owns the TMEM allocation, so that no softmax
 //              warp ever serialises MMA issue with its share of the exp work; chunks are handed over through mbarriers
-//              (p_full: one arrival per softmax warp, p_free: tcgen05.commit) — there is no CTA-wide barrier in the chunk loop
+//              (p_full[c]: one arrival per softmax warp) — there is no CTA-wide barrier in the chunk loop
 //   softmax    FOUR threads per query row (warp w reads TMEM lane quarter w % 4; column group g = w / 4): the exp work is what
 //              bounds this kernel, so it is spread over 16 warps.  Per 64-key chunk thread (row, g) owns 16 keys:
-//              tcgen05.ld.x16 -> ex2(s * k - max * k) -> bf16 (hi, lo) split -> 2 x 16 B stores into the 128B-swizzled K-major
-//              P tile (double buffered); row max / row sum partials are combined through shared memory in a fixed order
-//   tcgen05    O[128 x 64] += P_chunk V_chunk -> TMEM columns 320..383 (+ 384..447 for the hi*lo term), overlapped with the next
-//              chunk's softmax
+//              tcgen05.ld.x16 -> ex2(s * k - max * k) -> bf16 (hi, lo) split -> tcgen05.st of the packed pairs back into the thread's
+//              OWN 16 S columns (8 columns P_hi, 8 columns P_lo): P never leaves tensor memory; row max / row sum partials are
+//              combined through shared memory in a fixed order
+//   tcgen05    O[128 x 64] += P_chunk V_chunk with the A operand (P) read from TMEM, so each UMMA fetches only V from shared memory
+//              (the smem-operand form was fetch bound: 0.39 us per chunk, longer than the chunk's softmax) -> TMEM columns 320..383
+//              (+ 384..447 for the hi*lo term), overlapped with the next chunk's softmax
 //   epilogue   O / sum -> bf16 (hi, lo) tile staged in shared memory -> coalesced 16-byte stores into the proj GEMM's A operand.
-// The P buffers alias the Q/K staging area once S is complete, which keeps the CTA at ~192 KB of shared memory.
+// The output staging tile aliases the Q/K area once S is complete (~192 KB of shared memory per CTA).
 #include "tc_common.cuh"
 #include "vt_internal.h"
 
@@ -40,7 +42,7 @@ template <int NSPLIT>
 struct AttSmem {
     static constexpr int kParts = NSPLIT == 3 ? 2 : 1;
     static constexpr int kQK = kParts * (kQBytes + kKBytes);
-    static constexpr int kP = 2 * kParts * kPBytes;
+    static constexpr int kP = kParts * kPBytes;  // output staging tile
     static constexpr int kRegion1 = kQK > kP ? kQK : kP;
     static constexpr int kV = kParts * kVBytes;
     static constexpr int kTotal = kRegion1 + kV + 1024;
@@ -55,7 +57,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
                     int heads, int* err, unsigned long long* trace) {
     const CUtensorMap &mQhi = mp.mQhi, &mQlo = mp.mQlo, &mKhi = mp.mKhi, &mKlo = mp.mKlo, &mVhi = mp.mVhi, &mVlo = mp.mVlo;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_qk, bar_v, bar_s, p_full[2], p_free[2], bar_o;
+    __shared__ __align__(8) uint64_t bar_qk, bar_k1, bar_v, bar_s, p_full[kNChunks], bar_o;
     __shared__ uint32_t tmem_base_s;
     __shared__ float red[kColGroups][kQTile];  // row-max partials, then row-sum partials
     __shared__ unsigned long long* trace_slot;
@@ -64,7 +66,6 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                       // [P][128 x 128B]
     uint8_t* sK = smem + P * kQBytes;         // [P][320 x 128B]
-    uint8_t* sP = smem;                       // [2 bufs][P][128 x 128B], aliases Q/K after S is complete
     uint8_t* sV = smem + SM::kRegion1;        // [P][5 blocks][64 x 128B]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -79,8 +80,8 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
     tr.begin(&trace_slot, trace, 10);
 
     if (tid == 0) {
-        mbar_init(&bar_qk, 1), mbar_init(&bar_v, 1), mbar_init(&bar_s, 1), mbar_init(&bar_o, 1);
-        mbar_init(&p_full[0], kSoftmaxWarps), mbar_init(&p_full[1], kSoftmaxWarps), mbar_init(&p_free[0], 1), mbar_init(&p_free[1], 1);
+        mbar_init(&bar_qk, 1), mbar_init(&bar_k1, 1), mbar_init(&bar_v, 1), mbar_init(&bar_s, 1), mbar_init(&bar_o, 1);
+        for (int c = 0; c < kNChunks; ++c) mbar_init(&p_full[c], kSoftmaxWarps);
         fence_barrier_init();
     }
     if (ctrl) {
@@ -102,14 +103,16 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
 
     if (ctrl) {
         if (lane == 0) {
-            // ---- TMA: Q + K on one barrier, V^T on another (only needed after the softmax of the first chunk)
-            mbar_arrive_expect_tx(&bar_qk, P * (kQBytes + kKBytes));
+            // ---- TMA: Q + the first 160 keys on one barrier, the other 160 keys on a second (their UMMAs start while the first half
+            // computes), V^T on a third (only needed after the softmax of the first chunk)
+            constexpr int kHalfK = kNTok / 2, kHalfKBytes = kHalfK * kDh * 2;
+            mbar_arrive_expect_tx(&bar_qk, P * (kQBytes + kHalfKBytes));
             tma_load_3d(sQ, &mQhi, &bar_qk, 0, q0, bh);
-            if (P == 2) tma_load_3d(sQ + kQBytes, &mQlo, &bar_qk, 0, q0, bh);
-            for (int c = 0; c < kNChunks; ++c) {
-                tma_load_3d(sK + c * kKeyChunk * 128, &mKhi, &bar_qk, 0, c * kKeyChunk, bh);
-                if (P == 2) tma_load_3d(sK + kKBytes + c * kKeyChunk * 128, &mKlo, &bar_qk, 0, c * kKeyChunk, bh);
-            }
+            tma_load_3d(sK, &mKhi, &bar_qk, 0, 0, bh);
+            if (P == 2) tma_load_3d(sQ + kQBytes, &mQlo, &bar_qk, 0, q0, bh), tma_load_3d(sK + kKBytes, &mKlo, &bar_qk, 0, 0, bh);
+            mbar_arrive_expect_tx(&bar_k1, P * kHalfKBytes);
+            tma_load_3d(sK + kHalfKBytes, &mKhi, &bar_k1, 0, kHalfK, bh);
+            if (P == 2) tma_load_3d(sK + kKBytes + kHalfKBytes, &mKlo, &bar_k1, 0, kHalfK, bh);
             mbar_arrive_expect_tx(&bar_v, P * kVBytes);
             for (int c = 0; c < kNChunks; ++c) {  // per key chunk: [V^T hi 64 x 128 B][V^T lo 64 x 128 B], adjacent = one N = 128 B operand
                 tma_load_3d(sV + c * (P * kDh * 128), &mVhi, &bar_v, c * kKeyChunk, 0, bh);
@@ -119,43 +122,48 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
             ok &= mbar_wait(&bar_qk, 0);
             tcgen05_fence_after();
             const uint64_t dQ = umma_desc_sw128(smem_u32(sQ)), dK = umma_desc_sw128(smem_u32(sK));
-            constexpr uint32_t idesc256 = umma_idesc_bf16(kQTile, 256), idesc64 = umma_idesc_bf16(kQTile, 64);
-            constexpr uint64_t kLoQ = kQBytes >> 4, kLoK = kKBytes >> 4, kK256 = (256 * 128) >> 4;  // descriptor address units (16 B)
+            constexpr int kHalf = kNTok / 2;  // 160 keys per UMMA: two equal N = 160 instructions instead of N = 256 + a fetch-bound N = 64
+            constexpr uint32_t idescS = umma_idesc_bf16(kQTile, kHalf);
+            constexpr uint64_t kLoQ = kQBytes >> 4, kLoK = kKBytes >> 4, kK2 = (kHalf * 128) >> 4;  // descriptor address units (16 B)
 #pragma unroll
-            for (int k = 0; k < kDh / 16; ++k) {
-                const uint64_t qh = dQ + 2 * k, kh0 = dK + 2 * k, kh1 = kh0 + kK256;
-                umma_bf16(tmem, qh, kh0, idesc256, k != 0);
-                umma_bf16(tmem + 256, qh, kh1, idesc64, k != 0);
-                if (NSPLIT == 3) {
-                    umma_bf16(tmem, qh, kh0 + kLoK, idesc256, 1);
-                    umma_bf16(tmem + 256, qh, kh1 + kLoK, idesc64, 1);
-                    umma_bf16(tmem, qh + kLoQ, kh0, idesc256, 1);
-                    umma_bf16(tmem + 256, qh + kLoQ, kh1, idesc64, 1);
+            for (int half = 0; half < 2; ++half) {
+                if (half) {
+                    ok &= mbar_wait(&bar_k1, 0);
+                    tcgen05_fence_after();
+                }
+#pragma unroll
+                for (int k = 0; k < kDh / 16; ++k) {
+                    const uint64_t qh = dQ + 2 * k, kh = dK + 2 * k + half * kK2;
+                    umma_bf16(tmem + half * kHalf, qh, kh, idescS, k != 0);
+                    if (NSPLIT == 3) {
+                        umma_bf16(tmem + half * kHalf, qh, kh + kLoK, idescS, 1);
+                        umma_bf16(tmem + half * kHalf, qh + kLoQ, kh, idescS, 1);
+                    }
                 }
             }
             umma_commit(&bar_s);
             // ---- O += P_c V_c as the softmax warps hand the chunks over
-            const uint64_t dP = umma_desc_sw128(smem_u32(sP)), dV = umma_desc_sw128(smem_u32(sV));
-            // bf16x3 as P_hi x [V_hi; V_lo] (ONE N = 128 UMMA into O columns [0, 64) = hi*hi and [64, 128) = hi*lo) + P_lo x V_hi: the
-            // small-N UMMA is operand-fetch bound, 14 KB instead of 18 KB per K-step; the epilogue adds the two column halves
+            const uint64_t dV = umma_desc_sw128(smem_u32(sV));
+            // bf16x3 as P_hi x [V_hi; V_lo] (ONE N = 128 UMMA into O columns [0, 64) = hi*hi and [64, 128) = hi*lo) + P_lo x V_hi; the epilogue
+            // adds the two column halves.  K-step k of chunk c = the 16 keys of softmax column group k: P_hi in TMEM columns
+            // 64 c + 16 k .. + 7, P_lo in the next 8 (two bf16 per column).
             constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kDh), idesc2n = umma_idesc_bf16(kQTile, 2 * kDh);
-            constexpr uint64_t kLoP = kPBytes >> 4, kBufP = (uint64_t)(P * kPBytes) >> 4, kBlkV = (uint64_t)(P * kDh * 128) >> 4;
+            constexpr uint64_t kBlkV = (uint64_t)(P * kDh * 128) >> 4;
             ok &= mbar_wait(&bar_v, 0);
             for (int c = 0; c < kNChunks; ++c) {
-                const int buf = c & 1;
-                ok &= mbar_wait(&p_full[buf], (c >> 1) & 1);
+                ok &= mbar_wait(&p_full[c], 0);
                 tcgen05_fence_after();
 #pragma unroll
                 for (int k = 0; k < kKeyChunk / 16; ++k) {
-                    const uint64_t ph = dP + buf * kBufP + 2 * k, vh = dV + c * kBlkV + 2 * k;
+                    const uint32_t ph = tmem + c * kKeyChunk + k * kKeysPerThread;
+                    const uint64_t vh = dV + c * kBlkV + 2 * k;
                     if (NSPLIT == 3) {
-                        umma_bf16(tmem + kColO, ph, vh, idesc2n, (c | k) != 0);
-                        umma_bf16(tmem + kColO, ph + kLoP, vh, idesc, 1);
+                        umma_bf16_ta(tmem + kColO, ph, vh, idesc2n, (c | k) != 0);
+                        umma_bf16_ta(tmem + kColO, ph + 8, vh, idesc, 1);
                     } else {
-                        umma_bf16(tmem + kColO, ph, vh, idesc, (c | k) != 0);
+                        umma_bf16_ta(tmem + kColO, ph, vh, idesc, (c | k) != 0);
                     }
                 }
-                umma_commit(&p_free[buf]);
             }
             umma_commit(&bar_o);
         }
@@ -168,47 +176,48 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const float k2 = 1.4426950408889634f / sqrtf((float)kDh);  // scale * log2(e)
         float mx = -INFINITY;
+        const uint32_t col0 = lane_addr + g * kKeysPerThread;
+        uint32_t r[2][16];  // software pipeline over the key chunks: the TMEM load of chunk c + 1 is in flight while chunk c is processed
         if (q_ok) {
+            tmem_ld_32x16_issue(col0, r[0]);
 #pragma unroll
             for (int c = 0; c < kNChunks; ++c) {
-                float v[16];
-                tmem_ld_32x16(lane_addr + c * kKeyChunk + g * kKeysPerThread, v);
+                tmem_ld_wait(r[c & 1]);
+                if (c + 1 < kNChunks) tmem_ld_32x16_issue(col0 + (c + 1) * kKeyChunk, r[(c + 1) & 1]);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j]);
+                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[c & 1][j]));
             }
+            tmem_ld_32x16_issue(col0, r[0]);  // chunk 0 again, for the exp pass: in flight across the row-max exchange
         }
         red[g][row] = mx;
-        softmax_bar_sync();  // also: every softmax thread has finished reading Q/K-phase data before P overwrites that memory
+        softmax_bar_sync();
         mx = fmaxf(fmaxf(red[0][row], red[1][row]), fmaxf(red[2][row], red[3][row]));
         if (tid == 0) tr.mark(5);
         const float mk = mx * k2;
         float sum = 0.f;
+#pragma unroll
         for (int c = 0; c < kNChunks; ++c) {
-            const int buf = c & 1;
-            if (c >= 2) ok &= mbar_wait(&p_free[buf], ((c >> 1) - 1) & 1);  // the UMMAs that read this buffer are done
+            uint32_t hi[8], lo[8];
             if (q_ok) {
-                float v[16];
-                tmem_ld_32x16(lane_addr + c * kKeyChunk + g * kKeysPerThread, v);
-                uint32_t hi[8], lo[8];
+                tmem_ld_wait(r[c & 1]);
+                if (c + 1 < kNChunks) tmem_ld_32x16_issue(col0 + (c + 1) * kKeyChunk, r[(c + 1) & 1]);
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
-                    const float e0 = ex2_approx(fmaf(v[j], k2, -mk)), e1 = ex2_approx(fmaf(v[j + 1], k2, -mk));
+                    const float e0 = ex2_approx(fmaf(__uint_as_float(r[c & 1][j]), k2, -mk));
+                    const float e1 = ex2_approx(fmaf(__uint_as_float(r[c & 1][j + 1]), k2, -mk));
                     sum += e0;
                     sum += e1;
                     split2_bf16(e0, e1, hi[j >> 1], lo[j >> 1]);
                 }
-                uint8_t* pb = sP + buf * (P * kPBytes) + row * 128;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {  // 16-byte chunk index within the 128-byte row, XOR-swizzled with the row (Swizzle<3,4,3>)
-                    const int off = (((2 * g + j) ^ (row & 7)) << 4);
-                    *reinterpret_cast<uint4*>(pb + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                    if (P == 2) *reinterpret_cast<uint4*>(pb + kPBytes + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                }
             }
-            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+            if (q_ok) {  // P replaces the S values this thread has just consumed: columns [0, 8) of its 16 hold P_hi, [8, 16) P_lo
+                tmem_st_32x8(col0 + c * kKeyChunk, hi);
+                if (P == 2) tmem_st_32x8(col0 + c * kKeyChunk + 8, lo);
+                tmem_st_wait();
+            }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[buf]);  // one arrival per softmax warp: no CTA-wide barrier in this loop
+            if (lane == 0) mbar_arrive(&p_full[c]);  // one arrival per softmax warp: no CTA-wide barrier in this loop
             if (tid == 0 && c == 0) tr.mark(6);
         }
         if (tid == 0) tr.mark(7);
@@ -271,7 +280,7 @@ bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const 
     (void)batch;
     {   // Q, K: [batch*heads][320][64], box {64, rows, 1}
         const uint64_t dims[3] = {kDh, kNTok, (uint64_t)batch_heads}, strides[2] = {kDh * 2, (uint64_t)kDh * 2 * kNTok};
-        const uint32_t boxq[3] = {kDh, kQTile, 1}, boxk[3] = {kDh, kKeyChunk, 1};
+        const uint32_t boxq[3] = {kDh, kQTile, 1}, boxk[3] = {kDh, kNTok / 2, 1};  // K: two boxes of 160 keys
         ok &= tc_make_map(&p->mQhi, Qhi, 3, dims, strides, boxq) && tc_make_map(&p->mQlo, Qlo, 3, dims, strides, boxq);
         ok &= tc_make_map(&p->mKhi, Khi, 3, dims, strides, boxk) && tc_make_map(&p->mKlo, Klo, 3, dims, strides, boxk);
     }
