@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages], accum_bar, resid_bar, b2_bar, accum2_bar, ln_bar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float2 ln_part[kMaxLnCluster][kTcColGroups][kTcBM];
+    __shared__ float2 ln_loc[kTcColGroups][kTcBM];   // (sum, M2) of the CPT columns of thread (row, g)
+    __shared__ float2 ln_part[kMaxLnCluster][kTcBM];  // (sum, M2) of the BN columns of every CTA of the cluster, per row
     __shared__ unsigned long long* trace_slot;
     using SM = TcSmem<NSPLIT, BN>;
     constexpr int CPT = BN / kTcColGroups;   // accumulator columns per thread: 16 / 8
@@ -179,10 +180,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kTcBM;
     // split-K over blockIdx.z: this CTA contracts k-blocks [kb0, kb0 + num_kb) and stores its fp32 partial tile to C[.., z]
     const int num_kb = a.kb_per_split ? a.kb_per_split : a.K / kTcBK;
-    const int kb0 = blockIdx.z * num_kb;
+    const int kb0 = a.kb_per_split ? blockIdx.z * num_kb : 0;
+    // "spread" form (latency mode, idle SMs available): blockIdx.z replicates the FC1 tile and replica z computes and stores columns
+    // [64 z, 64 z + 64) of the chained product — a CTA's egress (~26 B/clk/SM) is what bounds the 96 KB partial-tile epilogue.
+    const bool sliced = a.chain_slices > 1;
+    const int N2 = sliced ? a.chain_n / a.chain_slices : a.chain_n;   // chained columns of this CTA
+    const int acc2_cols = (sliced && kLo) ? 2 * N2 : N2;              // sliced + bf16x3: hi*lo term in a second column half
+    const bool do_ln = a.ln_g != nullptr, do_c = a.c_on;
     const int npre = num_kb < kTcStages ? num_kb : kTcStages;
     constexpr uint32_t kAcc1Cols = kLo ? 2 * BN : BN;  // bf16x3 keeps hi*lo in a second column half
-    const uint32_t tmem_cols = a.chain_n == 0 ? (kAcc1Cols < 32 ? 32 : kAcc1Cols) : (kAcc1Cols + a.chain_n <= 128 ? 128 : (kAcc1Cols + a.chain_n <= 256 ? 256 : 512));
+    const uint32_t tmem_cols = a.chain_n == 0 ? (kAcc1Cols < 32 ? 32 : kAcc1Cols) : (kAcc1Cols + acc2_cols <= 128 ? 128 : (kAcc1Cols + acc2_cols <= 256 ? 256 : 512));
     bool ok = true;
     TraceRec tr;
     tr.begin(&trace_slot, a.trace, a.trace_id);
@@ -194,8 +201,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         for (int s = 0; s < kTcStages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
         mbar_init(&accum_bar, 1), mbar_init(&resid_bar, 1), mbar_init(&b2_bar, 1), mbar_init(&accum2_bar, 1), mbar_init(&ln_bar, 1);
         fence_barrier_init();
-        // LayerNorm exchange: every thread of every CTA of the cluster (this one included) sends one float2 into ln_part of this CTA
-        if (a.ln_g && cluster_nctarank() > 1) mbar_arrive_expect_tx(&ln_bar, cluster_nctarank() * kTcThreads * (uint32_t)sizeof(float2));
+        // LayerNorm exchange: every CTA of the cluster (this one included) sends one float2 per row into ln_part of this CTA
+        if (do_ln && cluster_nctarank() > 1) mbar_arrive_expect_tx(&ln_bar, cluster_nctarank() * kTcBM * (uint32_t)sizeof(float2));
         // the weights never depend on the preceding kernel: start streaming them right away
         for (int kb = 0; kb < npre; ++kb) {
             uint8_t* sb = smem + kb * SM::kStageBytes + SM::kParts * kTileABytes;
@@ -203,11 +210,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             tma_load_2d(sb, &mp.Bhi, &full_bar[kb], (kb0 + kb) * kTcBK, n0);
             if (kLo) tma_load_2d(sb + kTileBBytes, &mp.Blo, &full_bar[kb], (kb0 + kb) * kTcBK, n0);
         }
-        if (a.chain_n) {  // weight slice of the chained GEMM: W2[0..N2)[n0 .. n0 + 64), one box per precision part
+        if (a.chain_n) {  // weight slice of the chained GEMM: W2[rows of this CTA][n0 .. n0 + 64), 64-row boxes per precision part
             tma_prefetch_desc(&mp.B2hi);
-            mbar_arrive_expect_tx(&b2_bar, SM::kParts * a.chain_n * 128);
-            tma_load_2d(smem + SM::kOffB2, &mp.B2hi, &b2_bar, n0, 0);
-            if (kLo) tma_load_2d(smem + SM::kOffB2 + SM::kB2PartBytes, &mp.B2lo, &b2_bar, n0, 0);
+            mbar_arrive_expect_tx(&b2_bar, SM::kParts * N2 * 128);
+            if (sliced) {  // [W2_hi slice; W2_lo slice] adjacent: one N = 128 B operand
+                tma_load_2d(smem + SM::kOffB2, &mp.B2hi, &b2_bar, n0, blockIdx.z * N2);
+                if (kLo) tma_load_2d(smem + SM::kOffB2 + N2 * 128, &mp.B2lo, &b2_bar, n0, blockIdx.z * N2);
+            } else {
+                for (int r = 0; r < N2; r += 64) {
+                    tma_load_2d(smem + SM::kOffB2 + r * 128, &mp.B2hi, &b2_bar, n0, r);
+                    if (kLo) tma_load_2d(smem + SM::kOffB2 + SM::kB2PartBytes + r * 128, &mp.B2lo, &b2_bar, n0, r);
+                }
+            }
         }
         if (a.residual) tma_prefetch_desc(&mp.R);
     }
@@ -356,9 +370,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             v[4 * q] += r4.x, v[4 * q + 1] += r4.y, v[4 * q + 2] += r4.z, v[4 * q + 3] += r4.w;
         }
     }
+    if (do_ln) {  // row statistics of this thread's CPT columns; combined per row after the staging barrier below
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) s += v[j];
+        const float mu = s * (1.f / CPT);
+        float m2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const float d = v[j] - mu;
+            m2 = fmaf(d, d, m2);
+        }
+        ln_loc[g][row] = make_float2(s, m2);
+    }
     if (tid == 0) tr.mark(4);
     // ---- stage the output tiles in shared memory (the pipeline ring is dead: every MMA has completed)
-    if (a.c_on) {
+    if (do_c) {
 #pragma unroll
         for (int q = 0; q < CPT / 4; ++q)
             *reinterpret_cast<float4*>(c_row + (((c_chunk0 + q) ^ sw) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -381,7 +408,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     }
     if (a.o_mode == 3) fence_proxy_async_smem();  // the staged tile is read by the tensor core (async proxy) in the chained GEMM
     __syncthreads();
-    if (a.c_on) {  // split-K partials: plane = blockIdx.z
+    if (do_ln && g == 0) {  // one thread per row: (sum, M2) over the BN columns of this CTA (Chan), sent to every CTA of the cluster
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < kTcColGroups; ++q) s += ln_loc[q][row].x;
+        const float mu = s * (1.f / BN);
+        float m2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < kTcColGroups; ++q) {
+            const float2 p = ln_loc[q][row];
+            const float d = p.x * (1.f / CPT) - mu;
+            m2 += p.y + (float)CPT * d * d;
+        }
+        if (cluster_nctarank() > 1) {
+            const uint32_t mine = smem_u32(&ln_part[cluster_ctarank()][row]), bar = smem_u32(&ln_bar);  // (peers are known to run: cluster handshake above)
+            for (uint32_t r = 0; r < cluster_nctarank(); ++r) st_async_cluster_f2(cluster_map_shared(mine, r), s, m2, cluster_map_shared(bar, r));
+        } else {  // N = BN: the row lives in this CTA alone (launched without a cluster: st.async would be an illegal instruction)
+            ln_part[0][row] = make_float2(s, m2);
+        }
+    }
+    if (do_c) {  // split-K partials: plane = blockIdx.z
 #pragma unroll
         for (int bx = 0; bx < BN / 32; ++bx)
             tile_to_global<128>(sC + bx * (kTcBM * 128), a.c, (int64_t)(n0 + 32 * bx) * 4, tr_rows, a.c_row_off, 0, a.kb_per_split ? blockIdx.z : 0, tid);
@@ -403,19 +449,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         // ---- chained GEMM: P_j[128, N2] = hidden tile (just staged as a 128B-swizzled K-major A operand, bf16 hi / lo) x
         // W2[:, n0 .. n0 + 64)^T.  The hidden activations never travel to global memory; the N / 64 partial results P_j of one row
         // tile are summed in a fixed order by reduce_ln_kernel, which also applies bias, residual and the next LayerNorm.
-        const int N2 = a.chain_n;
         if (warp == 1 && lane == 0) {
             ok &= mbar_wait(&b2_bar, 0);
             tcgen05_fence_after();
-            const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2);  // K = the 64 hidden columns of this CTA
             const uint64_t dA = umma_desc_sw128(smem_u32(smem + SM::kOffOhi)), dB = umma_desc_sw128(smem_u32(smem + SM::kOffB2));
             constexpr uint64_t kLoA = kTileOBytes >> 4, kLoB = SM::kB2PartBytes >> 4;
+            if (sliced && kLo) {  // H_hi x [W2_hi; W2_lo] as one UMMA of 2 N2 columns + H_lo x W2_hi (the epilogue adds the halves)
+                const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2), idesc2n = umma_idesc_bf16(kTcBM, 2 * N2);
 #pragma unroll
-            for (int k = 0; k < kChainBN / 16; ++k) {
-                umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + 2 * k, idesc2, k != 0);
-                if (kLo) {
-                    umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + kLoB + 2 * k, idesc2, 1);
+                for (int k = 0; k < kChainBN / 16; ++k) {
+                    umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + 2 * k, idesc2n, k != 0);
                     umma_bf16(tmem + kAcc1Cols, dA + kLoA + 2 * k, dB + 2 * k, idesc2, 1);
+                }
+            } else {
+                const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2);  // K = the 64 hidden columns of this CTA
+#pragma unroll
+                for (int k = 0; k < kChainBN / 16; ++k) {
+                    umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + 2 * k, idesc2, k != 0);
+                    if (kLo) {
+                        umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + kLoB + 2 * k, idesc2, 1);
+                        umma_bf16(tmem + kAcc1Cols, dA + kLoA + 2 * k, dB + 2 * k, idesc2, 1);
+                    }
                 }
             }
             umma_commit(&accum2_bar);
@@ -429,6 +483,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         for (int c = g * cols_per; c < (g + 1) * cols_per; c += 16) {
             float p[16];
             tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kAcc1Cols + c, p);
+            if (sliced && kLo) {
+                float hl[16];
+                tmem_ld_32x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kAcc1Cols + N2 + c, hl);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) p[j] += hl[j];
+            }
             uint8_t* prow = smem + SM::kOffP + (c >> 5) * (kTcBM * 128) + row * 128;
             const int ch0 = (c & 31) >> 2;
 #pragma unroll
@@ -438,26 +498,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         __syncthreads();
         if (tid == 0) tr.mark(4);
         for (int cb = 0; cb < N2 / 32; ++cb)  // P[j = blockIdx.x][target][row][32 cb ..]
-            tile_to_global<128>(smem + SM::kOffP + cb * (kTcBM * 128), a.p, (int64_t)cb * 128, tr_rows, 0, 0, blockIdx.x, tid);
+            tile_to_global<128>(smem + SM::kOffP + cb * (kTcBM * 128), a.p, (int64_t)cb * 128 + (sliced ? (int64_t)blockIdx.z * N2 * 4 : 0), tr_rows, 0, 0,
+                                blockIdx.x, tid);
     }
-    if (a.ln_g) {  // ---- fused LayerNorm over the full row (N columns = cluster of N / 64 CTAs x 4 column groups)
-        const uint32_t nct = cluster_nctarank(), me = cluster_ctarank();
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) s += v[j];
-        const float mu = s * (1.f / CPT);
-        float m2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-            const float d = v[j] - mu;
-            m2 = fmaf(d, d, m2);
-        }
-        const uint32_t mine = smem_u32(&ln_part[me][g][row]), bar = smem_u32(&ln_bar);  // (peers are known to run: cluster handshake above)
-        if (nct > 1) {
-            for (uint32_t r = 0; r < nct; ++r) st_async_cluster_f2(cluster_map_shared(mine, r), s, m2, cluster_map_shared(bar, r));
-        } else {  // N = 64: the row lives in this CTA alone (launched without a cluster: st.async would be an illegal instruction)
-            ln_part[0][g][row] = make_float2(s, m2);
-        }
+    if (do_ln) {  // ---- fused LayerNorm over the full row (N columns = cluster of N / BN CTAs)
+        const uint32_t nct = cluster_nctarank();
         float gam[CPT], bet[CPT];
 #pragma unroll
         for (int j = 0; j < CPT; j += 4) {
@@ -471,18 +516,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         else __syncthreads();
         if (tid == 0) tr.mark(5);
         float tot = 0.f;
-        for (uint32_t r = 0; r < nct; ++r)
-#pragma unroll
-            for (int q = 0; q < kTcColGroups; ++q) tot += ln_part[r][q][row].x;
+        for (uint32_t r = 0; r < nct; ++r) tot += ln_part[r][row].x;
         const float mean = tot / (float)a.N;
         float M2 = 0.f;
-        for (uint32_t r = 0; r < nct; ++r)
-#pragma unroll
-            for (int q = 0; q < kTcColGroups; ++q) {
-                const float2 p = ln_part[r][q][row];
-                const float d = p.x * (1.f / CPT) - mean;
-                M2 += p.y + (float)CPT * d * d;
-            }
+        for (uint32_t r = 0; r < nct; ++r) {
+            const float2 p = ln_part[r][row];
+            const float d = p.x * (1.f / BN) - mean;
+            M2 += p.y + (float)BN * d * d;
+        }
         const float rstd = 1.f / sqrtf(M2 / (float)a.N + 1e-6f);
         float y[CPT];
 #pragma unroll
@@ -584,7 +625,7 @@ bool tc_plan_chain(TcGemmPlan* p, const __nv_bfloat16* W2hi, const __nv_bfloat16
     }
     const uint64_t K2 = (uint64_t)p->args.N;
     const uint64_t dims[2] = {K2, (uint64_t)N2}, strides[1] = {K2 * 2};
-    const uint32_t box[2] = {(uint32_t)kTcBK, (uint32_t)N2};
+    const uint32_t box[2] = {(uint32_t)kTcBK, 64};  // loaded as 64-row boxes (a CTA of the sliced form takes one of them)
     bool ok = tc_make_map(&p->maps.B2hi, W2hi, 2, dims, strides, box) && tc_make_map(&p->maps.B2lo, W2lo ? W2lo : W2hi, 2, dims, strides, box);
     p->args.p = tc_out(P, 4, N2, rows, 1, batch, K2 / kChainBN);
     p->args.chain_n = N2, p->args.o_mode = 3;
@@ -628,12 +669,15 @@ cudaError_t tc_gemm_setup() {
     return e;
 }
 
-cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl) {
+cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl, bool spread) {
     if (M <= 0) return cudaSuccess;
     TcGemmArgs a = p.args;
     a.M = M;
     const int bn = p.bn;
-    const dim3 grid(a.N / bn, (M + kTcBM - 1) / kTcBM, a.kb_per_split ? a.K / kTcBK / a.kb_per_split : 1);
+    dim3 grid(a.N / bn, (M + kTcBM - 1) / kTcBM, a.kb_per_split ? a.K / kTcBK / a.kb_per_split : 1);
+    a.chain_slices = 0;
+    // latency mode: replicate the FC1 tiles over idle SMs, each replica computes and stores one 64-column slice of the chained product
+    if (spread && !a.kb_per_split && a.chain_n && a.chain_n % (3 * 64) == 0 && grid.x * grid.y * 3 <= (unsigned)kSpreadCtas) a.chain_slices = 3, grid.z = 3;
     int cluster_x = 1;
     if (a.ln_g) {
         cluster_x = a.N / bn;

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -56,6 +57,11 @@ struct WeightSet {
     }
 };
 static std::mutex g_weight_mutex;
+// Live tracker handles per device.  With one or two streams on a GPU most SMs idle during a frame, and the "spread" GEMM forms trade
+// them for latency (tiles replicated so that each replica stores a share of the epilogue output); with more streams SM time is the
+// budget and the plain forms are used.  Read at every frame: the graph variant follows the handle count.
+constexpr int kMaxDevices = 64, kSpreadMaxHandles = 2;
+static std::atomic<int> g_live_handles[kMaxDevices];
 static std::map<std::string, std::weak_ptr<WeightSet>> g_weight_cache;
 
 enum { EV_START = 0, EV_H2D, EV_PRE, EV_VIT, EV_DEC, EV_OVL, EV_END, EV_COUNT };
@@ -128,6 +134,8 @@ struct vt_tracker {
     float *Phead = nullptr, *d_cand = nullptr;  // [9 taps][B][256][head_ch] conv partials; [B][16][8] row candidates of the decode
     unsigned* d_counters = nullptr;
     bool pdl = true;            // programmatic dependent launch along the kernel chain
+    bool spread_ok = true;      // latency-mode GEMM forms allowed (VT_B200_NO_SPREAD disables)
+    bool counted = false;       // this handle is included in g_live_handles
     bool tc_attention = false;  // head_dim == 64
     TcAttentionPlan plan_att;
     int* d_tc_err = nullptr;
@@ -292,7 +300,7 @@ static GemmArgs gemm_args(const float* A, int64_t lda, const float* W, const flo
     } while (0)
 
 // Enqueues crop -> ViT -> decode (-> box overlay) for the n active targets on t->stream.
-static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool record_events, bool capturing) {
+static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool record_events, bool capturing, bool spread) {
     const int D = t->D, Hd = t->hidden, C = t->head_ch;
     (void)record_events, (void)capturing;  // stage times come from device stamps (ST_*), not from event nodes
     cudaStream_t s = t->stream;
@@ -371,9 +379,9 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                 VT_LAUNCH(tc_attention_launch(t->plan_att, n, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace));
             else
                 VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
-            VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention));  // fused: + LN2
+            VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention, spread));  // fused: + LN2
             if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
-            VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s, pdl));  // chained: + the FC2 partial products of its 64 hidden columns
+            VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s, pdl, spread && t->chain_mlp));  // chained: + the FC2 partial products of its 64 hidden columns
             if (t->chain_mlp) {  // X += fc2_b + sum of the partials; LN1 of the next block / the final LN of the search rows
                 const bool last = l + 1 == t->depth;
                 ReduceLnArgs r{};
@@ -407,18 +415,20 @@ static vt_status run_forward(vt_tracker* t) {
     const int n = (int)t->active.size();
     if (n == 0) return VT_OK;
     int launches = 0;
+    const int dev = t->cfg.device;
+    const bool spread = t->spread_ok && dev >= 0 && dev < kMaxDevices && g_live_handles[dev].load(std::memory_order_relaxed) <= kSpreadMaxHandles;
     if (!t->cfg.use_cuda_graph || t->debug_capture) {
-        vt_status st = enqueue_forward(t, n, launches, true, false);
+        vt_status st = enqueue_forward(t, n, launches, true, false, spread);
         t->kernel_launches += launches;
         t->kernels_per_frame = launches;
         return st;
     }
-    const int key = n * 2 + (t->frame_valid ? 1 : 0);  // frame_valid is a kernel parameter baked into the captured graph
+    const int key = (n * 2 + (t->frame_valid ? 1 : 0)) * 2 + (spread ? 1 : 0);  // frame_valid is a kernel parameter baked into the graph
     auto it = t->graphs.find(key);
     if (it == t->graphs.end()) {
         cudaGraph_t graph = nullptr;
         VT_CUDA(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
-        vt_status st = enqueue_forward(t, n, launches, true, true);
+        vt_status st = enqueue_forward(t, n, launches, true, true, spread);
         cudaError_t e = cudaStreamEndCapture(t->stream, &graph);
         if (st != VT_OK) {
             if (graph) cudaGraphDestroy(graph);
@@ -768,6 +778,7 @@ void vt_tracker_destroy(vt_tracker* t) {
                 (unsigned long long)t->hp_n, t->hp[0] / n, t->hp[1] / n, t->hp[2] / n, t->hp[3] / n, t->hp[4] / n, t->hp[5] / n, t->hp[6] / n);
     }
     cudaSetDevice(t->cfg.device);
+    if (t->counted) g_live_handles[t->cfg.device].fetch_sub(1);
     if (t->stream) cudaStreamSynchronize(t->stream);
     for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
     for (auto& e : t->ev)
@@ -908,6 +919,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         VT_TRY(tc_gemm_setup());
         t->fuse_ln = D / 64 <= 8 && !getenv("VT_B200_NO_FUSE_LN");
         t->pdl = !getenv("VT_B200_NO_PDL");
+        t->spread_ok = !getenv("VT_B200_NO_SPREAD");
         t->chain_mlp = t->fuse_ln && D <= 192 && !getenv("VT_B200_NO_CHAIN");
         if (t->chain_mlp) VT_TRY(cudaMalloc(&t->Pbuf, sizeof(float) * (Hd / 64) * B * kNTok * D));
         t->split_k = t->chain_mlp && Hd / 64 >= 4 && (C == 64 || C == 128) && !getenv("VT_B200_NO_SPLITK");
@@ -1056,6 +1068,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     t->inited.assign(B, 0);
     VT_TRY(cudaStreamSynchronize(t->stream));
 #undef VT_TRY
+    if (t->cfg.device >= 0 && t->cfg.device < kMaxDevices) g_live_handles[t->cfg.device].fetch_add(1), t->counted = true;
     *out = t;
     return VT_OK;
 }

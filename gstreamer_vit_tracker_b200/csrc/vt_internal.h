@@ -238,6 +238,7 @@ struct TcGemmArgs {
     TcOut c, o[6], ln_out[2], p;
     int o_mode;               // 0 off; 1 bf16 split tile -> o[0] (hi), o[1] (lo); 2 QKV scatter -> o[0..5] = Q, K, V^T (hi, lo);
                               // 3 staged in shared memory only (A operand of the chained GEMM)
+    int chain_slices;         // set at launch ("spread" form): the chained product is computed in 3 column slices by 3 replicas of the tile
     int mcast;                // set at launch: > 1 = the activation tile is multicast to this many column-tile CTAs of the cluster
     int kb_per_split;         // split-K: 64-wide k-blocks per blockIdx.z slice (0 = no split); the fp32 partial tile of slice z goes to
                               // plane z of c and bias / activations / residual must be off
@@ -268,7 +269,10 @@ TcOut tc_out(void* base, int elem_bytes, int64_t cols, int rows, int heads, int 
 TcOut tc_out_vt(void* base, int tokens, int heads, int batch);
 bool tc_resid_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols);
 cudaError_t tc_gemm_setup();
-cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl);
+// spread: latency mode — tiles are replicated over idle SMs so that each replica stores a share of the epilogue output (only when the
+// whole grid still fits in one wave of kSpreadCtas CTAs)
+constexpr int kSpreadCtas = 132;
+cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl, bool spread = false);
 struct TcAttentionPlan {      // kernel parameter block (__grid_constant__)
     CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo;
     __nv_bfloat16 *out_hi, *out_lo;  // [B][320][D]: the proj GEMM's A operand
