@@ -228,21 +228,26 @@ cudaError_t launch_layernorm_split(const float* x, int64_t ldx, const float* g, 
 // fully coalesced 8-byte loads, all issued before the first add (one L2 round trip).  The partials are added in index order,
 // so the result does not depend on scheduling.
 // ------------------------------------------------------------------------------------------------
+// Rows (= warps) per CTA.  (Measured: 2 rows per CTA — 160 CTAs instead of 40 for one target — changes nothing; the kernel is bound by
+// the L2 round trips of its dependent loads, not by the per-SM read rate.)
+constexpr int kReduceRows = 8;
 template <int NPAIR, int NP>  // D / 64 column pairs per lane; number of partials (0 = runtime np, batches of 4)
-__global__ void __launch_bounds__(256) reduce_ln_kernel(const ReduceLnArgs a) {
+__global__ void __launch_bounds__(32 * kReduceRows) reduce_ln_kernel(const ReduceLnArgs a) {
     constexpr int D = NPAIR * 64;
+    const int m = blockIdx.x * kReduceRows + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (m >= a.M) return;
     const int b = m / a.period, t = m - b * a.period;
     const int64_t xrow = (int64_t)b * a.x_rows + t + a.x_row_off;
-    float2 acc[NPAIR];
     const float2* ar = reinterpret_cast<const float2*>(a.add + (a.add_period ? (int64_t)(m % a.add_period) : xrow) * D);
+    // LayerNorm gain / bias are fetched with the first batch of loads: a late __ldg would add an L2 round trip behind the reductions.
+    // (Measured: issuing the parameter loads BEFORE griddepcontrol.wait makes the kernel 0.7 us slower, so they stay behind it.)
+    float2 acc[NPAIR], gam[NPAIR], bet[NPAIR], x2[NPAIR];
 #pragma unroll
     for (int i = 0; i < NPAIR; ++i) {
-        const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.bias) + lane + 32 * i), x2 = ar[lane + 32 * i];
-        acc[i] = make_float2(x2.x + b2.x, x2.y + b2.y);
+        acc[i] = __ldg(reinterpret_cast<const float2*>(a.bias) + lane + 32 * i), x2[i] = ar[lane + 32 * i];
+        gam[i] = __ldg(reinterpret_cast<const float2*>(a.ln_g) + lane + 32 * i), bet[i] = __ldg(reinterpret_cast<const float2*>(a.ln_b) + lane + 32 * i);
     }
     const float2* pr = reinterpret_cast<const float2*>(a.P + (int64_t)m * D);
     const int64_t ps = a.p_stride / 2;
@@ -253,10 +258,14 @@ __global__ void __launch_bounds__(256) reduce_ln_kernel(const ReduceLnArgs a) {
 #pragma unroll
             for (int i = 0; i < NPAIR; ++i) v[j][i] = pr[j * ps + lane + 32 * i];
 #pragma unroll
+        for (int i = 0; i < NPAIR; ++i) acc[i].x = x2[i].x + acc[i].x, acc[i].y = x2[i].y + acc[i].y;  // (x + bias) first, as before
+#pragma unroll
         for (int j = 0; j < NP; ++j)
 #pragma unroll
             for (int i = 0; i < NPAIR; ++i) acc[i].x += v[j][i].x, acc[i].y += v[j][i].y;
     } else {
+#pragma unroll
+        for (int i = 0; i < NPAIR; ++i) acc[i].x = x2[i].x + acc[i].x, acc[i].y = x2[i].y + acc[i].y;
         for (int j0 = 0; j0 < a.np; j0 += 4) {
             float2 v[4][NPAIR];
 #pragma unroll
@@ -287,7 +296,7 @@ __global__ void __launch_bounds__(256) reduce_ln_kernel(const ReduceLnArgs a) {
     uint32_t* ol = reinterpret_cast<uint32_t*>(a.ln_lo + orow * D);
 #pragma unroll
     for (int i = 0; i < NPAIR; ++i) {
-        const float2 g2 = __ldg(reinterpret_cast<const float2*>(a.ln_g) + lane + 32 * i), b2 = __ldg(reinterpret_cast<const float2*>(a.ln_b) + lane + 32 * i);
+        const float2 g2 = gam[i], b2 = bet[i];
         const float y0 = (acc[i].x - mean) * rstd * g2.x + b2.x, y1 = (acc[i].y - mean) * rstd * g2.y + b2.y;
         const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
         const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
@@ -298,7 +307,7 @@ __global__ void __launch_bounds__(256) reduce_ln_kernel(const ReduceLnArgs a) {
 
 cudaError_t launch_reduce_ln(const ReduceLnArgs& a, cudaStream_t s, bool pdl) {
     if (a.M <= 0) return cudaSuccess;
-    const dim3 grid((a.M + 7) / 8), block(256);
+    const dim3 grid((a.M + kReduceRows - 1) / kReduceRows), block(32 * kReduceRows);
 #define VT_RL(NPAIR_, NP_) return launch_ex(reduce_ln_kernel<NPAIR_, NP_>, grid, block, 0, s, pdl, 1, a)
     switch (a.D / 64) {
         case 1:
