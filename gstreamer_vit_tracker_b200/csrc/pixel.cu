@@ -578,15 +578,17 @@ __global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t
                                                           const DeviceResult* __restrict__ res, const int32_t* __restrict__ slots,
                                                           float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
                                                           uint8_t* const* frame_slot) {
-    __shared__ uint8_t* s_host;
+    // frame / host addresses and the slot table were written at the start of the frame (complete long before the kernel ahead of this
+    // one): every thread fetches them in one batch; only the decode result waits for the dependency
     if (frame_slot) frame = *frame_slot;
-    if (threadIdx.x == 0) s_host = host_slot ? *reinterpret_cast<uint8_t* const volatile*>(host_slot) : nullptr;
-    __syncthreads();
-    const DeviceResult r = res[slots[blockIdx.x]];
+    uint8_t* const host = host_slot ? *reinterpret_cast<uint8_t* const volatile*>(host_slot) : nullptr;
+    const int slot = slots[blockIdx.x];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const DeviceResult r = res[slot];
     if (r.status == VT_OK && r.success && r.score > gate) {
         const int x = r.bbox[0], y = r.bbox[1], w = r.bbox[2], h = r.bbox[3];
         for (int pass = 0; pass < 2; ++pass) {
-            uint8_t* dst = pass == 0 ? frame : s_host;
+            uint8_t* dst = pass == 0 ? frame : host;
             if (!dst) break;
             Surface s{dst, len, W, H, fmt};
             if (fmt == VT_FMT_NV12) {
@@ -606,10 +608,10 @@ __global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t
 
 cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
                                const int32_t* d_slots, int n, float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
-                               cudaStream_t s, uint8_t* const* frame_slot) {
+                               cudaStream_t s, uint8_t* const* frame_slot, bool pdl) {
     if (n <= 0) return cudaSuccess;
-    box_overlay_kernel<<<n, 256, 0, s>>>(d_frame, len, width, height, format, d_res, d_slots, gate, host_slot, stamp_end, frame_slot);
-    return cudaGetLastError();
+    return launch_ex(box_overlay_kernel, dim3(n), dim3(256), 0, s, pdl, 1, d_frame, len, width, height, format, d_res, d_slots, gate, host_slot,
+                     stamp_end, frame_slot);
 }
 
 // per-frame, outside the graph: submit stamp + the address of the frame this step reads (FrameDesc::data_slot)

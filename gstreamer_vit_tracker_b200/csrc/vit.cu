@@ -557,7 +557,7 @@ template <int N> struct VecOf;
 template <> struct VecOf<4> { typedef float4 type; };
 template <> struct VecOf<2> { typedef float2 type; };
 constexpr int kCandStride = 8;  // floats per row candidate: value, index, off_x, off_y, size_w, size_h
-template <int CPL>  // channels per lane: head_ch / 32
+template <int CPL, int NP>  // channels per lane: head_ch / 32; taps (0 = runtime np, three in flight)
 __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restrict__ P, int np, int64_t p_stride, const float* __restrict__ b1,
                                                           const float* __restrict__ w2, const float* __restrict__ b2,
                                                           const float* __restrict__ hann, TargetState* __restrict__ state,
@@ -569,31 +569,56 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restric
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (stamps && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) stamps[ST_DEC] = device_time_ns();
-    const int bi = blockIdx.y, slot = slots[bi], y = blockIdx.x;
+    const int bi = blockIdx.y, y = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float w[5][CPL], bch[CPL];
+    // Every load this CTA needs is issued in ONE batch (parameters, hann weights, all taps of both cells): the kernel is a chain of L2
+    // round trips (~0.7 us each), not of bytes, so nothing is fetched behind a reduction.
+    const int slot = slots[bi];
+    float w[5][CPL], bch[CPL], b2v[5], hw[2];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
         bch[c] = __ldg(b1 + lane * CPL + c);
 #pragma unroll
         for (int k = 0; k < 5; ++k) w[k][c] = __ldg(w2 + k * C + lane * CPL + c);
     }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) b2v[k] = __ldg(b2 + k);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) hw[cc] = __ldg(hann + y * kMap + 2 * warp + cc);
     using Vec = typename VecOf<CPL>::type;  // float4 / float2: one coalesced load per lane and partial
     float hsum[2][CPL];
+    if (NP > 0) {
+        Vec v[2][NP > 0 ? NP : 1];
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-        const int cell = y * kMap + 2 * warp + cc;
-        const float* pr = P + ((int64_t)bi * kNTx + cell) * C + lane * CPL;
+        for (int cc = 0; cc < 2; ++cc) {
+            const float* pr = P + ((int64_t)bi * kNTx + y * kMap + 2 * warp + cc) * C + lane * CPL;
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) hsum[cc][c] = bch[c];
-        for (int j0 = 0; j0 < np; j0 += 3) {  // three taps (one kernel row) in flight per cell
-            Vec v[3];
+            for (int j = 0; j < NP; ++j) v[cc][j] = *reinterpret_cast<const Vec*>(pr + (int64_t)j * p_stride);
+        }
 #pragma unroll
-            for (int jj = 0; jj < 3; ++jj) v[jj] = j0 + jj < np ? *reinterpret_cast<const Vec*>(pr + (int64_t)(j0 + jj) * p_stride) : Vec{};
+        for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
-            for (int jj = 0; jj < 3; ++jj)
+            for (int c = 0; c < CPL; ++c) hsum[cc][c] = bch[c];
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) hsum[cc][c] += reinterpret_cast<const float*>(&v[jj])[c];
+            for (int j = 0; j < NP; ++j)  // taps in index order, as the runtime form
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) hsum[cc][c] += reinterpret_cast<const float*>(&v[cc][j])[c];
+        }
+    } else {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const float* pr = P + ((int64_t)bi * kNTx + y * kMap + 2 * warp + cc) * C + lane * CPL;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) hsum[cc][c] = bch[c];
+            for (int j0 = 0; j0 < np; j0 += 3) {  // three taps (one kernel row) in flight per cell
+                Vec v[3];
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj) v[jj] = j0 + jj < np ? *reinterpret_cast<const Vec*>(pr + (int64_t)(j0 + jj) * p_stride) : Vec{};
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj)
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) hsum[cc][c] += reinterpret_cast<const float*>(&v[jj])[c];
+            }
         }
     }
 #pragma unroll
@@ -605,12 +630,12 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restric
             float d = 0.f;
 #pragma unroll
             for (int c = 0; c < CPL; ++c) d = fmaf(fmaxf(hsum[cc][c], 0.f), w[k][c], d);
-            o[k] = warp_sum(d) + __ldg(b2 + k);
+            o[k] = warp_sum(d) + b2v[k];
         }
         if (lane == 0) {
             const float conf = 1.f / (1.f + expf(-o[0]));
             const float sw = 1.f / (1.f + expf(-o[1])), sh = 1.f / (1.f + expf(-o[2]));
-            const float cw = __fmul_rn(conf, hann[p]);
+            const float cw = __fmul_rn(conf, hw[cc]);
             float* mm = maps + (int64_t)slot * 1280;
             mm[p] = cw, mm[256 + p] = sw, mm[512 + p] = sh, mm[768 + p] = o[3], mm[1024 + p] = o[4];
             float* sc = s_c[2 * warp + cc];
@@ -623,21 +648,34 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restric
         for (int i = 1; i < 16; ++i)
             if (s_c[i][0] > s_c[best][0]) best = i;  // first maximum of the row
         float* cd = cand + ((int64_t)bi * 16 + y) * kCandStride;
-        cd[0] = s_c[best][0], cd[1] = (float)(y * kMap + best), cd[2] = s_c[best][1], cd[3] = s_c[best][2], cd[4] = s_c[best][3], cd[5] = s_c[best][4];
+        *reinterpret_cast<float4*>(cd) = make_float4(s_c[best][0], (float)(y * kMap + best), s_c[best][1], s_c[best][2]);
+        *reinterpret_cast<float2*>(cd + 4) = make_float2(s_c[best][3], s_c[best][4]);
         __threadfence();
         s_last = atomicAdd(&counters[bi], 1u) == 15u;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last && warp == 0) {
+        // the last CTA to arrive merges the 16 row candidates: lane i fetches candidate i (all of them in flight at once, L2 loads),
+        // then a shuffle arg-max with "lower row wins ties" = first row-major maximum
         __threadfence();
-        const volatile float* cd = cand + (int64_t)bi * 16 * kCandStride;
-        int by = 0;
-        for (int i = 1; i < 16; ++i)
-            if (cd[i * kCandStride] > cd[by * kCandStride]) by = i;  // rows in ascending order: first row-major maximum
-        const volatile float* c = cd + by * kCandStride;
-        decode_finish(state + slot, slot, threshold, c[0], (int)c[1], c[2], c[3], c[4], c[5], res);
-        counters[bi] = 0;  // ready for the next frame
-        if (stamps && bi == gridDim.y - 1) stamps[ST_DEC_END] = device_time_ns();
+        const float* cd = cand + ((int64_t)bi * 16 + (lane & 15)) * kCandStride;
+        const float4 c0 = __ldcg(reinterpret_cast<const float4*>(cd));
+        const float2 c1 = __ldcg(reinterpret_cast<const float2*>(cd + 4));
+        float bv = c0.x;
+        int by = lane & 15;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oy = __shfl_xor_sync(0xffffffffu, by, o);
+            if (ov > bv || (ov == bv && oy < by)) bv = ov, by = oy;
+        }
+        const float f1 = __shfl_sync(0xffffffffu, c0.y, by), f2 = __shfl_sync(0xffffffffu, c0.z, by), f3 = __shfl_sync(0xffffffffu, c0.w, by);
+        const float f4 = __shfl_sync(0xffffffffu, c1.x, by), f5 = __shfl_sync(0xffffffffu, c1.y, by);
+        if (lane == 0) {
+            decode_finish(state + slot, slot, threshold, bv, (int)f1, f2, f3, f4, f5, res);
+            counters[bi] = 0;  // ready for the next frame
+            if (stamps && bi == gridDim.y - 1) stamps[ST_DEC_END] = device_time_ns();
+        }
     }
 }
 
@@ -646,10 +684,14 @@ cudaError_t launch_head_decode(const float* P, int np, int64_t p_stride, int hea
                                float* d_maps, float* d_cand, unsigned* d_counters, unsigned long long* stamps, cudaStream_t s, bool pdl) {
     if (n <= 0) return cudaSuccess;
     const dim3 grid(kMap, n), block(256);
+    if (head_ch == 128 && np == 9)
+        return launch_ex(head_decode_kernel<4, 9>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
+    if (head_ch == 64 && np == 9)
+        return launch_ex(head_decode_kernel<2, 9>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
     if (head_ch == 128)
-        return launch_ex(head_decode_kernel<4>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
+        return launch_ex(head_decode_kernel<4, 0>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
     if (head_ch == 64)
-        return launch_ex(head_decode_kernel<2>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
+        return launch_ex(head_decode_kernel<2, 0>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
     return cudaErrorInvalidValue;
 }
 
