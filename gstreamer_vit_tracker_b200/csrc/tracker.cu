@@ -60,7 +60,7 @@ static std::mutex g_weight_mutex;
 // Live tracker handles per device.  With one or two streams on a GPU most SMs idle during a frame, and the "spread" GEMM forms trade
 // them for latency (tiles replicated so that each replica stores a share of the epilogue output); with more streams SM time is the
 // budget and the plain forms are used.  Read at every frame: the graph variant follows the handle count.
-constexpr int kMaxDevices = 64, kSpreadMaxHandles = 2;
+constexpr int kMaxDevices = 64, kSpreadMaxHandles = 2, kUnchainTargets = 8;
 static std::atomic<int> g_live_handles[kMaxDevices];
 static std::map<std::string, std::weak_ptr<WeightSet>> g_weight_cache;
 
@@ -135,6 +135,7 @@ struct vt_tracker {
     unsigned* d_counters = nullptr;
     bool pdl = true;            // programmatic dependent launch along the kernel chain
     bool spread_ok = true;      // latency-mode GEMM forms allowed (VT_B200_NO_SPREAD disables)
+    int unchain_n = kUnchainTargets;  // active targets from which the MLP runs unchained (VT_B200_UNCHAIN_N overrides)
     bool counted = false;       // this handle is included in g_live_handles
     bool tc_attention = false;  // head_dim == 64
     TcAttentionPlan plan_att;
@@ -381,8 +382,18 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                 VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
             VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention, spread));  // fused: + LN2
             if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
-            VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s, pdl, spread && t->chain_mlp));  // chained: + the FC2 partial products of its 64 hidden columns
-            if (t->chain_mlp) {  // X += fc2_b + sum of the partials; LN1 of the next block / the final LN of the search rows
+            // Chained form (FC2 partial products inside the FC1 kernel, summed by reduce_ln): shortest critical path for a few targets.
+            // From kUnchainTargets targets on the 12 fp32 partial planes per row tile cost more than the hidden round trip
+            // (cfg4, 16 targets: ViT stage 905 -> 819 us unchained), so FC1 writes the hidden tile and FC2 runs as its own GEMM.
+            const bool chain = t->chain_mlp && n < t->unchain_n;
+            if (chain) {
+                VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s, pdl, spread));
+            } else {
+                TcGemmPlan fc1 = p.fc1;
+                fc1.args.chain_n = 0, fc1.args.o_mode = 1;
+                VT_LAUNCH(tc_gemm_launch(fc1, M, ns, s, pdl));
+            }
+            if (chain) {  // X += fc2_b + sum of the partials; LN1 of the next block / the final LN of the search rows
                 const bool last = l + 1 == t->depth;
                 ReduceLnArgs r{};
                 r.P = t->Pbuf, r.np = Hd / 64, r.p_stride = (int64_t)t->maxT * kNTok * D, r.bias = b.fc2_b, r.add = t->X, r.add_period = 0;
@@ -920,6 +931,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         t->fuse_ln = D / 64 <= 8 && !getenv("VT_B200_NO_FUSE_LN");
         t->pdl = !getenv("VT_B200_NO_PDL");
         t->spread_ok = !getenv("VT_B200_NO_SPREAD");
+        if (const char* e = getenv("VT_B200_UNCHAIN_N")) t->unchain_n = atoi(e);
         t->chain_mlp = t->fuse_ln && D <= 192 && !getenv("VT_B200_NO_CHAIN");
         if (t->chain_mlp) VT_TRY(cudaMalloc(&t->Pbuf, sizeof(float) * (Hd / 64) * B * kNTok * D));
         t->split_k = t->chain_mlp && Hd / 64 >= 4 && (C == 64 || C == 128) && !getenv("VT_B200_NO_SPLITK");

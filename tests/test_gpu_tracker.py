@@ -687,3 +687,33 @@ def test_gray8_input_format(api, oracle, weight_dir):
     trk.overlay(fr, [api.overlay_cmd(api.L.VT_OV_RECT, 100, 80, 60, 40, 3, 200)])
     oracle.draw_rect_nv12(want, W, H, 100, 80, 60, 40, 3, 200)
     assert np.array_equal(fr, want[:W * H])
+
+
+def test_kernel_forms_agree(api, weight_dir, monkeypatch):
+    """The latency-mode "spread" form (FC1 tile computed by three CTAs, one 64-column slice of the chained FC2 product each; used
+    while <= 2 handles are alive on the GPU), the plain chained form and the unchained FC1 / FC2 GEMMs (>= 8 targets) are
+    re-associations of the same sums: boxes equal, scores within 2e-6 of each other over a sequence."""
+    import gc
+    gc.collect()  # handles of earlier tests would count as live streams
+    spec = synth.CONFIGS["cfg1"]
+    st = synth.SyntheticStream(spec)
+    w = weights.ensure_weight_file("tiny", weight_dir, variant="wild")
+    frames = [np.ascontiguousarray(st.frame(i)).reshape(-1) for i in range(6)]
+
+    def run(env):
+        for k in ("VT_B200_NO_SPREAD", "VT_B200_UNCHAIN_N"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        trk = api.VitTrack.new(w, spec.width, spec.height, gemm_mode=1)
+        trk.init(frames[0], api.BBox(*st.target_boxes(0)[0]))
+        out = [trk.update(f) for f in frames[1:]]
+        trk.close()
+        return out
+
+    spread = run({})
+    plain = run({"VT_B200_NO_SPREAD": "1"})
+    unchained = run({"VT_B200_UNCHAIN_N": "1"})
+    for a, b, c in zip(spread, plain, unchained):
+        assert a.success and a.bbox == b.bbox == c.bbox
+        assert abs(a.score - b.score) < 2e-6 and abs(a.score - c.score) < 2e-6

@@ -17,7 +17,11 @@ from gstreamer_vit_tracker_b200 import api, synth, weights  # noqa: E402
 
 
 def run(name, model="tiny", frames=200, warm=20, ring=16):
+    name, _, limit = name.partition(":")  # "cfg4:8" = the first 8 targets of cfg4
     spec = synth.CONFIGS[name]
+    if limit:
+        import dataclasses
+        spec = dataclasses.replace(spec, targets=spec.targets[:int(limit)])
     st = synth.SyntheticStream(spec)
     wpath = weights.ensure_weight_file(model, os.path.join(tempfile.gettempdir(), "vt_b200_weights"))
     nt = len(spec.targets)
