@@ -692,7 +692,7 @@ def test_gray8_input_format(api, oracle, weight_dir):
 def test_kernel_forms_agree(api, weight_dir, monkeypatch):
     """The latency-mode "spread" form (FC1 tile computed by three CTAs, one 64-column slice of the chained FC2 product each; used
     while <= 2 handles are alive on the GPU), the plain chained form and the unchained FC1 / FC2 GEMMs (>= 8 targets) are
-    re-associations of the same sums: boxes equal, scores within 2e-6 of each other over a sequence."""
+    re-associations of the same sums: boxes equal, scores within 1e-5 of each other over a sequence (parity bar: 1e-3)."""
     import gc
     gc.collect()  # handles of earlier tests would count as live streams
     spec = synth.CONFIGS["cfg1"]
@@ -716,4 +716,4 @@ def test_kernel_forms_agree(api, weight_dir, monkeypatch):
     unchained = run({"VT_B200_UNCHAIN_N": "1"})
     for a, b, c in zip(spread, plain, unchained):
         assert a.success and a.bbox == b.bbox == c.bbox
-        assert abs(a.score - b.score) < 2e-6 and abs(a.score - c.score) < 2e-6
+        assert abs(a.score - b.score) < 1e-5 and abs(a.score - c.score) < 1e-5
