@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const int N2 = sliced ? a.chain_n / a.chain_slices : a.chain_n;   // chained columns of this CTA
     const int acc2_cols = (sliced && kLo) ? 2 * N2 : N2;              // sliced + bf16x3: hi*lo term in a second column half
     const bool do_ln = a.ln_g != nullptr, do_c = a.c_on;
+    // dup_hl (spread form of the QKV scatter): replica 0 stores the bf16 hi tiles, replica 1 the lo tiles
+    const bool st_hi = !a.dup_hl || blockIdx.z == 0, st_lo = kLo && (!a.dup_hl || blockIdx.z == 1);
     const int npre = num_kb < kTcStages ? num_kb : kTcStages;
     constexpr uint32_t kAcc1Cols = kLo ? 2 * BN : BN;  // bf16x3 keeps hi*lo in a second column half
     const uint32_t tmem_cols = a.chain_n == 0 ? (kAcc1Cols < 32 ? 32 : kAcc1Cols) : (kAcc1Cols + acc2_cols <= 128 ? 128 : (kAcc1Cols + acc2_cols <= 256 ? 256 : 512));
@@ -433,15 +435,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             tile_to_global<128>(sC + bx * (kTcBM * 128), a.c, (int64_t)(n0 + 32 * bx) * 4, tr_rows, a.c_row_off, 0, a.kb_per_split ? blockIdx.z : 0, tid);
     }
     if (a.o_mode == 1) {
-        tile_to_global<RB>(smem + SM::kOffOhi, a.o[0], (int64_t)n0 * 2, tr_rows, a.o_row_off, 0, 0, tid);
-        if (kLo) tile_to_global<RB>(smem + SM::kOffOlo, a.o[1], (int64_t)n0 * 2, tr_rows, a.o_row_off, 0, 0, tid);
+        if (st_hi) tile_to_global<RB>(smem + SM::kOffOhi, a.o[0], (int64_t)n0 * 2, tr_rows, a.o_row_off, 0, 0, tid);
+        if (st_lo) tile_to_global<RB>(smem + SM::kOffOlo, a.o[1], (int64_t)n0 * 2, tr_rows, a.o_row_off, 0, 0, tid);
     } else if (a.o_mode == 2) {  // Q / K: [B][heads][320][64]; V^T: [B][heads][64][320]
         if (o_which < 2) {
-            tile_to_global<RB>(smem + SM::kOffOhi, a.o[2 * o_which], (int64_t)o_d * 2, tr_rows, 0, o_h, 0, tid);
-            if (kLo) tile_to_global<RB>(smem + SM::kOffOlo, a.o[2 * o_which + 1], (int64_t)o_d * 2, tr_rows, 0, o_h, 0, tid);
+            if (st_hi) tile_to_global<RB>(smem + SM::kOffOhi, a.o[2 * o_which], (int64_t)o_d * 2, tr_rows, 0, o_h, 0, tid);
+            if (st_lo) tile_to_global<RB>(smem + SM::kOffOlo, a.o[2 * o_which + 1], (int64_t)o_d * 2, tr_rows, 0, o_h, 0, tid);
         } else {
-            vt_tile_to_global<BN>(smem + SM::kOffOhi, a.o[4], tr_rows, o_h, o_d, tid);
-            if (kLo) vt_tile_to_global<BN>(smem + SM::kOffOlo, a.o[5], tr_rows, o_h, o_d, tid);
+            if (st_hi) vt_tile_to_global<BN>(smem + SM::kOffOhi, a.o[4], tr_rows, o_h, o_d, tid);
+            if (st_lo) vt_tile_to_global<BN>(smem + SM::kOffOlo, a.o[5], tr_rows, o_h, o_d, tid);
         }
     }
     if (tid == 0) tr.mark(7);
@@ -675,7 +677,10 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t 
     a.M = M;
     const int bn = p.bn;
     dim3 grid(a.N / bn, (M + kTcBM - 1) / kTcBM, a.kb_per_split ? a.K / kTcBK / a.kb_per_split : 1);
-    a.chain_slices = 0;
+    a.chain_slices = 0, a.dup_hl = 0;
+    if (spread && !a.kb_per_split && nsplit == 3 && !a.chain_n && !a.ln_g && !a.c_on && (a.o_mode == 1 || a.o_mode == 2) &&
+        grid.x * grid.y * 2 <= (unsigned)kSpreadCtas)
+        a.dup_hl = 1, grid.z = 2;  // two replicas of every tile, one stores the hi parts and one the lo parts (halves the per-CTA egress)
     // latency mode: replicate the FC1 tiles over idle SMs, each replica computes and stores one 64-column slice of the chained product
     if (spread && !a.kb_per_split && a.chain_n && a.chain_n % (3 * 64) == 0 && grid.x * grid.y * 3 <= (unsigned)kSpreadCtas) a.chain_slices = 3, grid.z = 3;
     int cluster_x = 1;

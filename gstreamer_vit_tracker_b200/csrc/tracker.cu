@@ -375,7 +375,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             const BlockW& b = t->blk[l];
             const vt_tracker::BlockPlans& p = t->plans[l];
             if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
-            VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s, pdl));
+            VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s, pdl, spread));
             if (t->tc_attention)
                 VT_LAUNCH(tc_attention_launch(t->plan_att, n, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace));
             else
