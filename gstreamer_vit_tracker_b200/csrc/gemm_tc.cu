@@ -186,7 +186,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const bool sliced = a.chain_slices > 1;
     const int N2 = sliced ? a.chain_n / a.chain_slices : a.chain_n;   // chained columns of this CTA
     const int acc2_cols = (sliced && kLo) ? 2 * N2 : N2;              // sliced + bf16x3: hi*lo term in a second column half
-    const bool do_ln = a.ln_g != nullptr, do_c = a.c_on;
+    // dup_ln (spread form of a GEMM with fused LayerNorm): replica 0 stores the fp32 tile, replica 1 the LayerNorm hi tile, replica 2 the lo tile
+    const bool do_ln = a.ln_g != nullptr && (!a.dup_ln || blockIdx.z > 0), do_c = a.c_on && (!a.dup_ln || blockIdx.z == 0);
+    const bool ln_hi = !a.dup_ln || blockIdx.z == 1, ln_lo = kLo && (!a.dup_ln || blockIdx.z == 2);
     // dup_hl (spread form of the QKV scatter): replica 0 stores the bf16 hi tiles, replica 1 the lo tiles
     const bool st_hi = !a.dup_hl || blockIdx.z == 0, st_lo = kLo && (!a.dup_hl || blockIdx.z == 1);
     const int npre = num_kb < kTcStages ? num_kb : kTcStages;
@@ -532,8 +534,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         for (int j = 0; j < CPT; ++j) y[j] = (v[j] - mean) * rstd * gam[j] + bet[j];
         stage_split<CPT>(y, smem + SM::kOffLnHi, smem + SM::kOffLnLo, row, g, kLo);
         __syncthreads();
-        tile_to_global<RB>(smem + SM::kOffLnHi, a.ln_out[0], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
-        if (kLo) tile_to_global<RB>(smem + SM::kOffLnLo, a.ln_out[1], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
+        if (ln_hi) tile_to_global<RB>(smem + SM::kOffLnHi, a.ln_out[0], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
+        if (ln_lo) tile_to_global<RB>(smem + SM::kOffLnLo, a.ln_out[1], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
     }
     if (!ok && a.err) atomicExch(a.err, 1);
     tcgen05_fence_before();
@@ -677,7 +679,9 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t 
     a.M = M;
     const int bn = p.bn;
     dim3 grid(a.N / bn, (M + kTcBM - 1) / kTcBM, a.kb_per_split ? a.K / kTcBK / a.kb_per_split : 1);
-    a.chain_slices = 0, a.dup_hl = 0;
+    a.chain_slices = 0, a.dup_hl = 0, a.dup_ln = 0;
+    if (spread && !a.kb_per_split && nsplit == 3 && a.ln_g && a.c_on && !a.chain_n && !a.o_mode && grid.x * grid.y * 3 <= (unsigned)kSpreadCtas)
+        a.dup_ln = 1, grid.z = 3;  // three replicas of every tile: fp32 tile / LayerNorm hi / LayerNorm lo
     if (spread && !a.kb_per_split && nsplit == 3 && !a.chain_n && !a.ln_g && !a.c_on && (a.o_mode == 1 || a.o_mode == 2) &&
         grid.x * grid.y * 2 <= (unsigned)kSpreadCtas)
         a.dup_hl = 1, grid.z = 2;  // two replicas of every tile, one stores the hi parts and one the lo parts (halves the per-CTA egress)

@@ -238,6 +238,7 @@ struct TcGemmArgs {
     TcOut c, o[6], ln_out[2], p;
     int o_mode;               // 0 off; 1 bf16 split tile -> o[0] (hi), o[1] (lo); 2 QKV scatter -> o[0..5] = Q, K, V^T (hi, lo);
                               // 3 staged in shared memory only (A operand of the chained GEMM)
+    int dup_ln;               // set at launch ("spread" form): replica 0 stores the fp32 tile, 1 the LayerNorm hi tile, 2 the lo tile
     int dup_hl;               // set at launch ("spread" form): replica z = 0 stores the bf16 hi tiles, z = 1 the lo tiles
     int chain_slices;         // set at launch ("spread" form): the chained product is computed in 3 column slices by 3 replicas of the tile
     int mcast;                // set at launch: > 1 = the activation tile is multicast to this many column-tile CTAs of the cluster

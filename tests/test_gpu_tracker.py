@@ -280,22 +280,31 @@ def test_free_running_sequence_iou(api, oracle, weight_dir):
 # ---- multi-target, formats, errors -----------------------------------------------------------------------------
 @pytest.mark.parametrize("gemm_mode", [0, 1], ids=["fp32simt", "tcgen05x3"])
 def test_multi_target_equals_independent_singles(api, weight_dir, gemm_mode):
-    """16 targets batched through one forward (cfg4 geometry at 1/2 scale for speed) == 16 single-target trackers, bit for bit."""
+    """16 targets batched through one forward (cfg4 geometry at 1/2 scale for speed) == 16 single-target trackers: bit for bit while
+    the same kernel forms run (fp32 path; tensor-core path below 8 targets, checked with a 4-target handle); from 8 targets on the
+    tensor-core MLP runs unchained (FC2 as its own GEMM instead of 12 partial products) — a re-association of the same sums, boxes
+    equal and scores within 1e-5."""
     spec = synth.StreamSpec("mt", 1920, 1080, 1004, [(190 + (i % 4) * 450, 110 + (i // 4) * 250, 100, 75, 3 + i % 4, 2 + i // 4) for i in range(16)])
     st = synth.SyntheticStream(spec)
     wpath = weights.ensure_weight_file("nano", weight_dir, variant="wild")
     multi = api.VitTrack.new(wpath, spec.width, spec.height, max_targets=16, gemm_mode=gemm_mode)
+    multi4 = api.VitTrack.new(wpath, spec.width, spec.height, max_targets=4, gemm_mode=gemm_mode)
     singles = [api.VitTrack.new(wpath, spec.width, spec.height, gemm_mode=gemm_mode) for _ in range(16)]
     f0 = st.frame(0)
     for i, b in enumerate(st.target_boxes(0)):
         multi.init(f0, api.BBox(*b), target=i)
         singles[i].init(f0, api.BBox(*b))
+        if i < 4:
+            multi4.init(f0, api.BBox(*b), target=i)
+    tol = 0.0 if gemm_mode == 0 else 1e-5
     for n in range(5):
         fr = st.frame(n)
-        rs = multi.update_all(fr)
+        rs, rs4 = multi.update_all(fr), multi4.update_all(fr)
         for i in range(16):
             r1 = singles[i].update(fr)
-            assert rs[i].status == 0 and rs[i].success == r1.success and rs[i].bbox == r1.bbox and rs[i].score == r1.score, (n, i, rs[i], r1)
+            assert rs[i].status == 0 and rs[i].success == r1.success and rs[i].bbox == r1.bbox and abs(rs[i].score - r1.score) <= tol, (n, i, rs[i], r1)
+            if i < 4:
+                assert rs4[i] == r1, (n, i, rs4[i], r1)
     # dropping a target leaves the others untouched; un-initialised slots report VT_ERR_NOT_INIT
     multi.drop(3)
     rs = multi.update_all(st.frame(5))
