@@ -54,7 +54,7 @@ __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, %
 template <int NSPLIT>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int D,
-                    int heads, int* err, unsigned long long* trace) {
+                    int heads, int* err, unsigned long long* trace, int dup) {
     const CUtensorMap &mQhi = mp.mQhi, &mQlo = mp.mQlo, &mKhi = mp.mKhi, &mKlo = mp.mKlo, &mVhi = mp.mVhi, &mVlo = mp.mVlo;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_qk, bar_k1, bar_v, bar_s, p_full[kNChunks], bar_o;
@@ -72,7 +72,12 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
     const bool ctrl = warp == kSoftmaxWarps;  // warp 16: TMA + MMA issue (one elected lane), TMEM alloc / dealloc
     const int row = (warp & 3) * 32 + lane;   // query row inside the tile = TMEM lane
     const int g = (warp >> 2) & 3;            // column group
-    const int q0 = blockIdx.x * kQTile, h = blockIdx.y, b = blockIdx.z;
+    // dup ("spread" form, idle SMs available): every (query tile, head, target) is computed by two CTAs, replica 0 stores the hi tile
+    // and replica 1 the lo tile (a CTA's store rate is what bounds the end of the kernel)
+    constexpr int kQTiles = (kNTok + kQTile - 1) / kQTile;
+    const int replica = blockIdx.x / kQTiles;
+    const bool st_hi = !dup || replica == 0, st_lo = P == 2 && (!dup || replica == 1);
+    const int q0 = (blockIdx.x % kQTiles) * kQTile, h = blockIdx.y, b = blockIdx.z;
     const int bh = b * heads + h;
     const bool q_ok = q0 + row < kNTok;       // uniform per warp (320 = 2 * 128 + 64)
     bool ok = true;
@@ -258,8 +263,8 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
             if (q0 + r < kNTok) {
                 const int off = r * 128 + ((ch ^ (r & 7)) << 4);
                 const int64_t dst = (((int64_t)b * kNTok + q0 + r) * D + h * kDh) * 2 + ch * 16;
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out_hi) + dst) = *reinterpret_cast<const uint4*>(smem + off);
-                if (P == 2) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out_lo) + dst) = *reinterpret_cast<const uint4*>(smem + kPBytes + off);
+                if (st_hi) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out_hi) + dst) = *reinterpret_cast<const uint4*>(smem + off);
+                if (st_lo) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out_lo) + dst) = *reinterpret_cast<const uint4*>(smem + kPBytes + off);
             }
         }
     }
@@ -298,11 +303,14 @@ cudaError_t tc_attention_setup() {
     return cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem<3>::kTotal);
 }
 
-cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int nsplit, int* err, cudaStream_t s, bool pdl, unsigned long long* trace) {
+cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int nsplit, int* err, cudaStream_t s, bool pdl, unsigned long long* trace,
+                                bool spread) {
     if (B <= 0) return cudaSuccess;
-    const dim3 grid((kNTok + kQTile - 1) / kQTile, heads, B);
-    if (nsplit == 3) return launch_ex(attention_tc_kernel<3>, grid, dim3(kAttThreads), AttSmem<3>::kTotal, s, pdl, 1, p, p.out_hi, p.out_lo, p.D, heads, err, trace);
-    return launch_ex(attention_tc_kernel<1>, grid, dim3(kAttThreads), AttSmem<1>::kTotal, s, pdl, 1, p, p.out_hi, p.out_lo, p.D, heads, err, trace);
+    dim3 grid((kNTok + kQTile - 1) / kQTile, heads, B);
+    const int dup = spread && nsplit == 3 && (int)(grid.x * grid.y * grid.z) * 2 <= kSpreadCtas;
+    if (dup) grid.x *= 2;
+    if (nsplit == 3) return launch_ex(attention_tc_kernel<3>, grid, dim3(kAttThreads), AttSmem<3>::kTotal, s, pdl, 1, p, p.out_hi, p.out_lo, p.D, heads, err, trace, dup);
+    return launch_ex(attention_tc_kernel<1>, grid, dim3(kAttThreads), AttSmem<1>::kTotal, s, pdl, 1, p, p.out_hi, p.out_lo, p.D, heads, err, trace, dup);
 }
 
 }  // namespace vt

@@ -377,7 +377,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
             VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s, pdl, spread));
             if (t->tc_attention)
-                VT_LAUNCH(tc_attention_launch(t->plan_att, n, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace));
+                VT_LAUNCH(tc_attention_launch(t->plan_att, n, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace, spread));
             else
                 VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
             VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention, spread));  // fused: + LN2

@@ -285,7 +285,7 @@ bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const 
                             int batch);
 cudaError_t tc_attention_setup();
 cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int nsplit, int* err, cudaStream_t s, bool pdl,
-                                unsigned long long* trace = nullptr);
+                                unsigned long long* trace = nullptr, bool spread = false);
 cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t s);
 
 }  // namespace vt
