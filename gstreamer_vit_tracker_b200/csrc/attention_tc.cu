@@ -16,6 +16,12 @@
 //              (+ 384..447 for the hi*lo term), overlapped with the next chunk's softmax
 //   epilogue   O / sum -> bf16 (hi, lo) tile staged in shared memory -> coalesced 16-byte stores into the proj GEMM's A operand.
 // The output staging tile aliases the Q/K area once S is complete (~192 KB of shared memory per CTA).
+//
+// Chained form (latency mode, `chain`): the proj GEMM is folded in.  The staged O tile (bf16 hi / lo, 128B-swizzled K-major) IS a UMMA
+// A operand, so the CTA multiplies it with a 64-row slice of W_proj[:, 64 h .. 64 h + 64) (fetched before the dependency wait) into TMEM
+// columns 0..127 (dead P) and stores the fp32 partial product [128 x 64] of head h to plane h of the partial buffer; reduce_ln_kernel
+// adds the heads in index order with bias, residual and LayerNorm 2.  Each (query tile, head) is computed by D / 64 CTAs, one
+// per 64-column slice of the product, so that every CTA stores 32 KB: one kernel and one dependency edge less per block.
 #include "tc_common.cuh"
 #include "vt_internal.h"
 
@@ -45,7 +51,8 @@ struct AttSmem {
     static constexpr int kP = kParts * kPBytes;  // output staging tile
     static constexpr int kRegion1 = kQK > kP ? kQK : kP;
     static constexpr int kV = kParts * kVBytes;
-    static constexpr int kTotal = kRegion1 + kV + 1024;
+    static constexpr int kW2 = kParts * kDh * 128;  // chained form: [W_proj slice hi 64 x 128 B][lo], adjacent = one N = 128 B operand
+    static constexpr int kTotal = kRegion1 + kV + kW2 + 1024;
 };
 
 // named barrier over the 16 softmax warps only (the control warp never joins it)
@@ -57,7 +64,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
                     int heads, int* err, unsigned long long* trace, int dup) {
     const CUtensorMap &mQhi = mp.mQhi, &mQlo = mp.mQlo, &mKhi = mp.mKhi, &mKlo = mp.mKlo, &mVhi = mp.mVhi, &mVlo = mp.mVlo;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_qk, bar_k1, bar_v, bar_s, p_full[kNChunks], bar_o;
+    __shared__ __align__(8) uint64_t bar_qk, bar_k1, bar_v, bar_s, p_full[kNChunks], bar_o, bar_w2, bar_a2, bar_o2;
     __shared__ uint32_t tmem_base_s;
     __shared__ float red[kColGroups][kQTile];  // row-max partials, then row-sum partials
     __shared__ unsigned long long* trace_slot;
@@ -67,6 +74,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
     uint8_t* sQ = smem;                       // [P][128 x 128B]
     uint8_t* sK = smem + P * kQBytes;         // [P][320 x 128B]
     uint8_t* sV = smem + SM::kRegion1;        // [P][5 blocks][64 x 128B]
+    uint8_t* sW2 = sV + SM::kV;               // chained form: W_proj slice
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool ctrl = warp == kSoftmaxWarps;  // warp 16: TMA + MMA issue (one elected lane), TMEM alloc / dealloc
@@ -77,6 +85,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
     constexpr int kQTiles = (kNTok + kQTile - 1) / kQTile;
     const int replica = blockIdx.x / kQTiles;
     const bool st_hi = !dup || replica == 0, st_lo = P == 2 && (!dup || replica == 1);
+    const bool chain = mp.chain != 0;         // replica = 64-column slice of the chained proj product
     const int q0 = (blockIdx.x % kQTiles) * kQTile, h = blockIdx.y, b = blockIdx.z;
     const int bh = b * heads + h;
     const bool q_ok = q0 + row < kNTok;       // uniform per warp (320 = 2 * 128 + 64)
@@ -86,6 +95,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
 
     if (tid == 0) {
         mbar_init(&bar_qk, 1), mbar_init(&bar_k1, 1), mbar_init(&bar_v, 1), mbar_init(&bar_s, 1), mbar_init(&bar_o, 1);
+        mbar_init(&bar_w2, 1), mbar_init(&bar_a2, kSoftmaxWarps), mbar_init(&bar_o2, 1);
         for (int c = 0; c < kNChunks; ++c) mbar_init(&p_full[c], kSoftmaxWarps);
         fence_barrier_init();
     }
@@ -99,6 +109,12 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (chain && ctrl && lane == 0) {  // weights never depend on the preceding kernel: W_proj[64 replica .. + 64)[64 h .. 64 h + 64)
+        tma_prefetch_desc(&mp.mW2hi);
+        mbar_arrive_expect_tx(&bar_w2, P * kDh * 128);
+        tma_load_2d(sW2, &mp.mW2hi, &bar_w2, h * kDh, replica * 64);
+        if (P == 2) tma_load_2d(sW2 + kDh * 128, &mp.mW2lo, &bar_w2, h * kDh, replica * 64);
+    }
     tcgen05_fence_after();
     const uint32_t tmem = tmem_base_s;
 
@@ -171,6 +187,23 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
                 }
             }
             umma_commit(&bar_o);
+            if (chain) {  // ---- partial proj product of this head: O (staged by the softmax warps) x W_proj slice^T -> TMEM columns 0..127
+                ok &= mbar_wait(&bar_w2, 0);
+                ok &= mbar_wait(&bar_a2, 0);
+                tcgen05_fence_after();
+                const uint64_t dA = umma_desc_sw128(smem_u32(smem)), dW = umma_desc_sw128(smem_u32(sW2));
+                constexpr uint64_t kLoA = kPBytes >> 4;
+#pragma unroll
+                for (int k = 0; k < kDh / 16; ++k) {
+                    if (NSPLIT == 3) {
+                        umma_bf16(tmem, dA + 2 * k, dW + 2 * k, idesc2n, k != 0);  // O_hi x [W_hi; W_lo]
+                        umma_bf16(tmem, dA + kLoA + 2 * k, dW + 2 * k, idesc, 1);   // O_lo x W_hi
+                    } else {
+                        umma_bf16(tmem, dA + 2 * k, dW + 2 * k, idesc, k != 0);
+                    }
+                }
+                umma_commit(&bar_o2);
+            }
         }
         __syncwarp();
     } else {
@@ -255,6 +288,38 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
                 if (P == 2) *reinterpret_cast<uint4*>(smem + kPBytes + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
         }
+        if (chain) {
+            fence_proxy_async_smem();  // the staged O tile is read by the tensor core (async proxy)
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_a2);
+            ok &= mbar_wait(&bar_o2, 0);
+            tcgen05_fence_after();
+            float v[16];
+            tmem_ld_32x16(lane_addr + g * 16, v);
+            if (NSPLIT == 3) {
+                float hl[16];
+                tmem_ld_32x16(lane_addr + 64 + g * 16, hl);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += hl[j];
+            }
+            // fp32 tile [128][64] staged as two swizzled boxes of [128 rows][128 B] behind the O tiles (dead K area)
+            uint8_t* prow = smem + 2 * kPBytes + (g >> 1) * (kQTile * 128) + row * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(prow + ((((g & 1) * 4 + q) ^ (row & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            softmax_bar_sync();
+            // -> partial plane h: [B][320][D] fp32, columns 64 replica ..: 256 contiguous bytes per row, 2 rows per warp instruction
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = (tid >> 4) + 32 * i, c16 = tid & 15, bx = c16 >> 3, ch = c16 & 7;
+                if (q0 + r < kNTok) {
+                    const float4 val = *reinterpret_cast<const float4*>(smem + 2 * kPBytes + bx * (kQTile * 128) + r * 128 + ((ch ^ (r & 7)) << 4));
+                    float* dst = mp.p2 + (int64_t)h * mp.p2_plane + ((int64_t)b * kNTok + q0 + r) * D + replica * 64 + c16 * 4;
+                    *reinterpret_cast<float4*>(dst) = val;
+                }
+            }
+        } else {
         softmax_bar_sync();
         // staged [128][128 B] tiles -> att_hi / att_lo [B][320][D], columns h*64..: coalesced 16-byte stores, 4 rows per warp instruction
 #pragma unroll
@@ -266,6 +331,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
                 if (st_hi) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out_hi) + dst) = *reinterpret_cast<const uint4*>(smem + off);
                 if (st_lo) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out_lo) + dst) = *reinterpret_cast<const uint4*>(smem + kPBytes + off);
             }
+        }
         }
     }
     if (!ok && err) atomicExch(err, 2);
@@ -282,6 +348,7 @@ bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const 
                             int batch) {
     bool ok = true;
     p->out_hi = out_hi, p->out_lo = out_lo, p->D = D;
+    p->p2 = nullptr, p->p2_plane = 0, p->chain = 0;
     (void)batch;
     {   // Q, K: [batch*heads][320][64], box {64, rows, 1}
         const uint64_t dims[3] = {kDh, kNTok, (uint64_t)batch_heads}, strides[2] = {kDh * 2, (uint64_t)kDh * 2 * kNTok};
@@ -304,13 +371,30 @@ cudaError_t tc_attention_setup() {
 }
 
 cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int nsplit, int* err, cudaStream_t s, bool pdl, unsigned long long* trace,
-                                bool spread) {
+                                int form) {
     if (B <= 0) return cudaSuccess;
     dim3 grid((kNTok + kQTile - 1) / kQTile, heads, B);
-    const int dup = spread && nsplit == 3 && (int)(grid.x * grid.y * grid.z) * 2 <= kSpreadCtas;
-    if (dup) grid.x *= 2;
-    if (nsplit == 3) return launch_ex(attention_tc_kernel<3>, grid, dim3(kAttThreads), AttSmem<3>::kTotal, s, pdl, 1, p, p.out_hi, p.out_lo, p.D, heads, err, trace, dup);
-    return launch_ex(attention_tc_kernel<1>, grid, dim3(kAttThreads), AttSmem<1>::kTotal, s, pdl, 1, p, p.out_hi, p.out_lo, p.D, heads, err, trace, dup);
+    const int ctas = (int)(grid.x * grid.y * grid.z);
+    int dup = 0;
+    TcAttentionPlan q = p;
+    q.chain = 0;
+    if (form == VT_ATT_CHAIN) {
+        if (!p.p2 || ctas * (p.D / 64) > kSpreadCtas) return cudaErrorInvalidValue;
+        q.chain = 1, grid.x *= p.D / 64;
+    } else if (form == VT_ATT_DUP && nsplit == 3 && ctas * 2 <= kSpreadCtas) {
+        dup = 1, grid.x *= 2;
+    }
+    if (nsplit == 3) return launch_ex(attention_tc_kernel<3>, grid, dim3(kAttThreads), AttSmem<3>::kTotal, s, pdl, 1, q, p.out_hi, p.out_lo, p.D, heads, err, trace, dup);
+    return launch_ex(attention_tc_kernel<1>, grid, dim3(kAttThreads), AttSmem<1>::kTotal, s, pdl, 1, q, p.out_hi, p.out_lo, p.D, heads, err, trace, dup);
+}
+
+// chained form: W_proj [D out][D in] (bf16 hi / lo) and the fp32 partial planes [heads][batch][320][D]
+bool tc_attention_plan_chain(TcAttentionPlan* p, const __nv_bfloat16* Whi, const __nv_bfloat16* Wlo, float* P2, int64_t plane_elems) {
+    const uint64_t dims[2] = {(uint64_t)p->D, (uint64_t)p->D}, strides[1] = {(uint64_t)p->D * 2};
+    const uint32_t box[2] = {64, 64};
+    const bool ok = tc_make_map(&p->mW2hi, Whi, 2, dims, strides, box) && tc_make_map(&p->mW2lo, Wlo ? Wlo : Whi, 2, dims, strides, box);
+    p->p2 = P2, p->p2_plane = plane_elems;
+    return ok;
 }
 
 }  // namespace vt

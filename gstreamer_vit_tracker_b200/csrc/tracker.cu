@@ -144,7 +144,9 @@ struct vt_tracker {
     TcGemmPlan plan_patch_x, plan_patch_z, plan_head;
     struct BlockPlans {
         TcGemmPlan qkv, proj, fc1, fc2;
+        TcAttentionPlan att;  // plan_att + this block's W_proj maps (chained form)
     };
+    bool att_chain_ok = false;  // the chained attention form is available (VT_B200_NO_ATT_CHAIN disables)
     std::vector<BlockPlans> plans;
 
     std::map<int, cudaGraphExec_t> graphs;
@@ -376,11 +378,23 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             const vt_tracker::BlockPlans& p = t->plans[l];
             if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
             VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s, pdl, spread));
+            // Latency mode: the proj GEMM is folded into the attention kernel (per-head partial products, D / 64 replicas per tile) and
+            // reduce_ln adds the heads + bias + residual and applies LN2 — one kernel and one dependency edge less per block.
+            const bool att_chain = spread && t->att_chain_ok && n * t->heads * 3 * (D / 64) <= kSpreadCtas;
             if (t->tc_attention)
-                VT_LAUNCH(tc_attention_launch(t->plan_att, n, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace, spread));
+                VT_LAUNCH(tc_attention_launch(att_chain ? p.att : t->plan_att, n, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace,
+                                              att_chain ? VT_ATT_CHAIN : (spread ? VT_ATT_DUP : VT_ATT_PLAIN)));
             else
                 VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
-            VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention, spread));  // fused: + LN2
+            if (att_chain) {
+                ReduceLnArgs r{};
+                r.P = t->Pbuf, r.np = t->heads, r.p_stride = (int64_t)t->maxT * kNTok * D, r.bias = b.proj_b, r.add = t->X, r.add_period = 0;
+                r.X = t->X, r.M = M, r.D = D, r.period = kNTok, r.x_rows = kNTok, r.x_row_off = 0;
+                r.ln_g = b.ln2_g, r.ln_b = b.ln2_b, r.ln_hi = t->ln_hi, r.ln_lo = t->ln_lo, r.ln_rows = kNTok, r.ln_row_off = 0;
+                VT_LAUNCH(launch_reduce_ln(r, s, pdl));
+            } else {
+                VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention, spread));  // fused: + LN2
+            }
             if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
             // Chained form (FC2 partial products inside the FC1 kernel, summed by reduce_ln): shortest critical path for a few targets.
             // From kUnchainTargets targets on the 12 fp32 partial planes per row tile cost more than the hidden round trip
@@ -934,6 +948,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         if (const char* e = getenv("VT_B200_UNCHAIN_N")) t->unchain_n = atoi(e);
         t->chain_mlp = t->fuse_ln && D <= 192 && !getenv("VT_B200_NO_CHAIN");
         if (t->chain_mlp) VT_TRY(cudaMalloc(&t->Pbuf, sizeof(float) * (Hd / 64) * B * kNTok * D));
+        t->att_chain_ok = t->chain_mlp && t->fuse_ln && D / t->heads == 64 && (int)(Hd / 64) >= t->heads && t->nsplit && !getenv("VT_B200_NO_ATT_CHAIN");
         t->split_k = t->chain_mlp && Hd / 64 >= 4 && (C == 64 || C == 128) && !getenv("VT_B200_NO_SPLITK");
         if (t->split_k) {
             VT_TRY(cudaMalloc(&t->Phead, sizeof(float) * 9 * B * kNTx * C));
@@ -1042,6 +1057,10 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             p.fc1.args.bias = b.fc1_b, p.fc1.args.gelu = 1, p.fc1.args.period = kNTok, p.fc1.args.o_mode = 1;
             p.fc1.args.o[0] = oHid[0], p.fc1.args.o[1] = oHid[1];
             if (t->chain_mlp) ok &= tc_plan_chain(&p.fc1, whi(b.fc2_w), wlo(b.fc2_w), (int)D, t->Pbuf, kNTok, B);
+            if (t->att_chain_ok) {
+                p.att = t->plan_att;
+                ok &= tc_attention_plan_chain(&p.att, whi(b.proj_w), wlo(b.proj_w), t->Pbuf, (int64_t)B * kNTok * D);
+            }
             ok &= tc_plan_init(&p.fc2, t->hid_hi, t->hid_lo, rows, whi(b.fc2_w), wlo(b.fc2_w), (int)D, (int)Hd, 0, 0);
             p.fc2.args.bias = b.fc2_b, p.fc2.args.period = kNTok, p.fc2.args.residual = 1, p.fc2.args.c_on = 1;
             p.fc2.maps.R = mXres, p.fc2.args.c = oX;

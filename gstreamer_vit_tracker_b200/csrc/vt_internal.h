@@ -277,15 +277,22 @@ constexpr int kSpreadCtas = 132;
 cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl, bool spread = false);
 struct TcAttentionPlan {      // kernel parameter block (__grid_constant__)
     CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo;
+    CUtensorMap mW2hi, mW2lo;        // chained form: W_proj [D][D], boxes of 64 x 64
     __nv_bfloat16 *out_hi, *out_lo;  // [B][320][D]: the proj GEMM's A operand
-    int D;
+    float* p2;                       // chained form: fp32 partial proj products, plane h = head h: [heads][batch][320][D]
+    int64_t p2_plane;                // elements per plane
+    int D, chain;                    // chain: set at launch
 };
 bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const __nv_bfloat16* Qlo, const __nv_bfloat16* Khi, const __nv_bfloat16* Klo,
                             const __nv_bfloat16* Vthi, const __nv_bfloat16* Vtlo, int batch_heads, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int D,
                             int batch);
+bool tc_attention_plan_chain(TcAttentionPlan* p, const __nv_bfloat16* Whi, const __nv_bfloat16* Wlo, float* P2, int64_t plane_elems);
 cudaError_t tc_attention_setup();
+// form: plain; DUP = two replicas per tile storing the hi / lo output tiles; CHAIN = proj folded in (D / 64 replicas per tile, each
+// stores one 64-column slice of the head's partial proj product; needs tc_attention_plan_chain) — the latter two are "spread" forms
+enum { VT_ATT_PLAIN = 0, VT_ATT_DUP = 1, VT_ATT_CHAIN = 2 };
 cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int nsplit, int* err, cudaStream_t s, bool pdl,
-                                unsigned long long* trace = nullptr, bool spread = false);
+                                unsigned long long* trace = nullptr, int form = VT_ATT_PLAIN);
 cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t s);
 
 }  // namespace vt
