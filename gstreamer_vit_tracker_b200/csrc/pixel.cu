@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, Targ
                                                                const float* __restrict__ lut, float* __restrict__ patches,
                                                                size_t patches_stride, __nv_bfloat16* __restrict__ p_hi,
                                                                __nv_bfloat16* __restrict__ p_lo, unsigned long long* stamp) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the template gather behind this kernel does not depend on it
     if (stamp && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) *stamp = device_time_ns();
     if (f.data_slot) f.data = *f.data_slot;
     const int bi = blockIdx.y;

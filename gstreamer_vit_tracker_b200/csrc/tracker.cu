@@ -268,13 +268,13 @@ static vt_status load_weights(vt_tracker* t, const char* path) {
 }
 
 // template tokens (fixed since init) -> rows 0..63 of every target's sequence: residual stream X and, on the fused-LN
-// tensor-core path, their block-0 LN1 as the bf16 split A operand of the first QKV GEMM
+// tensor-core path, their block-0 LN1 as the bf16 split A operand of the first QKV GEMM.
+// Independent of the crop kernel ahead of it: launched as its programmatic dependent, it does its copies WHILE the crop runs and only
+// then waits for it, so that the patch GEMM behind (whose dependency wait covers this kernel only) still starts after the crop.
 __global__ void gather_template_kernel(float* __restrict__ X, const float* __restrict__ Zemb, const int32_t* __restrict__ slots, int D,
                                        uint32_t* __restrict__ ln_hi, uint32_t* __restrict__ ln_lo, const uint32_t* __restrict__ zln_hi,
                                        const uint32_t* __restrict__ zln_lo, unsigned long long* stamp) {
-    tc::pdl_wait();
     tc::pdl_launch_dependents();
-    if (stamp && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) *stamp = device_time_ns();
     const int bi = blockIdx.y;
     const int n = kNTz * D;
     const size_t so = (size_t)slots[bi] * n, xo = (size_t)bi * kNTok * D;
@@ -282,6 +282,8 @@ __global__ void gather_template_kernel(float* __restrict__ X, const float* __res
         X[xo + i] = Zemb[so + i];
         if (ln_hi && i < n / 2) ln_hi[xo / 2 + i] = zln_hi[so / 2 + i], ln_lo[xo / 2 + i] = zln_lo[so / 2 + i];
     }
+    tc::pdl_wait();  // the crop kernel has completed: end of the preprocess stage
+    if (stamp && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) *stamp = device_time_ns();
 }
 
 static GemmArgs gemm_args(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc, int M, int N, int K) {
@@ -313,9 +315,9 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     {
         dim3 grid((kNTz * D + 255) / 256, n);
         const bool f = t->fuse_ln;
-        gather_template_kernel<<<grid, 256, 0, s>>>(t->X, t->Zemb, t->d_slots, D, f ? (uint32_t*)t->ln_hi : nullptr, (uint32_t*)t->ln_lo,
-                                                    (const uint32_t*)t->zln_hi, (const uint32_t*)t->zln_lo, t->d_stamps + ST_VIT);
-        VT_LAUNCH(cudaGetLastError());
+        VT_LAUNCH(launch_ex(gather_template_kernel, grid, dim3(256), 0, s, t->pdl && !t->debug_capture, 1, t->X, (const float*)t->Zemb,
+                            (const int32_t*)t->d_slots, D, f ? (uint32_t*)t->ln_hi : nullptr, (uint32_t*)t->ln_lo, (const uint32_t*)t->zln_hi,
+                            (const uint32_t*)t->zln_lo, t->d_stamps + ST_VIT));
     }
     const int M = n * kNTok;
     if (t->nsplit == 0) {
