@@ -317,6 +317,7 @@ cudaError_t launch_reduce_ln(const ReduceLnArgs& a, cudaStream_t s, bool pdl) {
         case 3:
             if (a.np == 12) VT_RL(3, 12);
             if (a.np == 4) VT_RL(3, 4);
+            if (a.np == 3) VT_RL(3, 3);  // per-head partial proj products of the chained attention form
             VT_RL(3, 0);
         default: return cudaErrorInvalidValue;
     }
