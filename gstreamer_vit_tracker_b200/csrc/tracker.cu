@@ -108,6 +108,7 @@ struct vt_tracker {
     int* h_tc_err = nullptr;
     const uint8_t** d_frame_slot = nullptr;  // device cell: address of the frame the step reads (d_frame, or the caller's device frame)
     uint8_t** d_host_slot = nullptr;   // device cell: address of the caller's pinned host frame for the zero-copy overlay mirror (or null)
+    uint32_t** d_hblk_slot = nullptr;  // device cell: address of the pinned host result block of the frame's queue slot
     bool inflight_mirrored = false;
     float* d_maps = nullptr;
     OverlayCmdDev *d_cmds = nullptr, *h_cmds = nullptr;
@@ -435,6 +436,8 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     if (t->cfg.box_overlay)
         VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, overlay_format(t->fmt), t->d_res, t->d_slots, n, t->cfg.overlay_gate,
                                      t->d_host_slot, t->d_stamps + ST_OVL_END, s, (uint8_t* const*)t->d_frame_slot, t->pdl && !t->debug_capture));
+    // results, stage stamps and the error flag -> the pinned host block of this frame's queue slot
+    VT_LAUNCH(launch_publish(t->d_res, t->d_hblk_slot, t->res_block_bytes, s, t->pdl && !t->debug_capture));
     return VT_OK;
 }
 
@@ -690,7 +693,8 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
         VT_CUDA(cudaEventRecord(t->ev_up[slot], t->copy_stream));
         VT_CUDA(cudaStreamWaitEvent(t->stream, t->ev_up[slot], 0));
     }
-    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_frame_slot, in_place ? d_src : t->d_frame, t->d_host_slot, q.mirrored ? frame : nullptr, t->stream));
+    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_frame_slot, in_place ? d_src : t->d_frame, t->d_host_slot, q.mirrored ? frame : nullptr,
+                         t->d_hblk_slot, reinterpret_cast<uint32_t*>(t->h_blk[slot]), t->stream));
     ++t->kernel_launches;
     if (in_place) {
         t->frame_valid = 1;
@@ -705,7 +709,8 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     vt_status st = run_forward(t);
     if (st != VT_OK) return st;
     const double hp2 = t->hostprof ? now_us() : 0;
-    VT_CUDA(cudaMemcpyAsync(t->h_blk[slot], t->d_res, t->res_block_bytes, cudaMemcpyDeviceToHost, t->stream));
+    // the result block reaches t->h_blk[slot] through publish_kernel, the last kernel of run_forward (no target active: nothing ran)
+    if (t->active.empty()) VT_CUDA(cudaMemcpyAsync(t->h_blk[slot], t->d_res, t->res_block_bytes, cudaMemcpyDeviceToHost, t->stream));
     VT_CUDA(cudaEventRecord(t->q_done[slot], t->stream));
     t->d2h_bytes += t->res_block_bytes;
     if (t->hostprof) t->hp[0] += hp1 - hp0, t->hp[1] += hp2 - hp1, t->hp[2] += now_us() - hp2;
@@ -827,6 +832,7 @@ void vt_tracker_destroy(vt_tracker* t) {
         if (t->q_done[i]) cudaEventDestroy(t->q_done[i]);
     }
     if (t->d_host_slot) cudaFree(t->d_host_slot);
+    if (t->d_hblk_slot) cudaFree(t->d_hblk_slot);
     if (t->d_frame_slot) cudaFree(t->d_frame_slot);
     if (t->h_cmds) cudaFreeHost(t->h_cmds);
     if (t->stream) cudaStreamDestroy(t->stream);
@@ -921,6 +927,8 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     VT_TRY(cudaMemcpy(t->d_frame_slot, &t->d_frame, sizeof(uint8_t*), cudaMemcpyHostToDevice));
     VT_TRY(cudaMalloc(&t->d_host_slot, sizeof(uint8_t*)));
     VT_TRY(cudaMemset(t->d_host_slot, 0, sizeof(uint8_t*)));
+    VT_TRY(cudaMalloc(&t->d_hblk_slot, sizeof(uint32_t*)));
+    VT_TRY(cudaMemset(t->d_hblk_slot, 0, sizeof(uint32_t*)));
     VT_TRY(cudaMalloc(&t->d_maps, sizeof(float) * 1280 * B));
     VT_TRY(cudaMemset(t->d_maps, 0, sizeof(float) * 1280 * B));
     VT_TRY(cudaMalloc(&t->d_cmds, sizeof(OverlayCmdDev) * kMaxCmds));

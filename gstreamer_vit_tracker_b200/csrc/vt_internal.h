@@ -116,7 +116,9 @@ __device__ __forceinline__ unsigned long long device_time_ns() {
     return t;
 }
 cudaError_t launch_stamp(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, uint8_t** host_slot, uint8_t* host_frame,
-                         cudaStream_t s);
+                         uint32_t** hblk_slot, uint32_t* hblk, cudaStream_t s);
+// last kernel of a frame: result block -> the pinned host block whose address stamp_kernel put into *hblk_slot (zero-copy stores)
+cudaError_t launch_publish(const void* d_blk, uint32_t* const* hblk_slot, size_t bytes, cudaStream_t s, bool pdl);
 
 // ---- pixel kernels (pixel.cu) ------------------------------------------------------------------
 struct FrameDesc {
