@@ -51,7 +51,7 @@ struct AttSmem {
     static constexpr int kP = kParts * kPBytes;  // output staging tile
     static constexpr int kRegion1 = kQK > kP ? kQK : kP;
     static constexpr int kV = kParts * kVBytes;
-    static constexpr int kW2 = kParts * kDh * 128;  // chained form: [W_proj slice hi 64 x 128 B][lo], adjacent = one N = 128 B operand
+    static constexpr int kW2 = kParts * kAttChainW * 128;  // chained form: [W_proj slice hi W x 128 B][lo], adjacent = one N = 2 W B operand
     static constexpr int kTotal = kRegion1 + kV + kW2 + 1024;
 };
 
@@ -111,9 +111,9 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
     __syncthreads();
     if (chain && ctrl && lane == 0) {  // weights never depend on the preceding kernel: W_proj[64 replica .. + 64)[64 h .. 64 h + 64)
         tma_prefetch_desc(&mp.mW2hi);
-        mbar_arrive_expect_tx(&bar_w2, P * kDh * 128);
-        tma_load_2d(sW2, &mp.mW2hi, &bar_w2, h * kDh, replica * 64);
-        if (P == 2) tma_load_2d(sW2 + kDh * 128, &mp.mW2lo, &bar_w2, h * kDh, replica * 64);
+        mbar_arrive_expect_tx(&bar_w2, P * kAttChainW * 128);
+        tma_load_2d(sW2, &mp.mW2hi, &bar_w2, h * kDh, replica * kAttChainW);
+        if (P == 2) tma_load_2d(sW2 + kAttChainW * 128, &mp.mW2lo, &bar_w2, h * kDh, replica * kAttChainW);
     }
     tcgen05_fence_after();
     const uint32_t tmem = tmem_base_s;
@@ -193,13 +193,14 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
                 tcgen05_fence_after();
                 const uint64_t dA = umma_desc_sw128(smem_u32(smem)), dW = umma_desc_sw128(smem_u32(sW2));
                 constexpr uint64_t kLoA = kPBytes >> 4;
+                constexpr uint32_t idescW = umma_idesc_bf16(kQTile, kAttChainW), idescW2 = umma_idesc_bf16(kQTile, 2 * kAttChainW);
 #pragma unroll
                 for (int k = 0; k < kDh / 16; ++k) {
                     if (NSPLIT == 3) {
-                        umma_bf16(tmem, dA + 2 * k, dW + 2 * k, idesc2n, k != 0);  // O_hi x [W_hi; W_lo]
-                        umma_bf16(tmem, dA + kLoA + 2 * k, dW + 2 * k, idesc, 1);   // O_lo x W_hi
+                        umma_bf16(tmem, dA + 2 * k, dW + 2 * k, idescW2, k != 0);  // O_hi x [W_hi; W_lo]
+                        umma_bf16(tmem, dA + kLoA + 2 * k, dW + 2 * k, idescW, 1);  // O_lo x W_hi
                     } else {
-                        umma_bf16(tmem, dA + 2 * k, dW + 2 * k, idesc, k != 0);
+                        umma_bf16(tmem, dA + 2 * k, dW + 2 * k, idescW, k != 0);
                     }
                 }
                 umma_commit(&bar_o2);
@@ -295,27 +296,30 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
             if (lane == 0) mbar_arrive(&bar_a2);
             ok &= mbar_wait(&bar_o2, 0);
             tcgen05_fence_after();
-            float v[16];
-            tmem_ld_32x16(lane_addr + g * 16, v);
+            constexpr int CW = kAttChainW / kColGroups;  // product columns per thread: 8 / 16
+            float v[CW];
+            tmem_ld_cols(lane_addr + g * CW, v);
             if (NSPLIT == 3) {
-                float hl[16];
-                tmem_ld_32x16(lane_addr + 64 + g * 16, hl);
+                float hl[CW];
+                tmem_ld_cols(lane_addr + kAttChainW + g * CW, hl);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += hl[j];
+                for (int j = 0; j < CW; ++j) v[j] += hl[j];
             }
-            // fp32 tile [128][64] staged as two swizzled boxes of [128 rows][128 B] behind the O tiles (dead K area)
-            uint8_t* prow = smem + 2 * kPBytes + (g >> 1) * (kQTile * 128) + row * 128;
+            // fp32 tile [128][W] staged as swizzled boxes of [128 rows][128 B] behind the O tiles (dead K area)
+            uint8_t* prow = smem + 2 * kPBytes + ((g * CW) >> 5) * (kQTile * 128) + row * 128;
+            const int ch0 = ((g * CW) & 31) >> 2;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(prow + ((((g & 1) * 4 + q) ^ (row & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            for (int q = 0; q < CW / 4; ++q)
+                *reinterpret_cast<float4*>(prow + (((ch0 + q) ^ (row & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             softmax_bar_sync();
-            // -> partial plane h: [B][320][D] fp32, columns 64 replica ..: 256 contiguous bytes per row, 2 rows per warp instruction
+            // -> partial plane h: [B][320][D] fp32, columns W replica ..: W * 4 contiguous bytes per row
+            constexpr int CH = kAttChainW / 4, RPP = kSoftmaxThreads / CH;  // 16-byte chunks per row, rows per pass
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = (tid >> 4) + 32 * i, c16 = tid & 15, bx = c16 >> 3, ch = c16 & 7;
+            for (int i = 0; i < kQTile / RPP; ++i) {
+                const int r = tid / CH + RPP * i, c16 = tid % CH, bx = c16 >> 3, ch = c16 & 7;
                 if (q0 + r < kNTok) {
                     const float4 val = *reinterpret_cast<const float4*>(smem + 2 * kPBytes + bx * (kQTile * 128) + r * 128 + ((ch ^ (r & 7)) << 4));
-                    float* dst = mp.p2 + (int64_t)h * mp.p2_plane + ((int64_t)b * kNTok + q0 + r) * D + replica * 64 + c16 * 4;
+                    float* dst = mp.p2 + (int64_t)h * mp.p2_plane + ((int64_t)b * kNTok + q0 + r) * D + replica * kAttChainW + c16 * 4;
                     *reinterpret_cast<float4*>(dst) = val;
                 }
             }
@@ -379,8 +383,8 @@ cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int 
     TcAttentionPlan q = p;
     q.chain = 0;
     if (form == VT_ATT_CHAIN) {
-        if (!p.p2 || ctas * (p.D / 64) > kSpreadCtas) return cudaErrorInvalidValue;
-        q.chain = 1, grid.x *= p.D / 64;
+        if (!p.p2 || ctas * (p.D / kAttChainW) > kSpreadCtas) return cudaErrorInvalidValue;
+        q.chain = 1, grid.x *= p.D / kAttChainW;
     } else if (form == VT_ATT_DUP && nsplit == 3 && ctas * 2 <= kSpreadCtas) {
         dup = 1, grid.x *= 2;
     }
@@ -391,7 +395,7 @@ cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int 
 // chained form: W_proj [D out][D in] (bf16 hi / lo) and the fp32 partial planes [heads][batch][320][D]
 bool tc_attention_plan_chain(TcAttentionPlan* p, const __nv_bfloat16* Whi, const __nv_bfloat16* Wlo, float* P2, int64_t plane_elems) {
     const uint64_t dims[2] = {(uint64_t)p->D, (uint64_t)p->D}, strides[1] = {(uint64_t)p->D * 2};
-    const uint32_t box[2] = {64, 64};
+    const uint32_t box[2] = {64, kAttChainW};
     const bool ok = tc_make_map(&p->mW2hi, Whi, 2, dims, strides, box) && tc_make_map(&p->mW2lo, Wlo ? Wlo : Whi, 2, dims, strides, box);
     p->p2 = P2, p->p2_plane = plane_elems;
     return ok;

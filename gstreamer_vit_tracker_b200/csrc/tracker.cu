@@ -383,7 +383,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s, pdl, spread));
             // Latency mode: the proj GEMM is folded into the attention kernel (per-head partial products, D / 64 replicas per tile) and
             // reduce_ln adds the heads + bias + residual and applies LN2 — one kernel and one dependency edge less per block.
-            const bool att_chain = spread && t->att_chain_ok && n * t->heads * 3 * (D / 64) <= kSpreadCtas;
+            const bool att_chain = spread && t->att_chain_ok && n * t->heads * 3 * (D / kAttChainW) <= kSpreadCtas;
             if (t->tc_attention)
                 VT_LAUNCH(tc_attention_launch(att_chain ? p.att : t->plan_att, n, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace,
                                               att_chain ? VT_ATT_CHAIN : (spread ? VT_ATT_DUP : VT_ATT_PLAIN)));

@@ -293,6 +293,7 @@ cudaError_t tc_attention_setup();
 // form: plain; DUP = two replicas per tile storing the hi / lo output tiles; CHAIN = proj folded in (D / 64 replicas per tile, each
 // stores one 64-column slice of the head's partial proj product; needs tc_attention_plan_chain) — the latter two are "spread" forms
 enum { VT_ATT_PLAIN = 0, VT_ATT_DUP = 1, VT_ATT_CHAIN = 2 };
+constexpr int kAttChainW = 32;  // columns of the partial proj product per replica CTA of the chained form (32 or 64)
 cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int nsplit, int* err, cudaStream_t s, bool pdl,
                                 unsigned long long* trace = nullptr, int form = VT_ATT_PLAIN);
 cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t s);
