@@ -17,11 +17,12 @@
 //   epilogue   O / sum -> bf16 (hi, lo) tile staged in shared memory -> coalesced 16-byte stores into the proj GEMM's A operand.
 // The output staging tile aliases the Q/K area once S is complete (~192 KB of shared memory per CTA).
 //
-// Chained form (latency mode, `chain`): the proj GEMM is folded in.  The staged O tile (bf16 hi / lo, 128B-swizzled K-major) IS a UMMA
-// A operand, so the CTA multiplies it with a 64-row slice of W_proj[:, 64 h .. 64 h + 64) (fetched before the dependency wait) into TMEM
-// columns 0..127 (dead P) and stores the fp32 partial product [128 x 64] of head h to plane h of the partial buffer; reduce_ln_kernel
-// adds the heads in index order with bias, residual and LayerNorm 2.  Each (query tile, head) is computed by D / 64 CTAs, one
-// per 64-column slice of the product, so that every CTA stores 32 KB: one kernel and one dependency edge less per block.
+// Chained form (latency mode, `chain`): the proj GEMM is folded in.  The normalised O tile goes back into tensor memory as packed
+// bf16 (hi, lo) — a UMMA A operand, like P — and the CTA multiplies it with a kAttChainW-row slice of W_proj[:, 64 h .. 64 h + 64)
+// (fetched before the dependency wait) into TMEM columns 0.. (dead P) and stores the fp32 partial product [128 x kAttChainW] of
+// head h to plane h of the partial buffer; reduce_ln_kernel adds the heads in index order with bias, residual and LayerNorm 2.
+// Each (query tile, head) is computed by D / kAttChainW CTAs, one per column slice of the product, so that every CTA stores only
+// 16 KB: one kernel and one dependency edge less per block.
 #include "tc_common.cuh"
 #include "vt_internal.h"
 
@@ -39,6 +40,7 @@ constexpr int kVBytes = kDh * kNTok * 2;          // 40 KB (5 blocks of [64 x 64
 constexpr int kPBytes = kQTile * kKeyChunk * 2;   // 16 KB
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColO = 320;
+constexpr uint32_t kColA = 128;  // chained form: normalised O as a packed bf16 A operand (dead P columns; the product uses 0..63)
 constexpr int kSoftmaxWarps = 16, kSoftmaxThreads = kSoftmaxWarps * 32;
 constexpr int kAttThreads = kSoftmaxThreads + 32;     // + one control warp (TMA, MMA issue, TMEM alloc)
 constexpr int kColGroups = kSoftmaxThreads / kQTile;  // 4 threads per query row
@@ -191,16 +193,18 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
                 ok &= mbar_wait(&bar_w2, 0);
                 ok &= mbar_wait(&bar_a2, 0);
                 tcgen05_fence_after();
-                const uint64_t dA = umma_desc_sw128(smem_u32(smem)), dW = umma_desc_sw128(smem_u32(sW2));
-                constexpr uint64_t kLoA = kPBytes >> 4;
+                // A = normalised O, written by the softmax warps as packed bf16 into TMEM columns kColA.. (K-step k = their column group
+                // k: 8 columns hi, 8 columns lo), so the UMMA fetches only the weight slice from shared memory
+                const uint64_t dW = umma_desc_sw128(smem_u32(sW2));
                 constexpr uint32_t idescW = umma_idesc_bf16(kQTile, kAttChainW), idescW2 = umma_idesc_bf16(kQTile, 2 * kAttChainW);
 #pragma unroll
                 for (int k = 0; k < kDh / 16; ++k) {
+                    const uint32_t ah = tmem + kColA + k * 16;
                     if (NSPLIT == 3) {
-                        umma_bf16(tmem, dA + 2 * k, dW + 2 * k, idescW2, k != 0);  // O_hi x [W_hi; W_lo]
-                        umma_bf16(tmem, dA + kLoA + 2 * k, dW + 2 * k, idescW, 1);  // O_lo x W_hi
+                        umma_bf16_ta(tmem, ah, dW + 2 * k, idescW2, k != 0);  // O_hi x [W_hi; W_lo]
+                        umma_bf16_ta(tmem, ah + 8, dW + 2 * k, idescW, 1);    // O_lo x W_hi
                     } else {
-                        umma_bf16(tmem, dA + 2 * k, dW + 2 * k, idescW, k != 0);
+                        umma_bf16_ta(tmem, ah, dW + 2 * k, idescW, k != 0);
                     }
                 }
                 umma_commit(&bar_o2);
@@ -282,15 +286,20 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) split2_bf16(v[j] * inv, v[j + 1] * inv, hi[j >> 1], lo[j >> 1]);
+            if (chain) {  // A operand of the chained product, in tensor memory
+                tmem_st_32x8(lane_addr + kColA + g * 16, hi);
+                if (P == 2) tmem_st_32x8(lane_addr + kColA + g * 16 + 8, lo);
+                tmem_st_wait();
+            } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int off = row * 128 + (((2 * g + j) ^ (row & 7)) << 4);
-                *reinterpret_cast<uint4*>(smem + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                if (P == 2) *reinterpret_cast<uint4*>(smem + kPBytes + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                for (int j = 0; j < 2; ++j) {
+                    const int off = row * 128 + (((2 * g + j) ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4*>(smem + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    if (P == 2) *reinterpret_cast<uint4*>(smem + kPBytes + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
             }
         }
         if (chain) {
-            fence_proxy_async_smem();  // the staged O tile is read by the tensor core (async proxy)
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_a2);
