@@ -578,7 +578,8 @@ cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, 
 __global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t len, int W, int H, int fmt,
                                                           const DeviceResult* __restrict__ res, const int32_t* __restrict__ slots,
                                                           float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
-                                                          uint8_t* const* frame_slot) {
+                                                          uint8_t* const* frame_slot, const uint32_t* __restrict__ blk,
+                                                          uint32_t* const* hblk_slot, int blk_words) {
     // frame / host addresses and the slot table were written at the start of the frame (complete long before the kernel ahead of this
     // one): every thread fetches them in one batch; only the decode result waits for the dependency
     if (frame_slot) frame = *frame_slot;
@@ -604,15 +605,23 @@ __global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t
             __syncthreads();
         }
     }
-    if (stamp_end && threadIdx.x == 0 && blockIdx.x == 0) *stamp_end = device_time_ns();
+    if (blockIdx.x != 0) return;
+    if (stamp_end && threadIdx.x == 0) *stamp_end = device_time_ns();
+    if (hblk_slot) {  // last kernel of the frame: publish the result block (see publish_kernel) — one kernel boundary less
+        uint32_t* dst = *reinterpret_cast<uint32_t* const volatile*>(hblk_slot);
+        __threadfence();  // the end stamp above is part of the block
+        __syncthreads();
+        if (dst)
+            for (int i = threadIdx.x; i < blk_words; i += blockDim.x) dst[i] = __ldcg(blk + i);
+    }
 }
 
 cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
                                const int32_t* d_slots, int n, float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
-                               cudaStream_t s, uint8_t* const* frame_slot, bool pdl) {
+                               cudaStream_t s, uint8_t* const* frame_slot, bool pdl, const void* d_blk, uint32_t* const* hblk_slot, size_t blk_bytes) {
     if (n <= 0) return cudaSuccess;
     return launch_ex(box_overlay_kernel, dim3(n), dim3(256), 0, s, pdl, 1, d_frame, len, width, height, format, d_res, d_slots, gate, host_slot,
-                     stamp_end, frame_slot);
+                     stamp_end, frame_slot, (const uint32_t*)d_blk, hblk_slot, (int)(blk_bytes / 4));
 }
 
 // per-frame, outside the graph: submit stamp + the addresses that change from frame to frame, handed to the graph's kernels through

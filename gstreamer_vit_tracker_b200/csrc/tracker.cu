@@ -435,9 +435,10 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
         VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, t->d_stamps, s));
     if (t->cfg.box_overlay)
         VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, overlay_format(t->fmt), t->d_res, t->d_slots, n, t->cfg.overlay_gate,
-                                     t->d_host_slot, t->d_stamps + ST_OVL_END, s, (uint8_t* const*)t->d_frame_slot, t->pdl && !t->debug_capture));
-    // results, stage stamps and the error flag -> the pinned host block of this frame's queue slot
-    VT_LAUNCH(launch_publish(t->d_res, t->d_hblk_slot, t->res_block_bytes, s, t->pdl && !t->debug_capture));
+                                     t->d_host_slot, t->d_stamps + ST_OVL_END, s, (uint8_t* const*)t->d_frame_slot, t->pdl && !t->debug_capture,
+                                     t->d_res, t->d_hblk_slot, t->res_block_bytes));  // ... and publishes the result block
+    else  // results, stage stamps and the error flag -> the pinned host block of this frame's queue slot
+        VT_LAUNCH(launch_publish(t->d_res, t->d_hblk_slot, t->res_block_bytes, s, t->pdl && !t->debug_capture));
     return VT_OK;
 }
 

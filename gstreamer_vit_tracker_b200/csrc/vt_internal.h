@@ -157,7 +157,8 @@ cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, 
 // device-side box overlay straight from the decode result (rect thickness 3 + crosshair 15, src/pipeline.rs:165-168)
 cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
                                const int32_t* d_slots, int n, float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
-                               cudaStream_t s, uint8_t* const* frame_slot = nullptr, bool pdl = false);
+                               cudaStream_t s, uint8_t* const* frame_slot = nullptr, bool pdl = false, const void* d_blk = nullptr,
+                               uint32_t* const* hblk_slot = nullptr, size_t blk_bytes = 0);  // d_blk..: also publishes the result block
 
 // ---- ViT kernels (vit.cu) ----------------------------------------------------------------------
 struct GemmArgs {
