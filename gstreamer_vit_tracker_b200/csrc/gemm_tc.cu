@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const bool st_hi = !a.dup_hl || blockIdx.z == 0, st_lo = kLo && (!a.dup_hl || blockIdx.z == 1);
     const int npre = num_kb < kTcStages ? num_kb : kTcStages;
     constexpr uint32_t kAcc1Cols = kLo ? 2 * BN : BN;  // bf16x3 keeps hi*lo in a second column half
-    const uint32_t tmem_cols = a.chain_n == 0 ? (kAcc1Cols < 32 ? 32 : kAcc1Cols) : (kAcc1Cols + acc2_cols <= 128 ? 128 : (kAcc1Cols + acc2_cols <= 256 ? 256 : 512));
+    constexpr uint32_t kColA2 = 256;  // sliced chain: the hidden tile as a packed bf16 A operand (columns 256..319)
+    const uint32_t tmem_need = a.chain_n == 0 ? kAcc1Cols : ((sliced && kLo) ? kColA2 + 64 : kAcc1Cols + acc2_cols);
+    const uint32_t tmem_cols = tmem_need <= 32 ? 32 : (tmem_need <= 64 ? 64 : (tmem_need <= 128 ? 128 : (tmem_need <= 256 ? 256 : 512)));
     bool ok = true;
     TraceRec tr;
     tr.begin(&trace_slot, a.trace, a.trace_id);
@@ -394,7 +396,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         for (int q = 0; q < CPT / 4; ++q)
             *reinterpret_cast<float4*>(c_row + (((c_chunk0 + q) ^ sw) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
-    if (a.o_mode) {  // (o_mode 3: staged only — the tile is the A operand of the chained GEMM)
+    // sliced chain with the 64-column tile: the hidden tile goes back into tensor memory as packed bf16 (thread (row, g) = K-step g: 8
+    // columns hi, 8 columns lo), so the chained UMMAs fetch only the weight slice from shared memory
+    const bool a_tmem = BN == kChainBN && sliced && kLo && a.o_mode == 3;
+    if (a_tmem) {
+        if constexpr (CPT == 16) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) split2_bf16(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
+            const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + kColA2 + g * 16;
+            tmem_st_32x8(ta, hi);
+            tmem_st_32x8(ta + 8, lo);
+            tmem_st_wait();
+        }
+    } else if (a.o_mode) {  // (o_mode 3: staged only — the tile is the A operand of the chained GEMM)
         if (o_which < 2) {
             stage_split<CPT>(v, smem + SM::kOffOhi, smem + SM::kOffOlo, row, g, kLo);
         } else {  // V^T: two unswizzled [BN d][64 tokens] sub-tiles; lanes are consecutive tokens -> 64-byte contiguous runs
@@ -410,7 +425,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             }
         }
     }
-    if (a.o_mode == 3) fence_proxy_async_smem();  // the staged tile is read by the tensor core (async proxy) in the chained GEMM
+    if (a.o_mode == 3) {
+        if (a_tmem) tcgen05_fence_before();
+        else fence_proxy_async_smem();  // the staged tile is read by the tensor core (async proxy) in the chained GEMM
+    }
     __syncthreads();
     if (do_ln && g == 0) {  // one thread per row: (sum, M2) over the BN columns of this CTA (Chan), sent to every CTA of the cluster
         float s = 0.f;
@@ -462,8 +480,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2), idesc2n = umma_idesc_bf16(kTcBM, 2 * N2);
 #pragma unroll
                 for (int k = 0; k < kChainBN / 16; ++k) {
-                    umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + 2 * k, idesc2n, k != 0);
-                    umma_bf16(tmem + kAcc1Cols, dA + kLoA + 2 * k, dB + 2 * k, idesc2, 1);
+                    umma_bf16_ta(tmem + kAcc1Cols, tmem + kColA2 + 16 * k, dB + 2 * k, idesc2n, k != 0);
+                    umma_bf16_ta(tmem + kAcc1Cols, tmem + kColA2 + 16 * k + 8, dB + 2 * k, idesc2, 1);
                 }
             } else {
                 const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2);  // K = the 64 hidden columns of this CTA
