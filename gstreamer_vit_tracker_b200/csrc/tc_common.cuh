@@ -67,11 +67,13 @@ struct TraceRec {
         slot = shared_slot;
         if (threadIdx.x == 0) {
             unsigned long long* rec = nullptr;
-            if (trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+            // id bit 8 (VT_B200_TRACE_LASTX): trace the CTA with the LAST blockIdx.x instead of the first (e.g. a V^T tile of the QKV GEMM)
+            const unsigned bx = (id & 0x100) ? gridDim.x - 1 : 0u;
+            if (trace && blockIdx.x == bx && blockIdx.y == 0 && blockIdx.z == 0) {
                 const unsigned long long i = atomicAdd(trace, 1ull);
                 if (i < 2048) {
                     rec = trace + 1 + 8 * i;
-                    rec[0] = (unsigned long long)id, rec[1] = globaltimer_ns();
+                    rec[0] = (unsigned long long)(id & 0xff), rec[1] = globaltimer_ns();
                 }
             }
             *slot = rec;

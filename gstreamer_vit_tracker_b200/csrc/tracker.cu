@@ -1103,6 +1103,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
             for (auto& p : t->plans) {
                 p.qkv.args.trace = p.proj.args.trace = p.fc1.args.trace = p.fc2.args.trace = t->d_trace;
                 p.qkv.args.trace_id = 2, p.proj.args.trace_id = 3, p.fc1.args.trace_id = 4, p.fc2.args.trace_id = 5;
+                if (getenv("VT_B200_TRACE_LASTX")) p.qkv.args.trace_id |= 0x100, p.fc1.args.trace_id |= 0x100;  // trace the last column tile
             }
         }
     }
