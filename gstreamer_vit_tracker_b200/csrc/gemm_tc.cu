@@ -416,12 +416,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             const int sub = (row >> 6) * (BN * kHalfRows) + (g * CPT) * kHalfRows + (row & 63);
             __nv_bfloat16* th = reinterpret_cast<__nv_bfloat16*>(smem + SM::kOffOhi) + sub;
             __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(smem + SM::kOffOlo) + sub;
+            // (packed cvt.rn.bf16x2: the scalar cvt.rn.bf16.f32 runs on the 16/clk conversion pipe — 32 of them per thread made the V^T
+            // tiles finish 0.3 us after the Q / K tiles)
+            unsigned short* uh = reinterpret_cast<unsigned short*>(th);
+            unsigned short* ul = reinterpret_cast<unsigned short*>(tl);
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                __nv_bfloat16 h, l;
-                split_bf16(v[j], h, l);
-                th[j * kHalfRows] = h;
-                if (kLo) tl[j * kHalfRows] = l;
+            for (int j = 0; j < CPT; j += 2) {
+                uint32_t h2, l2;
+                split2_bf16(v[j], v[j + 1], h2, l2);
+                uh[j * kHalfRows] = (unsigned short)(h2 & 0xffffu), uh[(j + 1) * kHalfRows] = (unsigned short)(h2 >> 16);
+                if (kLo) ul[j * kHalfRows] = (unsigned short)(l2 & 0xffffu), ul[(j + 1) * kHalfRows] = (unsigned short)(l2 >> 16);
             }
         }
     }

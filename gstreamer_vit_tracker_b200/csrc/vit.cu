@@ -298,10 +298,13 @@ __global__ void __launch_bounds__(32 * kReduceRows) reduce_ln_kernel(const Reduc
     for (int i = 0; i < NPAIR; ++i) {
         const float2 g2 = gam[i], b2 = bet[i];
         const float y0 = (acc[i].x - mean) * rstd * g2.x + b2.x, y1 = (acc[i].y - mean) * rstd * g2.y + b2.y;
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
-        oh[lane + 32 * i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        ol[lane + 32 * i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        // packed cvt.rn.bf16x2 (bit-identical to two scalar splits; the scalar conversion runs on the slow 16/clk pipe)
+        uint32_t h2, l2;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(y1), "f"(y0));
+        const float r0 = y0 - __uint_as_float(h2 << 16), r1 = y1 - __uint_as_float(h2 & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(r1), "f"(r0));
+        oh[lane + 32 * i] = h2;
+        ol[lane + 32 * i] = l2;
     }
 }
 
