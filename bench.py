@@ -200,9 +200,17 @@ def cpu_baseline(args, n_frames):
         t_conv += b - a
         t_track += c - b
     dt = time.perf_counter() - t0
+    # the reference sizes its conversion pool at 8 threads (/root/reference/src/main.rs:43-46): the same conversion with 8 and with 1
+    conv_t = {}
+    for nt in (8, 1):
+        a = time.perf_counter()
+        for i in range(20):
+            oracle.nv12_to_rgb(frames[2 + i % n_frames], W, H, nt)
+        conv_t[nt] = (time.perf_counter() - a) / 20 * 1e3
     return {"value": n_frames / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n_frames} frames of cfg2 (convert + VitTrack::update + box overlay), OpenMP {threads} threads",
-            "conv_ms": t_conv / n_frames * 1e3, "track_ms": t_track / n_frames * 1e3}
+            "conv_ms": t_conv / n_frames * 1e3, "track_ms": t_track / n_frames * 1e3,
+            "conv_ms_8_threads": conv_t[8], "conv_ms_1_thread": conv_t[1]}
 
 
 # ---------------------------------------------------------------------------------------------------
