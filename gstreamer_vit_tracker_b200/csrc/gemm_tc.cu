@@ -23,6 +23,12 @@
 // Precision: VT_GEMM_TCGEN05_BF16 issues A_hi*W_hi only; VT_GEMM_TCGEN05_BF16X3 adds A_hi*W_lo + A_lo*W_hi into the same
 // accumulator (error ~2^-17 relative per product), which is what the 1e-3 score / exact-box parity needs; the extra tensor
 // FLOPs are free at these sizes (the step is latency bound).
+// Forms selected at launch (tc_gemm_launch): split-K over blockIdx.z (patch embed, head conv: fp32 partial planes); a chained second
+// GEMM (FC1 -> FC2 partial products, the hidden tile never leaves the SM); LayerNorm fused through a cluster exchange; and, in latency
+// mode (`spread`: at most two live handles on the GPU, most SMs idle), replicas of a tile over blockIdx.z so that each replica stores
+// a share of the epilogue output — a CTA stores at ~26 B/clk, which is what bounds the 32..96 KB epilogues: FC1 chain in three
+// 64-column slices (the GELU'd hidden tile then is a TMEM A operand), QKV scatter as hi / lo replicas, fused-LN GEMM as fp32 / LN-hi /
+// LN-lo replicas.  All forms are re-associations of the same sums (tests/test_gpu_tracker.py::test_kernel_forms_agree).
 // The 3x3 head convolution runs through the same kernel: its A operand is gathered by TMA from the [B,16,16,D] token grid with
 // shifted (possibly negative) coordinates; out-of-bounds elements are zero-filled by the TMA unit = zero padding of the conv.
 #include <stdlib.h>
@@ -42,8 +48,8 @@ constexpr int kTileABytes = kTcBM * kTcBK * 2;  // 16 KB, one precision part
 constexpr int kMaxChainN = 192;                 // widest chained second GEMM (TMEM: 128 + N2 <= 512 columns)
 constexpr int kChainBN = 64;                    // the chained GEMM consumes a 64-column hidden tile
 
-// BN = 64: the throughput tile (FC1 + chained FC2).  BN = 32: twice the CTAs, half the epilogue per CTA and a shorter operand fetch
-// per UMMA for the GEMMs whose epilogue is on the critical path of a single stream (QKV, proj, patch embed, head conv).
+// BN = 64: the default tile.  BN = 32 (VT_B200_TILE32): twice the CTAs, half the epilogue per CTA — measured without gain
+// (profiles/r1d_final.md), kept as an option for QKV, proj, patch embed and head conv.
 template <int NSPLIT, int BN>
 struct TcSmem {
     static constexpr int kParts = NSPLIT == 3 ? 2 : 1;
