@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=60)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="tiny", choices=["tiny", "nano"])
-    ap.add_argument("--gemm", default="tcgen05x3", choices=["fp32simt", "tcgen05x3", "tcgen05"],
+    ap.add_argument("--gemm", default="tcgen05x3", choices=list(GEMM_MODES),
                     help="precision/engine of the dense contractions (tcgen05x3 = bf16 split operands, the parity-safe default)")
     ap.add_argument("--streams-per-gpu", type=int, default=1)
     ap.add_argument("--ring", type=int, default=384,
@@ -173,6 +173,9 @@ def run_reference(args):
         "note": "reference = CPU oracle port (the Rust reference + absent vit_tracker crate cannot be built in this image)"}))
 
 
+GEMM_MODES = {"fp32simt": 0, "tcgen05x3": 1, "tcgen05": 2, "tcgen05fp16": 3}
+
+
 def cpu_baseline(args, n_frames):
     from gstreamer_vit_tracker_b200 import synth
     from oracle import oracle
@@ -249,7 +252,7 @@ def run_b200(args):
         st = synth.SyntheticStream(spec)
         fb = st.frame_bytes()
         trk = api.VitTrack.new(wpath, spec.width, spec.height, fmt="nv12", device=local_rank, box_overlay=True,
-                               upload_window=not args.full_upload, gemm_mode={"fp32simt": 0, "tcgen05x3": 1, "tcgen05": 2}[args.gemm])
+                               upload_window=not args.full_upload, gemm_mode=GEMM_MODES[args.gemm])
         pin = api.PinnedBuffer(ring_n * fb)
         host = pin.array.reshape(ring_n, fb)
         for i in range(ring_n):
@@ -346,7 +349,7 @@ def run_b200(args):
         try:
             s0_ = streams[0]
             ttrk = api.VitTrack.new(wpath, s0_["spec"].width, s0_["spec"].height, fmt="nv12", device=local_rank, box_overlay=True,
-                                    gemm_mode={"fp32simt": 0, "tcgen05x3": 1, "tcgen05": 2}[args.gemm])
+                                    gemm_mode=GEMM_MODES[args.gemm])
         finally:
             del os.environ["VT_B200_TRACE"]
         ttrk.init(s0_["pristine"][0], api.BBox(*s0_["init_box"]))
@@ -423,7 +426,8 @@ def run_b200(args):
         out = {
             "metric": METRIC, "value": frames_g / (ms_dev_g * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_dev_g / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32simt": "f32", "tcgen05x3": "bf16x3 (split bf16 operands, fp32 accumulate)", "tcgen05": "bf16"}[args.gemm],
+            "dtype": {"fp32simt": "f32", "tcgen05x3": "bf16x3 (split bf16 operands, fp32 accumulate)", "tcgen05": "bf16",
+                      "tcgen05fp16": "f16 (single-pass fp16 operands, fp32 accumulate)"}[args.gemm],
             "data": "synthetic",
             "config": {"workload": workload_name(args), "resolution": "1920x1080", "format": "NV12", "targets": 1, "model": args.model, "gemm": args.gemm,
                        "streams_per_gpu": S, "weights": "constructed random-init (SURVEY.md §8c)",

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libvittrack_b200.so")
 
 VT_OK, VT_ERR_INVALID, VT_ERR_CUDA, VT_ERR_WEIGHTS, VT_ERR_CROP_OUTSIDE, VT_ERR_NOT_INIT, VT_ERR_GLYPH = 0, -1, -2, -3, -4, -5, -6
 VT_FMT_NV12, VT_FMT_RGB24, VT_FMT_GRAY8 = 0, 1, 2
-VT_GEMM_FP32_SIMT, VT_GEMM_TCGEN05_BF16X3, VT_GEMM_TCGEN05_BF16 = 0, 1, 2
+VT_GEMM_FP32_SIMT, VT_GEMM_TCGEN05_BF16X3, VT_GEMM_TCGEN05_BF16, VT_GEMM_TCGEN05_FP16 = 0, 1, 2, 3
 VT_OV_RECT, VT_OV_CROSSHAIR, VT_OV_TEXT, VT_OV_BACKGROUND, VT_OV_CURSOR, VT_OV_SELECTION = range(6)
 
 

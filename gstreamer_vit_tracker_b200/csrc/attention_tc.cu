@@ -48,7 +48,7 @@ constexpr int kKeysPerThread = kKeyChunk / kColGroups;  // 16 keys of every chun
 
 template <int NSPLIT>
 struct AttSmem {
-    static constexpr int kParts = NSPLIT == 3 ? 2 : 1;
+    static constexpr int kParts = NSPLIT == 3 ? 2 : 1;  // NSPLIT: 1 = bf16, 2 = fp16 (single pass), 3 = bf16 hi + lo
     static constexpr int kQK = kParts * (kQBytes + kKBytes);
     static constexpr int kP = kParts * kPBytes;  // output staging tile
     static constexpr int kRegion1 = kQK > kP ? kQK : kP;
@@ -146,7 +146,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
             tcgen05_fence_after();
             const uint64_t dQ = umma_desc_sw128(smem_u32(sQ)), dK = umma_desc_sw128(smem_u32(sK));
             constexpr int kHalf = kNTok / 2;  // 160 keys per UMMA: two equal N = 160 instructions instead of N = 256 + a fetch-bound N = 64
-            constexpr uint32_t idescS = umma_idesc_bf16(kQTile, kHalf);
+            constexpr uint32_t idescS = umma_idesc_h<NSPLIT == 2>(kQTile, kHalf);
             constexpr uint64_t kLoQ = kQBytes >> 4, kLoK = kKBytes >> 4, kK2 = (kHalf * 128) >> 4;  // descriptor address units (16 B)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -170,7 +170,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
             // bf16x3 as P_hi x [V_hi; V_lo] (ONE N = 128 UMMA into O columns [0, 64) = hi*hi and [64, 128) = hi*lo) + P_lo x V_hi; the epilogue
             // adds the two column halves.  K-step k of chunk c = the 16 keys of softmax column group k: P_hi in TMEM columns
             // 64 c + 16 k .. + 7, P_lo in the next 8 (two bf16 per column).
-            constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kDh), idesc2n = umma_idesc_bf16(kQTile, 2 * kDh);
+            constexpr uint32_t idesc = umma_idesc_h<NSPLIT == 2>(kQTile, kDh), idesc2n = umma_idesc_h<NSPLIT == 2>(kQTile, 2 * kDh);
             constexpr uint64_t kBlkV = (uint64_t)(P * kDh * 128) >> 4;
             ok &= mbar_wait(&bar_v, 0);
             for (int c = 0; c < kNChunks; ++c) {
@@ -196,7 +196,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
                 // A = normalised O, written by the softmax warps as packed bf16 into TMEM columns kColA.. (K-step k = their column group
                 // k: 8 columns hi, 8 columns lo), so the UMMA fetches only the weight slice from shared memory
                 const uint64_t dW = umma_desc_sw128(smem_u32(sW2));
-                constexpr uint32_t idescW = umma_idesc_bf16(kQTile, kAttChainW), idescW2 = umma_idesc_bf16(kQTile, 2 * kAttChainW);
+                constexpr uint32_t idescW = umma_idesc_h<NSPLIT == 2>(kQTile, kAttChainW), idescW2 = umma_idesc_h<NSPLIT == 2>(kQTile, 2 * kAttChainW);
 #pragma unroll
                 for (int k = 0; k < kDh / 16; ++k) {
                     const uint32_t ah = tmem + kColA + k * 16;
@@ -250,7 +250,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
                     const float e1 = ex2_approx(fmaf(__uint_as_float(r[c & 1][j + 1]), k2, -mk));
                     sum += e0;
                     sum += e1;
-                    split2_bf16(e0, e1, hi[j >> 1], lo[j >> 1]);
+                    split2_h<NSPLIT == 2>(e0, e1, hi[j >> 1], lo[j >> 1]);
                 }
             }
             if (q_ok) {  // P replaces the S values this thread has just consumed: columns [0, 8) of its 16 hold P_hi, [8, 16) P_lo
@@ -285,7 +285,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
             }
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) split2_bf16(v[j] * inv, v[j + 1] * inv, hi[j >> 1], lo[j >> 1]);
+            for (int j = 0; j < 16; j += 2) split2_h<NSPLIT == 2>(v[j] * inv, v[j + 1] * inv, hi[j >> 1], lo[j >> 1]);
             if (chain) {  // A operand of the chained product, in tensor memory
                 tmem_st_32x8(lane_addr + kColA + g * 16, hi);
                 if (P == 2) tmem_st_32x8(lane_addr + kColA + g * 16 + 8, lo);
@@ -380,6 +380,8 @@ bool tc_attention_plan_init(TcAttentionPlan* p, const __nv_bfloat16* Qhi, const 
 cudaError_t tc_attention_setup() {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem<1>::kTotal);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem<2>::kTotal);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem<3>::kTotal);
 }
 
@@ -398,6 +400,7 @@ cudaError_t tc_attention_launch(const TcAttentionPlan& p, int B, int heads, int 
         dup = 1, grid.x *= 2;
     }
     if (nsplit == 3) return launch_ex(attention_tc_kernel<3>, grid, dim3(kAttThreads), AttSmem<3>::kTotal, s, pdl, 1, q, p.out_hi, p.out_lo, p.D, heads, err, trace, dup);
+    if (nsplit == 2) return launch_ex(attention_tc_kernel<2>, grid, dim3(kAttThreads), AttSmem<2>::kTotal, s, pdl, 1, q, p.out_hi, p.out_lo, p.D, heads, err, trace, dup);
     return launch_ex(attention_tc_kernel<1>, grid, dim3(kAttThreads), AttSmem<1>::kTotal, s, pdl, 1, q, p.out_hi, p.out_lo, p.D, heads, err, trace, dup);
 }
 

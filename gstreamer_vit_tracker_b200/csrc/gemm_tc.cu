@@ -52,7 +52,7 @@ constexpr int kChainBN = 64;                    // the chained GEMM consumes a 6
 // (profiles/r1d_final.md), kept as an option for QKV, proj, patch embed and head conv.
 template <int NSPLIT, int BN>
 struct TcSmem {
-    static constexpr int kParts = NSPLIT == 3 ? 2 : 1;
+    static constexpr int kParts = NSPLIT == 3 ? 2 : 1;  // NSPLIT: 1 = bf16, 2 = fp16 (single pass), 3 = bf16 hi + lo
     static constexpr int kTileBBytes = BN * kTcBK * 2;   // 8 / 4 KB
     static constexpr int kTileOBytes = kTcBM * BN * 2;   // 16 / 8 KB: one bf16 output tile, rows of 128 / 64 bytes
     static constexpr int kTileCBytes = kTcBM * BN * 4;   // 32 / 16 KB: the fp32 tile as BN / 32 boxes of [128 rows][128 B]
@@ -102,12 +102,12 @@ __device__ __forceinline__ int swz(int row, int chunk) {
 }
 
 // CPT (16 or 8) fp32 -> bf16 (hi, lo) into the staging tiles of a BN = 4 CPT column tile
-template <int CPT>
+template <int CPT, bool F16>
 __device__ __forceinline__ void stage_split(const float (&v)[CPT], uint8_t* tile_hi, uint8_t* tile_lo, int row, int g, bool with_lo) {
     constexpr int RB = CPT * 8;  // bytes per tile row
     uint32_t hi[CPT / 2], lo[CPT / 2];
 #pragma unroll
-    for (int j = 0; j < CPT; j += 2) split2_bf16(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
+    for (int j = 0; j < CPT; j += 2) split2_h<F16>(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
 #pragma unroll
     for (int q = 0; q < CPT / 8; ++q) {
         const int off = row * RB + (swz<RB>(row, (CPT / 8) * g + q) << 4);
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     constexpr int CPT = BN / kTcColGroups;   // accumulator columns per thread: 16 / 8
     constexpr int RB = BN * 2;               // bytes per row of a bf16 staging tile
     constexpr int kTileBBytes = SM::kTileBBytes, kTileOBytes = SM::kTileOBytes, kTileCBytes = SM::kTileCBytes;
-    constexpr bool kLo = NSPLIT == 3;
+    constexpr bool kLo = NSPLIT == 3, kF16 = NSPLIT == 2;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             // bf16x3: A_hi x [W_hi; W_lo] as ONE N = 128 UMMA (the two weight parts are adjacent 64-row tiles of the stage) into
             // accumulator columns [0, 64) (hi*hi) and [64, 128) (hi*lo), then A_lo x W_hi (N = 64) into [0, 64); the epilogue adds the
             // two halves.  UMMA issue is operand-fetch bound (~85 clk for 4 KB A + 2 KB B): 14 KB per K-step instead of 18 KB.
-            constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, BN), idesc2n = umma_idesc_bf16(kTcBM, 2 * BN);
+            constexpr uint32_t idesc = umma_idesc_h<kF16>(kTcBM, BN), idesc2n = umma_idesc_h<kF16>(kTcBM, 2 * BN);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kTcStages;
                 ok &= mbar_wait(&full_bar[s], (kb / kTcStages) & 1);
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         }
     } else if (a.o_mode) {  // (o_mode 3: staged only — the tile is the A operand of the chained GEMM)
         if (o_which < 2) {
-            stage_split<CPT>(v, smem + SM::kOffOhi, smem + SM::kOffOlo, row, g, kLo);
+            stage_split<CPT, kF16>(v, smem + SM::kOffOhi, smem + SM::kOffOlo, row, g, kLo);
         } else {  // V^T: two unswizzled [BN d][64 tokens] sub-tiles; lanes are consecutive tokens -> 64-byte contiguous runs
             const int sub = (row >> 6) * (BN * kHalfRows) + (g * CPT) * kHalfRows + (row & 63);
             __nv_bfloat16* th = reinterpret_cast<__nv_bfloat16*>(smem + SM::kOffOhi) + sub;
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < CPT; j += 2) {
                 uint32_t h2, l2;
-                split2_bf16(v[j], v[j + 1], h2, l2);
+                split2_h<kF16>(v[j], v[j + 1], h2, l2);
                 uh[j * kHalfRows] = (unsigned short)(h2 & 0xffffu), uh[(j + 1) * kHalfRows] = (unsigned short)(h2 >> 16);
                 if (kLo) ul[j * kHalfRows] = (unsigned short)(l2 & 0xffffu), ul[(j + 1) * kHalfRows] = (unsigned short)(l2 >> 16);
             }
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     umma_bf16_ta(tmem + kAcc1Cols, tmem + kColA2 + 16 * k + 8, dB + 2 * k, idesc2, 1);
                 }
             } else {
-                const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2);  // K = the 64 hidden columns of this CTA
+                const uint32_t idesc2 = kF16 ? umma_idesc_f16(kTcBM, N2) : umma_idesc_bf16(kTcBM, N2);  // K = the 64 hidden columns of this CTA
 #pragma unroll
                 for (int k = 0; k < kChainBN / 16; ++k) {
                     umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + 2 * k, idesc2, k != 0);
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         float y[CPT];
 #pragma unroll
         for (int j = 0; j < CPT; ++j) y[j] = (v[j] - mean) * rstd * gam[j] + bet[j];
-        stage_split<CPT>(y, smem + SM::kOffLnHi, smem + SM::kOffLnLo, row, g, kLo);
+        stage_split<CPT, kF16>(y, smem + SM::kOffLnHi, smem + SM::kOffLnLo, row, g, kLo);
         __syncthreads();
         if (ln_hi) tile_to_global<RB>(smem + SM::kOffLnHi, a.ln_out[0], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
         if (ln_lo) tile_to_global<RB>(smem + SM::kOffLnLo, a.ln_out[1], (int64_t)n0 * 2, tr_rows, a.ln_row_off, 0, 0, tid);
@@ -696,6 +696,7 @@ bool tc_plan_init(TcGemmPlan* p, const __nv_bfloat16* Ahi, const __nv_bfloat16* 
 cudaError_t tc_gemm_setup() {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<1, 64>::kTotal);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<3, 64>::kTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<2, 64>::kTotal);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<1, 32>::kTotal);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<3, 32>::kTotal);
     return e;
@@ -730,7 +731,9 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t 
     const int num_kb = a.kb_per_split ? a.kb_per_split : a.K / kTcBK;
     a.mcast = (p.mcast_ok && cluster_x > 1 && num_kb <= kTcStages && !a.conv_feat) ? cluster_x : 0;
     if (!a.mcast && !a.ln_g) cluster_x = 1;
+    if (nsplit == 2 && bn != 64) return cudaErrorInvalidValue;  // the fp16 form exists for the 64-column tile only
     if (bn == 64) {
+        if (nsplit == 2) return launch_ex(gemm_tc_kernel<2, 64>, grid, dim3(kTcThreads), TcSmem<2, 64>::kTotal, s, pdl, cluster_x, p.maps, a);
         if (nsplit == 3) return launch_ex(gemm_tc_kernel<3, 64>, grid, dim3(kTcThreads), TcSmem<3, 64>::kTotal, s, pdl, cluster_x, p.maps, a);
         return launch_ex(gemm_tc_kernel<1, 64>, grid, dim3(kTcThreads), TcSmem<1, 64>::kTotal, s, pdl, cluster_x, p.maps, a);
     }
@@ -739,8 +742,13 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t 
 }
 
 // fp32 -> bf16 (hi, lo) split of a dense buffer
+// lo == nullptr: single-pass fp16 operands (hi holds fp16 values)
 __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (!lo) {
+            reinterpret_cast<unsigned short*>(hi)[i] = half_bits(x[i], true);
+            continue;
+        }
         __nv_bfloat16 h, l;
         split_bf16(x[i], h, l);
         hi[i] = h, lo[i] = l;
@@ -760,7 +768,7 @@ cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* 
 extern "C" vt_status vt_debug_gemm(int32_t device, int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias,
                                    int32_t nsplit, int32_t gelu, float* C_out, int32_t* err_out) {
     using namespace vt;
-    if (!A || !W || !C_out || M <= 0 || (nsplit != 1 && nsplit != 3)) return VT_ERR_INVALID;
+    if (!A || !W || !C_out || M <= 0 || nsplit < 1 || nsplit > 3) return VT_ERR_INVALID;  // 1 bf16, 2 fp16, 3 bf16 hi + lo
     VT_CUDA(cudaSetDevice(device));
     VT_CUDA(tc_gemm_setup());
     float *dA = nullptr, *dW = nullptr, *dB = nullptr, *dC = nullptr;
@@ -776,7 +784,7 @@ extern "C" vt_status vt_debug_gemm(int32_t device, int32_t M, int32_t N, int32_t
         VT_CUDA(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
     }
     VT_CUDA(cudaMemset(dC, 0, (size_t)M * N * 4));
-    VT_CUDA(launch_split_bf16(dA, Ahi, Alo, na, 0)); VT_CUDA(launch_split_bf16(dW, Whi, Wlo, nw, 0));
+    VT_CUDA(launch_split_bf16(dA, Ahi, nsplit == 2 ? nullptr : Alo, na, 0)); VT_CUDA(launch_split_bf16(dW, Whi, nsplit == 2 ? nullptr : Wlo, nw, 0));
     TcGemmPlan plan;
     vt_status st = VT_OK;
     const char* tile = getenv("VT_DBG_TILE");  // diagnostics knob: column-tile width 64 (default) or 32

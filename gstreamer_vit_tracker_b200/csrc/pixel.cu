@@ -329,7 +329,9 @@ __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, Targ
         const int v = (((ty.a0 * (t0 >> 4)) >> 16) + ((ty.a1 * (t1 >> 4)) >> 16) + 2) >> 2;
         const float val = lut[ch * 256 + (v & 255)];
         patches[off + ch * 256] = val;
-        if (p_hi) {
+        if (p_hi && !p_lo) {  // single-pass fp16 operands
+            reinterpret_cast<unsigned short*>(p_hi)[off + ch * 256] = operand_bits(val, true);
+        } else if (p_hi) {
             const __nv_bfloat16 h = __float2bfloat16_rn(val);
             p_hi[off + ch * 256] = h;
             p_lo[off + ch * 256] = __float2bfloat16_rn(val - __bfloat162float(h));

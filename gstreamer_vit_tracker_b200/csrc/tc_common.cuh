@@ -6,6 +6,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -174,11 +175,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 // kind::f16, A = B = bf16, D = fp32, both operands K-major, dense.
+// a_format = b_format = F16 (0): same instruction kind, 10 mantissa bits instead of 7 (VT_GEMM_TCGEN05_FP16)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <bool F16>
+__host__ __device__ constexpr uint32_t umma_idesc_h(int M, int N);
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4)                    // c_format = F32
            | (1u << 7) | (1u << 10)     // a_format = b_format = BF16
            | ((uint32_t)(N >> 3) << 17) // n_dim
            | ((uint32_t)(M >> 4) << 24);// m_dim
+}
+template <bool F16>
+__host__ __device__ constexpr uint32_t umma_idesc_h(int M, int N) {
+    return F16 ? umma_idesc_f16(M, N) : umma_idesc_bf16(M, N);
 }
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -321,6 +332,22 @@ __device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
     const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+// (a, b) -> packed fp16x2, a in the low half (single-pass fp16 operands: no lo part)
+__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// operand split by mode: F16 -> hi = fp16 pair, lo unused; otherwise the bf16 (hi, lo) split
+template <bool F16>
+__device__ __forceinline__ void split2_h(float a, float b, uint32_t& hi, uint32_t& lo) {
+    if (F16) hi = pack2_f16(a, b), lo = 0;
+    else split2_bf16(a, b, hi, lo);
+}
+// scalar form for the small kernels: f16 != 0 -> the 16 bits of the fp16 value, else of the bf16 value
+__device__ __forceinline__ unsigned short half_bits(float v, bool f16) {
+    return f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);

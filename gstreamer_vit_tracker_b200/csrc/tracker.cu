@@ -46,6 +46,7 @@ struct WeightSet {
     int device = 0;
     float* d_weights = nullptr;
     __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
+    __nv_bfloat16* w_f16 = nullptr;  // fp16 copy for handles in VT_GEMM_TCGEN05_FP16 mode (made on first use)
     size_t n = 0;
     int32_t hdr[7] = {0, 0, 0, 0, 0, 0, 0};
     std::mutex split_mutex;
@@ -54,6 +55,7 @@ struct WeightSet {
         if (d_weights) cudaFree(d_weights);
         if (w_hi) cudaFree(w_hi);
         if (w_lo) cudaFree(w_lo);
+        if (w_f16) cudaFree(w_f16);
     }
 };
 static std::mutex g_weight_mutex;
@@ -122,7 +124,8 @@ struct vt_tracker {
     int debug_capture = 0;
 
     // tensor-core mode (gemm_mode != VT_GEMM_FP32_SIMT): bf16 (hi, lo) copies of the weights and of every GEMM A operand
-    int nsplit = 0;  // 0 = fp32 SIMT, 1 = bf16, 3 = bf16x3
+    int nsplit = 0;  // 0 = fp32 SIMT, 1 = bf16, 2 = fp16 (single pass), 3 = bf16x3
+    bool f16 = false;  // nsplit == 2: the operand "hi" buffers hold fp16 values, the "lo" buffers are unused (kernels get null)
     __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
     __nv_bfloat16 *px_hi = nullptr, *px_lo = nullptr, *pz_hi = nullptr, *pz_lo = nullptr, *ln_hi = nullptr, *ln_lo = nullptr, *att_hi = nullptr,
                   *att_lo = nullptr, *hid_hi = nullptr, *hid_lo = nullptr, *yf_hi = nullptr, *yf_lo = nullptr;
@@ -281,7 +284,10 @@ __global__ void gather_template_kernel(float* __restrict__ X, const float* __res
     const size_t so = (size_t)slots[bi] * n, xo = (size_t)bi * kNTok * D;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         X[xo + i] = Zemb[so + i];
-        if (ln_hi && i < n / 2) ln_hi[xo / 2 + i] = zln_hi[so / 2 + i], ln_lo[xo / 2 + i] = zln_lo[so / 2 + i];
+        if (ln_hi && i < n / 2) {
+            ln_hi[xo / 2 + i] = zln_hi[so / 2 + i];
+            if (ln_lo) ln_lo[xo / 2 + i] = zln_lo[so / 2 + i];
+        }
     }
     tc::pdl_wait();  // the crop kernel has completed: end of the preprocess stage
     if (stamp && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) *stamp = device_time_ns();
@@ -311,13 +317,14 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     (void)record_events, (void)capturing;  // stage times come from device stamps (ST_*), not from event nodes
     cudaStream_t s = t->stream;
     FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid, t->d_frame_slot};
+    auto LO = [&](__nv_bfloat16* p) { return t->f16 ? nullptr : p; };  // fp16 mode: "hi only" (see vt_internal.h: operand_bits)
     VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, n, 4, kSearch, t->d_lut, t->patches_x, (size_t)kNTx * kPatchK, t->px_hi,
-                                      t->px_lo, s, t->d_stamps + ST_PRE));
+                                      LO(t->px_lo), s, t->d_stamps + ST_PRE));
     {
         dim3 grid((kNTz * D + 255) / 256, n);
         const bool f = t->fuse_ln;
         VT_LAUNCH(launch_ex(gather_template_kernel, grid, dim3(256), 0, s, t->pdl && !t->debug_capture, 1, t->X, (const float*)t->Zemb,
-                            (const int32_t*)t->d_slots, D, f ? (uint32_t*)t->ln_hi : nullptr, (uint32_t*)t->ln_lo, (const uint32_t*)t->zln_hi,
+                            (const int32_t*)t->d_slots, D, f ? (uint32_t*)t->ln_hi : nullptr, (uint32_t*)LO(t->ln_lo), (const uint32_t*)t->zln_hi,
                             (const uint32_t*)t->zln_lo, t->d_stamps + ST_VIT));
     }
     const int M = n * kNTok;
@@ -372,14 +379,14 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             ReduceLnArgs r{};
             r.P = t->Pbuf, r.np = 4, r.p_stride = (int64_t)t->maxT * kNTx * D, r.bias = t->patch_b, r.add = t->pos_x, r.add_period = kNTx;
             r.X = t->X, r.M = n * kNTx, r.D = D, r.period = kNTx, r.x_rows = kNTok, r.x_row_off = kNTz;
-            r.ln_g = t->blk[0].ln1_g, r.ln_b = t->blk[0].ln1_b, r.ln_hi = t->ln_hi, r.ln_lo = t->ln_lo, r.ln_rows = kNTok, r.ln_row_off = kNTz;
+            r.ln_g = t->blk[0].ln1_g, r.ln_b = t->blk[0].ln1_b, r.ln_hi = t->ln_hi, r.ln_lo = LO(t->ln_lo), r.ln_rows = kNTok, r.ln_row_off = kNTz;
             VT_LAUNCH(launch_reduce_ln(r, s, pdl));
         }
         if (t->debug_capture) VT_CUDA(cudaMemcpyAsync(t->d_dbg, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
         for (int l = 0; l < t->depth; ++l) {
             const BlockW& b = t->blk[l];
             const vt_tracker::BlockPlans& p = t->plans[l];
-            if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
+            if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, LO(t->ln_lo), M, D, 1 << 30, 0, 0, s, pdl));
             VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s, pdl, spread));
             // Latency mode: the proj GEMM is folded into the attention kernel (per-head partial products, D / 64 replicas per tile) and
             // reduce_ln adds the heads + bias + residual and applies LN2 — one kernel and one dependency edge less per block.
@@ -388,17 +395,17 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                 VT_LAUNCH(tc_attention_launch(att_chain ? p.att : t->plan_att, n, t->heads, ns, t->d_tc_err, s, pdl, t->d_trace,
                                               att_chain ? VT_ATT_CHAIN : (spread ? VT_ATT_DUP : VT_ATT_PLAIN)));
             else
-                VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, t->att_lo, n, D, t->heads, s));
+                VT_LAUNCH(launch_attention(t->QKV, nullptr, t->att_hi, LO(t->att_lo), n, D, t->heads, s));
             if (att_chain) {
                 ReduceLnArgs r{};
                 r.P = t->Pbuf, r.np = t->heads, r.p_stride = (int64_t)t->maxT * kNTok * D, r.bias = b.proj_b, r.add = t->X, r.add_period = 0;
                 r.X = t->X, r.M = M, r.D = D, r.period = kNTok, r.x_rows = kNTok, r.x_row_off = 0;
-                r.ln_g = b.ln2_g, r.ln_b = b.ln2_b, r.ln_hi = t->ln_hi, r.ln_lo = t->ln_lo, r.ln_rows = kNTok, r.ln_row_off = 0;
+                r.ln_g = b.ln2_g, r.ln_b = b.ln2_b, r.ln_hi = t->ln_hi, r.ln_lo = LO(t->ln_lo), r.ln_rows = kNTok, r.ln_row_off = 0;
                 VT_LAUNCH(launch_reduce_ln(r, s, pdl));
             } else {
                 VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention, spread));  // fused: + LN2
             }
-            if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, t->ln_lo, M, D, 1 << 30, 0, 0, s, pdl));
+            if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, LO(t->ln_lo), M, D, 1 << 30, 0, 0, s, pdl));
             // Chained form (FC2 partial products inside the FC1 kernel, summed by reduce_ln): shortest critical path for a few targets.
             // From kUnchainTargets targets on the 12 fp32 partial planes per row tile cost more than the hidden round trip
             // (cfg4, 16 targets: ViT stage 905 -> 819 us unchained), so FC1 writes the hidden tile and FC2 runs as its own GEMM.
@@ -416,7 +423,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                 r.P = t->Pbuf, r.np = Hd / 64, r.p_stride = (int64_t)t->maxT * kNTok * D, r.bias = b.fc2_b, r.add = t->X, r.add_period = 0;
                 r.X = t->X, r.M = M, r.D = D, r.period = kNTok, r.x_rows = kNTok, r.x_row_off = 0;
                 r.ln_g = last ? t->lnf_g : t->blk[l + 1].ln1_g, r.ln_b = last ? t->lnf_b : t->blk[l + 1].ln1_b;
-                r.ln_hi = last ? t->yf_hi : t->ln_hi, r.ln_lo = last ? t->yf_lo : t->ln_lo;
+                r.ln_hi = last ? t->yf_hi : t->ln_hi, r.ln_lo = LO(last ? t->yf_lo : t->ln_lo);
                 r.ln_rows = last ? kNTx : kNTok, r.ln_row_off = last ? -kNTz : 0;
                 VT_LAUNCH(launch_reduce_ln(r, s, pdl));
             } else {
@@ -425,7 +432,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             if (t->debug_capture)
                 VT_CUDA(cudaMemcpyAsync(t->d_dbg + (size_t)(l + 1) * t->maxT * kNTok * D, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
         }
-        if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, t->lnf_g, t->lnf_b, t->yf_hi, t->yf_lo, n * kNTx, D, kNTx, kNTok, kNTz, s, pdl));
+        if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, t->lnf_g, t->lnf_b, t->yf_hi, LO(t->yf_lo), n * kNTx, D, kNTx, kNTok, kNTz, s, pdl));
         VT_LAUNCH(tc_gemm_launch(t->plan_head, n * kNTx, ns, s, pdl));
     }
     if (t->nsplit && t->split_k)
@@ -846,7 +853,7 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         set_error("vt_tracker_create: invalid configuration");
         return VT_ERR_INVALID;
     }
-    if (cfg->gemm_mode != VT_GEMM_FP32_SIMT && cfg->gemm_mode != VT_GEMM_TCGEN05_BF16X3 && cfg->gemm_mode != VT_GEMM_TCGEN05_BF16) {
+    if (cfg->gemm_mode < VT_GEMM_FP32_SIMT || cfg->gemm_mode > VT_GEMM_TCGEN05_FP16) {
         set_error("vt_tracker_create: unknown gemm_mode %d", cfg->gemm_mode);
         return VT_ERR_INVALID;
     }
@@ -946,7 +953,8 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
     VT_TRY(cudaMemset(t->patches_x, 0, sizeof(float) * B * kNTx * kPatchK));
     VT_TRY(cudaMemset(t->patches_z, 0, sizeof(float) * kNTz * kPatchK));
     if (t->debug_capture) VT_TRY(cudaMalloc(&t->d_dbg, sizeof(float) * (size_t)(t->depth + 1) * B * kNTok * D));
-    t->nsplit = cfg->gemm_mode == VT_GEMM_TCGEN05_BF16X3 ? 3 : (cfg->gemm_mode == VT_GEMM_TCGEN05_BF16 ? 1 : 0);
+    t->nsplit = cfg->gemm_mode == VT_GEMM_TCGEN05_BF16X3 ? 3 : (cfg->gemm_mode == VT_GEMM_TCGEN05_BF16 ? 1 : (cfg->gemm_mode == VT_GEMM_TCGEN05_FP16 ? 2 : 0));
+    t->f16 = t->nsplit == 2;
     if (t->nsplit) {
         if (D % 64 || Hd % 64 || C % 64) {
             set_error("the tcgen05 path needs D, hidden and head_ch to be multiples of 64 (D=%zu hidden=%zu head_ch=%zu)", D, Hd, C);
@@ -977,6 +985,14 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
                 VT_TRY(cudaStreamSynchronize(t->stream));
             }
             t->w_hi = t->wset->w_hi, t->w_lo = t->wset->w_lo;
+            if (t->f16) {  // single-pass fp16 operands: an fp16 copy of the weights stands in for the hi part
+                if (!t->wset->w_f16) {
+                    VT_TRY(cudaMalloc(&t->wset->w_f16, t->n_weights * 2));
+                    VT_TRY(launch_split_bf16(t->d_weights, t->wset->w_f16, nullptr, t->n_weights, t->stream));
+                    VT_TRY(cudaStreamSynchronize(t->stream));
+                }
+                t->w_hi = t->wset->w_f16;
+            }
         }
         auto balloc = [&](__nv_bfloat16** hi, __nv_bfloat16** lo, size_t n) -> cudaError_t {
             cudaError_t e = cudaMalloc(hi, n * 2);
@@ -1152,7 +1168,7 @@ vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, s
     FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid, nullptr};
     int launches = 0;
     VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, 1, 2, kTemplate, t->d_lut, t->patches_z, (size_t)kNTz * kPatchK, t->pz_hi,
-                                      t->pz_lo, t->stream));
+                                      t->f16 ? nullptr : t->pz_lo, t->stream));
     if (t->nsplit == 0) {
         GemmArgs g = gemm_args(t->patches_z, kPatchK, t->patch_w, t->patch_b, t->Zemb + (size_t)target * kNTz * t->D, t->D, kNTz, t->D, kPatchK);
         g.pos = t->pos_z;
@@ -1163,7 +1179,7 @@ vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, s
         p.args.batch_off = target;
         VT_LAUNCH(tc_gemm_launch(p, kNTz, t->nsplit, t->stream, false));
         VT_LAUNCH(launch_layernorm_split(t->Zemb + (size_t)target * kNTz * t->D, t->D, t->blk[0].ln1_g, t->blk[0].ln1_b, t->zln_hi + (size_t)target * kNTz * t->D,
-                                         t->zln_lo + (size_t)target * kNTz * t->D, kNTz, t->D, 1 << 30, 0, 0, t->stream, false));
+                                         t->f16 ? nullptr : t->zln_lo + (size_t)target * kNTz * t->D, kNTz, t->D, 1 << 30, 0, 0, t->stream, false));
     }
     t->kernel_launches += launches;
     VT_CUDA(cudaStreamSynchronize(t->stream));

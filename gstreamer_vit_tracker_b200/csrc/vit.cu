@@ -210,6 +210,10 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
     const float rstd = 1.f / sqrtf(warp_sum(v) / (float)D + 1e-6f);
     for (int k = lane; k < D; k += 32) {
         const float y = (r[k] - mean) * rstd * g[k] + b[k];
+        if (!lo) {  // single-pass fp16 operands
+            reinterpret_cast<unsigned short*>(hi)[(int64_t)m * D + k] = operand_bits(y, true);
+            continue;
+        }
         const __nv_bfloat16 h = __float2bfloat16_rn(y);
         hi[(int64_t)m * D + k] = h;
         lo[(int64_t)m * D + k] = __float2bfloat16_rn(y - __bfloat162float(h));
@@ -300,6 +304,11 @@ __global__ void __launch_bounds__(32 * kReduceRows) reduce_ln_kernel(const Reduc
         const float y0 = (acc[i].x - mean) * rstd * g2.x + b2.x, y1 = (acc[i].y - mean) * rstd * g2.y + b2.y;
         // packed cvt.rn.bf16x2 (bit-identical to two scalar splits; the scalar conversion runs on the slow 16/clk pipe)
         uint32_t h2, l2;
+        if (!a.ln_lo) {  // single-pass fp16 operands
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(y1), "f"(y0));
+            oh[lane + 32 * i] = h2;
+            continue;
+        }
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(y1), "f"(y0));
         const float r0 = y0 - __uint_as_float(h2 << 16), r1 = y1 - __uint_as_float(h2 & 0xffff0000u);
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(r1), "f"(r0));
@@ -400,6 +409,10 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
         const int64_t idx = ((int64_t)b * kNTok + q0 + qg * kQPer + i) * D + h * DH + d;
         if (out) out[idx] = o[i];
         if (out_hi) {
+            if (!out_lo) {  // single-pass fp16 operands
+                reinterpret_cast<unsigned short*>(out_hi)[idx] = operand_bits(o[i], true);
+                continue;
+            }
             const __nv_bfloat16 hh = __float2bfloat16_rn(o[i]);
             out_hi[idx] = hh;
             out_lo[idx] = __float2bfloat16_rn(o[i] - __bfloat162float(hh));

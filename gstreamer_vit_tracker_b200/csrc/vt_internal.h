@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -194,6 +195,13 @@ cudaError_t launch_layernorm_split(const float* x, int64_t ldx, const float* g, 
 //   X[xrow, :] = v                      xrow = (m / period) * x_rows + m % period + x_row_off
 //   ln_hi/lo[lrow, :] = split(LN(v))    lrow = (m / period) * ln_rows + m % period + ln_row_off   (skipped when m % period + ln_row_off < 0)
 // MLP: add = X (residual), add_period = 0.  Patch embed: add = pos_x, add_period = 256, rows land at 64.. of every target.
+#ifdef __CUDACC__
+// Single-pass fp16 operands (VT_GEMM_TCGEN05_FP16): the small kernels that write a GEMM operand take a null `lo` pointer as "hi only,
+// fp16 values" — the 16 bits of the fp16 value go where the bf16 hi part would.
+__device__ __forceinline__ unsigned short operand_bits(float v, bool f16) {
+    return f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+#endif
 struct ReduceLnArgs {
     const float* P;
     int np;

@@ -47,7 +47,9 @@ enum {
 /* VT_FMT_GRAY8: one byte per pixel (IR sensors; BASELINE config "IR/GRAY8 at 640x512"): the tracker sees r = g = b = gray and the
  * overlays follow the NV12 luma-plane semantics (src/nv12_convert.rs:172-343 write the Y plane only). */
 typedef enum { VT_FMT_NV12 = 0, VT_FMT_RGB24 = 1, VT_FMT_GRAY8 = 2 } vt_format;
-typedef enum { VT_GEMM_FP32_SIMT = 0, VT_GEMM_TCGEN05_BF16X3 = 1, VT_GEMM_TCGEN05_BF16 = 2 } vt_gemm_mode;
+/* BF16X3 (default): bf16 hi + lo operands, three products per K-step, scores within ~1e-5 of the fp32 oracle.  BF16 / FP16: single-pass
+ * operands, 17 % faster, score error ~1e-3 / ~3e-4 — opt-in (near-tie arg-max flips are possible at that error). */
+typedef enum { VT_GEMM_FP32_SIMT = 0, VT_GEMM_TCGEN05_BF16X3 = 1, VT_GEMM_TCGEN05_BF16 = 2, VT_GEMM_TCGEN05_FP16 = 3 } vt_gemm_mode;
 
 /* ≙ vit_tracker::BBox {x, y, width, height: i32} (uses: src/selection_state.rs:44, src/pipeline.rs:166) */
 typedef struct { int32_t x, y, width, height; } vt_bbox;

@@ -221,7 +221,7 @@ def test_single_steps_vs_cv2_golden(api, weight_dir, variant, gemm_mode):
 
 
 # ---- teacher-forced long sequences vs the oracle ------------------------------------------------------------
-@pytest.mark.parametrize("gemm_mode", [0, 1], ids=["fp32simt", "tcgen05x3"])
+@pytest.mark.parametrize("gemm_mode", [0, 1, 3], ids=["fp32simt", "tcgen05x3", "tcgen05fp16"])
 @pytest.mark.parametrize("model,cfg,frames", [("nano", "cfg1", 120), ("tiny", "cfg2", 60)])
 def test_teacher_forced_sequence(api, oracle, weight_dir, model, cfg, frames, gemm_mode):
     spec = synth.CONFIGS[cfg]
