@@ -5,7 +5,7 @@
 //   -> K2 crop+convert+resize+normalise (search window of every active target, rect_last read on device)
 //   -> template-token gather -> patch-embed GEMM -> depth x [LN+QKV, attention, proj+res, LN+FC1+GELU, FC2+res]
 //   -> final LN -> 3x3 head conv (im2col GEMM) -> K8 decode (updates rect_last on device)
-//   -> optional K9 box overlay -> D2H results (+ touched rows).
+//   -> optional K9 box overlay -> results published into the pinned host block by the last kernel (+ touched rows for pageable frames).
 // rect_last never leaves the device between frames, so consecutive frames can be enqueued without a
 // host round trip.
 #include <math.h>
@@ -103,7 +103,7 @@ struct vt_tracker {
     int frame_valid = 1;
     TargetState* d_state = nullptr;
     int32_t* d_slots = nullptr;
-    // one device block [DeviceResult x maxT][u64 stamps x ST_COUNT][int tc_err, pad] mirrored in pinned host memory by one copy
+    // one device block [DeviceResult x maxT][u64 stamps x ST_COUNT][int tc_err, pad] written into the pinned host block of the frame's queue slot by the frame's last kernel
     DeviceResult *d_res = nullptr, *h_res = nullptr;
     size_t res_block_bytes = 0;
     unsigned long long *d_stamps = nullptr, *h_stamps = nullptr;
