@@ -699,30 +699,36 @@ def test_gray8_input_format(api, oracle, weight_dir):
 
 
 def test_kernel_forms_agree(api, weight_dir, monkeypatch):
-    """The latency-mode "spread" form (FC1 tile computed by three CTAs, one 64-column slice of the chained FC2 product each; used
-    while <= 2 handles are alive on the GPU), the plain chained form and the unchained FC1 / FC2 GEMMs (>= 8 targets) are
-    re-associations of the same sums: boxes equal, scores within 1e-5 of each other over a sequence (parity bar: 1e-3)."""
+    """The latency-mode "spread" forms (used while <= 2 handles are alive on the GPU: FC1 tile computed by three CTAs with one
+    64-column slice of the chained FC2 product each, proj folded into the attention kernel, hi / lo replicas of the QKV scatter), the
+    plain chained forms and the unchained FC1 / FC2 GEMMs (>= 8 targets) are re-associations of the same sums: boxes equal, scores
+    within 1e-5 of each other over a sequence (parity bar: 1e-3).  One and two targets per handle (different forms qualify)."""
     import gc
     gc.collect()  # handles of earlier tests would count as live streams
-    spec = synth.CONFIGS["cfg1"]
-    st = synth.SyntheticStream(spec)
     w = weights.ensure_weight_file("tiny", weight_dir, variant="wild")
-    frames = [np.ascontiguousarray(st.frame(i)).reshape(-1) for i in range(6)]
+    spec1 = synth.CONFIGS["cfg1"]
+    spec2 = synth.StreamSpec("two", 1920, 1080, 1005, [(400, 300, 140, 100, 4, 2), (1300, 600, 120, 160, -3, 3)])
+    for spec in (spec1, spec2):
+        st = synth.SyntheticStream(spec)
+        nt = len(spec.targets)
+        frames = [np.ascontiguousarray(st.frame(i)).reshape(-1) for i in range(6)]
 
-    def run(env):
-        for k in ("VT_B200_NO_SPREAD", "VT_B200_UNCHAIN_N"):
-            monkeypatch.delenv(k, raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        trk = api.VitTrack.new(w, spec.width, spec.height, gemm_mode=1)
-        trk.init(frames[0], api.BBox(*st.target_boxes(0)[0]))
-        out = [trk.update(f) for f in frames[1:]]
-        trk.close()
-        return out
+        def run(env):
+            for k in ("VT_B200_NO_SPREAD", "VT_B200_UNCHAIN_N", "VT_B200_NO_ATT_CHAIN"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            trk = api.VitTrack.new(w, spec.width, spec.height, gemm_mode=1, max_targets=nt)
+            for k, b in enumerate(st.target_boxes(0)):
+                trk.init(frames[0], api.BBox(*b), target=k)
+            out = [trk.update_all(f) for f in frames[1:]]
+            trk.close()
+            return out
 
-    spread = run({})
-    plain = run({"VT_B200_NO_SPREAD": "1"})
-    unchained = run({"VT_B200_UNCHAIN_N": "1"})
-    for a, b, c in zip(spread, plain, unchained):
-        assert a.success and a.bbox == b.bbox == c.bbox
-        assert abs(a.score - b.score) < 1e-5 and abs(a.score - c.score) < 1e-5
+        ref = run({"VT_B200_NO_SPREAD": "1"})
+        for env in ({}, {"VT_B200_NO_ATT_CHAIN": "1"}, {"VT_B200_UNCHAIN_N": "1"}):
+            got = run(env)
+            for fa, fb in zip(got, ref):
+                for a, b in zip(fa, fb):
+                    assert a.success and a.status == 0 and a.bbox == b.bbox, (spec.name, env, a, b)
+                    assert abs(a.score - b.score) < 1e-5, (spec.name, env, a, b)
