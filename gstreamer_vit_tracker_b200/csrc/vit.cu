@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(32 * kReduceRows) reduce_ln_kernel(const Reduc
     float2 acc[NPAIR], gam[NPAIR], bet[NPAIR], x2[NPAIR];
 #pragma unroll
     for (int i = 0; i < NPAIR; ++i) {
-        acc[i] = __ldg(reinterpret_cast<const float2*>(a.bias) + lane + 32 * i), x2[i] = ar[lane + 32 * i];
+        acc[i] = __ldg(reinterpret_cast<const float2*>(a.bias) + lane + 32 * i), x2[i] = __ldcg(ar + lane + 32 * i);
         gam[i] = __ldg(reinterpret_cast<const float2*>(a.ln_g) + lane + 32 * i), bet[i] = __ldg(reinterpret_cast<const float2*>(a.ln_b) + lane + 32 * i);
     }
     const float2* pr = reinterpret_cast<const float2*>(a.P + (int64_t)m * D);
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(32 * kReduceRows) reduce_ln_kernel(const Reduc
 #pragma unroll
         for (int j = 0; j < NP; ++j)
 #pragma unroll
-            for (int i = 0; i < NPAIR; ++i) v[j][i] = pr[j * ps + lane + 32 * i];
+            for (int i = 0; i < NPAIR; ++i) v[j][i] = __ldcg(pr + j * ps + lane + 32 * i);  // L2 loads: the partials were written by other SMs a moment ago
 #pragma unroll
         for (int i = 0; i < NPAIR; ++i) acc[i].x = x2[i].x + acc[i].x, acc[i].y = x2[i].y + acc[i].y;  // (x + bias) first, as before
 #pragma unroll
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(32 * kReduceRows) reduce_ln_kernel(const Reduc
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-                for (int i = 0; i < NPAIR; ++i) v[jj][i] = j0 + jj < a.np ? pr[(j0 + jj) * ps + lane + 32 * i] : make_float2(0.f, 0.f);
+                for (int i = 0; i < NPAIR; ++i) v[jj][i] = j0 + jj < a.np ? __ldcg(pr + (j0 + jj) * ps + lane + 32 * i) : make_float2(0.f, 0.f);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
