@@ -120,7 +120,9 @@ def _tensor(buf: memoryview) -> Tuple[str, np.ndarray]:
         arr = np.asarray(floats, np.float32)
     else:
         arr = np.asarray(ints, _DTYPES[dtype])
-    return name, arr.reshape(dims) if dims else arr.reshape(())
+    if any(d < 0 for d in dims) or int(np.prod(dims, dtype=np.float64)) != arr.size:
+        raise OnnxImportError(f"tensor {name!r}: {arr.size} elements for dims {dims}")
+    return name, arr.reshape(dims)
 
 
 @dataclass
@@ -202,21 +204,35 @@ class OnnxModel:
     opset: int
 
 
+def _malformed(fn):
+    """The file comes from outside: whatever a malformed byte string trips over inside the decoders is reported as OnnxImportError."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **kw):
+        try:
+            return fn(*a, **kw)
+        except OnnxImportError:
+            raise
+        except (struct.error, IndexError, KeyError, ValueError, TypeError, OverflowError, UnicodeDecodeError, MemoryError, AttributeError) as e:
+            raise OnnxImportError(f"malformed ONNX file ({type(e).__name__}: {e})") from None
+
+    return wrapper
+
+
+@_malformed
 def read_onnx(path: str) -> OnnxModel:
     """ModelProto: graph = 7, opset_import = 8 { version = 2 }; GraphProto: node = 1, initializer = 5, input = 11, output = 12."""
     with open(path, "rb") as f:
         buf = memoryview(f.read())
     graph, opset = None, 0
-    try:
-        for fno, wt, v in _fields(buf):
-            if fno == 7 and wt == 2:
-                graph = v
-            elif fno == 8 and wt == 2:
-                for f2, _, v2 in _fields(v):
-                    if f2 == 2:
-                        opset = max(opset, v2)
-    except (struct.error, IndexError) as e:
-        raise OnnxImportError(f"{path}: not a protobuf file ({e})") from None
+    for fno, wt, v in _fields(buf):
+        if fno == 7 and wt == 2:
+            graph = v
+        elif fno == 8 and wt == 2:
+            for f2, _, v2 in _fields(v):
+                if f2 == 2:
+                    opset = max(opset, v2)
     if graph is None:
         raise OnnxImportError(f"{path}: no GraphProto in the file")
     m = OnnxModel([], OrderedDict(), OrderedDict(), OrderedDict(), opset)
@@ -283,6 +299,7 @@ def _layernorms(m: OnnxModel) -> List[Tuple[np.ndarray, np.ndarray, float]]:
     return out
 
 
+@_malformed
 def detect_and_map(m: OnnxModel) -> Tuple[W.ModelConfig, "OrderedDict[str, np.ndarray]"]:
     """Graph -> (ModelConfig, tensors in `weights.tensor_specs` order).  Raises OnnxImportError on any other topology."""
     ops: Dict[str, int] = {}

@@ -84,3 +84,27 @@ def test_architecture_mismatch_is_reported(nano_onnx):
     del m.initializers[key]
     with pytest.raises(oi.OnnxImportError, match="position"):
         oi.detect_and_map(m)
+
+
+def test_reader_never_crashes_on_arbitrary_bytes(tmp_path):
+    """Fuzz: any byte string either parses or raises OnnxImportError — nothing else (the file comes from outside)."""
+    from hypothesis import given, settings, strategies as stt
+
+    p = tmp_path / "fuzz.onnx"
+
+    @settings(max_examples=300, deadline=None)
+    @given(stt.binary(min_size=0, max_size=256))
+    def run(blob):
+        # half of the cases get a valid outer frame (field 7 = graph) so that the nested decoders are reached
+        for data in (blob, _ld(7, blob), _ld(7, _ld(5, blob)), _ld(7, _ld(1, blob)), _ld(7, _ld(11, blob))):
+            p.write_bytes(data)
+            try:
+                m = oi.read_onnx(str(p))
+                try:
+                    oi.detect_and_map(m)
+                except oi.OnnxImportError:
+                    pass
+            except oi.OnnxImportError:
+                pass
+
+    run()
