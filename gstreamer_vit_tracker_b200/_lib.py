@@ -72,6 +72,7 @@ SYMBOLS = {
     "vt_config_default": (None, [C.POINTER(vt_config)]),
     "vt_alloc_pinned": (C.c_int32, [C.c_size_t, C.POINTER(_vp)]),
     "vt_free_pinned": (None, [_vp]),
+    "vt_weights_probe": (C.c_int32, [C.c_char_p, C.POINTER(C.c_int32)]),
     "vt_tracker_create": (C.c_int32, [C.POINTER(vt_config), C.POINTER(_vp)]),
     "vt_tracker_destroy": (None, [_vp]),
     "vt_tracker_init": (C.c_int32, [_vp, C.c_int32, _vp, C.c_size_t, vt_bbox]),

@@ -112,6 +112,14 @@ def make_config(weights: str, width: int, height: int, fmt: str = "nv12", max_ta
     return cfg
 
 
+def weights_probe(path: str) -> Tuple[int, int, int, int, int]:
+    """(D, depth, heads, hidden, head_channels) of a VTW1 model file; raises VtError(VT_ERR_WEIGHTS) when `VitTrack.new` would reject
+    it.  Needs no GPU."""
+    shape = (C.c_int32 * 5)()
+    check(lib().vt_weights_probe(path.encode(), shape), "vt_weights_probe")
+    return tuple(int(v) for v in shape)
+
+
 def _import_onnx_cached(onnx_path: str) -> str:
     """ONNX model file -> flat VTW1 file next to the system temp dir (keyed by path, size, mtime); see onnx_import.py."""
     import hashlib

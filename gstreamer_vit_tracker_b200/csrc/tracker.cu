@@ -194,10 +194,51 @@ static bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+// Header of a VTW1 file: magic, shape, and the float count the shape implies — checked against the file size BEFORE anything is
+// allocated (the file comes from outside: negative or absurd header fields must not turn into a huge allocation or an overflow).
+static vt_status read_weight_header(const char* path, FILE** f_out, int32_t hdr[7], size_t* n_out, struct stat* sb_out) {
+    struct stat sb;
+    if (!path || stat(path, &sb) != 0 || !S_ISREG(sb.st_mode)) {
+        set_error("cannot open weight file %s", path ? path : "(null)");
+        return VT_ERR_WEIGHTS;
+    }
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        set_error("cannot open weight file %s", path);
+        return VT_ERR_WEIGHTS;
+    }
+    char magic[4];
+    if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "VTW1", 4) != 0 || fread(hdr, 4, 7, f) != 7) {
+        fclose(f);
+        set_error("%s is not a VTW1 weight file", path);
+        return VT_ERR_WEIGHTS;
+    }
+    const long long Dl = hdr[0], L = hdr[1], heads = hdr[2], Hl = hdr[3], Cl = hdr[4];
+    if (Dl <= 0 || Dl > 1024 || Dl % 32 || L <= 0 || L > 64 || Hl <= 0 || Hl > 8192 || Hl % 32 || Cl <= 0 || Cl > 1024 || Cl % 32 || heads <= 0 ||
+        Dl % heads || (Dl / heads != 16 && Dl / heads != 32 && Dl / heads != 64)) {
+        fclose(f);
+        set_error("unsupported model shape D=%d depth=%d heads=%d hidden=%d head_ch=%d", hdr[0], hdr[1], hdr[2], hdr[3], hdr[4]);
+        return VT_ERR_WEIGHTS;
+    }
+    const size_t D = (size_t)Dl, H = (size_t)Hl, C = (size_t)Cl;
+    const size_t n = D * kPatchK + D + kNTz * D + kNTx * D + (size_t)L * (4 * D + 3 * D * D + 3 * D + D * D + D + H * D + H + D * H + D) + 2 * D +
+                     C * D * 9 + C + 5 * C + 5;
+    if ((unsigned long long)sb.st_size != 32ull + 4ull * n) {
+        fclose(f);
+        set_error("weight file %s: %lld bytes, the header implies %llu", path, (long long)sb.st_size, 32ull + 4ull * n);
+        return VT_ERR_WEIGHTS;
+    }
+    *n_out = n;
+    if (sb_out) *sb_out = sb;
+    if (f_out) *f_out = f;
+    else fclose(f);
+    return VT_OK;
+}
+
 static vt_status load_weights(vt_tracker* t, const char* path) {
     struct stat sb;
-    if (stat(path, &sb) != 0) {
-        set_error("cannot open weight file %s", path);
+    if (!path || stat(path, &sb) != 0) {
+        set_error("cannot open weight file %s", path ? path : "(null)");
         return VT_ERR_WEIGHTS;
     }
     char key[1200];
@@ -205,27 +246,12 @@ static vt_status load_weights(vt_tracker* t, const char* path) {
     std::lock_guard<std::mutex> lock(g_weight_mutex);
     std::shared_ptr<WeightSet> ws = g_weight_cache[key].lock();
     if (!ws) {
-        FILE* f = fopen(path, "rb");
-        if (!f) {
-            set_error("cannot open weight file %s", path);
-            return VT_ERR_WEIGHTS;
-        }
-        char magic[4];
+        FILE* f = nullptr;
         int32_t hdr[7];
-        if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "VTW1", 4) != 0 || fread(hdr, 4, 7, f) != 7) {
-            fclose(f);
-            set_error("%s is not a VTW1 weight file", path);
-            return VT_ERR_WEIGHTS;
-        }
-        const size_t D = hdr[0], H = hdr[3], C = hdr[4];
-        const int heads = hdr[2];
-        if (D == 0 || D % 32 || H % 32 || C % 32 || heads <= 0 || D % heads || (D / heads != 16 && D / heads != 32 && D / heads != 64)) {
-            fclose(f);
-            set_error("unsupported model shape D=%d heads=%d hidden=%d head_ch=%d", hdr[0], hdr[2], hdr[3], hdr[4]);
-            return VT_ERR_WEIGHTS;
-        }
-        const size_t n = D * kPatchK + D + kNTz * D + kNTx * D + (size_t)hdr[1] * (4 * D + 3 * D * D + 3 * D + D * D + D + H * D + H + D * H + D) +
-                         2 * D + C * D * 9 + C + 5 * C + 5;
+        size_t n = 0;
+        vt_status hs = read_weight_header(path, &f, hdr, &n, nullptr);
+        if (hs != VT_OK) return hs;
+        const size_t D = hdr[0], C = hdr[4];
         std::vector<float> host(n);
         const size_t got = fread(host.data(), sizeof(float), n, f);
         fclose(f);
@@ -798,6 +824,14 @@ void vt_config_default(vt_config* c) {
     c->use_cuda_graph = 1;
     c->box_overlay = 0;
     c->overlay_gate = 0.25f;  // src/tracker_context.rs:93,122
+}
+
+vt_status vt_weights_probe(const char* path, int32_t shape_out[5]) {
+    int32_t hdr[7];
+    size_t n = 0;
+    vt_status st = read_weight_header(path, nullptr, hdr, &n, nullptr);
+    if (st == VT_OK && shape_out) memcpy(shape_out, hdr, 5 * sizeof(int32_t));
+    return st;
 }
 
 vt_status vt_alloc_pinned(size_t bytes, void** out) {

@@ -97,6 +97,10 @@ void vt_config_default(vt_config* cfg);
 /* pinned host memory for frames (what a GstAllocator for the upstream element would hand out) */
 vt_status vt_alloc_pinned(size_t bytes, void** out);
 void vt_free_pinned(void* p);
+/* Validates a model file without touching the GPU — what VitTrack::new's Err branch reports up front (src/tracker_context.rs:21):
+ * VT_OK and shape_out = {D, depth, heads, hidden, head_channels} when vt_tracker_create would accept the file, VT_ERR_WEIGHTS (and
+ * vt_last_error()) when the file is missing, not a VTW1 file, of an unsupported shape, or its size does not match its header. */
+vt_status vt_weights_probe(const char* path, int32_t shape_out[5]);
 
 /* ------------------------------------------------------------------------------------------- */
 /* VitTrack                                                                                     */

@@ -420,6 +420,12 @@ vto_tracker* vto_tracker_new(const char* path, int threads) {
         fclose(f);
         return NULL;
     }
+    /* same shape limits as the library's loader: a corrupt header must not become a huge allocation */
+    if (hdr[0] <= 0 || hdr[0] > 1024 || hdr[1] <= 0 || hdr[1] > 64 || hdr[2] <= 0 || hdr[0] % hdr[2] || hdr[3] <= 0 || hdr[3] > 8192 ||
+        hdr[4] <= 0 || hdr[4] > 1024) {
+        fclose(f);
+        return NULL;
+    }
     vto_tracker* t = (vto_tracker*)calloc(1, sizeof(*t));
     t->D = hdr[0], t->depth = hdr[1], t->heads = hdr[2], t->hidden = hdr[3], t->head_ch = hdr[4];
     t->threads = threads > 0 ? threads : 1;
