@@ -298,11 +298,16 @@ struct vt_timing_stats {
 };
 vt_timing_stats* vt_timing_stats_create(void) { return new vt_timing_stats(); }
 void vt_timing_stats_destroy(vt_timing_stats* s) { delete s; }
-void vt_timing_stats_add_interval(vt_timing_stats* s, uint64_t us) { s->s.add_interval(us); }
-void vt_timing_stats_add_times(vt_timing_stats* s, uint64_t conv_us, uint64_t track_us) { s->s.add_times(conv_us, track_us); }
-double vt_timing_stats_fps(const vt_timing_stats* s) { return s->s.fps(); }
-double vt_timing_stats_avg_conv_ms(const vt_timing_stats* s) { return s->s.avg_conv_ms(); }
-double vt_timing_stats_avg_track_ms(const vt_timing_stats* s) { return s->s.avg_track_ms(); }
+// (a null object reads as the empty TimingStats: every accessor of src/timing_stats.rs:36-60 returns 0.0 then)
+void vt_timing_stats_add_interval(vt_timing_stats* s, uint64_t us) {
+    if (s) s->s.add_interval(us);
+}
+void vt_timing_stats_add_times(vt_timing_stats* s, uint64_t conv_us, uint64_t track_us) {
+    if (s) s->s.add_times(conv_us, track_us);
+}
+double vt_timing_stats_fps(const vt_timing_stats* s) { return s ? s->s.fps() : 0.0; }
+double vt_timing_stats_avg_conv_ms(const vt_timing_stats* s) { return s ? s->s.avg_conv_ms() : 0.0; }
+double vt_timing_stats_avg_track_ms(const vt_timing_stats* s) { return s ? s->s.avg_track_ms() : 0.0; }
 
 static vt_overlay_cmd make_cmd(int kind, int x, int y, int w, int h, int a, uint8_t r, uint8_t g, uint8_t b, const char* text = nullptr,
                                int strict = 0) {

@@ -65,3 +65,27 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", "Makefile")):
                 txt = open(os.path.join(base, f), errors="replace").read()
                 assert "vt_oracle" not in txt and "vto_" not in txt and "from oracle" not in txt and "import oracle" not in txt, os.path.join(base, f)
+
+
+def test_null_arguments_are_rejected_not_dereferenced(built):
+    """Every entry point called with NULL handles / buffers and zero sizes: a negative vt_status (or a harmless default), never a
+    crash — the boundary is `extern "C"`, a null from the host language must not take the process down."""
+    from gstreamer_vit_tracker_b200 import _lib
+
+    lib = _lib.lib()
+    for name, (res, args) in _lib.SYMBOLS.items():
+        vals = []
+        for a in args:
+            if a in (C.c_int32, C.c_int, C.c_size_t, C.c_uint8, C.c_float, C.c_uint64, C.c_double):
+                vals.append(a(0))
+            elif a is _lib.vt_bbox:
+                vals.append(_lib.vt_bbox(0, 0, 0, 0))
+            else:
+                vals.append(None)
+        r = getattr(lib, name)(*vals)
+        if name == "vt_timing_stats_create":  # no arguments: a real object
+            assert r
+            lib.vt_timing_stats_destroy(C.c_void_p(r))
+        elif res is C.c_int32 and name not in ("vt_abi_version", "vt_command_from_key", "vt_tracker_model_dim", "vt_context_current_bbox",
+                                                "vt_context_lost_frames"):
+            assert r < 0, (name, r)
