@@ -89,3 +89,30 @@ def test_null_arguments_are_rejected_not_dereferenced(built):
         elif res is C.c_int32 and name not in ("vt_abi_version", "vt_command_from_key", "vt_tracker_model_dim", "vt_context_current_bbox",
                                                 "vt_context_lost_frames"):
             assert r < 0, (name, r)
+
+
+def test_header_is_plain_c_and_links(built, tmp_path):
+    """include/vt_tracker.h is the FFI contract: it must compile as C99 (and C++11) on its own, and a C program must link against the
+    library and get the documented defaults back — no torch, no C++ types in the boundary."""
+    import shutil
+    import subprocess
+
+    from gstreamer_vit_tracker_b200 import _lib
+
+    if not shutil.which("gcc"):
+        import pytest
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "vt_tracker.h"\n#include <stdio.h>\n'
+                   "int main(void) { vt_config c; vt_config_default(&c); int32_t cmd = -1, fast = -1;\n"
+                   "  printf(\"%d %d %d %d %d\\n\", vt_abi_version(), (int)c.struct_size == (int)sizeof(vt_config), c.width, c.gemm_mode,\n"
+                   "         vt_command_from_key((uint8_t)'q', &cmd, &fast));\n  return 0; }\n")
+    inc, libdir = os.path.join(ROOT, "include"), os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, str(src), "-L", libdir, "-lvittrack_b200",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[:4] == ["1", "1", "1920", "1"], out
+    if shutil.which("g++"):
+        subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True,
+                       capture_output=True)
