@@ -219,7 +219,7 @@ vt_status vt_overlay_current(vt_tracker* t, uint8_t* frame, size_t len, const vt
 /* timing                                                                                       */
 /* ------------------------------------------------------------------------------------------- */
 /* ≙ TimingStats (src/timing_stats.rs): same 120-sample windows and accessors, plus the
- * device-timed (cudaEvent) stage breakdown of the last frame and its rolling means. */
+ * device-timed stage breakdown (%globaltimer stamps written by the kernels) of the last frame and its rolling means. */
 typedef struct {
     double fps;            /* ≙ TimingStats::fps()          1e6 / mean(interval_us) */
     double avg_conv_ms;    /* ≙ TimingStats::avg_conv_ms()  (device: preprocess stage) */

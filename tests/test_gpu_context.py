@@ -161,3 +161,46 @@ def test_context_flow_rgb24(api, oracle, weight_dir):
         assert g.state_name() == name
         assert np.array_equal(got, ref), (n, name, int((got != ref).sum()))
     assert g.state_name() == "TRACKING"
+
+
+@pytest.mark.gpu
+def test_c_example_matches_the_python_binding(built, weight_dir, tmp_path):
+    """examples/track_nv12.c (plain C against include/vt_tracker.h) tracks a synthetic NV12 file and prints the same boxes and scores
+    as the ctypes binding: the boundary really is usable from C alone."""
+    import os
+    import re
+    import shutil
+    import subprocess
+
+    import numpy as np
+
+    from gstreamer_vit_tracker_b200 import _lib, api, synth, weights
+
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "track_nv12")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "track_nv12.c"), "-L", libdir,
+                    "-lvittrack_b200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True, capture_output=True)
+    spec = synth.CONFIGS["cfg1"]
+    st = synth.SyntheticStream(spec)
+    w = weights.ensure_weight_file("tiny", weight_dir)
+    frames = [np.ascontiguousarray(st.frame(i)).reshape(-1) for i in range(6)]
+    path = tmp_path / "frames.nv12"
+    with open(path, "wb") as f:
+        for fr in frames:
+            f.write(fr.tobytes())
+    box = st.target_boxes(0)[0]
+    out = subprocess.run([exe, w, str(path), str(spec.width), str(spec.height), *map(str, box)], check=True, capture_output=True, text=True).stdout
+    got = [(float(m.group(1)), tuple(int(v) for v in m.group(2, 3, 4, 5)))
+           for m in re.finditer(r"score ([0-9.]+) box \((-?\d+), (-?\d+), (-?\d+), (-?\d+)\)", out)]
+    assert len(got) == 5, out
+    trk = api.VitTrack.new(w, spec.width, spec.height, box_overlay=True, upload_window=True)
+    pin = api.PinnedBuffer(frames[0].size)
+    pin.array[:] = frames[0]
+    trk.init(pin.array, api.BBox(*box))
+    for i in range(1, 6):
+        pin.array[:] = frames[i]
+        r = trk.update(pin.array)
+        assert tuple(r.bbox) == got[i - 1][1] and abs(r.score - got[i - 1][0]) < 1e-4, (i, r, got[i - 1])
