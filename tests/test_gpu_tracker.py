@@ -3,23 +3,35 @@ against the CPU oracle and the cv2.TrackerVit fixtures.
 
 Tolerances (BASELINE.json north_star): NV12 conversion and the u8 preprocessing bit-exact; score within
 1e-3 absolute; boxes IoU >= 0.99.  Boxes are floor()s of fp32 expressions scaled by the crop size, so a
-relative error e in the size/offset maps moves a pre-floor coordinate by ~e*crop px: frames whose oracle
-pre-floor value lies within BOUNDARY_PX of an integer may legitimately differ by one pixel and are counted
-separately (reported, bounded), everything else must match exactly."""
+relative error e in the size/offset maps moves a pre-floor coordinate by ~e*crop px.  Two kinds of frame are
+numerically undecidable and are counted, bounded (<= 3 % of the frames of a sequence, together) and recorded:
+  * boundary: an oracle pre-floor coordinate lies within BOUNDARY_PX of an integer -> that coordinate may differ by one pixel;
+  * tie: the oracle's hann-weighted top-1/top-2 margin is below TIE_MARGIN -> the GPU may pick another of the tied cells; the
+    cell it picked must be one of the oracle's tied maxima and its score / box must equal the oracle's values FOR THAT CELL.
+Everything else must match exactly.  The per-test counts go to gpurun_out/parity_stats.json (and are asserted on at the end of
+this file), so they survive `pytest -q`."""
 import hashlib
+import json
+import math
+import os
 
 import numpy as np
 import pytest
 
-from conftest import golden
+from conftest import ROOT, golden
 from gstreamer_vit_tracker_b200 import synth, weights
 
 pytestmark = pytest.mark.gpu
 
 SCORE_TOL = 1e-3
 IOU_MIN = 0.99
-TIE_MARGIN = 2e-3     # hann-weighted top-1/top-2 margin under which the argmax is numerically undecidable
-BOUNDARY_PX = 0.02    # distance of a pre-floor coordinate from an integer under which +-1 px is accepted
+TIE_MARGIN = 1e-4        # fp32 / bf16x3 paths (measured |dscore| ~1e-5): top-1/top-2 margin under which the argmax is undecidable
+TIE_MARGIN_FP16 = 2e-3   # single-pass fp16 operands (opt-in mode, |dscore| ~3e-4)
+BOUNDARY_PX = 0.02       # distance of a pre-floor coordinate from an integer under which +-1 px is accepted
+EXEMPT_FRAC = 0.03       # ties + boundary frames per sequence
+THRESHOLD = 0.2
+
+PARITY_STATS = {}        # test id -> stats dict, written to gpurun_out/parity_stats.json by the last test of this file
 
 
 @pytest.fixture(scope="module")
@@ -44,10 +56,11 @@ def iou(a, b):
     return inter / union if union > 0 else 1.0
 
 
-def oracle_prefloor(ref, rect_before):
-    """Pre-floor bbox coordinates of the oracle's last update (fp32 arithmetic as in App. A.6)."""
+def oracle_prefloor(ref, rect_before, cell=None):
+    """Pre-floor bbox coordinates the oracle's last update gives for map cell `cell` (default: its own argmax), in the fp32
+    arithmetic of App. A.6, and the hann-weighted top-1/top-2 margin."""
     cw, sm, om, _ = ref.last_maps()
-    best = int(np.argmax(cw))
+    best = int(np.argmax(cw)) if cell is None else int(cell)
     my, mx = divmod(best, 16)
     f = np.float32
     cx = (f(mx) + om[best]) / f(16)
@@ -61,28 +74,53 @@ def oracle_prefloor(ref, rect_before):
     return [float(v) for v in vals], float(srt[0] - srt[1])
 
 
-def compare_step(r, ok, score, bb, prefloor, margin, stats, where):
-    """One teacher-forced step: GPU result r vs oracle (ok, score, bb)."""
-    assert abs(r.score - score) <= SCORE_TOL or margin < TIE_MARGIN, (where, r.score, score)
-    stats["max_dscore"] = max(stats["max_dscore"], abs(r.score - score) if margin >= TIE_MARGIN else 0.0)
-    if margin < TIE_MARGIN:
+def compare_step(trk, r, ref, rect_before, stats, where, target=0, tie_margin=TIE_MARGIN):
+    """One step from the same rect_last: GPU result r (target `target` of handle trk) vs the oracle tracker `ref`, which has just
+    run update() on the same frame.  Returns True when the step matched exactly."""
+    cw = ref.last_maps()[0]
+    best = int(np.argmax(cw))
+    srt = np.sort(cw)[::-1]
+    margin = float(srt[0] - srt[1])
+    cell = best
+    if margin < tie_margin:  # undecidable argmax: the GPU's cell must be one of the oracle's tied maxima
         stats["ties"] += 1
-        return
-    assert r.success == ok, where
-    if not ok:
-        return
-    if tuple(r.bbox) == tuple(bb):
-        stats["exact"] += 1
-        return
-    near = [abs(v - round(v)) < BOUNDARY_PX for v in prefloor]
-    diff = [abs(a - b) for a, b in zip(r.bbox, bb)]
-    assert all(d <= 1 for d in diff) and all(n for d, n in zip(diff, near) if d), (where, r.bbox, bb, prefloor)
+        cell = int(np.argmax(trk.debug_read(target)["conf_win"]))
+        assert cw[cell] >= cw[best] - tie_margin, (where, "argmax outside the oracle's tied set", cell, best, float(cw[cell]), float(cw[best]))
+    score = float(cw[cell])
+    d = abs(r.score - score)
+    stats["max_dscore"] = max(stats["max_dscore"], d)
+    assert d <= SCORE_TOL, (where, r.score, score)
+    if abs(score - THRESHOLD) > SCORE_TOL:
+        assert r.success == (score >= THRESHOLD), where
+    if not r.success:
+        stats["exact"] += cell == best
+        return cell == best
+    pre, _ = oracle_prefloor(ref, rect_before, cell)
+    want = tuple(int(math.floor(v)) for v in pre)
+    if tuple(r.bbox) == want:
+        stats["exact"] += cell == best
+        return cell == best
+    near = [abs(v - round(v)) < BOUNDARY_PX for v in pre]
+    diff = [abs(a - b) for a, b in zip(r.bbox, want)]
+    assert all(dd <= 1 for dd in diff) and all(n for dd, n in zip(diff, near) if dd), (where, r.bbox, want, pre)
     stats["boundary"] += 1
-    stats["min_iou_boundary"] = min(stats["min_iou_boundary"], iou(r.bbox, bb))
+    stats["min_iou_boundary"] = min(stats["min_iou_boundary"], iou(r.bbox, want))
+    return False
 
 
 def new_stats():
-    return {"exact": 0, "boundary": 0, "ties": 0, "max_dscore": 0.0, "min_iou_boundary": 1.0}
+    return {"frames": 0, "exact": 0, "boundary": 0, "ties": 0, "max_dscore": 0.0, "min_iou_boundary": 1.0}
+
+
+def finish_stats(name, stats, frames):
+    """Bounds of a teacher-forced sequence + the record that survives `pytest -q`."""
+    stats["frames"] = frames
+    PARITY_STATS[name] = dict(stats)
+    print(f"\n[parity {name}] {frames} steps: exact {stats['exact']}, boundary(+-1px) {stats['boundary']}, ties {stats['ties']}, "
+          f"max|dscore| {stats['max_dscore']:.2e}, min IoU on boundary steps {stats['min_iou_boundary']:.4f}")
+    assert stats["max_dscore"] <= SCORE_TOL
+    assert stats["ties"] + stats["boundary"] <= max(1, math.ceil(EXEMPT_FRAC * frames)), (name, stats)
+    assert stats["exact"] >= frames - stats["ties"] - stats["boundary"], (name, stats)
 
 
 # ---- preprocessing: bit-exact ----------------------------------------------------------------------
@@ -166,9 +204,11 @@ def test_layerwise_tokens(api, oracle, weight_dir, model, gemm_mode):
 # ---- against the third-party cv2.TrackerVit fixtures -----------------------------------------------------
 @pytest.mark.parametrize("gemm_mode", [0, 1], ids=["fp32simt", "tcgen05x3"])
 @pytest.mark.parametrize("variant", ["stable", "wild"])
-def test_sequences_vs_cv2_golden(api, weight_dir, variant, gemm_mode):
-    g = golden("trackervit_nano.json")["models"][variant]
-    wpath = weights.ensure_weight_file("nano", weight_dir, variant=variant)
+@pytest.mark.parametrize("model", ["nano", "tiny"])
+def test_sequences_vs_cv2_golden(api, weight_dir, model, variant, gemm_mode):
+    """Free-running sequences recorded from the third-party cv2.TrackerVit (nano and the bench model tiny; cfg2 leads the tiny set)."""
+    g = golden(f"trackervit_{model}.json")["models"][variant]
+    wpath = weights.ensure_weight_file(model, weight_dir, variant=variant)
     assert hashlib.sha256(open(wpath, "rb").read()).hexdigest() == g["weights_sha256"]
     for seq in g["sequences"]:
         sp = seq["spec"]
@@ -176,9 +216,10 @@ def test_sequences_vs_cv2_golden(api, weight_dir, variant, gemm_mode):
         st = synth.SyntheticStream(spec)
         trk = api.VitTrack.new(wpath, spec.width, spec.height, gemm_mode=gemm_mode)
         trk.init(st.frame(0), api.BBox(*seq["init_box"]))
-        n_exact = 0
+        n_exact, dmax = 0, 0.0
         for i, fr in enumerate(seq["frames"]):
             r = trk.update(st.frame(i))
+            dmax = max(dmax, abs(r.score - fr["score"]))
             assert abs(r.score - fr["score"]) <= SCORE_TOL, (seq["name"], i, r.score, fr["score"])
             assert r.success == fr["ok"]
             if fr["ok"]:
@@ -187,14 +228,17 @@ def test_sequences_vs_cv2_golden(api, weight_dir, variant, gemm_mode):
                 else:  # resynchronise on cv2's box so that one boundary flip cannot cascade
                     assert iou(r.bbox, fr["bbox"]) >= 0.95 and max(abs(a - b) for a, b in zip(r.bbox, fr["bbox"])) <= 1, (seq["name"], i, r.bbox, fr["bbox"])
                     trk.set_rect(fr["bbox"])
+        PARITY_STATS[f"cv2_sequence/{model}/{variant}/{seq['name']}/gemm{gemm_mode}"] = {
+            "frames": len(seq["frames"]), "exact": n_exact, "max_dscore": dmax}
         assert n_exact >= len(seq["frames"]) - 2, (seq["name"], n_exact)
 
 
 @pytest.mark.parametrize("gemm_mode", [0, 1], ids=["fp32simt", "tcgen05x3"])
 @pytest.mark.parametrize("variant", ["stable", "wild"])
-def test_single_steps_vs_cv2_golden(api, weight_dir, variant, gemm_mode):
-    g = golden("trackervit_nano.json")["models"][variant]
-    wpath = weights.ensure_weight_file("nano", weight_dir, variant=variant)
+@pytest.mark.parametrize("model", ["nano", "tiny"])
+def test_single_steps_vs_cv2_golden(api, weight_dir, model, variant, gemm_mode):
+    g = golden(f"trackervit_{model}.json")["models"][variant]
+    wpath = weights.ensure_weight_file(model, weight_dir, variant=variant)
     sp = g["steps_spec"]
     spec = synth.StreamSpec("steps", sp["w"], sp["h"], sp["seed"], [tuple(t) for t in sp["targets"]])
     st = synth.SyntheticStream(spec)
@@ -235,46 +279,94 @@ def test_teacher_forced_sequence(api, oracle, weight_dir, model, cfg, frames, ge
     trk.init(f0, api.BBox(*box))
     ref.init(oracle.nv12_to_rgb(f0, W, H, 8), box)
     stats = new_stats()
+    fp16 = gemm_mode == 3
     for n in range(frames):
         fr = st.frame(n)
         before = ref.rect
         trk.set_rect(before)
         r = trk.update(fr)
-        rc, ok, score, bb = ref.update(oracle.nv12_to_rgb(fr, W, H, 8))
+        rc = ref.update(oracle.nv12_to_rgb(fr, W, H, 8))[0]
         assert rc == 0
-        pre, margin = oracle_prefloor(ref, before)
-        compare_step(r, ok, score, bb, pre, margin, stats, (model, cfg, n))
-    print(f"\n[parity {model}/{cfg}/gemm_mode={gemm_mode}] {frames} frames: exact {stats['exact']}, boundary(+-1px) {stats['boundary']}, ties {stats['ties']}, "
-          f"max|dscore| {stats['max_dscore']:.2e}, min IoU on boundary frames {stats['min_iou_boundary']:.4f}")
-    assert stats["exact"] >= 0.9 * frames
-    assert stats["max_dscore"] <= SCORE_TOL
+        compare_step(trk, r, ref, before, stats, (model, cfg, n), tie_margin=TIE_MARGIN_FP16 if fp16 else TIE_MARGIN)
+    if fp16:  # opt-in mode: its wider tie window is not held to the 3 % bound of the default paths; the score bar is the same
+        PARITY_STATS[f"teacher_forced/{model}/{cfg}/gemm{gemm_mode}"] = dict(stats, frames=frames)
+        assert stats["max_dscore"] <= SCORE_TOL and stats["exact"] >= 0.85 * frames, stats
+    else:
+        finish_stats(f"teacher_forced/{model}/{cfg}/gemm{gemm_mode}", stats, frames)
 
 
-def test_free_running_sequence_iou(api, oracle, weight_dir):
-    """No teacher forcing: both trackers run free for 60 frames; IoU >= 0.99 on every frame up to the first
-    numerically undecidable frame (tie / floor boundary), which must not come early."""
-    spec = synth.CONFIGS["cfg1"]
+@pytest.mark.parametrize("model,cfg,frames,first_min", [("nano", "cfg1", 120, 30), ("tiny", "cfg2", 300, 100)])
+def test_free_running_sequence_iou(api, oracle, weight_dir, model, cfg, frames, first_min):
+    """No teacher forcing: the GPU tracker and the oracle run free from the same init box (cfg2 / tiny = the bench workload, 300 frames).
+    IoU >= 0.99 and |dscore| <= 1e-3 on every frame up to the first numerically undecidable one (tie / floor boundary), which must not
+    come before frame `first_min`; there the GPU state is resynchronised on the oracle's rect (a one-pixel difference would otherwise
+    feed back through the crop) and the run continues under the same rules; undecidable frames stay <= 3 %."""
+    spec = synth.CONFIGS[cfg]
     W, H = spec.width, spec.height
-    wpath = weights.ensure_weight_file("nano", weight_dir)
+    wpath = weights.ensure_weight_file(model, weight_dir)
     st = synth.SyntheticStream(spec)
-    trk = api.VitTrack.new(wpath, W, H)
-    ref = oracle.VitTrack(wpath, threads=8)
+    trk = api.VitTrack.new(wpath, W, H, gemm_mode=1)
+    ref = oracle.VitTrack(wpath, threads=16)
     box = st.target_boxes(0)[0]
     trk.init(st.frame(0), api.BBox(*box))
-    ref.init(oracle.nv12_to_rgb(st.frame(0), W, H, 8), box)
-    agreed = 0
-    for n in range(60):
+    ref.init(oracle.nv12_to_rgb(st.frame(0), W, H, 16), box)
+    stats = new_stats()
+    first = None
+    min_iou = 1.0
+    for n in range(frames):
         fr = st.frame(n)
         before = ref.rect
+        assert trk.get_rect() == tuple(before), n   # both trackers enter the frame with the same rect_last
         r = trk.update(fr)
-        rc, ok, score, bb = ref.update(oracle.nv12_to_rgb(fr, W, H, 8))
-        pre, margin = oracle_prefloor(ref, before)
-        if tuple(r.bbox) != tuple(bb):
-            assert margin < TIE_MARGIN or any(abs(v - round(v)) < BOUNDARY_PX for v in pre), (n, r.bbox, bb, pre, margin)
-            break
-        assert iou(r.bbox, bb) >= IOU_MIN and abs(r.score - score) <= SCORE_TOL
-        agreed += 1
-    assert agreed >= 30, agreed
+        rc, ok, score, bb = ref.update(oracle.nv12_to_rgb(fr, W, H, 16))
+        assert rc == 0
+        same = compare_step(trk, r, ref, before, stats, (model, cfg, n))
+        if same:
+            assert r.success == ok and (not ok or (tuple(r.bbox) == tuple(bb) and iou(r.bbox, bb) >= IOU_MIN)), (n, r, bb)
+        else:
+            first = n if first is None else first
+            if ok:
+                min_iou = min(min_iou, iou(r.bbox, bb))
+            trk.set_rect(ref.rect)
+    stats["first_undecidable_frame"] = first
+    stats["min_iou_undecidable"] = min_iou
+    finish_stats(f"free_running/{model}/{cfg}", stats, frames)
+    assert first is None or first > first_min, (first, stats)
+
+
+@pytest.mark.gpu
+def test_cfg4_full_size_16_targets_vs_oracle(api, oracle, weight_dir):
+    """BASELINE config 4 at full size: 3840x2160 NV12, tiny, 16 targets through ONE batched forward (M = 5120 rows: the unchained
+    MLP form, FC2 as its own GEMM), 5 teacher-forced frames, EVERY target against its own oracle.VitTrack (one fp32 forward per target
+    and frame): score within 1e-3, box equal off floor ties (reference semantics: /root/reference/src/tracker_context.rs:120-125,
+    one VitTrack per target)."""
+    spec = synth.CONFIGS["cfg4"]
+    W, H = spec.width, spec.height
+    st = synth.SyntheticStream(spec)
+    nt = len(spec.targets)
+    assert nt == 16
+    wpath = weights.ensure_weight_file("tiny", weight_dir)
+    trk = api.VitTrack.new(wpath, W, H, max_targets=nt, gemm_mode=1)
+    refs = [oracle.VitTrack(wpath, threads=16) for _ in range(nt)]
+    f0 = st.frame(0)
+    rgb0 = oracle.nv12_to_rgb(f0, W, H, 16)
+    for k, b in enumerate(st.target_boxes(0)):
+        trk.init(f0, api.BBox(*b), target=k)
+        assert refs[k].init(rgb0, b) == 0
+    stats = new_stats()
+    frames = 5
+    for n in range(frames):
+        fr = st.frame(n)
+        rgb = oracle.nv12_to_rgb(fr, W, H, 16)
+        before = [refs[k].rect for k in range(nt)]
+        for k in range(nt):
+            trk.set_rect(before[k], target=k)
+        rs = trk.update_all(fr)
+        for k in range(nt):
+            assert rs[k].status == 0, (n, k, rs[k])
+            assert refs[k].update(rgb)[0] == 0
+            compare_step(trk, rs[k], refs[k], before[k], stats, ("cfg4", n, k), target=k)
+    finish_stats("teacher_forced/tiny/cfg4x16/gemm1", stats, frames * nt)
 
 
 # ---- multi-target, formats, errors -----------------------------------------------------------------------------
@@ -574,20 +666,16 @@ def test_bench_workload_teacher_forced_300_frames(api, oracle, weight_dir):
         trk.set_rect(before)
         pin.array[:] = fr
         r = trk.update(pin.array)
-        rc, ok, score, bb = ref.update(oracle.nv12_to_rgb(fr, W, H, 16))
+        rc = ref.update(oracle.nv12_to_rgb(fr, W, H, 16))[0]
         assert rc == 0
-        pre, margin = oracle_prefloor(ref, before)
-        compare_step(r, ok, score, bb, pre, margin, stats, ("tiny", "cfg2", n))
+        compare_step(trk, r, ref, before, stats, ("tiny", "cfg2", n))
         if n % 50 == 0 and r.success and r.score > 0.25:
             want = fr.copy()
             x, y, w, h = r.bbox
             oracle.draw_rect_nv12(want, W, H, x, y, w, h, 3, 255)
             oracle.draw_crosshair_nv12(want, W, H, x + w // 2, y + h // 2, 15, 255)
             assert np.array_equal(pin.array, want), n
-    print(f"\n[parity bench workload] {frames} frames: exact {stats['exact']}, boundary(+-1px) {stats['boundary']}, ties {stats['ties']}, "
-          f"max|dscore| {stats['max_dscore']:.2e}, min IoU on boundary frames {stats['min_iou_boundary']:.4f}")
-    assert stats["exact"] >= 0.9 * frames
-    assert stats["max_dscore"] <= SCORE_TOL
+    finish_stats("teacher_forced/tiny/cfg2/bench_workload_300", stats, frames)
 
 
 @pytest.mark.gpu
@@ -732,3 +820,26 @@ def test_kernel_forms_agree(api, weight_dir, monkeypatch):
                 for a, b in zip(fa, fb):
                     assert a.success and a.status == 0 and a.bbox == b.bbox, (spec.name, env, a, b)
                     assert abs(a.score - b.score) < 1e-5, (spec.name, env, a, b)
+
+
+def test_zz_parity_stats_recorded():
+    """Last test of the file: the tie / boundary / |dscore| counts of every sequence above go to gpurun_out/parity_stats.json (the
+    numbers behind the 1e-3 / IoU claims survive `pytest -q`), and the global bounds hold over everything that ran."""
+    if not PARITY_STATS:
+        pytest.skip("no parity sequence ran in this session")
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    tot = {"frames": 0, "exact": 0, "boundary": 0, "ties": 0, "max_dscore": 0.0}
+    for name, stt in PARITY_STATS.items():
+        if "gemm3" in name:
+            continue  # opt-in fp16 mode: recorded, not part of the default-path totals
+        tot["frames"] += stt["frames"]
+        tot["exact"] += stt["exact"]
+        tot["boundary"] += stt.get("boundary", 0)
+        tot["ties"] += stt.get("ties", 0)
+        tot["max_dscore"] = max(tot["max_dscore"], stt["max_dscore"])
+    with open(os.path.join(out, "parity_stats.json"), "w") as f:
+        json.dump({"bars": {"score_tol": SCORE_TOL, "tie_margin": TIE_MARGIN, "boundary_px": BOUNDARY_PX, "exempt_frac": EXEMPT_FRAC},
+                   "total_default_paths": tot, "sequences": PARITY_STATS}, f, indent=1, sort_keys=True)
+    assert tot["max_dscore"] <= SCORE_TOL
+    assert tot["ties"] + tot["boundary"] <= EXEMPT_FRAC * tot["frames"], tot

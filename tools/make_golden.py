@@ -14,8 +14,8 @@ Sources of truth, none of which is the C oracle:
   * yuy2_golden.json     — YUY2 -> RGB known answers / frame hashes from a pure-Python evaluation of the reference's BT.601 integer
                            formulas on packed 4:2:2, and cv2.resize(INTER_LINEAR) up-scale hashes (SURVEY.md §8(f) row 1);
   * keymap.json          — the keyboard byte -> UserCommand table parsed out of /root/reference/src/raw_mode_guard.rs:65-101;
-  * trackervit_nano.json — boxes and scores produced by the third-party cv2.TrackerVit (OpenCV 4.13, DNN CPU
-                           backend) running an ONNX export of the same weight file.
+  * trackervit_nano.json, trackervit_tiny.json — boxes and scores produced by the third-party cv2.TrackerVit (OpenCV 4.13, DNN CPU
+                           backend) running an ONNX export of the same weight file; `tiny` is the bench model.
 The tests compare the C oracle (and, on the GPU, the CUDA path) with these files.
 """
 from __future__ import annotations
@@ -448,7 +448,9 @@ def doctored_std():
     return (n / s[0], -n / s[1], -n / s[2], 0.0)
 
 
-def gen_trackervit():
+def gen_trackervit(model="nano"):
+    """trackervit_<model>.json.  `nano` (D=64, L=2) is the quick fixture; `tiny` (D=192, L=12, the bench / headline model) pins the
+    oracle and the GPU path at the depth and width where rounding accumulates (the headline model had no third-party check)."""
     import cv2
     from torch_model import export_onnx
     import tempfile
@@ -457,9 +459,9 @@ def gen_trackervit():
     out = {"source": f"cv2.TrackerVit (OpenCV {cv2.__version__}, DNN CPU), ONNX export of the same VTW1 file (opset 17)",
            "threshold": 0.2, "models": {}}
     for variant in ("stable", "wild"):
-        wpath = weights.ensure_weight_file("nano", tmp, variant=variant)
+        wpath = weights.ensure_weight_file(model, tmp, variant=variant)
         whash = hashlib.sha256(open(wpath, "rb").read()).hexdigest()
-        onnx = os.path.join(tmp, f"nano_{variant}.onnx")
+        onnx = os.path.join(tmp, f"{model}_{variant}.onnx")
         export_onnx(wpath, onnx)
 
         def make():
@@ -470,6 +472,8 @@ def gen_trackervit():
         # (a) free-running sequences
         seqs = [("cfg1", synth.CONFIGS["cfg1"], 40), ("corner", synth.StreamSpec("corner", 640, 360, 31, [(2, 4, 90, 70, -3, -2)]), 30),
                 ("small", synth.StreamSpec("small", 320, 240, 32, [(150, 100, 30, 24, 2, 1)]), 30)]
+        if model == "tiny":  # the bench workload itself (cfg2, 1080p) leads
+            seqs = [("cfg2", synth.CONFIGS["cfg2"], 40)] + [(n, s, 20) for n, s, _ in seqs]
         for name, spec, n in seqs:
             st = synth.SyntheticStream(spec)
             trk = make()
@@ -501,7 +505,7 @@ def gen_trackervit():
                 entry["single_steps"].append({"box": [bx, by, bw, bh], "error": True})
         entry["steps_spec"] = {"w": spec.width, "h": spec.height, "seed": spec.seed, "targets": [list(t) for t in spec.targets], "frames": [0, 5]}
         out["models"][variant] = entry
-    json.dump(out, open(os.path.join(GOLD, "trackervit_nano.json"), "w"))
+    json.dump(out, open(os.path.join(GOLD, f"trackervit_{model}.json"), "w"))
 
 
 def gen_yuy2():
@@ -569,7 +573,7 @@ def gen_keymap():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["kat", "glyphs", "overlay", "state", "resize", "trackervit", "keymap", "yuy2"]
+    which = sys.argv[1:] or ["kat", "glyphs", "overlay", "state", "resize", "trackervit", "trackervit_tiny", "keymap", "yuy2"]
     if "keymap" in which: gen_keymap()
     if "yuy2" in which: gen_yuy2()
     font = gen_glyphs() if ("glyphs" in which or "overlay" in which) else None
@@ -577,6 +581,7 @@ if __name__ == "__main__":
     if "overlay" in which: gen_overlay(font)
     if "state" in which: gen_state_traces()
     if "resize" in which: gen_resize()
-    if "trackervit" in which: gen_trackervit()
+    if "trackervit" in which: gen_trackervit("nano")
+    if "trackervit_tiny" in which: gen_trackervit("tiny")
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
