@@ -17,6 +17,7 @@ Everything here runs on the GPU through libvittrack_b200.so; nothing falls back 
 from __future__ import annotations
 
 import ctypes as C
+from collections import deque
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -88,7 +89,8 @@ class PinnedBuffer:
 
 
 def _ptr(a: np.ndarray) -> C.c_void_p:
-    assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"], "frames are contiguous uint8 arrays"
+    if not isinstance(a, np.ndarray) or a.dtype != np.uint8 or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("frames are C-contiguous uint8 numpy arrays")
     return C.c_void_p(a.ctypes.data)
 
 
@@ -158,6 +160,9 @@ class VitTrack:
             check(lib().vt_tracker_create(C.byref(cfg), C.byref(h)), "vt_tracker_create")
             self._h = h
         self._res = (vt_result * self.max_targets)()
+        # frames handed to submit() and not yet returned by wait(): the C side keeps the raw pointer until wait() (the overlay writes
+        # into it), so the arrays must stay alive — a temporary like submit(fr.copy()) would otherwise be freed under the library
+        self._inflight = deque()
 
     @classmethod
     def new(cls, model_path: str, width: int = 1920, height: int = 1080, **kw) -> "VitTrack":
@@ -195,13 +200,24 @@ class VitTrack:
         return self._results()
 
     def submit_device(self, d_ptr: int, nbytes: int) -> None:
+        """Frame already in device memory, tracked in place.  The caller keeps the device buffer alive until the matching wait()."""
         check(lib().vt_tracker_submit_device(self._h, C.c_void_p(d_ptr), nbytes), "vt_tracker_submit_device")
+        self._inflight.append(None)
 
     def submit(self, frame: np.ndarray) -> None:
-        check(lib().vt_tracker_submit(self._h, _ptr(frame), frame.size), "vt_tracker_submit")
+        """Enqueue one frame (up to two may be in flight).  Lifetime rule of the C ABI: `frame` must stay valid until the matching
+        wait() returns — with box_overlay the library WRITES the box pixels into it.  This binding holds a reference to the array
+        until then, so temporaries are safe; the caller must still not resize / free the underlying buffer."""
+        p = _ptr(frame)
+        check(lib().vt_tracker_submit(self._h, p, frame.size), "vt_tracker_submit")
+        self._inflight.append(frame)
 
     def wait(self) -> List[TrackResult]:
-        check(lib().vt_tracker_wait(self._h, self._res), "vt_tracker_wait")
+        try:
+            check(lib().vt_tracker_wait(self._h, self._res), "vt_tracker_wait")
+        finally:
+            if self._inflight:
+                self._inflight.popleft()
         return self._results()
 
     def update_device(self, d_ptr: int, nbytes: int) -> List[TrackResult]:
