@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libvittrack_b200.so")
 VT_OK, VT_ERR_INVALID, VT_ERR_CUDA, VT_ERR_WEIGHTS, VT_ERR_CROP_OUTSIDE, VT_ERR_NOT_INIT, VT_ERR_GLYPH = 0, -1, -2, -3, -4, -5, -6
 VT_FMT_NV12, VT_FMT_RGB24, VT_FMT_GRAY8 = 0, 1, 2
 VT_GEMM_FP32_SIMT, VT_GEMM_TCGEN05_BF16X3, VT_GEMM_TCGEN05_BF16, VT_GEMM_TCGEN05_FP16 = 0, 1, 2, 3
+VT_DECODE_CEIL4, VT_DECODE_4FLOOR = 0, 1
+VT_WINDOW_HANN, VT_WINDOW_ONE_MINUS_HANN = 0, 1
 VT_OV_RECT, VT_OV_CROSSHAIR, VT_OV_TEXT, VT_OV_BACKGROUND, VT_OV_CURSOR, VT_OV_SELECTION = range(6)
 
 
@@ -35,7 +37,10 @@ class vt_config(C.Structure):
         ("struct_size", C.c_uint32), ("weights_path", C.c_char_p), ("device", C.c_int32), ("format", C.c_int32),
         ("width", C.c_int32), ("height", C.c_int32), ("max_targets", C.c_int32), ("score_threshold", C.c_float),
         ("gemm_mode", C.c_int32), ("use_cuda_graph", C.c_int32), ("box_overlay", C.c_int32), ("overlay_gate", C.c_float),
-        ("debug_capture", C.c_int32), ("upload_window", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("debug_capture", C.c_int32), ("upload_window", C.c_int32),
+        # SURVEY.md App. A.7 variant switches (VT_ABI_VERSION 2)
+        ("pad_plus1", C.c_int32), ("decode_window", C.c_int32), ("window", C.c_int32), ("norm_custom", C.c_int32),
+        ("norm_scale", C.c_float * 3), ("norm_bias", C.c_float * 3), ("reserved", C.c_int32 * 4),
     ]
 
 

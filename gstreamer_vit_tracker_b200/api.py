@@ -96,7 +96,11 @@ def _ptr(a: np.ndarray) -> C.c_void_p:
 
 def make_config(weights: str, width: int, height: int, fmt: str = "nv12", max_targets: int = 1, device: int = 0,
                 use_cuda_graph: bool = True, box_overlay: bool = False, score_threshold: float = 0.20,
-                gemm_mode: int = L.VT_GEMM_TCGEN05_BF16X3, debug_capture: bool = False, upload_window: bool = False) -> vt_config:
+                gemm_mode: int = L.VT_GEMM_TCGEN05_BF16X3, debug_capture: bool = False, upload_window: bool = False,
+                pad_plus1: bool = False, decode_window: int = L.VT_DECODE_CEIL4, window: int = L.VT_WINDOW_HANN,
+                norm: Optional[Tuple[Sequence[float], Sequence[float]]] = None) -> vt_config:
+    """`pad_plus1`, `decode_window`, `window`, `norm=(scale[3], bias[3])` are the SURVEY.md App. A.7 variant switches (defaults: OpenCV 4.13
+    TrackerVit with the intended (u8/255 - mean)/std normalisation; `norm` replaces it by blob = u8*scale[c] + bias[c])."""
     cfg = vt_config()
     lib().vt_config_default(C.byref(cfg))
     if weights.lower().endswith(".onnx"):  # ≙ VitTrack::new(model_path) with the network in its public ONNX form
@@ -111,6 +115,11 @@ def make_config(weights: str, width: int, height: int, fmt: str = "nv12", max_ta
     cfg.box_overlay = int(box_overlay)
     cfg.debug_capture = int(debug_capture)
     cfg.upload_window = int(upload_window)
+    cfg.pad_plus1, cfg.decode_window, cfg.window = int(pad_plus1), int(decode_window), int(window)
+    if norm is not None:
+        cfg.norm_custom = 1
+        for k in range(3):
+            cfg.norm_scale[k], cfg.norm_bias[k] = float(norm[0][k]), float(norm[1][k])
     return cfg
 
 

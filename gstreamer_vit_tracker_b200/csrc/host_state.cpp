@@ -95,14 +95,16 @@ int vt_glyph_rows(int ch, uint8_t rows[7]) {
 vt_status vt_context_create(const vt_config* cfg, vt_context** out) {
     if (!cfg || !out) return VT_ERR_INVALID;
     *out = nullptr;
-    vt_config c = *cfg;
+    vt_config c;
+    const vt_status rs = vt::resolve_config(cfg, &c);
+    if (rs != VT_OK) return rs;
     c.max_targets = 1;   // one VitTrack per TrackerContext (src/tracker_context.rs:8)
     c.box_overlay = 0;   // the probe issues explicit overlay commands
     c.upload_window = 0; // ... on the device copy of the whole frame (vt_overlay_current)
     vt_tracker* t = nullptr;
     vt_status st = vt_tracker_create(&c, &t);  // ≙ VitTrack::new(model_path)?, src/tracker_context.rs:21
     if (st != VT_OK) return st;
-    vt_context* ctx = new vt_context(cfg->width, cfg->height);
+    vt_context* ctx = new vt_context(c.width, c.height);
     ctx->tracker = t;
     ctx->cfg = c;
     ctx->cfg.weights_path = nullptr;

@@ -269,7 +269,9 @@ __device__ __forceinline__ Tap lin_tap(int i, int s, int d, bool clamp_frac) {
 // RGB of the frame pixel (fx, fy); zero outside the frame (constant border of the crop).
 __device__ __forceinline__ void frame_rgb(const FrameDesc& f, int fx, int fy, int& r, int& g, int& b) {
     r = g = b = 0;
-    if (!f.valid || fx < 0 || fy < 0 || fx >= f.width || fy >= f.height) return;
+    // pad_plus1 (App. A.7, older OpenCV): a crop that reaches the right / bottom edge pads one pixel more, i.e. the last column / row of
+    // the frame reads as border; a crop that stays inside never addresses it, so the bound can move unconditionally
+    if (!f.valid || fx < 0 || fy < 0 || fx >= f.width - f.pad_plus1 || fy >= f.height - f.pad_plus1) return;
     if (f.format == VT_FMT_RGB24) {
         const uint8_t* p = f.data + ((size_t)fy * f.width + fx) * 3;
         r = p[0], g = p[1], b = p[2];
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, Targ
     if (bw > 0 && bh > 0) c = (int)ceil(__dmul_rn(sqrt((double)(int)area), (double)factor));
     const int x1 = bx + (bw - c) / 2, y1 = by + (bh - c) / 2;
     const int pl = max(0, -x1), pt = max(0, -y1);
-    const int pr = max(x1 + c - f.width, 0), pb = max(y1 + c - f.height, 0);
+    const int pr = max(x1 + c - f.width + f.pad_plus1, 0), pb = max(y1 + c - f.height + f.pad_plus1, 0);
     const bool outside = (c <= 0) || (c - pl - pr <= 0) || (c - pt - pb <= 0);
     if (threadIdx.x == 0 && blockIdx.x == 0 && factor == 4) st->crop_err = outside ? 1 : 0;
     if (outside) return;

@@ -82,14 +82,15 @@ vt_status vt_convert_nv12_rgb(vt_tracker* t, const uint8_t* nv12, size_t len, ui
     if (!t || !nv12 || !rgb_out || t->in_flight) return VT_ERR_INVALID;
     VT_CUDA(cudaSetDevice(t->cfg.device));
     const size_t W = t->W, H = t->H, out_bytes = W * H * 3;
+    if (t->fmt != VT_FMT_NV12) {
+        set_error("vt_convert_nv12_rgb: the handle was not created for NV12 frames");
+        return VT_ERR_INVALID;
+    }
     if (len < W * H * 3 / 2) {  // src/nv12_convert.rs:48-50
         memset(rgb_out, 0, out_bytes);
         return VT_OK;
     }
-    if (t->fmt != VT_FMT_NV12) {
-        set_error("vt_convert_nv12_rgb: handle was created for RGB24 frames");
-        return VT_ERR_INVALID;
-    }
+    t->d_frame_is_last_host_frame = false;  // the frame buffer is reused as the conversion's input
     if (!t->d_rgb) VT_CUDA(cudaMalloc(&t->d_rgb, out_bytes + 256));
     const size_t n = std::min(len, t->frame_bytes);
     const bool pin_in = is_pinned(nv12), pin_out = is_pinned(rgb_out);
@@ -271,6 +272,7 @@ static vt_status overlay_impl(vt_tracker* t, uint8_t* frame, size_t len, const v
     VT_CUDA(cudaEventRecord(t->ev[EV_DEC], t->stream));
     if (upload) {
         const size_t nb = std::min(len, t->frame_bytes);
+        t->d_frame_is_last_host_frame = false;
         if (is_pinned(frame)) {
             VT_CUDA(cudaMemcpyAsync(t->d_frame, frame, nb, cudaMemcpyHostToDevice, t->stream));
         } else {
@@ -306,7 +308,10 @@ vt_status vt_overlay_current(vt_tracker* t, uint8_t* frame, size_t len, const vt
         set_error("vt_overlay_current needs the whole frame on the device: create the handle with upload_window = 0");
         return VT_ERR_INVALID;
     }
-    return overlay_impl(t, frame, len, cmds, n, false);
+    // The device copy must BE the frame most recently given to update()/submit(): after a device-resident frame (tracked in place in
+    // the caller's memory), a conversion or an explicit vt_overlay() it is something else — upload `frame` instead of drawing on a
+    // stale image (the caller's frame is the same picture by contract).
+    return overlay_impl(t, frame, len, cmds, n, t ? !t->d_frame_is_last_host_frame : false);
 }
 
 // ---- timing --------------------------------------------------------------------------------------

@@ -156,6 +156,8 @@ void vt_config_default(vt_config* c) {
     c->use_cuda_graph = 1;
     c->box_overlay = 0;
     c->overlay_gate = 0.25f;  // src/tracker_context.rs:93,122
+    // App. A.7 switches: all zero = the OpenCV 4.13 behaviour with the intended normalisation
+    for (int k = 0; k < 3; ++k) c->norm_scale[k] = 1.f, c->norm_bias[k] = 0.f;  // (only read with norm_custom = 1)
 }
 
 vt_status vt_weights_probe(const char* path, int32_t shape_out[5]) {
@@ -213,14 +215,45 @@ void vt_tracker_destroy(vt_tracker* t) {
     delete t;
 }
 
-vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
-    if (!cfg || !out || !cfg->weights_path || cfg->width <= 0 || cfg->height <= 0 || cfg->max_targets <= 0 || cfg->max_targets > 64 ||
+}  // extern "C"
+
+namespace vt {
+// The caller's struct may be older (smaller) than the library's: copy what it has over the defaults.
+vt_status resolve_config(const vt_config* in, vt_config* out) {
+    constexpr size_t kMin = offsetof(vt_config, max_targets) + sizeof(int32_t);
+    if (!in || !out || in->struct_size < kMin || in->struct_size > sizeof(vt_config)) {
+        set_error("vt_config: struct_size %u is not a size this library knows (%zu..%zu): call vt_config_default() first", in ? in->struct_size : 0u,
+                  kMin, sizeof(vt_config));
+        return VT_ERR_INVALID;
+    }
+    vt_config_default(out);
+    memcpy(out, in, in->struct_size);
+    out->struct_size = (uint32_t)sizeof(vt_config);
+    return VT_OK;
+}
+}  // namespace vt
+
+extern "C" {
+
+vt_status vt_tracker_create(const vt_config* cfg_in, vt_tracker** out) {
+    vt_config cfg_full;
+    if (!out) return VT_ERR_INVALID;
+    {
+        const vt_status rs = resolve_config(cfg_in, &cfg_full);
+        if (rs != VT_OK) return rs;
+    }
+    const vt_config* cfg = &cfg_full;
+    if (!cfg->weights_path || cfg->width <= 0 || cfg->height <= 0 || cfg->max_targets <= 0 || cfg->max_targets > 64 ||
         (cfg->format != VT_FMT_NV12 && cfg->format != VT_FMT_RGB24 && cfg->format != VT_FMT_GRAY8)) {
         set_error("vt_tracker_create: invalid configuration");
         return VT_ERR_INVALID;
     }
     if (cfg->gemm_mode < VT_GEMM_FP32_SIMT || cfg->gemm_mode > VT_GEMM_TCGEN05_FP16) {
         set_error("vt_tracker_create: unknown gemm_mode %d", cfg->gemm_mode);
+        return VT_ERR_INVALID;
+    }
+    if ((cfg->pad_plus1 | cfg->decode_window | cfg->window | cfg->norm_custom) & ~1) {
+        set_error("vt_tracker_create: pad_plus1 / decode_window / window / norm_custom are 0 or 1 (SURVEY.md App. A.7)");
         return VT_ERR_INVALID;
     }
     *out = nullptr;
@@ -263,14 +296,16 @@ vt_status vt_tracker_create(const vt_config* cfg, vt_tracker** out) {
         const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};
         float lut[768];
         for (int c = 0; c < 3; ++c)
-            for (int v = 0; v < 256; ++v) lut[c * 256 + v] = (float)(((double)v / 255.0 - mean[c]) / stdv[c]);
+            for (int v = 0; v < 256; ++v)
+                lut[c * 256 + v] = cfg->norm_custom ? (float)((double)v * (double)cfg->norm_scale[c] + (double)cfg->norm_bias[c])  // App. A.7
+                                                    : (float)(((double)v / 255.0 - mean[c]) / stdv[c]);
         VT_TRY(cudaMalloc(&t->d_lut, sizeof(lut)));
         VT_TRY(cudaMemcpy(t->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
         // A.5 hann window, fp32 exactly as OpenCV builds it
         float h1[16], hann[256];
         for (int i = 0; i < 16; ++i) h1[i] = 0.5f * (1.f - cosf((float)(2 * M_PI / 17) * (float)(i + 1)));
         for (int y = 0; y < 16; ++y)
-            for (int x = 0; x < 16; ++x) hann[y * 16 + x] = h1[y] * h1[x];
+            for (int x = 0; x < 16; ++x) hann[y * 16 + x] = cfg->window == VT_WINDOW_ONE_MINUS_HANN ? 1.f - h1[y] * h1[x] : h1[y] * h1[x];
         VT_TRY(cudaMalloc(&t->d_hann, sizeof(hann)));
         VT_TRY(cudaMemcpy(t->d_hann, hann, sizeof(hann), cudaMemcpyHostToDevice));
     }

@@ -47,7 +47,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     const int D = t->D, Hd = t->hidden, C = t->head_ch;
     (void)record_events, (void)capturing;  // stage times come from device stamps (ST_*), not from event nodes
     cudaStream_t s = t->stream;
-    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid, t->d_frame_slot};
+    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid, t->d_frame_slot, t->cfg.pad_plus1};
     auto LO = [&](__nv_bfloat16* p) { return t->f16 ? nullptr : p; };  // fp16 mode: "hi only" (see vt_internal.h: operand_bits)
     VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, n, 4, kSearch, t->d_lut, t->patches_x, (size_t)kNTx * kPatchK, t->px_hi,
                                       LO(t->px_lo), s, t->d_stamps + ST_PRE));
@@ -168,9 +168,11 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     }
     if (t->nsplit && t->split_k)
         VT_LAUNCH(launch_head_decode(t->Phead, 9, (int64_t)t->maxT * kNTx * C, C, t->h1_b, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n,
-                                     t->threshold, t->d_res, t->d_maps, t->d_cand, t->d_counters, t->d_stamps, s, t->pdl && !t->debug_capture));
+                                     t->threshold, t->d_res, t->d_maps, t->d_cand, t->d_counters, t->d_stamps, s, t->pdl && !t->debug_capture,
+                                     t->cfg.decode_window, t->d_tc_err));
     else
-        VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, t->d_stamps, s));
+        VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, t->d_stamps, s,
+                                t->cfg.decode_window));
     if (t->cfg.box_overlay)
         VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, overlay_format(t->fmt), t->d_res, t->d_slots, n, t->cfg.overlay_gate,
                                      t->d_host_slot, t->d_stamps + ST_OVL_END, s, (uint8_t* const*)t->d_frame_slot, t->pdl && !t->debug_capture,
@@ -275,9 +277,11 @@ vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, bool all
                 }
             }
             if (!device_src) t->h2d_bytes += bytes;
+            t->d_frame_is_last_host_frame = false;  // only the search windows are on the device
             return VT_OK;
         }
     }
+    t->d_frame_is_last_host_frame = !device_src && n >= t->frame_bytes;
     if (!device_src) t->h2d_bytes += n;
     if (pinned) {
         VT_CUDA(cudaMemcpyAsync(t->d_frame, frame, n, kind, stream));
@@ -430,6 +434,7 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     ++t->kernel_launches;
     if (in_place) {
         t->frame_valid = 1;
+        t->d_frame_is_last_host_frame = false;  // tracked in the caller's device memory: the internal buffer holds an older frame
     } else if (d_src) {  // short device frame: device->device copy of what there is (NV12: black frame, src/nv12_convert.rs:48-50)
         vt_status st = upload_frame(t, d_src, len, false, true);
         if (st != VT_OK) return st;
@@ -524,7 +529,8 @@ vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, s
         }
         const int c = (int)ceil(sqrt((double)((long long)box.width * box.height)) * 2.0);
         const int x1 = box.x + (box.width - c) / 2, y1 = box.y + (box.height - c) / 2;
-        const int pl = std::max(0, -x1), pt = std::max(0, -y1), pr = std::max(x1 + c - t->W, 0), pb = std::max(y1 + c - t->H, 0);
+        const int pp = t->cfg.pad_plus1;
+        const int pl = std::max(0, -x1), pt = std::max(0, -y1), pr = std::max(x1 + c - t->W + pp, 0), pb = std::max(y1 + c - t->H + pp, 0);
         if (c - pl - pr <= 0 || c - pt - pb <= 0) {
             set_error("vt_tracker_init: template window lies outside the frame");
             return VT_ERR_CROP_OUTSIDE;
@@ -539,7 +545,7 @@ vt_status vt_tracker_init(vt_tracker* t, int32_t target, const uint8_t* frame, s
     VT_CUDA(cudaMemcpyAsync(t->d_state + target, &hs, sizeof(hs), cudaMemcpyHostToDevice, t->stream));
     // d_slots is reused as a one-element list for the template pass, then restored
     VT_CUDA(cudaMemcpyAsync(t->d_slots, &slot, sizeof(slot), cudaMemcpyHostToDevice, t->stream));
-    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid, nullptr};
+    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid, nullptr, t->cfg.pad_plus1};
     int launches = 0;
     VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, 1, 2, kTemplate, t->d_lut, t->patches_z, (size_t)kNTz * kPatchK, t->pz_hi,
                                       t->f16 ? nullptr : t->pz_lo, t->stream));

@@ -89,6 +89,10 @@ struct vt_tracker {
     uint8_t* h_stage = nullptr;  // pinned staging for non-pinned callers
     size_t h_stage_bytes = 0;
     int frame_valid = 1;
+    // what the device frame buffer t->d_frame holds: the whole host frame most recently given to update()/submit()/init() (what
+    // vt_overlay_current draws on), or something else (search windows only, a convert / overlay scratch upload, nothing: the last frame
+    // was tracked in place in the caller's device memory)
+    bool d_frame_is_last_host_frame = false;
     TargetState* d_state = nullptr;
     int32_t* d_slots = nullptr;
     // one device block [DeviceResult x maxT][u64 stamps x ST_COUNT][int tc_err, pad] written into the pinned host block of the frame's queue slot by the frame's last kernel

@@ -434,6 +434,9 @@ cudaError_t launch_attention(const float* qkv, float* out, __nv_bfloat16* out_hi
     return cudaGetLastError();
 }
 
+__device__ void decode_finish(TargetState* st, int slot, float threshold, float score, int best, float ox, float oy, float bw, float bh,
+                              DeviceResult* res, int decode_window, const int* tc_err);
+
 // ------------------------------------------------------------------------------------------------
 // K8 decode: 1x1 conv -> sigmoid -> hann window -> first-maximum argmax -> bbox (App. A.5-A.6).
 // One CTA (256 threads = 256 map cells) per target; the winning cell is found with a
@@ -443,7 +446,8 @@ cudaError_t launch_attention(const float* qkv, float* out, __nv_bfloat16* out_hi
 __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ h1, int C, const float* __restrict__ w2,
                                                      const float* __restrict__ b2, const float* __restrict__ hann,
                                                      TargetState* __restrict__ state, const int32_t* __restrict__ slots, float threshold,
-                                                     DeviceResult* __restrict__ res, float* __restrict__ maps, unsigned long long* stamps) {
+                                                     DeviceResult* __restrict__ res, float* __restrict__ maps, unsigned long long* stamps,
+                                                     int decode_window) {
     if (stamps && threadIdx.x == 0 && blockIdx.x == 0) stamps[ST_DEC] = device_time_ns();
     __shared__ float s_val[8];
     __shared__ int s_idx[8];
@@ -500,41 +504,17 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ h
     if (p == best) s_out[0] = o[3], s_out[1] = o[4], s_out[2] = sw, s_out[3] = sh;
     __syncthreads();
     if (p == 0) {
-        TargetState* st = state + slot;
-        DeviceResult r;
-        r.success = 0, r.score = 0.f, r.bbox[0] = r.bbox[1] = r.bbox[2] = r.bbox[3] = 0, r.best = best;
-        r.status = VT_OK;
-        if (!st->active) {
-            r.status = VT_ERR_NOT_INIT;
-        } else if (st->crop_err) {
-            r.status = VT_ERR_CROP_OUTSIDE;
-        } else {
-            r.score = s_val[0];
-            if (r.score >= threshold) {
-                const int my = best / kMap, mx = best % kMap;
-                const float cx = __fdiv_rn(__fadd_rn((float)mx, s_out[0]), 16.f);
-                const float cy = __fdiv_rn(__fadd_rn((float)my, s_out[1]), 16.f);
-                const float bw = s_out[2], bh = s_out[3];
-                const int lx = st->rect[0], ly = st->rect[1], lw = st->rect[2], lh = st->rect[3];
-                const int cwin = (int)ceil(__dmul_rn(sqrt((double)((long long)lw * lh)), 4.0));
-                const int x0 = lx + (lw - cwin) / 2, y0 = ly + (lh - cwin) / 2;
-                const float fc = (float)cwin;
-                r.bbox[0] = (int)floorf(__fadd_rn(__fmul_rn(__fsub_rn(cx, __fdiv_rn(bw, 2.f)), fc), (float)x0));
-                r.bbox[1] = (int)floorf(__fadd_rn(__fmul_rn(__fsub_rn(cy, __fdiv_rn(bh, 2.f)), fc), (float)y0));
-                r.bbox[2] = (int)floorf(__fmul_rn(bw, fc));
-                r.bbox[3] = (int)floorf(__fmul_rn(bh, fc));
-                r.success = 1;
-                st->rect[0] = r.bbox[0], st->rect[1] = r.bbox[1], st->rect[2] = r.bbox[2], st->rect[3] = r.bbox[3];
-            }
-        }
-        res[slot] = r;
+        decode_finish(state + slot, slot, threshold, s_val[0], best, s_out[0], s_out[1], s_out[2], s_out[3], res, decode_window, nullptr);
         if (stamps && blockIdx.x == 0) stamps[ST_DEC_END] = device_time_ns();
     }
 }
 
-// rect_last update + result record from the winning cell (App. A.6); shared by both decode kernels
+// rect_last update + result record from the winning cell (App. A.6); shared by both decode kernels.
+// decode_window (App. A.7): 0 = the crop's own c = ceil(sqrt(w*h)*4) (OpenCV 4.13), 1 = 4*floor(sqrt(w*h)) (older OpenCV).
+// tc_err: the tensor-core kernels' error flag of this frame — an expired pipeline wait means the maps are garbage: the frame is reported
+// as failed by wait() and rect_last must keep the last good box.
 __device__ void decode_finish(TargetState* st, int slot, float threshold, float score, int best, float ox, float oy, float bw, float bh,
-                              DeviceResult* res) {
+                              DeviceResult* res, int decode_window, const int* tc_err) {
     DeviceResult r;
     r.success = 0, r.score = 0.f, r.bbox[0] = r.bbox[1] = r.bbox[2] = r.bbox[3] = 0, r.best = best;
     r.status = VT_OK;
@@ -549,7 +529,8 @@ __device__ void decode_finish(TargetState* st, int slot, float threshold, float 
             const float cx = __fdiv_rn(__fadd_rn((float)mx, ox), 16.f);
             const float cy = __fdiv_rn(__fadd_rn((float)my, oy), 16.f);
             const int lx = st->rect[0], ly = st->rect[1], lw = st->rect[2], lh = st->rect[3];
-            const int cwin = (int)ceil(__dmul_rn(sqrt((double)((long long)lw * lh)), 4.0));
+            const double sq = sqrt((double)((long long)lw * lh));
+            const int cwin = decode_window ? 4 * (int)floor(sq) : (int)ceil(__dmul_rn(sq, 4.0));
             const int x0 = lx + (lw - cwin) / 2, y0 = ly + (lh - cwin) / 2;
             const float fc = (float)cwin;
             r.bbox[0] = (int)floorf(__fadd_rn(__fmul_rn(__fsub_rn(cx, __fdiv_rn(bw, 2.f)), fc), (float)x0));
@@ -557,7 +538,8 @@ __device__ void decode_finish(TargetState* st, int slot, float threshold, float 
             r.bbox[2] = (int)floorf(__fmul_rn(bw, fc));
             r.bbox[3] = (int)floorf(__fmul_rn(bh, fc));
             r.success = 1;
-            st->rect[0] = r.bbox[0], st->rect[1] = r.bbox[1], st->rect[2] = r.bbox[2], st->rect[3] = r.bbox[3];
+            if (!(tc_err && *reinterpret_cast<const volatile int*>(tc_err)))
+                st->rect[0] = r.bbox[0], st->rect[1] = r.bbox[1], st->rect[2] = r.bbox[2], st->rect[3] = r.bbox[3];
         }
     }
     res[slot] = r;
@@ -579,7 +561,8 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restric
                                                           const float* __restrict__ w2, const float* __restrict__ b2,
                                                           const float* __restrict__ hann, TargetState* __restrict__ state,
                                                           const int32_t* __restrict__ slots, float threshold, DeviceResult* __restrict__ res,
-                                                          float* __restrict__ maps, float* cand, unsigned* counters, unsigned long long* stamps) {
+                                                          float* __restrict__ maps, float* cand, unsigned* counters, unsigned long long* stamps,
+                                                          int decode_window, const int* tc_err) {
     constexpr int C = CPL * 32;
     __shared__ float s_c[16][6];
     __shared__ int s_last;
@@ -689,7 +672,7 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restric
         const float f1 = __shfl_sync(0xffffffffu, c0.y, by), f2 = __shfl_sync(0xffffffffu, c0.z, by), f3 = __shfl_sync(0xffffffffu, c0.w, by);
         const float f4 = __shfl_sync(0xffffffffu, c1.x, by), f5 = __shfl_sync(0xffffffffu, c1.y, by);
         if (lane == 0) {
-            decode_finish(state + slot, slot, threshold, bv, (int)f1, f2, f3, f4, f5, res);
+            decode_finish(state + slot, slot, threshold, bv, (int)f1, f2, f3, f4, f5, res, decode_window, tc_err);
             counters[bi] = 0;  // ready for the next frame
             if (stamps && bi == gridDim.y - 1) stamps[ST_DEC_END] = device_time_ns();
         }
@@ -698,25 +681,26 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restric
 
 cudaError_t launch_head_decode(const float* P, int np, int64_t p_stride, int head_ch, const float* b1, const float* w2, const float* b2,
                                const float* hann, TargetState* d_state, const int32_t* d_slots, int n, float threshold, DeviceResult* d_res,
-                               float* d_maps, float* d_cand, unsigned* d_counters, unsigned long long* stamps, cudaStream_t s, bool pdl) {
+                               float* d_maps, float* d_cand, unsigned* d_counters, unsigned long long* stamps, cudaStream_t s, bool pdl,
+                               int decode_window, const int* tc_err) {
     if (n <= 0) return cudaSuccess;
     const dim3 grid(kMap, n), block(256);
     if (head_ch == 128 && np == 9)
-        return launch_ex(head_decode_kernel<4, 9>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
+        return launch_ex(head_decode_kernel<4, 9>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps, decode_window, tc_err);
     if (head_ch == 64 && np == 9)
-        return launch_ex(head_decode_kernel<2, 9>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
+        return launch_ex(head_decode_kernel<2, 9>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps, decode_window, tc_err);
     if (head_ch == 128)
-        return launch_ex(head_decode_kernel<4, 0>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
+        return launch_ex(head_decode_kernel<4, 0>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps, decode_window, tc_err);
     if (head_ch == 64)
-        return launch_ex(head_decode_kernel<2, 0>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps);
+        return launch_ex(head_decode_kernel<2, 0>, grid, block, 0, s, pdl, 1, P, np, p_stride, b1, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, d_cand, d_counters, stamps, decode_window, tc_err);
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_decode(const float* h1, int head_ch, const float* w2, const float* b2, const float* hann, TargetState* d_state,
                           const int32_t* d_slots, int n, float threshold, DeviceResult* d_res, float* d_maps, unsigned long long* stamps,
-                          cudaStream_t s) {
+                          cudaStream_t s, int decode_window) {
     if (n <= 0) return cudaSuccess;
-    decode_kernel<<<n, 256, 0, s>>>(h1, head_ch, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, stamps);
+    decode_kernel<<<n, 256, 0, s>>>(h1, head_ch, w2, b2, hann, d_state, d_slots, threshold, d_res, d_maps, stamps, decode_window);
     return cudaGetLastError();
 }
 

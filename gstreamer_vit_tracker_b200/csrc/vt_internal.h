@@ -25,6 +25,8 @@ constexpr int kWindow = 120;    // TimingStats window (src/timing_stats.rs:19)
 constexpr int kMaxCmds = 32;
 
 void set_error(const char* fmt, ...);
+// caller's vt_config (any struct_size the ABI ever had) -> the library's full struct with defaults for what the caller's header lacks
+vt_status resolve_config(const vt_config* in, vt_config* out);
 
 // GRAY8 frames are a bare luma plane: drawn on with the NV12 (Y plane) overlay semantics
 inline int overlay_format(int fmt) { return fmt == VT_FMT_GRAY8 ? VT_FMT_NV12 : fmt; }
@@ -131,6 +133,7 @@ struct FrameDesc {
     // while vt_tracker_update_device tracks straight out of the caller's device frame (no device->device copy) by letting the
     // per-frame stamp kernel store the caller's pointer here.
     const uint8_t* const* data_slot;
+    int32_t pad_plus1;     // App. A.7: 1 = the crop treats the last column / row of the frame as padding (older OpenCV: padR = x2-W+1)
 };
 
 cudaError_t launch_nv12_to_rgb(const uint8_t* d_nv12, size_t stride_in, uint8_t* d_rgb, size_t stride_out, int width, int height,
@@ -219,14 +222,15 @@ cudaError_t launch_reduce_ln(const ReduceLnArgs& a, cudaStream_t s, bool pdl);
 // 16 CTAs per target (one map row each); the last one to finish merges the 16 row candidates and updates rect_last.
 cudaError_t launch_head_decode(const float* P, int np, int64_t p_stride, int head_ch, const float* b1, const float* w2, const float* b2,
                                const float* hann, TargetState* d_state, const int32_t* d_slots, int n, float threshold, DeviceResult* d_res,
-                               float* d_maps, float* d_cand, unsigned* d_counters, unsigned long long* stamps, cudaStream_t s, bool pdl);
+                               float* d_maps, float* d_cand, unsigned* d_counters, unsigned long long* stamps, cudaStream_t s, bool pdl,
+                               int decode_window = 0, const int* tc_err = nullptr);
 // qkv: [B*320, 3D]; out: [B*320, D] fp32 (nullable) and/or bf16 split (nullable)
 cudaError_t launch_attention(const float* qkv, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int B, int D, int heads,
                              cudaStream_t s);
 // head 1x1 conv + sigmoid + hann + argmax + bbox decode, one CTA per target
 cudaError_t launch_decode(const float* h1, int head_ch, const float* w2, const float* b2, const float* hann, TargetState* d_state,
                           const int32_t* d_slots, int n, float threshold, DeviceResult* d_res, float* d_maps, unsigned long long* stamps,
-                          cudaStream_t s);
+                          cudaStream_t s, int decode_window = 0);
 
 // ---- tensor-core GEMM (gemm_tc.cu) ------------------------------------------------------------------
 struct TcOut {                // dense output [planes][batch][heads][rows][cols] the epilogue copies staged tiles into

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 1
+#define VT_ABI_VERSION 2   /* 2: vt_config grew the SURVEY.md App. A.7 variant switches (struct_size keeps v1 callers working) */
 
 typedef int32_t vt_status;
 enum {
@@ -50,6 +50,10 @@ typedef enum { VT_FMT_NV12 = 0, VT_FMT_RGB24 = 1, VT_FMT_GRAY8 = 2 } vt_format;
 /* BF16X3 (default): bf16 hi + lo operands, three products per K-step, scores within ~1e-5 of the fp32 oracle.  BF16 / FP16: single-pass
  * operands, 17 % faster, score error ~1e-3 / ~3e-4 — opt-in (near-tie arg-max flips are possible at that error). */
 typedef enum { VT_GEMM_FP32_SIMT = 0, VT_GEMM_TCGEN05_BF16X3 = 1, VT_GEMM_TCGEN05_BF16 = 2, VT_GEMM_TCGEN05_FP16 = 3 } vt_gemm_mode;
+/* the `vit_tracker` crate (src absent: Cargo.toml:24) wraps OpenCV's TrackerVit through opencv 0.98.1
+ * (Cargo.lock:700-716) and may follow an older upstream than the 4.13 behaviour the defaults restate. */
+typedef enum { VT_DECODE_CEIL4 = 0 /* cw = ceil(sqrt(w*h)*4), the crop's own c (4.13) */, VT_DECODE_4FLOOR = 1 /* cw = 4*floor(sqrt(w*h)) (older) */ } vt_decode_window;
+typedef enum { VT_WINDOW_HANN = 0 /* conf * hann (4.13) */, VT_WINDOW_ONE_MINUS_HANN = 1 /* conf * (1 - hann) (older) */ } vt_window;
 
 /* ≙ vit_tracker::BBox {x, y, width, height: i32} (uses: src/selection_state.rs:44, src/pipeline.rs:166) */
 typedef struct { int32_t x, y, width, height; } vt_bbox;
@@ -66,7 +70,8 @@ typedef struct {
 
 /* Hard-coded constants of the reference become fields (SURVEY.md §5 "config / flags"). */
 typedef struct {
-    uint32_t struct_size;        /* sizeof(vt_config), for ABI evolution */
+    uint32_t struct_size;        /* sizeof(vt_config) of the caller's header: fields beyond it take their defaults (ABI evolution);
+                                    0 or larger than the library's own sizeof is VT_ERR_INVALID */
     const char* weights_path;    /* ≙ MODEL_PATH, src/pipeline.rs:11 (flat "VTW1" file instead of .rknn) */
     int32_t device;              /* CUDA device ordinal */
     int32_t format;              /* vt_format of the frames handed to init/update */
@@ -82,7 +87,15 @@ typedef struct {
     int32_t upload_window;       /* 1: update()/submit() upload only the search windows of the active targets (2-D copies out of a
                                        pinned frame; rect_last is mirrored on the host) instead of the whole frame.  The device copy
                                        of the frame is then partial: vt_overlay_current needs upload_window = 0. */
-    int32_t reserved[6];
+    /* --- since VT_ABI_VERSION 2: variant switches of VitTrack's pre/post-processing; all-zero = OpenCV 4.13 --- */
+    int32_t pad_plus1;           /* crop padding: 0 padR = max(x2-W, 0) (4.13); 1 padR = max(x2-W+1, 0), likewise at the bottom (older) */
+    int32_t decode_window;       /* vt_decode_window */
+    int32_t window;              /* vt_window */
+    int32_t norm_custom;         /* 0: blob = (u8/255 - mean_c)/std_c, ImageNet mean/std on the channels in memory order (App. A.4);
+                                    1: blob = u8*norm_scale[c] + norm_bias[c] — any per-channel affine map: the cv2 Scalar-division quirk
+                                       (SURVEY.md §8c), or scale 1 / bias 0 when the NPU model normalises internally */
+    float norm_scale[3], norm_bias[3];
+    int32_t reserved[4];
 } vt_config;
 
 typedef struct vt_tracker vt_tracker;
@@ -212,7 +225,9 @@ typedef struct {
 /* Applies cmds in order to a host frame (upload, draw on device, copy the touched rows back). */
 vt_status vt_overlay(vt_tracker* t, uint8_t* frame, size_t len, const vt_overlay_cmd* cmds, int32_t n);
 /* Same, on the device-resident copy of the frame most recently given to update()/submit(); only the
- * touched rows travel back into `frame`.  This is what the probe shim uses. */
+ * touched rows travel back into `frame`.  This is what the probe shim uses for pageable frames.  When the device copy is not that
+ * frame (the last frame was device-resident and tracked in place, or a conversion / vt_overlay() reused the buffer) `frame` is
+ * uploaded first, as vt_overlay() does. */
 vt_status vt_overlay_current(vt_tracker* t, uint8_t* frame, size_t len, const vt_overlay_cmd* cmds, int32_t n);
 
 /* ------------------------------------------------------------------------------------------- */

@@ -35,6 +35,12 @@ class Result(C.Structure):
     _fields_ = [("success", C.c_int32), ("score", C.c_float), ("bbox", BBox)]
 
 
+class Variant(C.Structure):
+    """SURVEY.md App. A.7 switches (vto_variant)."""
+    _fields_ = [("pad_plus1", C.c_int32), ("decode_window", C.c_int32), ("window", C.c_int32), ("norm_custom", C.c_int32),
+                ("scale", C.c_float * 3), ("bias", C.c_float * 3)]
+
+
 _u8p = C.POINTER(C.c_uint8)
 _f32p = C.POINTER(C.c_float)
 _lib: Optional[C.CDLL] = None
@@ -76,6 +82,7 @@ def lib() -> C.CDLL:
         L.vto_tracker_new.restype = C.c_void_p
         L.vto_tracker_free.argtypes = [C.c_void_p]
         L.vto_tracker_set_threshold.argtypes = [C.c_void_p, C.c_float]
+        L.vto_tracker_set_variant.argtypes = [C.c_void_p, C.POINTER(Variant)]
         L.vto_tracker_init.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, BBox]
         L.vto_tracker_init.restype = C.c_int
         L.vto_tracker_update.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.POINTER(Result)]
@@ -241,6 +248,14 @@ class VitTrack:
 
     def set_threshold(self, s: float):
         lib().vto_tracker_set_threshold(self._h, s)
+
+    def set_variant(self, pad_plus1: bool = False, decode_window: int = 0, window: int = 0, norm=None):
+        """App. A.7 switches; norm = (scale[3], bias[3]) -> blob = u8*scale[c] + bias[c]."""
+        v = Variant(int(pad_plus1), int(decode_window), int(window), int(norm is not None))
+        if norm is not None:
+            for k in range(3):
+                v.scale[k], v.bias[k] = float(norm[0][k]), float(norm[1][k])
+        lib().vto_tracker_set_variant(self._h, C.byref(v))
 
     def init(self, rgb: np.ndarray, box) -> int:
         h, w, _ = rgb.shape

@@ -399,6 +399,7 @@ struct vto_tracker {
     const float *patch_w, *patch_b, *pos_z, *pos_x, *lnf_g, *lnf_b, *h1_w, *h1_b, *h2_w, *h2_b;
     blk_t* blk;
     float threshold;
+    vto_variant var; /* App. A.7 switches */
     vto_bbox rect_last;
     float norm_lut[3][256];
     float hann[256];
@@ -484,6 +485,18 @@ void vto_tracker_free(vto_tracker* t) {
     free(t);
 }
 void vto_tracker_set_threshold(vto_tracker* t, float s) { t->threshold = s; }
+/* App. A.7: rebuilds the normalisation LUT and the window table for the chosen variant */
+void vto_tracker_set_variant(vto_tracker* t, const vto_variant* v) {
+    t->var = *v;
+    for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < 256; ++i)
+            t->norm_lut[c][i] = v->norm_custom ? (float)((double)i * (double)v->scale[c] + (double)v->bias[c])
+                                               : (float)(((double)i / 255.0 - MEANV[c]) / STDV[c]);
+    float h1[16];
+    for (int i = 0; i < 16; ++i) h1[i] = 0.5f * (1.f - cosf((float)(2 * M_PI / 17) * (float)(i + 1)));
+    for (int y = 0; y < 16; ++y)
+        for (int x = 0; x < 16; ++x) t->hann[y * 16 + x] = v->window ? 1.f - h1[y] * h1[x] : h1[y] * h1[x];
+}
 void vto_tracker_get_rect(const vto_tracker* t, vto_bbox* o) { *o = t->rect_last; }
 void vto_tracker_set_rect(vto_tracker* t, vto_bbox b) { t->rect_last = b; }
 int vto_model_dim(const vto_tracker* t, int which) {
@@ -501,14 +514,20 @@ static int crop_size(vto_bbox b, int factor) { return (int)ceil(sqrt((double)(b.
 
 /* A.1 crop with zero border.  Returns 0, or -1 when the crop lies entirely outside the frame
  * (cv2 throws an ROI assertion there).  out: c*c*3 */
+static int crop_square_v(const uint8_t* rgb, int W, int H, vto_bbox box, int factor, uint8_t* out, int* c_out, int pad_plus1);
 int vto_crop_square(const uint8_t* rgb, int W, int H, vto_bbox box, int factor, uint8_t* out, int* c_out) {
+    return crop_square_v(rgb, W, H, box, factor, out, c_out, 0);
+}
+/* pad_plus1 (App. A.7, older OpenCV): x2_pad = max(x2 - W + 1, 0), y2_pad likewise — a crop that reaches the right / bottom edge
+ * treats the last column / row of the frame as border */
+static int crop_square_v(const uint8_t* rgb, int W, int H, vto_bbox box, int factor, uint8_t* out, int* c_out, int pad_plus1) {
     const int c = crop_size(box, factor);
     if (c_out) *c_out = c;
     if (c <= 0) return -1;
     const int x1 = box.x + (box.width - c) / 2, y1 = box.y + (box.height - c) / 2; /* C truncating division */
     const int x2 = x1 + c, y2 = y1 + c;
     const int pl = x1 < 0 ? -x1 : 0, pt = y1 < 0 ? -y1 : 0;
-    const int pr = x2 - W > 0 ? x2 - W : 0, pb = y2 - H > 0 ? y2 - H : 0;
+    const int pr = x2 - W + pad_plus1 > 0 ? x2 - W + pad_plus1 : 0, pb = y2 - H + pad_plus1 > 0 ? y2 - H + pad_plus1 : 0;
     const int rw = c - pl - pr, rh = c - pt - pb;
     if (rw <= 0 || rh <= 0) return -1;
     if (!out) return 0;
@@ -730,10 +749,10 @@ void vto_net_debug_tokens(const vto_tracker* t, int which, float* out) {
 
 static int make_blob(vto_tracker* t, const uint8_t* rgb, int W, int H, vto_bbox box, int factor, int size, float* blob) {
     int c;
-    if (vto_crop_square(rgb, W, H, box, factor, NULL, &c) != 0) return -1;
+    if (crop_square_v(rgb, W, H, box, factor, NULL, &c, t->var.pad_plus1) != 0) return -1;
     uint8_t* crop = (uint8_t*)malloc((size_t)c * c * 3);
     uint8_t* rs = (uint8_t*)malloc((size_t)size * size * 3);
-    vto_crop_square(rgb, W, H, box, factor, crop, NULL);
+    crop_square_v(rgb, W, H, box, factor, crop, NULL, t->var.pad_plus1);
     vto_resize_linear_u8c3(crop, c, c, rs, size, size);
     normalize_with_lut(t->norm_lut, rs, size, blob);
     free(crop);
@@ -768,7 +787,8 @@ int vto_tracker_update(vto_tracker* t, const uint8_t* rgb, int W, int H, vto_res
         const float cy = ((float)my + t->off_map[256 + best]) / 16.f;
         const float bw = t->size_map[best], bh = t->size_map[256 + best];
         const vto_bbox L = t->rect_last;
-        const int cw = crop_size(L, 4);
+        /* A.6: the crop's own c; App. A.7 decode_window = 1: the older 4 * floor(sqrt(w*h)) */
+        const int cw = t->var.decode_window ? 4 * (int)floor(sqrt((double)(L.width * L.height))) : crop_size(L, 4);
         const int x0 = L.x + (L.width - cw) / 2, y0 = L.y + (L.height - cw) / 2;
         vto_bbox r;
         r.x = (int)floorf((cx - bw / 2.f) * (float)cw + (float)x0);

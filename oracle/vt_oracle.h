@@ -69,6 +69,13 @@ typedef struct vto_tracker vto_tracker;
 vto_tracker* vto_tracker_new(const char* weight_path, int threads);
 void vto_tracker_free(vto_tracker*);
 void vto_tracker_set_threshold(vto_tracker*, float score_threshold);
+/* SURVEY.md Appendix A.7 variant switches (all zero = OpenCV 4.13, the default):
+ *   pad_plus1      crop padding padR = max(x2-W+1, 0), padB likewise (older OpenCV) instead of max(x2-W, 0)
+ *   decode_window  1: cw = 4*floor(sqrt(w*h)) (older) instead of the crop's c = ceil(sqrt(w*h)*4)
+ *   window         1: conf * (1 - hann) (older) instead of conf * hann
+ *   norm_custom    1: blob = u8*scale[c] + bias[c] instead of (u8/255 - mean_c)/std_c */
+typedef struct { int32_t pad_plus1, decode_window, window, norm_custom; float scale[3], bias[3]; } vto_variant;
+void vto_tracker_set_variant(vto_tracker*, const vto_variant*);
 int vto_tracker_init(vto_tracker*, const uint8_t* rgb, int width, int height, vto_bbox box);
 /* returns 0 ok, <0 error (crop lies entirely outside the frame) */
 int vto_tracker_update(vto_tracker*, const uint8_t* rgb, int width, int height, vto_result* out);

@@ -23,7 +23,7 @@ def test_exports_every_declared_symbol(built):
         assert hasattr(L, n), f"{n} is declared in include/vt_tracker.h but not exported"
     # and the Python binding table covers the same set
     assert set(_lib.SYMBOLS) == set(names)
-    assert _lib.lib().vt_abi_version() == 1
+    assert _lib.lib().vt_abi_version() == 2
 
 
 def test_struct_layouts_match_header(built):
@@ -112,7 +112,7 @@ def test_header_is_plain_c_and_links(built, tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, str(src), "-L", libdir, "-lvittrack_b200",
                     f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True, capture_output=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert out[:4] == ["1", "1", "1920", "1"], out
+    assert out[:4] == ["2", "1", "1920", "1"], out
     if shutil.which("g++"):
         subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True,
                        capture_output=True)

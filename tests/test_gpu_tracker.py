@@ -56,7 +56,7 @@ def iou(a, b):
     return inter / union if union > 0 else 1.0
 
 
-def oracle_prefloor(ref, rect_before, cell=None):
+def oracle_prefloor(ref, rect_before, cell=None, decode_window=0):
     """Pre-floor bbox coordinates the oracle's last update gives for map cell `cell` (default: its own argmax), in the fp32
     arithmetic of App. A.6, and the hann-weighted top-1/top-2 margin."""
     cw, sm, om, _ = ref.last_maps()
@@ -67,14 +67,14 @@ def oracle_prefloor(ref, rect_before, cell=None):
     cy = (f(my) + om[256 + best]) / f(16)
     bw, bh = sm[best], sm[256 + best]
     x, y, w, h = rect_before
-    c = int(np.ceil(np.sqrt(float(w * h)) * 4))
+    c = 4 * int(np.floor(np.sqrt(float(w * h)))) if decode_window else int(np.ceil(np.sqrt(float(w * h)) * 4))  # App. A.7 / A.6
     x0, y0 = x + int((w - c) / 2), y + int((h - c) / 2)
     vals = [(cx - bw / f(2)) * f(c) + f(x0), (cy - bh / f(2)) * f(c) + f(y0), bw * f(c), bh * f(c)]
     srt = np.sort(cw)[::-1]
     return [float(v) for v in vals], float(srt[0] - srt[1])
 
 
-def compare_step(trk, r, ref, rect_before, stats, where, target=0, tie_margin=TIE_MARGIN):
+def compare_step(trk, r, ref, rect_before, stats, where, target=0, tie_margin=TIE_MARGIN, decode_window=0):
     """One step from the same rect_last: GPU result r (target `target` of handle trk) vs the oracle tracker `ref`, which has just
     run update() on the same frame.  Returns True when the step matched exactly."""
     cw = ref.last_maps()[0]
@@ -95,7 +95,7 @@ def compare_step(trk, r, ref, rect_before, stats, where, target=0, tie_margin=TI
     if not r.success:
         stats["exact"] += cell == best
         return cell == best
-    pre, _ = oracle_prefloor(ref, rect_before, cell)
+    pre, _ = oracle_prefloor(ref, rect_before, cell, decode_window)
     want = tuple(int(math.floor(v)) for v in pre)
     if tuple(r.bbox) == want:
         stats["exact"] += cell == best
@@ -820,6 +820,93 @@ def test_kernel_forms_agree(api, weight_dir, monkeypatch):
                 for a, b in zip(fa, fb):
                     assert a.success and a.status == 0 and a.bbox == b.bbox, (spec.name, env, a, b)
                     assert abs(a.score - b.score) < 1e-5, (spec.name, env, a, b)
+
+
+# ---- SURVEY.md App. A.7 variant switches ----------------------------------------------------------------------------------------
+def _quirk_norm():
+    g = golden("trackervit_variants.json")
+    return (g["norm_scale"], g["norm_bias"])
+
+
+@pytest.mark.parametrize("gemm_mode", [0, 1], ids=["fp32simt", "tcgen05x3"])
+@pytest.mark.parametrize("switch", ["pad_plus1", "decode_window", "window", "norm", "all"])
+def test_variant_switch_vs_oracle(api, oracle, weight_dir, switch, gemm_mode):
+    """One GPU-vs-oracle test per App. A.7 switch in vt_config (and all of them together): 12 teacher-forced frames of a target whose
+    search window overhangs the right and bottom frame edges (so pad_plus1 matters), blobs bit-exact, score within 1e-3, boxes equal."""
+    kw = {"pad_plus1": dict(pad_plus1=True), "decode_window": dict(decode_window=1), "window": dict(window=1), "norm": dict(norm=_quirk_norm()),
+          "all": dict(pad_plus1=True, decode_window=1, window=1, norm=_quirk_norm())}[switch]
+    W, H = 640, 360
+    spec = synth.StreamSpec("v", W, H, 77, [(560, 300, 80, 60, 2, 1)])
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir, variant="wild")
+    trk = api.VitTrack.new(wpath, W, H, gemm_mode=gemm_mode, **kw)
+    ref = oracle.VitTrack(wpath, threads=4)
+    ref.set_variant(**kw)
+    base = oracle.VitTrack(wpath, threads=4)   # default variant: the switch must actually change something
+    f0 = st.frame(0)
+    rgb0 = oracle.nv12_to_rgb(f0, W, H, 4)
+    box = st.target_boxes(0)[0]
+    trk.init(f0, api.BBox(*box))
+    ref.init(rgb0, box)
+    base.init(rgb0, box)
+    stats = new_stats()
+    changed = False
+    for n in range(12):
+        fr = st.frame(n)
+        rgb = oracle.nv12_to_rgb(fr, W, H, 4)
+        before = ref.rect
+        trk.set_rect(before)
+        base.rect = before
+        r = trk.update(fr)
+        assert ref.update(rgb)[0] == 0 and base.update(rgb)[0] == 0
+        sb, tb = ref.last_blobs()
+        d = trk.debug_read(0)
+        assert np.array_equal(d["search_blob"], sb) and np.array_equal(d["template_blob"], tb), (switch, n)
+        compare_step(trk, r, ref, before, stats, (switch, n), decode_window=kw.get("decode_window", 0))
+        changed |= (not np.array_equal(base.last_blobs()[0], sb)) or (not np.array_equal(base.last_maps()[0], ref.last_maps()[0])) or base.rect != ref.rect
+    assert changed, "the switch changed nothing on this sequence"
+    finish_stats(f"variant/{switch}/gemm{gemm_mode}", stats, 12)
+
+
+def test_custom_norm_vs_cv2_default_std_golden(api, weight_dir):
+    """vt_config.norm_custom against the third party: cv2.TrackerVit with its default stdvalue (Scalar-division quirk)."""
+    g = golden("trackervit_variants.json")
+    wpath = weights.ensure_weight_file(g["model"], weight_dir, variant=g["variant"])
+    assert hashlib.sha256(open(wpath, "rb").read()).hexdigest() == g["weights_sha256"]
+    for seq in g["sequences"]:
+        sp = seq["spec"]
+        spec = synth.StreamSpec(seq["name"], sp["w"], sp["h"], sp["seed"], [tuple(t) for t in sp["targets"]])
+        st = synth.SyntheticStream(spec)
+        trk = api.VitTrack.new(wpath, spec.width, spec.height, gemm_mode=1, norm=(g["norm_scale"], g["norm_bias"]))
+        trk.init(st.frame(0), api.BBox(*seq["init_box"]))
+        for i, fr in enumerate(seq["frames"]):
+            r = trk.update(st.frame(i))
+            assert abs(r.score - fr["score"]) <= SCORE_TOL and r.success == fr["ok"], (seq["name"], i, r, fr)
+            if fr["ok"] and list(r.bbox) != fr["bbox"]:
+                assert max(abs(a - b) for a, b in zip(r.bbox, fr["bbox"])) <= 1, (seq["name"], i, r.bbox, fr["bbox"])
+                trk.set_rect(fr["bbox"])
+
+
+def test_config_struct_size_evolution(api, weight_dir):
+    """vt_config.struct_size: a caller built against the v1 header (no App. A.7 fields) gets the defaults for what its struct lacks;
+    0 and oversized values are rejected."""
+    import ctypes as C
+    L = api.L
+    wpath = weights.ensure_weight_file("nano", weight_dir)
+    cfg = api.make_config(wpath, 640, 360, pad_plus1=True, window=1)   # v2 fields set ...
+    cfg.struct_size = L.vt_config.pad_plus1.offset                     # ... but the caller claims the v1 size: they must be ignored
+    h = C.c_void_p()
+    api.check(L.lib().vt_tracker_create(C.byref(cfg), C.byref(h)), "create v1-sized")
+    a = api.VitTrack(cfg, _handle=h)
+    b = api.VitTrack.new(wpath, 640, 360)
+    st = synth.SyntheticStream(synth.StreamSpec("v", 640, 360, 77, [(560, 300, 80, 60, 2, 1)]))
+    for t in (a, b):
+        t.init(st.frame(0), api.BBox(*st.target_boxes(0)[0]))
+    assert a.update(st.frame(1)) == b.update(st.frame(1))
+    for bad in (0, C.sizeof(L.vt_config) + 8, 12):
+        cfg.struct_size = bad
+        h2 = C.c_void_p()
+        assert L.lib().vt_tracker_create(C.byref(cfg), C.byref(h2)) == L.VT_ERR_INVALID and not h2.value
 
 
 def test_zz_parity_stats_recorded():

@@ -508,6 +508,46 @@ def gen_trackervit(model="nano"):
     json.dump(out, open(os.path.join(GOLD, f"trackervit_{model}.json"), "w"))
 
 
+def quirk_norm():
+    """cv2 4.13 TrackerVit with its DEFAULT stdvalue normalises with OpenCV's quaternion Scalar division: the blob is
+    (u8/255 - mean_c) * k_c with k = (s0, -s1, -s2) / (s0^2 + s1^2 + s2^2).  As the App. A.7 custom map blob = u8*scale_c + bias_c."""
+    s = np.array([0.229, 0.224, 0.225])
+    mean = np.array([0.485, 0.456, 0.406])
+    k = np.array([s[0], -s[1], -s[2]]) / np.sum(s ** 2)
+    return [float(v) for v in k / 255.0], [float(v) for v in -mean * k]
+
+
+def gen_trackervit_variants():
+    """trackervit_variants.json — the App. A.7 normalisation switch pinned against the third party: cv2.TrackerVit run with its default
+    (undoctored) stdvalue, i.e. with the Scalar-division quirk, must equal the tracker configured with norm = quirk_norm().  (The other
+    A.7 switches restate older OpenCV releases from recollection; no executable copy exists offline, they are checked GPU-vs-oracle only.)"""
+    import cv2
+    from torch_model import export_onnx
+    import tempfile
+
+    tmp = tempfile.mkdtemp()
+    wpath = weights.ensure_weight_file("nano", tmp, variant="wild")
+    onnx = os.path.join(tmp, "nano_wild.onnx")
+    export_onnx(wpath, onnx)
+    scale, bias = quirk_norm()
+    out = {"source": f"cv2.TrackerVit (OpenCV {cv2.__version__}) with default stdvalue (Scalar-division quirk)", "model": "nano", "variant": "wild",
+           "weights_sha256": hashlib.sha256(open(wpath, "rb").read()).hexdigest(), "norm_scale": scale, "norm_bias": bias, "sequences": []}
+    for name, spec, n in [("cfg1", synth.CONFIGS["cfg1"], 20), ("corner", synth.StreamSpec("corner", 640, 360, 31, [(2, 4, 90, 70, -3, -2)]), 15)]:
+        st = synth.SyntheticStream(spec)
+        prm = cv2.TrackerVit_Params()
+        prm.net, prm.tracking_score_threshold = onnx, 0.2
+        trk = cv2.TrackerVit_create(prm)
+        box = st.target_boxes(0)[0]
+        trk.init(py_nv12_frame_to_rgb(st.frame(0), spec.width, spec.height), box)
+        frames = []
+        for i in range(n):
+            ok, bb = trk.update(py_nv12_frame_to_rgb(st.frame(i), spec.width, spec.height))
+            frames.append({"ok": bool(ok), "bbox": [int(v) for v in bb], "score": float(trk.getTrackingScore())})
+        out["sequences"].append({"name": name, "spec": {"w": spec.width, "h": spec.height, "seed": spec.seed, "targets": [list(t) for t in spec.targets]},
+                                 "init_box": list(box), "frames": frames})
+    json.dump(out, open(os.path.join(GOLD, "trackervit_variants.json"), "w"))
+
+
 def gen_yuy2():
     """yuy2_golden.json — (a) known answers and sha256 of frames converted by a pure-Python evaluation of the reference's BT.601
     integer formulas (/root/reference/src/nv12_convert.rs:24-30,124-126,41-43) on packed 4:2:2 input (rows of round_up_4(2*w) bytes,
@@ -573,7 +613,7 @@ def gen_keymap():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["kat", "glyphs", "overlay", "state", "resize", "trackervit", "trackervit_tiny", "keymap", "yuy2"]
+    which = sys.argv[1:] or ["kat", "glyphs", "overlay", "state", "resize", "trackervit", "trackervit_tiny", "variants", "keymap", "yuy2"]
     if "keymap" in which: gen_keymap()
     if "yuy2" in which: gen_yuy2()
     font = gen_glyphs() if ("glyphs" in which or "overlay" in which) else None
@@ -583,5 +623,6 @@ if __name__ == "__main__":
     if "resize" in which: gen_resize()
     if "trackervit" in which: gen_trackervit("nano")
     if "trackervit_tiny" in which: gen_trackervit("tiny")
+    if "variants" in which: gen_trackervit_variants()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
