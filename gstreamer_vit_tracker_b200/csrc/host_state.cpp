@@ -99,11 +99,11 @@ vt_status vt_context_create(const vt_config* cfg, vt_context** out) {
     const vt_status rs = vt::resolve_config(cfg, &c);
     if (rs != VT_OK) return rs;
     c.max_targets = 1;   // one VitTrack per TrackerContext (src/tracker_context.rs:8)
-    c.box_overlay = 0;   // the probe issues explicit overlay commands
-    c.upload_window = 0; // ... on the device copy of the whole frame (vt_overlay_current)
+    c.box_overlay = 0;   // the probe queues explicit overlay commands (the box is one of them)
     vt_tracker* t = nullptr;
     vt_status st = vt_tracker_create(&c, &t);  // ≙ VitTrack::new(model_path)?, src/tracker_context.rs:21
     if (st != VT_OK) return st;
+    vt::tracker_enable_hud(t);  // the frame's last kernel runs the probe's HUD list (one synchronisation per probed frame)
     vt_context* ctx = new vt_context(c.width, c.height);
     ctx->tracker = t;
     ctx->cfg = c;
@@ -320,17 +320,75 @@ static vt_overlay_cmd make_cmd(int kind, int x, int y, int w, int h, int a, uint
     return c;
 }
 
-// ≙ the pad-probe closure body: src/pipeline.rs:67-184 (NV12) / src/pipeline_ir.rs:100-228 (RGB24)
-vt_status vt_probe_frame(vt_context* c, uint8_t* frame, size_t len, const char* const* hud_override) {
-    if (!c || !c->tracker || !frame) return VT_ERR_INVALID;
-    vt_tracker* t = c->tracker;
-    const bool nv12 = vt::format_is_luma(c->cfg.format);  // GRAY8 frames take the luma-plane HUD of src/pipeline.rs:125-174
-    // interval timing, src/pipeline.rs:69-79
-    const auto now = std::chrono::steady_clock::now();
-    if (c->have_last) vt_timing_add_interval(t, (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(now - c->last_time).count());
-    c->last_time = now, c->have_last = true;
-    const uint64_t num = c->frame_num++;
+// HUD strings of one probe invocation (src/pipeline.rs:126-156 / src/pipeline_ir.rs:168-190)
+struct HudText {
+    char fps[48], timing[48];
+};
+static void hud_text(vt_context* c, bool nv12, const char* const* hud_override, HudText& h) {
+    vt_timing tm;
+    vt_timing_get(c->tracker, &tm);
+    snprintf(h.fps, sizeof(h.fps), "FPS: %.0f", tm.fps);
+    if (nv12) snprintf(h.timing, sizeof(h.timing), "conv:%.1fms trk:%.1fms", tm.avg_conv_ms, tm.avg_track_ms);
+    else snprintf(h.timing, sizeof(h.timing), "trk:%.1fms", tm.avg_track_ms);
+    if (hud_override && hud_override[0]) snprintf(h.fps, sizeof(h.fps), "%s", hud_override[0]);
+    if (hud_override && hud_override[1]) snprintf(h.timing, sizeof(h.timing), "%s", hud_override[1]);
+}
 
+// The overlay of one probe invocation as a command list, draw order of the reference (src/pipeline.rs:125-174 /
+// src/pipeline_ir.rs:165-202: background, state, FPS, timing, score, cursor / selection, box + crosshair).
+// `state` = state_name() after process_frame; score / box as ctx.current_score / the box the reference would draw.
+// cond / from_result != 0 are used by the one-synchronisation path, where score and box come from the device-side result.
+static void hud_commands(const vt_context* c, bool nv12, int state, const HudText& h, bool draw_box, const vt_bbox& b, float score, uint8_t cond,
+                         bool from_result, std::vector<vt::HudCmd>& out) {
+    static const char* const names[4] = {"SELECT START", "SELECT END", "TRACKING", "LOST"};
+    const bool tracking = state == VT_STATE_TRACKING, selecting = state == VT_STATE_SELECT_START || state == VT_STATE_SELECT_END;
+    const int strict = nv12 ? 0 : 1;  // the RGB path looks glyphs up with get_glyph, which panics (src/drawing.rs:99)
+    auto push = [&](const vt_overlay_cmd& cmd, uint8_t cnd, uint8_t fr = vt::VT_HUD_GIVEN) { out.push_back(vt::HudCmd{cmd, cnd, fr}); };
+    char score_line[48];
+    snprintf(score_line, sizeof(score_line), "score: %.0f%%", score * 100.0f);
+    push(make_cmd(VT_OV_TEXT, 15, 15, 0, 0, 2, 255, 0, 0, names[state], strict), cond);
+    if (cond != vt::VT_HUD_IF_FAIL) {  // (the lines common to both outcomes are queued once, with the first variant)
+        push(make_cmd(VT_OV_TEXT, 15, 40, 0, 0, 2, 255, 0, 0, h.fps, strict), vt::VT_HUD_ALWAYS);
+        push(make_cmd(VT_OV_TEXT, 15, 65, 0, 0, 1, 200, 0, 0, h.timing, strict), vt::VT_HUD_ALWAYS);
+    }
+    if (tracking) {
+        if (from_result) push(make_cmd(VT_OV_TEXT, nv12 ? 250 : 200, 15, 0, 0, 2, 255, 0, 0, "score: ", strict), cond, vt::VT_HUD_SCORE_TEXT);
+        else push(make_cmd(VT_OV_TEXT, nv12 ? 250 : 200, 15, 0, 0, 2, 255, 0, 0, score_line, strict), cond);
+    }
+    const vt_selection sel{c->selection.cursor_x, c->selection.cursor_y, c->selection.start_x, c->selection.start_y, c->selection.phase, 0, 0};
+    if (selecting) {
+        // (the fail variant of a confirm frame shows the reset selection: cursor back in the centre, src/tracker_context.rs:100-109)
+        const bool reset = cond == vt::VT_HUD_IF_FAIL;
+        const int cx = reset ? c->frame_width / 2 : sel.cursor_x, cy = reset ? c->frame_height / 2 : sel.cursor_y;
+        if (nv12) push(make_cmd(VT_OV_CURSOR, cx, cy, 0, 0, 0, 255, 0, 0), cond);
+        else push(make_cmd(VT_OV_CURSOR, cx, cy, 0, 0, 0, 0, 255, 0), cond);
+        if (!reset && state == VT_STATE_SELECT_END) {
+            if (nv12) push(make_cmd(VT_OV_SELECTION, sel.start_x, sel.start_y, sel.cursor_x, sel.cursor_y, 0, 255, 0, 0), cond);
+            else push(make_cmd(VT_OV_SELECTION, sel.start_x, sel.start_y, sel.cursor_x, sel.cursor_y, 0, 255, 255, 0), cond);
+        }
+    }
+    if (draw_box) {
+        const uint8_t r = nv12 ? 255 : 0, g = nv12 ? 0 : 255;
+        push(make_cmd(VT_OV_RECT, b.x, b.y, b.width, b.height, 3, r, g, 0), cond, from_result ? vt::VT_HUD_RESULT_RECT : vt::VT_HUD_GIVEN);
+        push(make_cmd(VT_OV_CROSSHAIR, b.x + b.width / 2, b.y + b.height / 2, 0, 0, 15, r, g, 0), cond,
+             from_result ? vt::VT_HUD_RESULT_CROSS : vt::VT_HUD_GIVEN);
+    }
+}
+
+static void probe_log(vt_context* c, bool nv12, uint64_t num) {
+    const uint64_t every = nv12 ? 120 : 60;  // src/pipeline.rs:176 / src/pipeline_ir.rs:210
+    static const bool log_enabled = getenv("VT_PROBE_LOG") != nullptr;  // the reference prints unconditionally
+    if (log_enabled && num % every == 0 && num > 0) {
+        vt_timing tm;
+        vt_timing_get(c->tracker, &tm);
+        printf("\r[%s] FPS: %.0f | conv: %.1fms | track: %.1fms\r\n", vt_context_state_name(c), tm.fps, tm.avg_conv_ms, tm.avg_track_ms);
+    }
+}
+
+// Pageable frames: process_frame (one synchronisation), then the overlay as explicit commands on the device copy of the frame and a
+// copy of the touched rows back (a second synchronisation).
+static vt_status probe_two_step(vt_context* c, uint8_t* frame, size_t len, const char* const* hud_override, bool nv12) {
+    vt_tracker* t = c->tracker;
     // conversion + tracking, src/pipeline.rs:104-120.  The conversion is fused into the crop kernel, so
     // `conv` is the device-timed preprocess stage of this frame and `track` the wall time of process_frame.
     const auto t1 = std::chrono::steady_clock::now();
@@ -342,61 +400,86 @@ vt_status vt_probe_frame(vt_context* c, uint8_t* frame, size_t len, const char* 
     vt_timing tm;
     vt_timing_get(t, &tm);
     vt_timing_add_times(t, c->frame_on_device ? (uint64_t)(tm.preprocess_ms * 1000.f) : 0, track_us);
-    vt_timing_get(t, &tm);
-
-    const std::string state_name = vt_context_state_name(c);
-    char fps_line[48], time_line[48], score_line[48];
-    snprintf(fps_line, sizeof(fps_line), "FPS: %.0f", tm.fps);
-    if (nv12) snprintf(time_line, sizeof(time_line), "conv:%.1fms trk:%.1fms", tm.avg_conv_ms, tm.avg_track_ms);
-    else snprintf(time_line, sizeof(time_line), "trk:%.1fms", tm.avg_track_ms);
-    snprintf(score_line, sizeof(score_line), "score: %.0f%%", c->current_score * 100.0f);
-    const char* fps_s = hud_override && hud_override[0] ? hud_override[0] : fps_line;
-    const char* time_s = hud_override && hud_override[1] ? hud_override[1] : time_line;
-
+    HudText h;
+    hud_text(c, nv12, hud_override, h);
+    const int state = vt_context_state(c);
+    std::vector<vt::HudCmd> hud;
+    if (nv12) hud.push_back(vt::HudCmd{make_cmd(VT_OV_BACKGROUND, 10, 10, 400, 80, 150, 0, 0, 0), vt::VT_HUD_ALWAYS, vt::VT_HUD_GIVEN});
+    const bool draw_box = has || (state == VT_STATE_TRACKING && c->has_bbox);
+    hud_commands(c, nv12, state, h, draw_box, has ? bb : c->current_bbox, c->current_score, vt::VT_HUD_ALWAYS, false, hud);
     std::vector<vt_overlay_cmd> cmds;
-    const bool tracking = state_name == "TRACKING", selecting = state_name.rfind("SELECT", 0) == 0;
-    if (nv12) {  // src/pipeline.rs:125-174
-        cmds.push_back(make_cmd(VT_OV_BACKGROUND, 10, 10, 400, 80, 150, 0, 0, 0));
-        cmds.push_back(make_cmd(VT_OV_TEXT, 15, 15, 0, 0, 2, 255, 0, 0, state_name.c_str()));
-        cmds.push_back(make_cmd(VT_OV_TEXT, 15, 40, 0, 0, 2, 255, 0, 0, fps_s));
-        cmds.push_back(make_cmd(VT_OV_TEXT, 15, 65, 0, 0, 1, 200, 0, 0, time_s));
-        if (tracking) cmds.push_back(make_cmd(VT_OV_TEXT, 250, 15, 0, 0, 2, 255, 0, 0, score_line));
-        if (selecting) {
-            cmds.push_back(make_cmd(VT_OV_CURSOR, c->selection.cursor_x, c->selection.cursor_y, 0, 0, 0, 255, 0, 0));
-            if (c->selection.phase == 1)
-                cmds.push_back(make_cmd(VT_OV_SELECTION, c->selection.start_x, c->selection.start_y, c->selection.cursor_x, c->selection.cursor_y, 0, 255, 0, 0));
-        }
-        const bool draw_box = has || (tracking && c->has_bbox);
-        const vt_bbox b = has ? bb : c->current_bbox;
-        if (draw_box) {
-            cmds.push_back(make_cmd(VT_OV_RECT, b.x, b.y, b.width, b.height, 3, 255, 0, 0));
-            cmds.push_back(make_cmd(VT_OV_CROSSHAIR, b.x + b.width / 2, b.y + b.height / 2, 0, 0, 15, 255, 0, 0));
-        }
-    } else {  // src/pipeline_ir.rs:165-202 (draw_background_rgb call is commented out there)
-        cmds.push_back(make_cmd(VT_OV_TEXT, 15, 15, 0, 0, 2, 255, 0, 0, state_name.c_str(), 1));
-        cmds.push_back(make_cmd(VT_OV_TEXT, 15, 40, 0, 0, 2, 255, 0, 0, fps_s, 1));
-        cmds.push_back(make_cmd(VT_OV_TEXT, 15, 65, 0, 0, 1, 200, 0, 0, time_s, 1));
-        if (tracking) cmds.push_back(make_cmd(VT_OV_TEXT, 200, 15, 0, 0, 2, 255, 0, 0, score_line, 1));
-        if (selecting) {
-            cmds.push_back(make_cmd(VT_OV_CURSOR, c->selection.cursor_x, c->selection.cursor_y, 0, 0, 0, 0, 255, 0));
-            if (c->selection.phase == 1)
-                cmds.push_back(make_cmd(VT_OV_SELECTION, c->selection.start_x, c->selection.start_y, c->selection.cursor_x, c->selection.cursor_y, 0, 255, 255, 0));
-        }
-        const bool draw_box = has || (tracking && c->has_bbox);
-        const vt_bbox b = has ? bb : c->current_bbox;
-        if (draw_box) {
-            cmds.push_back(make_cmd(VT_OV_RECT, b.x, b.y, b.width, b.height, 3, 0, 255, 0));
-            cmds.push_back(make_cmd(VT_OV_CROSSHAIR, b.x + b.width / 2, b.y + b.height / 2, 0, 0, 15, 0, 255, 0));
-        }
-    }
-    st = c->frame_on_device ? vt_overlay_current(t, frame, len, cmds.data(), (int32_t)cmds.size())
-                            : vt_overlay(t, frame, len, cmds.data(), (int32_t)cmds.size());
-    if (st != VT_OK) return st;
+    for (const vt::HudCmd& hc : hud) cmds.push_back(hc.cmd);
+    return c->frame_on_device ? vt_overlay_current(t, frame, len, cmds.data(), (int32_t)cmds.size())
+                              : vt_overlay(t, frame, len, cmds.data(), (int32_t)cmds.size());
+}
 
-    const uint64_t every = nv12 ? 120 : 60;  // src/pipeline.rs:176 / src/pipeline_ir.rs:210
-    static const bool log_enabled = getenv("VT_PROBE_LOG") != nullptr;  // the reference prints unconditionally
-    if (log_enabled && num % every == 0 && num > 0)
-        printf("\r[%s] FPS: %.0f | conv: %.1fms | track: %.1fms\r\n", state_name.c_str(), tm.fps, tm.avg_conv_ms, tm.avg_track_ms);
+// Pinned frames: ONE synchronisation per probed frame.  Everything in the HUD except score / box / the state after the gate is known
+// before the frame runs; the list carries the commands of both outcomes and the frame's last kernel picks by the gate, renders the
+// score digits and the box from the device-side result and mirrors the touched pixels into the pinned frame.  The timing line shows
+// the rolling means up to the PREVIOUS frame (this frame's own conv / track times exist only once it has completed; the text is
+// timing dependent and not part of pixel parity).
+static vt_status probe_one_sync(vt_context* c, uint8_t* frame, size_t len, const char* const* hud_override, bool nv12) {
+    vt_tracker* t = c->tracker;
+    const auto t1 = std::chrono::steady_clock::now();
+    HudText h;
+    hud_text(c, nv12, hud_override, h);
+    // what process_frame will do with this frame (src/tracker_context.rs:64-155)
+    const bool init_update = c->state == AppState::Selecting && c->pending_confirm && c->selection.phase == 1;
+    const bool update = c->state == AppState::Tracking;
+    std::vector<vt::HudCmd> hud;
+    if (nv12) hud.push_back(vt::HudCmd{make_cmd(VT_OV_BACKGROUND, 10, 10, 400, 80, 150, 0, 0, 0), vt::VT_HUD_ALWAYS, vt::VT_HUD_GIVEN});
+    int32_t has = 0;
+    vt_bbox bb{0, 0, 0, 0};
+    vt_status st;
+    if (!init_update && !update) {
+        // no tracker call on this frame: the state machine steps on the host first, the HUD shows the new state
+        process_frame_core(c, [&](vt_bbox) { return UpdateOutcome{false, vt_result{}}; }, [&]() { return UpdateOutcome{false, vt_result{}}; }, &has, &bb);
+        hud_commands(c, nv12, vt_context_state(c), h, false, bb, c->current_score, vt::VT_HUD_ALWAYS, false, hud);
+        if ((st = vt::tracker_set_hud(t, hud.data(), (int)hud.size())) != VT_OK) return st;
+        if ((st = vt::tracker_submit_hud_only(t, frame, len)) != VT_OK) return st;
+        vt_result r;
+        st = vt_tracker_wait(t, &r);
+        if (st != VT_OK) return st;
+        vt_timing_add_times(t, 0, (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t1).count());
+        return VT_OK;
+    }
+    if (init_update) vt_tracker_init(t, 0, frame, len, c->selection.get_bbox());  // return value ignored, like the reference (:88)
+    // both outcomes: gate passed -> TRACKING + score + box; failed -> LOST (tracking frame) / SELECT START with the selection reset (confirm frame)
+    hud_commands(c, nv12, VT_STATE_TRACKING, h, true, bb, 0.f, vt::VT_HUD_IF_PASS, true, hud);
+    hud_commands(c, nv12, update ? VT_STATE_LOST : VT_STATE_SELECT_START, h, false, bb, 0.f, vt::VT_HUD_IF_FAIL, false, hud);
+    if ((st = vt::tracker_set_hud(t, hud.data(), (int)hud.size())) != VT_OK) return st;
+    UpdateOutcome o;
+    memset(&o.r, 0, sizeof(o.r));
+    st = vt_tracker_submit(t, frame, len);
+    if (st == VT_OK) st = vt_tracker_wait(t, &o.r);
+    o.ok = st == VT_OK && o.r.status == VT_OK;
+    c->frame_on_device = st == VT_OK;
+    // the state machine consumes the outcome exactly as in process_frame (the device applied the same gate to the same fp32 score)
+    process_frame_core(c, [&](vt_bbox) { return o; }, [&]() { return o; }, &has, &bb);
+    const uint64_t track_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t1).count();
+    vt_timing tm;
+    vt_timing_get(t, &tm);
+    vt_timing_add_times(t, c->frame_on_device ? (uint64_t)(tm.preprocess_ms * 1000.f) : 0, track_us);
+    return VT_OK;
+}
+
+// ≙ the pad-probe closure body: src/pipeline.rs:67-184 (NV12) / src/pipeline_ir.rs:100-228 (RGB24)
+vt_status vt_probe_frame(vt_context* c, uint8_t* frame, size_t len, const char* const* hud_override) {
+    if (!c || !c->tracker || !frame) return VT_ERR_INVALID;
+    vt_tracker* t = c->tracker;
+    const bool nv12 = vt::format_is_luma(c->cfg.format);  // GRAY8 frames take the luma-plane HUD of src/pipeline.rs:125-174
+    // interval timing, src/pipeline.rs:69-79
+    const auto now = std::chrono::steady_clock::now();
+    if (c->have_last) vt_timing_add_interval(t, (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(now - c->last_time).count());
+    c->last_time = now, c->have_last = true;
+    const uint64_t num = c->frame_num++;
+    const size_t need = c->cfg.format == VT_FMT_NV12 ? (size_t)c->frame_width * c->frame_height * 3 / 2
+                                                     : (size_t)c->frame_width * c->frame_height * (c->cfg.format == VT_FMT_RGB24 ? 3 : 1);
+    static const bool two_step = getenv("VT_PROBE_TWO_STEP") != nullptr;  // diagnostics: force the pageable-frame path
+    const vt_status st = (!two_step && len >= need && vt::frame_is_pinned(frame)) ? probe_one_sync(c, frame, len, hud_override, nv12)
+                                                                                : probe_two_step(c, frame, len, hud_override, nv12);
+    if (st != VT_OK) return st;
+    probe_log(c, nv12, num);
     return VT_OK;
 }
 

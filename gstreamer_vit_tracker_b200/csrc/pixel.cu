@@ -266,22 +266,34 @@ __device__ __forceinline__ Tap lin_tap(int i, int s, int d, bool clamp_frac) {
     return t;
 }
 
+// Where the pixels of this frame live: the device frame inside the valid window (the part that was uploaded this frame), the
+// caller's pinned host frame (zero-copy loads over PCIe) outside of it.  With whole-frame uploads the window is the frame.
+struct PixelSrc {
+    const uint8_t* dev;
+    const uint8_t* host;   // null: everything is on the device
+    int x0, y0, x1, y1;    // valid window of the device frame (even-aligned, so a pixel and its chroma pair sit on the same side)
+    __device__ __forceinline__ const uint8_t* at(int fx, int fy) const {
+        return (host && (fx < x0 || fx >= x1 || fy < y0 || fy >= y1)) ? host : dev;
+    }
+};
+
 // RGB of the frame pixel (fx, fy); zero outside the frame (constant border of the crop).
-__device__ __forceinline__ void frame_rgb(const FrameDesc& f, int fx, int fy, int& r, int& g, int& b) {
+__device__ __forceinline__ void frame_rgb(const FrameDesc& f, const PixelSrc& ps, int fx, int fy, int& r, int& g, int& b) {
     r = g = b = 0;
     // pad_plus1 (App. A.7, older OpenCV): a crop that reaches the right / bottom edge pads one pixel more, i.e. the last column / row of
     // the frame reads as border; a crop that stays inside never addresses it, so the bound can move unconditionally
     if (!f.valid || fx < 0 || fy < 0 || fx >= f.width - f.pad_plus1 || fy >= f.height - f.pad_plus1) return;
+    const uint8_t* data = ps.at(fx, fy);
     if (f.format == VT_FMT_RGB24) {
-        const uint8_t* p = f.data + ((size_t)fy * f.width + fx) * 3;
+        const uint8_t* p = data + ((size_t)fy * f.width + fx) * 3;
         r = p[0], g = p[1], b = p[2];
     } else if (f.format == VT_FMT_GRAY8) {
-        r = g = b = f.data[(size_t)fy * f.width + fx];
+        r = g = b = data[(size_t)fy * f.width + fx];
     } else {
         const size_t ysz = (size_t)f.width * f.height;
-        const int yv = f.data[(size_t)fy * f.width + fx];
+        const int yv = data[(size_t)fy * f.width + fx];
         const size_t uvi = ysz + (size_t)(fy >> 1) * f.width + (fx & ~1);
-        const Chroma c = chroma_terms(f.data[uvi], f.data[uvi + 1]);
+        const Chroma c = chroma_terms(data[uvi], data[uvi + 1]);
         yuv_px(yv, c, r, g, b);
     }
 }
@@ -293,8 +305,17 @@ __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, Targ
                                                                __nv_bfloat16* __restrict__ p_lo, unsigned long long* stamp) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the template gather behind this kernel does not depend on it
     if (stamp && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) *stamp = device_time_ns();
-    if (f.data_slot) f.data = *f.data_slot;
     const int bi = blockIdx.y;
+    PixelSrc ps{f.data, nullptr, 0, 0, f.width, f.height};
+    if (f.ctl) {  // per-frame control block: frame address, and which part of the device frame holds this frame's pixels
+        ps.dev = f.ctl->frame;
+        const int nw = f.ctl->n_win;
+        if (nw >= 0) {
+            ps.host = f.ctl->host_frame;
+            if (bi < nw) ps.x0 = f.ctl->win[bi][0], ps.y0 = f.ctl->win[bi][1], ps.x1 = f.ctl->win[bi][2], ps.y1 = f.ctl->win[bi][3];
+            else ps.x1 = ps.y1 = 0;  // nothing of this target was uploaded
+        }
+    }
     const int slot = slots[bi];
     TargetState* st = state + slot;
     const int bx = st->rect[0], by = st->rect[1], bw = st->rect[2], bh = st->rect[3];
@@ -317,10 +338,10 @@ __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, Targ
     const int cx0 = tx.ofs, cx1 = min(tx.ofs + 1, c - 1);
     const int cy0 = min(max(ty.ofs, 0), c - 1), cy1 = min(max(ty.ofs + 1, 0), c - 1);
     int p00[3], p01[3], p10[3], p11[3];
-    frame_rgb(f, x1 + cx0, y1 + cy0, p00[0], p00[1], p00[2]);
-    frame_rgb(f, x1 + cx1, y1 + cy0, p01[0], p01[1], p01[2]);
-    frame_rgb(f, x1 + cx0, y1 + cy1, p10[0], p10[1], p10[2]);
-    frame_rgb(f, x1 + cx1, y1 + cy1, p11[0], p11[1], p11[2]);
+    frame_rgb(f, ps, x1 + cx0, y1 + cy0, p00[0], p00[1], p00[2]);
+    frame_rgb(f, ps, x1 + cx1, y1 + cy0, p01[0], p01[1], p01[2]);
+    frame_rgb(f, ps, x1 + cx0, y1 + cy1, p10[0], p10[1], p10[2]);
+    frame_rgb(f, ps, x1 + cx1, y1 + cy1, p11[0], p11[1], p11[2]);
     const int nt = S >> 4;
     const int token = (dy >> 4) * nt + (dx >> 4);
     const size_t off = (size_t)bi * patches_stride + (size_t)token * kPatchK + (dy & 15) * 16 + (dx & 15);
@@ -574,27 +595,76 @@ cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, 
     return cudaGetLastError();
 }
 
-// Box overlay straight from the device-side decode result: one CTA per target,
-// rect (thickness 3) then crosshair (size 15) at the box centre ≙ src/pipeline.rs:165-168 / src/pipeline_ir.rs:192-195.
-// `host_slot` (nullable) points at a device cell (set per frame by stamp_kernel) holding the address of the caller's pinned frame (or null): the
-// same pixels are then also written straight into the host frame (zero-copy stores over PCIe, ~3.4 K bytes), so no
-// device->host row copy and no second synchronisation is needed to hand the overlaid frame back.
-__global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t len, int W, int H, int fmt,
-                                                          const DeviceResult* __restrict__ res, const int32_t* __restrict__ slots,
-                                                          float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
-                                                          uint8_t* const* frame_slot, const uint32_t* __restrict__ blk,
-                                                          uint32_t* const* hblk_slot, int blk_words) {
-    // frame / host addresses and the slot table were written at the start of the frame (complete long before the kernel ahead of this
-    // one): every thread fetches them in one batch; only the decode result waits for the dependency
-    if (frame_slot) frame = *frame_slot;
-    uint8_t* const host = host_slot ? *reinterpret_cast<uint8_t* const volatile*>(host_slot) : nullptr;
-    const int slot = slots[blockIdx.x];
+// Last kernel of a frame.  (a) Box overlay straight from the device-side decode result: one CTA per target, rect (thickness 3) then
+// crosshair (size 15) at the box centre ≙ src/pipeline.rs:165-168 / src/pipeline_ir.rs:192-195.  (b) The frame's HUD command list
+// (probe: ≙ src/pipeline.rs:125-174 / src/pipeline_ir.rs:165-202), CTA 0: the list holds the commands of BOTH outcomes of the frame
+// and the kernel picks by the gate (status ok && success && score > gate, src/tracker_context.rs:93,122), takes the box geometry and
+// the score digits from the decode result — the host queued it before the frame's result existed, so the whole probe needs ONE
+// synchronisation.  (c) With a pinned caller frame (ctl->host_frame) the touched pixels are also written straight into the host frame
+// (zero-copy stores over PCIe; the dimmed background is copied out of the device frame), so no device->host row copy and no second
+// synchronisation is needed to hand the overlaid frame back.  (d) The result block is published into the pinned host block.
+__device__ void hud_score_glyphs(OverlayCmdDev& c, float score) {  // "score: " + "{:.0}%" of score*100 (src/pipeline.rs:146-156)
+    const float pct = rintf(__fmul_rn(score, 100.0f));            // round-half-even, as Rust's {:.0} / printf("%.0f")
+    int v = pct > 0.f ? (pct < 999.f ? (int)pct : 999) : 0;
+    int dig[3], nd = 0;
+    do { dig[nd++] = v % 10, v /= 10; } while (v && nd < 3);
+    int k = c.nchar;
+    for (int i = nd - 1; i >= 0 && k < 36; --i, ++k) {
+        for (int r = 0; r < 7; ++r) c.glyph[k][r] = c.glyph[kHudDigitSlot + dig[i]][r];
+        c.known[k] = c.known[kHudDigitSlot + dig[i]];
+    }
+    if (k < 36) {
+        for (int r = 0; r < 7; ++r) c.glyph[k][r] = c.glyph[kHudPercentSlot][r];
+        c.known[k] = c.known[kHudPercentSlot], ++k;
+    }
+    c.nchar = (uint8_t)k;
+}
+
+// rows [y0, y1) x byte columns [b0, b1) of a plane with `pitch` bytes per row: device frame -> host frame, 4-byte words where both sides
+// allow it (same offset on both sides, so alignment is shared)
+__device__ void mirror_region(uint8_t* host, const uint8_t* dev, size_t len, size_t pitch, long long y0, long long y1, long long b0, long long b1) {
+    if (y1 <= y0 || b1 <= b0) return;
+    const long long nb = b1 - b0;
+    for (long long y = y0; y < y1; ++y) {
+        const size_t row = (size_t)y * pitch + (size_t)b0;
+        if (row + (size_t)nb > len) break;
+        const size_t head = (4 - ((reinterpret_cast<uintptr_t>(dev) + row) & 3)) & 3;
+        const long long h = head < (size_t)nb ? (long long)head : nb;
+        const long long words = (nb - h) >> 2, tail0 = h + (words << 2);
+        for (long long i = threadIdx.x; i < words; i += blockDim.x)
+            *reinterpret_cast<uint32_t*>(host + row + h + 4 * i) = *reinterpret_cast<const uint32_t*>(dev + row + h + 4 * i);
+        if ((long long)threadIdx.x < h) host[row + threadIdx.x] = dev[row + threadIdx.x];
+        if ((long long)threadIdx.x < nb - tail0) host[row + tail0 + threadIdx.x] = dev[row + tail0 + threadIdx.x];
+    }
+}
+
+__global__ void __launch_bounds__(256) box_overlay_kernel(size_t len, int W, int H, int fmt, const DeviceResult* __restrict__ res,
+                                                          const int32_t* __restrict__ slots, int n, float gate, const FrameCtl* ctl,
+                                                          unsigned long long* stamp_end, const uint32_t* __restrict__ blk, int blk_words,
+                                                          int draw_box) {
+    __shared__ OverlayCmdDev s_cmd[kMaxCmds];
+    // the control block was written at the start of the frame (complete long before the kernel ahead of this one): every thread fetches
+    // what it needs in one batch, and the HUD list comes out of pinned host memory, BEFORE the dependency wait: only the decode result
+    // waits for the preceding kernel
+    uint8_t* const frame = const_cast<uint8_t*>(ctl->frame);
+    uint8_t* const host = ctl->host_frame;
+    int n_hud = blockIdx.x == 0 ? ctl->n_hud : 0;
+    if (n_hud > kMaxCmds) n_hud = kMaxCmds;
+    if (n_hud > 0) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(ctl->hud);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_cmd);
+        for (int i = threadIdx.x; i < n_hud * (int)(sizeof(OverlayCmdDev) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    const int slot = (int)blockIdx.x < n ? slots[blockIdx.x] : -1;
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const DeviceResult r = res[slot];
-    if (r.status == VT_OK && r.success && r.score > gate) {
+    DeviceResult r;
+    r.status = VT_ERR_NOT_INIT, r.success = 0, r.score = 0.f, r.bbox[0] = r.bbox[1] = r.bbox[2] = r.bbox[3] = 0, r.best = 0;
+    if (slot >= 0) r = res[slot];
+    const bool pass = r.status == VT_OK && r.success && r.score > gate;
+    if (draw_box && pass) {
         const int x = r.bbox[0], y = r.bbox[1], w = r.bbox[2], h = r.bbox[3];
-        for (int pass = 0; pass < 2; ++pass) {
-            uint8_t* dst = pass == 0 ? frame : host;
+        for (int p = 0; p < 2; ++p) {
+            uint8_t* dst = p == 0 ? frame : host;
             if (!dst) break;
             Surface s{dst, len, W, H, fmt};
             if (fmt == VT_FMT_NV12) {
@@ -610,9 +680,40 @@ __global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t
         }
     }
     if (blockIdx.x != 0) return;
+    if (n_hud > 0) {
+        __syncthreads();
+        // resolve the result-dependent commands once (shared copy), drop the ones of the other outcome
+        if ((int)threadIdx.x < n_hud) {
+            OverlayCmdDev& c = s_cmd[threadIdx.x];
+            if ((c.cond == VT_HUD_IF_PASS && !pass) || (c.cond == VT_HUD_IF_FAIL && pass)) c.kind = -1;
+            else if (c.from_result == VT_HUD_RESULT_RECT) c.x = r.bbox[0], c.y = r.bbox[1], c.w = r.bbox[2], c.h = r.bbox[3];
+            else if (c.from_result == VT_HUD_RESULT_CROSS) c.x = r.bbox[0] + r.bbox[2] / 2, c.y = r.bbox[1] + r.bbox[3] / 2;
+            else if (c.from_result == VT_HUD_SCORE_TEXT) hud_score_glyphs(c, r.score);
+        }
+        __syncthreads();
+        for (int p = 0; p < 2; ++p) {
+            uint8_t* dst = p == 0 ? frame : host;
+            if (!dst) break;
+            Surface s{dst, len, W, H, fmt};
+            for (int i = 0; i < n_hud; ++i) {
+                const OverlayCmdDev& c = s_cmd[i];
+                if (c.kind < 0) continue;
+                if (p == 1 && c.kind == VT_OV_BACKGROUND && fmt == VT_FMT_NV12) {
+                    // read-modify-write: the host copy takes the final pixels of the region from the device frame (the later commands
+                    // of this pass re-draw what lies on top of it)
+                    const u64 x0 = (u64)c.x, y0 = (u64)c.y;  // the region ov_background touched (same usize arithmetic)
+                    const u64 x1 = umin64(x0 + (u64)c.w, (u64)W), y1 = umin64(y0 + (u64)c.h, (u64)H);
+                    if (x1 > x0 && y1 > y0) mirror_region(host, frame, len, (size_t)W, (long long)y0, (long long)y1, (long long)x0, (long long)x1);
+                } else {
+                    ov_dispatch(s, c);
+                }
+                __syncthreads();
+            }
+        }
+    }
     if (stamp_end && threadIdx.x == 0) *stamp_end = device_time_ns();
-    if (hblk_slot) {  // last kernel of the frame: publish the result block (see publish_kernel) — one kernel boundary less
-        uint32_t* dst = *reinterpret_cast<uint32_t* const volatile*>(hblk_slot);
+    if (blk) {  // last kernel of the frame: publish the result block (see publish_kernel) — one kernel boundary less
+        uint32_t* dst = ctl->hblk;
         __threadfence();  // the end stamp above is part of the block
         __syncthreads();
         if (dst)
@@ -620,41 +721,36 @@ __global__ void __launch_bounds__(256) box_overlay_kernel(uint8_t* frame, size_t
     }
 }
 
-cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
-                               const int32_t* d_slots, int n, float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
-                               cudaStream_t s, uint8_t* const* frame_slot, bool pdl, const void* d_blk, uint32_t* const* hblk_slot, size_t blk_bytes) {
-    if (n <= 0) return cudaSuccess;
-    return launch_ex(box_overlay_kernel, dim3(n), dim3(256), 0, s, pdl, 1, d_frame, len, width, height, format, d_res, d_slots, gate, host_slot,
-                     stamp_end, frame_slot, (const uint32_t*)d_blk, hblk_slot, (int)(blk_bytes / 4));
+cudaError_t launch_box_overlay(size_t len, int width, int height, int format, const DeviceResult* d_res, const int32_t* d_slots, int n,
+                               float gate, const FrameCtl* d_ctl, unsigned long long* stamp_end, cudaStream_t s, bool pdl, const void* d_blk,
+                               size_t blk_bytes, int draw_box) {
+    return launch_ex(box_overlay_kernel, dim3(n > 0 ? n : 1), dim3(256), 0, s, pdl, 1, len, width, height, format, d_res, d_slots, n, gate, d_ctl,
+                     stamp_end, (const uint32_t*)d_blk, (int)(blk_bytes / 4), draw_box);
 }
 
-// per-frame, outside the graph: submit stamp + the addresses that change from frame to frame, handed to the graph's kernels through
-// device cells: the frame this step reads (FrameDesc::data_slot), the caller's pinned frame for the overlay mirror, and the pinned
-// host block the results are published to
-__global__ void stamp_kernel(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, uint8_t** host_slot, uint8_t* host_frame,
-                             uint32_t** hblk_slot, uint32_t* hblk) {
-    *stamp = device_time_ns();
-    if (frame_slot) *frame_slot = frame;
-    if (host_slot) *host_slot = host_frame;
-    if (hblk_slot) *hblk_slot = hblk;
+// per-frame, outside the graph: submit stamp + the control block (addresses and parameters that change from frame to frame)
+__global__ void stamp_kernel(unsigned long long* stamp, FrameCtl* dst, const FrameCtl val) {
+    if (threadIdx.x == 0) *stamp = device_time_ns();
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&val);
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameCtl) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(dst)[i] = src[i];
 }
-cudaError_t launch_stamp(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, uint8_t** host_slot, uint8_t* host_frame,
-                         uint32_t** hblk_slot, uint32_t* hblk, cudaStream_t s) {
-    stamp_kernel<<<1, 1, 0, s>>>(stamp, frame_slot, frame, host_slot, host_frame, hblk_slot, hblk);
+cudaError_t launch_stamp(unsigned long long* stamp, FrameCtl* d_ctl, const FrameCtl& ctl, cudaStream_t s) {
+    static_assert(sizeof(FrameCtl) % 4 == 0, "word copy");
+    stamp_kernel<<<1, 96, 0, s>>>(stamp, d_ctl, ctl);
     return cudaGetLastError();
 }
 
 // Last kernel of a frame: the result block (results, stage stamps, error flag; < 2 KB) is written straight into the pinned host block
 // of the frame's queue slot (zero-copy stores).  A kernel -> copy-engine -> kernel hand-over on the stream costs ~14 us per frame
 // (measured between the overlay's end stamp and the next frame's submit stamp); a dependent kernel costs ~4 us.
-__global__ void __launch_bounds__(128) publish_kernel(const uint32_t* __restrict__ blk, uint32_t* const* hblk_slot, int words) {
-    uint32_t* dst = *reinterpret_cast<uint32_t* const volatile*>(hblk_slot);  // written by stamp_kernel at the start of the frame
+__global__ void __launch_bounds__(128) publish_kernel(const uint32_t* __restrict__ blk, const FrameCtl* ctl, int words) {
+    uint32_t* dst = ctl->hblk;  // written by stamp_kernel at the start of the frame
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (!dst) return;
     for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldcg(blk + i);
 }
-cudaError_t launch_publish(const void* d_blk, uint32_t* const* hblk_slot, size_t bytes, cudaStream_t s, bool pdl) {
-    return launch_ex(publish_kernel, dim3(1), dim3(128), 0, s, pdl, 1, (const uint32_t*)d_blk, hblk_slot, (int)(bytes / 4));
+cudaError_t launch_publish(const void* d_blk, const FrameCtl* d_ctl, size_t bytes, cudaStream_t s, bool pdl) {
+    return launch_ex(publish_kernel, dim3(1), dim3(128), 0, s, pdl, 1, (const uint32_t*)d_blk, d_ctl, (int)(bytes / 4));
 }
 
 }  // namespace vt

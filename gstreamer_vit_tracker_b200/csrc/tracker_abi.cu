@@ -205,6 +205,34 @@ vt_status vt_tracker_sync(vt_tracker* t) {
 // ---- overlay -------------------------------------------------------------------------------------
 int vt_glyph_rows(int ch, uint8_t rows[7]);  // host_state.cpp
 
+}  // extern "C"
+namespace vt {
+vt_status fill_cmd_dev(const vt_overlay_cmd& c, OverlayCmdDev& d) {
+    memset(&d, 0, sizeof(d));
+    d.kind = c.kind, d.x = c.x, d.y = c.y, d.w = c.w, d.h = c.h, d.a = c.a, d.r = c.r, d.g = c.g, d.b = c.b;
+    if (c.kind < VT_OV_RECT || c.kind > VT_OV_SELECTION) {
+        set_error("vt_overlay: unknown command kind %d", c.kind);
+        return VT_ERR_INVALID;
+    }
+    if (c.kind == VT_OV_TEXT) {
+        const size_t len = strnlen(c.text, sizeof(c.text));
+        d.nchar = (uint8_t)len;
+        for (size_t k = 0; k < len; ++k) {
+            uint8_t rows[7];
+            if (vt_glyph_rows((unsigned char)c.text[k], rows) == 0) {
+                d.known[k] = 1;
+                memcpy(d.glyph[k], rows, 7);
+            } else if (c.strict_glyphs) {
+                set_error("vt_overlay: no glyph for character 0x%02x", (unsigned char)c.text[k]);
+                return VT_ERR_GLYPH;
+            }
+        }
+    }
+    return VT_OK;
+}
+}  // namespace vt
+extern "C" {
+
 static vt_status build_cmds(vt_tracker* t, const vt_overlay_cmd* cmds, int n, std::vector<std::pair<int, int>>& spans) {
     if (n < 0 || n > kMaxCmds) {
         set_error("vt_overlay: at most %d commands", kMaxCmds);
@@ -214,8 +242,8 @@ static vt_status build_cmds(vt_tracker* t, const vt_overlay_cmd* cmds, int n, st
     for (int i = 0; i < n; ++i) {
         const vt_overlay_cmd& c = cmds[i];
         OverlayCmdDev& d = t->h_cmds[i];
-        memset(&d, 0, sizeof(d));
-        d.kind = c.kind, d.x = c.x, d.y = c.y, d.w = c.w, d.h = c.h, d.a = c.a, d.r = c.r, d.g = c.g, d.b = c.b;
+        const vt_status fs = fill_cmd_dev(c, d);
+        if (fs != VT_OK) return fs;
         long long r0 = 0, r1 = -1;
         switch (c.kind) {
             case VT_OV_RECT:
@@ -224,22 +252,7 @@ static vt_status build_cmds(vt_tracker* t, const vt_overlay_cmd* cmds, int n, st
             case VT_OV_CROSSHAIR:
                 if (!cross_rows(H, c.y, c.a, r0, r1)) r0 = 0, r1 = -1;
                 break;
-            case VT_OV_TEXT: {
-                size_t len = strnlen(c.text, sizeof(c.text));
-                d.nchar = (uint8_t)len;
-                for (size_t k = 0; k < len; ++k) {
-                    uint8_t rows[7];
-                    if (vt_glyph_rows((unsigned char)c.text[k], rows) == 0) {
-                        d.known[k] = 1;
-                        memcpy(d.glyph[k], rows, 7);
-                    } else if (c.strict_glyphs) {
-                        set_error("vt_overlay: no glyph for character 0x%02x", (unsigned char)c.text[k]);
-                        return VT_ERR_GLYPH;
-                    }
-                }
-                r0 = c.y, r1 = (long long)c.y + 7LL * std::max(c.a, 0);
-                break;
-            }
+            case VT_OV_TEXT: r0 = c.y, r1 = (long long)c.y + 7LL * std::max(c.a, 0); break;
             case VT_OV_BACKGROUND:
                 r0 = c.y, r1 = (long long)c.y + c.h;
                 if (t->fmt == VT_FMT_RGB24 && (long long)c.y + c.h < 0) r0 = 0, r1 = H - 1;  // (y+bh) as usize wraps, src/drawing_rgb.rs:45

@@ -17,6 +17,7 @@ static std::mutex g_weight_mutex;
 std::atomic<int> g_live_handles[kMaxDevices];
 static std::map<std::string, std::weak_ptr<WeightSet>> g_weight_cache;
 
+bool frame_is_pinned(const void* p) { return is_pinned(p); }
 bool is_pinned(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -207,9 +208,9 @@ void vt_tracker_destroy(vt_tracker* t) {
         if (t->h_blk[i]) cudaFreeHost(t->h_blk[i]);
         if (t->q_done[i]) cudaEventDestroy(t->q_done[i]);
     }
-    if (t->d_host_slot) cudaFree(t->d_host_slot);
-    if (t->d_hblk_slot) cudaFree(t->d_hblk_slot);
-    if (t->d_frame_slot) cudaFree(t->d_frame_slot);
+    if (t->d_ctl) cudaFree(t->d_ctl);
+    for (auto& h : t->h_hud)
+        if (h) cudaFreeHost(h);
     if (t->h_cmds) cudaFreeHost(t->h_cmds);
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;
@@ -274,6 +275,7 @@ vt_status vt_tracker_create(const vt_config* cfg_in, vt_tracker** out) {
     t->threshold = cfg->score_threshold > 0.f ? cfg->score_threshold : 0.20f;
     t->debug_capture = cfg->debug_capture;
     t->hostprof = getenv("VT_B200_HOSTPROF") != nullptr;
+    if (const char* e = getenv("VT_B200_WINDOW_SHRINK")) t->win_shrink = atoi(e) & ~1;
     auto fail = [&](vt_status st) {
         vt_tracker_destroy(t);
         return st;
@@ -332,12 +334,13 @@ vt_status vt_tracker_create(const vt_config* cfg_in, vt_tracker** out) {
     t->d_stamps = reinterpret_cast<unsigned long long*>(t->d_res + B);
     t->d_tc_err = reinterpret_cast<int*>(t->d_stamps + ST_COUNT);
     bind_slot(t, 0);
-    VT_TRY(cudaMalloc(&t->d_frame_slot, sizeof(uint8_t*)));
-    VT_TRY(cudaMemcpy(t->d_frame_slot, &t->d_frame, sizeof(uint8_t*), cudaMemcpyHostToDevice));
-    VT_TRY(cudaMalloc(&t->d_host_slot, sizeof(uint8_t*)));
-    VT_TRY(cudaMemset(t->d_host_slot, 0, sizeof(uint8_t*)));
-    VT_TRY(cudaMalloc(&t->d_hblk_slot, sizeof(uint32_t*)));
-    VT_TRY(cudaMemset(t->d_hblk_slot, 0, sizeof(uint32_t*)));
+    {
+        FrameCtl ctl;
+        memset(&ctl, 0, sizeof(ctl));
+        ctl.frame = t->d_frame, ctl.n_win = -1;
+        VT_TRY(cudaMalloc(&t->d_ctl, sizeof(FrameCtl)));
+        VT_TRY(cudaMemcpy(t->d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice));
+    }
     VT_TRY(cudaMalloc(&t->d_maps, sizeof(float) * 1280 * B));
     VT_TRY(cudaMemset(t->d_maps, 0, sizeof(float) * 1280 * B));
     VT_TRY(cudaMalloc(&t->d_cmds, sizeof(OverlayCmdDev) * kMaxCmds));

@@ -10,6 +10,8 @@
 // host round trip.
 #include "tracker_state.h"
 
+extern "C" int vt_glyph_rows(int ch, uint8_t rows[7]);  // host_state.cpp
+
 namespace vt {
 
 // template tokens (fixed since init) -> rows 0..63 of every target's sequence: residual stream X and, on the fused-LN
@@ -47,7 +49,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     const int D = t->D, Hd = t->hidden, C = t->head_ch;
     (void)record_events, (void)capturing;  // stage times come from device stamps (ST_*), not from event nodes
     cudaStream_t s = t->stream;
-    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid, t->d_frame_slot, t->cfg.pad_plus1};
+    FrameDesc fd{t->d_frame, t->W, t->H, t->fmt, t->frame_valid, t->d_ctl, t->cfg.pad_plus1};
     auto LO = [&](__nv_bfloat16* p) { return t->f16 ? nullptr : p; };  // fp16 mode: "hi only" (see vt_internal.h: operand_bits)
     VT_LAUNCH(launch_crop_resize_norm(fd, t->d_state, t->d_slots, n, 4, kSearch, t->d_lut, t->patches_x, (size_t)kNTx * kPatchK, t->px_hi,
                                       LO(t->px_lo), s, t->d_stamps + ST_PRE));
@@ -173,12 +175,11 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
     else
         VT_LAUNCH(launch_decode(t->H1, C, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n, t->threshold, t->d_res, t->d_maps, t->d_stamps, s,
                                 t->cfg.decode_window));
-    if (t->cfg.box_overlay)
-        VT_LAUNCH(launch_box_overlay(t->d_frame, t->frame_bytes, t->W, t->H, overlay_format(t->fmt), t->d_res, t->d_slots, n, t->cfg.overlay_gate,
-                                     t->d_host_slot, t->d_stamps + ST_OVL_END, s, (uint8_t* const*)t->d_frame_slot, t->pdl && !t->debug_capture,
-                                     t->d_res, t->d_hblk_slot, t->res_block_bytes));  // ... and publishes the result block
+    if (t->cfg.box_overlay || t->hud_mode)  // box overlay and / or the frame's HUD list, pinned-frame mirror, ... and publishes the result block
+        VT_LAUNCH(launch_box_overlay(t->frame_bytes, t->W, t->H, overlay_format(t->fmt), t->d_res, t->d_slots, n, t->cfg.overlay_gate, t->d_ctl,
+                                     t->d_stamps + ST_OVL_END, s, t->pdl && !t->debug_capture, t->d_res, t->res_block_bytes, t->cfg.box_overlay));
     else  // results, stage stamps and the error flag -> the pinned host block of this frame's queue slot
-        VT_LAUNCH(launch_publish(t->d_res, t->d_hblk_slot, t->res_block_bytes, s, t->pdl && !t->debug_capture));
+        VT_LAUNCH(launch_publish(t->d_res, t->d_ctl, t->res_block_bytes, s, t->pdl && !t->debug_capture));
     return VT_OK;
 }
 
@@ -227,60 +228,96 @@ static vt_status sync_slots(vt_tracker* t) {
     return VT_OK;
 }
 
-// Search window of a target in frame coordinates (App. A.1 with factor 4), clipped to the frame and grown to even coordinates
+// Search window of a target in frame coordinates (App. A.1 with factor 4), grown by `margin_div` (0 = exact; d: by c / d on every side,
+// at least 16 px — used when the host's copy of rect_last lags by one frame), clipped to the frame and grown to even coordinates
 // (NV12 chroma pairs).  Returns false when the window misses the frame.
-static bool search_window(const vt_tracker* t, const vt_bbox& r, int& x0, int& y0, int& x1, int& y1) {
+static bool search_window(const vt_tracker* t, const vt_bbox& r, int margin_div, int& x0, int& y0, int& x1, int& y1) {
     if (r.width <= 0 || r.height <= 0) return false;
     const int c = (int)ceil(sqrt((double)(int)((long long)r.width * r.height)) * 4.0);
-    const int wx = r.x + (r.width - c) / 2, wy = r.y + (r.height - c) / 2;
-    x0 = std::max(wx, 0) & ~1, y0 = std::max(wy, 0) & ~1;
-    x1 = std::min((std::min(wx + c, t->W) + 1) & ~1, t->W), y1 = std::min((std::min(wy + c, t->H) + 1) & ~1, t->H);
+    const int m = margin_div > 0 ? std::max(16, c / margin_div) : 0;
+    const long long wx = (long long)r.x + (r.width - c) / 2 - m, wy = (long long)r.y + (r.height - c) / 2 - m, e = (long long)c + 2 * m;
+    x0 = (int)std::max(wx, 0LL) & ~1, y0 = (int)std::max(wy, 0LL) & ~1;
+    x1 = (int)std::min((std::min(wx + e, (long long)t->W) + 1) & ~1LL, (long long)t->W);
+    y1 = (int)std::min((std::min(wy + e, (long long)t->H) + 1) & ~1LL, (long long)t->H);
     return x1 > x0 && y1 > y0;
 }
 
-// host -> device frame upload (pinned: direct async; pageable: staged through the handle's pinned buffer).
-// cfg.upload_window: only the search windows of the active targets travel (PCIe is the end-to-end roofline):
-// the fused crop kernel reads nothing else.  rect_mirror is exact whenever no frame is in flight.
-vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, bool allow_window, bool device_src, cudaStream_t stream) {
+// What travels host -> device for one frame (PCIe is the end-to-end roofline): the whole frame, or — cfg.upload_window,
+// pinned frame — only the search window of every active target (+ the region a HUD list reads before writing).  The fused crop kernel
+// reads nothing else; should the real window leave the uploaded one (pipelined frames: rect_mirror lags by one frame and the window
+// is a prediction), the crop kernel fetches the missing pixels straight from the pinned host frame, so the result never depends on
+// the prediction.
+struct UploadPlan {
+    bool whole = true;
+    int n_win = 0;
+    int win[kMaxWin][4];
+    bool has_rmw = false;
+    int rmw[4] = {0, 0, 0, 0};
+    size_t bytes = 0;
+};
+static void plan_upload(vt_tracker* t, size_t len, bool pinned_host, bool lagging, const int* rmw, UploadPlan& p) {
+    p = UploadPlan();
+    const bool valid = (t->fmt == VT_FMT_NV12) ? (len >= (size_t)t->W * t->H * 3 / 2) : (len >= t->frame_bytes);
+    if (!t->cfg.upload_window || !pinned_host || !valid || len < t->frame_bytes || (int)t->active.size() > kMaxWin || (t->W % 2) ||
+        ((t->H % 2) && t->fmt == VT_FMT_NV12) || (t->active.empty() && !t->hud_mode))
+        return;
+    const size_t bpp2 = t->fmt == VT_FMT_NV12 ? 3 : (t->fmt == VT_FMT_GRAY8 ? 2 : 6);  // bytes per pixel x 2
+    size_t bytes = 0;
+    int k = 0;
+    for (int s : t->active) {
+        int* w = p.win[k++];
+        if (!search_window(t, t->rect_mirror[s], lagging ? 8 : 0, w[0], w[1], w[2], w[3])) {
+            w[0] = w[1] = w[2] = w[3] = 0;  // the window misses the frame: the crop kernel flags it; nothing to read
+            continue;
+        }
+        if (t->win_shrink > 0 && w[2] - w[0] > 4 * t->win_shrink && w[3] - w[1] > 4 * t->win_shrink)
+            w[0] += t->win_shrink, w[1] += t->win_shrink, w[2] -= t->win_shrink, w[3] -= t->win_shrink;
+        bytes += (size_t)(w[2] - w[0]) * (w[3] - w[1]) * bpp2 / 2;
+    }
+    if (rmw && rmw[2] > rmw[0] && rmw[3] > rmw[1] && format_is_luma(t->fmt)) {
+        p.has_rmw = true;
+        p.rmw[0] = std::max(rmw[0], 0), p.rmw[1] = std::max(rmw[1], 0), p.rmw[2] = std::min(rmw[2], t->W), p.rmw[3] = std::min(rmw[3], t->H);
+        if (p.rmw[2] > p.rmw[0] && p.rmw[3] > p.rmw[1]) bytes += (size_t)(p.rmw[2] - p.rmw[0]) * (p.rmw[3] - p.rmw[1]);
+        else p.has_rmw = false;
+    }
+    if (bytes * 2 > t->frame_bytes) return;  // not worth the extra copies
+    p.whole = false, p.n_win = k, p.bytes = bytes;
+}
+
+static vt_status do_upload(vt_tracker* t, const uint8_t* frame, size_t len, const UploadPlan& p, bool device_src, cudaStream_t stream) {
     if (!stream) stream = t->stream;
     size_t n = std::min(len, t->frame_bytes);
     t->frame_valid = (t->fmt == VT_FMT_NV12) ? (len >= (size_t)t->W * t->H * 3 / 2) : (len >= t->frame_bytes);
     if (!t->frame_valid && t->fmt == VT_FMT_NV12) n = 0;  // src/nv12_convert.rs:48-50 -> black image
     if (n == 0) return VT_OK;
-    const bool pinned = device_src || is_pinned(frame);
     const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (allow_window && t->cfg.upload_window && pinned && t->frame_valid && len >= t->frame_bytes && !t->active.empty() && (t->W % 2 == 0) &&
-        (t->H % 2 == 0 || t->fmt != VT_FMT_NV12)) {
-        struct Win { int x0, y0, x1, y1; };
-        std::vector<Win> wins;
-        size_t bytes = 0;
-        const size_t bpp_num = t->fmt == VT_FMT_NV12 ? 3 : (t->fmt == VT_FMT_GRAY8 ? 2 : 6);  // bytes per pixel x 2
-        for (int s : t->active) {
-            Win w;
-            if (!search_window(t, t->rect_mirror[s], w.x0, w.y0, w.x1, w.y1)) continue;  // the crop kernel flags it; nothing to read
-            wins.push_back(w);
-            bytes += (size_t)(w.x1 - w.x0) * (w.y1 - w.y0) * bpp_num / 2;
-        }
-        if (bytes * 2 <= t->frame_bytes) {
-            for (const Win& w : wins) {
-                const size_t cols = (size_t)(w.x1 - w.x0), rows = (size_t)(w.y1 - w.y0);
-                if (t->fmt == VT_FMT_GRAY8) {
-                    const size_t W = (size_t)t->W, o = (size_t)w.y0 * W + w.x0;
-                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, W, frame + o, W, cols, rows, kind, stream));
-                } else if (t->fmt == VT_FMT_NV12) {
-                    const size_t W = (size_t)t->W, yo = (size_t)w.y0 * W + w.x0, uvo = W * t->H + (size_t)(w.y0 / 2) * W + w.x0;
-                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + yo, W, frame + yo, W, cols, rows, kind, stream));
-                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + uvo, W, frame + uvo, W, cols, rows / 2, kind, stream));
-                } else {
-                    const size_t pitch = (size_t)t->W * 3, o = (size_t)w.y0 * pitch + (size_t)w.x0 * 3;
-                    VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, pitch, frame + o, pitch, cols * 3, rows, kind, stream));
-                }
+    if (!p.whole) {
+        const size_t W = (size_t)t->W;
+        for (int i = 0; i < p.n_win; ++i) {
+            const int* w = p.win[i];
+            const size_t cols = (size_t)(w[2] - w[0]), rows = (size_t)(w[3] - w[1]);
+            if (!cols || !rows) continue;
+            if (t->fmt == VT_FMT_GRAY8) {
+                const size_t o = (size_t)w[1] * W + w[0];
+                VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, W, frame + o, W, cols, rows, kind, stream));
+            } else if (t->fmt == VT_FMT_NV12) {
+                const size_t yo = (size_t)w[1] * W + w[0], uvo = W * t->H + (size_t)(w[1] / 2) * W + w[0];
+                VT_CUDA(cudaMemcpy2DAsync(t->d_frame + yo, W, frame + yo, W, cols, rows, kind, stream));
+                VT_CUDA(cudaMemcpy2DAsync(t->d_frame + uvo, W, frame + uvo, W, cols, rows / 2, kind, stream));
+            } else {
+                const size_t pitch = W * 3, o = (size_t)w[1] * pitch + (size_t)w[0] * 3;
+                VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, pitch, frame + o, pitch, cols * 3, rows, kind, stream));
             }
-            if (!device_src) t->h2d_bytes += bytes;
-            t->d_frame_is_last_host_frame = false;  // only the search windows are on the device
-            return VT_OK;
         }
+        if (p.has_rmw) {  // luma plane only (the NV12 / GRAY8 background dim reads and writes Y)
+            const size_t o = (size_t)p.rmw[1] * W + p.rmw[0];
+            VT_CUDA(cudaMemcpy2DAsync(t->d_frame + o, W, frame + o, W, (size_t)(p.rmw[2] - p.rmw[0]), (size_t)(p.rmw[3] - p.rmw[1]), kind, stream));
+        }
+        if (!device_src) t->h2d_bytes += p.bytes;
+        t->d_frame_is_last_host_frame = false;  // only windows of the frame are on the device
+        return VT_OK;
     }
+    const bool pinned = device_src || is_pinned(frame);
     t->d_frame_is_last_host_frame = !device_src && n >= t->frame_bytes;
     if (!device_src) t->h2d_bytes += n;
     if (pinned) {
@@ -290,6 +327,12 @@ vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, bool all
         VT_CUDA(cudaMemcpyAsync(t->d_frame, t->h_stage, n, cudaMemcpyHostToDevice, stream));
     }
     return VT_OK;
+}
+
+// whole-frame upload (init, and the callers outside the per-frame path)
+vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, bool allow_window, bool device_src, cudaStream_t stream) {
+    (void)allow_window;
+    return do_upload(t, frame, len, UploadPlan(), device_src, stream);
 }
 
 static void fill_results(vt_tracker* t, vt_result* results) {
@@ -401,7 +444,7 @@ static inline double now_us() {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_src, size_t len) {
+static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_src, size_t len, bool forward = true) {
     if (t->q_count >= vt_tracker::kQueue) {
         set_error("%d frames are already in flight on this handle", t->q_count);
         return VT_ERR_INVALID;
@@ -416,38 +459,61 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     vt_tracker::Slot& q = t->q[slot];
     q.t_submit = std::chrono::steady_clock::now();
     q.frame = d_src ? nullptr : frame, q.len = len, q.pageable = !pinned;
-    // zero-copy overlay mirror: only when the caller's frame is pinned (device-mapped under UVA)
-    q.mirrored = t->cfg.box_overlay && frame && !d_src && len >= t->frame_bytes && pinned;
+    // the caller's pinned frame is device-mapped under UVA: zero-copy target of the overlay mirror, fall-back source of the crop kernel
+    uint8_t* const host_frame = (frame && !d_src && pinned && len >= t->frame_bytes) ? frame : nullptr;
+    // this frame's HUD list (staged by tracker_set_hud in this slot's pinned block)
+    const int n_hud = t->hud_mode ? t->hud_next_n : 0;
+    q.hud_bytes = n_hud ? t->hud_next_bytes : 0;
+    q.mirrored = host_frame && (t->cfg.box_overlay || n_hud > 0);
     // device-resident frame: track (and draw the box) straight in the caller's device memory — no device->device copy
     const bool in_place = d_src && len >= t->frame_bytes;
     if (!in_place) t->d_frame = t->d_frames[slot];  // the slot's own frame buffer: the other one may still be read by the frame in flight
-    if (!in_place && !d_src && t->q_count > 0) {
-        // pipelined host frame: upload on the copy stream while the frame in flight computes (whole frame: the host mirror of
-        // rect_last lags by one frame); the main stream picks it up through an event
-        vt_status st = upload_frame(t, frame, len, false, false, t->copy_stream);
+    const bool lagging = t->q_count > 0;  // a frame is in flight: rect_mirror is one frame old, the windows are predictions
+    UploadPlan plan;
+    if (!in_place && !d_src) plan_upload(t, len, host_frame != nullptr, lagging, n_hud ? t->hud_next_rmw : nullptr, plan);
+    if (!in_place && !d_src && lagging) {
+        // pipelined host frame: upload on the copy stream while the frame in flight computes; the main stream picks it up through an event
+        vt_status st = do_upload(t, frame, len, plan, false, t->copy_stream);
         if (st != VT_OK) return st;
         VT_CUDA(cudaEventRecord(t->ev_up[slot], t->copy_stream));
         VT_CUDA(cudaStreamWaitEvent(t->stream, t->ev_up[slot], 0));
     }
-    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_frame_slot, in_place ? d_src : t->d_frame, t->d_host_slot, q.mirrored ? frame : nullptr,
-                         t->d_hblk_slot, reinterpret_cast<uint32_t*>(t->h_blk[slot]), t->stream));
+    FrameCtl ctl;
+    memset(&ctl, 0, sizeof(ctl));
+    ctl.frame = in_place ? d_src : t->d_frame, ctl.host_frame = host_frame, ctl.hblk = reinterpret_cast<uint32_t*>(t->h_blk[slot]);
+    ctl.hud = n_hud ? t->h_hud[slot] : nullptr, ctl.n_hud = n_hud;
+    ctl.n_win = plan.whole ? -1 : plan.n_win;
+    if (!plan.whole) memcpy(ctl.win, plan.win, sizeof(ctl.win));
+    t->hud_next_n = 0;
+    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_ctl, ctl, t->stream));
     ++t->kernel_launches;
     if (in_place) {
         t->frame_valid = 1;
         t->d_frame_is_last_host_frame = false;  // tracked in the caller's device memory: the internal buffer holds an older frame
     } else if (d_src) {  // short device frame: device->device copy of what there is (NV12: black frame, src/nv12_convert.rs:48-50)
-        vt_status st = upload_frame(t, d_src, len, false, true);
+        vt_status st = do_upload(t, d_src, len, plan, true, nullptr);
         if (st != VT_OK) return st;
-    } else if (t->q_count == 0) {
-        vt_status st = upload_frame(t, frame, len, true);  // the host mirror of rect_last is exact: the search windows suffice
+    } else if (!lagging) {
+        vt_status st = do_upload(t, frame, len, plan, false, nullptr);  // the host mirror of rect_last is exact: the search windows suffice
         if (st != VT_OK) return st;
     }
     const double hp1 = t->hostprof ? now_us() : 0;
-    vt_status st = run_forward(t);
-    if (st != VT_OK) return st;
+    const bool ran = forward && !t->active.empty();
+    if (ran) {
+        vt_status st = run_forward(t);
+        if (st != VT_OK) return st;
+    } else if (n_hud > 0) {  // no tracker runs on this frame (SELECT / LOST states of the probe): HUD list + publish only
+        cudaError_t e = launch_box_overlay(t->frame_bytes, t->W, t->H, overlay_format(t->fmt), t->d_res, t->d_slots, 0, t->cfg.overlay_gate, t->d_ctl,
+                                           t->d_stamps + ST_OVL_END, t->stream, false, t->d_res, t->res_block_bytes, 0);
+        if (e != cudaSuccess) {
+            set_error("overlay launch failed: %s", cudaGetErrorString(e));
+            return VT_ERR_CUDA;
+        }
+        ++t->kernel_launches;
+    }
     const double hp2 = t->hostprof ? now_us() : 0;
-    // the result block reaches t->h_blk[slot] through publish_kernel, the last kernel of run_forward (no target active: nothing ran)
-    if (t->active.empty()) VT_CUDA(cudaMemcpyAsync(t->h_blk[slot], t->d_res, t->res_block_bytes, cudaMemcpyDeviceToHost, t->stream));
+    // the result block reaches t->h_blk[slot] through the last kernel of the frame; nothing ran: copy it
+    if (!ran && n_hud == 0) VT_CUDA(cudaMemcpyAsync(t->h_blk[slot], t->d_res, t->res_block_bytes, cudaMemcpyDeviceToHost, t->stream));
     VT_CUDA(cudaEventRecord(t->q_done[slot], t->stream));
     t->d2h_bytes += t->res_block_bytes;
     if (t->hostprof) t->hp[0] += hp1 - hp0, t->hp[1] += hp2 - hp1, t->hp[2] += now_us() - hp2;
@@ -480,6 +546,7 @@ static vt_status wait_common(vt_tracker* t, vt_result* results) {
     }
     fill_results(t, results);
     const double hp2 = t->hostprof ? now_us() : 0;
+    if (q.hud_bytes && t->inflight_mirrored) t->d2h_bytes += q.hud_bytes;  // HUD pixels mirrored into the pinned frame
     if (t->cfg.box_overlay && t->inflight_frame && t->inflight_mirrored) {
         // the overlay kernel wrote the box pixels straight into the caller's pinned frame: count them as device->host traffic
         for (int sl : t->active) {
@@ -502,6 +569,56 @@ static vt_status wait_common(vt_tracker* t, vt_result* results) {
     collect_timing(t);
     ++t->frames;
     if (t->hostprof) t->hp[3] += hp1 - hp0, t->hp[4] += hp2 - hp1, t->hp[5] += hp3 - hp2, t->hp[6] += now_us() - hp3, ++t->hp_n;
+    return VT_OK;
+}
+
+// ---- probe support --------------------------------------------------------------------------------------------------------------
+void tracker_enable_hud(vt_tracker* t) {
+    if (t && t->graphs.empty()) t->hud_mode = true;  // (the frame's last kernel is part of the captured graph)
+}
+
+// Stages the HUD list of the NEXT submit in the pinned block of the queue slot that submit will use.
+vt_status tracker_set_hud(vt_tracker* t, const HudCmd* cmds, int n) {
+    if (!t || !t->hud_mode || n < 0 || n > kMaxCmds || (n > 0 && !cmds)) {
+        set_error("tracker_set_hud: invalid argument (HUD mode %d, %d commands)", t ? (int)t->hud_mode : -1, n);
+        return VT_ERR_INVALID;
+    }
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    const int slot = (t->q_head + t->q_count) % vt_tracker::kQueue;
+    if (!t->h_hud[slot]) VT_CUDA(cudaHostAlloc(&t->h_hud[slot], sizeof(OverlayCmdDev) * kMaxCmds, cudaHostAllocDefault));
+    int rmw[4] = {0, 0, 0, 0};
+    size_t bytes = 0;
+    for (int i = 0; i < n; ++i) {
+        OverlayCmdDev& d = t->h_hud[slot][i];
+        const vt_overlay_cmd& c = cmds[i].cmd;
+        vt_status st = fill_cmd_dev(c, d);
+        if (st != VT_OK) return st;
+        d.cond = cmds[i].cond, d.from_result = cmds[i].from_result;
+        if (d.from_result == VT_HUD_SCORE_TEXT) {  // digit and '%' glyphs for the device-side "{:.0}%" of the score
+            if (d.nchar > 32) {
+                set_error("tracker_set_hud: score text prefix too long");
+                return VT_ERR_INVALID;
+            }
+            for (int k = 0; k <= 10; ++k) {
+                uint8_t rows[7];
+                const int ch = k < 10 ? '0' + k : '%';
+                if (vt_glyph_rows(ch, rows) == 0) d.known[kHudDigitSlot + k] = 1, memcpy(d.glyph[kHudDigitSlot + k], rows, 7);
+            }
+        }
+        if (c.kind == VT_OV_BACKGROUND && format_is_luma(t->fmt) && c.x >= 0 && c.y >= 0 && c.w > 0 && c.h > 0) {
+            // the luma background dim reads before it writes (src/nv12_convert.rs:324-343): that region must be on the device
+            const int x1 = (int)std::min<long long>((long long)c.x + c.w, t->W), y1 = (int)std::min<long long>((long long)c.y + c.h, t->H);
+            if (rmw[2] <= rmw[0]) rmw[0] = c.x, rmw[1] = c.y, rmw[2] = x1, rmw[3] = y1;
+            else rmw[0] = std::min(rmw[0], c.x), rmw[1] = std::min(rmw[1], c.y), rmw[2] = std::max(rmw[2], x1), rmw[3] = std::max(rmw[3], y1);
+            bytes += (size_t)std::max(0, x1 - c.x) * std::max(0, y1 - c.y);
+        } else if (c.kind == VT_OV_TEXT) {
+            bytes += (size_t)35 * std::max(c.a, 0) * std::max(c.a, 0) * d.nchar;
+        } else {
+            bytes += 1024;  // rect / crosshair / cursor / selection outlines
+        }
+    }
+    t->hud_next_n = n, t->hud_next_bytes = bytes;
+    memcpy(t->hud_next_rmw, rmw, sizeof(rmw));
     return VT_OK;
 }
 
@@ -588,6 +705,16 @@ vt_status vt_tracker_submit(vt_tracker* t, uint8_t* frame, size_t len) {
     VT_CUDA(cudaSetDevice(t->cfg.device));
     return submit_common(t, frame, nullptr, len);
 }
+
+}  // extern "C"
+namespace vt {
+vt_status tracker_submit_hud_only(vt_tracker* t, uint8_t* frame, size_t len) {
+    if (!t || !frame) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    return submit_common(t, frame, nullptr, len, false);
+}
+}  // namespace vt
+extern "C" {
 
 vt_status vt_tracker_submit_device(vt_tracker* t, uint8_t* d_frame, size_t len) {
     if (!t || !d_frame) return VT_ERR_INVALID;

@@ -100,9 +100,16 @@ struct vt_tracker {
     size_t res_block_bytes = 0;
     unsigned long long *d_stamps = nullptr, *h_stamps = nullptr;
     int* h_tc_err = nullptr;
-    const uint8_t** d_frame_slot = nullptr;  // device cell: address of the frame the step reads (d_frame, or the caller's device frame)
-    uint8_t** d_host_slot = nullptr;   // device cell: address of the caller's pinned host frame for the zero-copy overlay mirror (or null)
-    uint32_t** d_hblk_slot = nullptr;  // device cell: address of the pinned host result block of the frame's queue slot
+    FrameCtl* d_ctl = nullptr;         // per-frame control block (frame / host frame / result block addresses, valid windows, HUD list)
+    // probe HUD (host_state.cpp): the frame's last kernel runs a per-frame command list; the list of the NEXT submit is staged in the
+    // pinned block of that submit's queue slot by tracker_set_hud()
+    int win_shrink = 0;                // diagnostics (VT_B200_WINDOW_SHRINK=px at create): upload windows that are too small on purpose,
+                                       // so that the crop kernel's fall-back reads from the pinned host frame are exercised
+    bool hud_mode = false;
+    OverlayCmdDev* h_hud[2] = {nullptr, nullptr};
+    int hud_next_n = 0;
+    int hud_next_rmw[4] = {0, 0, 0, 0};  // region the list reads before it writes (NV12 background dim): x0, y0, x1, y1; empty = none
+    size_t hud_next_bytes = 0;            // pixels the list touches (device -> host accounting)
     bool inflight_mirrored = false;
     float* d_maps = nullptr;
     OverlayCmdDev *d_cmds = nullptr, *h_cmds = nullptr;
@@ -156,6 +163,7 @@ struct vt_tracker {
         uint8_t* frame = nullptr;  // caller's host frame (null for device-resident frames)
         size_t len = 0;
         bool mirrored = false, pageable = false;
+        size_t hud_bytes = 0;      // pixels this frame's HUD list touches
         std::chrono::steady_clock::time_point t_submit;
     } q[kQueue];
     int q_head = 0, q_count = 0;
@@ -178,6 +186,8 @@ struct vt_tracker {
 namespace vt {
 
 bool is_pinned(const void* p);
+// vt_overlay_cmd -> device form (glyph rows resolved); VT_ERR_GLYPH for an unknown character in strict mode
+vt_status fill_cmd_dev(const vt_overlay_cmd& c, OverlayCmdDev& d);
 void bind_slot(vt_tracker* t, int slot);
 vt_status upload_frame(vt_tracker* t, const uint8_t* frame, size_t len, bool allow_window = false, bool device_src = false,
                        cudaStream_t stream = nullptr);

@@ -118,10 +118,23 @@ __device__ __forceinline__ unsigned long long device_time_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
     return t;
 }
-cudaError_t launch_stamp(unsigned long long* stamp, const uint8_t** frame_slot, const uint8_t* frame, uint8_t** host_slot, uint8_t* host_frame,
-                         uint32_t** hblk_slot, uint32_t* hblk, cudaStream_t s);
-// last kernel of a frame: result block -> the pinned host block whose address stamp_kernel put into *hblk_slot (zero-copy stores)
-cudaError_t launch_publish(const void* d_blk, uint32_t* const* hblk_slot, size_t bytes, cudaStream_t s, bool pdl);
+// Per-frame control block in device memory: the addresses and parameters that change from frame to frame reach the kernels of the
+// (captured once, replayed) per-frame graph through it.  Written by stamp_kernel at the start of every frame, outside the graph.
+struct OverlayCmdDev;
+constexpr int kMaxWin = 16;
+struct FrameCtl {
+    const uint8_t* frame;      // device frame this step reads: the handle's own buffer, or the caller's device frame tracked in place
+    uint8_t* host_frame;       // the caller's PINNED host frame (device-mapped under UVA) or null: zero-copy target of the overlay mirror
+                               // and the crop kernel's fall-back source for pixels outside the uploaded windows
+    uint32_t* hblk;            // pinned host result block of the frame's queue slot
+    const OverlayCmdDev* hud;  // this frame's overlay command list (probe HUD) in pinned host memory, n_hud entries
+    int32_t n_hud;
+    int32_t n_win;             // -1: the whole device frame holds this frame; else win[i] = the region that does, for active target i
+    int32_t win[kMaxWin][4];   // x0, y0, x1, y1 (exclusive), even-aligned
+};
+cudaError_t launch_stamp(unsigned long long* stamp, FrameCtl* d_ctl, const FrameCtl& ctl, cudaStream_t s);
+// last kernel of a frame: result block -> the pinned host block ctl->hblk (zero-copy stores)
+cudaError_t launch_publish(const void* d_blk, const FrameCtl* d_ctl, size_t bytes, cudaStream_t s, bool pdl);
 
 // ---- pixel kernels (pixel.cu) ------------------------------------------------------------------
 struct FrameDesc {
@@ -129,10 +142,10 @@ struct FrameDesc {
     int32_t width, height;
     int32_t format;        // vt_format
     int32_t valid;         // 0: buffer was short -> black image (src/nv12_convert.rs:48-50)
-    // When non-null the frame address is read from this device cell instead of `data`: the per-frame graph is captured once,
-    // while vt_tracker_update_device tracks straight out of the caller's device frame (no device->device copy) by letting the
-    // per-frame stamp kernel store the caller's pointer here.
-    const uint8_t* const* data_slot;
+    // When non-null the frame address (and the valid windows / host fall-back) are read from this per-frame control block instead
+    // of `data`: the per-frame graph is captured once, while vt_tracker_update_device tracks straight out of the caller's device frame
+    // (no device->device copy) and window uploads change from frame to frame.
+    const FrameCtl* ctl;
     int32_t pad_plus1;     // App. A.7: 1 = the crop treats the last column / row of the frame as padding (older OpenCV: padR = x2-W+1)
 };
 
@@ -155,14 +168,39 @@ struct OverlayCmdDev {     // device-side copy of vt_overlay_cmd with resolved g
     uint8_t r, g, b, nchar;
     uint8_t glyph[48][7];  // rows per character; 0xFF in row 0 marks "unknown: skip"
     uint8_t known[48];
+    // per-frame HUD lists (probe): the frame's outcome is only known on the device when the overlay kernel runs, so the host queues the
+    // commands of both outcomes and the kernel picks:
+    uint8_t cond;          // 0 always; 1 only when the gate passed (status ok && success && score > gate); 2 only when it did not
+    uint8_t from_result;   // 0 as given; 1 RECT = the result's bbox; 2 CROSSHAIR at the bbox centre; 3 TEXT + "<round(score*100)>%"
+                           //   (digit glyphs '0'..'9' in glyph[37..46], '%' in glyph[47])
+    uint8_t pad_[2];
 };
+enum { VT_HUD_ALWAYS = 0, VT_HUD_IF_PASS = 1, VT_HUD_IF_FAIL = 2 };
+enum { VT_HUD_GIVEN = 0, VT_HUD_RESULT_RECT = 1, VT_HUD_RESULT_CROSS = 2, VT_HUD_SCORE_TEXT = 3 };
+constexpr int kHudDigitSlot = 37, kHudPercentSlot = 47;
 cudaError_t launch_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const OverlayCmdDev* d_cmds, int n,
                            cudaStream_t s);
 // device-side box overlay straight from the decode result (rect thickness 3 + crosshair 15, src/pipeline.rs:165-168)
-cudaError_t launch_box_overlay(uint8_t* d_frame, size_t len, int width, int height, int format, const DeviceResult* d_res,
-                               const int32_t* d_slots, int n, float gate, uint8_t* const* host_slot, unsigned long long* stamp_end,
-                               cudaStream_t s, uint8_t* const* frame_slot = nullptr, bool pdl = false, const void* d_blk = nullptr,
-                               uint32_t* const* hblk_slot = nullptr, size_t blk_bytes = 0);  // d_blk..: also publishes the result block
+// also the frame's last kernel: runs the per-frame HUD list of the control block (if any), mirrors the touched pixels into the pinned
+// host frame and publishes the result block.  draw_box = 0: HUD list only (probe: the box is part of the list).  n = 0 is legal with
+// a HUD list (frames on which no tracker ran).
+cudaError_t launch_box_overlay(size_t len, int width, int height, int format, const DeviceResult* d_res, const int32_t* d_slots, int n,
+                               float gate, const FrameCtl* d_ctl, unsigned long long* stamp_end, cudaStream_t s, bool pdl, const void* d_blk,
+                               size_t blk_bytes, int draw_box);
+
+// ---- probe support (tracker_frame.cu; used by host_state.cpp) -----------------------------------------------------------------
+// One synchronisation per probed frame: the HUD of src/pipeline.rs:125-174 is queued BEFORE the frame's result exists, as the
+// commands of both outcomes; the frame's last kernel picks by the gate and takes box / score digits from the decode result.
+struct HudCmd {
+    vt_overlay_cmd cmd;
+    uint8_t cond;         // VT_HUD_ALWAYS / VT_HUD_IF_PASS / VT_HUD_IF_FAIL
+    uint8_t from_result;  // VT_HUD_GIVEN / VT_HUD_RESULT_RECT / VT_HUD_RESULT_CROSS / VT_HUD_SCORE_TEXT
+};
+void tracker_enable_hud(vt_tracker* t);                                   // before the handle's first frame
+vt_status tracker_set_hud(vt_tracker* t, const HudCmd* cmds, int n);      // the list of the NEXT submit on this handle
+// a frame on which no tracker runs (SELECT / LOST states): upload what the list reads, draw, mirror, publish — then vt_tracker_wait
+vt_status tracker_submit_hud_only(vt_tracker* t, uint8_t* frame, size_t len);
+bool frame_is_pinned(const void* p);
 
 // ---- ViT kernels (vit.cu) ----------------------------------------------------------------------
 struct GemmArgs {

@@ -26,12 +26,31 @@ def _select(ctx_g, ctx_o, api, moves1, moves2):
         ctx_o.handle_command({0: "up", 1: "down", 2: "left", 3: "right"}[c], fast)
 
 
-def test_context_flow_nv12(api, oracle, weight_dir):
+class FrameMem:
+    """Where the probed frame lives: pageable numpy memory (two-step probe: update, then overlay commands + row copies) or pinned
+    memory (one synchronisation per frame: HUD queued with the frame, drawn by the frame's last kernel, mirrored zero-copy)."""
+
+    def __init__(self, api, mode, nbytes):
+        self.pin = api.PinnedBuffer(nbytes) if mode != "pageable" else None
+
+    def load(self, fr):
+        if self.pin is None:
+            return fr.copy()
+        self.pin.array[:] = fr
+        return self.pin.array
+
+
+MEM_MODES = ["pageable", "pinned", "pinned_window"]
+
+
+@pytest.mark.parametrize("mem", MEM_MODES)
+def test_context_flow_nv12(api, oracle, weight_dir, mem):
     spec = synth.CONFIGS["cfg1"]
     W, H = spec.width, spec.height
     st = synth.SyntheticStream(spec)
     wpath = weights.ensure_weight_file("nano", weight_dir)
-    g = api.TrackerContext.new(wpath, W, H, fmt="nv12")
+    g = api.TrackerContext.new(wpath, W, H, fmt="nv12", upload_window=(mem == "pinned_window"))
+    fm = FrameMem(api, mem, st.frame_bytes())
     otrk = oracle.VitTrack(wpath, threads=8)
     o = oracle.TrackerContext(otrk, W, H)
     U = api.UserCommand
@@ -48,7 +67,7 @@ def test_context_flow_nv12(api, oracle, weight_dir):
         nonlocal n
         fr = st.frame(n)
         n += 1
-        got = fr.copy()
+        got = fm.load(fr)
         g.probe(got, hud)
         rgb = oracle.nv12_to_rgb(fr, W, H, 8)
         bb = o.process_frame(rgb)
@@ -93,9 +112,25 @@ def test_context_flow_nv12(api, oracle, weight_dir):
     assert g.state_name() == "TRACKING"
     for _ in range(10):
         frame()
+    # loss: the search window leaves the frame (≙ update Err -> Lost, src/tracker_context.rs:134-138), HUD shows LOST, no box
+    g.tracker.set_rect((-5000, -5000, 20, 20))
+    otrk.rect = (-5000, -5000, 20, 20)
+    frame()
+    assert g.state_name() == "LOST"
+    for _ in range(3):
+        frame()
     cmd(U.Cancel)
     frame()
     assert g.state_name() == "SELECT START" and g.current_bbox is None
+    # a confirm frame whose init + update fails the gate resets the selection (src/tracker_context.rs:100-109)
+    cmd(U.Confirm)
+    frame()
+    for _ in range(30):
+        cmd(U.MoveLeft, True)      # far left: the selection box lies on the background, away from the target
+    cmd(U.MoveUp, True)
+    cmd(U.Confirm)
+    frame()
+    assert g.state_name() == o.state_name()
 
 
 def test_context_lost_and_auto_reset(api, weight_dir):
@@ -120,13 +155,15 @@ def test_context_lost_and_auto_reset(api, weight_dir):
     assert g.state_name() == "SELECT START" and g.lost_frames == 61
 
 
-def test_context_flow_rgb24(api, oracle, weight_dir):
+@pytest.mark.parametrize("mem", MEM_MODES)
+def test_context_flow_rgb24(api, oracle, weight_dir, mem):
     """The path main() actually runs (src/pipeline_ir.rs): RGB24 640x512, RGB overlay set."""
     spec = synth.CONFIGS["cfg3"]
     W, H = spec.width, spec.height
     st = synth.SyntheticStream(spec)
     wpath = weights.ensure_weight_file("nano", weight_dir)
-    g = api.TrackerContext.new(wpath, W, H, fmt="rgb24")
+    g = api.TrackerContext.new(wpath, W, H, fmt="rgb24", upload_window=(mem == "pinned_window"))
+    fm = FrameMem(api, mem, st.frame_bytes())
     otrk = oracle.VitTrack(wpath, threads=8)
     o = oracle.TrackerContext(otrk, W, H)
     U = api.UserCommand
@@ -140,7 +177,7 @@ def test_context_flow_rgb24(api, oracle, weight_dir):
             continue
         fr = st.frame(n).reshape(-1)
         n += 1
-        got = fr.copy()
+        got = fm.load(fr)
         g.probe(got, hud)
         bb = o.process_frame(fr.reshape(H, W, 3))
         ref = fr.copy()
@@ -161,6 +198,42 @@ def test_context_flow_rgb24(api, oracle, weight_dir):
         assert g.state_name() == name
         assert np.array_equal(got, ref), (n, name, int((got != ref).sum()))
     assert g.state_name() == "TRACKING"
+
+
+def test_probe_score_text_rounding_on_device(api, oracle, weight_dir):
+    """The one-synchronisation probe renders "score: NN%" on the device from the fp32 score (round-half-even of score*100, as Rust's
+    {:.0} / printf %.0f): the pinned path must draw the same pixels as the two-step path, which formats the string on the host, over a
+    sequence whose scores differ (wild weights) — and through the live (timing dependent) HUD path nothing may crash."""
+    spec = synth.CONFIGS["cfg1"]
+    W, H = spec.width, spec.height
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir, variant="wild")
+    a = api.TrackerContext.new(wpath, W, H, fmt="nv12", upload_window=True)
+    b = api.TrackerContext.new(wpath, W, H, fmt="nv12")
+    U = api.UserCommand
+    pin = api.PinnedBuffer(st.frame_bytes())
+    hud = ("FPS: 59", "conv:0.0ms trk:0.3ms")
+    scores = set()
+    for n in range(14):
+        if n in (0, 1):
+            for c in (a, b):
+                if n == 1:
+                    c.handle_command(U.MoveRight, True)
+                    c.handle_command(U.MoveDown, True)
+                c.handle_command(U.Confirm)
+        fr = st.frame(n)
+        pin.array[:] = fr
+        pg = fr.copy()
+        a.probe(pin.array, hud)
+        b.probe(pg, hud)
+        assert a.state_name() == b.state_name() and a.current_score == b.current_score, n
+        assert np.array_equal(pin.array, pg), (n, a.state_name(), int((pin.array != pg).sum()))
+        scores.add(round(a.current_score * 100))
+    assert a.state_name() == "TRACKING" and len(scores) >= 2
+    for n in range(14, 18):                      # live HUD strings (timing dependent: no pixel comparison)
+        pin.array[:] = st.frame(n)
+        a.probe(pin.array)
+    assert a.state_name() == "TRACKING" and a.tracker.timing().fps > 0
 
 
 @pytest.mark.gpu

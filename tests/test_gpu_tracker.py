@@ -643,6 +643,50 @@ def test_window_upload_equals_full_upload(api, weight_dir, fmt, cfg):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fmt,cfg", [("nv12", "cfg1"), ("rgb24", "cfg3")])
+def test_window_miss_falls_back_to_the_pinned_host_frame(api, weight_dir, monkeypatch, fmt, cfg):
+    """Window uploads are predictions when a frame is in flight (rect_last on the host lags by one frame): whatever the uploaded
+    window misses, the crop kernel reads from the caller's pinned frame (zero-copy), so results never depend on the prediction.
+    Forced here by uploading windows that are 60 px too small on every side (VT_B200_WINDOW_SHRINK): synchronous and pipelined
+    results and overlay pixels must equal the whole-frame upload."""
+    spec = synth.CONFIGS[cfg]
+    st = synth.SyntheticStream(spec)
+    wpath = weights.ensure_weight_file("nano", weight_dir, variant="wild")
+    n = 8
+    frames = [np.asarray(st.frame(i)).reshape(-1) for i in range(n)]
+    box = api.BBox(*st.target_boxes(0)[0])
+    ref = api.VitTrack.new(wpath, spec.width, spec.height, fmt=fmt, box_overlay=True, gemm_mode=1, upload_window=False)
+    monkeypatch.setenv("VT_B200_WINDOW_SHRINK", "60")
+    a = api.VitTrack.new(wpath, spec.width, spec.height, fmt=fmt, box_overlay=True, gemm_mode=1, upload_window=True)
+    b = api.VitTrack.new(wpath, spec.width, spec.height, fmt=fmt, box_overlay=True, gemm_mode=1, upload_window=True)
+    monkeypatch.delenv("VT_B200_WINDOW_SHRINK")
+    pr, pa = api.PinnedBuffer(frames[0].size), api.PinnedBuffer(frames[0].size)
+    pins = [api.PinnedBuffer(frames[0].size) for _ in range(n)]
+    for t in (ref, a, b):
+        t.init(frames[0], box)
+    want, want_px = [], []
+    h2d0 = a.timing().h2d_bytes
+    for i in range(n):
+        pr.array[:] = frames[i]
+        pa.array[:] = frames[i]
+        want.append(ref.update(pr.array))
+        assert a.update(pa.array) == want[-1], i                 # synchronous, exact mirror, shrunk window
+        assert np.array_equal(pa.array, pr.array), i
+        want_px.append(pr.array.copy())
+        pins[i].array[:] = frames[i]
+    assert a.timing().h2d_bytes - h2d0 < 0.3 * n * frames[0].size  # the windows really were small
+    got = []
+    b.submit(pins[0].array)
+    for i in range(1, n):                                         # pipelined: lagging mirror, predicted + shrunk windows
+        b.submit(pins[i].array)
+        got.append(b.wait()[0])
+    got.append(b.wait()[0])
+    assert got == want
+    for i in range(n):
+        assert np.array_equal(pins[i].array, want_px[i]), i
+
+
+@pytest.mark.gpu
 def test_bench_workload_teacher_forced_300_frames(api, oracle, weight_dir):
     """The exact bench workload (cfg2, tiny, bf16x3, box overlay, window upload from a pinned frame) against the fp32 oracle over 300
     teacher-forced frames: boxes equal except numerically undecidable floor ties, |dscore| <= 1e-3, overlay pixels as the oracle draws."""
