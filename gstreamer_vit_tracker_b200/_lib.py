@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libvittrack_b200.so")
 VT_OK, VT_ERR_INVALID, VT_ERR_CUDA, VT_ERR_WEIGHTS, VT_ERR_CROP_OUTSIDE, VT_ERR_NOT_INIT, VT_ERR_GLYPH = 0, -1, -2, -3, -4, -5, -6
 VT_FMT_NV12, VT_FMT_RGB24, VT_FMT_GRAY8 = 0, 1, 2
 VT_GEMM_FP32_SIMT, VT_GEMM_TCGEN05_BF16X3, VT_GEMM_TCGEN05_BF16, VT_GEMM_TCGEN05_FP16 = 0, 1, 2, 3
+VT_RUN_HOST_SYNC, VT_RUN_HOST_PIPELINED, VT_RUN_DEVICE_SYNC, VT_RUN_DEVICE_PIPELINED = range(4)
 VT_DECODE_CEIL4, VT_DECODE_4FLOOR = 0, 1
 VT_WINDOW_HANN, VT_WINDOW_ONE_MINUS_HANN = 0, 1
 VT_OV_RECT, VT_OV_CROSSHAIR, VT_OV_TEXT, VT_OV_BACKGROUND, VT_OV_CURSOR, VT_OV_SELECTION = range(6)
@@ -86,6 +87,10 @@ SYMBOLS = {
     "vt_tracker_submit_device": (C.c_int32, [_vp, _vp, C.c_size_t]),
     "vt_tracker_wait": (C.c_int32, [_vp, C.POINTER(vt_result)]),
     "vt_tracker_update_device": (C.c_int32, [_vp, _vp, C.c_size_t, C.POINTER(vt_result)]),
+    "vt_tracker_run_ring": (C.c_int32, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.POINTER(vt_result),
+                                        C.POINTER(C.c_double)]),
+    "vt_context_run_ring": (C.c_int32, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_char_p), _vp,
+                                        C.POINTER(C.c_double)]),
     "vt_tracker_get_rect": (C.c_int32, [_vp, C.c_int32, C.POINTER(vt_bbox)]),
     "vt_tracker_set_rect": (C.c_int32, [_vp, C.c_int32, vt_bbox]),
     "vt_tracker_drop": (C.c_int32, [_vp, C.c_int32]),

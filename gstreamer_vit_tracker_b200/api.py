@@ -233,6 +233,16 @@ class VitTrack:
         check(lib().vt_tracker_update_device(self._h, C.c_void_p(d_ptr), nbytes, self._res), "vt_tracker_update_device")
         return self._results()
 
+    def run_ring(self, base_ptr: int, stride: int, frame_len: int, ring: int, first: int, n: int, mode: int, pristine_ptr: int = 0,
+                 want_latency: bool = False):
+        """n frames of a ring through this handle in one native call (vt_tracker_run_ring; the GIL is released for its duration, so
+        one Python thread per stream drives many streams).  Returns (results of the last frame, latencies in us or None)."""
+        lat = np.empty(n, np.float64) if want_latency else None
+        check(lib().vt_tracker_run_ring(self._h, C.c_void_p(base_ptr), stride, frame_len, ring, first, n, mode,
+                                        C.c_void_p(pristine_ptr) if pristine_ptr else None, self._res,
+                                        lat.ctypes.data_as(C.POINTER(C.c_double)) if want_latency else None), "vt_tracker_run_ring")
+        return self._results(), lat
+
     def get_rect(self, target: int = 0) -> Tuple[int, int, int, int]:
         b = vt_bbox()
         check(lib().vt_tracker_get_rect(self._h, target, C.byref(b)), "vt_tracker_get_rect")
@@ -489,6 +499,16 @@ class TrackerContext:
     @property
     def lost_frames(self) -> int:
         return lib().vt_context_lost_frames(self._h)
+
+    def run_ring(self, base_ptr: int, stride: int, frame_len: int, ring: int, first: int, n: int, hud: Optional[Tuple[str, str]] = None,
+                 pristine_ptr: int = 0, want_latency: bool = False):
+        """n frames of a host ring through vt_probe_frame in one native call (vt_context_run_ring)."""
+        arr = (C.c_char_p * 2)(hud[0].encode(), hud[1].encode()) if hud is not None else None
+        lat = np.empty(n, np.float64) if want_latency else None
+        check(lib().vt_context_run_ring(self._h, C.c_void_p(base_ptr), stride, frame_len, ring, first, n, arr,
+                                        C.c_void_p(pristine_ptr) if pristine_ptr else None,
+                                        lat.ctypes.data_as(C.POINTER(C.c_double)) if want_latency else None), "vt_context_run_ring")
+        return lat
 
     def probe(self, frame: np.ndarray, hud: Optional[Tuple[str, str]] = None) -> None:
         """≙ one invocation of the pad-probe closure (src/pipeline.rs:67-184 / src/pipeline_ir.rs:100-228)."""

@@ -463,6 +463,27 @@ static vt_status probe_one_sync(vt_context* c, uint8_t* frame, size_t len, const
     return VT_OK;
 }
 
+// ≙ the streaming thread invoking the probe once per buffer (src/pipeline.rs:65-67): n frames of a host ring through vt_probe_frame
+vt_status vt_context_run_ring(vt_context* c, uint8_t* frames, size_t stride, size_t frame_len, int32_t ring, int32_t first, int32_t n,
+                              const char* const* hud_override, const uint8_t* pristine, double* latency_us) {
+    if (!c || !c->tracker || !frames || ring <= 0 || first < 0 || n < 0 || frame_len > stride) return VT_ERR_INVALID;
+    const int fmt = c->cfg.format, W = c->frame_width, H = c->frame_height;
+    for (int i = 0; i < n; ++i) {
+        uint8_t* fr = frames + (size_t)((first + i) % ring) * stride;
+        const auto t0 = std::chrono::steady_clock::now();
+        const vt_status st = vt_probe_frame(c, fr, frame_len, hud_override);
+        if (latency_us) latency_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        if (st != VT_OK) return st;
+        if (pristine) {  // HUD block (background 10,10 400x80 resp. the text lines up to x = 410) and the box drawn this frame
+            const uint8_t* clean = pristine + (size_t)((first + i) % ring) * stride;
+            vt::restore_rect_region(fr, clean, fmt, W, H, 10, 10, 412, 92);
+            if (c->state == AppState::Tracking && c->has_bbox) vt::restore_box_region(fr, clean, fmt, W, H, c->current_bbox);
+            else if (c->state == AppState::Selecting) vt::restore_rect_region(fr, clean, fmt, W, H, 0, 0, W, H);  // cursor / selection: rare, whole frame
+        }
+    }
+    return VT_OK;
+}
+
 // ≙ the pad-probe closure body: src/pipeline.rs:67-184 (NV12) / src/pipeline_ir.rs:100-228 (RGB24)
 vt_status vt_probe_frame(vt_context* c, uint8_t* frame, size_t len, const char* const* hud_override) {
     if (!c || !c->tracker || !frame) return VT_ERR_INVALID;

@@ -572,6 +572,26 @@ static vt_status wait_common(vt_tracker* t, vt_result* results) {
     return VT_OK;
 }
 
+// ---- ring replay support ----------------------------------------------------------------------------------------------------------
+// [x0, x1) x [y0, y1) of the drawable plane (Y plane / luma for NV12 and GRAY8, the RGB image otherwise), clipped to the frame
+void restore_rect_region(uint8_t* frame, const uint8_t* clean, int fmt, int W, int H, long long x0, long long y0, long long x1, long long y1) {
+    x0 = std::max(x0, 0LL), y0 = std::max(y0, 0LL), x1 = std::min<long long>(x1, W), y1 = std::min<long long>(y1, H);
+    if (x1 <= x0 || y1 <= y0) return;
+    const size_t bpp = format_is_luma(fmt) ? 1 : 3, pitch = (size_t)W * bpp;
+    for (long long y = y0; y < y1; ++y) {
+        const size_t o = (size_t)y * pitch + (size_t)x0 * bpp;
+        memcpy(frame + o, clean + o, (size_t)(x1 - x0) * bpp);
+    }
+}
+// a box overlay touches the box outline (inclusive x..x+w, y..y+h in the luma formats) and a +-15 px crosshair at its centre
+void restore_box_region(uint8_t* frame, const uint8_t* clean, int fmt, int W, int H, const vt_bbox& b) {
+    if (b.width < 0 || b.height < 0 || b.width > 4 * W || b.height > 4 * H) {  // wrapped / absurd geometry: restore everything
+        restore_rect_region(frame, clean, fmt, W, H, 0, 0, W, H);
+        return;
+    }
+    restore_rect_region(frame, clean, fmt, W, H, (long long)b.x - 16, (long long)b.y - 16, (long long)b.x + b.width + 17, (long long)b.y + b.height + 17);
+}
+
 // ---- probe support --------------------------------------------------------------------------------------------------------------
 void tracker_enable_hud(vt_tracker* t) {
     if (t && t->graphs.empty()) t->hud_mode = true;  // (the frame's last kernel is part of the captured graph)
@@ -750,6 +770,57 @@ vt_status vt_tracker_update_device(vt_tracker* t, uint8_t* d_frame, size_t len, 
     vt_status st = submit_common(t, nullptr, d_frame, len);
     if (st != VT_OK) return st;
     return wait_common(t, results);
+}
+
+// ≙ the streaming thread's per-buffer loop (src/pipeline.rs:65-67), natively: see include/vt_tracker.h
+vt_status vt_tracker_run_ring(vt_tracker* t, uint8_t* frames, size_t stride, size_t frame_len, int32_t ring, int32_t first, int32_t n, int32_t mode,
+                              const uint8_t* pristine, vt_result* last, double* latency_us) {
+    if (!t || !frames || ring <= 0 || first < 0 || n < 0 || mode < VT_RUN_HOST_SYNC || mode > VT_RUN_DEVICE_PIPELINED || frame_len > stride) {
+        set_error("vt_tracker_run_ring: invalid argument");
+        return VT_ERR_INVALID;
+    }
+    if (t->q_count) {
+        set_error("vt_tracker_run_ring: frames are in flight; drain them first");
+        return VT_ERR_INVALID;
+    }
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    const bool device = mode >= VT_RUN_DEVICE_SYNC, pipelined = mode == VT_RUN_HOST_PIPELINED || mode == VT_RUN_DEVICE_PIPELINED;
+    std::vector<vt_result> res((size_t)t->maxT);
+    auto fr = [&](int i) { return frames + (size_t)((first + i) % ring) * stride; };
+    auto restore = [&](int i) {  // undo what the box overlay of frame i drew (host rings only)
+        if (!pristine || device || !t->cfg.box_overlay) return;
+        const uint8_t* clean = pristine + (size_t)((first + i) % ring) * stride;
+        for (int s : t->active) {
+            const vt_result& r = res[s];
+            if (r.status == VT_OK && r.success && r.score > t->cfg.overlay_gate) restore_box_region(fr(i), clean, t->fmt, t->W, t->H, r.bbox);
+        }
+    };
+    vt_status st = VT_OK;
+    if (!pipelined) {
+        for (int i = 0; i < n && st == VT_OK; ++i) {
+            const auto t0 = std::chrono::steady_clock::now();
+            st = submit_common(t, device ? nullptr : fr(i), device ? fr(i) : nullptr, frame_len);
+            if (st == VT_OK) st = wait_common(t, res.data());
+            if (latency_us) latency_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+            restore(i);
+        }
+    } else {
+        for (int i = 0; i < n && st == VT_OK; ++i) {
+            st = submit_common(t, device ? nullptr : fr(i), device ? fr(i) : nullptr, frame_len);
+            if (st == VT_OK && i > 0) {
+                st = wait_common(t, res.data());
+                restore(i - 1);
+            }
+        }
+        while (t->q_count && st == VT_OK) {
+            st = wait_common(t, res.data());
+            restore(n - 1);
+        }
+        if (st != VT_OK)  // leave no frame in flight behind an error
+            while (t->q_count) wait_common(t, nullptr);
+    }
+    if (last && st == VT_OK && n > 0) memcpy(last, res.data(), sizeof(vt_result) * (size_t)t->maxT);
+    return st;
 }
 
 vt_status vt_tracker_get_rect(vt_tracker* t, int32_t target, vt_bbox* out) {

@@ -201,6 +201,9 @@ vt_status tracker_set_hud(vt_tracker* t, const HudCmd* cmds, int n);      // the
 // a frame on which no tracker runs (SELECT / LOST states): upload what the list reads, draw, mirror, publish — then vt_tracker_wait
 vt_status tracker_submit_hud_only(vt_tracker* t, uint8_t* frame, size_t len);
 bool frame_is_pinned(const void* p);
+// copies the region of a frame that a box overlay (rect thickness 3 + crosshair 15) / the probe HUD touched back from a clean copy
+void restore_box_region(uint8_t* frame, const uint8_t* clean, int fmt, int W, int H, const vt_bbox& b);
+void restore_rect_region(uint8_t* frame, const uint8_t* clean, int fmt, int W, int H, long long x0, long long y0, long long x1, long long y1);
 
 // ---- ViT kernels (vit.cu) ----------------------------------------------------------------------
 struct GemmArgs {

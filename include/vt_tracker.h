@@ -148,6 +148,18 @@ vt_status vt_tracker_wait(vt_tracker* t, vt_result* results);
  * probe (src/pipeline.rs:90-100,165-168) on a device surface. */
 vt_status vt_tracker_update_device(vt_tracker* t, uint8_t* d_frame, size_t len, vt_result* results);
 
+/* The per-buffer loop of a streaming thread, run natively (≙ the GStreamer streaming thread invoking the probe once per buffer,
+ * src/pipeline.rs:65-67): n frames of a ring (`ring` frames of frame_len bytes, `stride` bytes apart, starting at index `first`,
+ * wrapping) go through this handle.  `frames` is host memory for the HOST modes (pinned for pipelining) and device memory for the
+ * DEVICE modes.  SYNC = vt_tracker_update[_device] per frame; PIPELINED = vt_tracker_submit[_device] / vt_tracker_wait with two frames
+ * in flight.  `pristine` (nullable, host modes with cfg.box_overlay): the same ring without overlays — after a frame's wait() the
+ * pixels its box overlay touched are restored from it, so a ring can be replayed on clean frames.  latency_us (nullable, n entries):
+ * wall time from handing frame i in to having its result (SYNC modes).  last (nullable): results[max_targets] of the final frame.
+ * Multi-stream drivers call this from one host thread per stream. */
+typedef enum { VT_RUN_HOST_SYNC = 0, VT_RUN_HOST_PIPELINED = 1, VT_RUN_DEVICE_SYNC = 2, VT_RUN_DEVICE_PIPELINED = 3 } vt_run_mode;
+vt_status vt_tracker_run_ring(vt_tracker* t, uint8_t* frames, size_t stride, size_t frame_len, int32_t ring, int32_t first, int32_t n,
+                              int32_t mode, const uint8_t* pristine, vt_result* last, double* latency_us);
+
 /* tracker state access (≙ rect_last inside VitTrack; used by tests for teacher forcing) */
 vt_status vt_tracker_get_rect(vt_tracker* t, int32_t target, vt_bbox* out);
 vt_status vt_tracker_set_rect(vt_tracker* t, int32_t target, vt_bbox box);
@@ -305,6 +317,11 @@ vt_tracker* vt_context_tracker(vt_context* c);
  * NULL) replaces the timing-dependent HUD strings so that pixel parity is testable:
  * {fps_line, timing_line}. */
 vt_status vt_probe_frame(vt_context* c, uint8_t* frame, size_t len, const char* const* hud_override);
+
+/* The same loop over vt_probe_frame (the drop-in call): n frames of a host ring through the context, HUD drawn into every frame.
+ * `pristine` (nullable): after each probe the HUD region and the box of that frame are restored from it. */
+vt_status vt_context_run_ring(vt_context* c, uint8_t* frames, size_t stride, size_t frame_len, int32_t ring, int32_t first, int32_t n,
+                              const char* const* hud_override, const uint8_t* pristine, double* latency_us);
 
 #ifdef __cplusplus
 }
