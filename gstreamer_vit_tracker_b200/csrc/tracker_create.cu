@@ -14,7 +14,6 @@ void set_error(const char* fmt, ...) {
 }
 
 static std::mutex g_weight_mutex;
-std::atomic<int> g_live_handles[kMaxDevices];
 static std::map<std::string, std::weak_ptr<WeightSet>> g_weight_cache;
 
 bool frame_is_pinned(const void* p) { return is_pinned(p); }
@@ -187,7 +186,7 @@ void vt_tracker_destroy(vt_tracker* t) {
                 (unsigned long long)t->hp_n, t->hp[0] / n, t->hp[1] / n, t->hp[2] / n, t->hp[3] / n, t->hp[4] / n, t->hp[5] / n, t->hp[6] / n);
     }
     cudaSetDevice(t->cfg.device);
-    if (t->counted) g_live_handles[t->cfg.device].fetch_sub(1);
+    if (t->counted) registry_add(t->cfg.device, -1);
     if (t->stream) cudaStreamSynchronize(t->stream);
     for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
     for (auto& e : t->ev)
@@ -531,7 +530,10 @@ vt_status vt_tracker_create(const vt_config* cfg_in, vt_tracker** out) {
     t->inited.assign(B, 0);
     VT_TRY(cudaStreamSynchronize(t->stream));
 #undef VT_TRY
-    if (t->cfg.device >= 0 && t->cfg.device < kMaxDevices) g_live_handles[t->cfg.device].fetch_add(1), t->counted = true;
+    if (t->cfg.device >= 0 && t->cfg.device < kMaxDevices) {
+        registry_add(t->cfg.device, +1), t->counted = true;
+        registry_sweep(t->cfg.device);
+    }
     *out = t;
     return VT_OK;
 }
@@ -543,6 +545,7 @@ int32_t vt_tracker_model_dim(const vt_tracker* t, int32_t which) {
         case 1: return t->depth;
         case 2: return t->heads;
         case 3: return t->hidden;
+        case 5: return registry_total(t->cfg.device);
         default: return t->head_ch;
     }
 }

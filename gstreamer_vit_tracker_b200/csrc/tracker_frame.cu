@@ -188,7 +188,7 @@ static vt_status run_forward(vt_tracker* t) {
     if (n == 0) return VT_OK;
     int launches = 0;
     const int dev = t->cfg.device;
-    const bool spread = t->spread_ok && dev >= 0 && dev < kMaxDevices && g_live_handles[dev].load(std::memory_order_relaxed) <= kSpreadMaxHandles;
+    const bool spread = t->spread_ok && dev >= 0 && dev < kMaxDevices && registry_total(dev) <= kSpreadMaxHandles;
     if (!t->cfg.use_cuda_graph || t->debug_capture) {
         vt_status st = enqueue_forward(t, n, launches, true, false, spread);
         t->kernel_launches += launches;

@@ -48,11 +48,11 @@ struct WeightSet {
         if (w_f16) cudaFree(w_f16);
     }
 };
-// Live tracker handles per device.  With one or two streams on a GPU most SMs idle during a frame, and the "spread" GEMM forms trade
-// them for latency (tiles replicated so that each replica stores a share of the epilogue output); with more streams SM time is the
-// budget and the plain forms are used.  Read at every frame: the graph variant follows the handle count.
+// Live tracker handles per device, counted across processes (handle_registry.cpp).  With one or two streams on a GPU most SMs idle
+// during a frame, and the "spread" GEMM forms trade them for latency (tiles replicated so that each replica stores a share of the
+// epilogue output); with more streams SM time is the budget and the plain forms are used.  Read at every frame: the graph variant
+// follows the handle count.
 constexpr int kMaxDevices = 64, kSpreadMaxHandles = 2, kUnchainTargets = 8;
-extern std::atomic<int> g_live_handles[kMaxDevices];
 
 enum { EV_START = 0, EV_H2D, EV_PRE, EV_VIT, EV_DEC, EV_OVL, EV_END, EV_COUNT };
 

@@ -188,6 +188,11 @@ cudaError_t launch_box_overlay(size_t len, int width, int height, int format, co
                                float gate, const FrameCtl* d_ctl, unsigned long long* stamp_end, cudaStream_t s, bool pdl, const void* d_blk,
                                size_t blk_bytes, int draw_box);
 
+// ---- live handles per GPU across processes (handle_registry.cpp) ----------------------------------------------------------------
+void registry_add(int device, int delta);
+int registry_total(int device);
+void registry_sweep(int device);
+
 // ---- probe support (tracker_frame.cu; used by host_state.cpp) -----------------------------------------------------------------
 // One synchronisation per probed frame: the HUD of src/pipeline.rs:125-174 is queued BEFORE the frame's result exists, as the
 // commands of both outcomes; the frame's last kernel picks by the gate and takes box / score digits from the decode result.

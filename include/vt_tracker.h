@@ -172,7 +172,9 @@ vt_status vt_tracker_drop(vt_tracker* t, int32_t target); /* forget a target */
  *   tokens       float[320*D]      final-LayerNorm token features */
 vt_status vt_tracker_debug_read(vt_tracker* t, int32_t target, float* search_blob, float* template_blob,
                                 float* conf_win, float* size_map, float* off_map, float* tokens);
-int32_t vt_tracker_model_dim(const vt_tracker* t, int32_t which); /* 0 D, 1 depth, 2 heads, 3 hidden, 4 head_ch */
+int32_t vt_tracker_model_dim(const vt_tracker* t, int32_t which); /* 0 D, 1 depth, 2 heads, 3 hidden, 4 head_ch;
+                                                                      5: tracker handles alive on this handle's GPU, all processes (the
+                                                                         latency / throughput kernel forms switch on it) */
 /* token features [320*D] after the embeddings (which = 0) or after block `which` (1..depth).  Needs
  * cfg.debug_capture = 1 at create time (captures one copy per block; disables graph replay). */
 vt_status vt_tracker_debug_tokens(vt_tracker* t, int32_t target, int32_t which, float* out);

@@ -830,6 +830,40 @@ def test_gray8_input_format(api, oracle, weight_dir):
     assert np.array_equal(fr, want[:W * H])
 
 
+def test_live_handles_are_counted_across_processes(api, weight_dir):
+    """The latency / throughput form switch counts tracker handles per GPU, not per process (one process per stream under torchrun, one
+    pipeline per camera process): handles of other processes are seen, and the slot of a process that died without destroying its
+    handle is reclaimed."""
+    import gc
+    import subprocess
+    import sys
+    gc.collect()
+    w = weights.ensure_weight_file("nano", weight_dir)
+    trk = api.VitTrack.new(w, 640, 360)
+    base = trk.model_dim(5)
+    assert base >= 1
+    child = ("import sys; sys.path.insert(0, %r)\nfrom gstreamer_vit_tracker_b200 import api\n"
+             "t = api.VitTrack.new(%r, 640, 360)\nprint('up', flush=True)\nsys.stdin.readline()\n") % (ROOT, w)
+    procs = [subprocess.Popen([sys.executable, "-c", child], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True) for _ in range(2)]
+    try:
+        for p in procs:
+            assert p.stdout.readline().strip() == "up"
+        assert trk.model_dim(5) == base + 2
+        procs[0].stdin.write("\n")
+        procs[0].stdin.flush()
+        procs[0].wait(timeout=60)              # clean exit: the handle is destroyed
+        procs[1].kill()                        # no destructor runs
+        procs[1].wait(timeout=60)
+        t2 = api.VitTrack.new(w, 640, 360)     # creating a handle sweeps the slots of dead processes
+        assert trk.model_dim(5) == base + 1
+        t2.close()
+        assert trk.model_dim(5) == base
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+
+
 def test_kernel_forms_agree(api, weight_dir, monkeypatch):
     """The latency-mode "spread" forms (used while <= 2 handles are alive on the GPU: FC1 tile computed by three CTAs with one
     64-column slice of the chained FC2 product each, proj folded into the attention kernel, hi / lo replicas of the QKV scatter), the
