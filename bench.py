@@ -56,9 +56,9 @@ def parse_args():
     ap.add_argument("--gemm", default="tcgen05x3", choices=list(GEMM_MODES),
                     help="precision/engine of the dense contractions (tcgen05x3 = bf16 split operands, the parity-safe default)")
     ap.add_argument("--streams-per-gpu", type=int, default=1)
-    ap.add_argument("--ring", type=int, default=384,
-                    help="distinct frames per stream; the bytes the step actually touches (search windows, ~0.45 MB per frame) over the ring "
-                         "must exceed the 126 MB L2: 384 x 0.45 MB = 171 MB (1.19 GB of frames)")
+    ap.add_argument("--ring", type=int, default=0,
+                    help="distinct frames per stream (0 = steps + warmup, at most 1024: no frame is used twice within a timed leg).  The bytes the "
+                         "step actually touches (search windows, ~0.45 MB per frame) over the ring must exceed the 126 MB L2: 660 x 0.45 MB = 297 MB")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 / cfg5 / multi-stream side legs")
     ap.add_argument("--cfg5-streams", type=int, default=64, help="total concurrent streams of the cfg5 leg (sharded over the ranks)")
@@ -79,12 +79,16 @@ def workload_name(args):
 
 def config_dict(args):
     """`config` of the JSON line: the same keys and, for the same flags, the same values in both arms."""
-    ring_n = max(8, min(args.ring, args.steps + args.warmup))
+    ring_n = ring_size(args)
     return {"workload": workload_name(args), "resolution": "1920x1080", "format": "NV12", "targets": 1, "model": args.model,
             "streams_per_gpu": args.streams_per_gpu, "weights": "constructed random-init (SURVEY.md §8c)",
             "call": "probe body per frame: convert + VitTrack::update + HUD overlay (src/pipeline.rs:104-174)",
             "l2": f"inputs larger than L2: every timed leg walks {args.steps + args.warmup} frames per stream out of a ring of {ring_n} distinct "
                   f"1080p frames ({ring_n * 3110400 / 1e6:.0f} MB; 126 MB L2), every frame on clean pixels (overlays are undone / never reused)"}
+
+
+def ring_size(args):
+    return max(8, min(args.ring or 1024, args.steps + args.warmup))
 
 
 def stream_spec(rank, k, args, world):
@@ -223,7 +227,7 @@ def run_reference(args):
         return
     threads = len(os.sched_getaffinity(0)) or 1
     p = CpuProbe(args.model, threads)
-    ring = [p.st.frame(i) for i in range(min(args.ring, args.warmup + args.steps))]
+    ring = [p.st.frame(i) for i in range(ring_size(args))]
     for i in range(args.warmup):
         p.step(ring[i % len(ring)].copy())
     t0 = time.perf_counter()
@@ -305,9 +309,7 @@ class Stream:
         self.host = self.pin.array.reshape(ring_n, self.fb)
         for i in range(ring_n):
             self.host[i] = np.asarray(self.st.frame(i)).reshape(-1)
-        self.pin0 = api.PinnedBuffer(ring_n * self.fb)           # the same ring, never drawn on
-        self.pristine = self.pin0.array.reshape(ring_n, self.fb)
-        self.pristine[:] = self.host
+        self.pristine = self.host.copy()                         # the same ring, never drawn on
         self.dev0 = torch.from_numpy(self.pristine).cuda(local_rank)
         self.dev = torch.empty((dev_frames, self.fb), dtype=torch.uint8, device=f"cuda:{local_rank}")
         self.boxes = self.st.target_boxes(0)
@@ -373,7 +375,7 @@ def run_b200(args):
     cfg_model = weights.MODELS[args.model]
     S = args.streams_per_gpu
     K, Wm = args.steps, args.warmup
-    ring_n = max(8, min(args.ring, K + Wm))
+    ring_n = ring_size(args)
     HUD = None  # live (timing dependent) HUD strings, as the reference draws them
 
     def barrier():
@@ -389,14 +391,16 @@ def run_b200(args):
 
         def worker(si):
             s = streams[si]
+            # a host ring shorter than the leg is replayed: the native loop then undoes every frame's overlay from the clean copy
+            clean = s.pristine.ctypes.data if s.ring_n < offset + n_steps else 0
             if kind == "probe":
-                lat[si] = s.ctx.run_ring(s.host.ctypes.data, s.fb, s.fb, s.ring_n, offset % s.ring_n, n_steps, HUD, s.pristine.ctypes.data, want_lat)
+                lat[si] = s.ctx.run_ring(s.host.ctypes.data, s.fb, s.fb, s.ring_n, offset % s.ring_n, n_steps, HUD, clean, want_lat)
             elif kind in ("device", "device_sync"):
                 mode = L.VT_RUN_DEVICE_PIPELINED if kind == "device" else L.VT_RUN_DEVICE_SYNC
                 _, lat[si] = s.trk.run_ring(s.dev.data_ptr(), s.fb, s.fb, s.dev_frames, offset % s.dev_frames, n_steps, mode, 0, want_lat)
             else:
                 mode = L.VT_RUN_HOST_PIPELINED if kind == "host_pipelined" else L.VT_RUN_HOST_SYNC
-                _, lat[si] = s.trk.run_ring(s.host.ctypes.data, s.fb, s.fb, s.ring_n, offset % s.ring_n, n_steps, mode, s.pristine.ctypes.data, want_lat)
+                _, lat[si] = s.trk.run_ring(s.host.ctypes.data, s.fb, s.fb, s.ring_n, offset % s.ring_n, n_steps, mode, clean, want_lat)
         if len(streams) == 1:
             worker(0)
         else:
@@ -647,14 +651,14 @@ def run_b200(args):
             "roofline_vit_stage": {"achieved": ach_tf, "unit": "TFLOP/s", "frac": (ach_tf / tf_peak) if ach_tf else None, "flops_per_frame": flops,
                                    "stage_ms": stage["vit_ms"], "timing": "device stamps, mean of the last 120 frames"},
             "kernels_in_chain": kern,
-            "roofline_convert": {"kernel": "nv12_to_rgb_vec_kernel", "bound": "hbm", "achieved": cvt_bytes / (cvt_ms * 1e-3) / 1e9, "peak": hbm_peak,
+            "roofline_convert": {"kernel": "nv12_to_rgb_vec4_kernel", "bound": "hbm", "achieved": cvt_bytes / (cvt_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                  "unit": "GB/s", "frac": cvt_bytes / (cvt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                                  "frames_per_launch": nb, "bytes_per_launch": cvt_bytes, "ms_per_launch": cvt_ms, "peak_source": peak_src},
             "clocks": clocks,
         }
         tpx = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpx):
-            out["roofline_convert"]["traffic"] = json.load(open(tpx)).get("nv12_to_rgb_vec_kernel", {}).get("dram_bytes_per_launch")
+            out["roofline_convert"]["traffic"] = json.load(open(tpx)).get("nv12_to_rgb_vec4_kernel", {}).get("dram_bytes_per_launch")
         for k, v in extras.items():
             if isinstance(v, dict) and v.get("vit_tflops"):
                 v["vit_frac_of_bf16_peak"] = v["vit_tflops"] / tf_peak

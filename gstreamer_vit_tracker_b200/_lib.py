@@ -108,6 +108,7 @@ SYMBOLS = {
     "vt_convert_yuy2_rgb_device": (C.c_int32, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.c_int32, C.c_int32, C.c_int32]),
     "vt_resize_rgb": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32]),
     "vt_resize_rgb_device": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32]),
+    "vt_resize_rgb_device_batch": (C.c_int32, [_vp, _vp, C.c_size_t, C.c_int32, C.c_int32, _vp, C.c_size_t, C.c_int32, C.c_int32, C.c_int32]),
     "vt_overlay": (C.c_int32, [_vp, _vp, C.c_size_t, C.POINTER(vt_overlay_cmd), C.c_int32]),
     "vt_overlay_current": (C.c_int32, [_vp, _vp, C.c_size_t, C.POINTER(vt_overlay_cmd), C.c_int32]),
     "vt_timing_get": (C.c_int32, [_vp, C.POINTER(vt_timing)]),

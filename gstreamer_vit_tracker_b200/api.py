@@ -322,6 +322,10 @@ class VitTrack:
     def resize_rgb_device(self, d_in: int, sw: int, sh: int, d_out: int, dw: int, dh: int) -> None:
         check(lib().vt_resize_rgb_device(self._h, C.c_void_p(d_in), sw, sh, C.c_void_p(d_out), dw, dh), "vt_resize_rgb_device")
 
+    def resize_rgb_device_batch(self, d_in: int, stride_in: int, sw: int, sh: int, d_out: int, stride_out: int, dw: int, dh: int, n: int) -> None:
+        check(lib().vt_resize_rgb_device_batch(self._h, C.c_void_p(d_in), stride_in, sw, sh, C.c_void_p(d_out), stride_out, dw, dh, n),
+              "vt_resize_rgb_device_batch")
+
     def overlay(self, frame: np.ndarray, cmds: Sequence[vt_overlay_cmd], current: bool = False) -> None:
         arr = (vt_overlay_cmd * len(cmds))(*cmds)
         fn = lib().vt_overlay_current if current else lib().vt_overlay

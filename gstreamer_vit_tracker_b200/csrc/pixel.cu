@@ -4,6 +4,8 @@
 //   K2  crop_resize_norm     ≙ K1 fused with VitTrack's crop/resize/blob (OpenCV TrackerVit semantics)
 //   K9  overlay / box_overlay ≙ draw_*_nv12 (src/nv12_convert.rs:172-343), draw_cursor/draw_selection (src/drawing.rs:5-50),
 //                               draw_*_rgb (src/drawing_rgb.rs:30-128)
+#include <stdlib.h>
+
 #include "vt_internal.h"
 
 namespace vt {
@@ -114,6 +116,67 @@ __global__ void __launch_bounds__(kCvtWarps * 32) nv12_to_rgb_vec_kernel(const u
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1 wide path: W % 16 == 0, H % 4 == 0.  One warp converts a 512-px segment of FOUR rows (two chroma rows): every lane has six
+// 16-byte loads in flight (4 x 16 luma bytes + 2 x 8 chroma pairs = 96 B per thread, 3 KB per warp) before it converts anything —
+// the kernel is a pure stream (4.5 B of traffic per pixel, no reuse), so what counts is bytes in flight per SM; the 8-byte / two-row
+// form above left ~25 % of the HBM rate on the table.  Rows are staged one at a time in 1.5 KB of shared memory per warp and leave as
+// 16-byte coalesced stores (a warp instruction writes 512 contiguous bytes).
+// ------------------------------------------------------------------------------------------------
+constexpr int kCvt4Warps = 4;
+
+__global__ void __launch_bounds__(kCvt4Warps * 32) nv12_to_rgb_vec4_kernel(const uint8_t* __restrict__ in, size_t stride_in,
+                                                                         uint8_t* __restrict__ out, size_t stride_out, int W, int H) {
+    __shared__ __align__(16) uint8_t stage[kCvt4Warps][1536];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int segs = (W + 511) >> 9;
+    const int seg = blockIdx.x * (blockDim.x >> 5) + warp, quad = blockIdx.y, frame = blockIdx.z;
+    if (seg >= segs) return;
+    const uint8_t* yp = in + (size_t)frame * stride_in;
+    const uint8_t* uvp = yp + (size_t)W * H;
+    uint8_t* op = out + (size_t)frame * stride_out;
+    const int x = seg * 512 + lane * 16;
+    const int seg_px = min(512, W - seg * 512);
+    uint4 yq[4], uvq[2];
+    if (x < W) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) yq[k] = __ldg(reinterpret_cast<const uint4*>(yp + (size_t)(4 * quad + k) * W + x));
+#pragma unroll
+        for (int k = 0; k < 2; ++k) uvq[k] = __ldg(reinterpret_cast<const uint4*>(uvp + (size_t)(2 * quad + k) * W + x));
+    }
+    const int row_bytes = seg_px * 3;  // multiple of 48
+#pragma unroll
+    for (int row = 0; row < 4; ++row) {
+        if (x < W) {
+            const uint32_t yw[4] = {yq[row].x, yq[row].y, yq[row].z, yq[row].w};
+            const uint32_t uvw[4] = {uvq[row >> 1].x, uvq[row >> 1].y, uvq[row >> 1].z, uvq[row >> 1].w};
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {  // 8 pixels = 4 chroma pairs per half
+                int r[8], g[8], b[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t w = uvw[2 * half + (q >> 1)] >> ((q & 1) * 16);
+                    const ChromaF c = chroma_folded((int)(w & 0xff), (int)((w >> 8) & 0xff));
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int i = q * 2 + k;
+                        yuv_px_fast((int)((yw[2 * half + (i >> 2)] >> ((i & 3) * 8)) & 0xff), c, r[i], g[i], b[i]);
+                    }
+                }
+                pack_rgb8(r, g, b, reinterpret_cast<uint2*>(&stage[warp][lane * 48 + half * 24]));
+            }
+        }
+        __syncwarp();
+        uint8_t* gp = op + ((size_t)(4 * quad + row) * W + (size_t)seg * 512) * 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int off = lane * 16 + j * 512;
+            if (off < row_bytes) *reinterpret_cast<uint4*>(gp + off) = *reinterpret_cast<const uint4*>(&stage[warp][off]);
+        }
+        __syncwarp();
+    }
+}
+
 // K1 generic path (odd sizes, W % 16 != 0): one thread per 2x2 quad, byte accesses.
 __global__ void nv12_to_rgb_generic_kernel(const uint8_t* __restrict__ in, size_t stride_in, uint8_t* __restrict__ out,
                                            size_t stride_out, int W, int H, int n_frames) {
@@ -146,7 +209,13 @@ cudaError_t launch_nv12_to_rgb(const uint8_t* d_nv12, size_t stride_in, uint8_t*
     const bool aligned = (width % 16 == 0) && (height % 2 == 0) && (height / 2 <= 65535) && (n_frames <= 65535) && (stride_in % 16 == 0) &&
                          (stride_out % 16 == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_nv12) | reinterpret_cast<uintptr_t>(d_rgb)) % 16 == 0);
-    if (aligned) {
+    static const bool no_wide = getenv("VT_B200_CVT_NARROW") != nullptr;  // diagnostics: the 8-byte / two-row form
+    if (aligned && height % 4 == 0 && !no_wide) {
+        const int segs = (width + 511) / 512;
+        const int wpb = segs < kCvt4Warps ? segs : kCvt4Warps;
+        const dim3 grid((segs + wpb - 1) / wpb, height / 4, n_frames);  // one warp per 512-px x 4-row item
+        nv12_to_rgb_vec4_kernel<<<grid, wpb * 32, 0, s>>>(d_nv12, stride_in, d_rgb, stride_out, width, height);
+    } else if (aligned) {
         const int segs = (width + 255) / 256;
         const int wpb = segs < kCvtWarps ? segs : kCvtWarps;  // narrow frames: no idle warps
         const dim3 grid((segs + wpb - 1) / wpb, height / 2, n_frames);  // one warp per 256-px x 2-row item
@@ -200,6 +269,56 @@ __global__ void __launch_bounds__(kCvtWarps * 32) yuy2_to_rgb_vec_kernel(const u
     }
 }
 
+// wide path (W % 16 == 0, H even): one warp converts a 512-px segment of TWO rows; every lane has four 16-byte loads (2 rows x 16 px)
+// in flight before it converts anything (see nv12_to_rgb_vec4_kernel: bytes in flight per SM are what a pure stream needs)
+__global__ void __launch_bounds__(kCvt4Warps * 32) yuy2_to_rgb_vec2_kernel(const uint8_t* __restrict__ in, size_t stride_in,
+                                                                         uint8_t* __restrict__ out, size_t stride_out, int W, int H) {
+    __shared__ __align__(16) uint8_t stage[kCvt4Warps][1536];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int segs = (W + 511) >> 9;
+    const size_t row_in = (size_t)W * 2;
+    (void)H;
+    const int seg = blockIdx.x * (blockDim.x >> 5) + warp, pair = blockIdx.y, frame = blockIdx.z;
+    if (seg >= segs) return;
+    const uint8_t* ip = in + (size_t)frame * stride_in + (size_t)(2 * pair) * row_in;
+    uint8_t* op = out + (size_t)frame * stride_out;
+    const int x = seg * 512 + lane * 16;
+    const int seg_px = min(512, W - seg * 512);
+    uint4 q[2][2];
+    if (x < W) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) q[r][k] = __ldg(reinterpret_cast<const uint4*>(ip + (size_t)r * row_in + (size_t)x * 2 + 16 * k));
+    }
+    const int row_bytes = seg_px * 3;
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+        if (x < W) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t w4[4] = {q[row][half].x, q[row][half].y, q[row][half].z, q[row][half].w};
+                int r[8], g[8], b[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // one Y0 U Y1 V word = two pixels
+                    const ChromaF c = chroma_folded((int)((w4[k] >> 8) & 0xff), (int)(w4[k] >> 24));
+                    yuv_px_fast((int)(w4[k] & 0xff), c, r[2 * k], g[2 * k], b[2 * k]);
+                    yuv_px_fast((int)((w4[k] >> 16) & 0xff), c, r[2 * k + 1], g[2 * k + 1], b[2 * k + 1]);
+                }
+                pack_rgb8(r, g, b, reinterpret_cast<uint2*>(&stage[warp][lane * 48 + half * 24]));
+            }
+        }
+        __syncwarp();
+        uint8_t* gp = op + ((size_t)(2 * pair + row) * W + (size_t)seg * 512) * 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int off = lane * 16 + j * 512;
+            if (off < row_bytes) *reinterpret_cast<uint4*>(gp + off) = *reinterpret_cast<const uint4*>(&stage[warp][off]);
+        }
+        __syncwarp();
+    }
+}
+
 // generic path: one thread per pixel pair, byte accesses, GStreamer row stride (width*2 rounded up to 4)
 __global__ void yuy2_to_rgb_generic_kernel(const uint8_t* __restrict__ in, size_t stride_in, uint8_t* __restrict__ out, size_t stride_out,
                                            int W, int H, int n_frames) {
@@ -227,7 +346,13 @@ cudaError_t launch_yuy2_to_rgb(const uint8_t* d_yuy2, size_t stride_in, uint8_t*
     const bool aligned = (width % 8 == 0) && (height <= 65535) && (n_frames <= 65535) && (stride_in % 16 == 0) && (stride_out % 16 == 0) &&
                          ((size_t)width * 3 % 16 == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_yuy2) | reinterpret_cast<uintptr_t>(d_rgb)) % 16 == 0);
-    if (aligned) {
+    static const bool no_wide = getenv("VT_B200_CVT_NARROW") != nullptr;  // diagnostics: the one-row / 16-byte form
+    if (aligned && width % 16 == 0 && height % 2 == 0 && height / 2 <= 65535 && !no_wide) {
+        const int segs = (width + 511) / 512;
+        const int wpb = segs < kCvt4Warps ? segs : kCvt4Warps;
+        const dim3 grid((segs + wpb - 1) / wpb, height / 2, n_frames);  // one warp per 512-px x 2-row item
+        yuy2_to_rgb_vec2_kernel<<<grid, wpb * 32, 0, s>>>(d_yuy2, stride_in, d_rgb, stride_out, width, height);
+    } else if (aligned) {
         const int segs = (width + 255) / 256;
         const int wpb = segs < kCvtWarps ? segs : kCvtWarps;
         const dim3 grid((segs + wpb - 1) / wpb, height, n_frames);  // one warp per 256-px row segment
@@ -394,6 +519,60 @@ __global__ void __launch_bounds__(256) resize_rgb_linear_kernel(const uint8_t* _
             o[ch] = (uint8_t)((((ty.a0 * (t0 >> 4)) >> 16) + ((ty.a1 * (t1 >> 4)) >> 16) + 2) >> 2);
         }
     }
+}
+
+// Batched form with the taps of every destination column / row precomputed on the host (ResizeTaps: the same float arithmetic, done
+// once per geometry instead of two double divisions per pixel): one warp produces 128 destination pixels of a row — 4 per lane, 12
+// bytes staged in shared memory — and writes them as 24 coalesced 16-byte stores.  0.98 MB read + 3.9 MB written per 640x512 ->
+// 1280x1024 frame: write bound.
+constexpr int kRszWarps = 8;
+__global__ void __launch_bounds__(kRszWarps * 32) resize_rgb_tab_kernel(const uint8_t* __restrict__ src, size_t stride_in, int sw, int sh,
+                                                                      uint8_t* __restrict__ dst, size_t stride_out, int dw, int dh,
+                                                                      const int4* __restrict__ xt, const int4* __restrict__ yt) {
+    __shared__ __align__(16) uint8_t stage[kRszWarps][384];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = blockIdx.x * kRszWarps + warp, dy = blockIdx.y, frame = blockIdx.z;
+    if (seg * 128 >= dw) return;
+    const uint8_t* sp = src + (size_t)frame * stride_in;
+    const int4 ty = __ldg(yt + dy);  // y0, y1 (clamped rows), b0, b1
+    const uint8_t *r0 = sp + (size_t)ty.x * sw * 3, *r1 = sp + (size_t)ty.y * sw * 3;
+    const int seg_px = min(128, dw - seg * 128);
+    uint32_t w3[3] = {0, 0, 0};
+    uint8_t px[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dx = seg * 128 + lane * 4 + k;
+        if (dx < dw) {
+            const int4 tx = __ldg(xt + dx);  // x0, x1 (clamped), a0, a1
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int t0 = r0[tx.x * 3 + ch] * tx.z + r0[tx.y * 3 + ch] * tx.w;
+                const int t1 = r1[tx.x * 3 + ch] * tx.z + r1[tx.y * 3 + ch] * tx.w;
+                px[3 * k + ch] = (uint8_t)((((ty.z * (t0 >> 4)) >> 16) + ((ty.w * (t1 >> 4)) >> 16) + 2) >> 2);
+            }
+        } else {
+            px[3 * k] = px[3 * k + 1] = px[3 * k + 2] = 0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) w3[j] = px[4 * j] | (px[4 * j + 1] << 8) | (px[4 * j + 2] << 16) | ((uint32_t)px[4 * j + 3] << 24);
+    uint32_t* st = reinterpret_cast<uint32_t*>(&stage[warp][lane * 12]);
+    st[0] = w3[0], st[1] = w3[1], st[2] = w3[2];
+    __syncwarp();
+    uint8_t* gp = dst + (size_t)frame * stride_out + ((size_t)dy * dw + (size_t)seg * 128) * 3;
+    const int row_bytes = seg_px * 3;
+    const int off = lane * 16;
+    if (off + 16 <= row_bytes) *reinterpret_cast<uint4*>(gp + off) = *reinterpret_cast<const uint4*>(&stage[warp][off]);
+    else if (off < row_bytes)
+        for (int b = off; b < row_bytes; ++b) gp[b] = stage[warp][b];
+}
+
+cudaError_t launch_resize_rgb_tab(const uint8_t* d_src, size_t stride_in, int sw, int sh, uint8_t* d_dst, size_t stride_out, int dw, int dh,
+                                  int n_frames, const int4* d_xt, const int4* d_yt, cudaStream_t s) {
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || n_frames <= 0) return cudaSuccess;
+    const dim3 grid((dw + 128 * kRszWarps - 1) / (128 * kRszWarps), dh, n_frames);
+    resize_rgb_tab_kernel<<<grid, kRszWarps * 32, 0, s>>>(d_src, stride_in, sw, sh, d_dst, stride_out, dw, dh, d_xt, d_yt);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_resize_rgb_linear(const uint8_t* d_src, int sw, int sh, uint8_t* d_dst, int dw, int dh, cudaStream_t s) {
@@ -620,28 +799,38 @@ __device__ void hud_score_glyphs(OverlayCmdDev& c, float score) {  // "score: " 
     c.nchar = (uint8_t)k;
 }
 
-// rows [y0, y1) x byte columns [b0, b1) of a plane with `pitch` bytes per row: device frame -> host frame, 4-byte words where both sides
-// allow it (same offset on both sides, so alignment is shared)
-__device__ void mirror_region(uint8_t* host, const uint8_t* dev, size_t len, size_t pitch, long long y0, long long y1, long long b0, long long b1) {
-    if (y1 <= y0 || b1 <= b0) return;
-    const long long nb = b1 - b0;
-    for (long long y = y0; y < y1; ++y) {
-        const size_t row = (size_t)y * pitch + (size_t)b0;
-        if (row + (size_t)nb > len) break;
-        const size_t head = (4 - ((reinterpret_cast<uintptr_t>(dev) + row) & 3)) & 3;
-        const long long h = head < (size_t)nb ? (long long)head : nb;
-        const long long words = (nb - h) >> 2, tail0 = h + (words << 2);
-        for (long long i = threadIdx.x; i < words; i += blockDim.x)
-            *reinterpret_cast<uint32_t*>(host + row + h + 4 * i) = *reinterpret_cast<const uint32_t*>(dev + row + h + 4 * i);
-        if ((long long)threadIdx.x < h) host[row + threadIdx.x] = dev[row + threadIdx.x];
-        if ((long long)threadIdx.x < nb - tail0) host[row + tail0 + threadIdx.x] = dev[row + tail0 + threadIdx.x];
-    }
+// The luma background dim of the probe HUD (src/nv12_convert.rs:324-343: Y = Y * (255 - darkness) / 255 over a rectangle) is the one
+// read-modify-write of the overlay.  Its pixels are fetched in 4-byte words, ALL loads of a thread issued before anything else
+// (a byte-wise loop whose loads wait for the previous iteration's stores — same array — costs one L2 round trip per pixel: measured
+// ~90 us for the 400x80 HUD block on one CTA), from the caller's pinned host frame when there is one: that needs no upload of the region
+// and, issued before the dependency wait, overlaps the kernels ahead.  The dimmed words go to the device frame and the host frame.
+constexpr int kOvThreads = 512;
+constexpr int kBgWords = 20;  // words per thread held in registers: 512 x 20 x 4 = 40 KB >= the 400 x 80 HUD block
+struct BgRegion {
+    long long x0, y0, x1, y1;  // clipped pixel rectangle (usize arithmetic of the reference), empty when x1 <= x0
+    long long ax0, ax1;        // 4-byte aligned interior of a row: [ax0, ax1), ax0 >= x0, ax1 <= x1
+    int wpr;                   // words per row
+    bool vec;                  // rows are word addressable (W % 4 == 0)
+};
+__device__ BgRegion bg_region(const OverlayCmdDev& c, int W, int H) {
+    BgRegion g;
+    const u64 x0 = (u64)c.x, y0 = (u64)c.y;
+    const u64 x1 = umin64(x0 + (u64)c.w, (u64)W), y1 = umin64(y0 + (u64)c.h, (u64)H);
+    g.x0 = (long long)x0, g.y0 = (long long)y0, g.x1 = x1 > x0 && y1 > y0 ? (long long)x1 : (long long)x0, g.y1 = (long long)y1;
+    g.vec = (W % 4) == 0;
+    g.ax0 = (g.x0 + 3) & ~3LL, g.ax1 = g.x1 & ~3LL;
+    g.wpr = g.vec && g.ax1 > g.ax0 ? (int)((g.ax1 - g.ax0) >> 2) : 0;
+    return g;
+}
+__device__ __forceinline__ uint32_t dim4(uint32_t v, unsigned factor) {
+    return ((v & 0xff) * factor / 255u) | ((((v >> 8) & 0xff) * factor / 255u) << 8) | ((((v >> 16) & 0xff) * factor / 255u) << 16) |
+           (((v >> 24) * factor / 255u) << 24);
 }
 
-__global__ void __launch_bounds__(256) box_overlay_kernel(size_t len, int W, int H, int fmt, const DeviceResult* __restrict__ res,
-                                                          const int32_t* __restrict__ slots, int n, float gate, const FrameCtl* ctl,
-                                                          unsigned long long* stamp_end, const uint32_t* __restrict__ blk, int blk_words,
-                                                          int draw_box) {
+__global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int W, int H, int fmt, const DeviceResult* __restrict__ res,
+                                                                 const int32_t* __restrict__ slots, int n, float gate, const FrameCtl* ctl,
+                                                                 unsigned long long* stamp_end, const uint32_t* __restrict__ blk, int blk_words,
+                                                                 int draw_box) {
     __shared__ OverlayCmdDev s_cmd[kMaxCmds];
     // the control block was written at the start of the frame (complete long before the kernel ahead of this one): every thread fetches
     // what it needs in one batch, and the HUD list comes out of pinned host memory, BEFORE the dependency wait: only the decode result
@@ -654,6 +843,26 @@ __global__ void __launch_bounds__(256) box_overlay_kernel(size_t len, int W, int
         const uint32_t* src = reinterpret_cast<const uint32_t*>(ctl->hud);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_cmd);
         for (int i = threadIdx.x; i < n_hud * (int)(sizeof(OverlayCmdDev) / 4); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    // the luma background dim, if it leads the list unconditionally (the probe's HUD): prefetch its pixels from the host frame now
+    const bool bg_first = n_hud > 0 && fmt == VT_FMT_NV12 && s_cmd[0].kind == VT_OV_BACKGROUND && s_cmd[0].cond == VT_HUD_ALWAYS;
+    BgRegion bg{0, 0, 0, 0, 0, 0, 0, false};
+    uint32_t bgw[kBgWords];
+    bool bg_pre = false;
+    if (bg_first) {
+        bg = bg_region(s_cmd[0], W, H);
+        const long long rows = bg.y1 - bg.y0;
+        if (((reinterpret_cast<uintptr_t>(host) | reinterpret_cast<uintptr_t>(frame)) & 3) != 0) bg.wpr = 0;  // bytewise
+        bg_pre = host && bg.wpr > 0 && rows * bg.wpr <= (long long)kBgWords * kOvThreads && (size_t)bg.y1 * (size_t)W <= len;
+        if (bg_pre) {
+            const int total = (int)rows * bg.wpr;
+#pragma unroll
+            for (int k = 0; k < kBgWords; ++k) {
+                const int i = threadIdx.x + k * kOvThreads;
+                if (i < total) bgw[k] = *reinterpret_cast<const volatile uint32_t*>(host + (size_t)(bg.y0 + i / bg.wpr) * W + bg.ax0 + 4 * (i % bg.wpr));
+            }
+        }
     }
     const int slot = (int)blockIdx.x < n ? slots[blockIdx.x] : -1;
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -681,7 +890,6 @@ __global__ void __launch_bounds__(256) box_overlay_kernel(size_t len, int W, int
     }
     if (blockIdx.x != 0) return;
     if (n_hud > 0) {
-        __syncthreads();
         // resolve the result-dependent commands once (shared copy), drop the ones of the other outcome
         if ((int)threadIdx.x < n_hud) {
             OverlayCmdDev& c = s_cmd[threadIdx.x];
@@ -691,19 +899,62 @@ __global__ void __launch_bounds__(256) box_overlay_kernel(size_t len, int W, int
             else if (c.from_result == VT_HUD_SCORE_TEXT) hud_score_glyphs(c, r.score);
         }
         __syncthreads();
+        int first = 0;
+        if (bg_first) {  // ---- the background dim: word interior from registers (or the device frame), ragged edges bytewise
+            const unsigned factor = 255u - (unsigned)(uint8_t)s_cmd[0].a;
+            const long long rows = bg.y1 - bg.y0;
+            if (bg.x1 > bg.x0 && (size_t)bg.y1 * (size_t)W <= len) {
+                if (bg.wpr > 0) {
+                    const long long total = rows * bg.wpr;
+                    for (long long base = 0; base < total; base += (long long)kBgWords * kOvThreads) {
+                        if (!bg_pre || base > 0) {  // not prefetched (no pinned frame, or a region larger than the register budget)
+                            const uint8_t* src = host ? host : frame;  // with a pinned frame the region was not uploaded
+#pragma unroll
+                            for (int k = 0; k < kBgWords; ++k) {
+                                const long long i = base + threadIdx.x + (long long)k * kOvThreads;
+                                if (i < total) bgw[k] = *reinterpret_cast<const uint32_t*>(src + (size_t)(bg.y0 + i / bg.wpr) * W + bg.ax0 + 4 * (i % bg.wpr));
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < kBgWords; ++k) {
+                            const long long i = base + threadIdx.x + (long long)k * kOvThreads;
+                            if (i < total) {
+                                const size_t o = (size_t)(bg.y0 + i / bg.wpr) * W + bg.ax0 + 4 * (i % bg.wpr);
+                                const uint32_t d = dim4(bgw[k], factor);
+                                *reinterpret_cast<uint32_t*>(frame + o) = d;
+                                if (host) *reinterpret_cast<uint32_t*>(host + o) = d;
+                            }
+                        }
+                    }
+                }
+                // columns outside the word interior (<= 3 + 3 per row; every column when rows are not word addressable)
+                const long long eh = bg.wpr > 0 ? bg.ax0 - bg.x0 : bg.x1 - bg.x0, et = bg.wpr > 0 ? bg.x1 - bg.ax1 : 0, ec = eh + et;
+                for (long long i = threadIdx.x; i < rows * ec; i += blockDim.x) {
+                    const long long yy = bg.y0 + i / ec, k = i % ec, xx = k < eh ? bg.x0 + k : bg.ax1 + (k - eh);
+                    const size_t o = (size_t)yy * W + (size_t)xx;
+                    const uint8_t d = (uint8_t)(((unsigned)(host ? host[o] : frame[o]) * factor) / 255u);
+                    frame[o] = d;
+                    if (host) host[o] = d;
+                }
+            }
+            __syncthreads();
+            first = 1;
+        }
         for (int p = 0; p < 2; ++p) {
             uint8_t* dst = p == 0 ? frame : host;
             if (!dst) break;
             Surface s{dst, len, W, H, fmt};
-            for (int i = 0; i < n_hud; ++i) {
+            for (int i = first; i < n_hud; ++i) {
                 const OverlayCmdDev& c = s_cmd[i];
                 if (c.kind < 0) continue;
                 if (p == 1 && c.kind == VT_OV_BACKGROUND && fmt == VT_FMT_NV12) {
-                    // read-modify-write: the host copy takes the final pixels of the region from the device frame (the later commands
-                    // of this pass re-draw what lies on top of it)
-                    const u64 x0 = (u64)c.x, y0 = (u64)c.y;  // the region ov_background touched (same usize arithmetic)
-                    const u64 x1 = umin64(x0 + (u64)c.w, (u64)W), y1 = umin64(y0 + (u64)c.h, (u64)H);
-                    if (x1 > x0 && y1 > y0) mirror_region(host, frame, len, (size_t)W, (long long)y0, (long long)y1, (long long)x0, (long long)x1);
+                    // a dim that does not lead the list: the host copy takes the final pixels of the region from the device frame (the
+                    // later commands of this pass re-draw what lies on top of it)
+                    const BgRegion g = bg_region(c, W, H);
+                    for (long long j = threadIdx.x; j < (g.y1 - g.y0) * (g.x1 - g.x0); j += blockDim.x) {
+                        const size_t o = (size_t)(g.y0 + j / (g.x1 - g.x0)) * W + (size_t)(g.x0 + j % (g.x1 - g.x0));
+                        if (o < len) host[o] = frame[o];
+                    }
                 } else {
                     ov_dispatch(s, c);
                 }
@@ -724,7 +975,7 @@ __global__ void __launch_bounds__(256) box_overlay_kernel(size_t len, int W, int
 cudaError_t launch_box_overlay(size_t len, int width, int height, int format, const DeviceResult* d_res, const int32_t* d_slots, int n,
                                float gate, const FrameCtl* d_ctl, unsigned long long* stamp_end, cudaStream_t s, bool pdl, const void* d_blk,
                                size_t blk_bytes, int draw_box) {
-    return launch_ex(box_overlay_kernel, dim3(n > 0 ? n : 1), dim3(256), 0, s, pdl, 1, len, width, height, format, d_res, d_slots, n, gate, d_ctl,
+    return launch_ex(box_overlay_kernel, dim3(n > 0 ? n : 1), dim3(kOvThreads), 0, s, pdl, 1, len, width, height, format, d_res, d_slots, n, gate, d_ctl,
                      stamp_end, (const uint32_t*)d_blk, (int)(blk_bytes / 4), draw_box);
 }
 

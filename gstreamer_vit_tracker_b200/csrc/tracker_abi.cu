@@ -170,12 +170,57 @@ vt_status vt_convert_yuy2_rgb(vt_tracker* t, const uint8_t* yuy2, size_t len, in
     return VT_OK;
 }
 
-vt_status vt_resize_rgb_device(vt_tracker* t, const uint8_t* d_rgb, int32_t sw, int32_t sh, uint8_t* d_out, int32_t dw, int32_t dh) {
-    if (!t || !d_rgb || !d_out || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return VT_ERR_INVALID;
+// OpenCV INTER_LINEAR taps of every destination index, host side: the arithmetic of lin_tap() in pixel.cu
+static void resize_taps(int s, int d, bool clamp_frac, std::vector<int32_t>& out /* 4 per index: i0, i1, a0, a1 */) {
+    const double scale = 1.0 / ((double)d / (double)s);
+    out.resize((size_t)d * 4);
+    for (int i = 0; i < d; ++i) {
+        float f = (float)(((double)i + 0.5) * scale - 0.5);
+        int ix = (int)floorf(f);
+        f -= (float)ix;
+        if (clamp_frac) {  // horizontal taps clamp the fraction at the borders ...
+            if (ix < 0) ix = 0, f = 0.f;
+            if (ix >= s - 1) ix = s - 1, f = 0.f;
+        }
+        const int a0 = (int)lrintf((1.f - f) * 2048.f), a1 = (int)lrintf(f * 2048.f);
+        int i0 = ix, i1 = ix + 1;
+        if (clamp_frac) i1 = std::min(i1, s - 1);
+        else i0 = std::min(std::max(i0, 0), s - 1), i1 = std::min(std::max(i1, 0), s - 1);  // ... vertical taps clamp the row index
+        out[4 * i] = i0, out[4 * i + 1] = i1, out[4 * i + 2] = a0, out[4 * i + 3] = a1;
+    }
+}
+
+vt_status vt_resize_rgb_device_batch(vt_tracker* t, const uint8_t* d_rgb, size_t stride_in, int32_t sw, int32_t sh, uint8_t* d_out, size_t stride_out,
+                                     int32_t dw, int32_t dh, int32_t n_frames) {
+    if (!t || !d_rgb || !d_out || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || n_frames <= 0) return VT_ERR_INVALID;
     VT_CUDA(cudaSetDevice(t->cfg.device));
-    VT_CUDA(launch_resize_rgb_linear(d_rgb, sw, sh, d_out, dw, dh, t->stream));
+    const bool fast = ((size_t)dw * 3) % 16 == 0 && stride_out % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0 && dh <= 65535 && n_frames <= 65535;
+    if (!fast) {  // odd geometry: the per-pixel kernel, frame by frame
+        for (int i = 0; i < n_frames; ++i) {
+            VT_CUDA(launch_resize_rgb_linear(d_rgb + (size_t)i * stride_in, sw, sh, d_out + (size_t)i * stride_out, dw, dh, t->stream));
+            ++t->kernel_launches;
+        }
+        return VT_OK;
+    }
+    if (t->rsz_geom[0] != sw || t->rsz_geom[1] != sh || t->rsz_geom[2] != dw || t->rsz_geom[3] != dh || !t->d_rsz_taps) {
+        std::vector<int32_t> xt, yt;
+        resize_taps(sw, dw, true, xt);
+        resize_taps(sh, dh, false, yt);
+        VT_CUDA(cudaStreamSynchronize(t->stream));  // an earlier launch may still read the old tables
+        if (t->d_rsz_taps) cudaFree(t->d_rsz_taps);
+        t->d_rsz_taps = nullptr;
+        VT_CUDA(cudaMalloc(&t->d_rsz_taps, sizeof(int4) * ((size_t)dw + dh)));
+        VT_CUDA(cudaMemcpy(t->d_rsz_taps, xt.data(), sizeof(int4) * dw, cudaMemcpyHostToDevice));
+        VT_CUDA(cudaMemcpy(t->d_rsz_taps + dw, yt.data(), sizeof(int4) * dh, cudaMemcpyHostToDevice));
+        t->rsz_geom[0] = sw, t->rsz_geom[1] = sh, t->rsz_geom[2] = dw, t->rsz_geom[3] = dh;
+    }
+    VT_CUDA(launch_resize_rgb_tab(d_rgb, stride_in, sw, sh, d_out, stride_out, dw, dh, n_frames, t->d_rsz_taps, t->d_rsz_taps + dw, t->stream));
     ++t->kernel_launches;
     return VT_OK;
+}
+
+vt_status vt_resize_rgb_device(vt_tracker* t, const uint8_t* d_rgb, int32_t sw, int32_t sh, uint8_t* d_out, int32_t dw, int32_t dh) {
+    return vt_resize_rgb_device_batch(t, d_rgb, (size_t)sw * sh * 3, sw, sh, d_out, (size_t)dw * dh * 3, dw, dh, 1);
 }
 
 vt_status vt_resize_rgb(vt_tracker* t, const uint8_t* rgb, int32_t sw, int32_t sh, uint8_t* out, int32_t dw, int32_t dh) {
@@ -185,8 +230,8 @@ vt_status vt_resize_rgb(vt_tracker* t, const uint8_t* rgb, int32_t sw, int32_t s
     vt_status st = fmt_scratch(t, in_bytes, out_bytes);
     if (st != VT_OK) return st;
     VT_CUDA(cudaMemcpyAsync(t->d_fmt_in, rgb, in_bytes, cudaMemcpyHostToDevice, t->stream));
-    VT_CUDA(launch_resize_rgb_linear(t->d_fmt_in, sw, sh, t->d_fmt_out, dw, dh, t->stream));
-    ++t->kernel_launches;
+    st = vt_resize_rgb_device_batch(t, t->d_fmt_in, in_bytes, sw, sh, t->d_fmt_out, out_bytes, dw, dh, 1);
+    if (st != VT_OK) return st;
     VT_CUDA(cudaMemcpyAsync(out, t->d_fmt_out, out_bytes, cudaMemcpyDeviceToHost, t->stream));
     VT_CUDA(cudaStreamSynchronize(t->stream));
     t->h2d_bytes += in_bytes, t->d2h_bytes += out_bytes;

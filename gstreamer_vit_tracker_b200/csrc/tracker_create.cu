@@ -191,6 +191,7 @@ void vt_tracker_destroy(vt_tracker* t) {
     for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
     for (auto& e : t->ev)
         if (e) cudaEventDestroy(e);
+    if (t->d_rsz_taps) cudaFree(t->d_rsz_taps);
     if (t->d_fmt_in) cudaFree(t->d_fmt_in);
     if (t->d_fmt_out) cudaFree(t->d_fmt_out);
     if (t->copy_stream) cudaStreamSynchronize(t->copy_stream), cudaStreamDestroy(t->copy_stream);

@@ -426,11 +426,12 @@ static void collect_timing(vt_tracker* t) {
     // stage boundaries stamped on the device (ns): submit, crop start, ViT start, decode start, decode end, overlay end
     const unsigned long long* st = t->h_stamps;
     auto span = [&](int a, int b) { return st[b] > st[a] && st[a] ? (float)((double)(st[b] - st[a]) * 1e-6) : 0.f; };
-    const int last_dev = t->cfg.box_overlay ? ST_OVL_END : ST_DEC_END;
+    const bool ovl = t->cfg.box_overlay || t->hud_mode;
+    const int last_dev = ovl ? ST_OVL_END : ST_DEC_END;
     const float wall = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t->t_submit).count();
     float ms[7];
     ms[0] = span(ST_SUBMIT, ST_PRE), ms[1] = span(ST_PRE, ST_VIT), ms[2] = span(ST_VIT, ST_DEC), ms[3] = span(ST_DEC, ST_DEC_END);
-    ms[4] = t->cfg.box_overlay ? span(ST_DEC_END, ST_OVL_END) : 0.f;
+    ms[4] = ovl ? span(ST_DEC_END, ST_OVL_END) : 0.f;
     const float dev = span(ST_SUBMIT, last_dev);
     ms[5] = wall > dev ? wall - dev : 0.f;  // results (and overlay rows) back in host memory + completion latency, host clock
     ms[6] = wall;
@@ -470,7 +471,9 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     if (!in_place) t->d_frame = t->d_frames[slot];  // the slot's own frame buffer: the other one may still be read by the frame in flight
     const bool lagging = t->q_count > 0;  // a frame is in flight: rect_mirror is one frame old, the windows are predictions
     UploadPlan plan;
-    if (!in_place && !d_src) plan_upload(t, len, host_frame != nullptr, lagging, n_hud ? t->hud_next_rmw : nullptr, plan);
+    // (the region a HUD list dims is read by the overlay kernel straight from the pinned host frame: it needs no upload of its own)
+    if (!in_place && !d_src)
+        plan_upload(t, len, host_frame != nullptr, lagging, (n_hud && !(host_frame && t->hud_next_bg_leads)) ? t->hud_next_rmw : nullptr, plan);
     if (!in_place && !d_src && lagging) {
         // pipelined host frame: upload on the copy stream while the frame in flight computes; the main stream picks it up through an event
         vt_status st = do_upload(t, frame, len, plan, false, t->copy_stream);
@@ -637,6 +640,9 @@ vt_status tracker_set_hud(vt_tracker* t, const HudCmd* cmds, int n) {
             bytes += 1024;  // rect / crosshair / cursor / selection outlines
         }
     }
+    int n_bg = 0;
+    for (int i = 0; i < n; ++i) n_bg += cmds[i].cmd.kind == VT_OV_BACKGROUND;
+    t->hud_next_bg_leads = n_bg == 1 && cmds[0].cmd.kind == VT_OV_BACKGROUND && cmds[0].cond == VT_HUD_ALWAYS;
     t->hud_next_n = n, t->hud_next_bytes = bytes;
     memcpy(t->hud_next_rmw, rmw, sizeof(rmw));
     return VT_OK;

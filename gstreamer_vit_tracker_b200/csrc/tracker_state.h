@@ -86,6 +86,8 @@ struct vt_tracker {
     uint8_t* d_rgb = nullptr;  // lazily allocated, vt_convert_nv12_rgb
     uint8_t *d_fmt_in = nullptr, *d_fmt_out = nullptr;  // lazily grown scratch of the format entry points (YUY2, resize)
     size_t fmt_in_cap = 0, fmt_out_cap = 0;
+    int4* d_rsz_taps = nullptr;          // resize taps of the last geometry: [dw] column taps then [dh] row taps
+    int rsz_geom[4] = {0, 0, 0, 0};      // sw, sh, dw, dh they were built for
     uint8_t* h_stage = nullptr;  // pinned staging for non-pinned callers
     size_t h_stage_bytes = 0;
     int frame_valid = 1;
@@ -110,6 +112,8 @@ struct vt_tracker {
     int hud_next_n = 0;
     int hud_next_rmw[4] = {0, 0, 0, 0};  // region the list reads before it writes (NV12 background dim): x0, y0, x1, y1; empty = none
     size_t hud_next_bytes = 0;            // pixels the list touches (device -> host accounting)
+    bool hud_next_bg_leads = false;       // the list's only background dim is its first, unconditional command: with a pinned frame the
+                                          // overlay kernel reads that region from the host frame and it needs no upload
     bool inflight_mirrored = false;
     float* d_maps = nullptr;
     OverlayCmdDev *d_cmds = nullptr, *h_cmds = nullptr;

@@ -214,6 +214,9 @@ vt_status vt_convert_yuy2_rgb_device(vt_tracker* t, const uint8_t* d_yuy2, size_
  * OpenCV INTER_LINEAR fixed-point semantics, bit-exact with cv2.resize (any source / destination size). */
 vt_status vt_resize_rgb(vt_tracker* t, const uint8_t* rgb, int32_t src_w, int32_t src_h, uint8_t* out, int32_t dst_w, int32_t dst_h);
 vt_status vt_resize_rgb_device(vt_tracker* t, const uint8_t* d_rgb, int32_t src_w, int32_t src_h, uint8_t* d_out, int32_t dst_w, int32_t dst_h);
+/* device-resident, batched: n_frames frames, frame i at d_rgb + i*stride_in -> d_out + i*stride_out (one launch) */
+vt_status vt_resize_rgb_device_batch(vt_tracker* t, const uint8_t* d_rgb, size_t stride_in, int32_t src_w, int32_t src_h, uint8_t* d_out,
+                                     size_t stride_out, int32_t dst_w, int32_t dst_h, int32_t n_frames);
 
 /* ------------------------------------------------------------------------------------------- */
 /* overlay                                                                                      */

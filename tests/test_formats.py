@@ -102,6 +102,45 @@ def test_gpu_resize_matches_cv2_golden_and_oracle(trk):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("sw,sh,dw,dh", [(640, 512, 1280, 1024), (320, 200, 1280, 720), (1280, 720, 640, 352), (100, 60, 16, 9), (64, 48, 160, 96)])
+def test_gpu_resize_device_batch(trk, sw, sh, dw, dh):
+    """vt_resize_rgb_device_batch (precomputed taps, one launch for n frames; the 16-byte store path needs dw*3 % 16 == 0, other
+    widths take the per-pixel kernel) against the oracle, up- and down-scales."""
+    import torch
+    n = 3
+    src = hash_bytes(900 + sw + dw, sw * sh * 3 * n).reshape(n, sh, sw, 3)
+    d_in = torch.from_numpy(src.copy()).cuda()
+    d_out = torch.zeros((n, dh, dw, 3), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    trk.resize_rgb_device_batch(d_in.data_ptr(), sw * sh * 3, sw, sh, d_out.data_ptr(), dw * dh * 3, dw, dh, n)
+    trk.sync()
+    out = d_out.cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(out[i], orc.resize_linear(np.ascontiguousarray(src[i]), dw, dh)), (i, sw, sh, dw, dh)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(1920, 1080), (1280, 720), (3840, 2160), (640, 512), (528, 4), (512, 6), (16, 4)])
+def test_gpu_nv12_wide_and_narrow_kernels_agree(w, h, tmp_path_factory):
+    """The 16-byte / four-row NV12->RGB kernel (W % 16 == 0, H % 4 == 0) and the 8-byte / two-row one (H % 4 != 0) against the oracle,
+    device-resident batch of 3 frames incl. a partial last 512-px segment."""
+    import torch
+    from gstreamer_vit_tracker_b200 import api
+    wpath = weights.ensure_weight_file("nano", str(tmp_path_factory.mktemp("w")))
+    t = api.VitTrack.new(wpath, w, h, fmt="nv12")
+    n, fb, ob = 3, w * h * 3 // 2, w * h * 3
+    buf = hash_bytes(4000 + w + h, fb * n)
+    d_in = torch.from_numpy(buf).cuda()
+    d_out = torch.zeros(ob * n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    t.nv12_to_rgb_device(d_in.data_ptr(), fb, d_out.data_ptr(), ob, n)
+    t.sync()
+    out = d_out.cpu().numpy().reshape(n, h, w, 3)
+    for i in range(n):
+        assert np.array_equal(out[i], orc.nv12_to_rgb(buf[i * fb:(i + 1) * fb], w, h, 4)), (i, w, h)
+
+
+@pytest.mark.gpu
 def test_gpu_ir_pipeline_chain(trk):
     """YUY2 640x512 -> RGB -> (probe: track + overlay on RGB24, covered elsewhere) -> 1280x1024 display frame, all on the GPU path,
     equals the oracle chain byte for byte."""

@@ -58,7 +58,7 @@ def test_both_arms_print_the_same_config_keys(built):
     sys.path.insert(0, ROOT)
     import bench
     import argparse
-    a = argparse.Namespace(model="tiny", streams_per_gpu=1, gpus=1, ring=384, steps=40, warmup=5)
+    a = argparse.Namespace(model="tiny", streams_per_gpu=1, gpus=1, ring=0, steps=40, warmup=5)
     assert set(bench.config_dict(a)) >= {"workload", "resolution", "format", "targets", "model", "streams_per_gpu", "weights", "call", "l2"}
     g = _run("--steps", "12", "--warmup", "3", "--no-cpu-baseline", "--no-extras")
     r = _run("--impl", "reference", "--steps", "12", "--warmup", "3")

@@ -40,7 +40,8 @@ def main():
     dst = torch.empty((n, W * H * 3), dtype=torch.uint8, device="cuda")
     ms = timed(trk, lambda: trk.nv12_to_rgb_device(src.data_ptr(), W * H * 3 // 2, dst.data_ptr(), W * H * 3, n))
     by = n * (W * H * 3 // 2 + W * H * 3)
-    out.append({"kernel": "nv12_to_rgb_vec_kernel", "frames": n, "resolution": "1920x1080", "bytes_per_launch": by, "ms_per_launch": ms,
+    narrow = bool(os.environ.get("VT_B200_CVT_NARROW"))
+    out.append({"kernel": "nv12_to_rgb_vec_kernel" if narrow else "nv12_to_rgb_vec4_kernel", "frames": n, "resolution": "1920x1080", "bytes_per_launch": by, "ms_per_launch": ms,
                 "achieved_gbs": by / ms / 1e6, "peak_gbs": hbm, "frac": by / ms / 1e6 / hbm})
     # YUY2 -> RGB, 256 x 640x512
     w, h, n2 = 640, 512, 256
@@ -48,8 +49,17 @@ def main():
     dst2 = torch.empty((n2, w * h * 3), dtype=torch.uint8, device="cuda")
     ms = timed(trk, lambda: trk.yuy2_to_rgb_device(src2.data_ptr(), w * h * 2, dst2.data_ptr(), w * h * 3, w, h, n2))
     by = n2 * (w * h * 2 + w * h * 3)
-    out.append({"kernel": "yuy2_to_rgb_vec_kernel", "frames": n2, "resolution": "640x512", "bytes_per_launch": by, "ms_per_launch": ms,
+    out.append({"kernel": "yuy2_to_rgb_vec_kernel" if narrow else "yuy2_to_rgb_vec2_kernel", "frames": n2, "resolution": "640x512", "bytes_per_launch": by, "ms_per_launch": ms,
                 "achieved_gbs": by / ms / 1e6, "peak_gbs": hbm, "frac": by / ms / 1e6 / hbm})
+    # RGB up-scale 640x512 -> 1280x1024, batch of 128 frames in one launch (126 MB in, 503 MB out)
+    nb = 128
+    srcb = dst2[: nb * w * h * 3]
+    upb = torch.empty(nb * 1280 * 1024 * 3, dtype=torch.uint8, device="cuda")
+    ms = timed(trk, lambda: trk.resize_rgb_device_batch(srcb.data_ptr(), w * h * 3, w, h, upb.data_ptr(), 1280 * 1024 * 3, 1280, 1024, nb), reps=10)
+    by = nb * (w * h * 3 + 1280 * 1024 * 3)
+    out.append({"kernel": "resize_rgb_tab_kernel", "frames": nb, "resolution": "640x512 -> 1280x1024", "bytes_per_launch": by, "ms_per_launch": ms,
+                "achieved_gbs": by / ms / 1e6, "peak_gbs": hbm, "frac": by / ms / 1e6 / hbm})
+    del upb
     # RGB up-scale 640x512 -> 1280x1024 (one frame per launch: 0.98 MB in, 3.9 MB out, L2 resident when repeated)
     up = torch.empty(1280 * 1024 * 3, dtype=torch.uint8, device="cuda")
     ms = timed(trk, lambda: trk.resize_rgb_device(dst2.data_ptr(), w, h, up.data_ptr(), 1280, 1024), reps=50)
