@@ -36,15 +36,11 @@
 
 #include <vector>
 
-#include "tc_common.cuh"
-#include "vt_internal.h"
+#include "gemm_epi.cuh"
 
 namespace vt {
 
-using namespace tc;
-
-constexpr int kTcBM = 128, kTcBK = 64, kTcStages = 3;
-constexpr int kTileABytes = kTcBM * kTcBK * 2;  // 16 KB, one precision part
+constexpr int kTcStages = 3;
 constexpr int kMaxChainN = 192;                 // widest chained second GEMM (TMEM: 128 + N2 <= 512 columns)
 constexpr int kChainBN = 64;                    // the chained GEMM consumes a 64-column hidden tile
 
@@ -71,18 +67,6 @@ struct TcSmem {
     static_assert(4 * kTileOBytes <= kPipeBytes, "staging must fit in the dead pipeline ring");
 };
 
-// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf by Abramowitz & Stegun 7.1.26 (one rcp, five FMAs, one ex2): |abs error| < 7e-7 in fp32
-// for erf, < 3e-7 for GELU — an order of magnitude below the bf16x3 operand error — at a third of erff's instruction count (the
-// FC1 epilogue is instruction-issue bound: 16 GELUs per thread).
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f), p = fmaf(p, t, -0.284496736f), p = fmaf(p, t, 0.254829592f);
-    const float e = ex2_approx(-1.4426950408889634f * z * z);
-    return 0.5f * x * (1.f + copysignf(1.f - p * t * e, x));
-}
 
 // LayerNorm fused into the epilogue of the GEMMs that produce the residual stream (patch-embed, proj, FC2): the N / 64 CTAs
 // that hold the column tiles of one 128-row tile form a thread-block cluster; every thread computes the (sum, M2) of its 16
@@ -90,80 +74,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // mbarrier: no cluster barrier on the critical path), and every CTA combines the partials in a fixed order (Chan's parallel variance) — every CTA gets bit-identical statistics — normalises its
 // own columns and stages the bf16 (hi, lo) A operand of the next GEMM for a TMA tile store.
 constexpr int kMaxLnCluster = 8;
-constexpr int kTcThreads = 512;                         // 16 warps: warp w reads TMEM lane quarter w % 4, column group w / 4
-constexpr int kTcColGroups = kTcThreads / kTcBM;        // 4 threads per accumulator row, BN / 4 columns each
 
-// Staging tiles live in shared memory as [128 rows][RB bytes] (RB = 128: 64 bf16 or 32 fp32 columns; RB = 64: 32 bf16 columns) with
-// the 16-byte chunks of a row XOR-swizzled so that both the per-row writes of the epilogue threads and the row-major reads of the
-// copy-out are bank-conflict free; RB = 128 is the hardware 128B swizzle (the staged hidden tile is a valid UMMA A operand).
-template <int RB>
-__device__ __forceinline__ int swz(int row, int chunk) {
-    return RB == 128 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3));
-}
-
-// CPT (16 or 8) fp32 -> bf16 (hi, lo) into the staging tiles of a BN = 4 CPT column tile
-template <int CPT, bool F16>
-__device__ __forceinline__ void stage_split(const float (&v)[CPT], uint8_t* tile_hi, uint8_t* tile_lo, int row, int g, bool with_lo) {
-    constexpr int RB = CPT * 8;  // bytes per tile row
-    uint32_t hi[CPT / 2], lo[CPT / 2];
-#pragma unroll
-    for (int j = 0; j < CPT; j += 2) split2_h<F16>(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
-#pragma unroll
-    for (int q = 0; q < CPT / 8; ++q) {
-        const int off = row * RB + (swz<RB>(row, (CPT / 8) * g + q) << 4);
-        *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-        if (with_lo) *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-    }
-}
-
-// Staged tile -> global memory.  Row m of the GEMM is row (m % period + row_off) of target (m / period + batch_off) of a dense
-// [targets][heads][rows][cols] output (TcOut); periods are multiples of 64, so each 64-row half of a tile stays inside one target
-// and its (row, target) is computed once (TileRows).  Rows outside [0, rows) — the template rows the final LayerNorm drops, the
-// padding rows of the last tile — and targets >= batch are skipped.
-// The copy is done by all 512 threads with fully coalesced 16-byte stores: RB / 16 lanes cover one tile row, a warp instruction
-// writes 4 (8) rows.  (Measured alternatives: thread-per-row stores straight from registers touch 32 lines per instruction and run at
-// ~9 B/clk/SM; TMA tile stores cost ~0.16 us per 8 KB box on the issuing SM, 2 us for the 96 KB partial tile of the chained GEMM.)
-constexpr int kHalfRows = 64;
-struct TileRows {  // (row-in-target, target) of the two 64-row halves of a tile; computed once, before the accumulator wait
-    int t[2], b[2];
-    __device__ __forceinline__ TileRows(int m0, int period, int batch_off) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int mr = m0 + k * kHalfRows;
-            b[k] = mr / period, t[k] = mr - b[k] * period, b[k] += batch_off;
-        }
-    }
-};
-// one [128 rows][RB bytes] swizzled tile; col_bytes = byte offset of the tile's first column inside a destination row
-template <int RB>
-__device__ __forceinline__ void tile_to_global(const uint8_t* tile, const TcOut& o, int64_t col_bytes, const TileRows& r, int row_off, int head,
-                                               int plane, int tid) {
-    constexpr int CH = RB / 16, kRowsPerPass = kTcThreads / CH;  // 8 chunks, 64 rows per pass / 4 chunks, 128 rows in one pass
-#pragma unroll
-    for (int i = 0; i < kTcBM / kRowsPerPass; ++i) {
-        const int row = tid / CH + kRowsPerPass * i, ch = tid % CH, half = row >> 6;
-        const int tt = r.t[half] + (row & 63) + row_off, b = r.b[half];
-        if (tt >= 0 && tt < o.rows && b < o.batch) {
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + row * RB + (swz<RB>(row, ch) << 4));
-            uint8_t* dst = o.base + (int64_t)plane * o.plane_bytes + (((int64_t)b * o.heads + head) * o.rows + tt) * o.row_bytes + col_bytes + ch * 16;
-            *reinterpret_cast<uint4*>(dst) = v;
-        }
-    }
-}
-// V^T: two unswizzled [BN d][64 tokens] sub-tiles -> rows d_off.. of [targets][heads][64 d][tokens]; sub-tile k holds tokens t[k]..t[k]+63
-template <int BN>
-__device__ __forceinline__ void vt_tile_to_global(const uint8_t* tile, const TcOut& o, const TileRows& r, int head, int d_off, int tid) {
-    constexpr int kPasses = 2 * BN * 8 / kTcThreads;  // 2 sub-tiles x BN rows x 8 chunks over 512 threads
-#pragma unroll
-    for (int i = 0; i < kPasses; ++i) {
-        const int idx = tid + i * kTcThreads, sub = idx / (BN * 8), d = (idx >> 3) % BN, ch = idx & 7, b = r.b[sub];
-        if (b < o.batch && r.t[sub] + kHalfRows <= o.rows) {
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + sub * (BN * 128) + d * 128 + ch * 16);
-            uint8_t* dst = o.base + (((int64_t)b * o.heads + head) * 64 + d_off + d) * o.row_bytes + (int64_t)r.t[sub] * 2 + ch * 16;
-            *reinterpret_cast<uint4*>(dst) = v;
-        }
-    }
-}
 
 template <int NSPLIT, int BN>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcGemmArgs a) {
@@ -194,6 +105,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const int acc2_cols = (sliced && kLo) ? 2 * N2 : N2;              // sliced + bf16x3: hi*lo term in a second column half
     // dup_ln (spread form of a GEMM with fused LayerNorm): replica 0 stores the fp32 tile, replica 1 the LayerNorm hi tile, replica 2 the lo tile
     const bool do_ln = a.ln_g != nullptr && (!a.dup_ln || blockIdx.z > 0), do_c = a.c_on && (!a.dup_ln || blockIdx.z == 0);
+    const bool do_ln_any = a.ln_g != nullptr;
     const bool ln_hi = !a.dup_ln || blockIdx.z == 1, ln_lo = kLo && (!a.dup_ln || blockIdx.z == 2);
     // dup_hl (spread form of the QKV scatter): replica 0 stores the bf16 hi tiles, replica 1 the lo tiles
     const bool st_hi = !a.dup_hl || blockIdx.z == 0, st_lo = kLo && (!a.dup_hl || blockIdx.z == 1);
@@ -210,7 +122,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     if (tid == 0) {
         tma_prefetch_desc(&mp.Ahi), tma_prefetch_desc(&mp.Bhi);
         if (kLo) tma_prefetch_desc(&mp.Alo), tma_prefetch_desc(&mp.Blo);
-        for (int s = 0; s < kTcStages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
+        // multicast activation tiles: a stage is refilled in every CTA of the cluster at once, so it is released by all of them
+        for (int s = 0; s < kTcStages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], a.mcast > 1 ? a.mcast : 1);
         mbar_init(&accum_bar, 1), mbar_init(&resid_bar, 1), mbar_init(&b2_bar, 1), mbar_init(&accum2_bar, 1), mbar_init(&ln_bar, 1);
         fence_barrier_init();
         // LayerNorm exchange: every CTA of the cluster (this one included) sends one float2 per row into ln_part of this CTA
@@ -316,7 +229,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                         umma_bf16(tmem, dAhi, dBhi, idesc, (kb | k) != 0);
                     }
                 }
-                umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
+                // stage reusable once these MMAs have read it
+                if (a.mcast > 1) umma_commit_mcast(&empty_bar[s], (uint16_t)((1u << a.mcast) - 1));
+                else umma_commit(&empty_bar[s]);
             }
             umma_commit(&accum_bar);
         }
@@ -570,6 +485,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     __syncthreads();
     if (tid == 0) tr.mark(3);
     if (warp == 1) tmem_dealloc(tmem, tmem_cols);
+    // multicast without the LayerNorm exchange: peers still deliver stage-release arrivals to this CTA's barriers until their own main
+    // loops end, so nobody leaves before everybody's has (with the LayerNorm exchange every CTA has already waited for every peer's epilogue)
+    if (a.mcast > 1 && !do_ln_any) cluster_arrive_release(), cluster_wait_acquire();
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -702,7 +620,7 @@ cudaError_t tc_gemm_setup() {
     return e;
 }
 
-cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl, bool spread) {
+cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl, bool spread, bool mcast_ln) {
     if (M <= 0) return cudaSuccess;
     TcGemmArgs a = p.args;
     a.M = M;
@@ -727,9 +645,10 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t 
                 break;
             }
     }
-    // multicast needs every k-block of a CTA to have its own stage (no ring reuse across CTAs) and plain 2-D activation boxes
-    const int num_kb = a.kb_per_split ? a.kb_per_split : a.K / kTcBK;
-    a.mcast = (p.mcast_ok && cluster_x > 1 && num_kb <= kTcStages && !a.conv_feat) ? cluster_x : 0;
+    // multicast needs plain 2-D activation boxes; the ring is reused cluster-wide (empty barriers count every CTA of the cluster).
+    // mcast_ln (throughput mode): the LayerNorm cluster of proj / FC2 shares its activation tile — with many rows these GEMMs are bound
+    // by L2 -> SM traffic (FC2: 393 KB of activations + 196 KB of weights per 128 x 64 tile), which the multicast cuts by 45 %.
+    a.mcast = ((p.mcast_ok || (mcast_ln && a.ln_g)) && cluster_x > 1 && !a.conv_feat && !a.kb_per_split) ? cluster_x : 0;
     if (!a.mcast && !a.ln_g) cluster_x = 1;
     if (nsplit == 2 && bn != 64) return cudaErrorInvalidValue;  // the fp16 form exists for the 64-column tile only
     if (bn == 64) {

@@ -120,7 +120,13 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             const BlockW& b = t->blk[l];
             const vt_tracker::BlockPlans& p = t->plans[l];
             if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln1_g, b.ln1_b, t->ln_hi, LO(t->ln_lo), M, D, 1 << 30, 0, 0, s, pdl));
-            VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s, pdl, spread));
+            // many rows (cfg4, stream groups): the A-stationary form — activation tile resident, epilogue of chunk i under the main loop of i + 1
+            const bool as_form = t->as_rows > 0 && M >= t->as_rows;
+            const bool tp_mcast = t->tp_rows > 0 && M >= t->tp_rows;
+            if (as_form && tc_gemm_as_supported(p.qkv))
+                VT_LAUNCH(tc_gemm_as_launch(p.qkv, M, ns, s, pdl, t->sm_count));
+            else
+                VT_LAUNCH(tc_gemm_launch(p.qkv, M, ns, s, pdl, spread));
             // Latency mode: the proj GEMM is folded into the attention kernel (per-head partial products, D / 64 replicas per tile) and
             // reduce_ln adds the heads + bias + residual and applies LN2 — one kernel and one dependency edge less per block.
             const bool att_chain = spread && t->att_chain_ok && n * t->heads * 3 * (D / kAttChainW) <= kSpreadCtas;
@@ -136,7 +142,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                 r.ln_g = b.ln2_g, r.ln_b = b.ln2_b, r.ln_hi = t->ln_hi, r.ln_lo = LO(t->ln_lo), r.ln_rows = kNTok, r.ln_row_off = 0;
                 VT_LAUNCH(launch_reduce_ln(r, s, pdl));
             } else {
-                VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention, spread));  // fused: + LN2
+                VT_LAUNCH(tc_gemm_launch(p.proj, M, ns, s, pdl && t->tc_attention, spread && !tp_mcast, tp_mcast));  // fused: + LN2
             }
             if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, b.ln2_g, b.ln2_b, t->ln_hi, LO(t->ln_lo), M, D, 1 << 30, 0, 0, s, pdl));
             // Chained form (FC2 partial products inside the FC1 kernel, summed by reduce_ln): shortest critical path for a few targets.
@@ -148,7 +154,10 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             } else {
                 TcGemmPlan fc1 = p.fc1;
                 fc1.args.chain_n = 0, fc1.args.o_mode = 1;
-                VT_LAUNCH(tc_gemm_launch(fc1, M, ns, s, pdl));
+                if (as_form && tc_gemm_as_supported(fc1))
+                    VT_LAUNCH(tc_gemm_as_launch(fc1, M, ns, s, pdl, t->sm_count));
+                else
+                    VT_LAUNCH(tc_gemm_launch(fc1, M, ns, s, pdl));
             }
             if (chain) {  // X += fc2_b + sum of the partials; LN1 of the next block / the final LN of the search rows
                 const bool last = l + 1 == t->depth;
@@ -160,7 +169,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                 r.ln_rows = last ? kNTx : kNTok, r.ln_row_off = last ? -kNTz : 0;
                 VT_LAUNCH(launch_reduce_ln(r, s, pdl));
             } else {
-                VT_LAUNCH(tc_gemm_launch(p.fc2, M, ns, s, pdl));  // fused: + LN1 of the next block / the final LN of the search rows
+                VT_LAUNCH(tc_gemm_launch(p.fc2, M, ns, s, pdl, false, tp_mcast));  // fused: + LN1 of the next block / the final LN of the search rows
             }
             if (t->debug_capture)
                 VT_CUDA(cudaMemcpyAsync(t->d_dbg + (size_t)(l + 1) * t->maxT * kNTok * D, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));

@@ -143,6 +143,9 @@ struct vt_tracker {
     bool pdl = true;            // programmatic dependent launch along the kernel chain
     bool spread_ok = true;      // latency-mode GEMM forms allowed (VT_B200_NO_SPREAD disables)
     int unchain_n = kUnchainTargets;  // active targets from which the MLP runs unchained (VT_B200_UNCHAIN_N overrides)
+    int sm_count = 148;         // SMs of the device (grid sizing of the throughput forms)
+    int as_rows = 1024;         // rows (M) from which QKV / unchained FC1 run in the A-stationary throughput form (VT_B200_AS_ROWS; 0 = never)
+    int tp_rows = 1024;         // rows from which proj / FC2 multicast their activation tile across the LayerNorm cluster (VT_B200_TP_ROWS; 0 = never)
     bool counted = false;       // this handle is included in g_live_handles
     bool tc_attention = false;  // head_dim == 64
     TcAttentionPlan plan_att;

@@ -900,6 +900,39 @@ def test_kernel_forms_agree(api, weight_dir, monkeypatch):
                     assert abs(a.score - b.score) < 1e-5, (spec.name, env, a, b)
 
 
+@pytest.mark.parametrize("gemm_mode", [1, 2, 3], ids=["tcgen05x3", "tcgen05", "tcgen05fp16"])
+def test_throughput_gemm_forms_bit_identical(api, weight_dir, monkeypatch, gemm_mode):
+    """The throughput forms that run from 1024 rows on (cfg4 / stream groups: QKV and FC1 in the A-stationary kernel of gemm_as.cu,
+    FC2 with the activation tile multicast across its LayerNorm cluster) add the same products in the same order as the one-tile
+    kernels: forced onto a 2-target handle (640 rows, 5 row tiles with a ragged last one), scores and boxes must be IDENTICAL."""
+    import gc
+    gc.collect()
+    w = weights.ensure_weight_file("tiny", weight_dir, variant="wild")
+    spec = synth.StreamSpec("two", 1920, 1080, 1005, [(400, 300, 140, 100, 4, 2), (1300, 600, 120, 160, -3, 3)])
+    st = synth.SyntheticStream(spec)
+    frames = [np.ascontiguousarray(st.frame(i)).reshape(-1) for i in range(5)]
+
+    def run(env):
+        for k in ("VT_B200_NO_SPREAD", "VT_B200_UNCHAIN_N", "VT_B200_AS_ROWS", "VT_B200_TP_ROWS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        trk = api.VitTrack.new(w, spec.width, spec.height, gemm_mode=gemm_mode, max_targets=2)
+        for k, b in enumerate(st.target_boxes(0)):
+            trk.init(frames[0], api.BBox(*b), target=k)
+        out = [trk.update_all(f) for f in frames[1:]]
+        trk.close()
+        return out
+
+    base = {"VT_B200_NO_SPREAD": "1", "VT_B200_UNCHAIN_N": "1"}
+    ref = run(dict(base, VT_B200_AS_ROWS="0", VT_B200_TP_ROWS="0"))
+    got = run(dict(base, VT_B200_AS_ROWS="1", VT_B200_TP_ROWS="1"))
+    for fa, fb in zip(got, ref):
+        for a, b in zip(fa, fb):
+            assert a.success and a.status == 0, a
+            assert a.bbox == b.bbox and a.score == b.score, (a, b)
+
+
 # ---- SURVEY.md App. A.7 variant switches ----------------------------------------------------------------------------------------
 def _quirk_norm():
     g = golden("trackervit_variants.json")
