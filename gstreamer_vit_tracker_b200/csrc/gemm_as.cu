@@ -26,6 +26,7 @@ constexpr int kAsStages = 4;           // weight k-block stages in flight
 constexpr int kAsMaxKb = 3;            // K <= 192
 constexpr int kAsThreads = 64 + kTcThreads;  // TMA warp, MMA warp, 16 epilogue warps
 constexpr int kAsChunk = 64;           // columns per accumulator / epilogue step
+constexpr int kMaxAsChainN = 192;      // widest chained second GEMM (TMEM: 2 x 128 + 64 + N2 <= 512 columns)
 
 template <int NSPLIT>
 struct AsSmem {
@@ -109,40 +110,40 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {  // ---- MMA issuer
-            constexpr uint32_t idesc = umma_idesc_h<kF16>(kTcBM, kAsChunk), idesc2n = umma_idesc_h<kF16>(kTcBM, 2 * kAsChunk);
-            int it = 0;
-            for (int i = 0; i < my_chunks; ++i) {
-                const int buf = i & 1;
-                if (i >= 2) {  // the epilogue of chunk i - 2 has read this accumulator
-                    ok &= mbar_wait(&acc_empty[buf], ((i >> 1) - 1) & 1);
-                    tcgen05_fence_after();
-                }
-                const uint32_t acc = tmem + buf * kAccCols;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % kAsStages;
-                    if (i == 0) ok &= mbar_wait(&a_bar[kb], 0);
-                    ok &= mbar_wait(&full_bar[s], (it / kAsStages) & 1);
-                    tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + kb * kParts * kTileABytes);
-                    const uint32_t sb = smem_u32(smem + SM::kOffB + s * SM::kStageBytes);
+        // ---- MMA issuer: the whole warp walks the loop (uniform control flow, waits included), one elected lane issues
+        constexpr uint32_t idesc = umma_idesc_h<kF16>(kTcBM, kAsChunk), idesc2n = umma_idesc_h<kF16>(kTcBM, 2 * kAsChunk);
+        const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem)), b_lo0 = umma_desc_lo(smem_u32(smem + SM::kOffB));
+        int it = 0;
+        for (int i = 0; i < my_chunks; ++i) {
+            const int buf = i & 1;
+            if (i >= 2) {  // the epilogue of chunk i - 2 has read this accumulator
+                ok &= mbar_wait(&acc_empty[buf], ((i >> 1) - 1) & 1);
+                tcgen05_fence_after();
+            }
+            const uint32_t acc = tmem + buf * kAccCols;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % kAsStages;
+                if (i == 0) ok &= mbar_wait(&a_bar[kb], 0);
+                ok &= mbar_wait(&full_bar[s], (it / kAsStages) & 1);
+                tcgen05_fence_after();
+                const uint32_t sa = a_lo0 + kb * (kParts * kTileABytes >> 4), sb = b_lo0 + s * (SM::kStageBytes >> 4);
+                if (elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < kTcBK / 16; ++k) {
-                        const uint32_t koff = k * 32;
-                        const uint64_t dAhi = umma_desc_sw128(sa + koff), dBhi = umma_desc_sw128(sb + koff);
+                        const uint64_t dAhi = umma_desc_from_lo(sa + 2 * k), dBhi = umma_desc_from_lo(sb + 2 * k);
                         if (kLo) {
                             umma_bf16(acc, dAhi, dBhi, idesc2n, (kb | k) != 0);
-                            umma_bf16(acc, umma_desc_sw128(sa + kTileABytes + koff), dBhi, idesc, 1);
+                            umma_bf16(acc, umma_desc_from_lo(sa + (kTileABytes >> 4) + 2 * k), dBhi, idesc, 1);
                         } else {
                             umma_bf16(acc, dAhi, dBhi, idesc, (kb | k) != 0);
                         }
                     }
                     umma_commit(&empty_bar[s]);
+                    if (kb == num_kb - 1) umma_commit(&acc_full[buf]);
                 }
-                umma_commit(&acc_full[buf]);
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
         // ---- epilogue warps: thread (row, g) owns 16 accumulator columns of its row in every chunk
         const int e = tid - 64, ew = e >> 5;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
             for (int j = 0; j < CPT; ++j) v[j] += bias_v[j];
             if (a.gelu) {
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) v[j] = gelu_erf(v[j]);
+                for (int j = 0; j < CPT; j += 2) gelu_erf2(v[j], v[j + 1]);
             }
             uint8_t* t_hi = smem + SM::kOffO + buf * kParts * SM::kTileOBytes;
             uint8_t* t_lo = t_hi + SM::kTileOBytes;
@@ -226,10 +227,257 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
     if (warp == 1) tmem_dealloc(tmem, 2 * kAccCols);
 }
 
+// ---- chained MLP, A-stationary ---------------------------------------------------------------------------------------------------------
+//   P[z][M, N2] = GELU( A[M, K] * W1[hidden range z, K]^T + b1 ) * W2[N2, hidden range z]^T        (bf16x3 only)
+// One CTA owns a 128-row tile and a contiguous range of 64-column hidden chunks.  Per chunk: MMA1 (as above) -> the epilogue warps apply
+// bias + GELU and write the hidden tile back into TENSOR MEMORY as packed bf16 (hi, lo) — a UMMA A operand — -> MMA2 multiplies it with
+// the matching 64-wide K-slice of W2 and accumulates into a third TMEM accumulator [128 x N2] that lives across all chunks of the CTA.
+// The hidden activations [M, hidden] never exist in memory (unchained: 15.7 MB written and read back three times at 5120 rows), and a
+// row tile leaves (hidden / 64) / chunks-per-CTA fp32 partial planes instead of hidden / 64; reduce_ln_kernel adds them in plane order
+// with bias, residual and the next LayerNorm.  W1 k-blocks and W2 row blocks share one ring of 16 KB stages, in MMA issue order:
+//   W1(0) | W1(1) W2(0) | W1(2) W2(1) | ... | W2(n-1)       (MMA1 of chunk c + 1 is issued before MMA2 of chunk c: it runs under c's GELU)
+// TMEM: accumulators of MMA1 2 x 128 columns, hidden tile 64, MMA2 accumulator N2 <= 192  = 512 columns.
+constexpr int kMlpStages = 7;
+constexpr int kMlpStageBytes = 2 * kAsChunk * kTcBK * 2;  // [W_hi; W_lo] of a 64 x 64 block
+constexpr int kMlpABytes = kAsMaxKb * 2 * kTileABytes;
+constexpr int kMlpSmemTotal = kMlpABytes + kMlpStages * kMlpStageBytes + 1024;
+constexpr uint32_t kMlpColH = 256, kMlpColAcc2 = 320;
+static_assert(kTcBM * kMaxAsChainN * 4 <= kMlpABytes + kMlpStages * kMlpStageBytes, "the partial tile is staged over the dead operand buffers");
+
+__device__ __forceinline__ void mlp_group(int g, int n, bool& is_w2, int& chunk) {
+    if (g == 0) is_w2 = false, chunk = 0;
+    else if (g == 2 * n - 1) is_w2 = true, chunk = n - 1;
+    else if (g & 1) is_w2 = false, chunk = (g + 1) >> 1;
+    else is_w2 = true, chunk = (g >> 1) - 1;
+}
+
+__global__ void __launch_bounds__(kAsThreads, 1) gemm_as_mlp_kernel(const __grid_constant__ TcMaps mp, const TcGemmArgs a, const int chunks_per_cta) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a_bar[kAsMaxKb], full_bar[kMlpStages], empty_bar[kMlpStages], acc_full[2], acc_empty[2], h_full, h_free, acc2_full;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned long long* trace_slot;
+    constexpr int CPT = kAsChunk / kTcColGroups;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem + kMlpABytes;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * kTcBM;
+    const int num_kb = a.K / kTcBK, n_chunks = a.N / kAsChunk, N2 = a.chain_n, nb2 = N2 / 64;
+    const int c_begin = blockIdx.x * chunks_per_cta;
+    const int c_end = c_begin + chunks_per_cta < n_chunks ? c_begin + chunks_per_cta : n_chunks;
+    const int n = c_end - c_begin, n_groups = 2 * n, n_items = n * (num_kb + nb2);
+    bool ok = true;
+    TraceRec tr;
+    tr.begin(&trace_slot, a.trace, a.trace_id);
+    __shared__ unsigned long long ev_buf[kTraceEvents][2];
+    __shared__ unsigned ev_cnt;
+    TraceEvents ev;
+    ev.begin(ev_buf, &ev_cnt, &tr);
+
+    // weight stream walker of the producer (thread 0): (group, index in group, item)
+    int p_g = 0, p_j = 0, p_it = 0;
+    auto issue_next = [&]() {
+        bool w2;
+        int ch;
+        mlp_group(p_g, n, w2, ch);
+        const int st = p_it % kMlpStages, c = c_begin + ch;
+        uint8_t* sb = ring + st * kMlpStageBytes;
+        mbar_arrive_expect_tx(&full_bar[st], kMlpStageBytes);
+        if (!w2) {  // W1[64 c .., 64 j ..]: k-block j of hidden chunk c
+            tma_load_2d(sb, &mp.Bhi, &full_bar[st], p_j * kTcBK, c * kAsChunk);
+            tma_load_2d(sb + kAsChunk * 128, &mp.Blo, &full_bar[st], p_j * kTcBK, c * kAsChunk);
+        } else {    // W2[64 j .., 64 c ..]: output row block j, K-slice = hidden chunk c
+            tma_load_2d(sb, &mp.B2hi, &full_bar[st], c * kAsChunk, p_j * 64);
+            tma_load_2d(sb + kAsChunk * 128, &mp.B2lo, &full_bar[st], c * kAsChunk, p_j * 64);
+        }
+        ++p_it;
+        if (++p_j == (w2 ? nb2 : num_kb)) p_j = 0, ++p_g;
+    };
+
+    if (tid == 0) {
+        tma_prefetch_desc(&mp.Ahi), tma_prefetch_desc(&mp.Alo), tma_prefetch_desc(&mp.Bhi), tma_prefetch_desc(&mp.Blo);
+        tma_prefetch_desc(&mp.B2hi), tma_prefetch_desc(&mp.B2lo);
+        for (int i = 0; i < kAsMaxKb; ++i) mbar_init(&a_bar[i], 1);
+        for (int s = 0; s < kMlpStages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
+        for (int b = 0; b < 2; ++b) mbar_init(&acc_full[b], 1), mbar_init(&acc_empty[b], kTcThreads / 32);
+        mbar_init(&h_full, kTcThreads / 32), mbar_init(&h_free, 1), mbar_init(&acc2_full, 1);
+        fence_barrier_init();
+        while (p_it < n_items && p_it < kMlpStages) issue_next();  // weights never depend on the preceding kernel
+    }
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_s, 512);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    pdl_wait();
+    if (tid == 0) tr.mark(2);
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer
+            for (int kb = 0; kb < num_kb; ++kb) {
+                uint8_t* sa = smem + kb * 2 * kTileABytes;
+                mbar_arrive_expect_tx(&a_bar[kb], 2 * kTileABytes);
+                tma_load_2d(sa, &mp.Ahi, &a_bar[kb], kb * kTcBK, m0);
+                tma_load_2d(sa + kTileABytes, &mp.Alo, &a_bar[kb], kb * kTcBK, m0);
+            }
+            while (p_it < n_items) {
+                ok &= mbar_wait(&empty_bar[p_it % kMlpStages], ((p_it / kMlpStages) - 1) & 1);
+                ev.event(2000 + p_it);  // item p_it is issued
+                issue_next();
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---- MMA issuer: the whole warp walks the loop, one elected lane issues
+        constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, kAsChunk), idesc2n = umma_idesc_bf16(kTcBM, 2 * kAsChunk);
+        const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem)), b_lo0 = umma_desc_lo(smem_u32(ring));
+        int it = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            bool w2;
+            int ch;
+            mlp_group(g, n, w2, ch);
+            if (!w2) {  // MMA1 of hidden chunk ch -> accumulator ch % 2
+                const int buf = ch & 1;
+                if (ch >= 2) {
+                    ok &= mbar_wait(&acc_empty[buf], ((ch >> 1) - 1) & 1);
+                    tcgen05_fence_after();
+                }
+                const uint32_t acc = tmem + buf * 128;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kMlpStages;
+                    if (ch == 0) ok &= mbar_wait(&a_bar[kb], 0);
+                    ok &= mbar_wait(&full_bar[s], (it / kMlpStages) & 1);
+                    tcgen05_fence_after();
+                    if (lane == 0) ev.event(1000 + it);  // item `it` has landed (seen by the MMA warp)
+                    const uint32_t sa = a_lo0 + kb * (2 * kTileABytes >> 4), sb = b_lo0 + s * (kMlpStageBytes >> 4);
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int k = 0; k < kTcBK / 16; ++k) {
+                            const uint64_t dAhi = umma_desc_from_lo(sa + 2 * k), dBhi = umma_desc_from_lo(sb + 2 * k);
+                            umma_bf16(acc, dAhi, dBhi, idesc2n, (kb | k) != 0);
+                            umma_bf16(acc, umma_desc_from_lo(sa + (kTileABytes >> 4) + 2 * k), dBhi, idesc, 1);
+                        }
+                        umma_commit(&empty_bar[s]);
+                        if (kb == num_kb - 1) umma_commit(&acc_full[buf]);
+                    }
+                    __syncwarp();
+                }
+            } else {    // MMA2: acc2[:, 64 j ..] += H(ch) x W2[64 j .., chunk ch]^T, H read from tensor memory
+                ok &= mbar_wait(&h_full, ch & 1);
+                tcgen05_fence_after();
+                for (int j = 0; j < nb2; ++j, ++it) {
+                    const int s = it % kMlpStages;
+                    ok &= mbar_wait(&full_bar[s], (it / kMlpStages) & 1);
+                    tcgen05_fence_after();
+                    if (lane == 0) ev.event(1000 + it);
+                    const uint32_t sb = b_lo0 + s * (kMlpStageBytes >> 4);
+                    const uint32_t acc2 = tmem + kMlpColAcc2 + 64 * j;
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int k = 0; k < kAsChunk / 16; ++k) {
+                            const uint32_t ah = tmem + kMlpColH + 16 * k;
+                            const uint64_t dBhi = umma_desc_from_lo(sb + 2 * k), dBlo = umma_desc_from_lo(sb + (kAsChunk * 128 >> 4) + 2 * k);
+                            umma_bf16_ta(acc2, ah, dBhi, idesc, (ch | k) != 0);
+                            umma_bf16_ta(acc2, ah, dBlo, idesc, 1);
+                            umma_bf16_ta(acc2, ah + 8, dBhi, idesc, 1);
+                        }
+                        umma_commit(&empty_bar[s]);
+                        if (j == nb2 - 1) {
+                            umma_commit(&h_free);  // the hidden-tile columns may be rewritten once these MMAs have read them
+                            if (ch == n - 1) umma_commit(&acc2_full);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) ev.event(140 + g);
+            }
+        }
+    } else {
+        // ---- epilogue warps
+        const int e = tid - 64, ew = e >> 5;
+        const int quarter = warp & 3, row = quarter * 32 + lane, g = ew >> 2;
+        const TileRows tr_rows(m0, a.period, a.batch_off);
+        const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+        for (int i = 0; i < n; ++i) {
+            const int buf = i & 1, nc = (c_begin + i) * kAsChunk + g * CPT;
+            float bias_v[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; j += 4) {
+                const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + nc + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                bias_v[j] = b4.x, bias_v[j + 1] = b4.y, bias_v[j + 2] = b4.z, bias_v[j + 3] = b4.w;
+            }
+            ok &= mbar_wait(&acc_full[buf], (i >> 1) & 1);
+            tcgen05_fence_after();
+            if (e == 0 && i == 0) tr.mark(6);
+            if (e == 0) ev.event(10 + i);  // epilogue: accumulator of chunk i ready
+            float v[CPT], hl[CPT];
+            tmem_ld_cols(lane_base + buf * 128 + g * CPT, v);
+            tmem_ld_cols(lane_base + buf * 128 + kAsChunk + g * CPT, hl);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) v[j] += hl[j];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) v[j] += bias_v[j];
+            if (a.gelu) {
+#pragma unroll
+                for (int j = 0; j < CPT; j += 2) gelu_erf2(v[j], v[j + 1]);
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) split2_bf16(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
+            if (e == 0) ev.event(20 + i);  // epilogue: GELU of chunk i done
+            if (i >= 1) {  // MMA2 of chunk i - 1 has read the hidden-tile columns
+                ok &= mbar_wait(&h_free, (i - 1) & 1);
+                tcgen05_fence_after();
+            }
+            if (e == 0) ev.event(30 + i);  // epilogue: hidden-tile columns free
+            const uint32_t ta = lane_base + kMlpColH + g * 16;   // thread (row, g) = K-step g of MMA2: 8 columns hi, 8 columns lo
+            tmem_st_32x8(ta, hi);
+            tmem_st_32x8(ta + 8, lo);
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_full);
+            if (e == 0 && i == 0) tr.mark(4);
+        }
+        // ---- the CTA's partial product [128, N2] -> plane blockIdx.x (staged over the dead operand buffers: every MMA has completed)
+        ok &= mbar_wait(&acc2_full, 0);
+        tcgen05_fence_after();
+        if (e == 0) tr.mark(5);
+        const int cols_per = N2 / kTcColGroups, sw = row & 7;
+        for (int c = g * cols_per; c < (g + 1) * cols_per; c += 16) {
+            float pv[16];
+            tmem_ld_32x16(lane_base + kMlpColAcc2 + c, pv);
+            uint8_t* prow = smem + (c >> 5) * (kTcBM * 128) + row * 128;
+            const int ch0 = (c & 31) >> 2;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(prow + (((ch0 + q) ^ sw) << 4)) = make_float4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcThreads) : "memory");
+        for (int cb = 0; cb < N2 / 32; ++cb)
+            tile_to_global<128>(smem + cb * (kTcBM * 128), a.p, (int64_t)cb * 128, tr_rows, 0, 0, blockIdx.x, e);
+        if (e == 0) tr.mark(7);
+    }
+    if (!ok && a.err) atomicExch(a.err, 1);
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) tr.mark(3), ev.flush(a.trace);
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 cudaError_t tc_gemm_as_setup() {
     cudaError_t e = cudaFuncSetAttribute(gemm_as_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AsSmem<1>::kTotal);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_as_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AsSmem<2>::kTotal);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_as_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AsSmem<3>::kTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_as_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmemTotal);
     return e;
 }
 
@@ -240,19 +488,41 @@ bool tc_gemm_as_supported(const TcGemmPlan& p) {
            !a.ln_g && !a.c_on && !a.residual && !a.pos && !a.relu && (a.o_mode == 1 || a.o_mode == 2) && (a.o_mode != 2 || (a.N / 3) % 64 == 0);
 }
 
+// as many CTAs per row tile as fit in one wave, chunks dealt out evenly (the makespan is the largest share); returns CTAs per row tile
+int tc_gemm_as_split(int M, int n_chunks, int sm_count, int* per_cta) {
+    const int row_tiles = (M + kTcBM - 1) / kTcBM;
+    int smax = sm_count / row_tiles;
+    if (smax < 1) smax = 1;
+    if (smax > n_chunks) smax = n_chunks;
+    *per_cta = (n_chunks + smax - 1) / smax;
+    return (n_chunks + *per_cta - 1) / *per_cta;
+}
+
+// plan = an FC1 plan with tc_plan_chain applied (bf16x3 operands); writes *planes partial planes to the chain output
+bool tc_gemm_as_mlp_supported(const TcGemmPlan& p, int nsplit) {
+    const TcGemmArgs& a = p.args;
+    return nsplit == 3 && p.bn == 64 && a.K % kTcBK == 0 && a.K / kTcBK <= kAsMaxKb && a.N % kAsChunk == 0 && !a.conv_feat && !a.kb_per_split &&
+           a.chain_n > 0 && a.chain_n % 64 == 0 && a.chain_n <= kMaxAsChainN && !a.ln_g && !a.c_on && !a.residual && !a.pos && !a.relu && a.o_mode == 3;
+}
+cudaError_t tc_gemm_as_mlp_launch(const TcGemmPlan& p, int M, cudaStream_t s, bool pdl, int sm_count, int* planes) {
+    if (!tc_gemm_as_mlp_supported(p, 3) || M <= 0) return cudaErrorInvalidValue;
+    TcGemmArgs a = p.args;
+    a.M = M;
+    a.chain_slices = 0, a.dup_hl = 0, a.dup_ln = 0, a.mcast = 0;
+    int per_cta = 1;
+    const int sx = tc_gemm_as_split(M, a.N / kAsChunk, sm_count, &per_cta);
+    *planes = sx;
+    return launch_ex(gemm_as_mlp_kernel, dim3(sx, (M + kTcBM - 1) / kTcBM, 1), dim3(kAsThreads), kMlpSmemTotal, s, pdl, 1, p.maps, a, per_cta);
+}
+
 cudaError_t tc_gemm_as_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl, int sm_count) {
     if (M <= 0) return cudaSuccess;
     if (!tc_gemm_as_supported(p)) return cudaErrorInvalidValue;
     TcGemmArgs a = p.args;
     a.M = M;
     a.chain_slices = 0, a.dup_hl = 0, a.dup_ln = 0, a.mcast = 0;
-    const int row_tiles = (M + kTcBM - 1) / kTcBM, n_chunks = a.N / kAsChunk;
-    // as many CTAs per row tile as fit in one wave, chunks dealt out evenly (the makespan is the largest share)
-    int smax = sm_count / row_tiles;
-    if (smax < 1) smax = 1;
-    if (smax > n_chunks) smax = n_chunks;
-    const int per_cta = (n_chunks + smax - 1) / smax;
-    dim3 grid((n_chunks + per_cta - 1) / per_cta, row_tiles, 1);
+    int per_cta = 1;
+    dim3 grid(tc_gemm_as_split(M, a.N / kAsChunk, sm_count, &per_cta), (M + kTcBM - 1) / kTcBM, 1);
     if (nsplit == 3) return launch_ex(gemm_as_kernel<3>, grid, dim3(kAsThreads), AsSmem<3>::kTotal, s, pdl, 1, p.maps, a, per_cta);
     if (nsplit == 2) return launch_ex(gemm_as_kernel<2>, grid, dim3(kAsThreads), AsSmem<2>::kTotal, s, pdl, 1, p.maps, a, per_cta);
     return launch_ex(gemm_as_kernel<1>, grid, dim3(kAsThreads), AsSmem<1>::kTotal, s, pdl, 1, p.maps, a, per_cta);

@@ -15,16 +15,32 @@ constexpr int kTcBM = 128, kTcBK = 64;
 constexpr int kTileABytes = kTcBM * kTcBK * 2;  // 16 KB, one precision part
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf by Abramowitz & Stegun 7.1.26 (one rcp, five FMAs, one ex2): |abs error| < 7e-7 in fp32
-// for erf, < 3e-7 for GELU — an order of magnitude below the bf16x3 operand error — at a third of erff's instruction count (the
-// FC1 epilogue is instruction-issue bound: 16 GELUs per thread).
+// for erf, < 3e-7 for GELU — an order of magnitude below the bf16x3 operand error.  The FC1 epilogue is instruction-issue bound (16 GELUs
+// per thread and chunk: 1.25 us of a 2.2 us epilogue step at 5120 rows), so two values go through the polynomial as one packed fp32 pair
+// (FFMA2 / FMUL2: half the issue slots; only the two MUFU ops per value stay scalar).  Every operation is written out (no contraction
+// left to the compiler), so every GEMM form computes bit-identical GELUs.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+    const uint64_t x = f2_pack(x0, x1);
+    const uint64_t z = f2_mul(x & 0x7fffffff7fffffffull, f2_bcast(0.70710678118654752440f));
+    float d0, d1, t0, t1;
+    f2_unpack(f2_fma(f2_bcast(0.3275911f), z, f2_bcast(1.f)), d0, d1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+    const uint64_t t = f2_pack(t0, t1);
+    uint64_t p = f2_fma(f2_bcast(1.061405429f), t, f2_bcast(-1.453152027f));
+    p = f2_fma(p, t, f2_bcast(1.421413741f)), p = f2_fma(p, t, f2_bcast(-0.284496736f)), p = f2_fma(p, t, f2_bcast(0.254829592f));
+    float a0, a1;
+    f2_unpack(f2_mul(f2_mul(z, f2_bcast(-1.4426950408889634f)), z), a0, a1);
+    const uint64_t e = f2_pack(ex2_approx(a0), ex2_approx(a1));
+    // s = copysign(1 - p t e, x)  (1 - p t e is in [0, 1): its sign bit is clear)
+    const uint64_t s = f2_fma(f2_mul(f2_mul(p, t), e), f2_bcast(-1.f), f2_bcast(1.f)) | (x & 0x8000000080000000ull);
+    const uint64_t h = f2_mul(x, f2_bcast(0.5f));
+    f2_unpack(f2_fma(h, s, h), x0, x1);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f), p = fmaf(p, t, -0.284496736f), p = fmaf(p, t, 0.254829592f);
-    const float e = ex2_approx(-1.4426950408889634f * z * z);
-    return 0.5f * x * (1.f + copysignf(1.f - p * t * e, x));
+    float y = x, dummy = 0.f;
+    gelu_erf2(y, dummy);
+    return y;
 }
 
 constexpr int kTcThreads = 512;                         // 16 warps: warp w reads TMEM lane quarter w % 4, column group w / 4

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     for (int j = 0; j < CPT; ++j) v[j] += bias_v[j];
     if (a.gelu) {
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < CPT; j += 2) gelu_erf2(v[j], v[j + 1]);
     }
     if (a.relu) {
 #pragma unroll

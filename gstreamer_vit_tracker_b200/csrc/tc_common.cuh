@@ -86,6 +86,34 @@ struct TraceRec {
         if (rec) rec[k] = globaltimer_ns();
     }
 };
+// Free-form events of the traced CTA (diagnostics; tools/chain_timeline.py --events): any thread appends (code, time) to a small
+// shared-memory log (one shared-memory atomic, ~20 clk), thread 0 copies the log into records {256 + code, t, kernel id} of the trace
+// buffer at the end of the kernel.
+constexpr int kTraceEvents = 96;
+struct TraceEvents {
+    unsigned long long (*buf)[2];
+    unsigned* cnt;
+    const TraceRec* tr;
+    __device__ __forceinline__ void begin(unsigned long long (*b)[2], unsigned* c, const TraceRec* t) {
+        buf = b, cnt = c, tr = t;
+        if (threadIdx.x == 0) *c = 0;
+    }
+    __device__ __forceinline__ void event(int code) const {  // valid after the first __syncthreads()
+        if (!*tr->slot) return;
+        const unsigned i = atomicAdd(cnt, 1u);
+        if (i < (unsigned)kTraceEvents) buf[i][0] = 256ull + (unsigned long long)code, buf[i][1] = globaltimer_ns();
+    }
+    __device__ __forceinline__ void flush(unsigned long long* trace) const {  // thread 0, after the closing __syncthreads()
+        unsigned long long* rec = *tr->slot;
+        if (!rec) return;
+        const unsigned n = *cnt < (unsigned)kTraceEvents ? *cnt : (unsigned)kTraceEvents;
+        const unsigned long long i0 = atomicAdd(trace, (unsigned long long)n);
+        for (unsigned i = 0; i < n && i0 + i < 2048; ++i) {
+            unsigned long long* r = trace + 1 + 8 * (i0 + i);
+            r[0] = buf[i][0], r[1] = buf[i][1], r[2] = rec[0], r[3] = r[4] = r[5] = r[6] = r[7] = 0;
+        }
+    }
+};
 constexpr size_t kTraceWords = 1 + 8 * 2048;
 
 // ---- thread-block clusters / distributed shared memory ------------------------------------------------
@@ -173,6 +201,24 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)1 << 46;                         // descriptor version   bits [46,48) = 1 on sm_100
     d |= (uint64_t)2 << 61;                         // layout type          bits [61,64) = SWIZZLE_128B
     return d;
+}
+// The same descriptor from its two halves: the high word is constant for every 128B-swizzled K-major tile, the low word is
+// (address >> 4) | LBO.  MMA issue loops keep `lo` of a tile in a (uniform) register and step it by 2 per K = 16 slice (32 bytes): one
+// add per operand and MMA instead of the shift / mask / or chain of umma_desc_sw128 — the issuing thread's instruction latency, not the
+// tensor pipe, paced the MMAs (measured: ~170 clk per UMMA pair step issued against a 96 clk floor).
+constexpr uint32_t kUmmaDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kUmmaDescHi));
+    return d;
+}
+// One lane of the (converged) warp: the compiler knows the guarded region runs in a single thread, so uniform-datapath instructions such
+// as tcgen05.mma need no per-thread election loop around them.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 // kind::f16, A = B = bf16, D = fp32, both operands K-major, dense.
 // a_format = b_format = F16 (0): same instruction kind, 10 mantissa bits instead of 7 (VT_GEMM_TCGEN05_FP16)
@@ -328,6 +374,30 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes; results identical to the scalar .rn ops) ----
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_bcast(float c) { return f2_pack(c, c); }
 
 // fp32 -> (hi, lo) bf16 split: v ~= hi + lo with ~16 mantissa bits
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {

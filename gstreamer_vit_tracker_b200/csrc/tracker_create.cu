@@ -369,6 +369,7 @@ vt_status vt_tracker_create(const vt_config* cfg_in, vt_tracker** out) {
         VT_TRY(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
         if (const char* e = getenv("VT_B200_AS_ROWS")) t->as_rows = atoi(e);
         if (const char* e = getenv("VT_B200_TP_ROWS")) t->tp_rows = atoi(e);
+        t->as_mlp = !getenv("VT_B200_NO_AS_MLP");
         t->fuse_ln = D / 64 <= 8 && !getenv("VT_B200_NO_FUSE_LN");
         t->pdl = !getenv("VT_B200_NO_PDL");
         t->spread_ok = !getenv("VT_B200_NO_SPREAD");

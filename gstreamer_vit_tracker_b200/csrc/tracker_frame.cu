@@ -148,8 +148,14 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             // Chained form (FC2 partial products inside the FC1 kernel, summed by reduce_ln): shortest critical path for a few targets.
             // From kUnchainTargets targets on the 12 fp32 partial planes per row tile cost more than the hidden round trip
             // (cfg4, 16 targets: ViT stage 905 -> 819 us unchained), so FC1 writes the hidden tile and FC2 runs as its own GEMM.
-            const bool chain = t->chain_mlp && n < t->unchain_n;
-            if (chain) {
+            // ... except in the A-stationary form, where a CTA accumulates the chained product over all of its hidden chunks (3 planes
+            // per row tile at 5120 rows, and no hidden round trip at all)
+            const bool as_mlp = as_form && t->chain_mlp && t->as_mlp && tc_gemm_as_mlp_supported(p.fc1, ns);
+            const bool chain = as_mlp || (t->chain_mlp && n < t->unchain_n);
+            int planes = (int)(Hd / 64);
+            if (as_mlp) {
+                VT_LAUNCH(tc_gemm_as_mlp_launch(p.fc1, M, s, pdl, t->sm_count, &planes));
+            } else if (chain) {
                 VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s, pdl, spread));
             } else {
                 TcGemmPlan fc1 = p.fc1;
@@ -162,7 +168,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             if (chain) {  // X += fc2_b + sum of the partials; LN1 of the next block / the final LN of the search rows
                 const bool last = l + 1 == t->depth;
                 ReduceLnArgs r{};
-                r.P = t->Pbuf, r.np = Hd / 64, r.p_stride = (int64_t)t->maxT * kNTok * D, r.bias = b.fc2_b, r.add = t->X, r.add_period = 0;
+                r.P = t->Pbuf, r.np = planes, r.p_stride = (int64_t)t->maxT * kNTok * D, r.bias = b.fc2_b, r.add = t->X, r.add_period = 0;
                 r.X = t->X, r.M = M, r.D = D, r.period = kNTok, r.x_rows = kNTok, r.x_row_off = 0;
                 r.ln_g = last ? t->lnf_g : t->blk[l + 1].ln1_g, r.ln_b = last ? t->lnf_b : t->blk[l + 1].ln1_b;
                 r.ln_hi = last ? t->yf_hi : t->ln_hi, r.ln_lo = LO(last ? t->yf_lo : t->ln_lo);

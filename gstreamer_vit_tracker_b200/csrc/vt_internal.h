@@ -346,6 +346,11 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t 
 cudaError_t tc_gemm_as_setup();
 bool tc_gemm_as_supported(const TcGemmPlan& p);
 cudaError_t tc_gemm_as_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream_t s, bool pdl, int sm_count);
+// chained MLP in the A-stationary form (bf16x3): plan = an FC1 plan with tc_plan_chain applied; the GELU'd hidden tile goes back into
+// tensor memory as the A operand of the chained product, which accumulates over all hidden chunks of the CTA; *planes partial planes
+// (CTAs per row tile) are written to the chain output for reduce_ln_kernel
+bool tc_gemm_as_mlp_supported(const TcGemmPlan& p, int nsplit);
+cudaError_t tc_gemm_as_mlp_launch(const TcGemmPlan& p, int M, cudaStream_t s, bool pdl, int sm_count, int* planes);
 struct TcAttentionPlan {      // kernel parameter block (__grid_constant__)
     CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo;
     CUtensorMap mW2hi, mW2lo;        // chained form: W_proj [D][D], boxes of 64 x 64

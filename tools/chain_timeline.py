@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--gemm", type=int, default=1)
     ap.add_argument("--frames", type=int, default=20)
     ap.add_argument("--targets", type=int, default=1)
+    ap.add_argument("--events", action="store_true", help="print the free-form events (TraceRec::event) of the first traced kernels")
     a = ap.parse_args()
     spec = synth.CONFIGS["cfg2"]
     st = synth.SyntheticStream(spec)
@@ -41,8 +42,15 @@ def main():
     trk.update_all(st.frame(3).copy())
     rec = trk.debug_trace().astype(np.int64)
     tm = trk.timing()
-    rec = rec[np.argsort(rec[:, 1])]
+    rec = rec[np.argsort(rec[:, 1], kind="stable")]
+    ev = rec[rec[:, 0] >= 256]
+    rec = rec[rec[:, 0] < 256]
     t0 = rec[0, 1]
+    if a.events:  # events of the traced CTA, relative to the dependency wait of the kernel they belong to (first 12 kernels)
+        for kid, te, tw, tend, *_ in rec[:12]:
+            mine = ev[(ev[:, 1] >= te) & (ev[:, 1] <= tend) & (ev[:, 2] == kid)]
+            if len(mine):
+                print(f"events of {NAMES.get(int(kid), str(kid))} @ {(te - t0) / 1e3:.2f}: " + " ".join(f"{int(c) - 256}:{(t - tw) / 1e3:.2f}" for c, t, *_ in mine))
     prev_end = None
     agg = {}
     print(f"{'kernel':8s} {'entry':>8s} {'prolog':>7s} {'body':>7s} {'gap':>7s} | marks 4..7 relative to the dependency wait"
