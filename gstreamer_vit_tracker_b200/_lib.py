@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvittrack_b200.so")
+LIB_PATH = os.environ.get("VT_B200_LIB") or os.path.join(_HERE, "libvittrack_b200.so")  # (override: A/B runs of two builds)
 
 VT_OK, VT_ERR_INVALID, VT_ERR_CUDA, VT_ERR_WEIGHTS, VT_ERR_CROP_OUTSIDE, VT_ERR_NOT_INIT, VT_ERR_GLYPH = 0, -1, -2, -3, -4, -5, -6
 VT_FMT_NV12, VT_FMT_RGB24, VT_FMT_GRAY8 = 0, 1, 2

@@ -102,7 +102,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
         fence_barrier_init();
     }
     if (ctrl) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             tma_prefetch_desc(&mQhi), tma_prefetch_desc(&mKhi), tma_prefetch_desc(&mVhi);
             if (P == 2) tma_prefetch_desc(&mQlo), tma_prefetch_desc(&mKlo), tma_prefetch_desc(&mVlo);
         }
@@ -111,7 +111,7 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (chain && ctrl && lane == 0) {  // weights never depend on the preceding kernel: W_proj[64 replica .. + 64)[64 h .. 64 h + 64)
+    if (chain && ctrl && elect_one_sync()) {  // weights never depend on the preceding kernel: W_proj[64 replica .. + 64)[64 h .. 64 h + 64)
         tma_prefetch_desc(&mp.mW2hi);
         mbar_arrive_expect_tx(&bar_w2, P * kAttChainW * 128);
         tma_load_2d(sW2, &mp.mW2hi, &bar_w2, h * kDh, replica * kAttChainW);
@@ -125,7 +125,9 @@ attention_tc_kernel(const __grid_constant__ TcAttentionPlan mp, __nv_bfloat16* _
     pdl_launch_dependents();
 
     if (ctrl) {
-        if (lane == 0) {
+        // (elect.sync instead of lane == 0: the compiler then knows that the region runs in one thread and emits the uniform-datapath
+        // instructions — tcgen05.mma, TMA — without a per-thread election loop around each of them)
+        if (elect_one_sync()) {
             // ---- TMA: Q + the first 160 keys on one barrier, the other 160 keys on a second (their UMMAs start while the first half
             // computes), V^T on a third (only needed after the softmax of the first chunk)
             constexpr int kHalfK = kNTok / 2, kHalfKBytes = kHalfK * kDh * 2;

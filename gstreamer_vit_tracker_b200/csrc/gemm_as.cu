@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
     tr.begin(&trace_slot, a.trace, a.trace_id);
 
     // ---- prologue: independent of the preceding kernel
-    if (tid == 0) {
+    if (warp == 0 && elect_one_sync()) {
         tma_prefetch_desc(&mp.Ahi), tma_prefetch_desc(&mp.Bhi);
         if (kLo) tma_prefetch_desc(&mp.Alo), tma_prefetch_desc(&mp.Blo);
         for (int i = 0; i < kAsMaxKb; ++i) mbar_init(&a_bar[i], 1);
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
     pdl_launch_dependents();
 
     if (warp == 0) {
-        if (lane == 0) {  // ---- TMA producer: the activation tile once, then the rest of the weight stream
+        if (elect_one_sync()) {  // ---- TMA producer: the activation tile once, then the rest of the weight stream
             for (int kb = 0; kb < num_kb; ++kb) {
                 uint8_t* sa = smem + kb * kParts * kTileABytes;
                 mbar_arrive_expect_tx(&a_bar[kb], kParts * kTileABytes);
@@ -110,24 +110,24 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ---- MMA issuer: the whole warp walks the loop (uniform control flow, waits included), one elected lane issues
+        // ---- MMA issuer: one elected lane (elect.sync: no per-thread election loop around tcgen05.mma); descriptors step by one add
         constexpr uint32_t idesc = umma_idesc_h<kF16>(kTcBM, kAsChunk), idesc2n = umma_idesc_h<kF16>(kTcBM, 2 * kAsChunk);
         const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem)), b_lo0 = umma_desc_lo(smem_u32(smem + SM::kOffB));
-        int it = 0;
-        for (int i = 0; i < my_chunks; ++i) {
-            const int buf = i & 1;
-            if (i >= 2) {  // the epilogue of chunk i - 2 has read this accumulator
-                ok &= mbar_wait(&acc_empty[buf], ((i >> 1) - 1) & 1);
-                tcgen05_fence_after();
-            }
-            const uint32_t acc = tmem + buf * kAccCols;
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % kAsStages;
-                if (i == 0) ok &= mbar_wait(&a_bar[kb], 0);
-                ok &= mbar_wait(&full_bar[s], (it / kAsStages) & 1);
-                tcgen05_fence_after();
-                const uint32_t sa = a_lo0 + kb * (kParts * kTileABytes >> 4), sb = b_lo0 + s * (SM::kStageBytes >> 4);
-                if (elect_one_sync()) {
+        if (elect_one_sync()) {
+            int it = 0;
+            for (int i = 0; i < my_chunks; ++i) {
+                const int buf = i & 1;
+                if (i >= 2) {  // the epilogue of chunk i - 2 has read this accumulator
+                    ok &= mbar_wait(&acc_empty[buf], ((i >> 1) - 1) & 1);
+                    tcgen05_fence_after();
+                }
+                const uint32_t acc = tmem + buf * kAccCols;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kAsStages;
+                    if (i == 0) ok &= mbar_wait(&a_bar[kb], 0);
+                    ok &= mbar_wait(&full_bar[s], (it / kAsStages) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t sa = a_lo0 + kb * (kParts * kTileABytes >> 4), sb = b_lo0 + s * (SM::kStageBytes >> 4);
 #pragma unroll
                     for (int k = 0; k < kTcBK / 16; ++k) {
                         const uint64_t dAhi = umma_desc_from_lo(sa + 2 * k), dBhi = umma_desc_from_lo(sb + 2 * k);
@@ -139,11 +139,11 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
                         }
                     }
                     umma_commit(&empty_bar[s]);
-                    if (kb == num_kb - 1) umma_commit(&acc_full[buf]);
                 }
-                __syncwarp();
+                umma_commit(&acc_full[buf]);
             }
         }
+        __syncwarp();
     } else {
         // ---- epilogue warps: thread (row, g) owns 16 accumulator columns of its row in every chunk
         const int e = tid - 64, ew = e >> 5;
@@ -274,35 +274,42 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_mlp_kernel(const __grid
     TraceEvents ev;
     ev.begin(ev_buf, &ev_cnt, &tr);
 
-    // weight stream walker of the producer (thread 0): (group, index in group, item)
+    // weight stream walker of the producer warp (all lanes keep the same state; one elected lane issues): (group, index in group, item)
     int p_g = 0, p_j = 0, p_it = 0;
-    auto issue_next = [&]() {
+    auto issue_next = [&](bool wait_empty) {
         bool w2;
         int ch;
         mlp_group(p_g, n, w2, ch);
         const int st = p_it % kMlpStages, c = c_begin + ch;
         uint8_t* sb = ring + st * kMlpStageBytes;
-        mbar_arrive_expect_tx(&full_bar[st], kMlpStageBytes);
-        if (!w2) {  // W1[64 c .., 64 j ..]: k-block j of hidden chunk c
-            tma_load_2d(sb, &mp.Bhi, &full_bar[st], p_j * kTcBK, c * kAsChunk);
-            tma_load_2d(sb + kAsChunk * 128, &mp.Blo, &full_bar[st], p_j * kTcBK, c * kAsChunk);
-        } else {    // W2[64 j .., 64 c ..]: output row block j, K-slice = hidden chunk c
-            tma_load_2d(sb, &mp.B2hi, &full_bar[st], c * kAsChunk, p_j * 64);
-            tma_load_2d(sb + kAsChunk * 128, &mp.B2lo, &full_bar[st], c * kAsChunk, p_j * 64);
+        if (elect_one_sync()) {  // (the elected lane alone polls the stage: 31 lanes spinning beside it cost issue slots of the MMA-heavy SM)
+            if (wait_empty) ok &= mbar_wait(&empty_bar[st], ((p_it / kMlpStages) - 1) & 1);
+            mbar_arrive_expect_tx(&full_bar[st], kMlpStageBytes);
+            if (!w2) {  // W1[64 c .., 64 j ..]: k-block j of hidden chunk c
+                tma_load_2d(sb, &mp.Bhi, &full_bar[st], p_j * kTcBK, c * kAsChunk);
+                tma_load_2d(sb + kAsChunk * 128, &mp.Blo, &full_bar[st], p_j * kTcBK, c * kAsChunk);
+            } else {    // W2[64 j .., 64 c ..]: output row block j, K-slice = hidden chunk c
+                tma_load_2d(sb, &mp.B2hi, &full_bar[st], c * kAsChunk, p_j * 64);
+                tma_load_2d(sb + kAsChunk * 128, &mp.B2lo, &full_bar[st], c * kAsChunk, p_j * 64);
+            }
         }
+        __syncwarp();
         ++p_it;
         if (++p_j == (w2 ? nb2 : num_kb)) p_j = 0, ++p_g;
     };
 
-    if (tid == 0) {
-        tma_prefetch_desc(&mp.Ahi), tma_prefetch_desc(&mp.Alo), tma_prefetch_desc(&mp.Bhi), tma_prefetch_desc(&mp.Blo);
-        tma_prefetch_desc(&mp.B2hi), tma_prefetch_desc(&mp.B2lo);
-        for (int i = 0; i < kAsMaxKb; ++i) mbar_init(&a_bar[i], 1);
-        for (int s = 0; s < kMlpStages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
-        for (int b = 0; b < 2; ++b) mbar_init(&acc_full[b], 1), mbar_init(&acc_empty[b], kTcThreads / 32);
-        mbar_init(&h_full, kTcThreads / 32), mbar_init(&h_free, 1), mbar_init(&acc2_full, 1);
-        fence_barrier_init();
-        while (p_it < n_items && p_it < kMlpStages) issue_next();  // weights never depend on the preceding kernel
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            tma_prefetch_desc(&mp.Ahi), tma_prefetch_desc(&mp.Alo), tma_prefetch_desc(&mp.Bhi), tma_prefetch_desc(&mp.Blo);
+            tma_prefetch_desc(&mp.B2hi), tma_prefetch_desc(&mp.B2lo);
+            for (int i = 0; i < kAsMaxKb; ++i) mbar_init(&a_bar[i], 1);
+            for (int s = 0; s < kMlpStages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
+            for (int b = 0; b < 2; ++b) mbar_init(&acc_full[b], 1), mbar_init(&acc_empty[b], kTcThreads / 32);
+            mbar_init(&h_full, kTcThreads / 32), mbar_init(&h_free, 1), mbar_init(&acc2_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        while (p_it < n_items && p_it < kMlpStages) issue_next(false);  // weights never depend on the preceding kernel
     }
     if (warp == 1) {
         tmem_alloc(&tmem_base_s, 512);
@@ -318,44 +325,40 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_mlp_kernel(const __grid
     pdl_launch_dependents();
 
     if (warp == 0) {
-        if (lane == 0) {  // ---- TMA producer
+        // ---- TMA producer
+        if (elect_one_sync()) {
             for (int kb = 0; kb < num_kb; ++kb) {
                 uint8_t* sa = smem + kb * 2 * kTileABytes;
                 mbar_arrive_expect_tx(&a_bar[kb], 2 * kTileABytes);
                 tma_load_2d(sa, &mp.Ahi, &a_bar[kb], kb * kTcBK, m0);
                 tma_load_2d(sa + kTileABytes, &mp.Alo, &a_bar[kb], kb * kTcBK, m0);
             }
-            while (p_it < n_items) {
-                ok &= mbar_wait(&empty_bar[p_it % kMlpStages], ((p_it / kMlpStages) - 1) & 1);
-                ev.event(2000 + p_it);  // item p_it is issued
-                issue_next();
-            }
         }
         __syncwarp();
+        while (p_it < n_items) issue_next(true);
     } else if (warp == 1) {
-        // ---- MMA issuer: the whole warp walks the loop, one elected lane issues
+        // ---- MMA issuer: one elected lane
         constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, kAsChunk), idesc2n = umma_idesc_bf16(kTcBM, 2 * kAsChunk);
         const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem)), b_lo0 = umma_desc_lo(smem_u32(ring));
-        int it = 0;
-        for (int g = 0; g < n_groups; ++g) {
-            bool w2;
-            int ch;
-            mlp_group(g, n, w2, ch);
-            if (!w2) {  // MMA1 of hidden chunk ch -> accumulator ch % 2
-                const int buf = ch & 1;
-                if (ch >= 2) {
-                    ok &= mbar_wait(&acc_empty[buf], ((ch >> 1) - 1) & 1);
-                    tcgen05_fence_after();
-                }
-                const uint32_t acc = tmem + buf * 128;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % kMlpStages;
-                    if (ch == 0) ok &= mbar_wait(&a_bar[kb], 0);
-                    ok &= mbar_wait(&full_bar[s], (it / kMlpStages) & 1);
-                    tcgen05_fence_after();
-                    if (lane == 0) ev.event(1000 + it);  // item `it` has landed (seen by the MMA warp)
-                    const uint32_t sa = a_lo0 + kb * (2 * kTileABytes >> 4), sb = b_lo0 + s * (kMlpStageBytes >> 4);
-                    if (elect_one_sync()) {
+        if (elect_one_sync()) {
+            int it = 0;
+            for (int g = 0; g < n_groups; ++g) {
+                bool w2;
+                int ch;
+                mlp_group(g, n, w2, ch);
+                if (!w2) {  // MMA1 of hidden chunk ch -> accumulator ch % 2
+                    const int buf = ch & 1;
+                    if (ch >= 2) {
+                        ok &= mbar_wait(&acc_empty[buf], ((ch >> 1) - 1) & 1);
+                        tcgen05_fence_after();
+                    }
+                    const uint32_t acc = tmem + buf * 128;
+                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                        const int s = it % kMlpStages;
+                        if (ch == 0) ok &= mbar_wait(&a_bar[kb], 0);
+                        ok &= mbar_wait(&full_bar[s], (it / kMlpStages) & 1);
+                        tcgen05_fence_after();
+                        const uint32_t sa = a_lo0 + kb * (2 * kTileABytes >> 4), sb = b_lo0 + s * (kMlpStageBytes >> 4);
 #pragma unroll
                         for (int k = 0; k < kTcBK / 16; ++k) {
                             const uint64_t dAhi = umma_desc_from_lo(sa + 2 * k), dBhi = umma_desc_from_lo(sb + 2 * k);
@@ -363,21 +366,17 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_mlp_kernel(const __grid
                             umma_bf16(acc, umma_desc_from_lo(sa + (kTileABytes >> 4) + 2 * k), dBhi, idesc, 1);
                         }
                         umma_commit(&empty_bar[s]);
-                        if (kb == num_kb - 1) umma_commit(&acc_full[buf]);
                     }
-                    __syncwarp();
-                }
-            } else {    // MMA2: acc2[:, 64 j ..] += H(ch) x W2[64 j .., chunk ch]^T, H read from tensor memory
-                ok &= mbar_wait(&h_full, ch & 1);
-                tcgen05_fence_after();
-                for (int j = 0; j < nb2; ++j, ++it) {
-                    const int s = it % kMlpStages;
-                    ok &= mbar_wait(&full_bar[s], (it / kMlpStages) & 1);
+                    umma_commit(&acc_full[buf]);
+                } else {    // MMA2: acc2[:, 64 j ..] += H(ch) x W2[64 j .., chunk ch]^T, H read from tensor memory
+                    ok &= mbar_wait(&h_full, ch & 1);
                     tcgen05_fence_after();
-                    if (lane == 0) ev.event(1000 + it);
-                    const uint32_t sb = b_lo0 + s * (kMlpStageBytes >> 4);
-                    const uint32_t acc2 = tmem + kMlpColAcc2 + 64 * j;
-                    if (elect_one_sync()) {
+                    for (int j = 0; j < nb2; ++j, ++it) {
+                        const int s = it % kMlpStages;
+                        ok &= mbar_wait(&full_bar[s], (it / kMlpStages) & 1);
+                        tcgen05_fence_after();
+                        const uint32_t sb = b_lo0 + s * (kMlpStageBytes >> 4);
+                        const uint32_t acc2 = tmem + kMlpColAcc2 + 64 * j;
 #pragma unroll
                         for (int k = 0; k < kAsChunk / 16; ++k) {
                             const uint32_t ah = tmem + kMlpColH + 16 * k;
@@ -387,16 +386,13 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_mlp_kernel(const __grid
                             umma_bf16_ta(acc2, ah + 8, dBhi, idesc, 1);
                         }
                         umma_commit(&empty_bar[s]);
-                        if (j == nb2 - 1) {
-                            umma_commit(&h_free);  // the hidden-tile columns may be rewritten once these MMAs have read them
-                            if (ch == n - 1) umma_commit(&acc2_full);
-                        }
                     }
-                    __syncwarp();
+                    umma_commit(&h_free);  // the hidden-tile columns may be rewritten once these MMAs have read them
+                    if (ch == n - 1) umma_commit(&acc2_full);
                 }
-                if (lane == 0) ev.event(140 + g);
             }
         }
+        __syncwarp();
     } else {
         // ---- epilogue warps
         const int e = tid - 64, ew = e >> 5;

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     tr.begin(&trace_slot, a.trace, a.trace_id);
 
     // ---- prologue: independent of the preceding kernel, overlaps its tail under PDL
-    if (tid == 0) {
+    if (warp == 0 && elect_one_sync()) {  // (one thread; elect.sync lets the compiler issue the TMA instructions without election loops)
         tma_prefetch_desc(&mp.Ahi), tma_prefetch_desc(&mp.Bhi);
         if (kLo) tma_prefetch_desc(&mp.Alo), tma_prefetch_desc(&mp.Blo);
         // multicast activation tiles: a stage is refilled in every CTA of the cluster at once, so it is released by all of them
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 
     uint8_t* sC = smem + SM::kOffC;
     if (warp == 0) {
-        if (lane == 0) {  // ---- TMA producer
+        if (elect_one_sync()) {  // ---- TMA producer
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kTcStages;
                 uint8_t* st = smem + s * SM::kStageBytes;
@@ -207,24 +207,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {  // ---- MMA issuer
-            // bf16x3: A_hi x [W_hi; W_lo] as ONE N = 128 UMMA (the two weight parts are adjacent 64-row tiles of the stage) into
-            // accumulator columns [0, 64) (hi*hi) and [64, 128) (hi*lo), then A_lo x W_hi (N = 64) into [0, 64); the epilogue adds the
-            // two halves.  UMMA issue is operand-fetch bound (~85 clk for 4 KB A + 2 KB B): 14 KB per K-step instead of 18 KB.
-            constexpr uint32_t idesc = umma_idesc_h<kF16>(kTcBM, BN), idesc2n = umma_idesc_h<kF16>(kTcBM, 2 * BN);
+        // ---- MMA issuer: one elected lane (elect.sync: the compiler emits tcgen05.mma without a per-thread election loop); descriptors
+        // step by one add
+        // bf16x3: A_hi x [W_hi; W_lo] as ONE N = 128 UMMA (the two weight parts are adjacent 64-row tiles of the stage) into
+        // accumulator columns [0, 64) (hi*hi) and [64, 128) (hi*lo), then A_lo x W_hi (N = 64) into [0, 64); the epilogue adds the
+        // two halves.  (tools/probes/probe_umma.cu: an MMA with both operands in shared memory costs ~43 + N / 2 clk — the 4 KB A slice
+        // is fetched before the math starts — so N = 128 + N = 64 (107 + 81 clk) beats three N = 64 MMAs (243 clk).)
+        constexpr uint32_t idesc = umma_idesc_h<kF16>(kTcBM, BN), idesc2n = umma_idesc_h<kF16>(kTcBM, 2 * BN);
+        const uint32_t lo0 = umma_desc_lo(smem_u32(smem));
+        if (elect_one_sync()) {
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kTcStages;
                 ok &= mbar_wait(&full_bar[s], (kb / kTcStages) & 1);
                 tcgen05_fence_after();
-                const uint32_t sa = smem_u32(smem + s * SM::kStageBytes);
-                const uint32_t sb = sa + SM::kParts * kTileABytes;
+                const uint32_t sa = lo0 + s * (SM::kStageBytes >> 4), sb = sa + (SM::kParts * kTileABytes >> 4);
 #pragma unroll
-                for (int k = 0; k < kTcBK / 16; ++k) {
-                    const uint32_t koff = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
-                    const uint64_t dAhi = umma_desc_sw128(sa + koff), dBhi = umma_desc_sw128(sb + koff);
+                for (int k = 0; k < kTcBK / 16; ++k) {  // 16 bf16 = 32 bytes inside the 128-byte swizzle row: descriptor + 2
+                    const uint64_t dAhi = umma_desc_from_lo(sa + 2 * k), dBhi = umma_desc_from_lo(sb + 2 * k);
                     if (kLo) {
                         umma_bf16(tmem, dAhi, dBhi, idesc2n, (kb | k) != 0);
-                        umma_bf16(tmem, umma_desc_sw128(sa + kTileABytes + koff), dBhi, idesc, 1);
+                        umma_bf16(tmem, umma_desc_from_lo(sa + (kTileABytes >> 4) + 2 * k), dBhi, idesc, 1);
                     } else {
                         umma_bf16(tmem, dAhi, dBhi, idesc, (kb | k) != 0);
                     }
@@ -396,30 +398,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         // ---- chained GEMM: P_j[128, N2] = hidden tile (just staged as a 128B-swizzled K-major A operand, bf16 hi / lo) x
         // W2[:, n0 .. n0 + 64)^T.  The hidden activations never travel to global memory; the N / 64 partial results P_j of one row
         // tile are summed in a fixed order by reduce_ln_kernel, which also applies bias, residual and the next LayerNorm.
-        if (warp == 1 && lane == 0) {
+        if (warp == 1) {
             ok &= mbar_wait(&b2_bar, 0);
             tcgen05_fence_after();
-            const uint64_t dA = umma_desc_sw128(smem_u32(smem + SM::kOffOhi)), dB = umma_desc_sw128(smem_u32(smem + SM::kOffB2));
-            constexpr uint64_t kLoA = kTileOBytes >> 4, kLoB = SM::kB2PartBytes >> 4;
-            if (sliced && kLo) {  // H_hi x [W2_hi; W2_lo] as one UMMA of 2 N2 columns + H_lo x W2_hi (the epilogue adds the halves)
-                const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2), idesc2n = umma_idesc_bf16(kTcBM, 2 * N2);
+            const uint32_t a_lo = umma_desc_lo(smem_u32(smem + SM::kOffOhi)), b_lo = umma_desc_lo(smem_u32(smem + SM::kOffB2));
+            constexpr uint32_t kLoA = kTileOBytes >> 4, kLoB = SM::kB2PartBytes >> 4;
+            if (elect_one_sync()) {
+                if (sliced && kLo) {  // H_hi x [W2_hi; W2_lo] as one UMMA of 2 N2 columns + H_lo x W2_hi (the epilogue adds the halves)
+                    const uint32_t idesc2 = umma_idesc_bf16(kTcBM, N2), idesc2n = umma_idesc_bf16(kTcBM, 2 * N2);
 #pragma unroll
-                for (int k = 0; k < kChainBN / 16; ++k) {
-                    umma_bf16_ta(tmem + kAcc1Cols, tmem + kColA2 + 16 * k, dB + 2 * k, idesc2n, k != 0);
-                    umma_bf16_ta(tmem + kAcc1Cols, tmem + kColA2 + 16 * k + 8, dB + 2 * k, idesc2, 1);
-                }
-            } else {
-                const uint32_t idesc2 = kF16 ? umma_idesc_f16(kTcBM, N2) : umma_idesc_bf16(kTcBM, N2);  // K = the 64 hidden columns of this CTA
+                    for (int k = 0; k < kChainBN / 16; ++k) {
+                        const uint64_t dB = umma_desc_from_lo(b_lo + 2 * k);
+                        umma_bf16_ta(tmem + kAcc1Cols, tmem + kColA2 + 16 * k, dB, idesc2n, k != 0);
+                        umma_bf16_ta(tmem + kAcc1Cols, tmem + kColA2 + 16 * k + 8, dB, idesc2, 1);
+                    }
+                } else {
+                    const uint32_t idesc2 = kF16 ? umma_idesc_f16(kTcBM, N2) : umma_idesc_bf16(kTcBM, N2);  // K = the 64 hidden columns of this CTA
 #pragma unroll
-                for (int k = 0; k < kChainBN / 16; ++k) {
-                    umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + 2 * k, idesc2, k != 0);
-                    if (kLo) {
-                        umma_bf16(tmem + kAcc1Cols, dA + 2 * k, dB + kLoB + 2 * k, idesc2, 1);
-                        umma_bf16(tmem + kAcc1Cols, dA + kLoA + 2 * k, dB + 2 * k, idesc2, 1);
+                    for (int k = 0; k < kChainBN / 16; ++k) {
+                        const uint64_t dA = umma_desc_from_lo(a_lo + 2 * k), dB = umma_desc_from_lo(b_lo + 2 * k);
+                        umma_bf16(tmem + kAcc1Cols, dA, dB, idesc2, k != 0);
+                        if (kLo) {
+                            umma_bf16(tmem + kAcc1Cols, dA, umma_desc_from_lo(b_lo + kLoB + 2 * k), idesc2, 1);
+                            umma_bf16(tmem + kAcc1Cols, umma_desc_from_lo(a_lo + kLoA + 2 * k), dB, idesc2, 1);
+                        }
                     }
                 }
+                umma_commit(&accum2_bar);
             }
-            umma_commit(&accum2_bar);
         }
         __syncwarp();
         ok &= mbar_wait(&accum2_bar, 0);
