@@ -554,6 +554,59 @@ def run_b200(args):
                 "achieved_tflops_per_gpu": (K5 * len(mine)) / (l5d["ms"] * 1e-3) * flops / 1e12}
             for s in st5:
                 s.trk.close()
+            # the same streams as stream GROUPS: up to 16 streams per handle stepped together through one batched forward
+            # (vt_tracker_update_streams; 320 x 16 = 5120 rows: the many-row GEMM forms), one host thread per group
+            try:
+                G = 16
+                groups = [st5[i:i + G] for i in range(0, len(st5), G)]
+                gtrk = []
+                for g in groups:
+                    t = api.VitTrack.new(wpath, g[0].spec.width, g[0].spec.height, fmt="nv12", device=local_rank, box_overlay=True,
+                                         upload_window=not args.full_upload, gemm_mode=GEMM_MODES[args.gemm], max_targets=len(g))
+                    gtrk.append(t)
+
+                def greset():
+                    for t, g in zip(gtrk, groups):
+                        for k, s in enumerate(g):
+                            s.host[:] = s.pristine
+                            t.init(s.pristine[0], api.BBox(*s.boxes[0]), target=k)
+
+                def grun(n_steps, offset, want_lat=False):
+                    lat = [None] * len(groups)
+
+                    def worker(gi):
+                        g = groups[gi]
+                        _, lat[gi] = gtrk[gi].run_streams_ring([s.host.ctypes.data for s in g], g[0].fb, g[0].fb, g[0].ring_n, offset % g[0].ring_n,
+                                                               n_steps, [s.pristine.ctypes.data for s in g], want_lat)
+                    th = [threading.Thread(target=worker, args=(i,)) for i in range(len(groups))]
+                    [x.start() for x in th]
+                    [x.join() for x in th]
+                    return lat
+                greset()
+                grun(W5, 0)
+                tm0 = [t.timing() for t in gtrk]
+                barrier()
+                w0 = time.perf_counter()
+                glat = grun(K5, W5, True)
+                for t in gtrk:
+                    t.sync()
+                barrier()
+                gms = (time.perf_counter() - w0) * 1e3
+                tm1 = [t.timing() for t in gtrk]
+                tg = sharding.combine_timings([gms], float(K5 * len(mine)), 0.0, device=f"cuda:{local_rank}")
+                gl = np.concatenate([x for x in glat if x is not None]) * 1e-3
+                h2d = sum(b.h2d_bytes - a.h2d_bytes for a, b in zip(tm0, tm1))
+                extras["cfg5"]["grouped"] = {
+                    "mode": f"stream groups of up to {G}: vt_tracker_update_streams per step (one batched forward per group, search-window uploads, "
+                            "each stream's box drawn into its own pinned frame), one host thread per group, timed on the host clock around all groups",
+                    "groups_per_gpu": len(groups), "e2e": tg.frames / (tg.ms_max[0] * 1e-3), "unit": "streams x frames/s (aggregate)",
+                    "p50_step_latency_ms": float(np.percentile(gl, 50)), "p99_step_latency_ms": float(np.percentile(gl, 99)),
+                    "vit_ms_per_step": tm1[0].avg_vit_ms, "h2d_gbs_per_gpu": h2d / (gms * 1e-3) / 1e9,
+                    "achieved_tflops_per_gpu": (K5 * len(mine)) / (gms * 1e-3) * flops / 1e12}
+                for t in gtrk:
+                    t.close()
+            except Exception as e:
+                extras["cfg5"]["grouped"] = {"error": repr(e)[:300]}
             del st5
         except Exception as e:
             extras["cfg5"] = {"error": repr(e)[:300]}

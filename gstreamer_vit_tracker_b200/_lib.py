@@ -87,6 +87,9 @@ SYMBOLS = {
     "vt_tracker_submit_device": (C.c_int32, [_vp, _vp, C.c_size_t]),
     "vt_tracker_wait": (C.c_int32, [_vp, C.POINTER(vt_result)]),
     "vt_tracker_update_device": (C.c_int32, [_vp, _vp, C.c_size_t, C.POINTER(vt_result)]),
+    "vt_tracker_run_streams_ring": (C.c_int32, [_vp, C.POINTER(C.c_void_p), C.c_int32, C.c_size_t, C.c_size_t, C.c_int32, C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_void_p), C.POINTER(vt_result), C.POINTER(C.c_double)]),
+    "vt_tracker_update_streams": (C.c_int32, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int32, C.POINTER(vt_result)]),
     "vt_tracker_run_ring": (C.c_int32, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.POINTER(vt_result),
                                         C.POINTER(C.c_double)]),
     "vt_context_run_ring": (C.c_int32, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_char_p), _vp,

@@ -208,6 +208,16 @@ class VitTrack:
         check(lib().vt_tracker_update(self._h, _ptr(frame), frame.size, self._res), "vt_tracker_update")
         return self._results()
 
+    def update_streams(self, frames: Sequence[np.ndarray]) -> List[TrackResult]:
+        """Stream group (vt_tracker_update_streams): frames[i] — a full frame in pinned host memory (PinnedBuffer) — is the current
+        frame of the i-th active target's own video stream; all targets go through one batched forward, each stream's box overlay is
+        drawn into its own frame.  ≙ n TrackerContexts (src/pipeline.rs:55) stepped together."""
+        n = len(frames)
+        ptrs = (C.c_void_p * n)(*[_ptr(f).value for f in frames])
+        lens = (C.c_size_t * n)(*[f.size for f in frames])
+        check(lib().vt_tracker_update_streams(self._h, ptrs, lens, n, self._res), "vt_tracker_update_streams")
+        return self._results()
+
     def submit_device(self, d_ptr: int, nbytes: int) -> None:
         """Frame already in device memory, tracked in place.  The caller keeps the device buffer alive until the matching wait()."""
         check(lib().vt_tracker_submit_device(self._h, C.c_void_p(d_ptr), nbytes), "vt_tracker_submit_device")
@@ -241,6 +251,17 @@ class VitTrack:
         check(lib().vt_tracker_run_ring(self._h, C.c_void_p(base_ptr), stride, frame_len, ring, first, n, mode,
                                         C.c_void_p(pristine_ptr) if pristine_ptr else None, self._res,
                                         lat.ctypes.data_as(C.POINTER(C.c_double)) if want_latency else None), "vt_tracker_run_ring")
+        return self._results(), lat
+
+    def run_streams_ring(self, ring_ptrs: Sequence[int], stride: int, frame_len: int, ring: int, first: int, n: int,
+                         pristine_ptrs: Optional[Sequence[int]] = None, want_latency: bool = False):
+        """n steps of a stream group in one native call (vt_tracker_run_streams_ring): ring_ptrs[i] = pinned host ring of stream i."""
+        k = len(ring_ptrs)
+        rings = (C.c_void_p * k)(*ring_ptrs)
+        clean = (C.c_void_p * k)(*pristine_ptrs) if pristine_ptrs is not None else None
+        lat = np.empty(n, np.float64) if want_latency else None
+        check(lib().vt_tracker_run_streams_ring(self._h, rings, k, stride, frame_len, ring, first, n, clean, self._res,
+                                                lat.ctypes.data_as(C.POINTER(C.c_double)) if want_latency else None), "vt_tracker_run_streams_ring")
         return self._results(), lat
 
     def get_rect(self, target: int = 0) -> Tuple[int, int, int, int]:

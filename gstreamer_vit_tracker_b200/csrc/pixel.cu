@@ -433,10 +433,11 @@ __global__ void __launch_bounds__(256) crop_resize_norm_kernel(FrameDesc f, Targ
     const int bi = blockIdx.y;
     PixelSrc ps{f.data, nullptr, 0, 0, f.width, f.height};
     if (f.ctl) {  // per-frame control block: frame address, and which part of the device frame holds this frame's pixels
-        ps.dev = f.ctl->frame;
+        const bool own = bi < kMaxWin && f.ctl->frames[bi] != nullptr;  // stream group: this target has its own frame
+        ps.dev = own ? f.ctl->frames[bi] : f.ctl->frame;
         const int nw = f.ctl->n_win;
         if (nw >= 0) {
-            ps.host = f.ctl->host_frame;
+            ps.host = own ? f.ctl->host_frames[bi] : f.ctl->host_frame;
             if (bi < nw) ps.x0 = f.ctl->win[bi][0], ps.y0 = f.ctl->win[bi][1], ps.x1 = f.ctl->win[bi][2], ps.y1 = f.ctl->win[bi][3];
             else ps.x1 = ps.y1 = 0;  // nothing of this target was uploaded
         }
@@ -835,8 +836,9 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
     // the control block was written at the start of the frame (complete long before the kernel ahead of this one): every thread fetches
     // what it needs in one batch, and the HUD list comes out of pinned host memory, BEFORE the dependency wait: only the decode result
     // waits for the preceding kernel
-    uint8_t* const frame = const_cast<uint8_t*>(ctl->frame);
-    uint8_t* const host = ctl->host_frame;
+    const bool own = blockIdx.x < (unsigned)kMaxWin && ctl->frames[blockIdx.x] != nullptr;  // stream group: block i draws into stream i's frame
+    uint8_t* const frame = const_cast<uint8_t*>(own ? ctl->frames[blockIdx.x] : ctl->frame);
+    uint8_t* const host = own ? ctl->host_frames[blockIdx.x] : ctl->host_frame;
     int n_hud = blockIdx.x == 0 ? ctl->n_hud : 0;
     if (n_hud > kMaxCmds) n_hud = kMaxCmds;
     if (n_hud > 0) {

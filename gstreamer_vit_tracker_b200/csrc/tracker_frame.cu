@@ -540,6 +540,79 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     return VT_OK;
 }
 
+// Stream group: the n active targets of the handle are n independent video streams (one target each, same geometry), stepped together
+// through ONE batched forward (M = 320 n rows: from 1024 rows on the GEMMs run in their throughput forms).  frames[i] is the pinned
+// host frame of the i-th active target; each target's search window is uploaded into that target's own device frame and the box overlay
+// is mirrored into that target's host frame.  Synchronous (rect_mirror is exact: the windows are the real search windows).
+static vt_status submit_streams(vt_tracker* t, uint8_t* const* frames, const size_t* lens, int n) {
+    if (t->q_count > 0 || t->hud_mode) {
+        set_error("vt_tracker_update_streams: frames are in flight on this handle, or it is a probe (HUD) handle");
+        return VT_ERR_INVALID;
+    }
+    if (n != (int)t->active.size() || n <= 0 || n > kMaxWin) {
+        set_error("vt_tracker_update_streams: %d frames for %d active targets (one frame per active target, at most %d)", n, (int)t->active.size(), kMaxWin);
+        return VT_ERR_INVALID;
+    }
+    for (int i = 0; i < n; ++i)
+        if (!frames[i] || lens[i] < t->frame_bytes || !is_pinned(frames[i])) {
+            set_error("vt_tracker_update_streams: frame %d must be a full frame in pinned host memory (vt_alloc_pinned)", i);
+            return VT_ERR_INVALID;
+        }
+    const int slot = t->q_head;
+    vt_tracker::Slot& q = t->q[slot];
+    q.t_submit = std::chrono::steady_clock::now();
+    q.frame = frames[0], q.len = lens[0], q.pageable = false, q.hud_bytes = 0, q.mirrored = true;
+    FrameCtl ctl;
+    memset(&ctl, 0, sizeof(ctl));
+    const bool windows = t->cfg.upload_window && !(t->W % 2) && !((t->H % 2) && t->fmt == VT_FMT_NV12);
+    const size_t W = (size_t)t->W;
+    for (int i = 0; i < n; ++i) {
+        if (!t->d_sframes[i]) {
+            VT_CUDA(cudaMalloc(&t->d_sframes[i], t->frame_bytes + 256));
+            VT_CUDA(cudaMemsetAsync(t->d_sframes[i], 0, t->frame_bytes + 256, t->stream));
+        }
+        uint8_t* dst = t->d_sframes[i];
+        const uint8_t* src = frames[i];
+        int* w = ctl.win[i];
+        if (!windows) {
+            VT_CUDA(cudaMemcpyAsync(dst, src, t->frame_bytes, cudaMemcpyHostToDevice, t->stream));
+            t->h2d_bytes += t->frame_bytes;
+            w[0] = w[1] = 0, w[2] = t->W, w[3] = t->H;
+        } else if (search_window(t, t->rect_mirror[t->active[i]], 0, w[0], w[1], w[2], w[3])) {
+            const size_t cols = (size_t)(w[2] - w[0]), rows = (size_t)(w[3] - w[1]);
+            if (t->fmt == VT_FMT_GRAY8) {
+                const size_t o = (size_t)w[1] * W + w[0];
+                VT_CUDA(cudaMemcpy2DAsync(dst + o, W, src + o, W, cols, rows, cudaMemcpyHostToDevice, t->stream));
+                t->h2d_bytes += cols * rows;
+            } else if (t->fmt == VT_FMT_NV12) {
+                const size_t yo = (size_t)w[1] * W + w[0], uvo = W * t->H + (size_t)(w[1] / 2) * W + w[0];
+                VT_CUDA(cudaMemcpy2DAsync(dst + yo, W, src + yo, W, cols, rows, cudaMemcpyHostToDevice, t->stream));
+                VT_CUDA(cudaMemcpy2DAsync(dst + uvo, W, src + uvo, W, cols, rows / 2, cudaMemcpyHostToDevice, t->stream));
+                t->h2d_bytes += cols * rows * 3 / 2;
+            } else {
+                const size_t pitch = W * 3, o = (size_t)w[1] * pitch + (size_t)w[0] * 3;
+                VT_CUDA(cudaMemcpy2DAsync(dst + o, pitch, src + o, pitch, cols * 3, rows, cudaMemcpyHostToDevice, t->stream));
+                t->h2d_bytes += cols * rows * 3;
+            }
+        } else {
+            w[0] = w[1] = w[2] = w[3] = 0;  // the window misses the frame: the crop kernel flags it
+        }
+        ctl.frames[i] = dst, ctl.host_frames[i] = frames[i];
+    }
+    ctl.frame = t->d_sframes[0], ctl.host_frame = frames[0], ctl.hblk = reinterpret_cast<uint32_t*>(t->h_blk[slot]);
+    ctl.n_win = n;
+    t->frame_valid = 1, t->d_frame_is_last_host_frame = false;
+    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_ctl, ctl, t->stream));
+    ++t->kernel_launches;
+    vt_status st = run_forward(t);
+    if (st != VT_OK) return st;
+    VT_CUDA(cudaEventRecord(t->q_done[slot], t->stream));
+    t->d2h_bytes += t->res_block_bytes;
+    ++t->q_count;
+    t->in_flight = true;
+    return VT_OK;
+}
+
 static vt_status wait_common(vt_tracker* t, vt_result* results) {
     if (t->q_count == 0) {
         set_error("no frame in flight");
@@ -781,6 +854,14 @@ vt_status vt_tracker_update(vt_tracker* t, uint8_t* frame, size_t len, vt_result
     return wait_common(t, results);
 }
 
+vt_status vt_tracker_update_streams(vt_tracker* t, uint8_t* const* frames, const size_t* lens, int32_t n, vt_result* results) {
+    if (!t || !frames || !lens) return VT_ERR_INVALID;
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    vt_status st = submit_streams(t, frames, lens, n);
+    if (st != VT_OK) return st;
+    return wait_common(t, results);
+}
+
 vt_status vt_tracker_update_device(vt_tracker* t, uint8_t* d_frame, size_t len, vt_result* results) {
     if (!t || !d_frame) return VT_ERR_INVALID;
     VT_CUDA(cudaSetDevice(t->cfg.device));
@@ -839,6 +920,36 @@ vt_status vt_tracker_run_ring(vt_tracker* t, uint8_t* frames, size_t stride, siz
         }
         if (st != VT_OK)  // leave no frame in flight behind an error
             while (t->q_count) wait_common(t, nullptr);
+    }
+    if (last && st == VT_OK && n > 0) memcpy(last, res.data(), sizeof(vt_result) * (size_t)t->maxT);
+    return st;
+}
+
+// vt_tracker_run_ring for a stream group: stream i's ring starts at rings[i] (pinned host memory; `ring` frames, `stride` apart)
+vt_status vt_tracker_run_streams_ring(vt_tracker* t, uint8_t* const* rings, int32_t n_streams, size_t stride, size_t frame_len, int32_t ring,
+                                      int32_t first, int32_t n, const uint8_t* const* pristine, vt_result* last, double* latency_us) {
+    if (!t || !rings || n_streams <= 0 || n_streams > kMaxWin || ring <= 0 || first < 0 || n < 0 || frame_len > stride) {
+        set_error("vt_tracker_run_streams_ring: invalid argument");
+        return VT_ERR_INVALID;
+    }
+    VT_CUDA(cudaSetDevice(t->cfg.device));
+    std::vector<vt_result> res((size_t)t->maxT);
+    uint8_t* fr[kMaxWin];
+    size_t lens[kMaxWin];
+    vt_status st = VT_OK;
+    for (int i = 0; i < n && st == VT_OK; ++i) {
+        const size_t off = (size_t)((first + i) % ring) * stride;
+        for (int k = 0; k < n_streams; ++k) fr[k] = rings[k] + off, lens[k] = frame_len;
+        const auto t0 = std::chrono::steady_clock::now();
+        st = submit_streams(t, fr, lens, n_streams);
+        if (st == VT_OK) st = wait_common(t, res.data());
+        if (latency_us) latency_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        if (st == VT_OK && pristine && t->cfg.box_overlay)  // undo what the box overlays drew: the rings are replayed on clean frames
+            for (int k = 0; k < n_streams && k < (int)t->active.size(); ++k) {
+                const vt_result& r = res[t->active[k]];
+                if (pristine[k] && r.status == VT_OK && r.success && r.score > t->cfg.overlay_gate)
+                    restore_box_region(fr[k], pristine[k] + off, t->fmt, t->W, t->H, r.bbox);
+            }
     }
     if (last && st == VT_OK && n > 0) memcpy(last, res.data(), sizeof(vt_result) * (size_t)t->maxT);
     return st;

@@ -80,6 +80,7 @@ struct vt_tracker {
 
     // frame + state
     uint8_t* d_frame = nullptr;
+    uint8_t* d_sframes[kMaxWin] = {};  // stream groups: one device frame per target slot (allocated on first use)
     uint8_t* d_frames[2] = {nullptr, nullptr};  // double buffer: d_frame points at the one most recently filled (queue slot s uses [s])
     cudaStream_t copy_stream = nullptr;          // uploads of pipelined host frames overlap the in-flight frame's kernels
     cudaEvent_t ev_up[2] = {nullptr, nullptr};

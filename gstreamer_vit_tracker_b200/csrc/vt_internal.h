@@ -131,6 +131,9 @@ struct FrameCtl {
     int32_t n_hud;
     int32_t n_win;             // -1: the whole device frame holds this frame; else win[i] = the region that does, for active target i
     int32_t win[kMaxWin][4];   // x0, y0, x1, y1 (exclusive), even-aligned
+    // stream groups (vt_tracker_update_streams): active target i reads — and is drawn into — its OWN frame; null = `frame` / `host_frame`
+    const uint8_t* frames[kMaxWin];
+    uint8_t* host_frames[kMaxWin];
 };
 cudaError_t launch_stamp(unsigned long long* stamp, FrameCtl* d_ctl, const FrameCtl& ctl, cudaStream_t s);
 // last kernel of a frame: result block -> the pinned host block ctl->hblk (zero-copy stores)

@@ -143,6 +143,15 @@ vt_status vt_tracker_submit(vt_tracker* t, uint8_t* frame, size_t len);
 vt_status vt_tracker_submit_device(vt_tracker* t, uint8_t* d_frame, size_t len);  /* frame already in device memory, tracked in place */
 vt_status vt_tracker_wait(vt_tracker* t, vt_result* results);
 
+/* Stream group: the handle's n active targets are n independent video streams of the same geometry — ≙ n TrackerContexts
+ * (src/pipeline.rs:55: one per pipeline) stepped together.  frames[i] (pinned host memory, a full frame) belongs to the i-th active
+ * target (ascending slot order); every stream's search window is uploaded into its own device frame, all n targets go through ONE
+ * batched ViT forward (from 4 streams on the GEMMs run in their many-row throughput forms), and with cfg.box_overlay each stream's
+ * box is drawn into ITS frame.  results[slot] as in update().  Each target is initialised on a frame of its own stream with
+ * vt_tracker_init(t, slot, frame_of_that_stream, len, box).  Results equal those of n single-target handles (boxes equal, scores
+ * within the re-association noise of the kernel forms, <= 1e-5). */
+vt_status vt_tracker_update_streams(vt_tracker* t, uint8_t* const* frames, const size_t* lens, int32_t n, vt_result* results);
+
 /* Same as update() but the frame is already in device memory (bench `value` leg, NVDEC/NVMM producers): the tracker reads the
  * caller's frame in place (no copy) and, with cfg.box_overlay, draws the box INTO it — the in-place semantics of the reference's
  * probe (src/pipeline.rs:90-100,165-168) on a device surface. */
@@ -159,6 +168,10 @@ vt_status vt_tracker_update_device(vt_tracker* t, uint8_t* d_frame, size_t len, 
 typedef enum { VT_RUN_HOST_SYNC = 0, VT_RUN_HOST_PIPELINED = 1, VT_RUN_DEVICE_SYNC = 2, VT_RUN_DEVICE_PIPELINED = 3 } vt_run_mode;
 vt_status vt_tracker_run_ring(vt_tracker* t, uint8_t* frames, size_t stride, size_t frame_len, int32_t ring, int32_t first, int32_t n,
                               int32_t mode, const uint8_t* pristine, vt_result* last, double* latency_us);
+/* The same loop for a stream group (vt_tracker_update_streams per step): rings[i] = ring of stream i (pinned host memory), pristine[i]
+ * (nullable array / entries) = its clean copy. */
+vt_status vt_tracker_run_streams_ring(vt_tracker* t, uint8_t* const* rings, int32_t n_streams, size_t stride, size_t frame_len, int32_t ring,
+                                      int32_t first, int32_t n, const uint8_t* const* pristine, vt_result* last, double* latency_us);
 
 /* tracker state access (≙ rect_last inside VitTrack; used by tests for teacher forcing) */
 vt_status vt_tracker_get_rect(vt_tracker* t, int32_t target, vt_bbox* out);

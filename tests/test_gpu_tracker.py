@@ -940,6 +940,52 @@ def test_throughput_gemm_forms_bit_identical(api, weight_dir, monkeypatch, gemm_
             assert abs(a.score - b.score) < 1e-5, (a, b)
 
 
+@pytest.mark.parametrize("upload_window", [True, False], ids=["windows", "whole"])
+def test_stream_group_equals_independent_handles(api, weight_dir, upload_window):
+    """vt_tracker_update_streams: 5 independent 1080p streams (cfg5 seeds) stepped together through one batched forward (1600 rows: the
+    many-row GEMM forms) against 5 single-stream handles on the same frames: boxes equal, scores within 1e-5 (re-association of the FC2
+    sum in the chained A-stationary MLP), and every stream's pinned frame carries exactly the overlay pixels its own handle draws."""
+    import gc
+    gc.collect()
+    w = weights.ensure_weight_file("tiny", weight_dir, variant="wild")
+    G, steps = 5, 6
+    streams = [synth.SyntheticStream(synth.cfg5_stream(i)) for i in range(G)]
+    spec = streams[0].spec
+    fb = streams[0].frame_bytes()
+    grp = api.VitTrack.new(w, spec.width, spec.height, gemm_mode=1, max_targets=G, box_overlay=True, upload_window=upload_window)
+    singles = [api.VitTrack.new(w, spec.width, spec.height, gemm_mode=1, box_overlay=True, upload_window=upload_window) for _ in range(G)]
+    pin_g = [api.PinnedBuffer(fb) for _ in range(G)]
+    pin_s = [api.PinnedBuffer(fb) for _ in range(G)]
+    for i, st in enumerate(streams):
+        f0 = np.ascontiguousarray(st.frame(0)).reshape(-1)
+        box = api.BBox(*st.target_boxes(0)[0])
+        grp.init(f0, box, target=i)
+        singles[i].init(f0, box)
+    for k in range(1, steps + 1):
+        for i, st in enumerate(streams):
+            f = np.ascontiguousarray(st.frame(k)).reshape(-1)
+            pin_g[i].array[:] = f
+            pin_s[i].array[:] = f
+        got = grp.update_streams([p.array for p in pin_g])
+        for i in range(G):
+            ref = singles[i].update(pin_s[i].array)
+            a = got[i]
+            assert a.status == 0 and a.success == ref.success and a.bbox == ref.bbox, (k, i, a, ref)
+            assert abs(a.score - ref.score) < 1e-5, (k, i, a, ref)
+            assert np.array_equal(pin_g[i].array, pin_s[i].array), (k, i, "overlay pixels differ")
+            assert not np.array_equal(pin_g[i].array, np.ascontiguousarray(streams[i].frame(k)).reshape(-1)), "no overlay was drawn"
+    # argument checks: frame count, pageable frames
+    with pytest.raises(Exception):
+        grp.update_streams([p.array for p in pin_g[:3]])
+    with pytest.raises(Exception):
+        grp.update_streams([np.zeros(fb, np.uint8) for _ in range(G)])
+    grp.close()
+    for t in singles:
+        t.close()
+    for p in pin_g + pin_s:
+        p.close()
+
+
 # ---- SURVEY.md App. A.7 variant switches ----------------------------------------------------------------------------------------
 def _quirk_norm():
     g = golden("trackervit_variants.json")
