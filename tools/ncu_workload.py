@@ -4,7 +4,7 @@
   python tools/ncu_workload.py cfg2     1080p NV12, one target, tiny: 4 warm-up frames + 2 frames (device-resident, synchronous)
   python tools/ncu_workload.py cfg4     2160p NV12, 16 targets in one batched forward: 3 + 2 frames
   python tools/ncu_workload.py probe    vt_probe_frame on a pinned 1080p frame: 4 + 2 frames (HUD list, one synchronisation per frame)
-  python tools/ncu_workload.py pixels   NV12->RGB (8 x 1080p), YUY2->RGB (32 x 640x512), RGB up-scale (16 x 640x512 -> 1280x1024): 2 launches each
+  python tools/ncu_workload.py pixels   NV12->RGB (32 x 1080p), YUY2->RGB (256 x 640x512), RGB up-scale (64 x 640x512 -> 1280x1024): 2 launches each
   python tools/ncu_workload.py streams  8 concurrent 1080p streams (plain kernel forms), 3 + 2 frames each, driven round-robin from one thread
 
 Typical use on the GPU box (B200_PROFILING.md):
@@ -67,13 +67,13 @@ def probe_frames(warm, frames):
 
 def pixel_launches():
     trk = api.VitTrack.new(weights.ensure_weight_file("nano", WDIR), 1920, 1080, fmt="nv12")
-    W, H, n = 1920, 1080, 8
+    W, H, n = 1920, 1080, 32   # 100 MB in + 199 MB out per launch: more than the 126 MB L2, so the writes reach DRAM inside the launch
     src = torch.randint(0, 256, (n, W * H * 3 // 2), dtype=torch.uint8, device="cuda")
     dst = torch.empty((n, W * H * 3), dtype=torch.uint8, device="cuda")
-    w, h, n2 = 640, 512, 32
+    w, h, n2 = 640, 512, 256
     src2 = torch.randint(0, 256, (n2, w * h * 2), dtype=torch.uint8, device="cuda")
     dst2 = torch.empty((n2, w * h * 3), dtype=torch.uint8, device="cuda")
-    n3 = 16
+    n3 = 64
     up = torch.empty(n3 * 1280 * 1024 * 3, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     for _ in range(2):
