@@ -837,8 +837,15 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
     // what it needs in one batch, and the HUD list comes out of pinned host memory, BEFORE the dependency wait: only the decode result
     // waits for the preceding kernel
     const bool own = blockIdx.x < (unsigned)kMaxWin && ctl->frames[blockIdx.x] != nullptr;  // stream group: block i draws into stream i's frame
-    uint8_t* const frame = const_cast<uint8_t*>(own ? ctl->frames[blockIdx.x] : ctl->frame);
-    uint8_t* const host = own ? ctl->host_frames[blockIdx.x] : ctl->host_frame;
+    // HUD mode runs two CTAs per target (gridDim.y = 2): y = 0 draws on the device frame (and publishes), y = 1 on the pinned host frame —
+    // the two passes over the command list (~8 us each on one CTA) run side by side
+    const bool split = gridDim.y > 1;
+    uint8_t* const frame0 = const_cast<uint8_t*>(own ? ctl->frames[blockIdx.x] : ctl->frame);
+    uint8_t* const host0 = own ? ctl->host_frames[blockIdx.x] : ctl->host_frame;
+    if (split && blockIdx.y == 1 && !host0) return;       // nothing to mirror into
+    uint8_t* const frame = frame0;
+    uint8_t* const host = host0;
+    const bool do_dev = !split || blockIdx.y == 0, do_host = host != nullptr && (!split || blockIdx.y == 1);
     int n_hud = blockIdx.x == 0 ? ctl->n_hud : 0;
     if (n_hud > kMaxCmds) n_hud = kMaxCmds;
     if (n_hud > 0) {
@@ -856,27 +863,35 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
         bg = bg_region(s_cmd[0], W, H);
         const long long rows = bg.y1 - bg.y0;
         if (((reinterpret_cast<uintptr_t>(host) | reinterpret_cast<uintptr_t>(frame)) & 3) != 0) bg.wpr = 0;  // bytewise
-        bg_pre = host && bg.wpr > 0 && rows * bg.wpr <= (long long)kBgWords * kOvThreads && (size_t)bg.y1 * (size_t)W <= len;
+        // source of the region: the device frame when it was uploaded with the windows (a copy-engine transfer ahead of the graph; an L2 hit
+        // here), else the pinned host frame (PCIe reads: ~12 us for the 260 x 90 block, on the critical path of a short frame)
+        const uint8_t* bsrc = (host && !ctl->bg_on_device) ? host : frame;
+        bg_pre = (host || ctl->bg_on_device) && bg.wpr > 0 && rows * bg.wpr <= (long long)kBgWords * kOvThreads && (size_t)bg.y1 * (size_t)W <= len;
         if (bg_pre) {
             const int total = (int)rows * bg.wpr;
 #pragma unroll
             for (int k = 0; k < kBgWords; ++k) {
                 const int i = threadIdx.x + k * kOvThreads;
-                if (i < total) bgw[k] = *reinterpret_cast<const volatile uint32_t*>(host + (size_t)(bg.y0 + i / bg.wpr) * W + bg.ax0 + 4 * (i % bg.wpr));
+                if (i < total) bgw[k] = *reinterpret_cast<const volatile uint32_t*>(bsrc + (size_t)(bg.y0 + i / bg.wpr) * W + bg.ax0 + 4 * (i % bg.wpr));
             }
         }
     }
     const int slot = (int)blockIdx.x < n ? slots[blockIdx.x] : -1;
+    if (stamp_end && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) stamp_end[1] = device_time_ns();  // diagnostics: prologue done
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (stamp_end && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) stamp_end[2] = device_time_ns();  // diagnostics: dependency satisfied
     DeviceResult r;
     r.status = VT_ERR_NOT_INIT, r.success = 0, r.score = 0.f, r.bbox[0] = r.bbox[1] = r.bbox[2] = r.bbox[3] = 0, r.best = 0;
     if (slot >= 0) r = res[slot];
     const bool pass = r.status == VT_OK && r.success && r.score > gate;
+    const int dbg_skip = draw_box >> 8;  // diagnostics (VT_B200_HUD_SKIP): 1 = no host pass, 2 = no device pass, 4 = no background dim
+    draw_box &= 0xff;
     if (draw_box && pass) {
         const int x = r.bbox[0], y = r.bbox[1], w = r.bbox[2], h = r.bbox[3];
         for (int p = 0; p < 2; ++p) {
             uint8_t* dst = p == 0 ? frame : host;
             if (!dst) break;
+            if ((p == 0 && !do_dev) || (p == 1 && !do_host)) continue;
             Surface s{dst, len, W, H, fmt};
             if (fmt == VT_FMT_NV12) {
                 ov_rect_nv12(s, x, y, w, h, 3, 255);
@@ -902,7 +917,8 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
         }
         __syncthreads();
         int first = 0;
-        if (bg_first) {  // ---- the background dim: word interior from registers (or the device frame), ragged edges bytewise
+        if (bg_first && (dbg_skip & 4)) first = 1;
+        else if (bg_first) {  // ---- the background dim: word interior from registers (or the device frame), ragged edges bytewise
             const unsigned factor = 255u - (unsigned)(uint8_t)s_cmd[0].a;
             const long long rows = bg.y1 - bg.y0;
             if (bg.x1 > bg.x0 && (size_t)bg.y1 * (size_t)W <= len) {
@@ -910,7 +926,7 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
                     const long long total = rows * bg.wpr;
                     for (long long base = 0; base < total; base += (long long)kBgWords * kOvThreads) {
                         if (!bg_pre || base > 0) {  // not prefetched (no pinned frame, or a region larger than the register budget)
-                            const uint8_t* src = host ? host : frame;  // with a pinned frame the region was not uploaded
+                            const uint8_t* src = (host && !ctl->bg_on_device) ? host : frame;  // (pinned frame: the region may not have been uploaded)
 #pragma unroll
                             for (int k = 0; k < kBgWords; ++k) {
                                 const long long i = base + threadIdx.x + (long long)k * kOvThreads;
@@ -923,8 +939,8 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
                             if (i < total) {
                                 const size_t o = (size_t)(bg.y0 + i / bg.wpr) * W + bg.ax0 + 4 * (i % bg.wpr);
                                 const uint32_t d = dim4(bgw[k], factor);
-                                *reinterpret_cast<uint32_t*>(frame + o) = d;
-                                if (host) *reinterpret_cast<uint32_t*>(host + o) = d;
+                                if (do_dev) *reinterpret_cast<uint32_t*>(frame + o) = d;
+                                if (do_host) *reinterpret_cast<uint32_t*>(host + o) = d;
                             }
                         }
                     }
@@ -934,9 +950,9 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
                 for (long long i = threadIdx.x; i < rows * ec; i += blockDim.x) {
                     const long long yy = bg.y0 + i / ec, k = i % ec, xx = k < eh ? bg.x0 + k : bg.ax1 + (k - eh);
                     const size_t o = (size_t)yy * W + (size_t)xx;
-                    const uint8_t d = (uint8_t)(((unsigned)(host ? host[o] : frame[o]) * factor) / 255u);
-                    frame[o] = d;
-                    if (host) host[o] = d;
+                    const uint8_t d = (uint8_t)(((unsigned)((host && !ctl->bg_on_device) ? host[o] : frame[o]) * factor) / 255u);
+                    if (do_dev) frame[o] = d;
+                    if (do_host) host[o] = d;
                 }
             }
             __syncthreads();
@@ -945,11 +961,12 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
         for (int p = 0; p < 2; ++p) {
             uint8_t* dst = p == 0 ? frame : host;
             if (!dst) break;
+            if ((p == 0 && ((dbg_skip & 2) || !do_dev)) || (p == 1 && ((dbg_skip & 1) || !do_host))) continue;
             Surface s{dst, len, W, H, fmt};
             for (int i = first; i < n_hud; ++i) {
                 const OverlayCmdDev& c = s_cmd[i];
                 if (c.kind < 0) continue;
-                if (p == 1 && c.kind == VT_OV_BACKGROUND && fmt == VT_FMT_NV12) {
+                if (p == 1 && c.kind == VT_OV_BACKGROUND && fmt == VT_FMT_NV12 && !split) {  // (split: this CTA dims the host pixels itself)
                     // a dim that does not lead the list: the host copy takes the final pixels of the region from the device frame (the
                     // later commands of this pass re-draw what lies on top of it)
                     const BgRegion g = bg_region(c, W, H);
@@ -964,6 +981,7 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
             }
         }
     }
+    if (split && blockIdx.y == 1) return;  // (the host waits for the whole grid: the mirrored pixels are complete when it reads the result)
     if (stamp_end && threadIdx.x == 0) *stamp_end = device_time_ns();
     if (blk) {  // last kernel of the frame: publish the result block (see publish_kernel) — one kernel boundary less
         uint32_t* dst = ctl->hblk;
@@ -977,8 +995,9 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
 cudaError_t launch_box_overlay(size_t len, int width, int height, int format, const DeviceResult* d_res, const int32_t* d_slots, int n,
                                float gate, const FrameCtl* d_ctl, unsigned long long* stamp_end, cudaStream_t s, bool pdl, const void* d_blk,
                                size_t blk_bytes, int draw_box) {
-    return launch_ex(box_overlay_kernel, dim3(n > 0 ? n : 1), dim3(kOvThreads), 0, s, pdl, 1, len, width, height, format, d_res, d_slots, n, gate, d_ctl,
-                     stamp_end, (const uint32_t*)d_blk, (int)(blk_bytes / 4), draw_box);
+    const bool split = (draw_box >> 16) != 0;  // HUD mode: device pass and host pass in two CTAs
+    return launch_ex(box_overlay_kernel, dim3(n > 0 ? n : 1, split ? 2 : 1), dim3(kOvThreads), 0, s, pdl, 1, len, width, height, format, d_res, d_slots, n,
+                     gate, d_ctl, stamp_end, (const uint32_t*)d_blk, (int)(blk_bytes / 4), draw_box & 0xffff);
 }
 
 // per-frame, outside the graph: submit stamp + the control block (addresses and parameters that change from frame to frame)
@@ -987,9 +1006,27 @@ __global__ void stamp_kernel(unsigned long long* stamp, FrameCtl* dst, const Fra
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&val);
     for (int i = threadIdx.x; i < (int)(sizeof(FrameCtl) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(dst)[i] = src[i];
 }
-cudaError_t launch_stamp(unsigned long long* stamp, FrameCtl* d_ctl, const FrameCtl& ctl, cudaStream_t s) {
-    static_assert(sizeof(FrameCtl) % 4 == 0, "word copy");
-    stamp_kernel<<<1, 96, 0, s>>>(stamp, d_ctl, ctl);
+struct HudInline {
+    OverlayCmdDev c[kHudInline];
+};
+__global__ void stamp_hud_kernel(unsigned long long* stamp, FrameCtl* dst, const FrameCtl val, const __grid_constant__ HudInline list, int n,
+                                 OverlayCmdDev* d_list) {
+    if (threadIdx.x == 0) *stamp = device_time_ns();
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&val);
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameCtl) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(dst)[i] = src[i];
+    const uint32_t* ls = reinterpret_cast<const uint32_t*>(&list);
+    for (int i = threadIdx.x; i < n * (int)(sizeof(OverlayCmdDev) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(d_list)[i] = ls[i];
+}
+cudaError_t launch_stamp(unsigned long long* stamp, FrameCtl* d_ctl, const FrameCtl& ctl, cudaStream_t s, const OverlayCmdDev* h_list, int n,
+                         OverlayCmdDev* d_list) {
+    static_assert(sizeof(FrameCtl) % 4 == 0 && sizeof(OverlayCmdDev) % 4 == 0, "word copy");
+    if (h_list && d_list && n > 0 && n <= kHudInline) {
+        HudInline blk;
+        memcpy(blk.c, h_list, sizeof(OverlayCmdDev) * (size_t)n);
+        stamp_hud_kernel<<<1, 256, 0, s>>>(stamp, d_ctl, ctl, blk, n, d_list);
+    } else {
+        stamp_kernel<<<1, 96, 0, s>>>(stamp, d_ctl, ctl);
+    }
     return cudaGetLastError();
 }
 

@@ -210,6 +210,8 @@ void vt_tracker_destroy(vt_tracker* t) {
         if (t->q_done[i]) cudaEventDestroy(t->q_done[i]);
     }
     if (t->d_ctl) cudaFree(t->d_ctl);
+    for (auto& h : t->d_hud)
+        if (h) cudaFree(h);
     for (auto& h : t->h_hud)
         if (h) cudaFreeHost(h);
     if (t->h_cmds) cudaFreeHost(t->h_cmds);

@@ -192,7 +192,9 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                                 t->cfg.decode_window));
     if (t->cfg.box_overlay || t->hud_mode)  // box overlay and / or the frame's HUD list, pinned-frame mirror, ... and publishes the result block
         VT_LAUNCH(launch_box_overlay(t->frame_bytes, t->W, t->H, overlay_format(t->fmt), t->d_res, t->d_slots, n, t->cfg.overlay_gate, t->d_ctl,
-                                     t->d_stamps + ST_OVL_END, s, t->pdl && !t->debug_capture, t->d_res, t->res_block_bytes, t->cfg.box_overlay));
+                                     t->d_stamps + ST_OVL_END, s, t->pdl && !t->debug_capture, t->d_res, t->res_block_bytes,
+                                     t->cfg.box_overlay | (getenv("VT_B200_HUD_SKIP") ? atoi(getenv("VT_B200_HUD_SKIP")) << 8 : 0) |
+                                         ((t->hud_mode && !getenv("VT_B200_HUD_ONE_CTA")) ? 1 << 16 : 0)));
     else  // results, stage stamps and the error flag -> the pinned host block of this frame's queue slot
         VT_LAUNCH(launch_publish(t->d_res, t->d_ctl, t->res_block_bytes, s, t->pdl && !t->debug_capture));
     return VT_OK;
@@ -451,6 +453,14 @@ static void collect_timing(vt_tracker* t) {
     ms[5] = wall > dev ? wall - dev : 0.f;  // results (and overlay rows) back in host memory + completion latency, host clock
     ms[6] = wall;
     if (t->active.empty()) ms[1] = ms[2] = ms[3] = ms[4] = 0.f;
+    if (getenv("VT_B200_STAMPDBG") && ovl) {  // diagnostics: overlay kernel prologue end / dependency satisfied / end, relative to the decode end
+        static double acc[3] = {0, 0, 0};
+        static int cnt = 0;
+        acc[0] += (double)((long long)st[6] - (long long)st[ST_DEC_END]), acc[1] += (double)((long long)st[7] - (long long)st[ST_DEC_END]);
+        acc[2] += (double)((long long)st[ST_OVL_END] - (long long)st[ST_DEC_END]);
+        if (++cnt % 50 == 0) fprintf(stderr, "[vt stampdbg] overlay vs decode end: prologue done %+.2f us, dependency satisfied %+.2f us, end %+.2f us\n",
+                                     acc[0] / cnt * 1e-3, acc[1] / cnt * 1e-3, acc[2] / cnt * 1e-3);
+    }
     memcpy(t->last, ms, sizeof(ms));
     t->r_h2d.push(ms[0]), t->r_pre.push(ms[1]), t->r_vit.push(ms[2]), t->r_dec.push(ms[3]), t->r_ovl.push(ms[4]), t->r_d2h.push(ms[5]),
         t->r_tot.push(ms[6]);
@@ -487,8 +497,9 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     const bool lagging = t->q_count > 0;  // a frame is in flight: rect_mirror is one frame old, the windows are predictions
     UploadPlan plan;
     // (the region a HUD list dims is read by the overlay kernel straight from the pinned host frame: it needs no upload of its own)
+    static const bool bg_from_host = getenv("VT_B200_HUD_BG_FROM_HOST") != nullptr;  // (measured slower: profiles/r2_final.md)
     if (!in_place && !d_src)
-        plan_upload(t, len, host_frame != nullptr, lagging, (n_hud && !(host_frame && t->hud_next_bg_leads)) ? t->hud_next_rmw : nullptr, plan);
+        plan_upload(t, len, host_frame != nullptr, lagging, (n_hud && !(bg_from_host && host_frame && t->hud_next_bg_leads)) ? t->hud_next_rmw : nullptr, plan);
     if (!in_place && !d_src && lagging) {
         // pipelined host frame: upload on the copy stream while the frame in flight computes; the main stream picks it up through an event
         vt_status st = do_upload(t, frame, len, plan, false, t->copy_stream);
@@ -500,10 +511,13 @@ static vt_status submit_common(vt_tracker* t, uint8_t* frame, const uint8_t* d_s
     memset(&ctl, 0, sizeof(ctl));
     ctl.frame = in_place ? d_src : t->d_frame, ctl.host_frame = host_frame, ctl.hblk = reinterpret_cast<uint32_t*>(t->h_blk[slot]);
     ctl.hud = n_hud ? t->h_hud[slot] : nullptr, ctl.n_hud = n_hud;
+    const bool hud_inline = n_hud > 0 && n_hud <= kHudInline && t->d_hud[slot] != nullptr;
+    if (hud_inline) ctl.hud = t->d_hud[slot];
     ctl.n_win = plan.whole ? -1 : plan.n_win;
     if (!plan.whole) memcpy(ctl.win, plan.win, sizeof(ctl.win));
+    ctl.bg_on_device = (n_hud && (in_place || d_src || plan.whole || plan.has_rmw)) ? 1 : 0;  // the dimmed region is in the device frame
     t->hud_next_n = 0;
-    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_ctl, ctl, t->stream));
+    VT_CUDA(launch_stamp(t->d_stamps + ST_SUBMIT, t->d_ctl, ctl, t->stream, hud_inline ? t->h_hud[slot] : nullptr, n_hud, t->d_hud[slot]));
     ++t->kernel_launches;
     if (in_place) {
         t->frame_valid = 1;
@@ -697,6 +711,7 @@ vt_status tracker_set_hud(vt_tracker* t, const HudCmd* cmds, int n) {
     VT_CUDA(cudaSetDevice(t->cfg.device));
     const int slot = (t->q_head + t->q_count) % vt_tracker::kQueue;
     if (!t->h_hud[slot]) VT_CUDA(cudaHostAlloc(&t->h_hud[slot], sizeof(OverlayCmdDev) * kMaxCmds, cudaHostAllocDefault));
+    if (!t->d_hud[slot]) VT_CUDA(cudaMalloc(&t->d_hud[slot], sizeof(OverlayCmdDev) * kHudInline));
     int rmw[4] = {0, 0, 0, 0};
     size_t bytes = 0;
     for (int i = 0; i < n; ++i) {

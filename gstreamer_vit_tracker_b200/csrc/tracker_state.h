@@ -110,6 +110,7 @@ struct vt_tracker {
                                        // so that the crop kernel's fall-back reads from the pinned host frame are exercised
     bool hud_mode = false;
     OverlayCmdDev* h_hud[2] = {nullptr, nullptr};
+    OverlayCmdDev* d_hud[2] = {nullptr, nullptr};  // device copies of the lists (written by the stamp kernel from its parameter block)
     int hud_next_n = 0;
     int hud_next_rmw[4] = {0, 0, 0, 0};  // region the list reads before it writes (NV12 background dim): x0, y0, x1, y1; empty = none
     size_t hud_next_bytes = 0;            // pixels the list touches (device -> host accounting)

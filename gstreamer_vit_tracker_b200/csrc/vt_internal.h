@@ -134,8 +134,14 @@ struct FrameCtl {
     // stream groups (vt_tracker_update_streams): active target i reads — and is drawn into — its OWN frame; null = `frame` / `host_frame`
     const uint8_t* frames[kMaxWin];
     uint8_t* host_frames[kMaxWin];
+    int32_t bg_on_device;      // the region a leading HUD background dim reads was uploaded with the windows: read it from the device frame
+    int32_t pad_;
 };
-cudaError_t launch_stamp(unsigned long long* stamp, FrameCtl* d_ctl, const FrameCtl& ctl, cudaStream_t s);
+// h_list / n / d_list (optional): the frame's HUD list travels in the kernel's parameter block and is written to d_list, so the overlay
+// kernel reads it from device memory (from the pinned block it was a PCIe round trip at the head of the frame's last kernel)
+constexpr int kHudInline = 12;
+cudaError_t launch_stamp(unsigned long long* stamp, FrameCtl* d_ctl, const FrameCtl& ctl, cudaStream_t s, const OverlayCmdDev* h_list = nullptr,
+                         int n = 0, OverlayCmdDev* d_list = nullptr);
 // last kernel of a frame: result block -> the pinned host block ctl->hblk (zero-copy stores)
 cudaError_t launch_publish(const void* d_blk, const FrameCtl* d_ctl, size_t bytes, cudaStream_t s, bool pdl);
 
