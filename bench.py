@@ -83,8 +83,10 @@ def config_dict(args):
     return {"workload": workload_name(args), "resolution": "1920x1080", "format": "NV12", "targets": 1, "model": args.model,
             "streams_per_gpu": args.streams_per_gpu, "weights": "constructed random-init (SURVEY.md §8c)",
             "call": "probe body per frame: convert + VitTrack::update + HUD overlay (src/pipeline.rs:104-174)",
-            "l2": f"inputs larger than L2: every timed leg walks {args.steps + args.warmup} frames per stream out of a ring of {ring_n} distinct "
-                  f"1080p frames ({ring_n * 3110400 / 1e6:.0f} MB; 126 MB L2), every frame on clean pixels (overlays are undone / never reused)"}
+            "l2": f"L2 flushed (256 MB device write) before every timed leg; within a leg every step reads a frame no earlier step of the leg "
+                  f"touched ({args.steps + args.warmup} frames per stream out of a ring of {ring_n} distinct 1080p frames = "
+                  f"{ring_n * 3110400 / 1e6:.0f} MB; 126 MB L2; a step reads only the ~0.4 MB search window of its frame), every frame on clean "
+                  "pixels (overlays are undone / never reused)"}
 
 
 def ring_size(args):
@@ -384,6 +386,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    l2_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+
+    def flush_l2():
+        """Write a buffer twice the size of L2: nothing an earlier leg touched (device rings, weights, activations) stays resident."""
+        l2_buf.fill_(1)
+        torch.cuda.synchronize()
+
     def run_leg(streams, kind, n_steps, offset, want_lat=False):
         """n_steps frames on every stream of this rank, one host thread per stream, each ONE native call (the GIL is released inside);
         returns per-stream latency arrays (us) for the synchronous kinds."""
@@ -417,6 +426,7 @@ def run_b200(args):
         handles = [(s.ctx.tracker if kind == "probe" else s.trk) for s in streams]
         run_leg(streams, kind, n_warm, 0)
         tm0 = [h.timing() for h in handles]
+        flush_l2()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ext = torch.cuda.ExternalStream(handles[0].stream, device=local_rank)  # events on the stream the kernels are launched on

@@ -806,6 +806,7 @@ __device__ void hud_score_glyphs(OverlayCmdDev& c, float score) {  // "score: " 
 // ~90 us for the 400x80 HUD block on one CTA), from the caller's pinned host frame when there is one: that needs no upload of the region
 // and, issued before the dependency wait, overlaps the kernels ahead.  The dimmed words go to the device frame and the host frame.
 constexpr int kOvThreads = 512;
+constexpr int kBgEdge = 2;    // ragged-edge bytes per thread held in registers (rows x <= 6 columns)
 constexpr int kBgWords = 20;  // words per thread held in registers: 512 x 20 x 4 = 40 KB >= the 400 x 80 HUD block
 struct BgRegion {
     long long x0, y0, x1, y1;  // clipped pixel rectangle (usize arithmetic of the reference), empty when x1 <= x0
@@ -858,7 +859,8 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
     const bool bg_first = n_hud > 0 && fmt == VT_FMT_NV12 && s_cmd[0].kind == VT_OV_BACKGROUND && s_cmd[0].cond == VT_HUD_ALWAYS;
     BgRegion bg{0, 0, 0, 0, 0, 0, 0, false};
     uint32_t bgw[kBgWords];
-    bool bg_pre = false;
+    uint8_t bge[kBgEdge];
+    bool bg_pre = false, bg_edge_pre = false;
     if (bg_first) {
         bg = bg_region(s_cmd[0], W, H);
         const long long rows = bg.y1 - bg.y0;
@@ -874,6 +876,36 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
                 const int i = threadIdx.x + k * kOvThreads;
                 if (i < total) bgw[k] = *reinterpret_cast<const volatile uint32_t*>(bsrc + (size_t)(bg.y0 + i / bg.wpr) * W + bg.ax0 + 4 * (i % bg.wpr));
             }
+            // ... and the columns outside the word interior (<= 3 + 3 per row), so that nothing of the region is read after the dependency
+            // wait: with two CTAs per target the other CTA dims the device frame's copy of the region after its own wait
+            const long long eh = bg.ax0 - bg.x0, ec = eh + (bg.x1 - bg.ax1);
+            bg_edge_pre = rows * ec <= (long long)kBgEdge * kOvThreads;
+            if (bg_edge_pre) {
+#pragma unroll
+                for (int k = 0; k < kBgEdge; ++k) {
+                    const long long i = threadIdx.x + (long long)k * kOvThreads;
+                    if (i < rows * ec) {
+                        const long long yy = bg.y0 + i / ec, kk = i % ec, xx = kk < eh ? bg.x0 + kk : bg.ax1 + (kk - eh);
+                        bge[k] = *reinterpret_cast<const volatile uint8_t*>(bsrc + (size_t)yy * W + (size_t)xx);
+                    }
+                }
+            }
+        }
+    }
+    // two CTAs, both prefetched the region from the DEVICE frame: the device-pass CTA may only dim it there once the host-pass CTA holds
+    // its copy (the loads are consumed below before the flag is raised)
+    const bool bg_handshake = split && host != nullptr && bg_pre && ctl->bg_on_device;
+    if (bg_handshake && blockIdx.y == 1) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < kBgWords; ++k) acc |= bgw[k];
+#pragma unroll
+        for (int k = 0; k < kBgEdge; ++k) acc |= bge[k];
+        asm volatile("" ::"r"(acc));
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicExch(const_cast<int32_t*>(&ctl->bg_ready), 1);
         }
     }
     const int slot = (int)blockIdx.x < n ? slots[blockIdx.x] : -1;
@@ -917,6 +949,13 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
         }
         __syncthreads();
         int first = 0;
+        if (bg_handshake && blockIdx.y == 0) {  // (bounded: a protocol error must not hang the GPU; the flag is normally long set)
+            if (threadIdx.x == 0) {
+                const volatile int32_t* f = &ctl->bg_ready;
+                for (int i = 0; i < (1 << 18) && *f == 0; ++i) {}
+            }
+            __syncthreads();
+        }
         if (bg_first && (dbg_skip & 4)) first = 1;
         else if (bg_first) {  // ---- the background dim: word interior from registers (or the device frame), ragged edges bytewise
             const unsigned factor = 255u - (unsigned)(uint8_t)s_cmd[0].a;
@@ -926,7 +965,9 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
                     const long long total = rows * bg.wpr;
                     for (long long base = 0; base < total; base += (long long)kBgWords * kOvThreads) {
                         if (!bg_pre || base > 0) {  // not prefetched (no pinned frame, or a region larger than the register budget)
-                            const uint8_t* src = (host && !ctl->bg_on_device) ? host : frame;  // (pinned frame: the region may not have been uploaded)
+                            // (pinned frame: the region may not have been uploaded; a host-pass CTA always reads the host frame — the device
+                            // frame's copy is being dimmed by the other CTA)
+                            const uint8_t* src = ((host && !ctl->bg_on_device) || (split && do_host)) ? host : frame;
 #pragma unroll
                             for (int k = 0; k < kBgWords; ++k) {
                                 const long long i = base + threadIdx.x + (long long)k * kOvThreads;
@@ -947,10 +988,12 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
                 }
                 // columns outside the word interior (<= 3 + 3 per row; every column when rows are not word addressable)
                 const long long eh = bg.wpr > 0 ? bg.ax0 - bg.x0 : bg.x1 - bg.x0, et = bg.wpr > 0 ? bg.x1 - bg.ax1 : 0, ec = eh + et;
-                for (long long i = threadIdx.x; i < rows * ec; i += blockDim.x) {
+                const bool edge_host = (host && !ctl->bg_on_device) || (split && do_host);
+                for (long long i = threadIdx.x, kk = 0; i < rows * ec; i += blockDim.x, ++kk) {
                     const long long yy = bg.y0 + i / ec, k = i % ec, xx = k < eh ? bg.x0 + k : bg.ax1 + (k - eh);
                     const size_t o = (size_t)yy * W + (size_t)xx;
-                    const uint8_t d = (uint8_t)(((unsigned)((host && !ctl->bg_on_device) ? host[o] : frame[o]) * factor) / 255u);
+                    const unsigned v = (bg_edge_pre && bg.wpr > 0) ? (unsigned)bge[kk < kBgEdge ? kk : 0] : (unsigned)(edge_host ? host[o] : frame[o]);
+                    const uint8_t d = (uint8_t)((v * factor) / 255u);
                     if (do_dev) frame[o] = d;
                     if (do_host) host[o] = d;
                 }

@@ -135,7 +135,7 @@ struct FrameCtl {
     const uint8_t* frames[kMaxWin];
     uint8_t* host_frames[kMaxWin];
     int32_t bg_on_device;      // the region a leading HUD background dim reads was uploaded with the windows: read it from the device frame
-    int32_t pad_;
+    int32_t bg_ready;          // set by the host-pass CTA of the overlay kernel once its copy of that region is in registers (reset per frame)
 };
 // h_list / n / d_list (optional): the frame's HUD list travels in the kernel's parameter block and is written to d_list, so the overlay
 // kernel reads it from device memory (from the pinned block it was a PCIe round trip at the head of the frame's last kernel)
