@@ -117,6 +117,6 @@ def test_header_is_plain_c_and_links(built, tmp_path):
         subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True,
                        capture_output=True)
     # the C examples (per-frame loop, interactive probe loop) build warning-free as well
-    for ex in ("track_nv12", "probe_loop"):
+    for ex in ("track_nv12", "probe_loop", "stream_group"):
         subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, os.path.join(ROOT, "examples", ex + ".c"), "-L", libdir,
                         "-lvittrack_b200", f"-Wl,-rpath,{libdir}", "-o", str(tmp_path / ex)], check=True, capture_output=True)

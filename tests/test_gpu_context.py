@@ -277,3 +277,53 @@ def test_c_example_matches_the_python_binding(built, weight_dir, tmp_path):
         pin.array[:] = frames[i]
         r = trk.update(pin.array)
         assert tuple(r.bbox) == got[i - 1][1] and abs(r.score - got[i - 1][0]) < 1e-4, (i, r, got[i - 1])
+
+
+@pytest.mark.gpu
+def test_c_stream_group_example(built, weight_dir, tmp_path):
+    """examples/stream_group.c: three NV12 files stepped together through vt_tracker_update_streams from plain C; every stream's
+    printed boxes / scores equal those of a single-stream handle on the same file."""
+    import os
+    import re
+    import shutil
+    import subprocess
+
+    import numpy as np
+
+    from gstreamer_vit_tracker_b200 import _lib, api, synth, weights
+
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "stream_group")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "stream_group.c"), "-L", libdir,
+                    "-lvittrack_b200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True, capture_output=True)
+    w = weights.ensure_weight_file("tiny", weight_dir)
+    n, steps = 3, 5
+    streams = [synth.SyntheticStream(synth.cfg5_stream(i)) for i in range(n)]
+    spec = streams[0].spec
+    box = streams[0].target_boxes(0)[0]
+    paths = []
+    for i, st in enumerate(streams):
+        p = tmp_path / f"s{i}.nv12"
+        with open(p, "wb") as f:
+            for k in range(steps + 1):
+                f.write(np.ascontiguousarray(st.frame(k)).tobytes())
+        paths.append(str(p))
+    out = subprocess.run([exe, w, str(spec.width), str(spec.height), *map(str, box), *paths], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for m in re.finditer(r"step (\d+) stream (\d+): \S+\s+score ([0-9.]+) box \((-?\d+), (-?\d+), (-?\d+), (-?\d+)\)", out):
+        got[(int(m.group(1)), int(m.group(2)))] = (float(m.group(3)), tuple(int(v) for v in m.group(4, 5, 6, 7)))
+    assert len(got) == n * steps, out
+    for i, st in enumerate(streams):
+        trk = api.VitTrack.new(w, spec.width, spec.height, box_overlay=True, upload_window=True)
+        pin = api.PinnedBuffer(st.frame_bytes())
+        pin.array[:] = np.ascontiguousarray(st.frame(0)).reshape(-1)
+        trk.init(pin.array, api.BBox(*box))
+        for k in range(1, steps + 1):
+            pin.array[:] = np.ascontiguousarray(st.frame(k)).reshape(-1)
+            r = trk.update(pin.array)
+            assert tuple(r.bbox) == got[(k, i)][1] and abs(r.score - got[(k, i)][0]) < 1e-4, (k, i, r, got[(k, i)])
+        trk.close()
+        pin.close()
