@@ -1073,6 +1073,38 @@ def test_config_struct_size_evolution(api, weight_dir):
         assert L.lib().vt_tracker_create(C.byref(cfg), C.byref(h2)) == L.VT_ERR_INVALID and not h2.value
 
 
+def test_one_process_two_devices(api, weight_dir):
+    """One process driving two GPUs (cfg.device): a handle per device, the same stream on both, driven alternately and from two threads —
+    results identical to each other (same kernels, same forms: one handle per GPU).  Skipped on a single-GPU box."""
+    import threading
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w = weights.ensure_weight_file("tiny", weight_dir)
+    spec = synth.CONFIGS["cfg1"]
+    st = synth.SyntheticStream(spec)
+    frames = [np.ascontiguousarray(st.frame(i)).reshape(-1) for i in range(8)]
+    trks = [api.VitTrack.new(w, spec.width, spec.height, device=d, box_overlay=True) for d in (0, 1)]
+    for t in trks:
+        t.init(frames[0].copy(), api.BBox(*st.target_boxes(0)[0]))
+    outs = [[], []]
+    for f in frames[1:4]:                       # alternately from one thread
+        for d, t in enumerate(trks):
+            outs[d].append(t.update(f.copy()))
+
+    def worker(d):                              # concurrently from two threads
+        for f in frames[4:]:
+            outs[d].append(trks[d].update(f.copy()))
+    th = [threading.Thread(target=worker, args=(d,)) for d in (0, 1)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    for a, b in zip(*outs):
+        assert a.success and a.bbox == b.bbox and a.score == b.score, (a, b)
+    for t in trks:
+        t.close()
+
+
 def test_zz_parity_stats_recorded():
     """Last test of the file: the tie / boundary / |dscore| counts of every sequence above go to gpurun_out/parity_stats.json (the
     numbers behind the 1e-3 / IoU claims survive `pytest -q`), and the global bounds hold over everything that ran."""
