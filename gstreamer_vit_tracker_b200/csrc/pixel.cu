@@ -608,9 +608,76 @@ __global__ void __launch_bounds__(kRszWarps * 32) resize_rgb_tab_kernel(const ui
         for (int b = off; b < row_bytes; ++b) gp[b] = stage[warp][b];
 }
 
+// Tiled separable form (up-scales: a tile of 16 destination rows needs at most kRszSrcRows source rows).  One CTA produces 16 rows x 256
+// pixels: phase 1 blends every needed source row horizontally ONCE — T[row][dx][ch] = (p0 a0 + p1 a1) >> 4 as u16 in shared memory (the
+// per-row kernel above recomputes it for every destination row: 12 scattered byte loads per pixel) — phase 2 blends two T rows vertically,
+// 16 output bytes per thread from four 16-byte shared-memory loads, written as one 16-byte store.  Same integer formulas, bit-exact.
+constexpr int kRszTileRows = 16, kRszTilePx = 256, kRszSrcRows = 12, kRszThreads = 256;
+__global__ void __launch_bounds__(kRszThreads) resize_rgb_tile_kernel(const uint8_t* __restrict__ src, size_t stride_in, int sw, int sh,
+                                                                     uint8_t* __restrict__ dst, size_t stride_out, int dw, int dh,
+                                                                     const int4* __restrict__ xt, const int4* __restrict__ yt) {
+    __shared__ __align__(16) uint16_t T[kRszSrcRows][kRszTilePx * 3];
+    const int x0 = blockIdx.x * kRszTilePx, dy0 = blockIdx.y * kRszTileRows, frame = blockIdx.z;
+    const int npx = min(kRszTilePx, dw - x0), nrow_out = min(kRszTileRows, dh - dy0);
+    const uint8_t* sp = src + (size_t)frame * stride_in;
+    const int ylo = __ldg(yt + dy0).x, yhi = __ldg(yt + dy0 + nrow_out - 1).y;  // (row taps are monotonic)
+    const int nsrc = min(yhi - ylo + 1, kRszSrcRows);
+    // ---- phase 1: thread t owns the flat (dx, ch) elements t, t + 256, t + 512 of a row, for every source row of the tile
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int e = threadIdx.x + k * kRszThreads;
+        if (e < npx * 3) {
+            const int dx = e / 3, ch = e - 3 * dx;
+            const int4 tx = __ldg(xt + x0 + dx);  // x0, x1 (clamped), a0, a1
+            const int rs = sw * 3;
+            const uint8_t *p0 = sp + (size_t)ylo * rs + tx.x * 3 + ch, *p1 = sp + (size_t)ylo * rs + tx.y * 3 + ch;
+            int v0[kRszSrcRows], v1[kRszSrcRows];  // every load of the column issued before the first use (one L2 round trip, not nsrc)
+#pragma unroll
+            for (int r = 0; r < kRszSrcRows; ++r)
+                if (r < nsrc) v0[r] = p0[r * rs], v1[r] = p1[r * rs];
+#pragma unroll
+            for (int r = 0; r < kRszSrcRows; ++r)
+                if (r < nsrc) T[r][e] = (uint16_t)((v0[r] * tx.z + v1[r] * tx.w) >> 4);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: 16 bytes (flat elements 16 q ..) of destination row dy0 + row per thread and step
+    const int q_per_row = npx * 3 / 16;
+    constexpr int kQ = kRszTilePx * 3 / 16;  // 48 16-byte slots per full tile row (constant divisor; slots past a narrow tile's row are skipped)
+    for (int u = threadIdx.x; u < nrow_out * kQ; u += kRszThreads) {
+        const int row = u / kQ, q = u - row * kQ;
+        if (q >= q_per_row) continue;
+        const int4 ty = __ldg(yt + dy0 + row);  // y0, y1 (clamped rows), b0, b1
+        const uint4* t0 = reinterpret_cast<const uint4*>(&T[ty.x - ylo][16 * q]);
+        const uint4* t1 = reinterpret_cast<const uint4*>(&T[ty.y - ylo][16 * q]);
+        uint32_t a[8], b[8], o[4];
+        *reinterpret_cast<uint4*>(a) = t0[0], *reinterpret_cast<uint4*>(a + 4) = t0[1];
+        *reinterpret_cast<uint4*>(b) = t1[0], *reinterpret_cast<uint4*>(b + 4) = t1[1];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t wa = a[2 * w + (j >> 1)], wb = b[2 * w + (j >> 1)];
+                const int ta = (j & 1) ? (int)(wa >> 16) : (int)(wa & 0xffff), tb = (j & 1) ? (int)(wb >> 16) : (int)(wb & 0xffff);
+                x[j] = (uint32_t)((((ty.z * ta) >> 16) + ((ty.w * tb) >> 16) + 2) >> 2);
+            }
+            o[w] = __byte_perm(__byte_perm(x[0], x[1], 0x0040), __byte_perm(x[2], x[3], 0x0040), 0x5410);
+        }
+        uint8_t* gp = dst + (size_t)frame * stride_out + ((size_t)(dy0 + row) * dw + x0) * 3 + 16 * q;
+        *reinterpret_cast<uint4*>(gp) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 cudaError_t launch_resize_rgb_tab(const uint8_t* d_src, size_t stride_in, int sw, int sh, uint8_t* d_dst, size_t stride_out, int dw, int dh,
-                                  int n_frames, const int4* d_xt, const int4* d_yt, cudaStream_t s) {
+                                  int n_frames, const int4* d_xt, const int4* d_yt, cudaStream_t s, int max_src_rows) {
     if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || n_frames <= 0) return cudaSuccess;
+    static const bool no_tile = getenv("VT_B200_RSZ_ROWWISE") != nullptr;  // diagnostics: the per-row form
+    if (max_src_rows > 0 && max_src_rows <= kRszSrcRows && !no_tile) {
+        const dim3 grid((dw + kRszTilePx - 1) / kRszTilePx, (dh + kRszTileRows - 1) / kRszTileRows, n_frames);
+        resize_rgb_tile_kernel<<<grid, kRszThreads, 0, s>>>(d_src, stride_in, sw, sh, d_dst, stride_out, dw, dh, d_xt, d_yt);
+        return cudaGetLastError();
+    }
     const dim3 grid((dw + 128 * kRszWarps - 1) / (128 * kRszWarps), dh, n_frames);
     resize_rgb_tab_kernel<<<grid, kRszWarps * 32, 0, s>>>(d_src, stride_in, sw, sh, d_dst, stride_out, dw, dh, d_xt, d_yt);
     return cudaGetLastError();

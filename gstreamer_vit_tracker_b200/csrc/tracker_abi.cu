@@ -213,8 +213,14 @@ vt_status vt_resize_rgb_device_batch(vt_tracker* t, const uint8_t* d_rgb, size_t
         VT_CUDA(cudaMemcpy(t->d_rsz_taps, xt.data(), sizeof(int4) * dw, cudaMemcpyHostToDevice));
         VT_CUDA(cudaMemcpy(t->d_rsz_taps + dw, yt.data(), sizeof(int4) * dh, cudaMemcpyHostToDevice));
         t->rsz_geom[0] = sw, t->rsz_geom[1] = sh, t->rsz_geom[2] = dw, t->rsz_geom[3] = dh;
+        t->rsz_max_src_rows = 0;
+        for (int d0 = 0; d0 < dh; d0 += 16) {  // tiles of 16 destination rows (kRszTileRows)
+            const int d1 = std::min(d0 + 16, (int)dh) - 1;
+            t->rsz_max_src_rows = std::max(t->rsz_max_src_rows, yt[4 * d1 + 1] - yt[4 * d0] + 1);
+        }
     }
-    VT_CUDA(launch_resize_rgb_tab(d_rgb, stride_in, sw, sh, d_out, stride_out, dw, dh, n_frames, t->d_rsz_taps, t->d_rsz_taps + dw, t->stream));
+    VT_CUDA(launch_resize_rgb_tab(d_rgb, stride_in, sw, sh, d_out, stride_out, dw, dh, n_frames, t->d_rsz_taps, t->d_rsz_taps + dw, t->stream,
+                                  t->rsz_max_src_rows));
     ++t->kernel_launches;
     return VT_OK;
 }

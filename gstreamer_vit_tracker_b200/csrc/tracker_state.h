@@ -87,6 +87,7 @@ struct vt_tracker {
     uint8_t* d_rgb = nullptr;  // lazily allocated, vt_convert_nv12_rgb
     uint8_t *d_fmt_in = nullptr, *d_fmt_out = nullptr;  // lazily grown scratch of the format entry points (YUY2, resize)
     size_t fmt_in_cap = 0, fmt_out_cap = 0;
+    int rsz_max_src_rows = 0;            // source rows needed by the neediest 16-row destination tile of that geometry
     int4* d_rsz_taps = nullptr;          // resize taps of the last geometry: [dw] column taps then [dh] row taps
     int rsz_geom[4] = {0, 0, 0, 0};      // sw, sh, dw, dh they were built for
     uint8_t* h_stage = nullptr;  // pinned staging for non-pinned callers

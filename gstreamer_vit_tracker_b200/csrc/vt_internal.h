@@ -166,8 +166,9 @@ cudaError_t launch_yuy2_to_rgb(const uint8_t* d_yuy2, size_t stride_in, uint8_t*
 cudaError_t launch_resize_rgb_linear(const uint8_t* d_src, int sw, int sh, uint8_t* d_dst, int dw, int dh, cudaStream_t s);
 // batched form: taps per destination column / row precomputed (xt[dw] = {x0, x1, a0, a1}, yt[dh] = {y0, y1, b0, b1}); needs
 // (dw * 3) % 16 == 0, 16-byte aligned destination and strides
+// max_src_rows: the largest number of source rows any tile of 16 destination rows needs (0 = unknown): up to 12 the tiled separable kernel runs
 cudaError_t launch_resize_rgb_tab(const uint8_t* d_src, size_t stride_in, int sw, int sh, uint8_t* d_dst, size_t stride_out, int dw, int dh,
-                                  int n_frames, const int4* d_xt, const int4* d_yt, cudaStream_t s);
+                                  int n_frames, const int4* d_xt, const int4* d_yt, cudaStream_t s, int max_src_rows = 0);
 
 // fused crop + (NV12->RGB) + bilinear resize + normalise -> patch-major tokens A[target][n_tok][768]
 // slots: list of target slot indices processed (device array), n = count. factor 2 -> 128 template, 4 -> 256 search
