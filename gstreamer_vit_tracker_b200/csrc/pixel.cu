@@ -722,8 +722,12 @@ __device__ void ov_rect_nv12(const Surface& s, int x, int y, int w, int h, int t
     const u64 y2 = umin64(i32_as_usize((int)((unsigned)y + (unsigned)h)), sat_sub(H, 1));
     const u64 nx = x2 >= x1 ? x2 - x1 + 1 : 0, ny = y2 >= y1 ? y2 - y1 + 1 : 0;
     const u64 n_h = th * 2 * nx;  // horizontal runs
+    // (index decomposition in 32 bits when the counts fit — every real frame: a 64-bit division costs ~100 instructions, and this code
+    // is most of the frame's last kernel)
+    const bool small = n_h < (1ull << 31) && ny * th * 2 < (1ull << 31);
     for (u64 i = threadIdx.x; i < n_h; i += blockDim.x) {
-        const u64 px = x1 + i % nx, k = i / nx, t = k >> 1;
+        const u64 kq = small ? (u64)((uint32_t)i / (uint32_t)nx) : i / nx;
+        const u64 px = x1 + (i - kq * nx), k = kq, t = k >> 1;
         if ((k & 1) == 0) {
             if (y1 + t < H) put_y(s, px, y1 + t, v);
         } else if (y2 >= t && y2 - t < H) {
@@ -732,7 +736,8 @@ __device__ void ov_rect_nv12(const Surface& s, int x, int y, int w, int h, int t
     }
     const u64 n_v = ny * th * 2;  // vertical runs
     for (u64 i = threadIdx.x; i < n_v; i += blockDim.x) {
-        const u64 py = y1 + i / (th * 2), k = i % (th * 2), t = k >> 1;
+        const u64 rq = small ? (u64)((uint32_t)i / (uint32_t)(th * 2)) : i / (th * 2);
+        const u64 py = y1 + rq, k = i - rq * (th * 2), t = k >> 1;
         if ((k & 1) == 0) {
             if (x1 + t < W) put_y(s, x1 + t, py, v);
         } else if (x2 >= t && x2 - t < W) {
@@ -774,10 +779,12 @@ __device__ void ov_text(const Surface& s, const OverlayCmdDev& c) {  // src/nv12
     const int scale = max(c.a, 0);
     const long long per_char = 35LL * scale * scale;
     const long long total = per_char * c.nchar;
+    const bool small = total < (1LL << 31);  // 32-bit index decomposition (see ov_rect_nv12)
     for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-        const int ch = (int)(i / per_char);
-        long long r = i % per_char;
-        const int cell = (int)(r / (scale * scale)), sub = (int)(r % (scale * scale));
+        const int ch = small ? (int)((uint32_t)i / (uint32_t)per_char) : (int)(i / per_char);
+        long long r = i - (long long)ch * per_char;
+        const int cell = small ? (int)((uint32_t)r / (uint32_t)(scale * scale)) : (int)(r / (scale * scale));
+        const int sub = (int)(r - (long long)cell * (scale * scale));
         const int row = cell / 5, col = cell % 5, dy = sub / scale, dx = sub % scale;
         if (!c.known[ch] || !((c.glyph[ch][row] >> (4 - col)) & 1)) continue;
         if (s.fmt == VT_FMT_NV12) {
@@ -992,7 +999,8 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
                 for (int k = 0; k < kBgEdge; ++k) {
                     const long long i = threadIdx.x + (long long)k * kOvThreads;
                     if (i < rows * ec) {
-                        const long long yy = bg.y0 + i / ec, kk = i % ec, xx = kk < eh ? bg.x0 + kk : bg.ax1 + (kk - eh);
+                        const uint32_t rq = (uint32_t)i / (uint32_t)ec;
+                        const long long yy = bg.y0 + rq, kk = i - (long long)rq * ec, xx = kk < eh ? bg.x0 + kk : bg.ax1 + (kk - eh);
                         bge[k] = *reinterpret_cast<const volatile uint8_t*>(bsrc + (size_t)yy * W + (size_t)xx);
                     }
                 }
@@ -1078,14 +1086,18 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
 #pragma unroll
                             for (int k = 0; k < kBgWords; ++k) {
                                 const long long i = base + threadIdx.x + (long long)k * kOvThreads;
-                                if (i < total) bgw[k] = *reinterpret_cast<const uint32_t*>(src + (size_t)(bg.y0 + i / bg.wpr) * W + bg.ax0 + 4 * (i % bg.wpr));
+                                if (i < total) {
+                                    const uint32_t rr = (uint32_t)i / (uint32_t)bg.wpr, cc = (uint32_t)i - rr * (uint32_t)bg.wpr;
+                                    bgw[k] = *reinterpret_cast<const uint32_t*>(src + (size_t)(bg.y0 + rr) * W + bg.ax0 + 4 * cc);
+                                }
                             }
                         }
 #pragma unroll
                         for (int k = 0; k < kBgWords; ++k) {
                             const long long i = base + threadIdx.x + (long long)k * kOvThreads;
                             if (i < total) {
-                                const size_t o = (size_t)(bg.y0 + i / bg.wpr) * W + bg.ax0 + 4 * (i % bg.wpr);
+                                const uint32_t rr = (uint32_t)i / (uint32_t)bg.wpr, cc = (uint32_t)i - rr * (uint32_t)bg.wpr;
+                                const size_t o = (size_t)(bg.y0 + rr) * W + bg.ax0 + 4 * cc;
                                 const uint32_t d = dim4(bgw[k], factor);
                                 if (do_dev) *reinterpret_cast<uint32_t*>(frame + o) = d;
                                 if (do_host) *reinterpret_cast<uint32_t*>(host + o) = d;
@@ -1097,7 +1109,8 @@ __global__ void __launch_bounds__(kOvThreads) box_overlay_kernel(size_t len, int
                 const long long eh = bg.wpr > 0 ? bg.ax0 - bg.x0 : bg.x1 - bg.x0, et = bg.wpr > 0 ? bg.x1 - bg.ax1 : 0, ec = eh + et;
                 const bool edge_host = (host && !ctl->bg_on_device) || (split && do_host);
                 for (long long i = threadIdx.x, kk = 0; i < rows * ec; i += blockDim.x, ++kk) {
-                    const long long yy = bg.y0 + i / ec, k = i % ec, xx = k < eh ? bg.x0 + k : bg.ax1 + (k - eh);
+                    const uint32_t rq = (uint32_t)i / (uint32_t)ec;  // (rows * ec < 2^31)
+                    const long long yy = bg.y0 + rq, k = i - (long long)rq * ec, xx = k < eh ? bg.x0 + k : bg.ax1 + (k - eh);
                     const size_t o = (size_t)yy * W + (size_t)xx;
                     const unsigned v = (bg_edge_pre && bg.wpr > 0) ? (unsigned)bge[kk < kBgEdge ? kk : 0] : (unsigned)(edge_host ? host[o] : frame[o]);
                     const uint8_t d = (uint8_t)((v * factor) / 255u);
