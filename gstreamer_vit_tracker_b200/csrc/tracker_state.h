@@ -149,7 +149,8 @@ struct vt_tracker {
     int sm_count = 148;         // SMs of the device (grid sizing of the throughput forms)
     int as_rows = 1024;         // rows (M) from which QKV / unchained FC1 run in the A-stationary throughput form (VT_B200_AS_ROWS; 0 = never)
     bool as_mlp = true;         // ... and the MLP as one chained A-stationary kernel + reduce (VT_B200_NO_AS_MLP disables: FC1 A-stationary, FC2 own GEMM)
-    int tp_rows = 1024;         // rows from which proj / FC2 multicast their activation tile across the LayerNorm cluster (VT_B200_TP_ROWS; 0 = never)
+    int tp_rows = 0;            // rows from which proj / FC2 multicast their activation tile across the LayerNorm cluster (VT_B200_TP_ROWS; 0 =
+                                // never: measured without gain at 5120 rows, profiles/r2_final.md)
     bool counted = false;       // this handle is included in g_live_handles
     bool tc_attention = false;  // head_dim == 64
     TcAttentionPlan plan_att;
