@@ -721,7 +721,11 @@ def run_b200(args):
         }
         tpx = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpx):
-            out["roofline_convert"]["traffic"] = json.load(open(tpx)).get("nv12_to_rgb_vec4_kernel", {}).get("dram_bytes_per_launch")
+            tj = json.load(open(tpx)).get("nv12_to_rgb_vec4_kernel", {})
+            if tj.get("dram_bytes_per_frame"):  # ncu capture of a 32-frame launch, scaled to this leg's frames per launch
+                out["roofline_convert"]["traffic"] = int(tj["dram_bytes_per_frame"]) * nb
+                out["roofline_convert"]["traffic_note"] = (f"dram__bytes_read + write per 1080p frame under ncu ({tj['dram_bytes_per_frame']} B; algorithmic "
+                                                           f"{tj.get('algorithmic_bytes_per_frame')} B, the rest of the writes is still in L2 when the kernel ends) x {nb} frames")
         for k, v in extras.items():
             if isinstance(v, dict) and v.get("vit_tflops"):
                 v["vit_frac_of_bf16_peak"] = v["vit_tflops"] / tf_peak
