@@ -143,6 +143,20 @@ __device__ __forceinline__ void st_async_cluster_f2(uint32_t remote_addr, float 
                  "r"(remote_mbar)
                  : "memory");
 }
+__device__ __forceinline__ void st_async_cluster_f4(uint32_t remote_addr, float x, float y, float z, float w, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr), "f"(x), "f"(y),
+                 "f"(z), "f"(w), "r"(remote_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_shared_cluster_f4(uint32_t addr, float x, float y, float z, float w) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// bulk copy from this CTA's shared memory into a peer's (addresses of the peer: mapa), completion counted on the peer's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(remote_dst), "r"(local_src),
+                 "r"(bytes), "r"(remote_mbar)
+                 : "memory");
+}
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 

@@ -154,7 +154,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
             const bool chain = as_mlp || (t->chain_mlp && n < t->unchain_n);
             int planes = (int)(Hd / 64);
             if (as_mlp) {
-                VT_LAUNCH(tc_gemm_as_mlp_launch(p.fc1, M, s, pdl, t->sm_count, &planes));
+                VT_LAUNCH(tc_gemm_as_mlp_launch(p.fc1, M, s, pdl, t->sm_count, &planes, t->fuse_ln ? &p.fc2 : nullptr));
             } else if (chain) {
                 VT_LAUNCH(tc_gemm_launch(p.fc1, M, ns, s, pdl, spread));
             } else {
@@ -165,7 +165,9 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                 else
                     VT_LAUNCH(tc_gemm_launch(fc1, M, ns, s, pdl));
             }
-            if (chain) {  // X += fc2_b + sum of the partials; LN1 of the next block / the final LN of the search rows
+            if (chain && planes == 0) {
+                // (reduced inside the MLP kernel's clusters)
+            } else if (chain) {  // X += fc2_b + sum of the partials; LN1 of the next block / the final LN of the search rows
                 const bool last = l + 1 == t->depth;
                 ReduceLnArgs r{};
                 r.P = t->Pbuf, r.np = planes, r.p_stride = (int64_t)t->maxT * kNTok * D, r.bias = b.fc2_b, r.add = t->X, r.add_period = 0;

@@ -360,7 +360,9 @@ cudaError_t tc_gemm_as_launch(const TcGemmPlan& p, int M, int nsplit, cudaStream
 // tensor memory as the A operand of the chained product, which accumulates over all hidden chunks of the CTA; *planes partial planes
 // (CTAs per row tile) are written to the chain output for reduce_ln_kernel
 bool tc_gemm_as_mlp_supported(const TcGemmPlan& p, int nsplit);
-cudaError_t tc_gemm_as_mlp_launch(const TcGemmPlan& p, int M, cudaStream_t s, bool pdl, int sm_count, int* planes);
+// fc2 (optional): with it, and N2 / 64 CTAs per row tile, the partials are reduced inside a cluster (bias, residual, LayerNorm fused):
+// *planes == 0 on return and no reduce_ln_kernel launch is needed
+cudaError_t tc_gemm_as_mlp_launch(const TcGemmPlan& p, int M, cudaStream_t s, bool pdl, int sm_count, int* planes, const TcGemmPlan* fc2 = nullptr);
 struct TcAttentionPlan {      // kernel parameter block (__grid_constant__)
     CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo;
     CUtensorMap mW2hi, mW2lo;        // chained form: W_proj [D][D], boxes of 64 x 64

@@ -913,7 +913,8 @@ def test_throughput_gemm_forms_bit_identical(api, weight_dir, monkeypatch, gemm_
     frames = [np.ascontiguousarray(st.frame(i)).reshape(-1) for i in range(5)]
 
     def run(env):
-        for k in ("VT_B200_NO_SPREAD", "VT_B200_UNCHAIN_N", "VT_B200_AS_ROWS", "VT_B200_TP_ROWS", "VT_B200_NO_AS_MLP"):
+        for k in ("VT_B200_NO_SPREAD", "VT_B200_UNCHAIN_N", "VT_B200_AS_ROWS", "VT_B200_TP_ROWS", "VT_B200_NO_AS_MLP", "VT_B200_AS_SPLIT",
+                  "VT_B200_AS_FUSE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -938,6 +939,15 @@ def test_throughput_gemm_forms_bit_identical(api, weight_dir, monkeypatch, gemm_
         for a, b in zip(fa, fb):
             assert a.success and a.status == 0 and a.bbox == b.bbox, (a, b)
             assert abs(a.score - b.score) < 1e-5, (a, b)
+    # three CTAs per row tile (what 5120 rows get on 148 SMs), opt-in form: the partial products are reduced inside a 3-CTA cluster through
+    # distributed shared memory, with bias, residual and the next LayerNorm fused (no partial planes, no reduce kernel; measured slower)
+    if gemm_mode == 1:
+        fused = run(dict(base, VT_B200_AS_ROWS="1", VT_B200_AS_SPLIT="3", VT_B200_AS_FUSE="1"))
+        planes = run(dict(base, VT_B200_AS_ROWS="1", VT_B200_AS_SPLIT="3"))
+        for fa, fb, fc in zip(fused, ref, planes):
+            for a, b, c in zip(fa, fb, fc):
+                assert a.success and a.status == 0 and a.bbox == b.bbox == c.bbox, (a, b, c)
+                assert abs(a.score - b.score) < 1e-5 and abs(a.score - c.score) < 1e-5, (a, b, c)
 
 
 @pytest.mark.parametrize("upload_window", [True, False], ids=["windows", "whole"])
