@@ -86,7 +86,7 @@ typedef struct {
     int32_t debug_capture;       /* 1: keep per-block token copies for vt_tracker_debug_tokens (disables graph replay) */
     int32_t upload_window;       /* 1: update()/submit() upload only the search windows of the active targets (2-D copies out of a
                                        pinned frame; rect_last is mirrored on the host) instead of the whole frame.  The device copy
-                                       of the frame is then partial: vt_overlay_current needs upload_window = 0. */
+                                       of the frame is then partial: vt_overlay_current re-uploads the whole frame when it needs it. */
     /* --- since VT_ABI_VERSION 2: variant switches of VitTrack's pre/post-processing; all-zero = OpenCV 4.13 --- */
     int32_t pad_plus1;           /* crop padding: 0 padR = max(x2-W, 0) (4.13); 1 padR = max(x2-W+1, 0), likewise at the bottom (older) */
     int32_t decode_window;       /* vt_decode_window */
@@ -138,7 +138,9 @@ vt_status vt_tracker_update(vt_tracker* t, uint8_t* frame, size_t len, vt_result
  * submitted frame's results are in host memory.  Up to two frames may be in flight per handle (rect_last lives on the device, so
  * frame t+1 can be enqueued before the result of frame t has been read): this hides the host round trip between frames.
  * `frame` must stay valid until its wait() returns.  Pageable (non-pinned) host frames cannot be pipelined (one staging buffer);
- * with cfg.upload_window a frame submitted while another is in flight is uploaded whole (the host mirror of rect_last lags). */
+ * with cfg.upload_window a frame submitted while another is in flight gets a predicted window (the host mirror of rect_last lags by
+ * one frame: its search window grown by 1/8 of its side); whatever the real window needs beyond it the crop kernel reads straight
+ * from the pinned frame, so results never depend on the prediction. */
 vt_status vt_tracker_submit(vt_tracker* t, uint8_t* frame, size_t len);
 vt_status vt_tracker_submit_device(vt_tracker* t, uint8_t* d_frame, size_t len);  /* frame already in device memory, tracked in place */
 vt_status vt_tracker_wait(vt_tracker* t, vt_result* results);
