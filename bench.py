@@ -645,6 +645,26 @@ def run_b200(args):
             except Exception as e:
                 extras["cfg4"] = {"error": repr(e)[:300]}
 
+        # cfg1 / cfg3: the reference's CPU-runnable 720p NV12 case and the 640x512 RGB24 path its main() runs (src/main.rs:49), one target each
+        if world == 1:
+            for name in ("cfg1", "cfg3"):
+                try:
+                    specx = synth.CONFIGS[name]
+                    Kx, Wx = max(40, K // 4), max(5, Wm // 4)
+                    sx_ = Stream(api, torch, specx, wpath, local_rank, args, 8, Kx + Wx, with_context=False)
+                    lxd = timed([sx_], "device", Kx, Wx)
+                    lxh = timed([sx_], "host", Kx, Wx)
+                    extras[name] = {
+                        "workload": f"{specx.width}x{specx.height} {specx.fmt.upper()}, one target", "steps": Kx,
+                        "value": Kx / (lxd["ms"] * 1e-3), "e2e": Kx / (lxh["ms"] * 1e-3), "unit": "frames/s",
+                        "e2e_mode": "synchronous vt_tracker_update, pinned frames, search-window upload, box overlay",
+                        "p50_latency_ms": float(np.percentile(lxh["lat"][0], 50) * 1e-3), "h2d_bytes_per_step": int(lxh["h2d"]),
+                        "stages_ms": lxh["stages"]}
+                    sx_.trk.close()
+                    del sx_
+                except Exception as e:
+                    extras[name] = {"error": repr(e)[:300]}
+
     if rank == 0:
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")

