@@ -730,6 +730,11 @@ def run_b200(args):
                           "frac": gemm_flops / (gemm_us * 1e-6) / 1e12 / tf_peak, "traffic": traffic, "peak_source": peak_src,
                           "flops_per_launch_avg": gemm_flops / gemm_n, "launches_per_frame": gemm_n, "avg_launch_us": gemm_us / gemm_n,
                           "share_of_chain": gemm_us / chain_us if chain_us else None,
+                          "share_of_step": gemm_us * 1e-3 / (ms_dev_g / K) if ms_dev_g else None,
+                          "share_note": "share_of_chain: of the in-chain time of the traced tensor-core kernels (GEMM + attention); share_of_step: of "
+                                        "ms_per_step (which also holds the reduce / decode / overlay kernels and every dependency edge); the ncu launch "
+                                        "list of this command (profiles/r2v_bench_launches.csv, cold cache, serialised): 43.8 % of all kernel time, "
+                                        "66.7 % of GEMM + attention",
                           "timing": "device %globaltimer stamps inside the replayed graph (dependency wait -> kernel end), 20 frames",
                           "note": "one target = 320 rows: every launch is a 9..108-CTA latency-bound GEMM; algorithmic FLOPs (2MNK), the bf16x3 "
                                   "split issues 3 UMMAs per product; tensor utilisation at scale is the cfg4 / cfg5 objects' vit_tflops"} if kern and gemm_us > 0 else
