@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
     (void)chunks_per_cta;
     const int c_begin = blockIdx.x, c_step = gridDim.x;
     const int my_chunks = c_begin < n_chunks ? (n_chunks - 1 - c_begin) / c_step + 1 : 0, n_items = my_chunks * num_kb;  // item = (chunk, k-block)
+    // ... and the CTA's LAST chunk (QKV: its V^T chunk) goes first, so that the slow epilogue runs under the main loops of the others
+    auto chunk_of = [&](int i) { return c_begin + ((i + my_chunks - 1) % my_chunks) * c_step; };
     bool ok = true;
     TraceRec tr;
     tr.begin(&trace_slot, a.trace, a.trace_id);
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
         fence_barrier_init();
         const int npre = n_items < kAsStages ? n_items : kAsStages;
         for (int it = 0; it < npre; ++it) {
-            const int c = c_begin + (it / num_kb) * c_step, kb = it % num_kb;
+            const int c = chunk_of(it / num_kb), kb = it % num_kb;
             uint8_t* sb = smem + SM::kOffB + it * SM::kStageBytes;
             mbar_arrive_expect_tx(&full_bar[it], SM::kStageBytes);
             tma_load_2d(sb, &mp.Bhi, &full_bar[it], kb * kTcBK, c * kAsChunk);
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
                 if (kLo) tma_load_2d(sa + kTileABytes, &mp.Alo, &a_bar[kb], kb * kTcBK, m0);
             }
             for (int it = kAsStages; it < n_items; ++it) {
-                const int s = it % kAsStages, c = c_begin + (it / num_kb) * c_step, kb = it % num_kb;
+                const int s = it % kAsStages, c = chunk_of(it / num_kb), kb = it % num_kb;
                 ok &= mbar_wait(&empty_bar[s], ((it / kAsStages) - 1) & 1);
                 uint8_t* sb = smem + SM::kOffB + s * SM::kStageBytes;
                 mbar_arrive_expect_tx(&full_bar[s], SM::kStageBytes);
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
         const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
         const int Dm = a.N / 3;
         for (int i = 0; i < my_chunks; ++i) {
-            const int buf = i & 1, n0 = (c_begin + i * c_step) * kAsChunk, nc = n0 + g * CPT;
+            const int buf = i & 1, n0 = chunk_of(i) * kAsChunk, nc = n0 + g * CPT;
             float bias_v[CPT];
             if (a.bias) {
 #pragma unroll
