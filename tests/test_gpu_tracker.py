@@ -336,8 +336,8 @@ def test_free_running_sequence_iou(api, oracle, weight_dir, model, cfg, frames, 
 
 @pytest.mark.gpu
 def test_cfg4_full_size_16_targets_vs_oracle(api, oracle, weight_dir):
-    """BASELINE config 4 at full size: 3840x2160 NV12, tiny, 16 targets through ONE batched forward (M = 5120 rows: the unchained
-    MLP form, FC2 as its own GEMM), 5 teacher-forced frames, EVERY target against its own oracle.VitTrack (one fp32 forward per target
+    """BASELINE config 4 at full size: 3840x2160 NV12, tiny, 16 targets through ONE batched forward (M = 5120 rows: the many-row
+    forms — A-stationary QKV, chained MLP with the hidden tile in tensor memory, three partial planes), 5 teacher-forced frames, EVERY target against its own oracle.VitTrack (one fp32 forward per target
     and frame): score within 1e-3, box equal off floor ties (reference semantics: /root/reference/src/tracker_context.rs:120-125,
     one VitTrack per target)."""
     spec = synth.CONFIGS["cfg4"]
@@ -367,6 +367,41 @@ def test_cfg4_full_size_16_targets_vs_oracle(api, oracle, weight_dir):
             assert refs[k].update(rgb)[0] == 0
             compare_step(trk, rs[k], refs[k], before[k], stats, ("cfg4", n, k), target=k)
     finish_stats("teacher_forced/tiny/cfg4x16/gemm1", stats, frames * nt)
+
+
+def test_stream_group_16_streams_vs_oracle(api, oracle, weight_dir):
+    """BASELINE config 5's unit of work as this repo runs it: 16 independent 1080p NV12 streams (cfg5 seeds) stepped together through
+    vt_tracker_update_streams (one batched forward of 5120 rows, every stream its own pinned frame, search-window upload and device-side
+    rect_last), 4 teacher-forced steps, EVERY stream against its own oracle.VitTrack on its own frames (one TrackerContext per
+    pipeline, /root/reference/src/pipeline.rs:55): score within 1e-3, box equal off floor ties."""
+    G, steps = 16, 4
+    streams = [synth.SyntheticStream(synth.cfg5_stream(i)) for i in range(G)]
+    spec = streams[0].spec
+    W, H = spec.width, spec.height
+    wpath = weights.ensure_weight_file("tiny", weight_dir)
+    trk = api.VitTrack.new(wpath, W, H, max_targets=G, gemm_mode=1, upload_window=True)
+    refs = [oracle.VitTrack(wpath, threads=16) for _ in range(G)]
+    pins = [api.PinnedBuffer(s_.frame_bytes()) for s_ in streams]
+    for i, s_ in enumerate(streams):
+        f0 = np.ascontiguousarray(s_.frame(0)).reshape(-1)
+        b = s_.target_boxes(0)[0]
+        trk.init(f0, api.BBox(*b), target=i)
+        assert refs[i].init(oracle.nv12_to_rgb(f0, W, H, 16), b) == 0
+    stats = new_stats()
+    for n in range(1, steps + 1):
+        before = [refs[i].rect for i in range(G)]
+        for i, s_ in enumerate(streams):
+            pins[i].array[:] = np.ascontiguousarray(s_.frame(n)).reshape(-1)
+            trk.set_rect(before[i], target=i)
+        rs = trk.update_streams([p.array for p in pins])
+        for i, s_ in enumerate(streams):
+            assert rs[i].status == 0, (n, i, rs[i])
+            assert refs[i].update(oracle.nv12_to_rgb(np.ascontiguousarray(s_.frame(n)).reshape(-1), W, H, 16))[0] == 0
+            compare_step(trk, rs[i], refs[i], before[i], stats, ("group16", n, i), target=i)
+    finish_stats("teacher_forced/tiny/stream_group16/gemm1", stats, steps * G)
+    trk.close()
+    for p in pins:
+        p.close()
 
 
 # ---- multi-target, formats, errors -----------------------------------------------------------------------------
