@@ -22,7 +22,10 @@
 
 namespace vt {
 
-constexpr int kAsStages = 4;           // weight k-block stages in flight
+#ifndef VT_AS_STAGES
+#define VT_AS_STAGES 4
+#endif
+constexpr int kAsStages = VT_AS_STAGES;  // weight k-block stages in flight (3 .. 4 fit beside the activation tile and two staging buffers)
 constexpr int kAsMaxKb = 3;            // K <= 192
 constexpr int kAsThreads = 64 + kTcThreads;  // TMA warp, MMA warp, 16 epilogue warps
 constexpr int kAsChunk = 64;           // columns per accumulator / epilogue step
@@ -241,7 +244,10 @@ __global__ void __launch_bounds__(kAsThreads, 1) gemm_as_kernel(const __grid_con
 // with bias, residual and the next LayerNorm.  W1 k-blocks and W2 row blocks share one ring of 16 KB stages, in MMA issue order:
 //   W1(0) | W1(1) W2(0) | W1(2) W2(1) | ... | W2(n-1)       (MMA1 of chunk c + 1 is issued before MMA2 of chunk c: it runs under c's GELU)
 // TMEM: accumulators of MMA1 2 x 128 columns, hidden tile 64, MMA2 accumulator N2 <= 192  = 512 columns.
-constexpr int kMlpStages = 7;
+#ifndef VT_MLP_STAGES
+#define VT_MLP_STAGES 6
+#endif
+constexpr int kMlpStages = VT_MLP_STAGES;
 constexpr int kMlpStageBytes = 2 * kAsChunk * kTcBK * 2;  // [W_hi; W_lo] of a 64 x 64 block
 constexpr int kMlpABytes = kAsMaxKb * 2 * kTileABytes;
 constexpr int kMlpSmemTotal = kMlpABytes + kMlpStages * kMlpStageBytes + 1024;
