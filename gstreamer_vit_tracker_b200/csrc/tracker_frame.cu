@@ -61,6 +61,7 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                             (const uint32_t*)t->zln_lo, t->d_stamps + ST_VIT));
     }
     const int M = n * kNTok;
+    int head_np = 9;
     if (t->nsplit == 0) {
         // ---------------- fp32 CUDA-core path ----------------
         {
@@ -107,10 +108,21 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
         // ---------------- tensor-core path: tcgen05 GEMMs fed by TMA, bf16 (x3 split) operands, fp32 TMEM accumulators ----------------
         const int ns = t->nsplit;
         const bool pdl = t->pdl && !t->debug_capture, fuse = t->fuse_ln;
-        VT_LAUNCH(tc_gemm_launch(t->plan_patch_x, n * kNTx, ns, s, pdl));  // fused: + LN1 of block 0 for the search rows
-        if (t->split_k) {  // X[64.., :] = pos_x + patch_b + sum of the 4 K-slices; LN1 of block 0
+        // Many targets: the split-K forms of patch embed (4 K-slices) and head conv (one 3x3 tap per slice) are shaped for one target's
+        // three row tiles; from 8 targets on they are 384 / 576 short CTAs (2.6 / 3.9 waves), so the slices are merged — 2 K-slices, 3 taps
+        // per slice: a third of the partial planes, CTAs that run three times as many MMAs per prologue.
+        const bool merge_slices = t->split_k && n >= kUnchainTargets && !getenv("VT_B200_NO_MERGE_SLICES");
+        int patch_np = 4;
+        if (merge_slices) {
+            TcGemmPlan pp = t->plan_patch_x;
+            pp.args.kb_per_split = kPatchK / 64 / 2, patch_np = 2;
+            VT_LAUNCH(tc_gemm_launch(pp, n * kNTx, ns, s, pdl));
+        } else {
+            VT_LAUNCH(tc_gemm_launch(t->plan_patch_x, n * kNTx, ns, s, pdl));  // fused: + LN1 of block 0 for the search rows
+        }
+        if (t->split_k) {  // X[64.., :] = pos_x + patch_b + sum of the K-slices; LN1 of block 0
             ReduceLnArgs r{};
-            r.P = t->Pbuf, r.np = 4, r.p_stride = (int64_t)t->maxT * kNTx * D, r.bias = t->patch_b, r.add = t->pos_x, r.add_period = kNTx;
+            r.P = t->Pbuf, r.np = patch_np, r.p_stride = (int64_t)t->maxT * kNTx * D, r.bias = t->patch_b, r.add = t->pos_x, r.add_period = kNTx;
             r.X = t->X, r.M = n * kNTx, r.D = D, r.period = kNTx, r.x_rows = kNTok, r.x_row_off = kNTz;
             r.ln_g = t->blk[0].ln1_g, r.ln_b = t->blk[0].ln1_b, r.ln_hi = t->ln_hi, r.ln_lo = LO(t->ln_lo), r.ln_rows = kNTok, r.ln_row_off = kNTz;
             VT_LAUNCH(launch_reduce_ln(r, s, pdl));
@@ -183,10 +195,16 @@ static vt_status enqueue_forward(vt_tracker* t, int n, int& launches, bool recor
                 VT_CUDA(cudaMemcpyAsync(t->d_dbg + (size_t)(l + 1) * t->maxT * kNTok * D, t->X, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, s));
         }
         if (!fuse) VT_LAUNCH(launch_layernorm_split(t->X, D, t->lnf_g, t->lnf_b, t->yf_hi, LO(t->yf_lo), n * kNTx, D, kNTx, kNTok, kNTz, s, pdl));
-        VT_LAUNCH(tc_gemm_launch(t->plan_head, n * kNTx, ns, s, pdl));
+        if (merge_slices) {
+            TcGemmPlan ph = t->plan_head;
+            ph.args.kb_per_split = 3 * (D / 64), head_np = 3;
+            VT_LAUNCH(tc_gemm_launch(ph, n * kNTx, ns, s, pdl));
+        } else {
+            VT_LAUNCH(tc_gemm_launch(t->plan_head, n * kNTx, ns, s, pdl));
+        }
     }
     if (t->nsplit && t->split_k)
-        VT_LAUNCH(launch_head_decode(t->Phead, 9, (int64_t)t->maxT * kNTx * C, C, t->h1_b, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n,
+        VT_LAUNCH(launch_head_decode(t->Phead, head_np, (int64_t)t->maxT * kNTx * C, C, t->h1_b, t->h2_w, t->h2_b, t->d_hann, t->d_state, t->d_slots, n,
                                      t->threshold, t->d_res, t->d_maps, t->d_cand, t->d_counters, t->d_stamps, s, t->pdl && !t->debug_capture,
                                      t->cfg.decode_window, t->d_tc_err));
     else
